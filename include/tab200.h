@@ -1,0 +1,161 @@
+/*
+ * tab200.h -- C ABI of libtab200.so, the B200 (sm_100a) implementation of the
+ * TensorAlloy energy / force / virial hot path.
+ *
+ * The reference (Bismarrck/tensoralloy) has NO C ABI: its boundary is the
+ * Python operator surface plus one `sess.run(ops, feed_dict)` call
+ * (tensoralloy/calculator.py:368-369).  Each entry point below names the
+ * reference interface it replaces.  The Python mirror of the reference classes
+ * (tensoralloy_b200/calculator.py, transformer/, nn/) binds these with ctypes;
+ * INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative TAB_E* code otherwise and
+ *     never throws; tab_last_error() returns a thread-local message.
+ *   - `d_` pointers are DEVICE pointers, `h_` pointers are HOST pointers; the
+ *     caller owns every buffer.  The library owns only opaque handles.
+ *   - all work is enqueued on the caller's CUDA stream (`stream` is a
+ *     cudaStream_t passed as void*; NULL = legacy default stream).
+ *   - one handle may be used from one host thread at a time (the reference
+ *     calculator is not thread-safe either: calculator.py:368-370).
+ *   - lattice matrices are 3x3 row-major with ROWS = lattice vectors (ASE / the
+ *     reference, transformer/universal.py:446).
+ *   - atom order of every input and output is the CALLER's order; the library's
+ *     internal cell-sorted order never leaks.
+ */
+#ifndef TAB200_H
+#define TAB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TAB_OK            0
+#define TAB_EINVAL       -1   /* bad argument */
+#define TAB_ECUDA        -2   /* CUDA runtime error, see tab_last_error() */
+#define TAB_ENOMEM       -3
+#define TAB_EUNSUPPORTED -4
+#define TAB_ESTATE       -5   /* call order violated (e.g. eval before build) */
+
+/* precision of the model arithmetic: reference tensoralloy/precision.py:21-134
+ * ('high' = float64, eps 1e-14; 'medium' = float32, eps 1e-8). */
+#define TAB_PRECISION_HIGH   0
+#define TAB_PRECISION_MEDIUM 1
+
+typedef struct tab_nbr   tab_nbr;    /* cell list + neighbour lists of one structure */
+typedef struct tab_model tab_model;  /* device-resident potential parameters        */
+
+int         tab_version(void);
+const char *tab_last_error(void);
+
+/* ------------------------------------------------------------------------
+ * Neighbour lists.
+ * Replaces  ase.neighborlist.neighbor_list('ijSdD', atoms, rc)  as called by
+ * get_radial_metadata (transformer/universal.py:58) and
+ * find_neighbor_size_of_atoms (neighbor.py:84), plus the Python index-map loops
+ * universal.py:69-106 (the slot of a pair is its position in the list).
+ * ---------------------------------------------------------------------- */
+int tab_nbr_create(tab_nbr **out);
+int tab_nbr_free(tab_nbr *nbr);
+
+/* Build the cell list, the periodic ghost images and the neighbour lists of
+ * `n` atoms.  d_pos: [n,3] float64; d_types: [n] int32 element indices
+ * (0..15) or NULL (all 0); h_cell: 9 doubles; h_pbc: 3 ints; rc: cutoff.
+ * Membership is decided exactly like ASE: D = pos[j]-pos[i]+S.cell,
+ * sqrt(D.D) < rc, float64, self pair excluded.  Synchronises the stream once
+ * (list size read-back). */
+int tab_nbr_build(tab_nbr *nbr, int32_t n, const double *d_pos,
+                  const int32_t *d_types, const double *h_cell,
+                  const int32_t *h_pbc, double rc, void *stream);
+
+/* Keep the lists, refresh the positions (and optionally the cell): the MD step
+ * between two rebuilds.  h_cell may be NULL (unchanged). */
+int tab_nbr_update(tab_nbr *nbr, const double *d_pos, const double *h_cell,
+                   void *stream);
+
+/* Sizes, the quantities of neighbor.py:34-47 NeighborSize.  nij = number of
+ * directed pairs; nnl_max = max neighbours of one atom (all species);
+ * n_ext = owned + ghost atoms held on the device. */
+int tab_nbr_sizes(const tab_nbr *nbr, int64_t *nij, int32_t *nnl_max,
+                  int32_t *n_ext);
+
+/* Per-atom neighbour counts in caller order, d_counts: [n] int32. */
+int tab_nbr_counts(const tab_nbr *nbr, int32_t *d_counts, void *stream);
+
+/* Export the list as the reference's (ilist, jlist, n1) arrays
+ * (universal.py:58), caller atom indices, rows sorted by i, inside a row in the
+ * library's deterministic cell order.  d_i, d_j: [nij] int32; d_S: [nij,3] int32. */
+int tab_nbr_export(const tab_nbr *nbr, int32_t *d_i, int32_t *d_j, int32_t *d_S,
+                   void *stream);
+
+/* ------------------------------------------------------------------------
+ * EAM / Finnis-Sinclair / ADP models.
+ * Replaces the TF sub-graphs built by EamNN._get_model_outputs
+ * (nn/eam/eam.py:495-570), EamAlloyNN._build_rho_nn (alloy.py:128-196),
+ * EamFsNN._build_rho_nn (fs.py:146-203), AdpNN (adp.py:315-586), the potential
+ * functions of nn/eam/potentials/*, and the autograd outputs of
+ * BasicNN.build (nn/basic.py:276-354,679-787).
+ * ---------------------------------------------------------------------- */
+#define TAB_EAM_ALLOY 0   /* rho is a function of the neighbour element      */
+#define TAB_EAM_FS    1   /* rho is a function of the ordered (centre,nbr) pair */
+#define TAB_EAM_ADP   2   /* alloy + dipole + quadrupole terms               */
+
+/* function kinds (one per rho / phi / embed / dipole / quadrupole slot) */
+#define TAB_FN_ZERO          0
+#define TAB_FN_ZHOU_RHO      1   /* zjw04.py:245-277   p = f_eq,beta,lamda,r_eq */
+#define TAB_FN_ZHOU_PHI      2   /* zjw04.py:187-227   p = A,alpha,kappa,B,beta,lamda,r_eq */
+#define TAB_FN_ZHOU_PHI_MIX  3   /* zjw04.py:229-243   p = [7 of a][4 rho of a][7 of b][4 rho of b] */
+#define TAB_FN_ZHOU_EMBED    4   /* zjw04.py:279-389   p = Fn0..3,F0..3,eta,Fe,rho_e,rho_s */
+#define TAB_FN_ZHOU_EMBED_XC 5   /* zjw04.py:440-550   same p, sigmoid blended */
+#define TAB_FN_MAX_PARAMS    32
+
+typedef struct tab_fn {
+    int32_t kind;
+    int32_t aux;
+    double  p[TAB_FN_MAX_PARAMS];
+} tab_fn;
+
+/* Create a model.  n_el <= 16 elements (indices = positions in the SORTED
+ * element list, as in the reference's transformer.elements).
+ *   rho   : n_el*n_el entries, rho[a*n_el+b] = density at a centre of element a
+ *           from a neighbour of element b (alloy: independent of a)
+ *   phi   : n_el*n_el entries (symmetric)
+ *   embed : n_el entries
+ *   dipole, quadrupole : n_el*n_el entries or NULL (ADP only)             */
+int tab_eam_create(tab_model **out, int32_t kind, int32_t n_el,
+                   const tab_fn *rho, const tab_fn *phi, const tab_fn *embed,
+                   const tab_fn *dipole, const tab_fn *quadrupole);
+int tab_model_free(tab_model *model);
+
+/* One E + F + virial evaluation on the lists held by `nbr`.
+ *   d_energy : [1]   total energy (eV)                      basic.py:742-787
+ *   d_eatom  : [n]   per-atom energies or NULL              eam.py:287-298
+ *   d_forces : [n,3] F = -dE/dR (eV/A) or NULL              basic.py:281-287
+ *   d_virial : [9]   sum_pairs dE/dD (x) D  (eV) or NULL    basic.py:306-317
+ * All outputs float64 in caller atom order.  `precision` selects the arithmetic
+ * of the pair functions (TAB_PRECISION_*). */
+int tab_eam_eval(tab_model *model, tab_nbr *nbr, int32_t precision,
+                 double *d_energy, double *d_eatom, double *d_forces,
+                 double *d_virial, void *stream);
+
+/* Host-buffer convenience: H2D of positions (+types), neighbour build, eval,
+ * D2H of the results -- the whole of TensorAlloyCalculator.calculate
+ * (calculator.py:335-370) in one call.  Host buffers should be pinned for full
+ * copy speed.  rebuild != 0 rebuilds the lists, else tab_nbr_update is used. */
+int tab_eam_compute_host(tab_model *model, tab_nbr *nbr, int32_t precision,
+                         int32_t n, const double *h_pos, const int32_t *h_types,
+                         const double *h_cell, const int32_t *h_pbc, double rc,
+                         int32_t rebuild, double *h_energy, double *h_eatom,
+                         double *h_forces, double *h_virial, void *stream);
+
+/* number of kernel launches the library has enqueued since load / last reset
+ * (feeds bench.py's `gpu_launches`). */
+int64_t tab_launch_count(void);
+void    tab_launch_count_reset(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TAB200_H */

@@ -1,0 +1,217 @@
+"""
+oracle/potentials.py -- TEST INFRASTRUCTURE (see oracle/__init__.py).
+
+torch (CPU, float64 by default) restatement of the analytic EAM potential
+functions of the reference, `tensoralloy/nn/eam/potentials/*`.  `torch.pow` with
+a floating exponent stands in for `tf.pow` (`safe_pow` without the env switch,
+extension/grad_ops.py:16-74).  Every function returns a tensor shaped like its
+input; autograd provides the derivatives exactly as TF autograd does in the
+reference.
+"""
+import json
+from pathlib import Path
+
+import torch
+
+_DATA = Path(__file__).resolve().parent / 'data'
+
+
+def _elements_of(term):
+    """utils.py:210-234 get_elements_from_kbody_term."""
+    out = []
+    for ch in term:
+        if ch.isupper():
+            out.append(ch)
+        else:
+            out[-1] += ch
+    return out
+
+
+# --------------------------------------------------------------------------
+# generic.py
+# --------------------------------------------------------------------------
+
+def density_exp(r, a, b, re):
+    """generic.py:87-99: a * exp(-b (r/re - 1))."""
+    return a * torch.exp(-b * (r / re - 1.0))
+
+
+def zhou_exp(r, a, b, c, re, order=20):
+    """generic.py:102-117: a exp(-b (r/re - 1)) / (1 + (r/re - c)^order)."""
+    x = r / re
+    upper = density_exp(r, a, b, re)
+    lower = 1.0 + torch.pow(x - c, torch.tensor(float(order), dtype=r.dtype))
+    return upper / lower
+
+
+def morse(r, d, gamma, r0):
+    """generic.py:15-30."""
+    gd = gamma * (r - r0)
+    return d * (torch.exp(-2.0 * gd) - 2.0 * torch.exp(-gd))
+
+
+def buckingham(r, A, rho, C, order=6):
+    """generic.py:33-49 (C / r^order via div_no_nan)."""
+    rs = torch.pow(r, order)
+    right = torch.where(rs == 0, torch.zeros_like(rs), C / rs)
+    return A * torch.exp(-r / rho) - right
+
+
+def mishin_cutoff(x):
+    """generic.py:52-66: psi(x) = x^4 / (1 + x^4) for x < 0 else 0."""
+    ix = torch.relu(-x)
+    x4 = torch.pow(ix, 4.0)
+    return x4 / (1.0 + x4)
+
+
+def mishin_polar(x, p1, p2, p3, rc, h):
+    """generic.py:69-84."""
+    z = (x - rc) / h
+    return (p1 * torch.exp(-p2 * x) + p3) * mishin_cutoff(z)
+
+
+# --------------------------------------------------------------------------
+# potential families
+# --------------------------------------------------------------------------
+
+class Potential:
+    """Interface: rho(r, element_or_term), phi(r, term), embed(rho, element),
+    optional dipole(r, term) / quadrupole(r, term)."""
+    name = 'base'
+
+    def __init__(self, params=None, dtype=torch.float64):
+        self.dtype = dtype
+        self.params = params if params is not None else self.defaults()
+
+    def p(self, section, key):
+        return torch.tensor(self.params[section][key], dtype=self.dtype)
+
+    def defaults(self):
+        raise NotImplementedError
+
+
+class Zjw04(Potential):
+    """zjw04.py:155-413."""
+    name = 'zjw04'
+
+    def defaults(self):
+        return json.loads((_DATA / 'zjw04.json').read_text())['zjw04']
+
+    def rho(self, r, element):
+        # zjw04.py:245-277; for eam/alloy `element` is the NEIGHBOUR element
+        # (alloy.py:162-176).
+        element = _elements_of(element)[-1]
+        P = lambda k: self.p(element, k)
+        return zhou_exp(r, a=P('f_eq'), b=P('beta'), c=P('lamda'), re=P('r_eq'))
+
+    def phi(self, r, term):
+        # zjw04.py:187-243
+        a, b = _elements_of(term)
+        if a == b:
+            P = lambda k: self.p(a, k)
+            return (zhou_exp(r, P('A'), P('alpha'), P('kappa'), P('r_eq')) -
+                    zhou_exp(r, P('B'), P('beta'), P('lamda'), P('r_eq')))
+        phi_a = self.phi(r, a + a)
+        rho_a = self.rho(r, a)
+        phi_b = self.phi(r, b + b)
+        rho_b = self.rho(r, b)
+        return 0.5 * (rho_a / rho_b * phi_b + rho_b / rho_a * phi_a)
+
+    def _branches(self, element):
+        P = lambda k: self.p(element, k)
+        rho_e = P('rho_e')
+        rho_s = P('rho_s')
+        rho_n = torch.tensor(0.85, dtype=self.dtype) * rho_e
+        rho_0 = torch.tensor(1.15, dtype=self.dtype) * rho_e
+        two = torch.tensor(2.0, dtype=self.dtype)
+        three = torch.tensor(3.0, dtype=self.dtype)
+
+        def e1(x):
+            x1 = x / rho_n - 1.0
+            return P('Fn0') + (P('Fn1') * x1 + P('Fn2') * torch.pow(x1, two)
+                               + P('Fn3') * torch.pow(x1, three))
+
+        def e2(x):
+            x1 = x / rho_e - 1.0
+            return P('F0') + (P('F1') * x1 + P('F2') * torch.pow(x1, two)
+                              + P('F3') * torch.pow(x1, three))
+
+        def e3(x, eps=0.0):
+            xs = x / rho_s + eps
+            return P('Fe') * (1.0 - P('eta') * torch.log(xs)) * torch.pow(
+                xs, P('eta'))
+
+        return rho_n, rho_0, e1, e2, e3
+
+    def embed(self, rho, element):
+        # zjw04.py:279-389: three branches selected by gather/scatter
+        rho_n, rho_0, e1, e2, e3 = self._branches(element)
+        out = torch.zeros_like(rho)
+        m1 = rho < rho_n
+        m2 = (rho >= rho_n) & (rho < rho_0)
+        m3 = rho >= rho_0
+        flat = rho.reshape(-1)
+        pieces = torch.zeros_like(flat)
+        for m, fn in ((m1, e1), (m2, e2), (m3, e3)):
+            idx = torch.nonzero(m.reshape(-1)).reshape(-1)
+            if idx.numel():
+                pieces = pieces.index_put((idx,), fn(flat[idx]),
+                                          accumulate=True)
+        return (out.reshape(-1) + pieces).reshape(rho.shape)
+
+
+class Zjw04xc(Zjw04):
+    """zjw04.py:420-550: sigmoid-blended embedding; adds 'Be' = Mo."""
+    name = 'zjw04xc'
+
+    def defaults(self):
+        params = dict(super().defaults())
+        params['Be'] = dict(params['Mo'])
+        return params
+
+    def embed(self, rho, element):
+        rho_n, rho_0, e1, e2, e3 = self._branches(element)
+        y1 = e1(rho)
+        y2 = e2(rho)
+        y3 = e3(rho, eps=1e-8)
+        c1 = torch.sigmoid(2.0 * (rho_n - rho))
+        c3 = torch.sigmoid(2.0 * (rho - rho_0))
+        c2 = 1.0 - (c1 + c3)
+        return c1 * y1 + c2 * y2 + c3 * y3
+
+
+class Zjw04uxc(Zjw04xc):
+    """zjw04.py:553-567 (same arithmetic, different fixed-variable set)."""
+    name = 'zjw04uxc'
+
+
+class Zjw04xcp(Zjw04xc):
+    """zjw04.py:570-696: A-B pair has its own zhou_exp parameter set."""
+    name = 'zjw04xcp'
+
+    def defaults(self):
+        params = dict(super().defaults())
+        over = json.loads((_DATA / 'zjw04.json').read_text())[
+            'zjw04xcp_overrides']
+        for k, v in over.items():
+            params[k] = dict(v)
+        return params
+
+    def phi(self, r, term):
+        a, b = _elements_of(term)
+        sec = a if a == b else term
+        if sec not in self.params:
+            sec = b + a
+        P = lambda k: self.p(sec, k)
+        return (zhou_exp(r, P('A'), P('alpha'), P('kappa'), P('r_eq')) -
+                zhou_exp(r, P('B'), P('beta'), P('lamda'), P('r_eq')))
+
+
+REGISTRY = {
+    'zjw04': Zjw04, 'zjw04xc': Zjw04xc, 'zjw04uxc': Zjw04uxc,
+    'zjw04xcp': Zjw04xcp,
+}
+
+
+def get_potential(name, dtype=torch.float64, params=None):
+    return REGISTRY[name](params=params, dtype=dtype)

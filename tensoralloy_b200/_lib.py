@@ -1,0 +1,238 @@
+"""
+ctypes binding of libtab200.so (C ABI: include/tab200.h).
+
+There is NO fallback: if the CUDA library is missing or cannot be loaded this
+module raises, and so does every product path that needs it.
+"""
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / 'csrc' / 'libtab200.so'
+
+TAB_FN_MAX_PARAMS = 32
+PRECISION_HIGH = 0
+PRECISION_MEDIUM = 1
+EAM_ALLOY, EAM_FS, EAM_ADP = 0, 1, 2
+
+FN_ZERO = 0
+FN_ZHOU_RHO = 1
+FN_ZHOU_PHI = 2
+FN_ZHOU_PHI_MIX = 3
+FN_ZHOU_EMBED = 4
+FN_ZHOU_EMBED_XC = 5
+
+
+class TabFn(C.Structure):
+    _fields_ = [('kind', C.c_int32), ('aux', C.c_int32),
+                ('p', C.c_double * TAB_FN_MAX_PARAMS)]
+
+
+def make_fn(kind, params=(), aux=0):
+    fn = TabFn()
+    fn.kind = int(kind)
+    fn.aux = int(aux)
+    if len(params) > TAB_FN_MAX_PARAMS:
+        raise ValueError("too many parameters for one tab_fn")
+    for k, v in enumerate(params):
+        fn.p[k] = float(v)
+    return fn
+
+
+class TabError(RuntimeError):
+    """A libtab200 call returned a non-zero status."""
+
+
+_lib = None
+
+# every symbol include/tab200.h declares (tests check the .so exports them all)
+EXPORTS = [
+    'tab_version', 'tab_last_error',
+    'tab_nbr_create', 'tab_nbr_free', 'tab_nbr_build', 'tab_nbr_update',
+    'tab_nbr_sizes', 'tab_nbr_counts', 'tab_nbr_export',
+    'tab_eam_create', 'tab_model_free', 'tab_eam_eval', 'tab_eam_compute_host',
+    'tab_launch_count', 'tab_launch_count_reset',
+]
+
+
+def lib():
+    """Load (once) and return the ctypes handle.  Raises if the library has not
+    been built: run `python -c "import __graft_entry__ as g; g.build()"`."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise ImportError(
+            f"{LIB_PATH} is missing: the CUDA extension has not been built "
+            "(python -c 'import __graft_entry__ as g; g.build()'). "
+            "tensoralloy_b200 has no CPU fallback.")
+    L = C.CDLL(str(LIB_PATH), mode=getattr(os, 'RTLD_LAZY', 1))
+    vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+    pp = C.POINTER(vp)
+    L.tab_version.restype = C.c_int
+    L.tab_last_error.restype = C.c_char_p
+    L.tab_nbr_create.argtypes = [pp]
+    L.tab_nbr_free.argtypes = [vp]
+    L.tab_nbr_build.argtypes = [vp, i32, vp, vp, C.POINTER(dbl), C.POINTER(i32),
+                                dbl, vp]
+    L.tab_nbr_update.argtypes = [vp, vp, C.POINTER(dbl), vp]
+    L.tab_nbr_sizes.argtypes = [vp, C.POINTER(i64), C.POINTER(i32),
+                                C.POINTER(i32)]
+    L.tab_nbr_counts.argtypes = [vp, vp, vp]
+    L.tab_nbr_export.argtypes = [vp, vp, vp, vp, vp]
+    L.tab_eam_create.argtypes = [pp, i32, i32, C.POINTER(TabFn),
+                                 C.POINTER(TabFn), C.POINTER(TabFn),
+                                 C.POINTER(TabFn), C.POINTER(TabFn)]
+    L.tab_model_free.argtypes = [vp]
+    L.tab_eam_eval.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]
+    L.tab_eam_compute_host.argtypes = [vp, vp, i32, i32, vp, vp,
+                                       C.POINTER(dbl), C.POINTER(i32), dbl, i32,
+                                       vp, vp, vp, vp, vp]
+    L.tab_launch_count.restype = i64
+    L.tab_launch_count_reset.restype = None
+    for name in EXPORTS:
+        getattr(L, name)
+    _lib = L
+    return L
+
+
+def check(status, what=''):
+    if status != 0:
+        msg = lib().tab_last_error().decode('utf-8', 'replace')
+        raise TabError(f"{what} failed with status {status}: {msg}")
+
+
+def _cell9(cell):
+    arr = np.ascontiguousarray(np.asarray(cell, dtype=np.float64).reshape(9))
+    return (C.c_double * 9)(*arr.tolist())
+
+
+def _pbc3(pbc):
+    p = np.asarray(pbc).astype(bool).reshape(-1)
+    if p.size == 1:
+        p = np.repeat(p, 3)
+    return (C.c_int32 * 3)(*[int(x) for x in p])
+
+
+def _ptr(t):
+    """Device (or pinned-host) pointer of a torch tensor / None."""
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class NeighborList:
+    """Owner of one `tab_nbr` handle (cell list + neighbour lists on the GPU)."""
+
+    def __init__(self):
+        self._h = C.c_void_p()
+        check(lib().tab_nbr_create(C.byref(self._h)), 'tab_nbr_create')
+        self.n = 0
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().tab_nbr_free(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def build(self, d_pos, d_types, cell, pbc, rc):
+        """d_pos: cuda float64 [n,3] contiguous; d_types: cuda int32 [n] or None."""
+        import torch
+        assert d_pos.is_cuda and d_pos.dtype == torch.float64 and d_pos.is_contiguous()
+        if d_types is not None:
+            assert d_types.is_cuda and d_types.dtype == torch.int32
+        self.n = int(d_pos.shape[0])
+        check(lib().tab_nbr_build(self._h, self.n, _ptr(d_pos), _ptr(d_types),
+                                  _cell9(cell), _pbc3(pbc), float(rc), _stream()),
+              'tab_nbr_build')
+
+    def update(self, d_pos, cell=None):
+        c = _cell9(cell) if cell is not None else None
+        check(lib().tab_nbr_update(self._h, _ptr(d_pos), c, _stream()),
+              'tab_nbr_update')
+
+    def sizes(self):
+        nij, nnl, next_ = C.c_int64(), C.c_int32(), C.c_int32()
+        check(lib().tab_nbr_sizes(self._h, C.byref(nij), C.byref(nnl),
+                                  C.byref(next_)), 'tab_nbr_sizes')
+        return int(nij.value), int(nnl.value), int(next_.value)
+
+    def counts(self):
+        import torch
+        out = torch.empty(self.n, dtype=torch.int32, device='cuda')
+        check(lib().tab_nbr_counts(self._h, _ptr(out), _stream()), 'tab_nbr_counts')
+        return out
+
+    def export(self):
+        """(i, j, S) as cuda int32 tensors, the reference's ilist/jlist/n1."""
+        import torch
+        nij = self.sizes()[0]
+        i = torch.empty(max(nij, 1), dtype=torch.int32, device='cuda')
+        j = torch.empty(max(nij, 1), dtype=torch.int32, device='cuda')
+        S = torch.empty((max(nij, 1), 3), dtype=torch.int32, device='cuda')
+        check(lib().tab_nbr_export(self._h, _ptr(i), _ptr(j), _ptr(S), _stream()),
+              'tab_nbr_export')
+        return i[:nij], j[:nij], S[:nij]
+
+
+class EamModel:
+    """Owner of one `tab_model` handle for an EAM-family potential."""
+
+    def __init__(self, kind, n_el, rho, phi, embed, dipole=None, quadrupole=None):
+        nn = n_el * n_el
+        assert len(rho) == nn and len(phi) == nn and len(embed) == n_el
+
+        def arr(fns):
+            if fns is None:
+                return None
+            return (TabFn * len(fns))(*fns)
+
+        self._keep = [arr(rho), arr(phi), arr(embed), arr(dipole), arr(quadrupole)]
+        self._h = C.c_void_p()
+        check(lib().tab_eam_create(C.byref(self._h), int(kind), int(n_el),
+                                   *self._keep), 'tab_eam_create')
+        self.n_el = n_el
+        self.kind = kind
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().tab_model_free(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def eval(self, nbr, precision=PRECISION_HIGH, energy=None, eatom=None,
+             forces=None, virial=None):
+        check(lib().tab_eam_eval(self._h, nbr.handle, int(precision), _ptr(energy),
+                                 _ptr(eatom), _ptr(forces), _ptr(virial),
+                                 _stream()), 'tab_eam_eval')
+
+    def compute_host(self, nbr, precision, h_pos, h_types, cell, pbc, rc, rebuild,
+                     h_energy, h_eatom, h_forces, h_virial):
+        """All arguments are HOST torch tensors (pinned for full speed)."""
+        n = int(h_pos.shape[0])
+        check(lib().tab_eam_compute_host(
+            self._h, nbr.handle, int(precision), n, _ptr(h_pos), _ptr(h_types),
+            _cell9(cell), _pbc3(pbc), float(rc), int(bool(rebuild)),
+            _ptr(h_energy), _ptr(h_eatom), _ptr(h_forces), _ptr(h_virial),
+            _stream()), 'tab_eam_compute_host')
+        nbr.n = n

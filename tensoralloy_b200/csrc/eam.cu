@@ -1,0 +1,425 @@
+// eam.cu -- EAM / Finnis-Sinclair energy, forces and virial on the ELL lists.
+//
+// Replaces, for the reference:
+//   transformer/universal.py:448-474,583-620  gather, D = Rj-Ri+S.h, r = sqrt(D.D+eps)
+//   nn/eam/alloy.py:128-196, fs.py:146-203    rho_i = sum_j rho(r_ij)
+//   nn/eam/eam.py:401-449                     F(rho_i)
+//   nn/eam/eam.py:300-362                     0.5 * sum_j phi(r_ij)
+//   nn/eam/eam.py:265-298                     E = sum_i E_i
+//   nn/basic.py:276-331                       F = -dE/dR, virial = sum_p dE/dD_p (x) D_p
+// TF autograd is replaced by the analytic derivative.  Lists are FULL (directed),
+// so the force on atom i is assembled from row i alone:
+//   F_i = sum_j [F'_i rho'_{ij}(r) + F'_j rho'_{ji}(r) + phi'_{ij}(r)] D_ij / r
+// -- no scatter to j, no atomics, deterministic summation order.
+//
+// Two passes, thread per owned atom, lanes of a warp = the 32 atoms of one ELL
+// slice (coalesced index loads), one 32-byte Atom4 gather per pair:
+//   pass 1: rho_i, F(rho_i), F'(rho_i)
+//   spread: Atom4.w <- F' for owned atoms and their ghost images
+//   pass 2: forces, per-atom energy, block-reduced energy and virial
+#include "potentials.cuh"
+
+struct EamDev {
+    int kind;
+    int n_el;
+    const tab_fn *rho;     // [n_el*n_el] centre a, neighbour b
+    const tab_fn *phi;     // [n_el*n_el]
+    const tab_fn *embed;   // [n_el]
+};
+
+struct tab_model {
+    int family = 0;        // 0 = EAM
+    int kind = 0;
+    int n_el = 0;
+    bool zhou1 = false;    // single element, all-zjw04: shared-exponential fast path
+    double zp[8];          // fe, beta, lamda, re, A, alpha, kappa, B
+    DevBuf tables;         // tab_fn [2*n_el*n_el + n_el (+ 2*n_el*n_el)]
+    tab_fn embed0;         // host copy (fast path epilogue parameters)
+};
+
+// single-element zjw04: rho and the B term of phi share one exponential
+struct Zhou1 {
+    double fe, beta, lamda, re, A, alpha, kappa, B;
+};
+
+#define EAM_T 256
+
+template <typename Real>
+__device__ __forceinline__ void pair_r(const Atom4 &me, const Atom4 &a, Real &dx,
+                                       Real &dy, Real &dz, Real &r) {
+    // geometry always in float64 (positions are float64), then the working type
+    const double ddx = a.x - me.x, ddy = a.y - me.y, ddz = a.z - me.z;
+    dx = (Real)ddx;
+    dy = (Real)ddy;
+    dz = (Real)ddz;
+    r = Math<Real>::sqrt_(dx * dx + dy * dy + dz * dz + Math<Real>::eps());
+}
+
+__device__ __forceinline__ void load_tables(tab_fn *s, const tab_fn *g, int count) {
+    const int words = count * (int)(sizeof(tab_fn) / 8);
+    const double *src = reinterpret_cast<const double *>(g);
+    double *dst = reinterpret_cast<double *>(s);
+    for (int k = threadIdx.x; k < words; k += blockDim.x) dst[k] = src[k];
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------
+// pass 1
+// ---------------------------------------------------------------------------
+template <typename Real, bool FAST>
+__global__ void __launch_bounds__(EAM_T)
+k_eam_rho(int n, const Atom4 *__restrict__ atoms,
+          const uint8_t *__restrict__ types_ext, const int *__restrict__ counts,
+          const uint32_t *__restrict__ slice_ptr, const uint32_t *__restrict__ col,
+          EamDev m, Zhou1 z, tab_fn embed0, double *__restrict__ fprime,
+          double *__restrict__ fembed) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    tab_fn *tabs = reinterpret_cast<tab_fn *>(smem_raw);
+    const int nn = m.n_el * m.n_el;
+    if (!FAST) load_tables(tabs, m.rho, 2 * nn + m.n_el);
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const Atom4 me = atoms[idx];
+    const int ti = FAST ? 0 : (int)types_ext[idx];
+    const int cnt = counts[idx];
+    const uint32_t *cp = col + ((size_t)slice_ptr[idx >> 5] * 32u + (idx & 31));
+    Real rho = Real(0);
+    for (int k = 0; k < cnt; ++k) {
+        const uint32_t c = cp[(size_t)k * 32u];
+        const Atom4 a = atoms[c & TAB_COL_IDX_MASK];
+        Real dx, dy, dz, r, f, df;
+        pair_r<Real>(me, a, dx, dy, dz, r);
+        if (FAST) {
+            zhou_exp<Real>(r, (Real)z.fe, (Real)z.beta, (Real)z.lamda, (Real)z.re, f, df);
+        } else {
+            const int tj = (int)(c >> TAB_COL_TYPE_SHIFT);
+            eval_pair_fn<Real>(tabs[ti * m.n_el + tj], r, f, df);
+        }
+        rho += f;
+    }
+    Real F, dF;
+    if (FAST) eval_embed_fn<Real>(embed0, rho, F, dF);
+    else eval_embed_fn<Real>(tabs[2 * nn + ti], rho, F, dF);
+    fprime[idx] = (double)dF;
+    fembed[idx] = (double)F;
+}
+
+// Atom4.w <- F'(rho) for every extended atom (ghosts read their owner)
+__global__ void k_spread_w(int n_owned, int n_ext, const double *__restrict__ v,
+                           const int *__restrict__ ghost_owner,
+                           Atom4 *__restrict__ atoms) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_ext) return;
+    const int o = e < n_owned ? e : ghost_owner[e - n_owned];
+    atoms[e].w = v[o];
+}
+
+// ---------------------------------------------------------------------------
+// pass 2
+// ---------------------------------------------------------------------------
+template <typename Real, bool FAST>
+__global__ void __launch_bounds__(EAM_T)
+k_eam_force(int n, const Atom4 *__restrict__ atoms,
+            const uint8_t *__restrict__ types_ext, const int *__restrict__ counts,
+            const uint32_t *__restrict__ slice_ptr, const uint32_t *__restrict__ col,
+            const int *__restrict__ perm, EamDev m, Zhou1 z,
+            const double *__restrict__ fembed, double *__restrict__ eatom,
+            double *__restrict__ forces, double *__restrict__ partial) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    tab_fn *tabs = reinterpret_cast<tab_fn *>(smem_raw);
+    __shared__ double red[EAM_T / 32][7];
+    const int nn = m.n_el * m.n_el;
+    if (!FAST) load_tables(tabs, m.rho, 2 * nn + m.n_el);
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    double acc[7] = {0, 0, 0, 0, 0, 0, 0};   // E, vxx, vyy, vzz, vyz, vxz, vxy
+    if (idx < n) {
+        const Atom4 me = atoms[idx];
+        const int ti = FAST ? 0 : (int)types_ext[idx];
+        const int cnt = counts[idx];
+        const uint32_t *cp = col + ((size_t)slice_ptr[idx >> 5] * 32u + (idx & 31));
+        const Real fpi = (Real)me.w;
+        Real fx = 0, fy = 0, fz = 0, ep = 0;
+        Real vxx = 0, vyy = 0, vzz = 0, vyz = 0, vxz = 0, vxy = 0;
+        for (int k = 0; k < cnt; ++k) {
+            const uint32_t c = cp[(size_t)k * 32u];
+            const Atom4 a = atoms[c & TAB_COL_IDX_MASK];
+            Real dx, dy, dz, r;
+            pair_r<Real>(me, a, dx, dy, dz, r);
+            const Real fpj = (Real)a.w;
+            Real phi, dphi, der;   // der = dE/dr of the undirected pair seen from i
+            if (FAST) {
+                Real ga, dga, gb, dgb;
+                zhou_exp<Real>(r, Real(1), (Real)z.alpha, (Real)z.kappa, (Real)z.re, ga, dga);
+                zhou_exp<Real>(r, Real(1), (Real)z.beta, (Real)z.lamda, (Real)z.re, gb, dgb);
+                phi = (Real)z.A * ga - (Real)z.B * gb;
+                dphi = (Real)z.A * dga - (Real)z.B * dgb;
+                der = (fpi + fpj) * ((Real)z.fe * dgb) + dphi;
+            } else {
+                const int tj = (int)(c >> TAB_COL_TYPE_SHIFT);
+                Real rij, drij, rji, drji;
+                eval_pair_fn<Real>(tabs[ti * m.n_el + tj], r, rij, drij);
+                if (ti == tj) drji = drij;
+                else eval_pair_fn<Real>(tabs[tj * m.n_el + ti], r, rji, drji);
+                eval_pair_fn<Real>(tabs[nn + ti * m.n_el + tj], r, phi, dphi);
+                der = fpi * drij + fpj * drji + dphi;
+            }
+            const Real s = der / r;
+            const Real gx = s * dx, gy = s * dy, gz = s * dz;
+            fx += gx;
+            fy += gy;
+            fz += gz;
+            ep += phi;
+            vxx += gx * dx;
+            vyy += gy * dy;
+            vzz += gz * dz;
+            vyz += gy * dz;
+            vxz += gx * dz;
+            vxy += gx * dy;
+        }
+        const double ei = fembed[idx] + 0.5 * (double)ep;
+        const int o = perm[idx];
+        if (eatom) eatom[o] = ei;
+        if (forces) {
+            forces[3 * o + 0] = (double)fx;
+            forces[3 * o + 1] = (double)fy;
+            forces[3 * o + 2] = (double)fz;
+        }
+        acc[0] = ei;
+        // every undirected pair is visited from both ends: half of g (x) D each
+        acc[1] = 0.5 * (double)vxx;
+        acc[2] = 0.5 * (double)vyy;
+        acc[3] = 0.5 * (double)vzz;
+        acc[4] = 0.5 * (double)vyz;
+        acc[5] = 0.5 * (double)vxz;
+        acc[6] = 0.5 * (double)vxy;
+    }
+#pragma unroll
+    for (int q = 0; q < 7; ++q) {
+        double v = acc[q];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][q] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 7) {
+        double v = 0;
+        for (int w = 0; w < EAM_T / 32; ++w) v += red[w][threadIdx.x];
+        partial[(size_t)blockIdx.x * 8 + threadIdx.x] = v;
+    }
+}
+
+// fixed-order final reduction: energy[0], virial[9]
+__global__ void __launch_bounds__(256)
+k_reduce_partials(int nblk, const double *__restrict__ partial,
+                  double *__restrict__ energy, double *__restrict__ virial) {
+    __shared__ double sm[256][7];
+    double a[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (int b = threadIdx.x; b < nblk; b += 256)
+#pragma unroll
+        for (int q = 0; q < 7; ++q) a[q] += partial[(size_t)b * 8 + q];
+#pragma unroll
+    for (int q = 0; q < 7; ++q) sm[threadIdx.x][q] = a[q];
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s)
+#pragma unroll
+            for (int q = 0; q < 7; ++q) sm[threadIdx.x][q] += sm[threadIdx.x + s][q];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        if (energy) energy[0] = sm[0][0];
+        if (virial) {
+            const double xx = sm[0][1], yy = sm[0][2], zz = sm[0][3], yz = sm[0][4],
+                         xz = sm[0][5], xy = sm[0][6];
+            virial[0] = xx; virial[1] = xy; virial[2] = xz;
+            virial[3] = xy; virial[4] = yy; virial[5] = yz;
+            virial[6] = xz; virial[7] = yz; virial[8] = zz;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+extern "C" int tab_eam_create(tab_model **out, int32_t kind, int32_t n_el,
+                              const tab_fn *rho, const tab_fn *phi,
+                              const tab_fn *embed, const tab_fn *dipole,
+                              const tab_fn *quadrupole) {
+    if (!out || !rho || !phi || !embed || n_el < 1 || n_el > TAB_MAX_ELEMENTS) {
+        tab_set_error("tab_eam_create: bad argument");
+        return TAB_EINVAL;
+    }
+    if (kind != TAB_EAM_ALLOY && kind != TAB_EAM_FS) {
+        tab_set_error("tab_eam_create: kind %d not supported yet", kind);
+        return TAB_EUNSUPPORTED;
+    }
+    if (n_el > 8) {
+        tab_set_error("tab_eam_create: more than 8 elements not supported");
+        return TAB_EUNSUPPORTED;
+    }
+    (void)dipole;
+    (void)quadrupole;
+    tab_model *m = new tab_model();
+    m->kind = kind;
+    m->n_el = n_el;
+    const int nn = n_el * n_el;
+    const size_t count = (size_t)2 * nn + n_el;
+    int rc = m->tables.ensure(count * sizeof(tab_fn));
+    if (rc != TAB_OK) {
+        delete m;
+        return rc;
+    }
+    tab_fn *host = new tab_fn[count];
+    memcpy(host, rho, nn * sizeof(tab_fn));
+    memcpy(host + nn, phi, nn * sizeof(tab_fn));
+    memcpy(host + 2 * nn, embed, n_el * sizeof(tab_fn));
+    cudaError_t e = cudaMemcpy(m->tables.p, host, count * sizeof(tab_fn),
+                               cudaMemcpyHostToDevice);
+    delete[] host;
+    if (e != cudaSuccess) {
+        tab_set_error("tab_eam_create: cudaMemcpy -> %s", cudaGetErrorString(e));
+        m->tables.release();
+        delete m;
+        return TAB_ECUDA;
+    }
+    m->embed0 = embed[0];
+    // fast path: one element, zjw04 rho/phi/embed whose B-term parameters agree
+    if (n_el == 1 && rho[0].kind == TAB_FN_ZHOU_RHO && phi[0].kind == TAB_FN_ZHOU_PHI &&
+        (embed[0].kind == TAB_FN_ZHOU_EMBED || embed[0].kind == TAB_FN_ZHOU_EMBED_XC) &&
+        rho[0].p[1] == phi[0].p[4] && rho[0].p[2] == phi[0].p[5] &&
+        rho[0].p[3] == phi[0].p[6]) {
+        m->zhou1 = true;
+        m->zp[0] = rho[0].p[0];   // f_eq
+        m->zp[1] = rho[0].p[1];   // beta
+        m->zp[2] = rho[0].p[2];   // lamda
+        m->zp[3] = rho[0].p[3];   // r_eq
+        m->zp[4] = phi[0].p[0];   // A
+        m->zp[5] = phi[0].p[1];   // alpha
+        m->zp[6] = phi[0].p[2];   // kappa
+        m->zp[7] = phi[0].p[3];   // B
+    }
+    *out = m;
+    return TAB_OK;
+}
+
+extern "C" int tab_model_free(tab_model *m) {
+    if (!m) return TAB_OK;
+    m->tables.release();
+    delete m;
+    return TAB_OK;
+}
+
+template <typename Real, bool FAST>
+static int eam_run(tab_model *m, tab_nbr *nbr, double *d_energy, double *d_eatom,
+                   double *d_forces, double *d_virial, cudaStream_t st) {
+    const int n = nbr->n;
+    const int nblk = (n + EAM_T - 1) / EAM_T;
+    TAB_TRY(nbr->rho.ensure(sizeof(double) * 2 * (size_t)n));
+    TAB_TRY(nbr->partial.ensure(sizeof(double) * 8 * (size_t)nblk));
+    double *fprime = nbr->rho.as<double>();
+    double *fembed = fprime + n;
+    EamDev dev;
+    dev.kind = m->kind;
+    dev.n_el = m->n_el;
+    const int nn = m->n_el * m->n_el;
+    dev.rho = m->tables.as<tab_fn>();
+    dev.phi = dev.rho + nn;
+    dev.embed = dev.rho + 2 * nn;
+    Zhou1 z;
+    memcpy(&z, m->zp, sizeof(z));
+    const size_t smem = FAST ? 0 : (size_t)(2 * nn + m->n_el) * sizeof(tab_fn);
+    const Atom4 *atoms = nbr->atoms.as<Atom4>();
+    k_eam_rho<Real, FAST><<<nblk, EAM_T, smem, st>>>(
+        n, atoms, nbr->types_ext.as<uint8_t>(), nbr->counts.as<int>(),
+        nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>(), dev, z, m->embed0,
+        fprime, fembed);
+    TAB_LAUNCH_CHECK();
+    k_spread_w<<<(nbr->n_ext + 255) / 256, 256, 0, st>>>(
+        n, nbr->n_ext, fprime, nbr->ghost_owner.as<int>(), nbr->atoms.as<Atom4>());
+    TAB_LAUNCH_CHECK();
+    k_eam_force<Real, FAST><<<nblk, EAM_T, smem, st>>>(
+        n, atoms, nbr->types_ext.as<uint8_t>(), nbr->counts.as<int>(),
+        nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>(), nbr->perm.as<int>(),
+        dev, z, fembed, d_eatom, d_forces, nbr->partial.as<double>());
+    TAB_LAUNCH_CHECK();
+    if (d_energy || d_virial) {
+        k_reduce_partials<<<1, 256, 0, st>>>(nblk, nbr->partial.as<double>(), d_energy,
+                                             d_virial);
+        TAB_LAUNCH_CHECK();
+    }
+    return TAB_OK;
+}
+
+extern "C" int tab_eam_eval(tab_model *m, tab_nbr *nbr, int32_t precision,
+                            double *d_energy, double *d_eatom, double *d_forces,
+                            double *d_virial, void *stream) {
+    if (!m || !nbr) {
+        tab_set_error("tab_eam_eval: null handle");
+        return TAB_EINVAL;
+    }
+    if (!nbr->built) {
+        tab_set_error("tab_eam_eval before tab_nbr_build");
+        return TAB_ESTATE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (precision == TAB_PRECISION_HIGH) {
+        return m->zhou1 ? eam_run<double, true>(m, nbr, d_energy, d_eatom, d_forces, d_virial, st)
+                        : eam_run<double, false>(m, nbr, d_energy, d_eatom, d_forces, d_virial, st);
+    } else if (precision == TAB_PRECISION_MEDIUM) {
+        return m->zhou1 ? eam_run<float, true>(m, nbr, d_energy, d_eatom, d_forces, d_virial, st)
+                        : eam_run<float, false>(m, nbr, d_energy, d_eatom, d_forces, d_virial, st);
+    }
+    tab_set_error("tab_eam_eval: unknown precision %d", precision);
+    return TAB_EINVAL;
+}
+
+// Host-buffer convenience: see include/tab200.h.
+struct HostStage {
+    DevBuf pos, types, out;
+};
+static HostStage g_stage;
+
+extern "C" int tab_eam_compute_host(tab_model *m, tab_nbr *nbr, int32_t precision,
+                                    int32_t n, const double *h_pos,
+                                    const int32_t *h_types, const double *h_cell,
+                                    const int32_t *h_pbc, double rc, int32_t rebuild,
+                                    double *h_energy, double *h_eatom,
+                                    double *h_forces, double *h_virial, void *stream) {
+    if (!m || !nbr || n <= 0 || !h_pos || !h_cell || !h_pbc) {
+        tab_set_error("tab_eam_compute_host: bad argument");
+        return TAB_EINVAL;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    TAB_TRY(g_stage.pos.ensure(sizeof(double) * 3 * (size_t)n));
+    TAB_TRY(g_stage.types.ensure(sizeof(int32_t) * (size_t)n));
+    // out: energy[1] virial[9] (pad to 16) | forces[3n] | eatom[n]
+    TAB_TRY(g_stage.out.ensure(sizeof(double) * (16 + 4 * (size_t)n)));
+    double *d_pos = g_stage.pos.as<double>();
+    int32_t *d_types = h_types ? g_stage.types.as<int32_t>() : nullptr;
+    double *d_out = g_stage.out.as<double>();
+    TAB_CUDA(cudaMemcpyAsync(d_pos, h_pos, sizeof(double) * 3 * (size_t)n,
+                             cudaMemcpyHostToDevice, st));
+    if (rebuild || !nbr->built || nbr->n != n) {
+        if (h_types)
+            TAB_CUDA(cudaMemcpyAsync(d_types, h_types, sizeof(int32_t) * (size_t)n,
+                                     cudaMemcpyHostToDevice, st));
+        TAB_TRY(tab_nbr_build(nbr, n, d_pos, d_types, h_cell, h_pbc, rc, stream));
+    } else {
+        TAB_TRY(tab_nbr_update(nbr, d_pos, h_cell, stream));
+    }
+    TAB_TRY(tab_eam_eval(m, nbr, precision, d_out, h_eatom ? d_out + 16 + 3 * (size_t)n : nullptr,
+                         h_forces ? d_out + 16 : nullptr, d_out + 1, stream));
+    if (h_energy)
+        TAB_CUDA(cudaMemcpyAsync(h_energy, d_out, sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (h_virial)
+        TAB_CUDA(cudaMemcpyAsync(h_virial, d_out + 1, 9 * sizeof(double),
+                                 cudaMemcpyDeviceToHost, st));
+    if (h_forces)
+        TAB_CUDA(cudaMemcpyAsync(h_forces, d_out + 16, sizeof(double) * 3 * (size_t)n,
+                                 cudaMemcpyDeviceToHost, st));
+    if (h_eatom)
+        TAB_CUDA(cudaMemcpyAsync(h_eatom, d_out + 16 + 3 * (size_t)n,
+                                 sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    TAB_CUDA(cudaStreamSynchronize(st));
+    return TAB_OK;
+}

@@ -1,0 +1,709 @@
+// nbr.cu -- GPU cell list, periodic ghost images and ELL neighbour lists.
+//
+// Replaces ase.neighborlist.neighbor_list as called by the reference at
+// tensoralloy/transformer/universal.py:58 and tensoralloy/neighbor.py:84, and the
+// Python index-map loops of universal.py:69-106.
+//
+// Pipeline (all on the caller's stream):
+//   k_bin          scaled coords -> owned-cell rank (+ wrap shift), histogram
+//   scan           cell_count -> cell_start
+//   k_scatter      atoms -> cell-sorted permutation (then k_sort_cells makes the
+//                  order inside a cell = caller index order: deterministic)
+//   k_gather_owned wrapped positions in sorted order -> Atom4 records
+//   k_ext_cells    extended (ghost-padded) cell table; ghost counts
+//   scan           ghost counts -> ghost starts
+//   k_fill_ghosts  ghost records = source record + S.h
+//   k_count        neighbours per atom, slice widths, nij, nnl_max
+//   scan           slice widths -> slice_ptr
+//   k_fill         ELL entries, 32 atoms per slice, entry k of lane l at
+//                  col[(slice_ptr[s] + k) * 32 + l]  (coalesced for thread-per-atom
+//                  consumers; no per-pair shift vectors: ghosts carry them)
+//
+// Membership is ASE's: D = pos[j] - pos[i] + S.cell, sqrt(D.D) < rc in float64.
+// The fast test uses the pre-shifted ghost records; candidates whose d^2 is
+// within 1e-9 relative of rc^2 are re-decided with exactly ASE's expression on
+// the caller's positions, so the list is bit-exact.
+#include <math.h>
+
+#include "tab_internal.h"
+
+#define B TAB_TILE_B
+
+// ---------------------------------------------------------------------------
+// cell indexing
+// ---------------------------------------------------------------------------
+__host__ __device__ inline int owned_rank(const Grid &g, int cx, int cy, int cz) {
+    const int tx = cx / B, ty = cy / B, tz = cz / B;
+    const int lx = cx % B, ly = cy % B, lz = cz % B;
+    return ((tz * g.tl[1] + ty) * g.tl[0] + tx) * (B * B * B) + (lz * B + ly) * B + lx;
+}
+
+__host__ __device__ inline void owned_unrank(const Grid &g, int rank, int &cx,
+                                             int &cy, int &cz) {
+    const int local = rank % (B * B * B);
+    int t = rank / (B * B * B);
+    const int tx = t % g.tl[0];
+    t /= g.tl[0];
+    const int ty = t % g.tl[1];
+    const int tz = t / g.tl[1];
+    cx = tx * B + local % B;
+    cy = ty * B + (local / B) % B;
+    cz = tz * B + local / (B * B);
+}
+
+__host__ __device__ inline int floordiv(int a, int b) {
+    int q = a / b;
+    if ((a % b != 0) && ((a < 0) != (b < 0))) --q;
+    return q;
+}
+
+// ---------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------
+__global__ void k_bin(int n, const double *__restrict__ pos, Grid g,
+                      int *__restrict__ cell_of, int *__restrict__ s0,
+                      uint32_t *__restrict__ cell_count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double x = pos[3 * i], y = pos[3 * i + 1], z = pos[3 * i + 2];
+    int c[3], sh[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double s = x * g.hinv[k] + y * g.hinv[3 + k] + z * g.hinv[6 + k];
+        int b = (int)floor(s * (double)g.nb[k]);
+        if (g.pbc[k]) {
+            sh[k] = floordiv(b, g.nb[k]);
+            b -= sh[k] * g.nb[k];
+        } else {
+            sh[k] = 0;
+            b = min(max(b, 0), g.nb[k] - 1);
+        }
+        c[k] = b;
+    }
+    const int rank = owned_rank(g, c[0], c[1], c[2]);
+    cell_of[i] = rank;
+    s0[i] = tab_pack_shift(sh[0], sh[1], sh[2]);
+    atomicAdd(&cell_count[rank], 1u);
+}
+
+__global__ void k_scatter(int n, const int *__restrict__ cell_of,
+                          const uint32_t *__restrict__ cell_start,
+                          uint32_t *__restrict__ cell_fill,
+                          int *__restrict__ perm) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int rank = cell_of[i];
+    const uint32_t slot = atomicAdd(&cell_fill[rank], 1u);
+    perm[cell_start[rank] + slot] = i;
+}
+
+// order inside a cell = ascending caller index (removes the atomics' race order)
+__global__ void k_sort_cells(int n_slots, const uint32_t *__restrict__ cell_start,
+                             const uint32_t *__restrict__ cell_count,
+                             int *__restrict__ perm) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_slots) return;
+    const int cnt = (int)cell_count[c];
+    int *p = perm + cell_start[c];
+    for (int a = 1; a < cnt; ++a) {
+        const int v = p[a];
+        int b = a - 1;
+        while (b >= 0 && p[b] > v) {
+            p[b + 1] = p[b];
+            --b;
+        }
+        p[b + 1] = v;
+    }
+}
+
+__global__ void k_gather_owned(int n, const double *__restrict__ pos,
+                               const int *__restrict__ types, Grid g,
+                               const int *__restrict__ perm,
+                               const int *__restrict__ s0,
+                               Atom4 *__restrict__ atoms,
+                               uint8_t *__restrict__ types_ext) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const int i = perm[idx];
+    double x = pos[3 * i], y = pos[3 * i + 1], z = pos[3 * i + 2];
+    const int s = s0[i];
+    if (s != tab_pack_shift(0, 0, 0)) {
+        int a, b, c;
+        tab_unpack_shift(s, a, b, c);
+        x -= a * g.h[0] + b * g.h[3] + c * g.h[6];
+        y -= a * g.h[1] + b * g.h[4] + c * g.h[7];
+        z -= a * g.h[2] + b * g.h[5] + c * g.h[8];
+    }
+    Atom4 r;
+    r.x = x;
+    r.y = y;
+    r.z = z;
+    r.w = 0.0;
+    atoms[idx] = r;
+    if (types_ext) types_ext[idx] = types ? (uint8_t)types[i] : (uint8_t)0;
+}
+
+// one thread per extended cell: interior cells point at the owned range, ghost
+// cells get the count of their source cell.
+__global__ void k_ext_cells(Grid g, const uint32_t *__restrict__ cell_start,
+                            const uint32_t *__restrict__ cell_count,
+                            uint32_t *__restrict__ ext_start,
+                            uint32_t *__restrict__ ext_count,
+                            uint32_t *__restrict__ gcount) {
+    const int lin = blockIdx.x * blockDim.x + threadIdx.x;
+    if (lin >= g.n_ecells) return;
+    int e[3];
+    e[0] = lin % g.ne[0];
+    e[1] = (lin / g.ne[0]) % g.ne[1];
+    e[2] = lin / (g.ne[0] * g.ne[1]);
+    int c[3];
+    bool ghost = false;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        c[k] = e[k] - g.g[k];
+        if (c[k] < 0 || c[k] >= g.nb[k]) {
+            ghost = true;
+            c[k] -= floordiv(c[k], g.nb[k]) * g.nb[k];
+        }
+    }
+    const int rank = owned_rank(g, c[0], c[1], c[2]);
+    const uint32_t cnt = cell_count[rank];
+    ext_count[lin] = cnt;
+    if (ghost) {
+        gcount[lin] = cnt;
+    } else {
+        gcount[lin] = 0;
+        ext_start[lin] = cell_start[rank];
+    }
+}
+
+// one warp per extended cell; ghosts only.
+__global__ void k_fill_ghosts(Grid g, int n_owned,
+                              const uint32_t *__restrict__ cell_start,
+                              const uint32_t *__restrict__ gstart,
+                              const uint32_t *__restrict__ gcount,
+                              uint32_t *__restrict__ ext_start,
+                              Atom4 *__restrict__ atoms,
+                              uint8_t *__restrict__ types_ext,
+                              int *__restrict__ ghost_owner,
+                              int *__restrict__ ghost_S, int refresh_only) {
+    const int lin = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (lin >= g.n_ecells) return;
+    const uint32_t cnt = gcount[lin];
+    if (cnt == 0) return;
+    int e[3], c[3], S[3];
+    e[0] = lin % g.ne[0];
+    e[1] = (lin / g.ne[0]) % g.ne[1];
+    e[2] = lin / (g.ne[0] * g.ne[1]);
+    bool ghost = false;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        c[k] = e[k] - g.g[k];
+        S[k] = 0;
+        if (c[k] < 0 || c[k] >= g.nb[k]) {
+            ghost = true;
+            S[k] = floordiv(c[k], g.nb[k]);
+            c[k] -= S[k] * g.nb[k];
+        }
+    }
+    if (!ghost) return;
+    const uint32_t src = cell_start[owned_rank(g, c[0], c[1], c[2])];
+    const uint32_t dst = (uint32_t)n_owned + gstart[lin];
+    if (lane == 0 && !refresh_only) ext_start[lin] = dst;
+    const double sx = S[0] * g.h[0] + S[1] * g.h[3] + S[2] * g.h[6];
+    const double sy = S[0] * g.h[1] + S[1] * g.h[4] + S[2] * g.h[7];
+    const double sz = S[0] * g.h[2] + S[1] * g.h[5] + S[2] * g.h[8];
+    const int packed = tab_pack_shift(S[0], S[1], S[2]);
+    for (uint32_t k = lane; k < cnt; k += 32) {
+        Atom4 a = atoms[src + k];
+        a.x += sx;
+        a.y += sy;
+        a.z += sz;
+        atoms[dst + k] = a;
+        if (!refresh_only) {
+            types_ext[dst + k] = types_ext[src + k];
+            ghost_owner[dst + k - n_owned] = (int)(src + k);
+            ghost_S[dst + k - n_owned] = packed;
+        }
+    }
+}
+
+struct ExactCtx {
+    const double *pos;       // caller positions
+    const int *perm;
+    const int *s0;           // caller order
+    const int *ghost_owner;
+    const int *ghost_S;
+    int n_owned;
+};
+
+// ASE's membership expression on the caller's positions (no FMA contraction).
+__device__ __noinline__ bool exact_inside(const Grid &g, const ExactCtx &x, int i,
+                                          int j) {
+    const int oi = x.perm[i];
+    int owner = j, Sa = 0, Sb = 0, Sc = 0;
+    if (j >= x.n_owned) {
+        owner = x.ghost_owner[j - x.n_owned];
+        tab_unpack_shift(x.ghost_S[j - x.n_owned], Sa, Sb, Sc);
+    }
+    const int oj = x.perm[owner];
+    int ia, ib, ic, ja, jb, jc;
+    tab_unpack_shift(x.s0[oi], ia, ib, ic);
+    tab_unpack_shift(x.s0[oj], ja, jb, jc);
+    const double S0 = (double)(Sa - ja + ia), S1 = (double)(Sb - jb + ib),
+                 S2 = (double)(Sc - jc + ic);
+    double D[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double sh = __dadd_rn(__dadd_rn(__dmul_rn(S0, g.h[k]),
+                                              __dmul_rn(S1, g.h[3 + k])),
+                                    __dmul_rn(S2, g.h[6 + k]));
+        D[k] = __dadd_rn(__dsub_rn(x.pos[3 * oj + k], x.pos[3 * oi + k]), sh);
+    }
+    const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(D[0], D[0]), __dmul_rn(D[1], D[1])),
+                                __dmul_rn(D[2], D[2]));
+    return __dsqrt_rn(d2) < g.rc;
+}
+
+// Shared traversal of the candidate cells of one owned atom.  F(j) is called
+// for every neighbour in deterministic order.
+template <typename F>
+__device__ __forceinline__ void for_each_neighbor(
+    const Grid &g, const ExactCtx &x, int idx, int rank,
+    const Atom4 *__restrict__ atoms, const uint32_t *__restrict__ ext_start,
+    const uint32_t *__restrict__ ext_count, F &&f) {
+    int cx, cy, cz;
+    owned_unrank(g, rank, cx, cy, cz);
+    const Atom4 me = atoms[idx];
+    const double tol = 1e-9 * g.rc2;
+    for (int dz = -g.sr[2]; dz <= g.sr[2]; ++dz) {
+        const int ez = cz + dz;
+        if (!g.pbc[2] && (ez < 0 || ez >= g.nb[2])) continue;
+        for (int dy = -g.sr[1]; dy <= g.sr[1]; ++dy) {
+            const int ey = cy + dy;
+            if (!g.pbc[1] && (ey < 0 || ey >= g.nb[1])) continue;
+            for (int dx = -g.sr[0]; dx <= g.sr[0]; ++dx) {
+                const int ex = cx + dx;
+                if (!g.pbc[0] && (ex < 0 || ex >= g.nb[0])) continue;
+                const int lin = ((ez + g.g[2]) * g.ne[1] + (ey + g.g[1])) * g.ne[0] +
+                                (ex + g.g[0]);
+                const uint32_t start = ext_start[lin];
+                const uint32_t cnt = ext_count[lin];
+                for (uint32_t k = 0; k < cnt; ++k) {
+                    const int j = (int)(start + k);
+                    if (j == idx) continue;
+                    const Atom4 a = atoms[j];
+                    const double ddx = a.x - me.x, ddy = a.y - me.y, ddz = a.z - me.z;
+                    const double d2 = ddx * ddx + ddy * ddy + ddz * ddz;
+                    bool in = d2 < g.rc2;
+                    if (fabs(d2 - g.rc2) <= tol) in = exact_inside(g, x, idx, j);
+                    if (in) f(j);
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128)
+k_count(int n, Grid g, ExactCtx x, const int *__restrict__ cell_of,
+        const Atom4 *__restrict__ atoms, const uint32_t *__restrict__ ext_start,
+        const uint32_t *__restrict__ ext_count, int *__restrict__ counts,
+        uint32_t *__restrict__ slice_w, unsigned long long *__restrict__ stats) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    int cnt = 0;
+    if (idx < n) {
+        const int rank = cell_of[x.perm[idx]];
+        for_each_neighbor(g, x, idx, rank, atoms, ext_start, ext_count,
+                          [&](int) { ++cnt; });
+        counts[idx] = cnt;
+    }
+    // slice width = warp max, nij = sum, nnl_max = max
+    int mx = cnt, sum = cnt;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+        sum += __shfl_xor_sync(0xffffffffu, sum, d);
+    }
+    if ((threadIdx.x & 31) == 0 && idx < n) {
+        slice_w[idx >> 5] = (uint32_t)mx;
+        atomicAdd(&stats[0], (unsigned long long)sum);
+        atomicMax(&stats[1], (unsigned long long)mx);
+    }
+}
+
+__global__ void __launch_bounds__(128)
+k_fill(int n, Grid g, ExactCtx x, const int *__restrict__ cell_of,
+       const Atom4 *__restrict__ atoms, const uint8_t *__restrict__ types_ext,
+       const uint32_t *__restrict__ ext_start,
+       const uint32_t *__restrict__ ext_count,
+       const uint32_t *__restrict__ slice_w,
+       const uint32_t *__restrict__ slice_ptr, uint32_t *__restrict__ col) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = idx >> 5, lane = idx & 31;
+    if (s >= (n + 31) / 32) return;
+    uint32_t *base = col + ((size_t)slice_ptr[s] * 32u + lane);
+    uint32_t k = 0;
+    if (idx < n) {
+        const int rank = cell_of[x.perm[idx]];
+        for_each_neighbor(g, x, idx, rank, atoms, ext_start, ext_count, [&](int j) {
+            base[(size_t)k * 32u] =
+                (uint32_t)j | ((uint32_t)types_ext[j] << TAB_COL_TYPE_SHIFT);
+            ++k;
+        });
+    }
+    const uint32_t w = slice_w[s];
+    for (; k < w; ++k) base[(size_t)k * 32u] = TAB_COL_PAD;
+}
+
+__global__ void k_scatter_counts(int n, const int *__restrict__ perm,
+                                 const int *__restrict__ counts,
+                                 int *__restrict__ out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < n) out[perm[idx]] = counts[idx];
+}
+
+__global__ void k_export(int n, int n_owned, const int *__restrict__ perm,
+                         const int *__restrict__ s0,
+                         const int *__restrict__ counts,
+                         const uint32_t *__restrict__ slice_ptr,
+                         const uint32_t *__restrict__ col,
+                         const int *__restrict__ ghost_owner,
+                         const int *__restrict__ ghost_S,
+                         const uint32_t *__restrict__ row_ptr,
+                         int *__restrict__ out_i, int *__restrict__ out_j,
+                         int *__restrict__ out_S) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const int oi = perm[idx];
+    int ia, ib, ic;
+    tab_unpack_shift(s0[oi], ia, ib, ic);
+    const uint32_t *base = col + ((size_t)slice_ptr[idx >> 5] * 32u + (idx & 31));
+    size_t o = row_ptr[oi];
+    const int cnt = counts[idx];
+    for (int k = 0; k < cnt; ++k, ++o) {
+        const int j = (int)(base[(size_t)k * 32u] & TAB_COL_IDX_MASK);
+        int owner = j, Sa = 0, Sb = 0, Sc = 0;
+        if (j >= n_owned) {
+            owner = ghost_owner[j - n_owned];
+            tab_unpack_shift(ghost_S[j - n_owned], Sa, Sb, Sc);
+        }
+        const int oj = perm[owner];
+        int ja, jb, jc;
+        tab_unpack_shift(s0[oj], ja, jb, jc);
+        out_i[o] = oi;
+        out_j[o] = oj;
+        out_S[3 * o + 0] = Sa - ja + ia;
+        out_S[3 * o + 1] = Sb - jb + ib;
+        out_S[3 * o + 2] = Sc - jc + ic;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+static void invert3(const double *h, double *inv, double *det_out) {
+    const double a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5],
+                 g = h[6], hh = h[7], i = h[8];
+    const double det = a * (e * i - f * hh) - b * (d * i - f * g) + c * (d * hh - e * g);
+    inv[0] = (e * i - f * hh) / det;
+    inv[1] = (c * hh - b * i) / det;
+    inv[2] = (b * f - c * e) / det;
+    inv[3] = (f * g - d * i) / det;
+    inv[4] = (a * i - c * g) / det;
+    inv[5] = (c * d - a * f) / det;
+    inv[6] = (d * hh - e * g) / det;
+    inv[7] = (b * g - a * hh) / det;
+    inv[8] = (a * e - b * d) / det;
+    *det_out = det;
+}
+
+static int setup_grid(Grid &g, int n, const double *h_cell, const int *h_pbc,
+                      double rc) {
+    memcpy(g.h, h_cell, 9 * sizeof(double));
+    double det;
+    invert3(g.h, g.hinv, &det);
+    if (!(fabs(det) > 1e-12)) {
+        tab_set_error("cell is singular (det=%g); non-periodic structures must be "
+                      "given a bounding cell by the caller", det);
+        return TAB_EINVAL;
+    }
+    g.rc = rc;
+    g.rc2 = rc * rc;
+    const double rpad = rc * (1.0 + 1e-6);
+    // face distance along direction k = 1 / |column k of hinv|
+    long long cells = 1;
+    double fd[3];
+    for (int k = 0; k < 3; ++k) {
+        const double nrm = sqrt(g.hinv[k] * g.hinv[k] + g.hinv[3 + k] * g.hinv[3 + k] +
+                                g.hinv[6 + k] * g.hinv[6 + k]);
+        fd[k] = 1.0 / nrm;
+        g.pbc[k] = h_pbc[k] ? 1 : 0;
+        int nb = (int)floor(fd[k] / rpad);
+        if (nb < 1) nb = 1;
+        g.nb[k] = nb;
+        cells *= nb;
+    }
+    // bound the table for dilute systems
+    const long long cap = 8LL * n + 4096;
+    while (cells > cap) {
+        int kmax = 0;
+        for (int k = 1; k < 3; ++k)
+            if (g.nb[k] > g.nb[kmax]) kmax = k;
+        cells /= g.nb[kmax];
+        g.nb[kmax] = (g.nb[kmax] + 1) / 2;
+        cells *= g.nb[kmax];
+    }
+    long long ecells = 1, slots = 1;
+    for (int k = 0; k < 3; ++k) {
+        const double w = fd[k] / g.nb[k];
+        int sr = (int)ceil(rpad / w);
+        if (sr < 1) sr = 1;
+        if (!g.pbc[k] && g.nb[k] == 1) sr = 0;
+        g.sr[k] = sr;
+        g.g[k] = g.pbc[k] ? sr : 0;
+        g.ne[k] = g.nb[k] + 2 * g.g[k];
+        g.tl[k] = (g.nb[k] + B - 1) / B;
+        ecells *= g.ne[k];
+        slots *= (long long)g.tl[k] * B;
+        if (sr > 500) {
+            tab_set_error("cutoff %g spans %d images of the cell: unsupported", rc, sr);
+            return TAB_EUNSUPPORTED;
+        }
+    }
+    if (ecells > 0x3fffffffLL || slots > 0x3fffffffLL) {
+        tab_set_error("cell table too large");
+        return TAB_EUNSUPPORTED;
+    }
+    g.n_ecells = (int)ecells;
+    g.n_slots = (int)slots;
+    return TAB_OK;
+}
+
+extern "C" int tab_nbr_create(tab_nbr **out) {
+    if (!out) return TAB_EINVAL;
+    *out = new tab_nbr();
+    return TAB_OK;
+}
+
+extern "C" int tab_nbr_free(tab_nbr *nbr) {
+    if (!nbr) return TAB_OK;
+    DevBuf *bufs[] = {&nbr->cell_of, &nbr->s0, &nbr->types_in, &nbr->perm, &nbr->counts,
+                      &nbr->atoms, &nbr->types_ext, &nbr->ghost_owner, &nbr->ghost_S,
+                      &nbr->cell_count, &nbr->cell_start, &nbr->cell_fill,
+                      &nbr->ext_start, &nbr->ext_count, &nbr->gcount, &nbr->gstart,
+                      &nbr->slice_w, &nbr->slice_ptr, &nbr->col, &nbr->scan_tmp,
+                      &nbr->stats, &nbr->row_ptr, &nbr->rho, &nbr->partial, &nbr->adp};
+    for (DevBuf *b : bufs) b->release();
+    delete nbr;
+    return TAB_OK;
+}
+
+static inline int nblocks(long long n, int t) { return (int)((n + t - 1) / t); }
+
+static int refresh_positions(tab_nbr *nbr, const double *d_pos, cudaStream_t st) {
+    const int n = nbr->n;
+    const Grid &g = nbr->grid;
+    k_gather_owned<<<nblocks(n, 256), 256, 0, st>>>(
+        n, d_pos, nullptr, g, nbr->perm.as<int>(), nbr->s0.as<int>(),
+        nbr->atoms.as<Atom4>(), nullptr);
+    TAB_LAUNCH_CHECK();
+    if (nbr->n_ghost > 0) {
+        k_fill_ghosts<<<nblocks((long long)g.n_ecells * 32, 256), 256, 0, st>>>(
+            g, n, nbr->cell_start.as<uint32_t>(), nbr->gstart.as<uint32_t>(),
+            nbr->gcount.as<uint32_t>(), nbr->ext_start.as<uint32_t>(),
+            nbr->atoms.as<Atom4>(), nbr->types_ext.as<uint8_t>(),
+            nbr->ghost_owner.as<int>(), nbr->ghost_S.as<int>(), 1);
+        TAB_LAUNCH_CHECK();
+    }
+    return TAB_OK;
+}
+
+extern "C" int tab_nbr_build(tab_nbr *nbr, int32_t n, const double *d_pos,
+                             const int32_t *d_types, const double *h_cell,
+                             const int32_t *h_pbc, double rc, void *stream) {
+    if (!nbr || n <= 0 || !d_pos || !h_cell || !h_pbc || !(rc > 0)) {
+        tab_set_error("tab_nbr_build: bad argument");
+        return TAB_EINVAL;
+    }
+    if ((unsigned)n > TAB_COL_IDX_MASK / 2) {
+        tab_set_error("tab_nbr_build: too many atoms for one device (%d)", n);
+        return TAB_EUNSUPPORTED;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    nbr->built = false;
+    Grid &g = nbr->grid;
+    TAB_TRY(setup_grid(g, n, h_cell, h_pbc, rc));
+    nbr->n = n;
+    nbr->n_slices = (n + 31) / 32;
+
+    TAB_TRY(nbr->cell_of.ensure(sizeof(int) * n));
+    TAB_TRY(nbr->s0.ensure(sizeof(int) * n));
+    TAB_TRY(nbr->perm.ensure(sizeof(int) * n));
+    TAB_TRY(nbr->counts.ensure(sizeof(int) * n));
+    TAB_TRY(nbr->cell_count.ensure(sizeof(uint32_t) * g.n_slots));
+    TAB_TRY(nbr->cell_start.ensure(sizeof(uint32_t) * g.n_slots));
+    TAB_TRY(nbr->cell_fill.ensure(sizeof(uint32_t) * g.n_slots));
+    TAB_TRY(nbr->ext_start.ensure(sizeof(uint32_t) * g.n_ecells));
+    TAB_TRY(nbr->ext_count.ensure(sizeof(uint32_t) * g.n_ecells));
+    TAB_TRY(nbr->gcount.ensure(sizeof(uint32_t) * g.n_ecells));
+    TAB_TRY(nbr->gstart.ensure(sizeof(uint32_t) * g.n_ecells));
+    TAB_TRY(nbr->slice_w.ensure(sizeof(uint32_t) * nbr->n_slices));
+    TAB_TRY(nbr->slice_ptr.ensure(sizeof(uint32_t) * nbr->n_slices));
+    TAB_TRY(nbr->stats.ensure(4 * sizeof(unsigned long long)));
+    unsigned long long *d_stats = nbr->stats.as<unsigned long long>();
+
+    TAB_CUDA(cudaMemsetAsync(nbr->cell_count.p, 0, sizeof(uint32_t) * g.n_slots, st));
+    TAB_CUDA(cudaMemsetAsync(nbr->cell_fill.p, 0, sizeof(uint32_t) * g.n_slots, st));
+    TAB_CUDA(cudaMemsetAsync(d_stats, 0, 4 * sizeof(unsigned long long), st));
+
+    k_bin<<<nblocks(n, 256), 256, 0, st>>>(n, d_pos, g, nbr->cell_of.as<int>(),
+                                           nbr->s0.as<int>(),
+                                           nbr->cell_count.as<uint32_t>());
+    TAB_LAUNCH_CHECK();
+    TAB_TRY(tab_scan_exclusive_u32(nbr->cell_count.as<uint32_t>(),
+                                   nbr->cell_start.as<uint32_t>(), g.n_slots, nullptr,
+                                   nbr->scan_tmp, st));
+    k_scatter<<<nblocks(n, 256), 256, 0, st>>>(n, nbr->cell_of.as<int>(),
+                                               nbr->cell_start.as<uint32_t>(),
+                                               nbr->cell_fill.as<uint32_t>(),
+                                               nbr->perm.as<int>());
+    TAB_LAUNCH_CHECK();
+    k_sort_cells<<<nblocks(g.n_slots, 128), 128, 0, st>>>(
+        g.n_slots, nbr->cell_start.as<uint32_t>(), nbr->cell_count.as<uint32_t>(),
+        nbr->perm.as<int>());
+    TAB_LAUNCH_CHECK();
+
+    // ghost bookkeeping -> n_ghost (one small read-back)
+    k_ext_cells<<<nblocks(g.n_ecells, 256), 256, 0, st>>>(
+        g, nbr->cell_start.as<uint32_t>(), nbr->cell_count.as<uint32_t>(),
+        nbr->ext_start.as<uint32_t>(), nbr->ext_count.as<uint32_t>(),
+        nbr->gcount.as<uint32_t>());
+    TAB_LAUNCH_CHECK();
+    TAB_TRY(tab_scan_exclusive_u32(nbr->gcount.as<uint32_t>(),
+                                   nbr->gstart.as<uint32_t>(), g.n_ecells, d_stats + 2,
+                                   nbr->scan_tmp, st));
+    unsigned long long n_ghost = 0;
+    TAB_CUDA(cudaMemcpyAsync(&n_ghost, d_stats + 2, sizeof(n_ghost),
+                             cudaMemcpyDeviceToHost, st));
+    TAB_CUDA(cudaStreamSynchronize(st));
+    if ((unsigned long long)n + n_ghost > TAB_COL_IDX_MASK) {
+        tab_set_error("owned + ghost atoms exceed the 28-bit index space");
+        return TAB_EUNSUPPORTED;
+    }
+    nbr->n_ghost = (int)n_ghost;
+    nbr->n_ext = n + nbr->n_ghost;
+    TAB_TRY(nbr->atoms.ensure(sizeof(Atom4) * (size_t)nbr->n_ext));
+    TAB_TRY(nbr->types_ext.ensure((size_t)nbr->n_ext + 16));
+    TAB_TRY(nbr->ghost_owner.ensure(sizeof(int) * (size_t)(nbr->n_ghost + 1)));
+    TAB_TRY(nbr->ghost_S.ensure(sizeof(int) * (size_t)(nbr->n_ghost + 1)));
+
+    k_gather_owned<<<nblocks(n, 256), 256, 0, st>>>(
+        n, d_pos, d_types, g, nbr->perm.as<int>(), nbr->s0.as<int>(),
+        nbr->atoms.as<Atom4>(), nbr->types_ext.as<uint8_t>());
+    TAB_LAUNCH_CHECK();
+    if (nbr->n_ghost > 0) {
+        k_fill_ghosts<<<nblocks((long long)g.n_ecells * 32, 256), 256, 0, st>>>(
+            g, n, nbr->cell_start.as<uint32_t>(), nbr->gstart.as<uint32_t>(),
+            nbr->gcount.as<uint32_t>(), nbr->ext_start.as<uint32_t>(),
+            nbr->atoms.as<Atom4>(), nbr->types_ext.as<uint8_t>(),
+            nbr->ghost_owner.as<int>(), nbr->ghost_S.as<int>(), 0);
+        TAB_LAUNCH_CHECK();
+    }
+
+    ExactCtx x;
+    x.pos = d_pos;
+    x.perm = nbr->perm.as<int>();
+    x.s0 = nbr->s0.as<int>();
+    x.ghost_owner = nbr->ghost_owner.as<int>();
+    x.ghost_S = nbr->ghost_S.as<int>();
+    x.n_owned = n;
+    const int nthreads = nbr->n_slices * 32;
+    k_count<<<nblocks(nthreads, 128), 128, 0, st>>>(
+        n, g, x, nbr->cell_of.as<int>(), nbr->atoms.as<Atom4>(),
+        nbr->ext_start.as<uint32_t>(), nbr->ext_count.as<uint32_t>(),
+        nbr->counts.as<int>(), nbr->slice_w.as<uint32_t>(), d_stats);
+    TAB_LAUNCH_CHECK();
+    TAB_TRY(tab_scan_exclusive_u32(nbr->slice_w.as<uint32_t>(),
+                                   nbr->slice_ptr.as<uint32_t>(), nbr->n_slices,
+                                   d_stats + 2, nbr->scan_tmp, st));
+    unsigned long long h_stats[3];
+    TAB_CUDA(cudaMemcpyAsync(h_stats, d_stats, sizeof(h_stats), cudaMemcpyDeviceToHost, st));
+    TAB_CUDA(cudaStreamSynchronize(st));
+    nbr->nij = (long long)h_stats[0];
+    nbr->nnl_max = (int)h_stats[1];
+    nbr->ell_rows = (long long)h_stats[2];
+    if (nbr->ell_rows > 0xffffffffLL) {
+        tab_set_error("neighbour table too large (%lld rows)", nbr->ell_rows);
+        return TAB_EUNSUPPORTED;
+    }
+    TAB_TRY(nbr->col.ensure(sizeof(uint32_t) * 32 * (size_t)(nbr->ell_rows + 1)));
+    k_fill<<<nblocks(nthreads, 128), 128, 0, st>>>(
+        n, g, x, nbr->cell_of.as<int>(), nbr->atoms.as<Atom4>(),
+        nbr->types_ext.as<uint8_t>(), nbr->ext_start.as<uint32_t>(),
+        nbr->ext_count.as<uint32_t>(), nbr->slice_w.as<uint32_t>(),
+        nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>());
+    TAB_LAUNCH_CHECK();
+    nbr->built = true;
+    return TAB_OK;
+}
+
+extern "C" int tab_nbr_update(tab_nbr *nbr, const double *d_pos, const double *h_cell,
+                              void *stream) {
+    if (!nbr || !d_pos) return TAB_EINVAL;
+    if (!nbr->built) {
+        tab_set_error("tab_nbr_update before tab_nbr_build");
+        return TAB_ESTATE;
+    }
+    if (h_cell) {
+        double det;
+        memcpy(nbr->grid.h, h_cell, 9 * sizeof(double));
+        invert3(nbr->grid.h, nbr->grid.hinv, &det);
+    }
+    return refresh_positions(nbr, d_pos, (cudaStream_t)stream);
+}
+
+extern "C" int tab_nbr_sizes(const tab_nbr *nbr, int64_t *nij, int32_t *nnl_max,
+                             int32_t *n_ext) {
+    if (!nbr) return TAB_EINVAL;
+    if (!nbr->built) {
+        tab_set_error("tab_nbr_sizes before tab_nbr_build");
+        return TAB_ESTATE;
+    }
+    if (nij) *nij = nbr->nij;
+    if (nnl_max) *nnl_max = nbr->nnl_max;
+    if (n_ext) *n_ext = nbr->n_ext;
+    return TAB_OK;
+}
+
+extern "C" int tab_nbr_counts(const tab_nbr *nbr, int32_t *d_counts, void *stream) {
+    if (!nbr || !d_counts) return TAB_EINVAL;
+    if (!nbr->built) return TAB_ESTATE;
+    k_scatter_counts<<<nblocks(nbr->n, 256), 256, 0, (cudaStream_t)stream>>>(
+        nbr->n, nbr->perm.as<int>(), nbr->counts.as<int>(), d_counts);
+    TAB_LAUNCH_CHECK();
+    return TAB_OK;
+}
+
+extern "C" int tab_nbr_export(const tab_nbr *cnbr, int32_t *d_i, int32_t *d_j,
+                              int32_t *d_S, void *stream) {
+    tab_nbr *nbr = const_cast<tab_nbr *>(cnbr);
+    if (!nbr || !d_i || !d_j || !d_S) return TAB_EINVAL;
+    if (!nbr->built) return TAB_ESTATE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = nbr->n;
+    TAB_TRY(nbr->row_ptr.ensure(sizeof(uint32_t) * (size_t)n));
+    k_scatter_counts<<<nblocks(n, 256), 256, 0, st>>>(
+        n, nbr->perm.as<int>(), nbr->counts.as<int>(), nbr->row_ptr.as<int>());
+    TAB_LAUNCH_CHECK();
+    TAB_TRY(tab_scan_exclusive_u32(nbr->row_ptr.as<uint32_t>(),
+                                   nbr->row_ptr.as<uint32_t>(), n, nullptr,
+                                   nbr->scan_tmp, st));
+    k_export<<<nblocks(n, 128), 128, 0, st>>>(
+        n, n, nbr->perm.as<int>(), nbr->s0.as<int>(), nbr->counts.as<int>(),
+        nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>(),
+        nbr->ghost_owner.as<int>(), nbr->ghost_S.as<int>(),
+        nbr->row_ptr.as<uint32_t>(), d_i, d_j, d_S);
+    TAB_LAUNCH_CHECK();
+    return TAB_OK;
+}

@@ -1,0 +1,148 @@
+// potentials.cuh -- device restatement of the analytic potential functions of
+// the reference (tensoralloy/nn/eam/potentials/*), value AND first derivative.
+// Each evaluator cites the reference lines it follows.  `Real` is the working
+// precision of the pair arithmetic (double = 'high', float = 'medium').
+#pragma once
+#include "tab_internal.h"
+
+template <typename Real> struct Math;
+template <> struct Math<double> {
+    static __device__ __forceinline__ double exp_(double x) { return exp(x); }
+    static __device__ __forceinline__ double log_(double x) { return log(x); }
+    static __device__ __forceinline__ double pow_(double x, double y) { return pow(x, y); }
+    static __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
+    static __device__ __forceinline__ double eps() { return 1e-14; }   // precision.py:113
+};
+template <> struct Math<float> {
+    static __device__ __forceinline__ float exp_(float x) { return expf(x); }
+    static __device__ __forceinline__ float log_(float x) { return logf(x); }
+    static __device__ __forceinline__ float pow_(float x, float y) { return powf(x, y); }
+    static __device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
+    static __device__ __forceinline__ float eps() { return 1e-8f; }    // precision.py:114
+};
+
+// generic.py:102-117  f(r) = a exp(-b (r/re - 1)) / (1 + (r/re - c)^20)
+// returns f, and df/dr.  (x-c)^20 is formed by repeated squaring; the reference
+// calls pow(x-c, 20.0), the two agree to a few ulp.
+template <typename Real>
+__device__ __forceinline__ void zhou_exp(Real r, Real a, Real b, Real c, Real re,
+                                         Real &f, Real &df) {
+    const Real x = r / re;
+    const Real u = x - c;
+    const Real u2 = u * u, u4 = u2 * u2, u8 = u4 * u4, u16 = u8 * u8;
+    const Real u19 = u16 * u2 * u;
+    const Real u20 = u19 * u;
+    const Real q = Real(1) / (Real(1) + u20);
+    const Real e = a * Math<Real>::exp_(-b * (x - Real(1)));
+    f = e * q;
+    df = -f * (b + Real(20) * u19 * q) / re;
+}
+
+// zjw04.py:279-389 (piecewise) and :440-550 (xc, sigmoid blended).
+// p = Fn0..Fn3, F0..F3, eta, Fe, rho_e, rho_s
+template <typename Real>
+__device__ __forceinline__ void zhou_embed(const double *p, bool blended, Real rho,
+                                           Real &F, Real &dF) {
+    const Real Fn0 = (Real)p[0], Fn1 = (Real)p[1], Fn2 = (Real)p[2], Fn3 = (Real)p[3];
+    const Real F0 = (Real)p[4], F1 = (Real)p[5], F2 = (Real)p[6], F3 = (Real)p[7];
+    const Real eta = (Real)p[8], Fe = (Real)p[9], rho_e = (Real)p[10],
+               rho_s = (Real)p[11];
+    const Real rho_n = Real(0.85) * rho_e;   // computed in working precision, as
+    const Real rho_0 = Real(1.15) * rho_e;   // the reference does (zjw04.py:319-322)
+    auto e1 = [&](Real &y, Real &dy) {
+        const Real x = rho / rho_n - Real(1);
+        y = Fn0 + (Fn1 * x + Fn2 * x * x + Fn3 * x * x * x);
+        dy = (Fn1 + Real(2) * Fn2 * x + Real(3) * Fn3 * x * x) / rho_n;
+    };
+    auto e2 = [&](Real &y, Real &dy) {
+        const Real x = rho / rho_e - Real(1);
+        y = F0 + (F1 * x + F2 * x * x + F3 * x * x * x);
+        dy = (F1 + Real(2) * F2 * x + Real(3) * F3 * x * x) / rho_e;
+    };
+    auto e3 = [&](Real shift, Real &y, Real &dy) {
+        const Real x = rho / rho_s + shift;
+        const Real lnx = Math<Real>::log_(x);
+        const Real xe = Math<Real>::pow_(x, eta);
+        y = Fe * (Real(1) - eta * lnx) * xe;
+        // d/dx [Fe (1 - eta ln x) x^eta] = -Fe eta^2 ln(x) x^(eta-1)
+        dy = -Fe * eta * eta * lnx * xe / x / rho_s;
+    };
+    if (!blended) {
+        if (rho < rho_n) e1(F, dF);
+        else if (rho < rho_0) e2(F, dF);
+        else e3(Real(0), F, dF);
+        return;
+    }
+    Real y1, d1, y2, d2, y3, d3;
+    e1(y1, d1);
+    e2(y2, d2);
+    e3(Real(1e-8), y3, d3);
+    const Real c1 = Real(1) / (Real(1) + Math<Real>::exp_(-Real(2) * (rho_n - rho)));
+    const Real c3 = Real(1) / (Real(1) + Math<Real>::exp_(-Real(2) * (rho - rho_0)));
+    const Real c2 = Real(1) - (c1 + c3);
+    const Real dc1 = -Real(2) * c1 * (Real(1) - c1);
+    const Real dc3 = Real(2) * c3 * (Real(1) - c3);
+    const Real dc2 = -(dc1 + dc3);
+    F = c1 * y1 + c2 * y2 + c3 * y3;
+    dF = dc1 * y1 + c1 * d1 + dc2 * y2 + c2 * d2 + dc3 * y3 + c3 * d3;
+}
+
+// One table entry -> value and d/dr.  The switch is warp-uniform for
+// single-species systems and cheap next to the transcendental work otherwise.
+template <typename Real>
+__device__ __forceinline__ void eval_pair_fn(const tab_fn &fn, Real r, Real &f,
+                                             Real &df) {
+    const double *p = fn.p;
+    switch (fn.kind) {
+    case TAB_FN_ZHOU_RHO:   // zjw04.py:245-277
+        zhou_exp<Real>(r, (Real)p[0], (Real)p[1], (Real)p[2], (Real)p[3], f, df);
+        break;
+    case TAB_FN_ZHOU_PHI: { // zjw04.py:187-227
+        Real fa, dfa, fb, dfb;
+        zhou_exp<Real>(r, (Real)p[0], (Real)p[1], (Real)p[2], (Real)p[6], fa, dfa);
+        zhou_exp<Real>(r, (Real)p[3], (Real)p[4], (Real)p[5], (Real)p[6], fb, dfb);
+        f = fa - fb;
+        df = dfa - dfb;
+        break;
+    }
+    case TAB_FN_ZHOU_PHI_MIX: { // zjw04.py:229-243
+        // p[0..6] phi of a, p[7..10] rho of a, p[11..17] phi of b, p[18..21] rho of b
+        Real t0, d0, t1, d1, pa, dpa, pb, dpb, ra, dra, rb, drb;
+        zhou_exp<Real>(r, (Real)p[0], (Real)p[1], (Real)p[2], (Real)p[6], t0, d0);
+        zhou_exp<Real>(r, (Real)p[3], (Real)p[4], (Real)p[5], (Real)p[6], t1, d1);
+        pa = t0 - t1;
+        dpa = d0 - d1;
+        zhou_exp<Real>(r, (Real)p[7], (Real)p[8], (Real)p[9], (Real)p[10], ra, dra);
+        zhou_exp<Real>(r, (Real)p[11], (Real)p[12], (Real)p[13], (Real)p[17], t0, d0);
+        zhou_exp<Real>(r, (Real)p[14], (Real)p[15], (Real)p[16], (Real)p[17], t1, d1);
+        pb = t0 - t1;
+        dpb = d0 - d1;
+        zhou_exp<Real>(r, (Real)p[18], (Real)p[19], (Real)p[20], (Real)p[21], rb, drb);
+        const Real qab = ra / rb, qba = rb / ra;
+        const Real dqab = (dra - qab * drb) / rb;
+        const Real dqba = (drb - qba * dra) / ra;
+        f = Real(0.5) * (qab * pb + qba * pa);
+        df = Real(0.5) * (dqab * pb + qab * dpb + dqba * pa + qba * dpa);
+        break;
+    }
+    default:
+        f = Real(0);
+        df = Real(0);
+    }
+}
+
+template <typename Real>
+__device__ __forceinline__ void eval_embed_fn(const tab_fn &fn, Real rho, Real &F,
+                                              Real &dF) {
+    switch (fn.kind) {
+    case TAB_FN_ZHOU_EMBED:
+        zhou_embed<Real>(fn.p, false, rho, F, dF);
+        break;
+    case TAB_FN_ZHOU_EMBED_XC:
+        zhou_embed<Real>(fn.p, true, rho, F, dF);
+        break;
+    default:
+        F = Real(0);
+        dF = Real(0);
+    }
+}
