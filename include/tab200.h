@@ -150,6 +150,13 @@ int tab_eam_compute_host(tab_model *model, tab_nbr *nbr, int32_t precision,
                          int32_t rebuild, double *h_energy, double *h_eatom,
                          double *h_forces, double *h_virial, void *stream);
 
+/* Per-kernel timing of tab_eam_eval with CUDA events recorded on the launching
+ * stream (used by bench.py for the roofline figures; off by default).
+ * tab_profile_read synchronises the device; ms[0..3] = mean milliseconds of the
+ * rho pass, the F' spread, the force pass and the final reduction. */
+int tab_profile_enable(int32_t on);
+int tab_profile_read(double *ms, int32_t *calls);
+
 /* number of kernel launches the library has enqueued since load / last reset
  * (feeds bench.py's `gpu_launches`). */
 int64_t tab_launch_count(void);

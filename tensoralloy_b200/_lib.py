@@ -55,6 +55,7 @@ EXPORTS = [
     'tab_nbr_sizes', 'tab_nbr_counts', 'tab_nbr_export',
     'tab_eam_create', 'tab_model_free', 'tab_eam_eval', 'tab_eam_compute_host',
     'tab_launch_count', 'tab_launch_count_reset',
+    'tab_profile_enable', 'tab_profile_read',
 ]
 
 
@@ -91,6 +92,8 @@ def lib():
     L.tab_eam_compute_host.argtypes = [vp, vp, i32, i32, vp, vp,
                                        C.POINTER(dbl), C.POINTER(i32), dbl, i32,
                                        vp, vp, vp, vp, vp]
+    L.tab_profile_enable.argtypes = [i32]
+    L.tab_profile_read.argtypes = [C.POINTER(dbl), C.POINTER(i32)]
     L.tab_launch_count.restype = i64
     L.tab_launch_count_reset.restype = None
     for name in EXPORTS:
@@ -236,3 +239,15 @@ class EamModel:
             _ptr(h_energy), _ptr(h_eatom), _ptr(h_forces), _ptr(h_virial),
             _stream()), 'tab_eam_compute_host')
         nbr.n = n
+
+
+def profile_enable(on=True):
+    check(lib().tab_profile_enable(int(bool(on))), 'tab_profile_enable')
+
+
+def profile_read():
+    """Mean milliseconds of (rho pass, F' spread, force pass, reduction), calls."""
+    ms = (C.c_double * 4)()
+    calls = C.c_int32()
+    check(lib().tab_profile_read(ms, C.byref(calls)), 'tab_profile_read')
+    return list(ms), int(calls.value)

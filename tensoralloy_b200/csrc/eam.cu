@@ -32,28 +32,58 @@ struct tab_model {
     int kind = 0;
     int n_el = 0;
     bool zhou1 = false;    // single element, all-zjw04: shared-exponential fast path
-    double zp[8];          // fe, beta, lamda, re, A, alpha, kappa, B
+    double zp[8];          // fe, beta, lamda, 1/re, A, alpha, kappa, B
     DevBuf tables;         // tab_fn [2*n_el*n_el + n_el (+ 2*n_el*n_el)]
     tab_fn embed0;         // host copy (fast path epilogue parameters)
 };
 
 // single-element zjw04: rho and the B term of phi share one exponential
 struct Zhou1 {
-    double fe, beta, lamda, re, A, alpha, kappa, B;
+    double fe, beta, lamda, re, A, alpha, kappa, B;   // re holds 1/r_eq
 };
 
 #define EAM_T 256
 
 template <typename Real>
 __device__ __forceinline__ void pair_r(const Atom4 &me, const Atom4 &a, Real &dx,
-                                       Real &dy, Real &dz, Real &r) {
+                                       Real &dy, Real &dz, Real &r, Real &rinv) {
     // geometry always in float64 (positions are float64), then the working type
     const double ddx = a.x - me.x, ddy = a.y - me.y, ddz = a.z - me.z;
     dx = (Real)ddx;
     dy = (Real)ddy;
     dz = (Real)ddz;
-    r = Math<Real>::sqrt_(dx * dx + dy * dy + dz * dz + Math<Real>::eps());
+    // r = sqrt(D.D + eps)  (universal.py:470-473), with 1/r for the force
+    const Real r2 = fma(dx, dx, fma(dy, dy, fma(dz, dz, Math<Real>::eps())));
+    rinv = Math<Real>::rsqrt_(r2);
+    r = r2 * rinv;
 }
+
+// Software-pipelined traversal of one ELL row: the index two entries ahead and
+// the Atom4 record one entry ahead are in flight while entry k is evaluated
+// (the gather latency was the top stall of the first version, profiles/r01a).
+struct RowIter {
+    const uint32_t *cp;
+    const Atom4 *atoms;
+    int cnt, k;
+    uint32_t c_cur, c_nx, c_nx2;
+    Atom4 a_nx;
+    __device__ __forceinline__ RowIter(const uint32_t *cp_, const Atom4 *atoms_, int cnt_)
+        : cp(cp_), atoms(atoms_), cnt(cnt_), k(0) {
+        c_nx = cnt > 0 ? cp[0] : 0u;
+        c_nx2 = cnt > 1 ? cp[32] : 0u;
+        a_nx = atoms[c_nx & TAB_COL_IDX_MASK];
+    }
+    __device__ __forceinline__ bool next(Atom4 &a, uint32_t &c) {
+        if (k >= cnt) return false;
+        a = a_nx;
+        c = c_nx;
+        c_nx = c_nx2;
+        ++k;
+        if (k < cnt) a_nx = atoms[c_nx & TAB_COL_IDX_MASK];
+        if (k + 1 < cnt) c_nx2 = cp[(size_t)(k + 1) * 32u];
+        return true;
+    }
+};
 
 __device__ __forceinline__ void load_tables(tab_fn *s, const tab_fn *g, int count) {
     const int words = count * (int)(sizeof(tab_fn) / 8);
@@ -84,11 +114,12 @@ k_eam_rho(int n, const Atom4 *__restrict__ atoms,
     const int cnt = counts[idx];
     const uint32_t *cp = col + ((size_t)slice_ptr[idx >> 5] * 32u + (idx & 31));
     Real rho = Real(0);
-    for (int k = 0; k < cnt; ++k) {
-        const uint32_t c = cp[(size_t)k * 32u];
-        const Atom4 a = atoms[c & TAB_COL_IDX_MASK];
-        Real dx, dy, dz, r, f, df;
-        pair_r<Real>(me, a, dx, dy, dz, r);
+    RowIter it(cp, atoms, cnt);
+    Atom4 a;
+    uint32_t c;
+    while (it.next(a, c)) {
+        Real dx, dy, dz, r, rinv, f, df;
+        pair_r<Real>(me, a, dx, dy, dz, r, rinv);
         if (FAST) {
             zhou_exp<Real>(r, (Real)z.fe, (Real)z.beta, (Real)z.lamda, (Real)z.re, f, df);
         } else {
@@ -140,11 +171,12 @@ k_eam_force(int n, const Atom4 *__restrict__ atoms,
         const Real fpi = (Real)me.w;
         Real fx = 0, fy = 0, fz = 0, ep = 0;
         Real vxx = 0, vyy = 0, vzz = 0, vyz = 0, vxz = 0, vxy = 0;
-        for (int k = 0; k < cnt; ++k) {
-            const uint32_t c = cp[(size_t)k * 32u];
-            const Atom4 a = atoms[c & TAB_COL_IDX_MASK];
-            Real dx, dy, dz, r;
-            pair_r<Real>(me, a, dx, dy, dz, r);
+        RowIter it(cp, atoms, cnt);
+        Atom4 a;
+        uint32_t c;
+        while (it.next(a, c)) {
+            Real dx, dy, dz, r, rinv;
+            pair_r<Real>(me, a, dx, dy, dz, r, rinv);
             const Real fpj = (Real)a.w;
             Real phi, dphi, der;   // der = dE/dr of the undirected pair seen from i
             if (FAST) {
@@ -163,7 +195,7 @@ k_eam_force(int n, const Atom4 *__restrict__ atoms,
                 eval_pair_fn<Real>(tabs[nn + ti * m.n_el + tj], r, phi, dphi);
                 der = fpi * drij + fpj * drji + dphi;
             }
-            const Real s = der / r;
+            const Real s = der * rinv;
             const Real gx = s * dx, gy = s * dy, gz = s * dz;
             fx += gx;
             fy += gy;
@@ -273,6 +305,18 @@ extern "C" int tab_eam_create(tab_model **out, int32_t kind, int32_t n_el,
     memcpy(host, rho, nn * sizeof(tab_fn));
     memcpy(host + nn, phi, nn * sizeof(tab_fn));
     memcpy(host + 2 * nn, embed, n_el * sizeof(tab_fn));
+    // device representation: the r_eq slots hold 1/r_eq (potentials.cuh)
+    for (size_t k = 0; k < count; ++k) {
+        tab_fn &f = host[k];
+        if (f.kind == TAB_FN_ZHOU_RHO) f.p[3] = 1.0 / f.p[3];
+        else if (f.kind == TAB_FN_ZHOU_PHI) f.p[6] = 1.0 / f.p[6];
+        else if (f.kind == TAB_FN_ZHOU_PHI_MIX) {
+            f.p[6] = 1.0 / f.p[6];
+            f.p[10] = 1.0 / f.p[10];
+            f.p[17] = 1.0 / f.p[17];
+            f.p[21] = 1.0 / f.p[21];
+        }
+    }
     cudaError_t e = cudaMemcpy(m->tables.p, host, count * sizeof(tab_fn),
                                cudaMemcpyHostToDevice);
     delete[] host;
@@ -292,7 +336,7 @@ extern "C" int tab_eam_create(tab_model **out, int32_t kind, int32_t n_el,
         m->zp[0] = rho[0].p[0];   // f_eq
         m->zp[1] = rho[0].p[1];   // beta
         m->zp[2] = rho[0].p[2];   // lamda
-        m->zp[3] = rho[0].p[3];   // r_eq
+        m->zp[3] = 1.0 / rho[0].p[3];   // 1 / r_eq
         m->zp[4] = phi[0].p[0];   // A
         m->zp[5] = phi[0].p[1];   // alpha
         m->zp[6] = phi[0].p[2];   // kappa
@@ -306,6 +350,49 @@ extern "C" int tab_model_free(tab_model *m) {
     if (!m) return TAB_OK;
     m->tables.release();
     delete m;
+    return TAB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// optional per-kernel timing with CUDA events on the launching stream
+// (bench.py's roofline numbers); off by default.
+// ---------------------------------------------------------------------------
+#define PROF_MAX_CALLS 512
+#define PROF_MARKS 5
+static bool g_prof_on = false;
+static int g_prof_calls = 0;
+static cudaEvent_t g_prof_ev[PROF_MAX_CALLS][PROF_MARKS];
+static int g_prof_created = 0;
+
+static inline void prof_mark(int k, cudaStream_t st) {
+    if (!g_prof_on || g_prof_calls >= PROF_MAX_CALLS) return;
+    while (g_prof_created <= g_prof_calls) {
+        for (int q = 0; q < PROF_MARKS; ++q) cudaEventCreate(&g_prof_ev[g_prof_created][q]);
+        ++g_prof_created;
+    }
+    cudaEventRecord(g_prof_ev[g_prof_calls][k], st);
+}
+
+extern "C" int tab_profile_enable(int32_t on) {
+    g_prof_on = on != 0;
+    g_prof_calls = 0;
+    return TAB_OK;
+}
+
+// ms[0..3] = mean duration of k_eam_rho, k_spread_w, k_eam_force, k_reduce_partials
+extern "C" int tab_profile_read(double *ms, int32_t *calls) {
+    if (!ms || !calls) return TAB_EINVAL;
+    TAB_CUDA(cudaDeviceSynchronize());
+    for (int q = 0; q < PROF_MARKS - 1; ++q) ms[q] = 0.0;
+    for (int c = 0; c < g_prof_calls; ++c)
+        for (int q = 0; q < PROF_MARKS - 1; ++q) {
+            float t = 0.f;
+            TAB_CUDA(cudaEventElapsedTime(&t, g_prof_ev[c][q], g_prof_ev[c][q + 1]));
+            ms[q] += t;
+        }
+    if (g_prof_calls > 0)
+        for (int q = 0; q < PROF_MARKS - 1; ++q) ms[q] /= g_prof_calls;
+    *calls = g_prof_calls;
     return TAB_OK;
 }
 
@@ -329,24 +416,30 @@ static int eam_run(tab_model *m, tab_nbr *nbr, double *d_energy, double *d_eatom
     memcpy(&z, m->zp, sizeof(z));
     const size_t smem = FAST ? 0 : (size_t)(2 * nn + m->n_el) * sizeof(tab_fn);
     const Atom4 *atoms = nbr->atoms.as<Atom4>();
+    prof_mark(0, st);
     k_eam_rho<Real, FAST><<<nblk, EAM_T, smem, st>>>(
         n, atoms, nbr->types_ext.as<uint8_t>(), nbr->counts.as<int>(),
         nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>(), dev, z, m->embed0,
         fprime, fembed);
     TAB_LAUNCH_CHECK();
+    prof_mark(1, st);
     k_spread_w<<<(nbr->n_ext + 255) / 256, 256, 0, st>>>(
         n, nbr->n_ext, fprime, nbr->ghost_owner.as<int>(), nbr->atoms.as<Atom4>());
     TAB_LAUNCH_CHECK();
+    prof_mark(2, st);
     k_eam_force<Real, FAST><<<nblk, EAM_T, smem, st>>>(
         n, atoms, nbr->types_ext.as<uint8_t>(), nbr->counts.as<int>(),
         nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>(), nbr->perm.as<int>(),
         dev, z, fembed, d_eatom, d_forces, nbr->partial.as<double>());
     TAB_LAUNCH_CHECK();
+    prof_mark(3, st);
     if (d_energy || d_virial) {
         k_reduce_partials<<<1, 256, 0, st>>>(nblk, nbr->partial.as<double>(), d_energy,
                                              d_virial);
         TAB_LAUNCH_CHECK();
     }
+    prof_mark(4, st);
+    if (g_prof_on && g_prof_calls < PROF_MAX_CALLS) ++g_prof_calls;
     return TAB_OK;
 }
 

@@ -5,37 +5,90 @@
 #pragma once
 #include "tab_internal.h"
 
+// ---------------------------------------------------------------------------
+// arithmetic building blocks.  float64: MUFU seed + Newton iterations and a
+// branch-free exp (arguments here are bounded: no overflow / denormal / NaN
+// paths needed); every routine is accurate to <= 2 ulp, three orders below the
+// 1e-10 eV/atom parity tolerance.  float32: hardware approximations (the
+// 'medium' tolerance is 1e-5 relative).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double tab_rcp(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+
+// 1/sqrt(x) for normal positive x
+__device__ __forceinline__ double tab_rsqrt(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double h = 0.5 * x;
+    double e = fma(-h * y, y, 0.5);
+    y = fma(y, e, y);
+    e = fma(-h * y, y, 0.5);
+    return fma(y, e, y);
+}
+
+// exp(t) for |t| < 700: n = rint(t log2 e), f = t - n ln2, degree-12 Taylor
+// polynomial on |f| <= 0.347 (truncation 1.7e-16), exponent patched in.
+__device__ __forceinline__ double tab_exp(double t) {
+    const double SHIFT = 6755399441055744.0;   // 1.5 * 2^52
+    const double z = fma(t, 1.4426950408889634074, SHIFT);
+    const int n = __double2loint(z);
+    const double nf = z - SHIFT;
+    double f = fma(nf, -6.93147180369123816490e-01, t);
+    f = fma(nf, -1.90821492927058770002e-10, f);
+    double p = 2.08767569878680989792e-09;      // 1/12!
+    p = fma(p, f, 2.50521083854417187751e-08);  // 1/11!
+    p = fma(p, f, 2.75573192239858906526e-07);  // 1/10!
+    p = fma(p, f, 2.75573192239858906526e-06);  // 1/9!
+    p = fma(p, f, 2.48015873015873015873e-05);  // 1/8!
+    p = fma(p, f, 1.98412698412698412698e-04);  // 1/7!
+    p = fma(p, f, 1.38888888888888888889e-03);  // 1/6!
+    p = fma(p, f, 8.33333333333333333333e-03);  // 1/5!
+    p = fma(p, f, 4.16666666666666666667e-02);  // 1/4!
+    p = fma(p, f, 1.66666666666666666667e-01);  // 1/3!
+    p = fma(p, f, 0.5);
+    p = fma(p, f, 1.0);
+    p = fma(p, f, 1.0);
+    return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+}
+
 template <typename Real> struct Math;
 template <> struct Math<double> {
-    static __device__ __forceinline__ double exp_(double x) { return exp(x); }
+    static __device__ __forceinline__ double exp_(double x) { return tab_exp(x); }
     static __device__ __forceinline__ double log_(double x) { return log(x); }
     static __device__ __forceinline__ double pow_(double x, double y) { return pow(x, y); }
-    static __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
+    static __device__ __forceinline__ double rcp_(double x) { return tab_rcp(x); }
+    static __device__ __forceinline__ double rsqrt_(double x) { return tab_rsqrt(x); }
     static __device__ __forceinline__ double eps() { return 1e-14; }   // precision.py:113
 };
 template <> struct Math<float> {
-    static __device__ __forceinline__ float exp_(float x) { return expf(x); }
+    static __device__ __forceinline__ float exp_(float x) { return __expf(x); }
     static __device__ __forceinline__ float log_(float x) { return logf(x); }
     static __device__ __forceinline__ float pow_(float x, float y) { return powf(x, y); }
-    static __device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
+    static __device__ __forceinline__ float rcp_(float x) { return __frcp_rn(x); }
+    static __device__ __forceinline__ float rsqrt_(float x) { return rsqrtf(x); }
     static __device__ __forceinline__ float eps() { return 1e-8f; }    // precision.py:114
 };
 
 // generic.py:102-117  f(r) = a exp(-b (r/re - 1)) / (1 + (r/re - c)^20)
-// returns f, and df/dr.  (x-c)^20 is formed by repeated squaring; the reference
-// calls pow(x-c, 20.0), the two agree to a few ulp.
+// returns f and df/dr.  `inv_re` = 1/re.  (x-c)^20 is formed by repeated
+// squaring; the reference calls pow(x-c, 20.0); the two agree to a few ulp.
 template <typename Real>
-__device__ __forceinline__ void zhou_exp(Real r, Real a, Real b, Real c, Real re,
+__device__ __forceinline__ void zhou_exp(Real r, Real a, Real b, Real c, Real inv_re,
                                          Real &f, Real &df) {
-    const Real x = r / re;
+    const Real x = r * inv_re;
     const Real u = x - c;
     const Real u2 = u * u, u4 = u2 * u2, u8 = u4 * u4, u16 = u8 * u8;
     const Real u19 = u16 * u2 * u;
-    const Real u20 = u19 * u;
-    const Real q = Real(1) / (Real(1) + u20);
-    const Real e = a * Math<Real>::exp_(-b * (x - Real(1)));
+    const Real q = Math<Real>::rcp_(fma(u19, u, Real(1)));
+    const Real e = a * Math<Real>::exp_(fma(-b, x, b));
     f = e * q;
-    df = -f * (b + Real(20) * u19 * q) / re;
+    df = -(f * inv_re) * fma(Real(20) * u19, q, b);
 }
 
 // zjw04.py:279-389 (piecewise) and :440-550 (xc, sigmoid blended).
@@ -87,6 +140,7 @@ __device__ __forceinline__ void zhou_embed(const double *p, bool blended, Real r
     dF = dc1 * y1 + c1 * d1 + dc2 * y2 + c2 * d2 + dc3 * y3 + c3 * d3;
 }
 
+// NOTE: tab_eam_create stores 1/r_eq in the r_eq slots of the device tables.
 // One table entry -> value and d/dr.  The switch is warp-uniform for
 // single-species systems and cheap next to the transcendental work otherwise.
 template <typename Real>

@@ -1,0 +1,155 @@
+"""
+BasicNN: the model base class of the reference (tensoralloy/nn/basic.py:99-1153)
+reduced to the energy / force / virial / stress / Hessian outputs of
+`BasicNN.build` (:679-787).  TF autograd (`tf.gradients`, :281,:306,:418) is
+replaced by the analytic backward kernels of libtab200.
+"""
+from typing import List
+
+import numpy as np
+
+from tensoralloy_b200.atoms import GPa
+from tensoralloy_b200.precision import get_float_dtype
+from tensoralloy_b200.utils import Defaults, ModeKeys
+
+API_VERSION = "1.1"
+
+
+class _PropertyError(ValueError):
+    label = "valid"
+
+    def __init__(self, name):
+        super().__init__()
+        self.name = name
+
+    def __str__(self):
+        return f"'{self.name}' is not a '{self.label}' property."
+
+
+class MinimizablePropertyError(_PropertyError):
+    label = "minimizable"
+
+
+class ExportablePropertyError(_PropertyError):
+    label = "exportable"
+
+
+# basic.py:74-96
+_all_properties = (
+    ('energy', True, True), ('eentropy', True, True), ('free_energy', True, True),
+    ('atomic', False, True), ('forces', True, True), ('stress', True, True),
+    ('total_pressure', True, True), ('hessian', False, True),
+    ('elastic', True, True), ('rose', True, False), ('eentropy/c', True, False),
+    ('hessian/c', True, False), ('extra/c', True, False))
+minimizable_properties = [n for n, m, e in _all_properties if m]
+exportable_properties = [n for n, m, e in _all_properties if e]
+
+VOIGT = ((0, 0), (1, 1), (2, 2), (1, 2), (0, 2), (0, 1))   # basic.py:341-343
+
+
+class BasicNN:
+    default_collection = None
+    scope = "Basic"
+
+    def __init__(self, elements: List[str], hidden_sizes=None, activation=None,
+                 minimize_properties=('energy', 'forces'),
+                 export_properties=('energy', 'forces')):
+        self._elements = sorted(list(elements))
+        self._hidden_sizes = self._get_hidden_sizes(
+            hidden_sizes if hidden_sizes is not None else Defaults.hidden_sizes)
+        self._activation = activation or Defaults.activation
+        if len(minimize_properties) == 0:
+            raise ValueError("At least one property should be minimized.")
+        for prop in minimize_properties:
+            if prop not in minimizable_properties:
+                raise MinimizablePropertyError(prop)
+        for prop in export_properties:
+            if prop not in exportable_properties:
+                raise ExportablePropertyError(prop)
+        self._minimize_properties = list(minimize_properties)
+        self._export_properties = list(export_properties)
+        self._transformer = None
+
+    elements = property(lambda self: self._elements)
+    hidden_sizes = property(lambda self: self._hidden_sizes)
+    minimize_properties = property(lambda self: self._minimize_properties)
+    predict_properties = property(lambda self: self._export_properties)
+    transformer = property(lambda self: self._transformer)
+
+    @property
+    def is_finite_temperature(self) -> bool:
+        return False
+
+    @property
+    def variational_energy(self) -> str:
+        return "free_energy" if self.is_finite_temperature else "energy"
+
+    def _get_hidden_sizes(self, hidden_sizes):
+        results = {}
+        for element in self._elements:
+            if isinstance(hidden_sizes, dict):
+                sizes = np.asarray(hidden_sizes.get(element, Defaults.hidden_sizes),
+                                   dtype=int)
+            else:
+                sizes = np.atleast_1d(hidden_sizes).astype(int)
+            assert (sizes > 0).all()
+            results[element] = sizes.tolist()
+        return results
+
+    def attach_transformer(self, clf):
+        self._transformer = clf
+
+    def as_dict(self):
+        raise NotImplementedError("This method must be overridden!")
+
+    # ------------------------------------------------------------------
+    # evaluation
+    # ------------------------------------------------------------------
+    def _evaluate(self, features, want_forces, want_virial, want_atomic):
+        """Subclass hook: run the kernels.  Returns a dict with float64 numpy
+        arrays in LOCAL (caller) atom order: energy (), energy/atom [N],
+        forces [N,3], virial [3,3]."""
+        raise NotImplementedError
+
+    def build(self, features, mode=ModeKeys.PREDICT, verbose=False):
+        """basic.py:679-787.  `features` = transformer.get_constant_features(atoms)
+        (the device-side lists).  Returns the reference's prediction dict as
+        numpy arrays in the working precision; per-atom arrays are in GSL order
+        without the virtual atom, exactly like the TF outputs."""
+        if self._transformer is None:
+            raise ValueError("A descriptor transformer must be attached.")
+        if mode in (ModeKeys.PREDICT, ModeKeys.LAMMPS, ModeKeys.KMC,
+                    ModeKeys.PRECOMPUTE, ModeKeys.NATIVE):
+            properties = self._export_properties
+        else:
+            properties = self._minimize_properties
+        want_stress = 'stress' in properties or 'total_pressure' in properties \
+            or 'elastic' in properties
+        want_forces = 'forces' in properties or want_stress
+        raw = self._evaluate(features, want_forces, want_stress, True)
+        return self._finalize(raw, features, properties)
+
+    def _finalize(self, raw, features, properties):
+        dtype = get_float_dtype().as_numpy_dtype
+        vap = features.vap
+        to_gsl = (lambda a: a) if vap.is_identity else \
+            (lambda a: vap.map_array(a.reshape(len(a), -1), reverse=False)[1:].reshape(
+                (vap.max_vap_natoms - 1,) + a.shape[1:]))
+        pred = {'energy': dtype(raw['energy'])}
+        if 'energy/atom' in raw:
+            pred['energy/atom'] = to_gsl(raw['energy/atom']).astype(dtype)
+        if 'forces' in raw:
+            pred['forces'] = to_gsl(raw['forces']).astype(dtype)
+        if 'virial' in raw and ('stress' in properties or
+                                'total_pressure' in properties or
+                                'elastic' in properties):
+            virial = raw['virial']
+            stress = virial / features.volume                 # basic.py:317
+            voigt = np.array([stress[a, b] for a, b in VOIGT])
+            pred['virial'] = virial.astype(dtype)
+            pred['stress'] = voigt.astype(dtype)
+            # basic.py:393-408: -trace/3 in GPa
+            pred['total_pressure'] = dtype(np.trace(stress) / (-3.0 * GPa))
+        if 'hessian' in raw:
+            pred['hessian'] = raw['hessian'].astype(dtype)
+        return pred

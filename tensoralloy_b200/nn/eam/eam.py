@@ -1,0 +1,144 @@
+"""
+EamNN: base of the EAM-family models.  Mirror of the reference's
+tensoralloy/nn/eam/eam.py:80-570 (constructor signature :88-94, `as_dict`
+:137-147, potential bookkeeping :149-260); `_get_model_outputs` (:495-570) is
+executed by csrc/eam.cu instead of a TF graph.
+"""
+from typing import List
+
+import numpy as np
+
+from tensoralloy_b200 import _lib
+from tensoralloy_b200.nn.basic import BasicNN
+from tensoralloy_b200.nn.eam.potentials import available_potentials
+from tensoralloy_b200.precision import get_float_dtype
+from tensoralloy_b200.utils import (Defaults, get_elements_from_kbody_term,
+                                    get_kbody_terms)
+
+
+class EamNN(BasicNN):
+    scope = "EAM"
+    tag = None
+    kind = _lib.EAM_ALLOY
+
+    def __init__(self, elements: List[str], custom_potentials=None,
+                 hidden_sizes=None, fixed_functions=None,
+                 minimize_properties=('energy', 'forces'),
+                 export_properties=('energy', 'forces', 'stress')):
+        self._fixed_functions = fixed_functions or []
+        self._unique_kbody_terms = None
+        self._kbody_terms = None
+        super().__init__(elements=elements, hidden_sizes=hidden_sizes,
+                         minimize_properties=minimize_properties,
+                         export_properties=export_properties)
+        self._potentials = self._setup_potentials(custom_potentials)
+        self._empirical_functions = {
+            key: cls() for key, cls in available_potentials.items()}
+        self._model = None
+        self._out = None
+        assert self._kbody_terms and self._unique_kbody_terms
+
+    unique_kbody_terms = property(lambda self: self._unique_kbody_terms)
+    potentials = property(lambda self: self._potentials)
+
+    def as_dict(self):
+        return {"class": self.__class__.__name__,
+                "elements": self._elements,
+                "custom_potentials": self._potentials,
+                "hidden_sizes": self._hidden_sizes,
+                "fixed_functions": self._fixed_functions,
+                "minimize_properties": self._minimize_properties,
+                "export_properties": self._export_properties}
+
+    @staticmethod
+    def _check_fn_avail(name: str):
+        name = name.lower()
+        return name == "nn" or name in available_potentials
+
+    def _setup_kbody_terms(self):
+        kbody_terms = get_kbody_terms(self._elements, angular=False)[1]
+        unique = []
+        for element in self._elements:
+            for term in kbody_terms[element]:
+                a, b = get_elements_from_kbody_term(term)
+                if a == b:
+                    unique.append(term)
+                else:
+                    ab = "".join(sorted([a, b]))
+                    if ab not in unique:
+                        unique.append(ab)
+        self._unique_kbody_terms = unique
+        self._kbody_terms = kbody_terms
+
+    # -- variables ---------------------------------------------------------
+    def get_variable(self, name):
+        """Value of `EAM/Shared/<section>/<param>` (potentials.py:171-200)."""
+        scope, shared, section, key = name.split('/')
+        for fn in self._empirical_functions.values():
+            if section in fn.params and key in fn.params[section]:
+                return fn.params[section][key]
+        raise KeyError(name)
+
+    def set_variable(self, name, value, potential=None):
+        """Set one shared variable (e.g. a Const node of a frozen .pb).  Shared
+        variables are keyed by section/param only (potentials.py:171-200), so
+        the value is applied to every registered potential unless one is named."""
+        parts = name.split('/')
+        section, key = parts[-2], parts[-1]
+        for pname, fn in self._empirical_functions.items():
+            if potential is None or pname == potential:
+                if section in fn.params or potential is not None:
+                    fn.set_param(section, key, value)
+        self._model = None
+
+    # -- device model --------------------------------------------------------
+    def _rho_entry(self, centre, other):
+        raise NotImplementedError
+
+    def _fn_of(self, section, key):
+        name = self._potentials[section][key]
+        if name == 'nn':
+            raise NotImplementedError(
+                "'nn' (MLP-parametrised) EAM functions are not available in "
+                "libtab200 yet")
+        return self._empirical_functions[name]
+
+    def _device_model(self):
+        if self._model is not None:
+            return self._model
+        els = self._elements
+        rho = [self._rho_entry(a, b) for a in els for b in els]
+        phi = []
+        for a in els:
+            for b in els:
+                key = "".join(sorted([a, b])) if a != b else f"{a}{a}"
+                phi.append(self._fn_of(key, 'phi').phi(key))
+        embed = [self._fn_of(a, 'embed').embed(a) for a in els]
+        self._model = _lib.EamModel(self.kind, len(els), rho, phi, embed)
+        return self._model
+
+    def _evaluate(self, features, want_forces, want_virial, want_atomic):
+        import torch
+        model = self._device_model()
+        n = features.n_atoms
+        if self._out is None or self._out['n'] != n:
+            dev = 'cuda'
+            self._out = {
+                'n': n,
+                'scal': torch.zeros(16, dtype=torch.float64, device=dev),
+                'eatom': torch.zeros(n, dtype=torch.float64, device=dev),
+                'forces': torch.zeros((n, 3), dtype=torch.float64, device=dev)}
+        o = self._out
+        model.eval(features.nbr, get_float_dtype().tab_precision,
+                   energy=o['scal'][0:1], eatom=o['eatom'] if want_atomic else None,
+                   forces=o['forces'] if want_forces else None,
+                   virial=o['scal'][1:10] if want_virial else None)
+        scal = o['scal'].cpu().numpy()
+        raw = {'energy': scal[0]}
+        if want_atomic:
+            raw['energy/atom'] = o['eatom'].cpu().numpy()
+        if want_forces:
+            raw['forces'] = o['forces'].cpu().numpy()
+        if want_virial:
+            raw['virial'] = scal[1:10].reshape(3, 3).copy()
+        return raw

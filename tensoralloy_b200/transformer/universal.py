@@ -1,0 +1,254 @@
+"""
+UniversalTransformer: the descriptor interface of the reference
+(tensoralloy/transformer/universal.py:236-918, base.py:27-587) on top of the GPU
+neighbour lists of libtab200.
+
+What changed under the hood:
+  * `ase.neighborlist.neighbor_list` + the Python index-map loops
+    (universal.py:46-233) -> one GPU cell-list build (csrc/nbr.cu);
+  * the dense padded g[4, T, Nvap, nnl_max] tensors (universal.py:583-620) are
+    never materialised: models consume the lists directly.
+What is kept: constructor signature, `as_dict`, k-body term bookkeeping, VAP
+handling, and -- for callers that want the reference wire format --
+`get_np_feed_dict`, which rebuilds the reference's arrays (`g2.v2g_map`,
+`g2.ilist`, ...) from the GPU list.
+"""
+from collections import Counter
+from typing import Dict, List
+
+import numpy as np
+
+from tensoralloy_b200 import _lib
+from tensoralloy_b200.atoms import chemical_symbols
+from tensoralloy_b200.precision import get_float_dtype
+from tensoralloy_b200.transformer.vap import VirtualAtomMap
+from tensoralloy_b200.utils import (get_elements_from_kbody_term,
+                                    get_kbody_terms)
+
+
+class DeviceFeatures:
+    """What crosses host -> device for one structure: the replacement of the
+    reference's feed dict (universal.py:728-785)."""
+
+    def __init__(self, atoms, vap, types, nbr, d_pos, cell, volume, pbc):
+        self.atoms = atoms
+        self.vap = vap
+        self.types = types          # int32 [N] host, index into sorted elements
+        self.nbr = nbr              # _lib.NeighborList (built)
+        self.d_pos = d_pos          # cuda float64 [N,3]
+        self.cell = cell            # float64 [3,3] host
+        self.volume = volume
+        self.pbc = pbc
+        self.n_atoms = len(types)
+
+
+class UniversalTransformer:
+    """See module docstring.  Signature: universal.py:243-244."""
+
+    def __init__(self, elements: List[str], rcut, acut=None, angular=False,
+                 periodic=True, symmetric=True, use_computed_dists=True):
+        for element in elements:
+            if element not in chemical_symbols:
+                raise ValueError(f"{element} is not a valid chemical symbol!")
+        if angular and acut is None:
+            acut = rcut
+        all_kbody_terms, kbody_terms_for_element, elements = get_kbody_terms(
+            elements, angular=angular, symmetric=symmetric)
+        self._all_kbody_terms = all_kbody_terms
+        self._kbody_terms_for_element = kbody_terms_for_element
+        self._max_nr_terms = max(
+            len([x for x in kbody_terms_for_element[e]
+                 if len(get_elements_from_kbody_term(x)) == 2]) for e in elements)
+        self._max_na_terms = max(
+            len([x for x in kbody_terms_for_element[e]
+                 if len(get_elements_from_kbody_term(x)) == 3]) for e in elements)
+        self._rcut = rcut
+        self._acut = acut
+        self._elements = elements
+        self._n_elements = len(elements)
+        self._periodic = periodic
+        self._angular = angular
+        self._symmetric = symmetric
+        self._use_computed_dists = use_computed_dists
+        self._vap_transformers: Dict[str, VirtualAtomMap] = {}
+        self._nbr = None
+        self._types_cache = (None, None)
+
+    # -- reference properties (universal.py:323-445) -----------------------
+    def as_dict(self) -> Dict:
+        return {'class': self.__class__.__name__, 'elements': self._elements,
+                'rcut': self._rcut, 'acut': self._acut,
+                'angular': self._angular, 'periodic': self._periodic,
+                'symmetric': self._symmetric,
+                'use_computed_dists': self._use_computed_dists}
+
+    descriptor = property(lambda self: "universal")
+    rc = property(lambda self: self._rcut)
+    rcut = property(lambda self: self._rcut)
+    acut = property(lambda self: self._acut)
+    elements = property(lambda self: self._elements)
+    n_elements = property(lambda self: self._n_elements)
+    periodic = property(lambda self: self._periodic)
+    angular = property(lambda self: self._angular)
+    symmetric = property(lambda self: self._symmetric)
+    use_computed_dists = property(lambda self: self._use_computed_dists)
+    all_kbody_terms = property(lambda self: self._all_kbody_terms)
+    kbody_terms_for_element = property(lambda self: self._kbody_terms_for_element)
+    max_nr_terms = property(lambda self: self._max_nr_terms)
+    max_na_terms = property(lambda self: self._max_na_terms)
+
+    # -- VAP (base.py:199-226) ----------------------------------------------
+    def get_vap_transformer(self, atoms) -> VirtualAtomMap:
+        types = self.get_types(atoms)
+        # same cache key semantics as get_chemical_formula(mode='reduce'):
+        # the run-length encoding of the symbol sequence
+        change = np.flatnonzero(np.diff(types)) + 1
+        starts = np.concatenate(([0], change))
+        lengths = np.diff(np.concatenate((starts, [len(types)])))
+        key = (tuple(types[starts].tolist()), tuple(lengths.tolist()))
+        if key not in self._vap_transformers:
+            symbols = atoms.get_chemical_symbols()
+            counter = Counter(symbols)
+            max_occurs = Counter()
+            for element in self._elements:
+                max_occurs[element] = max(1, counter[element])
+            self._vap_transformers[key] = VirtualAtomMap(max_occurs, symbols)
+        return self._vap_transformers[key]
+
+    def get_types(self, atoms) -> np.ndarray:
+        """Element index (into the sorted element list) of every atom."""
+        cached_atoms, cached = self._types_cache
+        if cached_atoms is atoms and cached is not None and len(cached) == len(atoms):
+            return cached
+        symbols = np.asarray(atoms.get_chemical_symbols())
+        els = np.asarray(self._elements)
+        idx = np.searchsorted(els, symbols)
+        idx = np.clip(idx, 0, len(els) - 1)
+        if not np.array_equal(els[idx], symbols):
+            bad = sorted(set(symbols[els[idx] != symbols].tolist()))
+            raise ValueError(f"elements {bad} are not supported by this transformer")
+        types = idx.astype(np.int32)
+        self._types_cache = (atoms, types)
+        return types
+
+    # -- device path ----------------------------------------------------------
+    def _cell_and_pbc(self, atoms):
+        cell = np.asarray(atoms.get_cell(complete=True), dtype=np.float64).reshape(3, 3)
+        pbc = np.asarray(atoms.get_pbc(), dtype=bool).reshape(3)
+        if not self._periodic:
+            pbc = np.zeros(3, dtype=bool)
+        if abs(np.linalg.det(cell)) < 1e-12 or not pbc.all():
+            cell, shift = _bounding_cell(np.asarray(atoms.positions), cell, pbc,
+                                         self._rcut)
+        return cell, pbc
+
+    def get_device_features(self, atoms, rc=None) -> DeviceFeatures:
+        """Build the GPU neighbour lists of `atoms` (replaces get_feed_dict)."""
+        import torch
+        if self._nbr is None:
+            self._nbr = _lib.NeighborList()
+        types = self.get_types(atoms)
+        cell, pbc = self._cell_and_pbc(atoms)
+        d_pos = torch.as_tensor(np.ascontiguousarray(atoms.positions, dtype=np.float64)
+                                ).to('cuda', non_blocking=True)
+        d_types = torch.as_tensor(types).to('cuda', non_blocking=True)
+        self._nbr.build(d_pos, d_types, cell, pbc, rc or self._rcut)
+        real_cell = np.asarray(atoms.get_cell(complete=True), dtype=np.float64)
+        return DeviceFeatures(atoms, self.get_vap_transformer(atoms), types,
+                              self._nbr, d_pos, real_cell.reshape(3, 3),
+                              float(atoms.get_volume()), pbc)
+
+    # -- reference wire format (universal.py:46-112,851-893) -------------------
+    def get_np_feed_dict(self, atoms):
+        """The reference's PREDICT-mode feed dict, rebuilt from the GPU list."""
+        import torch
+        np_dtype = get_float_dtype().as_numpy_dtype
+        feats = self.get_device_features(atoms)
+        vap = feats.vap
+        i, j, S = feats.nbr.export()
+        torch.cuda.synchronize()
+        i = i.cpu().numpy().astype(np.int64)
+        j = j.cpu().numpy().astype(np.int64)
+        S = S.cpu().numpy()
+        types = feats.types
+        n_el = self._n_elements
+        # index of the k-body term inside kbody_terms_for_element[centre]
+        ti, tj = types[i], types[j]
+        tlist = np.where(ti == tj, 0, tj - (tj > ti).astype(np.int64) + 1
+                         ).astype(np.int32) if n_el > 1 else np.zeros(len(i), np.int32)
+        l2g = vap.local_to_gsl_array
+        ilist = l2g[i + 1].astype(np.int32)
+        jlist = l2g[j + 1].astype(np.int32)
+        nij = len(i)
+        # slot counter per (centre, term) in list order (universal.py:90-101)
+        key = i * self._max_nr_terms + tlist
+        order = np.argsort(key, kind='stable')
+        ks = key[order]
+        first = np.concatenate(([True], ks[1:] != ks[:-1])) if nij else np.zeros(0, bool)
+        start = np.maximum.accumulate(np.where(first, np.arange(nij), 0))
+        inc = np.empty(nij, dtype=np.int32)
+        inc[order] = (np.arange(nij) - start).astype(np.int32)
+        v2g = np.zeros((nij, 5), dtype=np.int32)
+        v2g[:, 0] = tlist
+        v2g[:, 1] = ilist
+        v2g[:, 2] = inc
+        v2g[:, 4] = 1
+        positions = vap.map_positions(np.asarray(atoms.positions))
+        feed = dict()
+        if self._use_computed_dists:
+            feed["positions"] = positions.astype(np_dtype)
+            feed["cell"] = feats.cell.astype(np_dtype)
+            feed["volume"] = np_dtype(feats.volume)
+        feed["n_atoms_vap"] = np.int32(vap.max_vap_natoms)
+        feed["nnl_max"] = np.int32(inc.max() + 1 if nij else 0)
+        feed["atom_masks"] = vap.atom_masks.astype(np_dtype)
+        feed["etemperature"] = np_dtype(atoms.info.get('etemperature', 0.0))
+        feed["row_splits"] = np.int32([1] + [vap.max_occurs[e] for e in self._elements])
+        feed["g2.v2g_map"] = v2g
+        if self._use_computed_dists:
+            feed["g2.ilist"] = ilist
+            feed["g2.jlist"] = jlist
+            feed["g2.n1"] = S.astype(np_dtype)
+        else:
+            D = (np.asarray(atoms.positions)[j] - np.asarray(atoms.positions)[i]
+                 + S.astype(np.float64) @ feats.cell)
+            d = np.sqrt((D * D).sum(axis=1))
+            feed["g2.rij"] = np.concatenate((d[:, None], D), axis=1).T.astype(np_dtype)
+        return feed
+
+    def get_feed_dict(self, atoms):
+        """Kept for API compatibility: there are no TF placeholders here, the
+        numpy feed dict is returned keyed by name."""
+        return self.get_np_feed_dict(atoms)
+
+    def get_constant_features(self, atoms):
+        """universal.py:910-918: in this build the 'features' handed to
+        `BasicNN.build` are the device-side lists."""
+        return self.get_device_features(atoms)
+
+
+def _bounding_cell(positions, cell, pbc, rc):
+    """For non-periodic directions (or a missing cell) use an orthogonal-to-the-
+    -rest bounding extent so that the cell list has a frame to bin in.  Only the
+    binning frame changes; S stays 0 along non-periodic directions."""
+    cell = np.array(cell, dtype=np.float64)
+    out = cell.copy()
+    pos = np.asarray(positions, dtype=np.float64)
+    if not pbc.any():
+        lo = pos.min(axis=0) - 1.0
+        hi = pos.max(axis=0) + 1.0
+        ext = np.maximum(hi - lo, 2.0 * rc + 2.0)
+        # the library bins with scaled = pos @ inv(cell); an origin shift is not
+        # needed because non-periodic bins are clipped to the box edges
+        return np.diag(ext + np.abs(lo) + np.abs(hi)), lo
+    for k in range(3):
+        if not pbc[k] and not np.any(cell[k]):
+            others = [cell[m] for m in range(3) if m != k and np.any(cell[m])]
+            if len(others) == 2:
+                v = np.cross(others[0], others[1])
+            else:
+                v = np.eye(3)[k]
+            v = v / np.linalg.norm(v)
+            span = np.ptp(pos @ v) + 2.0 * rc + 2.0
+            out[k] = v * max(span, 1.0)
+    return out, np.zeros(3)
