@@ -70,6 +70,19 @@ int tab_nbr_build(tab_nbr *nbr, int32_t n, const double *d_pos,
                   const int32_t *d_types, const double *h_cell,
                   const int32_t *h_pbc, double rc, void *stream);
 
+/* Domain-decomposed build (one rank of a spatial decomposition).  d_pos / d_types
+ * hold n_owned owned atoms followed by n_halo HALO atoms received from other
+ * ranks, already shifted into this rank's frame (so that D = pos[j] - pos[i]).
+ * h_cell spans the local binning frame whose corner is h_origin (NULL = 0);
+ * decomposed directions must be non-periodic in h_pbc (their images arrive as
+ * halo atoms), the others get periodic images as usual.  Neighbour rows are built
+ * for the owned atoms only; indices >= n_owned in exports refer to halo atoms.
+ * The reference has no spatial decomposition. */
+int tab_nbr_build_dd(tab_nbr *nbr, int32_t n_owned, int32_t n_halo,
+                     const double *d_pos, const int32_t *d_types,
+                     const double *h_cell, const double *h_origin,
+                     const int32_t *h_pbc, double rc, void *stream);
+
 /* Keep the lists, refresh the positions (and optionally the cell): the MD step
  * between two rebuilds.  h_cell may be NULL (unchanged). */
 int tab_nbr_update(tab_nbr *nbr, const double *d_pos, const double *h_cell,
@@ -139,6 +152,19 @@ int tab_model_free(tab_model *model);
 int tab_eam_eval(tab_model *model, tab_nbr *nbr, int32_t precision,
                  double *d_energy, double *d_eatom, double *d_forces,
                  double *d_virial, void *stream);
+
+/* The same evaluation split at the point where a spatial decomposition must
+ * exchange F'(rho) of boundary atoms:
+ *   pass1: rho_i, F(rho_i), F'(rho_i) of the owned atoms;
+ *          d_fprime [n_owned] (caller order) receives F' (may be NULL)
+ *   pass2: d_fprime_halo [n_halo] = F' of the halo atoms in caller order (NULL
+ *          when there are none); then forces / energy / virial of the owned
+ *          atoms.  Energy and virial are this rank's partial sums. */
+int tab_eam_pass1(tab_model *model, tab_nbr *nbr, int32_t precision,
+                  double *d_fprime, void *stream);
+int tab_eam_pass2(tab_model *model, tab_nbr *nbr, int32_t precision,
+                  const double *d_fprime_halo, double *d_energy, double *d_eatom,
+                  double *d_forces, double *d_virial, void *stream);
 
 /* Host-buffer convenience: H2D of positions (+types), neighbour build, eval,
  * D2H of the results -- the whole of TensorAlloyCalculator.calculate

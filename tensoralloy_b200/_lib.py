@@ -51,9 +51,11 @@ _lib = None
 # every symbol include/tab200.h declares (tests check the .so exports them all)
 EXPORTS = [
     'tab_version', 'tab_last_error',
-    'tab_nbr_create', 'tab_nbr_free', 'tab_nbr_build', 'tab_nbr_update',
+    'tab_nbr_create', 'tab_nbr_free', 'tab_nbr_build', 'tab_nbr_build_dd',
+    'tab_nbr_update',
     'tab_nbr_sizes', 'tab_nbr_counts', 'tab_nbr_export',
-    'tab_eam_create', 'tab_model_free', 'tab_eam_eval', 'tab_eam_compute_host',
+    'tab_eam_create', 'tab_model_free', 'tab_eam_eval', 'tab_eam_pass1',
+    'tab_eam_pass2', 'tab_eam_compute_host',
     'tab_launch_count', 'tab_launch_count_reset',
     'tab_profile_enable', 'tab_profile_read',
 ]
@@ -79,6 +81,8 @@ def lib():
     L.tab_nbr_free.argtypes = [vp]
     L.tab_nbr_build.argtypes = [vp, i32, vp, vp, C.POINTER(dbl), C.POINTER(i32),
                                 dbl, vp]
+    L.tab_nbr_build_dd.argtypes = [vp, i32, i32, vp, vp, C.POINTER(dbl),
+                                   C.POINTER(dbl), C.POINTER(i32), dbl, vp]
     L.tab_nbr_update.argtypes = [vp, vp, C.POINTER(dbl), vp]
     L.tab_nbr_sizes.argtypes = [vp, C.POINTER(i64), C.POINTER(i32),
                                 C.POINTER(i32)]
@@ -89,6 +93,8 @@ def lib():
                                  C.POINTER(TabFn), C.POINTER(TabFn)]
     L.tab_model_free.argtypes = [vp]
     L.tab_eam_eval.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]
+    L.tab_eam_pass1.argtypes = [vp, vp, i32, vp, vp]
+    L.tab_eam_pass2.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, vp]
     L.tab_eam_compute_host.argtypes = [vp, vp, i32, i32, vp, vp,
                                        C.POINTER(dbl), C.POINTER(i32), dbl, i32,
                                        vp, vp, vp, vp, vp]
@@ -163,6 +169,17 @@ class NeighborList:
                                   _cell9(cell), _pbc3(pbc), float(rc), _stream()),
               'tab_nbr_build')
 
+    def build_dd(self, d_pos, d_types, n_owned, cell, origin, pbc, rc):
+        """Domain-decomposed build: d_pos = owned atoms then halo atoms."""
+        import torch
+        assert d_pos.is_cuda and d_pos.dtype == torch.float64 and d_pos.is_contiguous()
+        n_loc = int(d_pos.shape[0])
+        self.n = int(n_owned)
+        org = (C.c_double * 3)(*[float(x) for x in origin])
+        check(lib().tab_nbr_build_dd(self._h, self.n, n_loc - self.n, _ptr(d_pos),
+                                     _ptr(d_types), _cell9(cell), org, _pbc3(pbc),
+                                     float(rc), _stream()), 'tab_nbr_build_dd')
+
     def update(self, d_pos, cell=None):
         c = _cell9(cell) if cell is not None else None
         check(lib().tab_nbr_update(self._h, _ptr(d_pos), c, _stream()),
@@ -228,6 +245,17 @@ class EamModel:
         check(lib().tab_eam_eval(self._h, nbr.handle, int(precision), _ptr(energy),
                                  _ptr(eatom), _ptr(forces), _ptr(virial),
                                  _stream()), 'tab_eam_eval')
+
+    def pass1(self, nbr, precision, fprime=None):
+        check(lib().tab_eam_pass1(self._h, nbr.handle, int(precision), _ptr(fprime),
+                                  _stream()), 'tab_eam_pass1')
+
+    def pass2(self, nbr, precision, fprime_halo=None, energy=None, eatom=None,
+              forces=None, virial=None):
+        check(lib().tab_eam_pass2(self._h, nbr.handle, int(precision),
+                                  _ptr(fprime_halo), _ptr(energy), _ptr(eatom),
+                                  _ptr(forces), _ptr(virial), _stream()),
+              'tab_eam_pass2')
 
     def compute_host(self, nbr, precision, h_pos, h_types, cell, pbc, rc, rebuild,
                      h_energy, h_eatom, h_forces, h_virial):

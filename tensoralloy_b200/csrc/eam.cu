@@ -101,8 +101,9 @@ __global__ void __launch_bounds__(EAM_T)
 k_eam_rho(int n, const Atom4 *__restrict__ atoms,
           const uint8_t *__restrict__ types_ext, const int *__restrict__ counts,
           const uint32_t *__restrict__ slice_ptr, const uint32_t *__restrict__ col,
-          EamDev m, Zhou1 z, tab_fn embed0, double *__restrict__ fprime,
-          double *__restrict__ fembed) {
+          const int *__restrict__ perm, EamDev m, Zhou1 z, tab_fn embed0,
+          double *__restrict__ fprime, double *__restrict__ fembed,
+          double *__restrict__ fprime_caller) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     tab_fn *tabs = reinterpret_cast<tab_fn *>(smem_raw);
     const int nn = m.n_el * m.n_el;
@@ -133,16 +134,22 @@ k_eam_rho(int n, const Atom4 *__restrict__ atoms,
     else eval_embed_fn<Real>(tabs[2 * nn + ti], rho, F, dF);
     fprime[idx] = (double)dF;
     fembed[idx] = (double)F;
+    if (fprime_caller) fprime_caller[perm[idx]] = (double)dF;
 }
 
-// Atom4.w <- F'(rho) for every extended atom (ghosts read their owner)
-__global__ void k_spread_w(int n_owned, int n_ext, const double *__restrict__ v,
+// Atom4.w <- F'(rho) for every extended atom: owned atoms from pass 1, halo
+// atoms from the values received from their owner ranks (caller order), periodic
+// images from their source atom.
+__global__ void k_spread_w(int n_owned, int n_loc, int n_ext,
+                           const double *__restrict__ v,
+                           const double *__restrict__ halo_v,
+                           const int *__restrict__ perm,
                            const int *__restrict__ ghost_owner,
                            Atom4 *__restrict__ atoms) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_ext) return;
-    const int o = e < n_owned ? e : ghost_owner[e - n_owned];
-    atoms[e].w = v[o];
+    const int o = e < n_loc ? e : ghost_owner[e - n_loc];
+    atoms[e].w = o < n_owned ? v[o] : halo_v[perm[o] - n_owned];
 }
 
 // ---------------------------------------------------------------------------
@@ -396,45 +403,72 @@ extern "C" int tab_profile_read(double *ms, int32_t *calls) {
     return TAB_OK;
 }
 
-template <typename Real, bool FAST>
-static int eam_run(tab_model *m, tab_nbr *nbr, double *d_energy, double *d_eatom,
-                   double *d_forces, double *d_virial, cudaStream_t st) {
-    const int n = nbr->n;
-    const int nblk = (n + EAM_T - 1) / EAM_T;
-    TAB_TRY(nbr->rho.ensure(sizeof(double) * 2 * (size_t)n));
-    TAB_TRY(nbr->partial.ensure(sizeof(double) * 8 * (size_t)nblk));
-    double *fprime = nbr->rho.as<double>();
-    double *fembed = fprime + n;
+struct EamLaunch {
     EamDev dev;
-    dev.kind = m->kind;
-    dev.n_el = m->n_el;
-    const int nn = m->n_el * m->n_el;
-    dev.rho = m->tables.as<tab_fn>();
-    dev.phi = dev.rho + nn;
-    dev.embed = dev.rho + 2 * nn;
     Zhou1 z;
-    memcpy(&z, m->zp, sizeof(z));
-    const size_t smem = FAST ? 0 : (size_t)(2 * nn + m->n_el) * sizeof(tab_fn);
-    const Atom4 *atoms = nbr->atoms.as<Atom4>();
+    size_t smem;
+    int nblk;
+    double *fprime, *fembed;
+};
+
+static int eam_prepare(tab_model *m, tab_nbr *nbr, bool fast, EamLaunch &L) {
+    const int n = nbr->n;
+    L.nblk = (n + EAM_T - 1) / EAM_T;
+    TAB_TRY(nbr->rho.ensure(sizeof(double) * 2 * (size_t)n));
+    TAB_TRY(nbr->partial.ensure(sizeof(double) * 8 * (size_t)L.nblk));
+    L.fprime = nbr->rho.as<double>();
+    L.fembed = L.fprime + n;
+    L.dev.kind = m->kind;
+    L.dev.n_el = m->n_el;
+    const int nn = m->n_el * m->n_el;
+    L.dev.rho = m->tables.as<tab_fn>();
+    L.dev.phi = L.dev.rho + nn;
+    L.dev.embed = L.dev.rho + 2 * nn;
+    memcpy(&L.z, m->zp, sizeof(L.z));
+    L.smem = fast ? 0 : (size_t)(2 * nn + m->n_el) * sizeof(tab_fn);
+    return TAB_OK;
+}
+
+template <typename Real, bool FAST>
+static int eam_pass1(tab_model *m, tab_nbr *nbr, double *d_fprime_caller,
+                     cudaStream_t st) {
+    EamLaunch L;
+    TAB_TRY(eam_prepare(m, nbr, FAST, L));
     prof_mark(0, st);
-    k_eam_rho<Real, FAST><<<nblk, EAM_T, smem, st>>>(
-        n, atoms, nbr->types_ext.as<uint8_t>(), nbr->counts.as<int>(),
-        nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>(), dev, z, m->embed0,
-        fprime, fembed);
+    k_eam_rho<Real, FAST><<<L.nblk, EAM_T, L.smem, st>>>(
+        nbr->n, nbr->atoms.as<Atom4>(), nbr->types_ext.as<uint8_t>(),
+        nbr->counts.as<int>(), nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>(),
+        nbr->perm.as<int>(), L.dev, L.z, m->embed0, L.fprime, L.fembed,
+        d_fprime_caller);
     TAB_LAUNCH_CHECK();
     prof_mark(1, st);
+    return TAB_OK;
+}
+
+template <typename Real, bool FAST>
+static int eam_pass2(tab_model *m, tab_nbr *nbr, const double *d_fprime_halo,
+                     double *d_energy, double *d_eatom, double *d_forces,
+                     double *d_virial, cudaStream_t st) {
+    EamLaunch L;
+    TAB_TRY(eam_prepare(m, nbr, FAST, L));
+    if (nbr->n_halo > 0 && !d_fprime_halo) {
+        tab_set_error("tab_eam_pass2: halo atoms present but no halo F' given");
+        return TAB_EINVAL;
+    }
     k_spread_w<<<(nbr->n_ext + 255) / 256, 256, 0, st>>>(
-        n, nbr->n_ext, fprime, nbr->ghost_owner.as<int>(), nbr->atoms.as<Atom4>());
+        nbr->n, nbr->n_loc, nbr->n_ext, L.fprime, d_fprime_halo, nbr->perm.as<int>(),
+        nbr->ghost_owner.as<int>(), nbr->atoms.as<Atom4>());
     TAB_LAUNCH_CHECK();
     prof_mark(2, st);
-    k_eam_force<Real, FAST><<<nblk, EAM_T, smem, st>>>(
-        n, atoms, nbr->types_ext.as<uint8_t>(), nbr->counts.as<int>(),
-        nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>(), nbr->perm.as<int>(),
-        dev, z, fembed, d_eatom, d_forces, nbr->partial.as<double>());
+    k_eam_force<Real, FAST><<<L.nblk, EAM_T, L.smem, st>>>(
+        nbr->n, nbr->atoms.as<Atom4>(), nbr->types_ext.as<uint8_t>(),
+        nbr->counts.as<int>(), nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>(),
+        nbr->perm.as<int>(), L.dev, L.z, L.fembed, d_eatom, d_forces,
+        nbr->partial.as<double>());
     TAB_LAUNCH_CHECK();
     prof_mark(3, st);
     if (d_energy || d_virial) {
-        k_reduce_partials<<<1, 256, 0, st>>>(nblk, nbr->partial.as<double>(), d_energy,
+        k_reduce_partials<<<1, 256, 0, st>>>(L.nblk, nbr->partial.as<double>(), d_energy,
                                              d_virial);
         TAB_LAUNCH_CHECK();
     }
@@ -443,27 +477,55 @@ static int eam_run(tab_model *m, tab_nbr *nbr, double *d_energy, double *d_eatom
     return TAB_OK;
 }
 
-extern "C" int tab_eam_eval(tab_model *m, tab_nbr *nbr, int32_t precision,
-                            double *d_energy, double *d_eatom, double *d_forces,
-                            double *d_virial, void *stream) {
+#define EAM_DISPATCH(FN, ...)                                                        \
+    do {                                                                             \
+        if (precision == TAB_PRECISION_HIGH)                                         \
+            return m->zhou1 ? FN<double, true>(__VA_ARGS__) : FN<double, false>(__VA_ARGS__); \
+        if (precision == TAB_PRECISION_MEDIUM)                                       \
+            return m->zhou1 ? FN<float, true>(__VA_ARGS__) : FN<float, false>(__VA_ARGS__);   \
+        tab_set_error("unknown precision %d", precision);                            \
+        return TAB_EINVAL;                                                           \
+    } while (0)
+
+static int check_handles(tab_model *m, tab_nbr *nbr, const char *who) {
     if (!m || !nbr) {
-        tab_set_error("tab_eam_eval: null handle");
+        tab_set_error("%s: null handle", who);
         return TAB_EINVAL;
     }
     if (!nbr->built) {
-        tab_set_error("tab_eam_eval before tab_nbr_build");
+        tab_set_error("%s before tab_nbr_build", who);
         return TAB_ESTATE;
     }
+    return TAB_OK;
+}
+
+extern "C" int tab_eam_pass1(tab_model *m, tab_nbr *nbr, int32_t precision,
+                             double *d_fprime, void *stream) {
+    TAB_TRY(check_handles(m, nbr, "tab_eam_pass1"));
     cudaStream_t st = (cudaStream_t)stream;
-    if (precision == TAB_PRECISION_HIGH) {
-        return m->zhou1 ? eam_run<double, true>(m, nbr, d_energy, d_eatom, d_forces, d_virial, st)
-                        : eam_run<double, false>(m, nbr, d_energy, d_eatom, d_forces, d_virial, st);
-    } else if (precision == TAB_PRECISION_MEDIUM) {
-        return m->zhou1 ? eam_run<float, true>(m, nbr, d_energy, d_eatom, d_forces, d_virial, st)
-                        : eam_run<float, false>(m, nbr, d_energy, d_eatom, d_forces, d_virial, st);
+    EAM_DISPATCH(eam_pass1, m, nbr, d_fprime, st);
+}
+
+extern "C" int tab_eam_pass2(tab_model *m, tab_nbr *nbr, int32_t precision,
+                             const double *d_fprime_halo, double *d_energy,
+                             double *d_eatom, double *d_forces, double *d_virial,
+                             void *stream) {
+    TAB_TRY(check_handles(m, nbr, "tab_eam_pass2"));
+    cudaStream_t st = (cudaStream_t)stream;
+    EAM_DISPATCH(eam_pass2, m, nbr, d_fprime_halo, d_energy, d_eatom, d_forces, d_virial, st);
+}
+
+extern "C" int tab_eam_eval(tab_model *m, tab_nbr *nbr, int32_t precision,
+                            double *d_energy, double *d_eatom, double *d_forces,
+                            double *d_virial, void *stream) {
+    TAB_TRY(check_handles(m, nbr, "tab_eam_eval"));
+    if (nbr->n_halo > 0) {
+        tab_set_error("tab_eam_eval: lists hold halo atoms; use tab_eam_pass1/pass2");
+        return TAB_ESTATE;
     }
-    tab_set_error("tab_eam_eval: unknown precision %d", precision);
-    return TAB_EINVAL;
+    TAB_TRY(tab_eam_pass1(m, nbr, precision, nullptr, stream));
+    return tab_eam_pass2(m, nbr, precision, nullptr, d_energy, d_eatom, d_forces,
+                         d_virial, stream);
 }
 
 // Host-buffer convenience: see include/tab200.h.

@@ -19,6 +19,12 @@
 //                  col[(slice_ptr[s] + k) * 32 + l]  (coalesced for thread-per-atom
 //                  consumers; no per-pair shift vectors: ghosts carry them)
 //
+// Domain decomposition: the caller may append HALO atoms (received from other
+// ranks, already shifted into this rank's frame) after its owned atoms.  Owned and
+// halo atoms form two cell-sorted groups ([0,n) and [n,n_loc) of the extended
+// array); neighbour rows exist for owned atoms only; periodic images are generated
+// for both groups.
+//
 // Membership is ASE's: D = pos[j] - pos[i] + S.cell, sqrt(D.D) < rc in float64.
 // The fast test uses the pre-shifted ghost records; candidates whose d^2 is
 // within 1e-9 relative of rc^2 are re-decided with exactly ASE's expression on
@@ -60,12 +66,13 @@ __host__ __device__ inline int floordiv(int a, int b) {
 // ---------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------
-__global__ void k_bin(int n, const double *__restrict__ pos, Grid g,
+__global__ void k_bin(int n, int n_owned, const double *__restrict__ pos, Grid g,
                       int *__restrict__ cell_of, int *__restrict__ s0,
                       uint32_t *__restrict__ cell_count) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const double x = pos[3 * i], y = pos[3 * i + 1], z = pos[3 * i + 2];
+    const double x = pos[3 * i] - g.origin[0], y = pos[3 * i + 1] - g.origin[1],
+                 z = pos[3 * i + 2] - g.origin[2];
     int c[3], sh[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -80,10 +87,11 @@ __global__ void k_bin(int n, const double *__restrict__ pos, Grid g,
         }
         c[k] = b;
     }
-    const int rank = owned_rank(g, c[0], c[1], c[2]);
-    cell_of[i] = rank;
+    // slot = group * n_slots + rank: owned atoms sort before halo atoms
+    const int slot = owned_rank(g, c[0], c[1], c[2]) + (i >= n_owned ? g.n_slots : 0);
+    cell_of[i] = slot;
     s0[i] = tab_pack_shift(sh[0], sh[1], sh[2]);
-    atomicAdd(&cell_count[rank], 1u);
+    atomicAdd(&cell_count[slot], 1u);
 }
 
 __global__ void k_scatter(int n, const int *__restrict__ cell_of,
@@ -143,12 +151,12 @@ __global__ void k_gather_owned(int n, const double *__restrict__ pos,
     if (types_ext) types_ext[idx] = types ? (uint8_t)types[i] : (uint8_t)0;
 }
 
-// one thread per extended cell: interior cells point at the owned range, ghost
-// cells get the count of their source cell.
+// one thread per extended cell.  Table entry = {start_a, count_a, start_b,
+// count_b}: interior cells -> owned range + halo range; ghost cells get the total
+// count of their source cell (their start is filled in by k_fill_ghosts).
 __global__ void k_ext_cells(Grid g, const uint32_t *__restrict__ cell_start,
                             const uint32_t *__restrict__ cell_count,
-                            uint32_t *__restrict__ ext_start,
-                            uint32_t *__restrict__ ext_count,
+                            uint4 *__restrict__ ext_tab,
                             uint32_t *__restrict__ gcount) {
     const int lin = blockIdx.x * blockDim.x + threadIdx.x;
     if (lin >= g.n_ecells) return;
@@ -167,22 +175,24 @@ __global__ void k_ext_cells(Grid g, const uint32_t *__restrict__ cell_start,
         }
     }
     const int rank = owned_rank(g, c[0], c[1], c[2]);
-    const uint32_t cnt = cell_count[rank];
-    ext_count[lin] = cnt;
+    const uint32_t ca = cell_count[rank], cb = cell_count[g.n_slots + rank];
     if (ghost) {
-        gcount[lin] = cnt;
+        gcount[lin] = ca + cb;
+        ext_tab[lin] = make_uint4(0u, ca + cb, 0u, 0u);
     } else {
         gcount[lin] = 0;
-        ext_start[lin] = cell_start[rank];
+        ext_tab[lin] = make_uint4(cell_start[rank], ca, cell_start[g.n_slots + rank], cb);
     }
 }
 
-// one warp per extended cell; ghosts only.
-__global__ void k_fill_ghosts(Grid g, int n_owned,
+// one warp per extended cell; ghosts only.  Ghost records of a cell = images of
+// the owned atoms of the source cell followed by images of its halo atoms.
+__global__ void k_fill_ghosts(Grid g, int n_loc,
                               const uint32_t *__restrict__ cell_start,
+                              const uint32_t *__restrict__ cell_count,
                               const uint32_t *__restrict__ gstart,
                               const uint32_t *__restrict__ gcount,
-                              uint32_t *__restrict__ ext_start,
+                              uint4 *__restrict__ ext_tab,
                               Atom4 *__restrict__ atoms,
                               uint8_t *__restrict__ types_ext,
                               int *__restrict__ ghost_owner,
@@ -208,23 +218,26 @@ __global__ void k_fill_ghosts(Grid g, int n_owned,
         }
     }
     if (!ghost) return;
-    const uint32_t src = cell_start[owned_rank(g, c[0], c[1], c[2])];
-    const uint32_t dst = (uint32_t)n_owned + gstart[lin];
-    if (lane == 0 && !refresh_only) ext_start[lin] = dst;
+    const int rank = owned_rank(g, c[0], c[1], c[2]);
+    const uint32_t src_a = cell_start[rank], cnt_a = cell_count[rank];
+    const uint32_t src_b = cell_start[g.n_slots + rank];
+    const uint32_t dst = (uint32_t)n_loc + gstart[lin];
+    if (lane == 0 && !refresh_only) ext_tab[lin] = make_uint4(dst, cnt, 0u, 0u);
     const double sx = S[0] * g.h[0] + S[1] * g.h[3] + S[2] * g.h[6];
     const double sy = S[0] * g.h[1] + S[1] * g.h[4] + S[2] * g.h[7];
     const double sz = S[0] * g.h[2] + S[1] * g.h[5] + S[2] * g.h[8];
     const int packed = tab_pack_shift(S[0], S[1], S[2]);
     for (uint32_t k = lane; k < cnt; k += 32) {
-        Atom4 a = atoms[src + k];
+        const uint32_t src = k < cnt_a ? src_a + k : src_b + (k - cnt_a);
+        Atom4 a = atoms[src];
         a.x += sx;
         a.y += sy;
         a.z += sz;
         atoms[dst + k] = a;
         if (!refresh_only) {
-            types_ext[dst + k] = types_ext[src + k];
-            ghost_owner[dst + k - n_owned] = (int)(src + k);
-            ghost_S[dst + k - n_owned] = packed;
+            types_ext[dst + k] = types_ext[src];
+            ghost_owner[dst + k - n_loc] = (int)src;
+            ghost_S[dst + k - n_loc] = packed;
         }
     }
 }
@@ -235,7 +248,7 @@ struct ExactCtx {
     const int *s0;           // caller order
     const int *ghost_owner;
     const int *ghost_S;
-    int n_owned;
+    int n_loc;               // owned + halo: first library-generated image
 };
 
 // ASE's membership expression on the caller's positions (no FMA contraction).
@@ -243,9 +256,9 @@ __device__ __noinline__ bool exact_inside(const Grid &g, const ExactCtx &x, int 
                                           int j) {
     const int oi = x.perm[i];
     int owner = j, Sa = 0, Sb = 0, Sc = 0;
-    if (j >= x.n_owned) {
-        owner = x.ghost_owner[j - x.n_owned];
-        tab_unpack_shift(x.ghost_S[j - x.n_owned], Sa, Sb, Sc);
+    if (j >= x.n_loc) {
+        owner = x.ghost_owner[j - x.n_loc];
+        tab_unpack_shift(x.ghost_S[j - x.n_loc], Sa, Sb, Sc);
     }
     const int oj = x.perm[owner];
     int ia, ib, ic, ja, jb, jc;
@@ -271,8 +284,7 @@ __device__ __noinline__ bool exact_inside(const Grid &g, const ExactCtx &x, int 
 template <typename F>
 __device__ __forceinline__ void for_each_neighbor(
     const Grid &g, const ExactCtx &x, int idx, int rank,
-    const Atom4 *__restrict__ atoms, const uint32_t *__restrict__ ext_start,
-    const uint32_t *__restrict__ ext_count, F &&f) {
+    const Atom4 *__restrict__ atoms, const uint4 *__restrict__ ext_tab, F &&f) {
     int cx, cy, cz;
     owned_unrank(g, rank, cx, cy, cz);
     const Atom4 me = atoms[idx];
@@ -288,17 +300,22 @@ __device__ __forceinline__ void for_each_neighbor(
                 if (!g.pbc[0] && (ex < 0 || ex >= g.nb[0])) continue;
                 const int lin = ((ez + g.g[2]) * g.ne[1] + (ey + g.g[1])) * g.ne[0] +
                                 (ex + g.g[0]);
-                const uint32_t start = ext_start[lin];
-                const uint32_t cnt = ext_count[lin];
-                for (uint32_t k = 0; k < cnt; ++k) {
-                    const int j = (int)(start + k);
-                    if (j == idx) continue;
-                    const Atom4 a = atoms[j];
-                    const double ddx = a.x - me.x, ddy = a.y - me.y, ddz = a.z - me.z;
-                    const double d2 = ddx * ddx + ddy * ddy + ddz * ddz;
-                    bool in = d2 < g.rc2;
-                    if (fabs(d2 - g.rc2) <= tol) in = exact_inside(g, x, idx, j);
-                    if (in) f(j);
+                const uint4 t = ext_tab[lin];
+#pragma unroll
+                for (int part = 0; part < 2; ++part) {
+                    const uint32_t start = part ? t.z : t.x;
+                    const uint32_t cnt = part ? t.w : t.y;
+                    for (uint32_t k = 0; k < cnt; ++k) {
+                        const int j = (int)(start + k);
+                        if (j == idx) continue;
+                        const Atom4 a = atoms[j];
+                        const double ddx = a.x - me.x, ddy = a.y - me.y,
+                                     ddz = a.z - me.z;
+                        const double d2 = ddx * ddx + ddy * ddy + ddz * ddz;
+                        bool in = d2 < g.rc2;
+                        if (fabs(d2 - g.rc2) <= tol) in = exact_inside(g, x, idx, j);
+                        if (in) f(j);
+                    }
                 }
             }
         }
@@ -307,15 +324,14 @@ __device__ __forceinline__ void for_each_neighbor(
 
 __global__ void __launch_bounds__(128)
 k_count(int n, Grid g, ExactCtx x, const int *__restrict__ cell_of,
-        const Atom4 *__restrict__ atoms, const uint32_t *__restrict__ ext_start,
-        const uint32_t *__restrict__ ext_count, int *__restrict__ counts,
+        const Atom4 *__restrict__ atoms, const uint4 *__restrict__ ext_tab,
+        int *__restrict__ counts,
         uint32_t *__restrict__ slice_w, unsigned long long *__restrict__ stats) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     int cnt = 0;
     if (idx < n) {
         const int rank = cell_of[x.perm[idx]];
-        for_each_neighbor(g, x, idx, rank, atoms, ext_start, ext_count,
-                          [&](int) { ++cnt; });
+        for_each_neighbor(g, x, idx, rank, atoms, ext_tab, [&](int) { ++cnt; });
         counts[idx] = cnt;
     }
     // slice width = warp max, nij = sum, nnl_max = max
@@ -335,8 +351,7 @@ k_count(int n, Grid g, ExactCtx x, const int *__restrict__ cell_of,
 __global__ void __launch_bounds__(128)
 k_fill(int n, Grid g, ExactCtx x, const int *__restrict__ cell_of,
        const Atom4 *__restrict__ atoms, const uint8_t *__restrict__ types_ext,
-       const uint32_t *__restrict__ ext_start,
-       const uint32_t *__restrict__ ext_count,
+       const uint4 *__restrict__ ext_tab,
        const uint32_t *__restrict__ slice_w,
        const uint32_t *__restrict__ slice_ptr, uint32_t *__restrict__ col) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -346,7 +361,7 @@ k_fill(int n, Grid g, ExactCtx x, const int *__restrict__ cell_of,
     uint32_t k = 0;
     if (idx < n) {
         const int rank = cell_of[x.perm[idx]];
-        for_each_neighbor(g, x, idx, rank, atoms, ext_start, ext_count, [&](int j) {
+        for_each_neighbor(g, x, idx, rank, atoms, ext_tab, [&](int j) {
             base[(size_t)k * 32u] =
                 (uint32_t)j | ((uint32_t)types_ext[j] << TAB_COL_TYPE_SHIFT);
             ++k;
@@ -363,7 +378,7 @@ __global__ void k_scatter_counts(int n, const int *__restrict__ perm,
     if (idx < n) out[perm[idx]] = counts[idx];
 }
 
-__global__ void k_export(int n, int n_owned, const int *__restrict__ perm,
+__global__ void k_export(int n, int n_loc, const int *__restrict__ perm,
                          const int *__restrict__ s0,
                          const int *__restrict__ counts,
                          const uint32_t *__restrict__ slice_ptr,
@@ -384,9 +399,9 @@ __global__ void k_export(int n, int n_owned, const int *__restrict__ perm,
     for (int k = 0; k < cnt; ++k, ++o) {
         const int j = (int)(base[(size_t)k * 32u] & TAB_COL_IDX_MASK);
         int owner = j, Sa = 0, Sb = 0, Sc = 0;
-        if (j >= n_owned) {
-            owner = ghost_owner[j - n_owned];
-            tab_unpack_shift(ghost_S[j - n_owned], Sa, Sb, Sc);
+        if (j >= n_loc) {
+            owner = ghost_owner[j - n_loc];
+            tab_unpack_shift(ghost_S[j - n_loc], Sa, Sb, Sc);
         }
         const int oj = perm[owner];
         int ja, jb, jc;
@@ -418,9 +433,10 @@ static void invert3(const double *h, double *inv, double *det_out) {
     *det_out = det;
 }
 
-static int setup_grid(Grid &g, int n, const double *h_cell, const int *h_pbc,
-                      double rc) {
+static int setup_grid(Grid &g, int n, const double *h_cell, const double *h_origin,
+                      const int *h_pbc, double rc) {
     memcpy(g.h, h_cell, 9 * sizeof(double));
+    for (int k = 0; k < 3; ++k) g.origin[k] = h_origin ? h_origin[k] : 0.0;
     double det;
     invert3(g.h, g.hinv, &det);
     if (!(fabs(det) > 1e-12)) {
@@ -471,7 +487,7 @@ static int setup_grid(Grid &g, int n, const double *h_cell, const int *h_pbc,
             return TAB_EUNSUPPORTED;
         }
     }
-    if (ecells > 0x3fffffffLL || slots > 0x3fffffffLL) {
+    if (ecells > 0x3fffffffLL || slots > 0x1fffffffLL) {
         tab_set_error("cell table too large");
         return TAB_EUNSUPPORTED;
     }
@@ -491,7 +507,7 @@ extern "C" int tab_nbr_free(tab_nbr *nbr) {
     DevBuf *bufs[] = {&nbr->cell_of, &nbr->s0, &nbr->types_in, &nbr->perm, &nbr->counts,
                       &nbr->atoms, &nbr->types_ext, &nbr->ghost_owner, &nbr->ghost_S,
                       &nbr->cell_count, &nbr->cell_start, &nbr->cell_fill,
-                      &nbr->ext_start, &nbr->ext_count, &nbr->gcount, &nbr->gstart,
+                      &nbr->ext_tab, &nbr->gcount, &nbr->gstart,
                       &nbr->slice_w, &nbr->slice_ptr, &nbr->col, &nbr->scan_tmp,
                       &nbr->stats, &nbr->row_ptr, &nbr->rho, &nbr->partial, &nbr->adp};
     for (DevBuf *b : bufs) b->release();
@@ -502,50 +518,55 @@ extern "C" int tab_nbr_free(tab_nbr *nbr) {
 static inline int nblocks(long long n, int t) { return (int)((n + t - 1) / t); }
 
 static int refresh_positions(tab_nbr *nbr, const double *d_pos, cudaStream_t st) {
-    const int n = nbr->n;
     const Grid &g = nbr->grid;
-    k_gather_owned<<<nblocks(n, 256), 256, 0, st>>>(
-        n, d_pos, nullptr, g, nbr->perm.as<int>(), nbr->s0.as<int>(),
+    k_gather_owned<<<nblocks(nbr->n_loc, 256), 256, 0, st>>>(
+        nbr->n_loc, d_pos, nullptr, g, nbr->perm.as<int>(), nbr->s0.as<int>(),
         nbr->atoms.as<Atom4>(), nullptr);
     TAB_LAUNCH_CHECK();
     if (nbr->n_ghost > 0) {
         k_fill_ghosts<<<nblocks((long long)g.n_ecells * 32, 256), 256, 0, st>>>(
-            g, n, nbr->cell_start.as<uint32_t>(), nbr->gstart.as<uint32_t>(),
-            nbr->gcount.as<uint32_t>(), nbr->ext_start.as<uint32_t>(),
-            nbr->atoms.as<Atom4>(), nbr->types_ext.as<uint8_t>(),
-            nbr->ghost_owner.as<int>(), nbr->ghost_S.as<int>(), 1);
+            g, nbr->n_loc, nbr->cell_start.as<uint32_t>(), nbr->cell_count.as<uint32_t>(),
+            nbr->gstart.as<uint32_t>(), nbr->gcount.as<uint32_t>(),
+            nbr->ext_tab.as<uint4>(), nbr->atoms.as<Atom4>(),
+            nbr->types_ext.as<uint8_t>(), nbr->ghost_owner.as<int>(),
+            nbr->ghost_S.as<int>(), 1);
         TAB_LAUNCH_CHECK();
     }
     return TAB_OK;
 }
 
-extern "C" int tab_nbr_build(tab_nbr *nbr, int32_t n, const double *d_pos,
-                             const int32_t *d_types, const double *h_cell,
-                             const int32_t *h_pbc, double rc, void *stream) {
-    if (!nbr || n <= 0 || !d_pos || !h_cell || !h_pbc || !(rc > 0)) {
+extern "C" int tab_nbr_build_dd(tab_nbr *nbr, int32_t n_owned, int32_t n_halo,
+                                const double *d_pos, const int32_t *d_types,
+                                const double *h_cell, const double *h_origin,
+                                const int32_t *h_pbc, double rc, void *stream) {
+    if (!nbr || n_owned <= 0 || n_halo < 0 || !d_pos || !h_cell || !h_pbc || !(rc > 0)) {
         tab_set_error("tab_nbr_build: bad argument");
         return TAB_EINVAL;
     }
-    if ((unsigned)n > TAB_COL_IDX_MASK / 2) {
-        tab_set_error("tab_nbr_build: too many atoms for one device (%d)", n);
+    const long long n_loc_ll = (long long)n_owned + n_halo;
+    if (n_loc_ll > (long long)(TAB_COL_IDX_MASK / 2)) {
+        tab_set_error("tab_nbr_build: too many atoms for one device (%lld)", n_loc_ll);
         return TAB_EUNSUPPORTED;
     }
     cudaStream_t st = (cudaStream_t)stream;
     nbr->built = false;
     Grid &g = nbr->grid;
-    TAB_TRY(setup_grid(g, n, h_cell, h_pbc, rc));
+    const int n = n_owned, n_loc = (int)n_loc_ll;
+    TAB_TRY(setup_grid(g, n_loc, h_cell, h_origin, h_pbc, rc));
     nbr->n = n;
+    nbr->n_halo = n_halo;
+    nbr->n_loc = n_loc;
     nbr->n_slices = (n + 31) / 32;
+    const int slots2 = 2 * g.n_slots;
 
-    TAB_TRY(nbr->cell_of.ensure(sizeof(int) * n));
-    TAB_TRY(nbr->s0.ensure(sizeof(int) * n));
-    TAB_TRY(nbr->perm.ensure(sizeof(int) * n));
+    TAB_TRY(nbr->cell_of.ensure(sizeof(int) * n_loc));
+    TAB_TRY(nbr->s0.ensure(sizeof(int) * n_loc));
+    TAB_TRY(nbr->perm.ensure(sizeof(int) * n_loc));
     TAB_TRY(nbr->counts.ensure(sizeof(int) * n));
-    TAB_TRY(nbr->cell_count.ensure(sizeof(uint32_t) * g.n_slots));
-    TAB_TRY(nbr->cell_start.ensure(sizeof(uint32_t) * g.n_slots));
-    TAB_TRY(nbr->cell_fill.ensure(sizeof(uint32_t) * g.n_slots));
-    TAB_TRY(nbr->ext_start.ensure(sizeof(uint32_t) * g.n_ecells));
-    TAB_TRY(nbr->ext_count.ensure(sizeof(uint32_t) * g.n_ecells));
+    TAB_TRY(nbr->cell_count.ensure(sizeof(uint32_t) * slots2));
+    TAB_TRY(nbr->cell_start.ensure(sizeof(uint32_t) * slots2));
+    TAB_TRY(nbr->cell_fill.ensure(sizeof(uint32_t) * slots2));
+    TAB_TRY(nbr->ext_tab.ensure(sizeof(uint4) * g.n_ecells));
     TAB_TRY(nbr->gcount.ensure(sizeof(uint32_t) * g.n_ecells));
     TAB_TRY(nbr->gstart.ensure(sizeof(uint32_t) * g.n_ecells));
     TAB_TRY(nbr->slice_w.ensure(sizeof(uint32_t) * nbr->n_slices));
@@ -553,32 +574,31 @@ extern "C" int tab_nbr_build(tab_nbr *nbr, int32_t n, const double *d_pos,
     TAB_TRY(nbr->stats.ensure(4 * sizeof(unsigned long long)));
     unsigned long long *d_stats = nbr->stats.as<unsigned long long>();
 
-    TAB_CUDA(cudaMemsetAsync(nbr->cell_count.p, 0, sizeof(uint32_t) * g.n_slots, st));
-    TAB_CUDA(cudaMemsetAsync(nbr->cell_fill.p, 0, sizeof(uint32_t) * g.n_slots, st));
+    TAB_CUDA(cudaMemsetAsync(nbr->cell_count.p, 0, sizeof(uint32_t) * slots2, st));
+    TAB_CUDA(cudaMemsetAsync(nbr->cell_fill.p, 0, sizeof(uint32_t) * slots2, st));
     TAB_CUDA(cudaMemsetAsync(d_stats, 0, 4 * sizeof(unsigned long long), st));
 
-    k_bin<<<nblocks(n, 256), 256, 0, st>>>(n, d_pos, g, nbr->cell_of.as<int>(),
-                                           nbr->s0.as<int>(),
-                                           nbr->cell_count.as<uint32_t>());
+    k_bin<<<nblocks(n_loc, 256), 256, 0, st>>>(n_loc, n, d_pos, g, nbr->cell_of.as<int>(),
+                                               nbr->s0.as<int>(),
+                                               nbr->cell_count.as<uint32_t>());
     TAB_LAUNCH_CHECK();
     TAB_TRY(tab_scan_exclusive_u32(nbr->cell_count.as<uint32_t>(),
-                                   nbr->cell_start.as<uint32_t>(), g.n_slots, nullptr,
+                                   nbr->cell_start.as<uint32_t>(), slots2, nullptr,
                                    nbr->scan_tmp, st));
-    k_scatter<<<nblocks(n, 256), 256, 0, st>>>(n, nbr->cell_of.as<int>(),
-                                               nbr->cell_start.as<uint32_t>(),
-                                               nbr->cell_fill.as<uint32_t>(),
-                                               nbr->perm.as<int>());
+    k_scatter<<<nblocks(n_loc, 256), 256, 0, st>>>(n_loc, nbr->cell_of.as<int>(),
+                                                   nbr->cell_start.as<uint32_t>(),
+                                                   nbr->cell_fill.as<uint32_t>(),
+                                                   nbr->perm.as<int>());
     TAB_LAUNCH_CHECK();
-    k_sort_cells<<<nblocks(g.n_slots, 128), 128, 0, st>>>(
-        g.n_slots, nbr->cell_start.as<uint32_t>(), nbr->cell_count.as<uint32_t>(),
+    k_sort_cells<<<nblocks(slots2, 128), 128, 0, st>>>(
+        slots2, nbr->cell_start.as<uint32_t>(), nbr->cell_count.as<uint32_t>(),
         nbr->perm.as<int>());
     TAB_LAUNCH_CHECK();
 
     // ghost bookkeeping -> n_ghost (one small read-back)
     k_ext_cells<<<nblocks(g.n_ecells, 256), 256, 0, st>>>(
         g, nbr->cell_start.as<uint32_t>(), nbr->cell_count.as<uint32_t>(),
-        nbr->ext_start.as<uint32_t>(), nbr->ext_count.as<uint32_t>(),
-        nbr->gcount.as<uint32_t>());
+        nbr->ext_tab.as<uint4>(), nbr->gcount.as<uint32_t>());
     TAB_LAUNCH_CHECK();
     TAB_TRY(tab_scan_exclusive_u32(nbr->gcount.as<uint32_t>(),
                                    nbr->gstart.as<uint32_t>(), g.n_ecells, d_stats + 2,
@@ -587,27 +607,28 @@ extern "C" int tab_nbr_build(tab_nbr *nbr, int32_t n, const double *d_pos,
     TAB_CUDA(cudaMemcpyAsync(&n_ghost, d_stats + 2, sizeof(n_ghost),
                              cudaMemcpyDeviceToHost, st));
     TAB_CUDA(cudaStreamSynchronize(st));
-    if ((unsigned long long)n + n_ghost > TAB_COL_IDX_MASK) {
+    if ((unsigned long long)n_loc + n_ghost > TAB_COL_IDX_MASK) {
         tab_set_error("owned + ghost atoms exceed the 28-bit index space");
         return TAB_EUNSUPPORTED;
     }
     nbr->n_ghost = (int)n_ghost;
-    nbr->n_ext = n + nbr->n_ghost;
+    nbr->n_ext = n_loc + nbr->n_ghost;
     TAB_TRY(nbr->atoms.ensure(sizeof(Atom4) * (size_t)nbr->n_ext));
     TAB_TRY(nbr->types_ext.ensure((size_t)nbr->n_ext + 16));
     TAB_TRY(nbr->ghost_owner.ensure(sizeof(int) * (size_t)(nbr->n_ghost + 1)));
     TAB_TRY(nbr->ghost_S.ensure(sizeof(int) * (size_t)(nbr->n_ghost + 1)));
 
-    k_gather_owned<<<nblocks(n, 256), 256, 0, st>>>(
-        n, d_pos, d_types, g, nbr->perm.as<int>(), nbr->s0.as<int>(),
+    k_gather_owned<<<nblocks(n_loc, 256), 256, 0, st>>>(
+        n_loc, d_pos, d_types, g, nbr->perm.as<int>(), nbr->s0.as<int>(),
         nbr->atoms.as<Atom4>(), nbr->types_ext.as<uint8_t>());
     TAB_LAUNCH_CHECK();
     if (nbr->n_ghost > 0) {
         k_fill_ghosts<<<nblocks((long long)g.n_ecells * 32, 256), 256, 0, st>>>(
-            g, n, nbr->cell_start.as<uint32_t>(), nbr->gstart.as<uint32_t>(),
-            nbr->gcount.as<uint32_t>(), nbr->ext_start.as<uint32_t>(),
-            nbr->atoms.as<Atom4>(), nbr->types_ext.as<uint8_t>(),
-            nbr->ghost_owner.as<int>(), nbr->ghost_S.as<int>(), 0);
+            g, n_loc, nbr->cell_start.as<uint32_t>(), nbr->cell_count.as<uint32_t>(),
+            nbr->gstart.as<uint32_t>(), nbr->gcount.as<uint32_t>(),
+            nbr->ext_tab.as<uint4>(), nbr->atoms.as<Atom4>(),
+            nbr->types_ext.as<uint8_t>(), nbr->ghost_owner.as<int>(),
+            nbr->ghost_S.as<int>(), 0);
         TAB_LAUNCH_CHECK();
     }
 
@@ -617,12 +638,12 @@ extern "C" int tab_nbr_build(tab_nbr *nbr, int32_t n, const double *d_pos,
     x.s0 = nbr->s0.as<int>();
     x.ghost_owner = nbr->ghost_owner.as<int>();
     x.ghost_S = nbr->ghost_S.as<int>();
-    x.n_owned = n;
+    x.n_loc = n_loc;
     const int nthreads = nbr->n_slices * 32;
     k_count<<<nblocks(nthreads, 128), 128, 0, st>>>(
         n, g, x, nbr->cell_of.as<int>(), nbr->atoms.as<Atom4>(),
-        nbr->ext_start.as<uint32_t>(), nbr->ext_count.as<uint32_t>(),
-        nbr->counts.as<int>(), nbr->slice_w.as<uint32_t>(), d_stats);
+        nbr->ext_tab.as<uint4>(), nbr->counts.as<int>(), nbr->slice_w.as<uint32_t>(),
+        d_stats);
     TAB_LAUNCH_CHECK();
     TAB_TRY(tab_scan_exclusive_u32(nbr->slice_w.as<uint32_t>(),
                                    nbr->slice_ptr.as<uint32_t>(), nbr->n_slices,
@@ -640,12 +661,18 @@ extern "C" int tab_nbr_build(tab_nbr *nbr, int32_t n, const double *d_pos,
     TAB_TRY(nbr->col.ensure(sizeof(uint32_t) * 32 * (size_t)(nbr->ell_rows + 1)));
     k_fill<<<nblocks(nthreads, 128), 128, 0, st>>>(
         n, g, x, nbr->cell_of.as<int>(), nbr->atoms.as<Atom4>(),
-        nbr->types_ext.as<uint8_t>(), nbr->ext_start.as<uint32_t>(),
-        nbr->ext_count.as<uint32_t>(), nbr->slice_w.as<uint32_t>(),
-        nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>());
+        nbr->types_ext.as<uint8_t>(), nbr->ext_tab.as<uint4>(),
+        nbr->slice_w.as<uint32_t>(), nbr->slice_ptr.as<uint32_t>(),
+        nbr->col.as<uint32_t>());
     TAB_LAUNCH_CHECK();
     nbr->built = true;
     return TAB_OK;
+}
+
+extern "C" int tab_nbr_build(tab_nbr *nbr, int32_t n, const double *d_pos,
+                             const int32_t *d_types, const double *h_cell,
+                             const int32_t *h_pbc, double rc, void *stream) {
+    return tab_nbr_build_dd(nbr, n, 0, d_pos, d_types, h_cell, nullptr, h_pbc, rc, stream);
 }
 
 extern "C" int tab_nbr_update(tab_nbr *nbr, const double *d_pos, const double *h_cell,
@@ -700,7 +727,7 @@ extern "C" int tab_nbr_export(const tab_nbr *cnbr, int32_t *d_i, int32_t *d_j,
                                    nbr->row_ptr.as<uint32_t>(), n, nullptr,
                                    nbr->scan_tmp, st));
     k_export<<<nblocks(n, 128), 128, 0, st>>>(
-        n, n, nbr->perm.as<int>(), nbr->s0.as<int>(), nbr->counts.as<int>(),
+        n, nbr->n_loc, nbr->perm.as<int>(), nbr->s0.as<int>(), nbr->counts.as<int>(),
         nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>(),
         nbr->ghost_owner.as<int>(), nbr->ghost_S.as<int>(),
         nbr->row_ptr.as<uint32_t>(), d_i, d_j, d_S);
