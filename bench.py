@@ -190,6 +190,8 @@ def run_ours(args):
     if rank == 0:
         _build.build_library(force=False)
     torch.cuda.set_device(local_rank)
+    if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
+        os.environ['NCCL_DEBUG'] = 'WARN'     # keep stdout to the one JSON line
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
         dist.barrier()

@@ -1,0 +1,114 @@
+"""CPU tests of the host-side mirror: ordering rules (reference tests/test_utils.py,
+transformer/tests/test_vap.py), the Atoms stand-in, and that the C-ABI library
+loads and exports every symbol include/tab200.h declares (no compute calls)."""
+import os
+import re
+from collections import Counter
+
+import numpy as np
+import pytest
+
+from tensoralloy_b200 import utils
+from tensoralloy_b200.atoms import Atoms, bulk_fcc
+from tensoralloy_b200.transformer.vap import VirtualAtomMap
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_kbody_terms_order():
+    # reference tests/test_utils.py: order of terms defines the feature order
+    all_terms, per, els = utils.get_kbody_terms(['Ni', 'Al'], angular=False)
+    assert els == ['Al', 'Ni']
+    assert all_terms == ['AlAl', 'AlNi', 'NiNi', 'NiAl']
+    all_terms, per, els = utils.get_kbody_terms(['A', 'B', 'C'], angular=True)
+    assert per['A'] == ['AA', 'AB', 'AC', 'AAA', 'AAB', 'AAC', 'ABB', 'ABC', 'ACC']
+    assert per['B'][:3] == ['BB', 'BA', 'BC']
+    _, per, _ = utils.get_kbody_terms(['A', 'B'], angular=True, symmetric=False)
+    assert per['A'] == ['AA', 'AB', 'AAA', 'AAB', 'ABA', 'ABB']
+    assert utils.get_elements_from_kbody_term('AlCuNi') == ['Al', 'Cu', 'Ni']
+
+
+def test_pairing_functions():
+    # Szudzik pairing with negative support (utils.py:88-161)
+    seen = set()
+    for x in range(-3, 4):
+        for y in range(-3, 4):
+            z = utils.szudzik_pairing(x, y)
+            assert z not in seen
+            seen.add(z)
+    xs = np.array([0, 1, -1, 5, -7])
+    ys = np.array([0, -1, 1, 3, 2])
+    vec = utils.szudzik_pairing(xs, ys)
+    for k in range(len(xs)):
+        assert vec[k] == utils.szudzik_pairing(int(xs[k]), int(ys[k]))
+    assert utils.szudzik_pairing(3, 4, 5) == utils.szudzik_pairing(
+        utils.szudzik_pairing(3, 4), 5)
+    assert utils.cantor_pairing(3, 4) == (7 * 8) // 2 + 4
+
+
+def test_vap_matches_reference_semantics():
+    # transformer/tests/test_vap.py:24-64 style: Pd3O2 into a Pd4 O5 template
+    symbols = ['Pd', 'Pd', 'O', 'Pd', 'O']
+    max_occurs = Counter({'Pd': 4, 'O': 5})
+    vap = VirtualAtomMap(max_occurs, symbols)
+    assert vap.max_vap_natoms == 10
+    # sorted elements: O (5 slots: 1..5), Pd (4 slots: 6..9)
+    l2g = vap.local_to_gsl_map
+    assert [l2g[i] for i in range(6)] == [0, 6, 7, 1, 8, 2]
+    g2l = vap.gsl_to_local_map
+    assert g2l[6] == 0 and g2l[1] == 2 and g2l.get(3, -1) == -1
+    assert vap.atom_masks.tolist() == [False, True, True, False, False, False,
+                                       True, True, True, False]
+    pos = np.arange(15, dtype=float).reshape(5, 3)
+    mapped = vap.map_positions(pos)
+    assert mapped.shape == (10, 3)
+    assert np.array_equal(mapped[6], pos[0]) and np.array_equal(mapped[1], pos[2])
+    assert np.all(mapped[0] == 0) and np.all(mapped[3] == 0)
+    back = vap.map_positions(mapped, reverse=True)
+    assert np.array_equal(back, pos)
+    assert vap.vap_symbols == ['X'] + ['O'] * 5 + ['Pd'] * 4
+    # hessian remap
+    H = np.random.default_rng(0).random((10, 3, 10, 3))
+    h2 = vap.reverse_map_hessian(H)
+    assert h2.shape == (15, 15)
+    assert h2[0 * 3 + 1, 2 * 3 + 2] == H[6, 1, 1, 2]
+    h4 = vap.reverse_map_hessian(H, phonopy_format=True)
+    assert h4[3, 4, 0, 2] == H[8, 0, 2, 2]
+    with pytest.raises(ValueError):
+        vap.reverse_map_hessian(np.zeros((3, 3)))
+    single = VirtualAtomMap(Counter({'Ni': 4}), ['Ni'] * 4)
+    assert single.is_identity and not vap.is_identity
+
+
+def test_atoms_stand_in():
+    atoms = bulk_fcc('Ni', 3.52, (2, 2, 2))
+    assert len(atoms) == 32 and abs(atoms.get_volume() - 7.04 ** 3) < 1e-9
+    assert atoms.get_chemical_formula(mode='reduce') == 'Ni32'
+    a = Atoms('Pd3O2', positions=np.zeros((5, 3)), cell=[3, 3, 3], pbc=[1, 1, 0])
+    assert a.get_chemical_symbols() == ['Pd', 'Pd', 'Pd', 'O', 'O']
+    assert a.get_pbc().tolist() == [True, True, False]
+
+
+def test_library_exports_every_declared_symbol():
+    from tensoralloy_b200 import _build, _lib
+    _build.build_library()
+    header = open(os.path.join(ROOT, 'include', 'tab200.h')).read()
+    header = re.sub(r'/\*.*?\*/', '', header, flags=re.S)
+    declared = set(re.findall(r'\b(tab_[a-z0-9_]+)\s*\(', header))
+    assert declared, "no declarations parsed"
+    L = _lib.lib()
+    for name in sorted(declared):
+        assert hasattr(L, name), f"{name} declared in tab200.h but not exported"
+    assert declared == set(_lib.EXPORTS)
+    assert L.tab_version() >= 100
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: nothing under tensoralloy_b200/ may
+    import it (a product path routed through it would void parity)."""
+    pkg = os.path.join(ROOT, 'tensoralloy_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith('.py'):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle\b', src, flags=re.M), f
