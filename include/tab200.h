@@ -122,6 +122,16 @@ int tab_nbr_export(const tab_nbr *nbr, int32_t *d_i, int32_t *d_j, int32_t *d_S,
 #define TAB_FN_ZHOU_PHI_MIX  3   /* zjw04.py:229-243   p = [7 of a][4 rho of a][7 of b][4 rho of b] */
 #define TAB_FN_ZHOU_EMBED    4   /* zjw04.py:279-389   p = Fn0..3,F0..3,eta,Fe,rho_e,rho_s */
 #define TAB_FN_ZHOU_EMBED_XC 5   /* zjw04.py:440-550   same p, sigmoid blended */
+#define TAB_FN_SUTTON_RHO     6   /* sutton90.py:61-78    p = a            (a/r)^6 */
+#define TAB_FN_SUTTON_PHI     7   /* sutton90.py:43-59    p = b            (b/r)^12 */
+#define TAB_FN_SQRT_EMBED     8   /* sutton90.py:80-97, grimmes.py:86-101  p = G   -G sqrt(rho) */
+#define TAB_FN_AGRAWAL_RHO    9   /* agrawal.py:57-83     p = A,B,re,rc,m */
+#define TAB_FN_AGRAWAL_PHI   10   /* agrawal.py:124-152   p = D,alpha,re,rc,m */
+#define TAB_FN_AGRAWAL_EMBED 11   /* agrawal.py:85-122    p = F0,F1,beta,gamma */
+#define TAB_FN_GRIMES_RHO    12   /* grimmes.py:62-84     p = n */
+#define TAB_FN_GRIMES_PHI    13   /* grimmes.py:41-60     p = A,rho,C,D,gamma,r0 */
+#define TAB_FN_MISHIN_EMBED  14   /* mishin.py:196-260    p = s1..s7,eps */
+#define TAB_FN_MISHIN_POLAR  15   /* mishin.py:262-315, generic.py:52-84  p = p1,p2,p3,rc,h */
 #define TAB_FN_MAX_PARAMS    32
 
 typedef struct tab_fn {

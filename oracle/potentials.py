@@ -207,9 +207,146 @@ class Zjw04xcp(Zjw04xc):
                 zhou_exp(r, P('B'), P('beta'), P('lamda'), P('r_eq')))
 
 
+class AgSutton90(Potential):
+    """sutton90.py:18-121."""
+    name = 'sutton90'
+
+    def defaults(self):
+        return {'Ag': {'a': 2.928323832}, 'AgAg': {'b': 2.485883762}}
+
+    def rho(self, r, element):
+        el = _elements_of(element)[-1]
+        rinv = torch.where(r == 0, torch.zeros_like(r), 1.0 / r)   # div_no_nan
+        return torch.pow(self.p(el, 'a') * rinv, 6.0)
+
+    def phi(self, r, term):
+        rinv = torch.where(r == 0, torch.zeros_like(r), 1.0 / r)
+        return torch.pow(self.p(term, 'b') * rinv, 12.0)
+
+    def embed(self, rho, element):
+        return -torch.sqrt(rho)
+
+
+def morse_prime(r, d, gamma, r0):
+    """agrawal.py:20-32."""
+    gd = gamma * (r - r0)
+    return (torch.exp(-gd) - torch.exp(-2.0 * gd)) * (d * gamma * 2.0)
+
+
+class AgrawalBe(Potential):
+    """agrawal.py:35-170."""
+    name = 'Be/1'
+
+    def defaults(self):
+        return {"Be": {"A": 1.597, "B": 9.49713, "D": 0.41246, "alpha": 0.36324,
+                       "re": 2.29, "F0": -2.0393, "F1": 12.6178,
+                       "beta": 0.18752, "gamma": -2.28827, "m": 10, "rc": 5.0}}
+
+    def rho(self, r, element):
+        el = _elements_of(element)[-1]
+        P = lambda k: self.p(el, k)
+        A, B, re, rc, m = P('A'), P('B'), P('re'), P('rc'), P('m')
+        rho0 = A * torch.exp(-B * (r - re))
+        rho1 = A * torch.exp(-B * (rc - re))
+        drho = -A * B * torch.exp(-B * (rc - re))
+        rho2 = rc / m * (1.0 - (r / rc) ** m) * drho
+        return rho0 - rho1 + rho2
+
+    def phi(self, r, term):
+        el = _elements_of(term)[0]
+        P = lambda k: self.p(el, k)
+        D, alpha, re, rc, m = P('D'), P('alpha'), P('re'), P('rc'), P('m')
+        phi0 = morse(r, D, alpha, re)
+        phi1 = -morse(rc, D, alpha, re)
+        z = torch.pow(r / rc, m)
+        dphi = morse_prime(rc, D, alpha, re)
+        return phi0 + phi1 + rc / m * ((1.0 - z) * dphi)
+
+    def embed(self, rho, element):
+        P = lambda k: self.p(element, k)
+        x = torch.pow(rho, P('beta'))
+        y = torch.pow(rho, P('gamma'))
+        logrho = torch.log(torch.clamp(rho, min=1e-12))
+        return P('F0') * (1.0 - P('beta') * logrho) * x + P('F1') * y
+
+
+class RWGrimes(Potential):
+    """grimmes.py:20-126."""
+    name = 'grimes'
+
+    def defaults(self):
+        return {'PuPu': {'A': 18600.0, 'rho': 0.2637, 'C': 0.0, 'D': 0.70185,
+                         'gamma': 1.98008, 'r0': 2.34591},
+                'Pu': {'G': 2.168, 'n': 3980.058}}
+
+    def phi(self, r, term):
+        P = lambda k: self.p(term, k)
+        return morse(r, P('D'), P('gamma'), P('r0')) + buckingham(
+            r, P('A'), P('rho'), P('C'))
+
+    def rho(self, r, element):
+        el = _elements_of(element)[-1]
+        rs = torch.pow(r, 8)
+        left = torch.where(rs == 0, torch.zeros_like(rs), self.p(el, 'n') / rs)
+        right = 0.5 + 0.5 * torch.erf(20.0 * (r - 1.0 - 0.5))
+        return left * right
+
+    def embed(self, rho, element):
+        return -torch.sqrt(rho) * self.p(element, 'G')
+
+
+class MishinH(Potential):
+    """mishin.py:20-315 (embed, dipole, quadrupole; rho/phi are broken upstream)."""
+    name = 'mishinh'
+
+    def defaults(self):
+        params = {
+            "Mo": {"s1": -2.00695289e-01, "s2": -3.12178751e-04, "s3": 7.86343222e-05,
+                   "s4": 5.29721645e+00, "s5": 3.79481951e-02, "s6": 1.11800974e+02,
+                   "s7": 4.05948858e+00},
+            "Al": {"s1": -3.72848864e-01, "s2": 6.52035828e-03, "s3": 9.71742655e-05,
+                   "s4": 7.64264116e+00, "s5": 6.88604789e-02, "s6": 1.55694016e+01,
+                   "s7": 5.38646368e+00},
+            "H": {"s1": 8.08612, "s2": 1.46294e-2, "s3": -6.86143e-3, "s4": 3.19616,
+                  "s5": 1.17247e-1, "s6": 50, "s7": 15e5},
+            "NiNi": {"d1": 4.4657e-3, "d2": -1.3702e0, "d3": -0.9611e-1,
+                     "q1": 6.4502e0, "q2": 0.2608e-1, "q3": -6.0208e0,
+                     "h": 3.323, "rc": 5.168},
+            "FeFe": {"d1": 1.9135e-1, "d2": -1.0796e0, "d3": -0.8928e-1,
+                     "q1": -5.8954e-2, "q2": -1.3872e0, "q3": 2.4790e0,
+                     "h": 6.202, "rc": 5.055},
+        }
+        params['MoMo'] = dict(params['NiNi'])
+        params['MoNi'] = dict(params['NiNi'])
+        params['BeBe'] = dict(params['MoMo'])
+        return params
+
+    def embed(self, rho, element):
+        P = lambda k: self.p(element, k)
+        eps = 1e-14 if self.dtype == torch.float64 else 1e-8
+        rho2 = rho * rho
+        rho3 = rho * rho2
+        rho4 = rho2 * rho2
+        rhos5 = torch.pow(rho + eps, P('s5'))
+        a = 1.0 - P('s6') * rho2
+        b = 1.0 + P('s7') * rho4
+        omega = 1.0 - a / b
+        return (P('s1') * rho + P('s2') * rho2 + P('s3') * rho3
+                - P('s4') * rhos5) * omega
+
+    def dipole(self, r, term):
+        P = lambda k: self.p(term, k)
+        return mishin_polar(r, P('d1'), P('d2'), P('d3'), P('rc'), P('h'))
+
+    def quadrupole(self, r, term):
+        P = lambda k: self.p(term, k)
+        return mishin_polar(r, P('q1'), P('q2'), P('q3'), P('rc'), P('h'))
+
+
 REGISTRY = {
     'zjw04': Zjw04, 'zjw04xc': Zjw04xc, 'zjw04uxc': Zjw04uxc,
-    'zjw04xcp': Zjw04xcp,
+    'zjw04xcp': Zjw04xcp, 'sutton90': AgSutton90, 'Be/1': AgrawalBe,
+    'grimes': RWGrimes, 'mishinh': MishinH,
 }
 
 

@@ -24,6 +24,16 @@ FN_ZHOU_PHI = 2
 FN_ZHOU_PHI_MIX = 3
 FN_ZHOU_EMBED = 4
 FN_ZHOU_EMBED_XC = 5
+FN_SUTTON_RHO = 6
+FN_SUTTON_PHI = 7
+FN_SQRT_EMBED = 8
+FN_AGRAWAL_RHO = 9
+FN_AGRAWAL_PHI = 10
+FN_AGRAWAL_EMBED = 11
+FN_GRIMES_RHO = 12
+FN_GRIMES_PHI = 13
+FN_MISHIN_EMBED = 14
+FN_MISHIN_POLAR = 15
 
 
 class TabFn(C.Structure):

@@ -43,6 +43,7 @@ struct Zhou1 {
 };
 
 #define EAM_T 256
+#define ADP_MAX_EL 3     // ADP keeps n_el x 9 moment accumulators in registers
 
 template <typename Real>
 __device__ __forceinline__ void pair_r(const Atom4 &me, const Atom4 &a, Real &dx,
@@ -247,6 +248,226 @@ k_eam_force(int n, const Atom4 *__restrict__ atoms,
     }
 }
 
+
+// ---------------------------------------------------------------------------
+// ADP (nn/eam/adp.py:315-586): per centre atom and per NEIGHBOUR SPECIES T
+//   mu_T = sum_{p in T} u(r_p) D_p ,  lam_T = sum_{p in T} w(r_p) D_p (x) D_p
+//   E_i += sum_T [ 1/2 |mu_T|^2 + 1/2 sum_ab lam_T,ab^2 - 1/6 tr(lam_T)^2 ]
+// (the per-term squaring is the reference's behaviour: adp.py:370-389,455-494).
+// Moments are stored per extended atom as [n_el][9] = mux muy muz lxx lyy lzz
+// lyz lxz lxy; pass 2 needs the neighbour's moments w.r.t. the centre's species.
+// ---------------------------------------------------------------------------
+template <typename Real>
+__global__ void __launch_bounds__(EAM_T)
+k_adp_rho(int n, const Atom4 *__restrict__ atoms,
+          const uint8_t *__restrict__ types_ext, const int *__restrict__ counts,
+          const uint32_t *__restrict__ slice_ptr, const uint32_t *__restrict__ col,
+          EamDev m, double *__restrict__ fprime, double *__restrict__ fembed,
+          double *__restrict__ moments) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    tab_fn *tabs = reinterpret_cast<tab_fn *>(smem_raw);
+    const int nn = m.n_el * m.n_el;
+    load_tables(tabs, m.rho, 4 * nn + m.n_el);
+    const tab_fn *t_dip = tabs + 2 * nn + m.n_el, *t_quad = t_dip + nn;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const Atom4 me = atoms[idx];
+    const int ti = (int)types_ext[idx];
+    const int cnt = counts[idx];
+    const uint32_t *cp = col + ((size_t)slice_ptr[idx >> 5] * 32u + (idx & 31));
+    Real rho = Real(0);
+    Real mom[ADP_MAX_EL][9];
+#pragma unroll
+    for (int t = 0; t < ADP_MAX_EL; ++t)
+#pragma unroll
+        for (int q = 0; q < 9; ++q) mom[t][q] = Real(0);
+    RowIter it(cp, atoms, cnt);
+    Atom4 a;
+    uint32_t c;
+    while (it.next(a, c)) {
+        Real dx, dy, dz, r, rinv, f, df, u, du, w, dw;
+        pair_r<Real>(me, a, dx, dy, dz, r, rinv);
+        const int tj = (int)(c >> TAB_COL_TYPE_SHIFT);
+        eval_pair_fn<Real>(tabs[ti * m.n_el + tj], r, f, df);
+        eval_pair_fn<Real>(t_dip[ti * m.n_el + tj], r, u, du);
+        eval_pair_fn<Real>(t_quad[ti * m.n_el + tj], r, w, dw);
+        rho += f;
+#pragma unroll
+        for (int t = 0; t < ADP_MAX_EL; ++t) {
+            const Real sel = (t == tj) ? Real(1) : Real(0);
+            const Real us = u * sel, ws = w * sel;
+            mom[t][0] += us * dx;
+            mom[t][1] += us * dy;
+            mom[t][2] += us * dz;
+            mom[t][3] += ws * dx * dx;
+            mom[t][4] += ws * dy * dy;
+            mom[t][5] += ws * dz * dz;
+            mom[t][6] += ws * dy * dz;
+            mom[t][7] += ws * dx * dz;
+            mom[t][8] += ws * dx * dy;
+        }
+    }
+    Real F, dF;
+    eval_embed_fn<Real>(tabs[2 * nn + ti], rho, F, dF);
+    Real eadp = Real(0);
+#pragma unroll
+    for (int t = 0; t < ADP_MAX_EL; ++t) {
+        if (t >= m.n_el) break;
+        const Real *q = mom[t];
+        const Real tr = q[3] + q[4] + q[5];
+        eadp += Real(0.5) * (q[0] * q[0] + q[1] * q[1] + q[2] * q[2]) +
+                Real(0.5) * (q[3] * q[3] + q[4] * q[4] + q[5] * q[5] +
+                             Real(2) * (q[6] * q[6] + q[7] * q[7] + q[8] * q[8])) -
+                tr * tr / Real(6);
+#pragma unroll
+        for (int k = 0; k < 9; ++k)
+            moments[((size_t)idx * m.n_el + t) * 9 + k] = (double)q[k];
+    }
+    fprime[idx] = (double)dF;
+    fembed[idx] = (double)(F + eadp);
+}
+
+// moments of halo atoms are not exchanged yet: ADP runs single-domain only
+__global__ void k_adp_spread(int n_owned, int n_ext, int stride,
+                             const int *__restrict__ ghost_owner,
+                             double *__restrict__ moments) {
+    const int e = n_owned + blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_ext) return;
+    const int o = ghost_owner[e - n_owned];
+    for (int k = 0; k < stride; ++k)
+        moments[(size_t)e * stride + k] = moments[(size_t)o * stride + k];
+}
+
+template <typename Real>
+__global__ void __launch_bounds__(EAM_T)
+k_adp_force(int n, const Atom4 *__restrict__ atoms,
+            const uint8_t *__restrict__ types_ext, const int *__restrict__ counts,
+            const uint32_t *__restrict__ slice_ptr, const uint32_t *__restrict__ col,
+            const int *__restrict__ perm, EamDev m,
+            const double *__restrict__ moments, const double *__restrict__ fembed,
+            double *__restrict__ eatom, double *__restrict__ forces,
+            double *__restrict__ partial) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    tab_fn *tabs = reinterpret_cast<tab_fn *>(smem_raw);
+    __shared__ double red[EAM_T / 32][7];
+    const int nn = m.n_el * m.n_el;
+    load_tables(tabs, m.rho, 4 * nn + m.n_el);
+    const tab_fn *t_dip = tabs + 2 * nn + m.n_el, *t_quad = t_dip + nn;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+    if (idx < n) {
+        const Atom4 me = atoms[idx];
+        const int ti = (int)types_ext[idx];
+        const int cnt = counts[idx];
+        const uint32_t *cp = col + ((size_t)slice_ptr[idx >> 5] * 32u + (idx & 31));
+        const Real fpi = (Real)me.w;
+        const int stride = m.n_el * 9;
+        const double *mine = moments + (size_t)idx * stride;
+        Real fx = 0, fy = 0, fz = 0, ep = 0;
+        Real vxx = 0, vyy = 0, vzz = 0, vyz = 0, vxz = 0, vxy = 0;
+        RowIter it(cp, atoms, cnt);
+        Atom4 a;
+        uint32_t c;
+        while (it.next(a, c)) {
+            Real dx, dy, dz, r, rinv;
+            pair_r<Real>(me, a, dx, dy, dz, r, rinv);
+            const int j = (int)(c & TAB_COL_IDX_MASK);
+            const int tj = (int)(c >> TAB_COL_TYPE_SHIFT);
+            const Real fpj = (Real)a.w;
+            Real rij, drij, rji, drji, phi, dphi, u, du, w, dw;
+            eval_pair_fn<Real>(tabs[ti * m.n_el + tj], r, rij, drij);
+            if (ti == tj) drji = drij;
+            else eval_pair_fn<Real>(tabs[tj * m.n_el + ti], r, rji, drji);
+            eval_pair_fn<Real>(tabs[nn + ti * m.n_el + tj], r, phi, dphi);
+            eval_pair_fn<Real>(t_dip[ti * m.n_el + tj], r, u, du);
+            eval_pair_fn<Real>(t_quad[ti * m.n_el + tj], r, w, dw);
+            // EAM part, symmetric in the pair
+            const Real s = (fpi * drij + fpj * drji + dphi) * rinv;
+            Real gx = s * dx, gy = s * dy, gz = s * dz;
+            vxx += Real(0.5) * gx * dx;
+            vyy += Real(0.5) * gy * dy;
+            vzz += Real(0.5) * gz * dz;
+            vyz += Real(0.5) * gy * dz;
+            vxz += Real(0.5) * gx * dz;
+            vxy += Real(0.5) * gx * dy;
+            ep += phi;
+            // ADP part: own moments w.r.t. species tj, neighbour's w.r.t. species ti
+            const double *qi = mine + tj * 9;
+            const double *qj = moments + (size_t)j * stride + ti * 9;
+            Real mi[9], mj[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                mi[k] = (Real)qi[k];
+                mj[k] = (Real)qj[k];
+            }
+            const Real tri = (mi[3] + mi[4] + mi[5]) / Real(3);
+            const Real trj = (mj[3] + mj[4] + mj[5]) / Real(3);
+            // M = lam - tr/3 I  (xx yy zz yz xz xy)
+            const Real Mi[6] = {mi[3] - tri, mi[4] - tri, mi[5] - tri, mi[6], mi[7], mi[8]};
+            const Real Mj[6] = {mj[3] - trj, mj[4] - trj, mj[5] - trj, mj[6], mj[7], mj[8]};
+            auto Mv = [&](const Real *M, Real &x, Real &y, Real &z) {
+                x = M[0] * dx + M[5] * dy + M[4] * dz;
+                y = M[5] * dx + M[1] * dy + M[3] * dz;
+                z = M[4] * dx + M[3] * dy + M[2] * dz;
+            };
+            Real ax, ay, az, bx, by, bz;
+            Mv(Mi, ax, ay, az);
+            Mv(Mj, bx, by, bz);
+            const Real mudi = mi[0] * dx + mi[1] * dy + mi[2] * dz;
+            const Real mudj = mj[0] * dx + mj[1] * dy + mj[2] * dz;
+            const Real dMdi = ax * dx + ay * dy + az * dz;
+            const Real dMdj = bx * dx + by * dy + bz * dz;
+            // directed gradient g_{i->j} (own moments): virial
+            const Real ci = (du * mudi + dw * dMdi) * rinv;
+            const Real gix = ci * dx + u * mi[0] + Real(2) * w * ax;
+            const Real giy = ci * dy + u * mi[1] + Real(2) * w * ay;
+            const Real giz = ci * dz + u * mi[2] + Real(2) * w * az;
+            vxx += gix * dx;
+            vyy += giy * dy;
+            vzz += giz * dz;
+            vyz += Real(0.5) * (giy * dz + giz * dy);
+            vxz += Real(0.5) * (gix * dz + giz * dx);
+            vxy += Real(0.5) * (gix * dy + giy * dx);
+            // force: g_{i->j}(D) - g_{j->i}(-D)
+            const Real cj = (du * mudj - dw * dMdj) * rinv;
+            gx += gix - (cj * dx + u * mj[0] - Real(2) * w * bx);
+            gy += giy - (cj * dy + u * mj[1] - Real(2) * w * by);
+            gz += giz - (cj * dz + u * mj[2] - Real(2) * w * bz);
+            fx += gx;
+            fy += gy;
+            fz += gz;
+        }
+        const double ei = fembed[idx] + 0.5 * (double)ep;
+        const int o = perm[idx];
+        if (eatom) eatom[o] = ei;
+        if (forces) {
+            forces[3 * o + 0] = (double)fx;
+            forces[3 * o + 1] = (double)fy;
+            forces[3 * o + 2] = (double)fz;
+        }
+        acc[0] = ei;
+        acc[1] = (double)vxx;
+        acc[2] = (double)vyy;
+        acc[3] = (double)vzz;
+        acc[4] = (double)vyz;
+        acc[5] = (double)vxz;
+        acc[6] = (double)vxy;
+    }
+#pragma unroll
+    for (int q = 0; q < 7; ++q) {
+        double v = acc[q];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][q] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 7) {
+        double v = 0;
+        for (int w = 0; w < EAM_T / 32; ++w) v += red[w][threadIdx.x];
+        partial[(size_t)blockIdx.x * 8 + threadIdx.x] = v;
+    }
+}
+
 // fixed-order final reduction: energy[0], virial[9]
 __global__ void __launch_bounds__(256)
 k_reduce_partials(int nblk, const double *__restrict__ partial,
@@ -288,21 +509,25 @@ extern "C" int tab_eam_create(tab_model **out, int32_t kind, int32_t n_el,
         tab_set_error("tab_eam_create: bad argument");
         return TAB_EINVAL;
     }
-    if (kind != TAB_EAM_ALLOY && kind != TAB_EAM_FS) {
-        tab_set_error("tab_eam_create: kind %d not supported yet", kind);
+    if (kind != TAB_EAM_ALLOY && kind != TAB_EAM_FS && kind != TAB_EAM_ADP) {
+        tab_set_error("tab_eam_create: unknown kind %d", kind);
+        return TAB_EINVAL;
+    }
+    if (kind == TAB_EAM_ADP && (!dipole || !quadrupole || n_el > ADP_MAX_EL)) {
+        tab_set_error("tab_eam_create: ADP needs dipole+quadrupole tables and "
+                      "at most %d elements", ADP_MAX_EL);
         return TAB_EUNSUPPORTED;
     }
     if (n_el > 8) {
         tab_set_error("tab_eam_create: more than 8 elements not supported");
         return TAB_EUNSUPPORTED;
     }
-    (void)dipole;
-    (void)quadrupole;
     tab_model *m = new tab_model();
     m->kind = kind;
     m->n_el = n_el;
     const int nn = n_el * n_el;
-    const size_t count = (size_t)2 * nn + n_el;
+    const bool adp = kind == TAB_EAM_ADP;
+    const size_t count = (size_t)2 * nn + n_el + (adp ? 2 * nn : 0);
     int rc = m->tables.ensure(count * sizeof(tab_fn));
     if (rc != TAB_OK) {
         delete m;
@@ -312,6 +537,10 @@ extern "C" int tab_eam_create(tab_model **out, int32_t kind, int32_t n_el,
     memcpy(host, rho, nn * sizeof(tab_fn));
     memcpy(host + nn, phi, nn * sizeof(tab_fn));
     memcpy(host + 2 * nn, embed, n_el * sizeof(tab_fn));
+    if (adp) {
+        memcpy(host + 2 * nn + n_el, dipole, nn * sizeof(tab_fn));
+        memcpy(host + 3 * nn + n_el, quadrupole, nn * sizeof(tab_fn));
+    }
     // device representation: the r_eq slots hold 1/r_eq (potentials.cuh)
     for (size_t k = 0; k < count; ++k) {
         tab_fn &f = host[k];
@@ -477,6 +706,61 @@ static int eam_pass2(tab_model *m, tab_nbr *nbr, const double *d_fprime_halo,
     return TAB_OK;
 }
 
+template <typename Real>
+static int adp_pass1(tab_model *m, tab_nbr *nbr, cudaStream_t st) {
+    EamLaunch L;
+    TAB_TRY(eam_prepare(m, nbr, false, L));
+    if (nbr->n_halo > 0) {
+        tab_set_error("ADP with halo atoms (domain decomposition) is not supported");
+        return TAB_EUNSUPPORTED;
+    }
+    const int nn = m->n_el * m->n_el, stride = m->n_el * 9;
+    L.smem = (size_t)(4 * nn + m->n_el) * sizeof(tab_fn);
+    TAB_TRY(nbr->adp.ensure(sizeof(double) * (size_t)nbr->n_ext * stride));
+    prof_mark(0, st);
+    k_adp_rho<Real><<<L.nblk, EAM_T, L.smem, st>>>(
+        nbr->n, nbr->atoms.as<Atom4>(), nbr->types_ext.as<uint8_t>(),
+        nbr->counts.as<int>(), nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>(),
+        L.dev, L.fprime, L.fembed, nbr->adp.as<double>());
+    TAB_LAUNCH_CHECK();
+    if (nbr->n_ext > nbr->n) {
+        k_adp_spread<<<(nbr->n_ext - nbr->n + 255) / 256, 256, 0, st>>>(
+            nbr->n, nbr->n_ext, stride, nbr->ghost_owner.as<int>(), nbr->adp.as<double>());
+        TAB_LAUNCH_CHECK();
+    }
+    prof_mark(1, st);
+    return TAB_OK;
+}
+
+template <typename Real>
+static int adp_pass2(tab_model *m, tab_nbr *nbr, double *d_energy, double *d_eatom,
+                     double *d_forces, double *d_virial, cudaStream_t st) {
+    EamLaunch L;
+    TAB_TRY(eam_prepare(m, nbr, false, L));
+    const int nn = m->n_el * m->n_el;
+    L.smem = (size_t)(4 * nn + m->n_el) * sizeof(tab_fn);
+    k_spread_w<<<(nbr->n_ext + 255) / 256, 256, 0, st>>>(
+        nbr->n, nbr->n_loc, nbr->n_ext, L.fprime, nullptr, nbr->perm.as<int>(),
+        nbr->ghost_owner.as<int>(), nbr->atoms.as<Atom4>());
+    TAB_LAUNCH_CHECK();
+    prof_mark(2, st);
+    k_adp_force<Real><<<L.nblk, EAM_T, L.smem, st>>>(
+        nbr->n, nbr->atoms.as<Atom4>(), nbr->types_ext.as<uint8_t>(),
+        nbr->counts.as<int>(), nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>(),
+        nbr->perm.as<int>(), L.dev, nbr->adp.as<double>(), L.fembed, d_eatom, d_forces,
+        nbr->partial.as<double>());
+    TAB_LAUNCH_CHECK();
+    prof_mark(3, st);
+    if (d_energy || d_virial) {
+        k_reduce_partials<<<1, 256, 0, st>>>(L.nblk, nbr->partial.as<double>(), d_energy,
+                                             d_virial);
+        TAB_LAUNCH_CHECK();
+    }
+    prof_mark(4, st);
+    if (g_prof_on && g_prof_calls < PROF_MAX_CALLS) ++g_prof_calls;
+    return TAB_OK;
+}
+
 #define EAM_DISPATCH(FN, ...)                                                        \
     do {                                                                             \
         if (precision == TAB_PRECISION_HIGH)                                         \
@@ -503,6 +787,10 @@ extern "C" int tab_eam_pass1(tab_model *m, tab_nbr *nbr, int32_t precision,
                              double *d_fprime, void *stream) {
     TAB_TRY(check_handles(m, nbr, "tab_eam_pass1"));
     cudaStream_t st = (cudaStream_t)stream;
+    if (m->kind == TAB_EAM_ADP) {
+        if (precision == TAB_PRECISION_HIGH) return adp_pass1<double>(m, nbr, st);
+        return adp_pass1<float>(m, nbr, st);
+    }
     EAM_DISPATCH(eam_pass1, m, nbr, d_fprime, st);
 }
 
@@ -512,6 +800,11 @@ extern "C" int tab_eam_pass2(tab_model *m, tab_nbr *nbr, int32_t precision,
                              void *stream) {
     TAB_TRY(check_handles(m, nbr, "tab_eam_pass2"));
     cudaStream_t st = (cudaStream_t)stream;
+    if (m->kind == TAB_EAM_ADP) {
+        if (precision == TAB_PRECISION_HIGH)
+            return adp_pass2<double>(m, nbr, d_energy, d_eatom, d_forces, d_virial, st);
+        return adp_pass2<float>(m, nbr, d_energy, d_eatom, d_forces, d_virial, st);
+    }
     EAM_DISPATCH(eam_pass2, m, nbr, d_fprime_halo, d_energy, d_eatom, d_forces, d_virial, st);
 }
 

@@ -32,7 +32,7 @@ __device__ __forceinline__ double tab_rsqrt(double x) {
     return fma(y, e, y);
 }
 
-// exp(t) for |t| < 700: n = rint(t log2 e), f = t - n ln2, degree-12 Taylor
+// exp(t) for t < 700 (t < -700 -> 0): n = rint(t log2 e), f = t - n ln2, degree-12 Taylor
 // polynomial on |f| <= 0.347 (truncation 1.7e-16), exponent patched in.
 __device__ __forceinline__ double tab_exp(double t) {
     const double SHIFT = 6755399441055744.0;   // 1.5 * 2^52
@@ -54,7 +54,8 @@ __device__ __forceinline__ double tab_exp(double t) {
     p = fma(p, f, 0.5);
     p = fma(p, f, 1.0);
     p = fma(p, f, 1.0);
-    return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+    const double y = __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+    return t < -700.0 ? 0.0 : y;     // underflow guard (erf tails, far pairs)
 }
 
 template <typename Real> struct Math;
@@ -64,6 +65,8 @@ template <> struct Math<double> {
     static __device__ __forceinline__ double pow_(double x, double y) { return pow(x, y); }
     static __device__ __forceinline__ double rcp_(double x) { return tab_rcp(x); }
     static __device__ __forceinline__ double rsqrt_(double x) { return tab_rsqrt(x); }
+    static __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
+    static __device__ __forceinline__ double erf_(double x) { return erf(x); }
     static __device__ __forceinline__ double eps() { return 1e-14; }   // precision.py:113
 };
 template <> struct Math<float> {
@@ -72,6 +75,8 @@ template <> struct Math<float> {
     static __device__ __forceinline__ float pow_(float x, float y) { return powf(x, y); }
     static __device__ __forceinline__ float rcp_(float x) { return __frcp_rn(x); }
     static __device__ __forceinline__ float rsqrt_(float x) { return rsqrtf(x); }
+    static __device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
+    static __device__ __forceinline__ float erf_(float x) { return erff(x); }
     static __device__ __forceinline__ float eps() { return 1e-8f; }    // precision.py:114
 };
 
@@ -179,6 +184,79 @@ __device__ __forceinline__ void eval_pair_fn(const tab_fn &fn, Real r, Real &f,
         df = Real(0.5) * (dqab * pb + qab * dpb + dqba * pa + qba * dpa);
         break;
     }
+    case TAB_FN_SUTTON_RHO: {   // sutton90.py:61-78  (a/r)^6
+        const Real q = (Real)p[0] / r, q2 = q * q;
+        f = q2 * q2 * q2;
+        df = Real(-6) * f / r;
+        break;
+    }
+    case TAB_FN_SUTTON_PHI: {   // sutton90.py:43-59  (b/r)^12
+        const Real q = (Real)p[0] / r, q2 = q * q, q4 = q2 * q2;
+        f = q4 * q4 * q4;
+        df = Real(-12) * f / r;
+        break;
+    }
+    case TAB_FN_AGRAWAL_RHO: {  // agrawal.py:57-83
+        const Real A = (Real)p[0], Bq = (Real)p[1], re = (Real)p[2], rc = (Real)p[3],
+                   m = (Real)p[4];
+        const Real rho0 = A * Math<Real>::exp_(-Bq * (r - re));
+        const Real tail = A * Math<Real>::exp_(-Bq * (rc - re));
+        const Real drho = -Bq * tail;
+        const Real zm1 = Math<Real>::pow_(r / rc, m - Real(1));
+        f = rho0 - tail + rc / m * (Real(1) - zm1 * (r / rc)) * drho;
+        df = -Bq * rho0 - zm1 * drho;
+        break;
+    }
+    case TAB_FN_AGRAWAL_PHI: {  // agrawal.py:124-152 (generic.py:15-30 morse)
+        const Real D = (Real)p[0], al = (Real)p[1], re = (Real)p[2], rc = (Real)p[3],
+                   m = (Real)p[4];
+        const Real e1 = Math<Real>::exp_(-al * (r - re)), e1c = Math<Real>::exp_(-al * (rc - re));
+        const Real phi0 = D * (e1 * e1 - Real(2) * e1);
+        const Real phic = D * (e1c * e1c - Real(2) * e1c);
+        const Real dphic = Real(2) * D * al * (e1c - e1c * e1c);
+        const Real zm1 = Math<Real>::pow_(r / rc, m - Real(1));
+        f = phi0 - phic + rc / m * (Real(1) - zm1 * (r / rc)) * dphic;
+        df = Real(2) * D * al * (e1 - e1 * e1) - zm1 * dphic;
+        break;
+    }
+    case TAB_FN_GRIMES_RHO: {   // grimmes.py:62-84  n/r^8 * (1+erf(20(r-1.5)))/2
+        const Real r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
+        const Real left = (Real)p[0] / r8;
+        const Real t = Real(20) * (r - Real(1.5));
+        const Real right = Real(0.5) + Real(0.5) * Math<Real>::erf_(t);
+        f = left * right;
+        df = Real(-8) * f / r +
+             left * Real(20) * Real(0.56418958354775628695) * Math<Real>::exp_(-t * t);
+        break;
+    }
+    case TAB_FN_GRIMES_PHI: {   // grimmes.py:41-60: morse + buckingham
+        const Real A = (Real)p[0], rho = (Real)p[1], C = (Real)p[2], D = (Real)p[3],
+                   gm = (Real)p[4], r0 = (Real)p[5];
+        const Real e1 = Math<Real>::exp_(-gm * (r - r0));
+        const Real eb = A * Math<Real>::exp_(-r / rho);
+        const Real r2 = r * r, r6 = r2 * r2 * r2;
+        f = D * (e1 * e1 - Real(2) * e1) + eb - C / r6;
+        df = Real(2) * D * gm * (e1 - e1 * e1) - eb / rho + Real(6) * C / (r6 * r);
+        break;
+    }
+    case TAB_FN_MISHIN_POLAR: { // generic.py:52-84: (p1 e^{-p2 r} + p3) psi((r-rc)/h)
+        const Real p1 = (Real)p[0], p2 = (Real)p[1], p3 = (Real)p[2], rc = (Real)p[3],
+                   h = (Real)p[4];
+        const Real z = (r - rc) / h;
+        if (z >= Real(0)) {
+            f = Real(0);
+            df = Real(0);
+        } else {
+            const Real z2 = z * z, z4 = z2 * z2;
+            const Real den = Real(1) / (Real(1) + z4);
+            const Real psi = z4 * den;
+            const Real dpsi = Real(4) * z2 * z * den * den / h;
+            const Real ex = p1 * Math<Real>::exp_(-p2 * r);
+            f = (ex + p3) * psi;
+            df = -p2 * ex * psi + (ex + p3) * dpsi;
+        }
+        break;
+    }
     default:
         f = Real(0);
         df = Real(0);
@@ -195,6 +273,50 @@ __device__ __forceinline__ void eval_embed_fn(const tab_fn &fn, Real rho, Real &
     case TAB_FN_ZHOU_EMBED_XC:
         zhou_embed<Real>(fn.p, true, rho, F, dF);
         break;
+    case TAB_FN_SQRT_EMBED: {      // sutton90.py:80-97 (G = 1), grimmes.py:86-101
+        const Real G = (Real)fn.p[0];
+        if (rho > Real(0)) {
+            const Real sq = Math<Real>::sqrt_(rho);
+            F = -G * sq;
+            dF = -G * Real(0.5) / sq;
+        } else {
+            F = Real(0);
+            dF = Real(0);
+        }
+        break;
+    }
+    case TAB_FN_AGRAWAL_EMBED: {   // agrawal.py:85-122
+        const Real F0 = (Real)fn.p[0], F1 = (Real)fn.p[1], be = (Real)fn.p[2],
+                   ga = (Real)fn.p[3];
+        if (rho > Real(0)) {
+            const Real lg = Math<Real>::log_(rho > Real(1e-12) ? rho : Real(1e-12));
+            const Real xb = Math<Real>::pow_(rho, be), xg = Math<Real>::pow_(rho, ga);
+            F = F0 * (Real(1) - be * lg) * xb + F1 * xg;
+            const Real dlg = rho > Real(1e-12) ? Real(1) / rho : Real(0);
+            dF = F0 * (-be * dlg * xb + (Real(1) - be * lg) * be * xb / rho) +
+                 F1 * ga * xg / rho;
+        } else {
+            F = Real(0);
+            dF = Real(0);
+        }
+        break;
+    }
+    case TAB_FN_MISHIN_EMBED: {    // mishin.py:196-260
+        const double *s = fn.p;
+        const Real s1 = (Real)s[0], s2 = (Real)s[1], s3 = (Real)s[2], s4 = (Real)s[3],
+                   s5 = (Real)s[4], s6 = (Real)s[5], s7 = (Real)s[6], eps = (Real)s[7];
+        const Real r2 = rho * rho, r3 = r2 * rho, r4 = r2 * r2;
+        const Real re = rho + eps;
+        const Real pw = Math<Real>::pow_(re, s5);
+        const Real S = s1 * rho + s2 * r2 + s3 * r3 - s4 * pw;
+        const Real dS = s1 + Real(2) * s2 * rho + Real(3) * s3 * r2 - s4 * s5 * pw / re;
+        const Real a = Real(1) - s6 * r2, b = Real(1) + s7 * r4;
+        const Real om = Real(1) - a / b;
+        const Real dom = -((-Real(2) * s6 * rho) * b - a * (Real(4) * s7 * r3)) / (b * b);
+        F = S * om;
+        dF = dS * om + S * dom;
+        break;
+    }
     default:
         F = Real(0);
         dF = Real(0);

@@ -114,7 +114,16 @@ class EamNN(BasicNN):
                 key = "".join(sorted([a, b])) if a != b else f"{a}{a}"
                 phi.append(self._fn_of(key, 'phi').phi(key))
         embed = [self._fn_of(a, 'embed').embed(a) for a in els]
-        self._model = _lib.EamModel(self.kind, len(els), rho, phi, embed)
+        dipole = quadrupole = None
+        if self.kind == _lib.EAM_ADP:
+            dipole, quadrupole = [], []
+            for a in els:
+                for b in els:
+                    key = "".join(sorted([a, b])) if a != b else f"{a}{a}"
+                    dipole.append(self._fn_of(key, 'dipole').dipole(key))
+                    quadrupole.append(self._fn_of(key, 'quadrupole').quadrupole(key))
+        self._model = _lib.EamModel(self.kind, len(els), rho, phi, embed, dipole,
+                                    quadrupole)
         return self._model
 
     def _evaluate(self, features, want_forces, want_virial, want_atomic):

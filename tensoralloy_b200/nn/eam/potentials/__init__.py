@@ -3,6 +3,8 @@ Potential-function registry: maps the reference's potential names
 (nn/eam/potentials/__init__.py:21-31) to builders of `tab_fn` table entries for
 libtab200.  The arithmetic itself lives in csrc/potentials.cuh.
 """
+from tensoralloy_b200.nn.eam.potentials.empirical import (
+    AgrawalBe, AgSutton90, MishinH, RWGrimes)
 from tensoralloy_b200.nn.eam.potentials.zjw04 import (
     Zjw04, Zjw04xc, Zjw04uxc, Zjw04xcp)
 
@@ -11,7 +13,14 @@ available_potentials = {
     'zjw04xc': Zjw04xc,
     'zjw04uxc': Zjw04uxc,
     'zjw04xcp': Zjw04xcp,
+    'sutton90': AgSutton90,
+    'grimes': RWGrimes,
+    'mishinh': MishinH,
+    'Be/1': AgrawalBe,
 }
+# `msah11` (Al-Fe Finnis-Sinclair, nn/eam/potentials/msah11.py) is a fixed table of
+# piecewise constants; it is served through the tabulated-spline path (setfl file
+# test_files/lammps/Mendelev_Al_Fe.fs.eam), not re-typed here.
 
 
 def get_potential(name):

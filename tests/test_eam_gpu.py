@@ -85,3 +85,107 @@ def test_small_cell_images():
     pos = atoms.positions + rng.normal(scale=0.03, size=atoms.positions.shape)
     compare('zjw04', ['Ni'], atoms.get_chemical_symbols(), pos, atoms.cell,
             [1, 1, 1], 6.5)
+
+
+# ---------------------------------------------------------------------------
+# further potentials, Finnis-Sinclair and ADP through the model classes
+# ---------------------------------------------------------------------------
+def _calc_compare(nn, atoms, oracle_pot, kind, rc, fns=None, tol_e=1e-10,
+                  tol_f=1e-8):
+    from tensoralloy_b200.calculator import TensorAlloyCalculator
+    from tensoralloy_b200.precision import precision_scope
+    from tensoralloy_b200.transformer import UniversalTransformer
+    with precision_scope('high'):
+        nn.attach_transformer(UniversalTransformer(nn.elements, rcut=rc))
+        calc = TensorAlloyCalculator(nn)
+        calc.calculate(atoms, properties=['energy', 'forces', 'stress'])
+        e = calc.results['energy']
+        f = calc.get_forces(atoms)
+        s = calc.get_stress(atoms)
+        ea = calc.get_atomic(atoms)
+    ref = oeam.eam_evaluate(oracle_pot, kind, nn.elements,
+                            atoms.get_chemical_symbols(), atoms.positions,
+                            atoms.cell, atoms.pbc, rc, fns=fns)
+    n = len(atoms)
+    assert abs(e - ref['energy']) / n < tol_e
+    assert np.abs(ea - ref['energy/atom']).max() < tol_e * 10
+    assert np.abs(f - ref['forces']).max() < tol_f
+    assert np.abs(s - ref['stress']).max() < tol_f
+    return ref
+
+
+def _rattled(symbol, a, rep, seed, sigma=0.06):
+    atoms = bulk_fcc(symbol, a, rep)
+    rng = np.random.default_rng(seed)
+    atoms.positions += rng.normal(scale=sigma, size=atoms.positions.shape)
+    return atoms
+
+
+def test_sutton90_agrawal_grimes():
+    from tensoralloy_b200.nn.eam import EamAlloyNN
+    _calc_compare(EamAlloyNN(['Ag'], custom_potentials='sutton90'),
+                  _rattled('Ag', 4.09, (3, 3, 3), 1), opot.get_potential('sutton90'),
+                  'alloy', 6.0)
+    _calc_compare(EamAlloyNN(['Be'], custom_potentials='Be/1'),
+                  _rattled('Be', 3.2, (3, 3, 3), 2), opot.get_potential('Be/1'),
+                  'alloy', 5.0)
+    _calc_compare(EamAlloyNN(['Pu'], custom_potentials='grimes'),
+                  _rattled('Pu', 4.6, (3, 3, 3), 3), opot.get_potential('grimes'),
+                  'alloy', 6.0, tol_f=1e-7)
+
+
+def test_finnis_sinclair_ordered_pair_density():
+    """EAM/FS: rho depends on the ordered (centre, neighbour) pair (fs.py:180-203).
+    Built at the table level with four distinct density functions."""
+    pz = get_potential('zjw04')
+    els = ['Mo', 'Ni']
+    src = {'MoMo': 'Mo', 'MoNi': 'Cu', 'NiMo': 'Al', 'NiNi': 'Ni'}
+    rho = [pz.rho(src[a + b]) for a in els for b in els]
+    phi = [pz.phi(''.join(sorted([a, b]))) for a in els for b in els]
+    embed = [pz.embed(a) for a in els]
+    model = _lib.EamModel(_lib.EAM_FS, 2, rho, phi, embed)
+    atoms = _rattled('Ni', 3.6, (3, 3, 3), 5)
+    rng = np.random.default_rng(9)
+    sym = ['Mo' if x < 0.5 else 'Ni' for x in rng.random(len(atoms))]
+    n = len(atoms)
+    nl = _lib.NeighborList()
+    d_pos = torch.tensor(atoms.positions, device='cuda')
+    d_t = torch.tensor([els.index(s) for s in sym], dtype=torch.int32, device='cuda')
+    nl.build(d_pos, d_t, atoms.cell, [1, 1, 1], 6.0)
+    e = torch.zeros(1, dtype=torch.float64, device='cuda')
+    f = torch.zeros((n, 3), dtype=torch.float64, device='cuda')
+    v = torch.zeros(9, dtype=torch.float64, device='cuda')
+    model.eval(nl, 0, energy=e, forces=f, virial=v)
+    op = opot.get_potential('zjw04')
+    fns = {'rho': lambda r, term: op.rho(r, src[term])}
+    ref = oeam.eam_evaluate(op, 'fs', els, sym, atoms.positions, atoms.cell,
+                            [1, 1, 1], 6.0, fns=fns)
+    assert abs(e.item() - ref['energy']) / n < 1e-10
+    assert np.abs(f.cpu().numpy() - ref['forces']).max() < 1e-8
+    assert np.abs(v.cpu().numpy().reshape(3, 3) - ref['virial']).max() / n < 1e-8
+
+
+def test_adp_dipole_quadrupole():
+    """AdpNN: zjw04 rho/phi/embed + MishinH dipole/quadrupole (adp.py:315-586),
+    one and two species (per-term squaring of the moments)."""
+    from tensoralloy_b200.nn.eam import AdpNN
+    om = opot.get_potential('mishinh')
+    oz = opot.get_potential('zjw04')
+    fns = {'rho': oz.rho, 'phi': oz.phi, 'embed': oz.embed,
+           'dipole': om.dipole, 'quadrupole': om.quadrupole}
+    cp = {'Ni': {'rho': 'zjw04', 'embed': 'zjw04'},
+          'NiNi': {'phi': 'zjw04', 'dipole': 'mishinh', 'quadrupole': 'mishinh'}}
+    nn = AdpNN(['Ni'], custom_potentials=cp)
+    _calc_compare(nn, _rattled('Ni', 3.52, (3, 3, 3), 11), None, 'adp', 6.0, fns=fns)
+    cp2 = {'Mo': {'rho': 'zjw04', 'embed': 'zjw04'},
+           'Ni': {'rho': 'zjw04', 'embed': 'zjw04'},
+           'MoMo': {'phi': 'zjw04', 'dipole': 'mishinh', 'quadrupole': 'mishinh'},
+           'MoNi': {'phi': 'zjw04', 'dipole': 'mishinh', 'quadrupole': 'mishinh'},
+           'NiNi': {'phi': 'zjw04', 'dipole': 'mishinh', 'quadrupole': 'mishinh'}}
+    atoms = _rattled('Ni', 3.6, (3, 3, 3), 12)
+    rng = np.random.default_rng(13)
+    from tensoralloy_b200.atoms import Atoms
+    sym = ['Mo' if x < 0.45 else 'Ni' for x in rng.random(len(atoms))]
+    atoms = Atoms(sym, atoms.positions, atoms.cell, True)
+    _calc_compare(AdpNN(['Mo', 'Ni'], custom_potentials=cp2), atoms, None, 'adp', 6.0,
+                  fns=fns)
