@@ -186,6 +186,74 @@ int tab_eam_compute_host(tab_model *model, tab_nbr *nbr, int32_t precision,
                          int32_t rebuild, double *h_energy, double *h_eatom,
                          double *h_forces, double *h_virial, void *stream);
 
+/* ------------------------------------------------------------------------
+ * AtomicNN: Behler symmetry functions (G2 + G4) + per-element MLPs.
+ * Replaces SymmetryFunction.calculate (nn/atomic/sf.py:79-215), the triple
+ * enumeration of get_angular_metadata (transformer/universal.py:115-233),
+ * AtomicNN._get_model_outputs / _apply_minmax_normalization / _get_energy_ops
+ * (nn/atomic/atomic.py:157-302), convolution1x1 (nn/convolutional.py:154-300) and
+ * the autograd outputs of BasicNN.build (nn/basic.py:276-354).
+ * ---------------------------------------------------------------------- */
+typedef struct tab_atomic tab_atomic;
+
+#define TAB_CUTOFF_COSINE     0   /* nn/cutoff.py:20-48 */
+#define TAB_CUTOFF_POLYNOMIAL 1   /* nn/cutoff.py:51-85, gamma = 5 */
+
+/* activation ids (nn/utils.py:50-74) */
+#define TAB_ACT_SOFTPLUS   0
+#define TAB_ACT_TANH       1
+#define TAB_ACT_RELU       2
+#define TAB_ACT_LEAKY_RELU 3
+#define TAB_ACT_SIGMOID    4
+#define TAB_ACT_SOFTSIGN   5
+#define TAB_ACT_ELU        6
+#define TAB_ACT_SQUAREPLUS 7
+
+/* Symmetry-function hyper-parameters.  The radial sets are the (eta, omega)
+ * pairs in sklearn ParameterGrid order (eta outer, omega inner), the angular sets
+ * the (beta, gamma, zeta) triples (beta outer, gamma, zeta inner) -- sf.py:47-51.
+ * Feature layout of a centre of element c: G2 blocks of the terms
+ * [cc, c-x1, ...] then G4 blocks of c+(sorted pair j<=k) -- utils.py:262-286. */
+typedef struct tab_sf_desc {
+    int32_t n_el;
+    int32_t cutoff;           /* TAB_CUTOFF_* */
+    int32_t angular;
+    int32_t n_r, n_a;
+    double  rc, acut;
+    const double *eta, *omega;             /* [n_r] */
+    const double *beta, *gamma, *zeta;     /* [n_a] */
+} tab_sf_desc;
+
+/* One element's MLP: sizes[0] = descriptor length, sizes[n_layers] = 1;
+ * weights[l] is [sizes[l], sizes[l+1]] row-major (the reference's Conv1d kernel
+ * [1, in, out]), biases[l] [sizes[l+1]] (NULL = zeros); layer n_layers-1 is the
+ * linear 'Output' layer (bias used iff output_bias).  xlo/xhi: min-max
+ * normalisation vectors (atomic.py:181-195) or NULL. */
+typedef struct tab_mlp_desc {
+    int32_t n_layers;
+    int32_t sizes[9];
+    int32_t activation;       /* TAB_ACT_* */
+    int32_t use_resnet_dt;
+    int32_t output_bias;
+    const double *weights[8];
+    const double *biases[8];
+    const double *xlo, *xhi;
+} tab_mlp_desc;
+
+int tab_atomic_create(tab_atomic **out, const tab_sf_desc *sf, const tab_mlp_desc *mlps);
+int tab_atomic_free(tab_atomic *model);
+int tab_atomic_dim(const tab_atomic *model);   /* descriptor length per atom */
+
+/* E, per-atom E, forces, virial as tab_eam_eval.  The lists must have been built
+ * with a cutoff >= max(rc, acut). */
+int tab_atomic_eval(tab_atomic *model, tab_nbr *nbr, int32_t precision,
+                    double *d_energy, double *d_eatom, double *d_forces,
+                    double *d_virial, void *stream);
+
+/* Raw descriptors, d_desc [n, dim] float64 in caller atom order. */
+int tab_atomic_descriptors(tab_atomic *model, tab_nbr *nbr, int32_t precision,
+                           double *d_desc, void *stream);
+
 /* Per-kernel timing of tab_eam_eval with CUDA events recorded on the launching
  * stream (used by bench.py for the roofline figures; off by default).
  * tab_profile_read synchronises the device; ms[0..3] = mean milliseconds of the

@@ -1,0 +1,232 @@
+"""
+oracle/atomic.py -- TEST INFRASTRUCTURE (see oracle/__init__.py).
+
+torch-CPU restatement of the reference's symmetry-function AtomicNN:
+  * cutoffs        nn/cutoff.py:20-85
+  * G2             nn/atomic/sf.py:79-119
+  * triples        transformer/universal.py:115-233 (symmetric: all j<k pairs of a
+                   centre's neighbour row; r_jk from D_ik - D_ij, :213-218)
+  * G4             nn/atomic/sf.py:121-182
+  * feature order  per centre element c: G2 blocks of the radial terms
+                   [cc, c-x1, ...] (utils.py:262-273), then G4 blocks of the angular
+                   terms c+(sorted pair), pairs enumerated j<=k (utils.py:274-286);
+                   inside a block tau runs over sklearn ParameterGrid order
+                   (eta outer / omega inner; beta outer, gamma, zeta inner)
+  * min-max        nn/atomic/atomic.py:157-195
+  * MLP            nn/convolutional.py:257-290 (1x1 conv = per-atom dense layers,
+                   ResNet add when consecutive widths match), nn/utils.py:39-74
+  * energy         nn/atomic/atomic.py:270-302
+Pinned to test_files/amp_Pd3O2.npz (nn/atomic/tests/test_sf.py:666-691).
+"""
+import math
+
+import numpy as np
+import torch
+
+from oracle.eam import EPS, evaluate
+
+
+def cosine_cutoff(r, rc):
+    z = torch.clamp(r / rc, max=1.0)
+    return 0.5 * (torch.cos(z * math.pi) + 1.0)
+
+
+def polynomial_cutoff(r, rc, gamma=5.0):
+    d = torch.clamp(r / rc, max=1.0)
+    return 1.0 + gamma * d ** (gamma + 1.0) - (gamma + 1.0) * d ** gamma
+
+
+def _cut(name):
+    return cosine_cutoff if name == 'cosine' else polynomial_cutoff
+
+
+def radial_grid(eta, omega):
+    return [(e, o) for e in eta for o in omega]
+
+
+def angular_grid(beta, gamma, zeta):
+    return [(b, g, z) for b in beta for g in gamma for z in zeta]
+
+
+def kbody_terms(elements, angular):
+    """utils.py:237-290 (symmetric)."""
+    elements = sorted(set(elements))
+    per = {e: [e + e] for e in elements}
+    for a in elements:
+        for b in elements:
+            if a != b:
+                per[a].append(a + b)
+    if angular:
+        for c in elements:
+            for j, a in enumerate(elements):
+                for b in elements[j:]:
+                    per[c].append(c + ''.join(sorted([a, b])))
+    return per
+
+
+def build_triples(i, n_atoms):
+    """All (p, q) row-position pairs with p < q inside each centre's row
+    (universal.py:176-232, symmetric).  `i` must be sorted by centre."""
+    counts = np.bincount(i, minlength=n_atoms)
+    starts = np.concatenate(([0], np.cumsum(counts)[:-1]))
+    ps, qs = [], []
+    for a in range(n_atoms):
+        n = counts[a]
+        if n < 2:
+            continue
+        p, q = np.triu_indices(n, k=1)
+        ps.append(p + starts[a])
+        qs.append(q + starts[a])
+    if not ps:
+        return np.zeros(0, np.int64), np.zeros(0, np.int64)
+    return np.concatenate(ps), np.concatenate(qs)
+
+
+def descriptors(elements, types, R, cell, i, j, S, rc, acut=None, angular=True,
+                eta=(0.05, 4.0, 20.0, 80.0), omega=(0.0,), beta=(0.005,),
+                gamma=(1.0, -1.0), zeta=(1.0, 4.0), cutoff='cosine',
+                ang_list=None):
+    """Returns G [n_atoms, D] (row = the centre's own feature layout).
+    (i, j, S) = radial list (rc); ang_list = (i, j, S) for acut if different."""
+    elements = sorted(elements)
+    n = R.shape[0]
+    nel = len(elements)
+    dtype = R.dtype
+    fcut = _cut(cutoff)
+    rgrid = radial_grid(eta, omega)
+    agrid = angular_grid(beta, gamma, zeta)
+    n_r, n_a = len(rgrid), len(agrid)
+    D = nel * n_r + (nel * (nel + 1) // 2 * n_a if angular else 0)
+    ti = torch.as_tensor(i)
+    tj = torch.as_tensor(j)
+    tS = torch.as_tensor(S).to(dtype)
+    Dij = R[tj] - R[ti] + tS @ cell
+    rij = torch.sqrt((Dij * Dij).sum(-1) + EPS[dtype])
+    G = torch.zeros(n, D, dtype=dtype)
+    types_t = torch.as_tensor(types)
+    ci, cj = types_t[ti], types_t[tj]
+    # radial term index inside kbody_terms_for_element[centre]
+    tidx = torch.where(ci == cj, torch.zeros_like(ci), cj - (cj > ci).long() + 1)
+    fc = fcut(rij, rc)
+    for tau, (e, o) in enumerate(rgrid):
+        v = torch.exp(-e * (rij - o) ** 2 / rc ** 2) * fc
+        col = tidx * n_r + tau
+        G = G.index_put((ti, col), v, accumulate=True)
+    if not angular:
+        return G
+    acut = acut if acut is not None else rc
+    if ang_list is not None:
+        ai, aj, aS = ang_list
+        tai, taj = torch.as_tensor(ai), torch.as_tensor(aj)
+        Da = R[taj] - R[tai] + torch.as_tensor(aS).to(dtype) @ cell
+    else:
+        ai, tai, taj, Da = i, ti, tj, Dij
+    p, q = build_triples(np.asarray(ai), n)
+    p, q = torch.as_tensor(p), torch.as_tensor(q)
+    centre = tai[p]
+    D1, D2 = Da[p], Da[q]
+    D3 = D2 - D1
+    r1 = torch.sqrt((D1 * D1).sum(-1) + EPS[dtype])
+    r2 = torch.sqrt((D2 * D2).sum(-1) + EPS[dtype])
+    r3 = torch.sqrt((D3 * D3).sum(-1) + EPS[dtype])
+    sj, sk = types_t[taj[p]], types_t[taj[q]]
+    lo, hi = torch.minimum(sj, sk), torch.maximum(sj, sk)
+    # index of the sorted pair (lo <= hi) in the j<=k enumeration
+    pair_idx = lo * nel - lo * (lo - 1) // 2 + (hi - lo)
+    z = (r1 * r1 + r2 * r2 + r3 * r3) / acut ** 2
+    upper = r1 * r1 + r2 * r2 - r3 * r3
+    lower = 2.0 * r1 * r2
+    theta = torch.where(lower == 0, torch.zeros_like(lower), upper / lower)
+    fc3 = fcut(r1, acut) * (fcut(r2, acut) * fcut(r3, acut))
+    base = nel * n_r
+    for tau, (b, g, zt) in enumerate(agrid):
+        outer = 2.0 ** (1.0 - zt)
+        v = torch.pow(1.0 + g * theta, zt) * (torch.exp(-b * z) * fc3) * outer
+        col = base + pair_idx * n_a + tau
+        G = G.index_put((centre, col), v, accumulate=True)
+    return G
+
+
+def activation(name):
+    name = name.lower()
+    if name == 'softplus':
+        return torch.nn.functional.softplus
+    if name == 'tanh':
+        return torch.tanh
+    if name == 'relu':
+        return torch.relu
+    if name == 'leaky_relu':
+        return lambda x: torch.nn.functional.leaky_relu(x, 0.2)   # tf default alpha
+    if name == 'sigmoid':
+        return torch.sigmoid
+    if name == 'softsign':
+        return torch.nn.functional.softsign
+    if name == 'elu':
+        return torch.nn.functional.elu
+    if name == 'squareplus':
+        return lambda x: 0.5 * (x + torch.sqrt(x * x + 4.0))
+    raise ValueError(name)
+
+
+def mlp(x, weights, biases, act, use_resnet_dt=False, out_bias=None):
+    """convolutional.py:257-290.  weights[k]: [in, out]; last = output layer."""
+    fn = activation(act)
+    h = x
+    nh = len(weights) - 1
+    for k in range(nh):
+        y = fn(h @ weights[k] + biases[k])
+        if k and use_resnet_dt and weights[k].shape[1] == weights[k - 1].shape[1]:
+            h = y + h
+        else:
+            h = y
+    out = h @ weights[nh]
+    if out_bias is not None:
+        out = out + out_bias
+    return out[:, 0]
+
+
+def atomic_evaluate(elements, symbols, positions, cell, pbc, rc, params, sf=None,
+                    acut=None, angular=True, dtype=torch.float64, hessian=False,
+                    minmax=None):
+    """Full oracle call for AtomicNN + SymmetryFunction.
+    params[el] = dict(weights=[...], biases=[...], out_bias=float or None,
+                      activation=str, use_resnet_dt=bool)
+    minmax[el] = (xlo, xhi) arrays or None."""
+    from oracle import neighbor
+    elements = sorted(elements)
+    sf = dict(sf or {})
+    positions = np.asarray(positions, dtype=np.float64)
+    cell = np.asarray(cell, dtype=np.float64).reshape(3, 3)
+    nl = neighbor.neighbor_list(positions, cell, pbc, rc)
+    ang = None
+    acut_eff = acut if acut is not None else rc
+    if angular and abs(acut_eff - rc) > 5e-3:
+        ang = neighbor.neighbor_list(positions, cell, pbc, acut_eff)[:3]
+    types = np.array([elements.index(s) for s in symbols])
+
+    def energy_fn(R, h):
+        G = descriptors(elements, types, R, h, nl[0], nl[1], nl[2], rc, acut_eff,
+                        angular, ang_list=ang, **sf)
+        e_atom = torch.zeros(R.shape[0], dtype=R.dtype)
+        for a, el in enumerate(elements):
+            sel = torch.nonzero(torch.as_tensor(types == a)).reshape(-1)
+            if not sel.numel():
+                continue
+            x = G[sel]
+            if minmax and minmax.get(el) is not None:
+                xlo, xhi = [torch.as_tensor(v, dtype=R.dtype) for v in minmax[el]]
+                den = xhi - xlo
+                x = torch.where(den == 0, torch.zeros_like(x), (xhi - x) / den)
+            p = params[el]
+            W = [torch.as_tensor(w, dtype=R.dtype) for w in p['weights']]
+            b = [None if v is None else torch.as_tensor(v, dtype=R.dtype)
+                 for v in p['biases']]
+            ob = p.get('out_bias')
+            ob = None if ob is None else torch.as_tensor(ob, dtype=R.dtype)
+            y = mlp(x, W, b, p.get('activation', 'softplus'),
+                    p.get('use_resnet_dt', False), ob)
+            e_atom = e_atom.index_add(0, sel, y)
+        return e_atom.sum(), e_atom
+
+    return evaluate(energy_fn, torch.tensor(positions, dtype=dtype),
+                    torch.tensor(cell, dtype=dtype), hessian=hessian)

@@ -52,6 +52,28 @@ def make_fn(kind, params=(), aux=0):
     return fn
 
 
+CUTOFFS = {'cosine': 0, 'polynomial': 1}
+ACTIVATIONS = {'softplus': 0, 'tanh': 1, 'relu': 2, 'leaky_relu': 3, 'sigmoid': 4,
+               'softsign': 5, 'elu': 6, 'squareplus': 7}
+_DP = C.POINTER(C.c_double)
+
+
+class TabSfDesc(C.Structure):
+    _fields_ = [('n_el', C.c_int32), ('cutoff', C.c_int32), ('angular', C.c_int32),
+                ('n_r', C.c_int32), ('n_a', C.c_int32),
+                ('rc', C.c_double), ('acut', C.c_double),
+                ('eta', _DP), ('omega', _DP), ('beta', _DP), ('gamma', _DP),
+                ('zeta', _DP)]
+
+
+class TabMlpDesc(C.Structure):
+    _fields_ = [('n_layers', C.c_int32), ('sizes', C.c_int32 * 9),
+                ('activation', C.c_int32), ('use_resnet_dt', C.c_int32),
+                ('output_bias', C.c_int32),
+                ('weights', _DP * 8), ('biases', _DP * 8),
+                ('xlo', _DP), ('xhi', _DP)]
+
+
 class TabError(RuntimeError):
     """A libtab200 call returned a non-zero status."""
 
@@ -66,6 +88,8 @@ EXPORTS = [
     'tab_nbr_sizes', 'tab_nbr_counts', 'tab_nbr_export',
     'tab_eam_create', 'tab_model_free', 'tab_eam_eval', 'tab_eam_pass1',
     'tab_eam_pass2', 'tab_eam_compute_host',
+    'tab_atomic_create', 'tab_atomic_free', 'tab_atomic_dim', 'tab_atomic_eval',
+    'tab_atomic_descriptors',
     'tab_launch_count', 'tab_launch_count_reset',
     'tab_profile_enable', 'tab_profile_read',
 ]
@@ -108,6 +132,11 @@ def lib():
     L.tab_eam_compute_host.argtypes = [vp, vp, i32, i32, vp, vp,
                                        C.POINTER(dbl), C.POINTER(i32), dbl, i32,
                                        vp, vp, vp, vp, vp]
+    L.tab_atomic_create.argtypes = [pp, C.POINTER(TabSfDesc), C.POINTER(TabMlpDesc)]
+    L.tab_atomic_free.argtypes = [vp]
+    L.tab_atomic_dim.argtypes = [vp]
+    L.tab_atomic_eval.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]
+    L.tab_atomic_descriptors.argtypes = [vp, vp, i32, vp, vp]
     L.tab_profile_enable.argtypes = [i32]
     L.tab_profile_read.argtypes = [C.POINTER(dbl), C.POINTER(i32)]
     L.tab_launch_count.restype = i64
@@ -289,3 +318,82 @@ def profile_read():
     calls = C.c_int32()
     check(lib().tab_profile_read(ms, C.byref(calls)), 'tab_profile_read')
     return list(ms), int(calls.value)
+
+
+class AtomicModel:
+    """Owner of one `tab_atomic` handle (symmetry functions + per-element MLPs).
+
+    radial  : list of (eta, omega);  angular : list of (beta, gamma, zeta) or None
+    mlps    : per element (sorted order) dict(weights=[np [in,out]...],
+              biases=[np [out] or None...], activation=str, use_resnet_dt=bool,
+              output_bias=bool, xlo=np or None, xhi=np or None)
+    """
+
+    def __init__(self, n_el, rc, acut, radial, angular, cutoff, mlps):
+        self._keep = []
+
+        def darr(vals):
+            a = np.ascontiguousarray(np.asarray(vals, dtype=np.float64).reshape(-1))
+            self._keep.append(a)
+            return a.ctypes.data_as(_DP)
+
+        sf = TabSfDesc()
+        sf.n_el = n_el
+        sf.cutoff = CUTOFFS[cutoff]
+        sf.angular = 1 if angular else 0
+        sf.n_r = len(radial)
+        sf.n_a = len(angular) if angular else 0
+        sf.rc = float(rc)
+        sf.acut = float(acut if acut is not None else rc)
+        sf.eta = darr([r[0] for r in radial])
+        sf.omega = darr([r[1] for r in radial])
+        ang = angular or []
+        sf.beta = darr([a[0] for a in ang] or [0.0])
+        sf.gamma = darr([a[1] for a in ang] or [0.0])
+        sf.zeta = darr([a[2] for a in ang] or [0.0])
+        descs = (TabMlpDesc * n_el)()
+        for e, m in enumerate(mlps):
+            d = descs[e]
+            W = m['weights']
+            d.n_layers = len(W)
+            if len(W) > 8:
+                raise ValueError("at most 8 layers (hidden + output) are supported")
+            for k, w in enumerate(W):
+                w = np.asarray(w, dtype=np.float64)
+                d.sizes[k] = w.shape[0]
+                d.sizes[k + 1] = w.shape[1]
+                d.weights[k] = darr(w)
+                b = m['biases'][k] if k < len(m['biases']) else None
+                d.biases[k] = darr(b) if b is not None else None
+            d.activation = ACTIVATIONS[m.get('activation', 'softplus').lower()]
+            d.use_resnet_dt = int(bool(m.get('use_resnet_dt', False)))
+            d.output_bias = int(bool(m.get('output_bias', False)))
+            if m.get('xlo') is not None and m.get('xhi') is not None:
+                d.xlo = darr(m['xlo'])
+                d.xhi = darr(m['xhi'])
+        self._h = C.c_void_p()
+        check(lib().tab_atomic_create(C.byref(self._h), C.byref(sf), descs),
+              'tab_atomic_create')
+        self.dim = int(lib().tab_atomic_dim(self._h))
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().tab_atomic_free(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    def eval(self, nbr, precision=PRECISION_HIGH, energy=None, eatom=None,
+             forces=None, virial=None):
+        check(lib().tab_atomic_eval(self._h, nbr.handle, int(precision), _ptr(energy),
+                                    _ptr(eatom), _ptr(forces), _ptr(virial),
+                                    _stream()), 'tab_atomic_eval')
+
+    def descriptors(self, nbr, precision=PRECISION_HIGH):
+        import torch
+        out = torch.zeros((nbr.n, self.dim), dtype=torch.float64, device='cuda')
+        check(lib().tab_atomic_descriptors(self._h, nbr.handle, int(precision),
+                                           _ptr(out), _stream()),
+              'tab_atomic_descriptors')
+        return out

@@ -66,11 +66,17 @@ __host__ __device__ inline int floordiv(int a, int b) {
 // ---------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------
-__global__ void k_bin(int n, int n_owned, const double *__restrict__ pos, Grid g,
+__global__ void k_bin(int n, int n_owned, const double *__restrict__ pos,
+                      const int *__restrict__ types, Grid g,
                       int *__restrict__ cell_of, int *__restrict__ s0,
-                      uint32_t *__restrict__ cell_count) {
+                      uint32_t *__restrict__ cell_count,
+                      unsigned long long *__restrict__ stats) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (types) {
+        const int t = types[i];
+        if (t > 0) atomicMax(&stats[3], (unsigned long long)t);
+    }
     const double x = pos[3 * i] - g.origin[0], y = pos[3 * i + 1] - g.origin[1],
                  z = pos[3 * i + 2] - g.origin[2];
     int c[3], sh[3];
@@ -325,13 +331,25 @@ __device__ __forceinline__ void for_each_neighbor(
 __global__ void __launch_bounds__(128)
 k_count(int n, Grid g, ExactCtx x, const int *__restrict__ cell_of,
         const Atom4 *__restrict__ atoms, const uint4 *__restrict__ ext_tab,
-        int *__restrict__ counts,
+        const uint8_t *__restrict__ types_ext, int n_types,
+        int *__restrict__ counts, int *__restrict__ tcounts,
         uint32_t *__restrict__ slice_w, unsigned long long *__restrict__ stats) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     int cnt = 0;
     if (idx < n) {
         const int rank = cell_of[x.perm[idx]];
-        for_each_neighbor(g, x, idx, rank, atoms, ext_tab, [&](int) { ++cnt; });
+        if (n_types > 1) {
+            int tc[TAB_MAX_ELEMENTS];
+            for (int t = 0; t < n_types; ++t) tc[t] = 0;
+            for_each_neighbor(g, x, idx, rank, atoms, ext_tab, [&](int j) {
+                ++cnt;
+                ++tc[types_ext[j]];
+            });
+            for (int t = 0; t < n_types; ++t) tcounts[(size_t)idx * n_types + t] = tc[t];
+        } else {
+            for_each_neighbor(g, x, idx, rank, atoms, ext_tab, [&](int) { ++cnt; });
+            tcounts[idx] = cnt;
+        }
         counts[idx] = cnt;
     }
     // slice width = warp max, nij = sum, nnl_max = max
@@ -351,7 +369,8 @@ k_count(int n, Grid g, ExactCtx x, const int *__restrict__ cell_of,
 __global__ void __launch_bounds__(128)
 k_fill(int n, Grid g, ExactCtx x, const int *__restrict__ cell_of,
        const Atom4 *__restrict__ atoms, const uint8_t *__restrict__ types_ext,
-       const uint4 *__restrict__ ext_tab,
+       const uint4 *__restrict__ ext_tab, int n_types,
+       const int *__restrict__ tcounts,
        const uint32_t *__restrict__ slice_w,
        const uint32_t *__restrict__ slice_ptr, uint32_t *__restrict__ col) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -361,11 +380,26 @@ k_fill(int n, Grid g, ExactCtx x, const int *__restrict__ cell_of,
     uint32_t k = 0;
     if (idx < n) {
         const int rank = cell_of[x.perm[idx]];
-        for_each_neighbor(g, x, idx, rank, atoms, ext_tab, [&](int j) {
-            base[(size_t)k * 32u] =
-                (uint32_t)j | ((uint32_t)types_ext[j] << TAB_COL_TYPE_SHIFT);
-            ++k;
-        });
+        if (n_types > 1) {
+            // rows are grouped by neighbour species (stable inside a species)
+            uint32_t off[TAB_MAX_ELEMENTS];
+            uint32_t run = 0;
+            for (int t = 0; t < n_types; ++t) {
+                off[t] = run;
+                run += (uint32_t)tcounts[(size_t)idx * n_types + t];
+            }
+            for_each_neighbor(g, x, idx, rank, atoms, ext_tab, [&](int j) {
+                const uint32_t t = types_ext[j];
+                base[(size_t)(off[t]++) * 32u] = (uint32_t)j | (t << TAB_COL_TYPE_SHIFT);
+            });
+            k = run;
+        } else {
+            for_each_neighbor(g, x, idx, rank, atoms, ext_tab, [&](int j) {
+                base[(size_t)k * 32u] =
+                    (uint32_t)j | ((uint32_t)types_ext[j] << TAB_COL_TYPE_SHIFT);
+                ++k;
+            });
+        }
     }
     const uint32_t w = slice_w[s];
     for (; k < w; ++k) base[(size_t)k * 32u] = TAB_COL_PAD;
@@ -411,6 +445,52 @@ __global__ void k_export(int n, int n_loc, const int *__restrict__ perm,
         out_S[3 * o + 0] = Sa - ja + ia;
         out_S[3 * o + 1] = Sb - jb + ib;
         out_S[3 * o + 2] = Sc - jc + ic;
+    }
+}
+
+// rev[entry of (i -> j, S)] = position inside the row of owner(j) of the reverse
+// pair (owner(j) -> image of i with shift -S).  Needed by models whose per-pair
+// gradient g_p = dE_i/dD_p is not symmetric in the pair (symmetry functions):
+//   F_i = sum_{p in row i} g_p - sum_{p in row i} g_rev(p).
+#define TAB_REV_NONE 0xFFFFFFFFu
+__global__ void __launch_bounds__(128)
+k_build_reverse(int n, int n_loc, const int *__restrict__ counts,
+                const uint32_t *__restrict__ slice_ptr,
+                const uint32_t *__restrict__ col, const int *__restrict__ ghost_owner,
+                const int *__restrict__ ghost_S, uint32_t *__restrict__ rev) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const size_t base = (size_t)slice_ptr[idx >> 5] * 32u + (idx & 31);
+    const int cnt = counts[idx];
+    const int zero = tab_pack_shift(0, 0, 0);
+    for (int k = 0; k < cnt; ++k) {
+        const int j = (int)(col[base + (size_t)k * 32u] & TAB_COL_IDX_MASK);
+        int o = j, S = zero;
+        if (j >= n_loc) {
+            o = ghost_owner[j - n_loc];
+            S = ghost_S[j - n_loc];
+        }
+        uint32_t found = TAB_REV_NONE;
+        if (o < n) {
+            int a, b, c;
+            tab_unpack_shift(S, a, b, c);
+            const int want = tab_pack_shift(-a, -b, -c);
+            const size_t obase = (size_t)slice_ptr[o >> 5] * 32u + (o & 31);
+            const int ocnt = counts[o];
+            for (int q = 0; q < ocnt; ++q) {
+                const int e = (int)(col[obase + (size_t)q * 32u] & TAB_COL_IDX_MASK);
+                int eo = e, eS = zero;
+                if (e >= n_loc) {
+                    eo = ghost_owner[e - n_loc];
+                    eS = ghost_S[e - n_loc];
+                }
+                if (eo == idx && eS == want) {
+                    found = (uint32_t)q;
+                    break;
+                }
+            }
+        }
+        rev[base + (size_t)k * 32u] = found;
     }
 }
 
@@ -509,7 +589,8 @@ extern "C" int tab_nbr_free(tab_nbr *nbr) {
                       &nbr->cell_count, &nbr->cell_start, &nbr->cell_fill,
                       &nbr->ext_tab, &nbr->gcount, &nbr->gstart,
                       &nbr->slice_w, &nbr->slice_ptr, &nbr->col, &nbr->scan_tmp,
-                      &nbr->stats, &nbr->row_ptr, &nbr->rho, &nbr->partial, &nbr->adp};
+                      &nbr->stats, &nbr->row_ptr, &nbr->rho, &nbr->partial, &nbr->adp,
+                      &nbr->tcounts, &nbr->rev};
     for (DevBuf *b : bufs) b->release();
     delete nbr;
     return TAB_OK;
@@ -578,9 +659,9 @@ extern "C" int tab_nbr_build_dd(tab_nbr *nbr, int32_t n_owned, int32_t n_halo,
     TAB_CUDA(cudaMemsetAsync(nbr->cell_fill.p, 0, sizeof(uint32_t) * slots2, st));
     TAB_CUDA(cudaMemsetAsync(d_stats, 0, 4 * sizeof(unsigned long long), st));
 
-    k_bin<<<nblocks(n_loc, 256), 256, 0, st>>>(n_loc, n, d_pos, g, nbr->cell_of.as<int>(),
-                                               nbr->s0.as<int>(),
-                                               nbr->cell_count.as<uint32_t>());
+    k_bin<<<nblocks(n_loc, 256), 256, 0, st>>>(n_loc, n, d_pos, d_types, g,
+                                               nbr->cell_of.as<int>(), nbr->s0.as<int>(),
+                                               nbr->cell_count.as<uint32_t>(), d_stats);
     TAB_LAUNCH_CHECK();
     TAB_TRY(tab_scan_exclusive_u32(nbr->cell_count.as<uint32_t>(),
                                    nbr->cell_start.as<uint32_t>(), slots2, nullptr,
@@ -603,10 +684,16 @@ extern "C" int tab_nbr_build_dd(tab_nbr *nbr, int32_t n_owned, int32_t n_halo,
     TAB_TRY(tab_scan_exclusive_u32(nbr->gcount.as<uint32_t>(),
                                    nbr->gstart.as<uint32_t>(), g.n_ecells, d_stats + 2,
                                    nbr->scan_tmp, st));
-    unsigned long long n_ghost = 0;
-    TAB_CUDA(cudaMemcpyAsync(&n_ghost, d_stats + 2, sizeof(n_ghost),
-                             cudaMemcpyDeviceToHost, st));
+    unsigned long long two[2] = {0, 0};   // [n_ghost, max type]
+    TAB_CUDA(cudaMemcpyAsync(two, d_stats + 2, sizeof(two), cudaMemcpyDeviceToHost, st));
     TAB_CUDA(cudaStreamSynchronize(st));
+    const unsigned long long n_ghost = two[0];
+    nbr->n_types = (int)two[1] + 1;
+    nbr->has_rev = false;
+    if (nbr->n_types > TAB_MAX_ELEMENTS) {
+        tab_set_error("element index %d exceeds the supported maximum", nbr->n_types - 1);
+        return TAB_EINVAL;
+    }
     if ((unsigned long long)n_loc + n_ghost > TAB_COL_IDX_MASK) {
         tab_set_error("owned + ghost atoms exceed the 28-bit index space");
         return TAB_EUNSUPPORTED;
@@ -640,9 +727,11 @@ extern "C" int tab_nbr_build_dd(tab_nbr *nbr, int32_t n_owned, int32_t n_halo,
     x.ghost_S = nbr->ghost_S.as<int>();
     x.n_loc = n_loc;
     const int nthreads = nbr->n_slices * 32;
+    TAB_TRY(nbr->tcounts.ensure(sizeof(int) * (size_t)n * nbr->n_types));
     k_count<<<nblocks(nthreads, 128), 128, 0, st>>>(
         n, g, x, nbr->cell_of.as<int>(), nbr->atoms.as<Atom4>(),
-        nbr->ext_tab.as<uint4>(), nbr->counts.as<int>(), nbr->slice_w.as<uint32_t>(),
+        nbr->ext_tab.as<uint4>(), nbr->types_ext.as<uint8_t>(), nbr->n_types,
+        nbr->counts.as<int>(), nbr->tcounts.as<int>(), nbr->slice_w.as<uint32_t>(),
         d_stats);
     TAB_LAUNCH_CHECK();
     TAB_TRY(tab_scan_exclusive_u32(nbr->slice_w.as<uint32_t>(),
@@ -661,9 +750,9 @@ extern "C" int tab_nbr_build_dd(tab_nbr *nbr, int32_t n_owned, int32_t n_halo,
     TAB_TRY(nbr->col.ensure(sizeof(uint32_t) * 32 * (size_t)(nbr->ell_rows + 1)));
     k_fill<<<nblocks(nthreads, 128), 128, 0, st>>>(
         n, g, x, nbr->cell_of.as<int>(), nbr->atoms.as<Atom4>(),
-        nbr->types_ext.as<uint8_t>(), nbr->ext_tab.as<uint4>(),
-        nbr->slice_w.as<uint32_t>(), nbr->slice_ptr.as<uint32_t>(),
-        nbr->col.as<uint32_t>());
+        nbr->types_ext.as<uint8_t>(), nbr->ext_tab.as<uint4>(), nbr->n_types,
+        nbr->tcounts.as<int>(), nbr->slice_w.as<uint32_t>(),
+        nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>());
     TAB_LAUNCH_CHECK();
     nbr->built = true;
     return TAB_OK;
@@ -732,5 +821,18 @@ extern "C" int tab_nbr_export(const tab_nbr *cnbr, int32_t *d_i, int32_t *d_j,
         nbr->ghost_owner.as<int>(), nbr->ghost_S.as<int>(),
         nbr->row_ptr.as<uint32_t>(), d_i, d_j, d_S);
     TAB_LAUNCH_CHECK();
+    return TAB_OK;
+}
+
+// internal: make sure the reverse-pair index exists (lazy, once per build)
+int tab_nbr_ensure_reverse(tab_nbr *nbr, cudaStream_t st) {
+    if (nbr->has_rev) return TAB_OK;
+    TAB_TRY(nbr->rev.ensure(sizeof(uint32_t) * 32 * (size_t)(nbr->ell_rows + 1)));
+    k_build_reverse<<<nblocks(nbr->n, 128), 128, 0, st>>>(
+        nbr->n, nbr->n_loc, nbr->counts.as<int>(), nbr->slice_ptr.as<uint32_t>(),
+        nbr->col.as<uint32_t>(), nbr->ghost_owner.as<int>(), nbr->ghost_S.as<int>(),
+        nbr->rev.as<uint32_t>());
+    TAB_LAUNCH_CHECK();
+    nbr->has_rev = true;
     return TAB_OK;
 }

@@ -1,0 +1,830 @@
+// sf.cu -- Behler symmetry functions (G2 + G4) + per-element atomic MLPs:
+// energies, forces and virial of the reference's AtomicNN.
+//
+// Replaces, for the reference:
+//   nn/atomic/sf.py:79-119     G2_{i,T,tau} = sum_{p in T} exp(-eta (r-omega)^2/rc^2) fc(r)
+//   nn/atomic/sf.py:121-182    G4_{i,T,tau} = 2^{1-zeta} sum_{j<k in T} (1+gamma cos)^zeta
+//                              exp(-beta (rij^2+rik^2+rjk^2)/acut^2) fc fc fc
+//   transformer/universal.py:115-233  triple enumeration (host Python loops) and the
+//                              dense [12, Ta, N, nnl, ij2k] tensors -- never built here
+//   nn/cutoff.py:20-85         cosine / polynomial cutoffs
+//   nn/atomic/atomic.py:157-302, nn/convolutional.py:257-290   min-max + 1x1-conv MLP
+//   nn/basic.py:276-331        F = -dE/dR, virial (TF autograd -> analytic backward)
+//
+// Structure (all atomic-free, deterministic):
+//   k_sf_forward   warp per centre atom; its neighbour row (species-sorted) is staged
+//                  in shared memory; lanes stride over neighbours (G2) and over the
+//                  second index of the j<k pairs (G4); warp-shuffle reduction.
+//   k_mlp          warp per atom: forward + backward through the element's MLP,
+//                  giving E_i and dE_i/dG_i.
+//   k_sf_backward  warp per centre atom: E_i depends on the D vectors of row i only,
+//                  so g_p = dE_i/dD_p is computed for every entry p of the row by the
+//                  lane that owns p (each unordered triple is visited from both of
+//                  its legs -> no reduction, no atomics); g_p is stored per entry,
+//                  sum_p g_p and sum_p g_p (x) D_p are accumulated on the fly.
+//   k_sf_collect   thread per atom: F_i = sum_p g_p - sum_p g_rev(p)  (reverse-pair
+//                  index built once per list, nbr.cu:k_build_reverse).
+#include "potentials.cuh"
+
+#define SF_MAX_R 32      // radial parameter sets
+#define SF_MAX_A 32      // angular parameter sets
+#define SF_WARPS 4       // warps (= atoms) per block
+#define MLP_MAX_LAYERS 8
+#define MLP_MAX_WIDTH 256
+
+struct SfDev {
+    int n_el, n_r, n_a, angular, cutoff;   // cutoff: 0 cosine, 1 polynomial(gamma=5)
+    int d_r, dim;                          // d_r = n_el*n_r ; dim = full descriptor length
+    double rc, acut;
+    double eta[SF_MAX_R], omega[SF_MAX_R];
+    double beta[SF_MAX_A], gamma[SF_MAX_A], zeta[SF_MAX_A];
+};
+
+struct MlpDev {
+    int n_layers;                          // hidden layers + output layer
+    int act;                               // activation id
+    int resnet, has_out_bias, has_minmax;
+    int in[MLP_MAX_LAYERS], out[MLP_MAX_LAYERS];
+    long long w_off[MLP_MAX_LAYERS], b_off[MLP_MAX_LAYERS];   // into the blob
+    long long xlo_off, xhi_off;
+};
+
+struct tab_atomic {
+    SfDev sf;
+    int n_el;
+    MlpDev mlp[TAB_MAX_ELEMENTS];
+    DevBuf blob;        // double: weights, biases, xlo, xhi of every element + MlpDev table
+    size_t mlp_table_off = 0;   // offset (in doubles) of the MlpDev table inside blob
+    DevBuf G, dEdG, eat, gvec, fown;
+};
+
+// ---------------------------------------------------------------------------
+// cutoff functions: value and derivative  (nn/cutoff.py:20-85)
+// ---------------------------------------------------------------------------
+template <typename Real>
+__device__ __forceinline__ void cutoff_fn(int kind, Real r, Real rc, Real &f, Real &df) {
+    if (r >= rc) {
+        f = Real(0);
+        df = Real(0);
+        return;
+    }
+    const Real x = r / rc;
+    if (kind == 0) {
+        const Real a = x * Real(3.14159265358979323846);
+        f = Real(0.5) * (cos(a) + Real(1));
+        df = Real(-0.5) * sin(a) * Real(3.14159265358979323846) / rc;
+    } else {
+        const Real x2 = x * x, x4 = x2 * x2, x5 = x4 * x;
+        f = Real(1) + Real(5) * x5 * x - Real(6) * x5;        // 1 + g x^(g+1) - (g+1) x^g, g=5
+        df = (Real(30) * x5 - Real(30) * x4) / rc;
+    }
+}
+
+template <typename Real>
+__device__ __forceinline__ Real powz(Real base, Real z, Real &dpow) {
+    // base^z and d/dbase; integer exponents by multiplication (sf.py uses pow)
+    const int zi = (int)z;
+    if ((Real)zi == z && zi >= 1 && zi <= 16) {
+        Real p1 = Real(1);                     // base^(z-1)
+        for (int k = 1; k < zi; ++k) p1 *= base;
+        dpow = z * p1;
+        return p1 * base;
+    }
+    const Real p = pow(base, z);
+    dpow = (base != Real(0)) ? z * p / base : Real(0);
+    return p;
+}
+
+// shared-memory row layout per warp: 8 doubles per neighbour
+//   0..2 D, 3 r, 4 fc(r; acut), 5 dfc(r; acut)/dr, 6 type (as double), 7 unused
+#define ROW_W 8
+
+template <typename Real>
+__device__ __forceinline__ int stage_row(const SfDev &sf, int idx, int lane,
+                                         const Atom4 *__restrict__ atoms,
+                                         const int *__restrict__ counts,
+                                         const uint32_t *__restrict__ slice_ptr,
+                                         const uint32_t *__restrict__ col,
+                                         double *row) {
+    const Atom4 me = atoms[idx];
+    const int cnt = counts[idx];
+    const uint32_t *cp = col + ((size_t)slice_ptr[idx >> 5] * 32u + (idx & 31));
+    for (int k = lane; k < cnt; k += 32) {
+        const uint32_t c = cp[(size_t)k * 32u];
+        const Atom4 a = atoms[c & TAB_COL_IDX_MASK];
+        const double dx = a.x - me.x, dy = a.y - me.y, dz = a.z - me.z;
+        const Real fx = (Real)dx, fy = (Real)dy, fz = (Real)dz;
+        const Real r = sqrt(fx * fx + fy * fy + fz * fz + Math<Real>::eps());
+        Real f, df;
+        cutoff_fn<Real>(sf.cutoff, r, (Real)sf.acut, f, df);
+        double *e = row + (size_t)k * ROW_W;
+        e[0] = fx;
+        e[1] = fy;
+        e[2] = fz;
+        e[3] = r;
+        e[4] = f;
+        e[5] = df;
+        e[6] = (double)(c >> TAB_COL_TYPE_SHIFT);
+    }
+    __syncwarp();
+    return cnt;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+
+// index of the radial k-body term (centre ti, neighbour tj) inside the centre's
+// term list [cc, c-x1, ...] (utils.py:262-273)
+__device__ __forceinline__ int radial_term(int ti, int tj) {
+    return ti == tj ? 0 : tj - (tj > ti ? 1 : 0) + 1;
+}
+// index of the sorted pair (a <= b) in the j<=k enumeration (utils.py:274-286)
+__device__ __forceinline__ int pair_term(int a, int b, int nel) {
+    return a * nel - a * (a - 1) / 2 + (b - a);
+}
+
+// ---------------------------------------------------------------------------
+// forward: descriptors
+// ---------------------------------------------------------------------------
+template <typename Real>
+__global__ void __launch_bounds__(SF_WARPS * 32)
+k_sf_forward(int n, SfDev sf, int n_types, int row_cap,
+             const Atom4 *__restrict__ atoms, const uint8_t *__restrict__ types_ext,
+             const int *__restrict__ counts, const int *__restrict__ tcounts,
+             const uint32_t *__restrict__ slice_ptr, const uint32_t *__restrict__ col,
+             double *__restrict__ G) {
+    extern __shared__ __align__(16) double smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int idx = blockIdx.x * SF_WARPS + warp;
+    if (idx >= n) return;
+    double *row = smem + (size_t)warp * row_cap * ROW_W;
+    const int cnt = stage_row<Real>(sf, idx, lane, atoms, counts, slice_ptr, col, row);
+    const int ti = (int)types_ext[idx];
+    double *g = G + (size_t)idx * sf.dim;
+    const Real rc = (Real)sf.rc, rc2i = Real(1) / (rc * rc);
+    const Real ac2i = Real(1) / ((Real)sf.acut * (Real)sf.acut);
+    // species segments of the row
+    int seg[TAB_MAX_ELEMENTS + 1];
+    seg[0] = 0;
+    for (int t = 0; t < sf.n_el; ++t)
+        seg[t + 1] = seg[t] + (t < n_types ? tcounts[(size_t)idx * n_types + t] : 0);
+    (void)cnt;
+    // ---- G2
+    for (int t = 0; t < sf.n_el; ++t) {
+        const int term = radial_term(ti, t);
+        for (int tau = 0; tau < sf.n_r; ++tau) {
+            const Real eta = (Real)sf.eta[tau], om = (Real)sf.omega[tau];
+            Real acc = Real(0);
+            for (int k = seg[t] + lane; k < seg[t + 1]; k += 32) {
+                const Real r = (Real)row[k * ROW_W + 3];
+                Real f, df;
+                cutoff_fn<Real>(sf.cutoff, r, rc, f, df);
+                const Real d = r - om;
+                acc += Math<Real>::exp_(-eta * d * d * rc2i) * f;
+            }
+            const double tot = warp_sum((double)acc);
+            if (lane == 0) g[term * sf.n_r + tau] = tot;
+        }
+    }
+    if (!sf.angular) return;
+    // ---- G4: species pairs a <= b, neighbour pairs p < q
+    for (int a = 0; a < sf.n_el; ++a)
+        for (int b = a; b < sf.n_el; ++b) {
+            const int pt = pair_term(a, b, sf.n_el);
+            Real acc[SF_MAX_A];
+            for (int tau = 0; tau < sf.n_a; ++tau) acc[tau] = Real(0);
+            for (int p = seg[a]; p < seg[a + 1]; ++p) {
+                const double *ep = row + p * ROW_W;
+                const Real fp = (Real)ep[4];
+                if (fp == Real(0)) continue;
+                const Real px = (Real)ep[0], py = (Real)ep[1], pz = (Real)ep[2],
+                           r1 = (Real)ep[3];
+                const int q0 = (a == b) ? p + 1 : seg[b];
+                for (int q = q0 + lane; q < seg[b + 1]; q += 32) {
+                    const double *eq = row + q * ROW_W;
+                    const Real fq = (Real)eq[4];
+                    if (fq == Real(0)) continue;
+                    const Real r2 = (Real)eq[3];
+                    const Real jx = (Real)eq[0] - px, jy = (Real)eq[1] - py,
+                               jz = (Real)eq[2] - pz;
+                    const Real r3 = sqrt(jx * jx + jy * jy + jz * jz + Math<Real>::eps());
+                    Real f3, df3;
+                    cutoff_fn<Real>(sf.cutoff, r3, (Real)sf.acut, f3, df3);
+                    if (f3 == Real(0)) continue;
+                    const Real s2 = r1 * r1 + r2 * r2 + r3 * r3;
+                    const Real lower = Real(2) * r1 * r2;
+                    const Real ct = lower != Real(0)
+                                        ? (r1 * r1 + r2 * r2 - r3 * r3) / lower : Real(0);
+                    const Real fc = fp * (fq * f3);
+                    for (int tau = 0; tau < sf.n_a; ++tau) {
+                        Real dp;
+                        const Real z = (Real)sf.zeta[tau];
+                        const Real pw = powz<Real>(Real(1) + (Real)sf.gamma[tau] * ct, z, dp);
+                        acc[tau] += pw * (Math<Real>::exp_(-(Real)sf.beta[tau] * s2 * ac2i) * fc) *
+                                    exp2(Real(1) - z);
+                    }
+                }
+            }
+            for (int tau = 0; tau < sf.n_a; ++tau) {
+                const double tot = warp_sum((double)acc[tau]);
+                if (lane == 0) g[sf.d_r + pt * sf.n_a + tau] = tot;
+            }
+        }
+}
+
+// ---------------------------------------------------------------------------
+// MLP forward + backward, warp per atom  (convolutional.py:257-290)
+// ---------------------------------------------------------------------------
+template <typename Real>
+__device__ __forceinline__ Real act_fn(int kind, Real z, Real &d) {
+    switch (kind) {
+    case 0: {   // softplus
+        const Real e = exp(-fabs(z));
+        const Real sp = (z > Real(0) ? z : Real(0)) + log1p(e);
+        d = z >= Real(0) ? Real(1) / (Real(1) + e) : e / (Real(1) + e);
+        return sp;
+    }
+    case 1: {   // tanh
+        const Real t = tanh(z);
+        d = Real(1) - t * t;
+        return t;
+    }
+    case 2:     // relu
+        d = z > Real(0) ? Real(1) : Real(0);
+        return z > Real(0) ? z : Real(0);
+    case 3:     // leaky_relu (tf default alpha 0.2)
+        d = z > Real(0) ? Real(1) : Real(0.2);
+        return z > Real(0) ? z : Real(0.2) * z;
+    case 4: {   // sigmoid
+        const Real s = Real(1) / (Real(1) + exp(-z));
+        d = s * (Real(1) - s);
+        return s;
+    }
+    case 5: {   // softsign
+        const Real q = Real(1) + fabs(z);
+        d = Real(1) / (q * q);
+        return z / q;
+    }
+    case 6: {   // elu
+        const Real e = exp(z);
+        d = z > Real(0) ? Real(1) : e;
+        return z > Real(0) ? z : e - Real(1);
+    }
+    default: {  // 7 squareplus (nn/utils.py:39-47)
+        const Real s = sqrt(z * z + Real(4));
+        d = Real(0.5) * (Real(1) + z / s);
+        return Real(0.5) * (z + s);
+    }
+    }
+}
+
+// shared layout per warp: h[L][MLP_MAX_WIDTH] activations, dz[L][MLP_MAX_WIDTH]
+// activation derivatives, x[dim] inputs, delta/ delta2 scratch
+template <typename Real>
+__global__ void __launch_bounds__(SF_WARPS * 32)
+k_mlp(int n, int dim, const uint8_t *__restrict__ types_ext, const MlpDev *__restrict__ mlps,
+      const double *__restrict__ blob, const double *__restrict__ G,
+      double *__restrict__ eat, double *__restrict__ dEdG) {
+    extern __shared__ __align__(16) double smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int idx = blockIdx.x * SF_WARPS + warp;
+    if (idx >= n) return;
+    const MlpDev &M = mlps[types_ext[idx]];
+    const int L = M.n_layers;        // last one = output layer (no activation)
+    const int stride = MLP_MAX_WIDTH;
+    double *base = smem + (size_t)warp * ((2 * MLP_MAX_LAYERS + 2) * stride);
+    double *h = base;                               // [L+1][stride] (h[0] = x)
+    double *dz = base + (MLP_MAX_LAYERS + 1) * stride;   // [L][stride]
+    double *dl = dz + MLP_MAX_LAYERS * stride;           // delta scratch [stride]
+    const double *g = G + (size_t)idx * dim;
+    // input (+ min-max normalisation, atomic.py:157-195)
+    for (int k = lane; k < dim; k += 32) {
+        double x = g[k];
+        if (M.has_minmax) {
+            const double lo = blob[M.xlo_off + k], hi = blob[M.xhi_off + k];
+            const double den = hi - lo;
+            x = den != 0.0 ? (hi - x) / den : 0.0;
+        }
+        h[k] = x;
+    }
+    __syncwarp();
+    // forward
+    for (int l = 0; l < L; ++l) {
+        const double *W = blob + M.w_off[l];
+        const double *bb = blob + M.b_off[l];
+        const int ni = M.in[l], no = M.out[l];
+        const double *hin = h + (size_t)l * stride;
+        double *hout = h + (size_t)(l + 1) * stride;
+        const bool last = l == L - 1;
+        for (int o = lane; o < no; o += 32) {
+            Real z = (last && !M.has_out_bias) ? Real(0) : (Real)bb[o];
+            for (int k = 0; k < ni; ++k) z += (Real)hin[k] * (Real)W[(size_t)k * no + o];
+            if (last) {
+                hout[o] = z;
+            } else {
+                Real d;
+                Real y = act_fn<Real>(M.act, z, d);
+                dz[(size_t)l * stride + o] = d;
+                if (l > 0 && M.resnet && no == ni) y += (Real)hin[o];
+                hout[o] = y;
+            }
+        }
+        __syncwarp();
+    }
+    if (lane == 0) eat[idx] = h[(size_t)L * stride];
+    // backward: delta over the inputs of layer l+1
+    const int nlast = M.in[L - 1];
+    for (int k = lane; k < nlast; k += 32) dl[k] = blob[M.w_off[L - 1] + k];   // out width 1
+    __syncwarp();
+    for (int l = L - 2; l >= 0; --l) {
+        const double *W = blob + M.w_off[l];
+        const int ni = M.in[l], no = M.out[l];
+        const bool res = l > 0 && M.resnet && no == ni;
+        // dl holds dE/dh_{l+1} [no]; produce dE/dh_l [ni]
+        double *tmp = h + (size_t)(l + 1) * stride;     // reuse as scratch: a = dl * act'
+        for (int o = lane; o < no; o += 32) tmp[o] = dl[o] * dz[(size_t)l * stride + o];
+        __syncwarp();
+        double keep[MLP_MAX_WIDTH / 32];
+        int c = 0;
+        for (int k = lane; k < ni; k += 32, ++c) {
+            Real s = Real(0);
+            for (int o = 0; o < no; ++o) s += (Real)tmp[o] * (Real)W[(size_t)k * no + o];
+            keep[c] = (double)s + (res ? dl[k] : 0.0);
+        }
+        __syncwarp();
+        c = 0;
+        for (int k = lane; k < ni; k += 32, ++c) dl[k] = keep[c];
+        __syncwarp();
+    }
+    double *out = dEdG + (size_t)idx * dim;
+    for (int k = lane; k < dim; k += 32) {
+        double v = dl[k];
+        if (M.has_minmax) {
+            const double den = blob[M.xhi_off + k] - blob[M.xlo_off + k];
+            v = den != 0.0 ? -v / den : 0.0;
+        }
+        out[k] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// backward: per-entry gradients g_p = dE_i/dD_p
+// ---------------------------------------------------------------------------
+template <typename Real>
+__global__ void __launch_bounds__(SF_WARPS * 32)
+k_sf_backward(int n, SfDev sf, int n_types, int row_cap,
+              const Atom4 *__restrict__ atoms, const uint8_t *__restrict__ types_ext,
+              const int *__restrict__ counts, const int *__restrict__ tcounts,
+              const uint32_t *__restrict__ slice_ptr, const uint32_t *__restrict__ col,
+              const double *__restrict__ dEdG, double *__restrict__ gvec,
+              size_t plane, double *__restrict__ fown, double *__restrict__ partial) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ double red[SF_WARPS][6];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int idx = blockIdx.x * SF_WARPS + warp;
+    double vir[6] = {0, 0, 0, 0, 0, 0};
+    if (idx < n) {
+        double *row = smem + (size_t)warp * row_cap * ROW_W;
+        const int cnt = stage_row<Real>(sf, idx, lane, atoms, counts, slice_ptr, col, row);
+        const int ti = (int)types_ext[idx];
+        const double *c = dEdG + (size_t)idx * sf.dim;
+        const Real rc = (Real)sf.rc, rc2i = Real(1) / (rc * rc);
+        const Real ac2i = Real(1) / ((Real)sf.acut * (Real)sf.acut);
+        int seg[TAB_MAX_ELEMENTS + 1];
+        seg[0] = 0;
+        for (int t = 0; t < sf.n_el; ++t)
+            seg[t + 1] = seg[t] + (t < n_types ? tcounts[(size_t)idx * n_types + t] : 0);
+        const size_t ebase = (size_t)slice_ptr[idx >> 5] * 32u + (idx & 31);
+        double fx = 0, fy = 0, fz = 0;
+        for (int a = lane; a < cnt; a += 32) {
+            const double *ea = row + a * ROW_W;
+            const Real ax = (Real)ea[0], ay = (Real)ea[1], az = (Real)ea[2], ra = (Real)ea[3];
+            const Real fa = (Real)ea[4], dfa = (Real)ea[5];
+            const int ta = (int)ea[6];
+            // ---- G2 part
+            Real s_r = Real(0);                       // dE/dr_a
+            {
+                Real f, df;
+                cutoff_fn<Real>(sf.cutoff, ra, rc, f, df);
+                const int term = radial_term(ti, ta);
+                for (int tau = 0; tau < sf.n_r; ++tau) {
+                    const Real eta = (Real)sf.eta[tau], d = ra - (Real)sf.omega[tau];
+                    const Real e = Math<Real>::exp_(-eta * d * d * rc2i);
+                    s_r += (Real)c[term * sf.n_r + tau] *
+                           (e * df - Real(2) * eta * d * rc2i * e * f);
+                }
+            }
+            Real gx = s_r * ax / ra, gy = s_r * ay / ra, gz = s_r * az / ra;
+            // ---- G4 part: all other legs b of the triples (i; a, b)
+            if (sf.angular && fa != Real(0)) {
+                Real sa = Real(0);          // sum dV/dr_a
+                Real wx = 0, wy = 0, wz = 0;   // sum dV/dr_ab * (D_a - D_b)/r_ab
+                for (int b = 0; b < cnt; ++b) {
+                    if (b == a) continue;
+                    const double *eb = row + b * ROW_W;
+                    const Real fb = (Real)eb[4];
+                    if (fb == Real(0)) continue;
+                    const Real rb = (Real)eb[3];
+                    const Real jx = ax - (Real)eb[0], jy = ay - (Real)eb[1],
+                               jz = az - (Real)eb[2];
+                    const Real rab = sqrt(jx * jx + jy * jy + jz * jz + Math<Real>::eps());
+                    Real fab, dfab;
+                    cutoff_fn<Real>(sf.cutoff, rab, (Real)sf.acut, fab, dfab);
+                    if (fab == Real(0)) continue;
+                    const int tb = (int)eb[6];
+                    const int pt = ta <= tb ? pair_term(ta, tb, sf.n_el)
+                                            : pair_term(tb, ta, sf.n_el);
+                    const double *cc = c + sf.d_r + pt * sf.n_a;
+                    const Real s2 = ra * ra + rb * rb + rab * rab;
+                    const Real lower = Real(2) * ra * rb;
+                    const Real ct = lower != Real(0)
+                                        ? (ra * ra + rb * rb - rab * rab) / lower : Real(0);
+                    const Real dct_da = lower != Real(0) ? Real(1) / rb - ct / ra : Real(0);
+                    const Real dct_dab = lower != Real(0) ? -rab / (ra * rb) : Real(0);
+                    const Real F3 = fa * fb * fab;
+                    Real va = Real(0), vab = Real(0);
+                    for (int tau = 0; tau < sf.n_a; ++tau) {
+                        const Real z = (Real)sf.zeta[tau], gm = (Real)sf.gamma[tau],
+                                   be = (Real)sf.beta[tau];
+                        Real dP;
+                        const Real P = powz<Real>(Real(1) + gm * ct, z, dP);
+                        dP *= gm;
+                        const Real E = Math<Real>::exp_(-be * s2 * ac2i);
+                        const Real K = exp2(Real(1) - z) * (Real)cc[tau];
+                        const Real PE = P * E;
+                        va += K * (dP * dct_da * E * F3 - Real(2) * be * ra * ac2i * PE * F3 +
+                                   PE * dfa * fb * fab);
+                        vab += K * (dP * dct_dab * E * F3 - Real(2) * be * rab * ac2i * PE * F3 +
+                                    PE * fa * fb * dfab);
+                    }
+                    sa += va;
+                    const Real q = vab / rab;
+                    wx += q * jx;
+                    wy += q * jy;
+                    wz += q * jz;
+                }
+                const Real q = sa / ra;
+                gx += q * ax + wx;
+                gy += q * ay + wy;
+                gz += q * az + wz;
+            }
+            const size_t e = ebase + (size_t)a * 32u;
+            gvec[e] = (double)gx;
+            gvec[plane + e] = (double)gy;
+            gvec[2 * plane + e] = (double)gz;
+            fx += (double)gx;
+            fy += (double)gy;
+            fz += (double)gz;
+            vir[0] += (double)(gx * ax);
+            vir[1] += (double)(gy * ay);
+            vir[2] += (double)(gz * az);
+            vir[3] += 0.5 * (double)(gy * az + gz * ay);
+            vir[4] += 0.5 * (double)(gx * az + gz * ax);
+            vir[5] += 0.5 * (double)(gx * ay + gy * ax);
+        }
+        fx = warp_sum(fx);
+        fy = warp_sum(fy);
+        fz = warp_sum(fz);
+        if (lane == 0) {
+            fown[3 * (size_t)idx + 0] = fx;
+            fown[3 * (size_t)idx + 1] = fy;
+            fown[3 * (size_t)idx + 2] = fz;
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+        const double v = warp_sum(vir[q]);
+        if (lane == 0) red[warp][q] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        double v = 0;
+        for (int w = 0; w < SF_WARPS; ++w) v += red[w][threadIdx.x];
+        partial[(size_t)blockIdx.x * 8 + 1 + threadIdx.x] = v;
+    }
+}
+
+// F_i = sum_p g_p - sum_p g_rev(p); per-atom energies to caller order; energy partials
+__global__ void __launch_bounds__(128)
+k_sf_collect(int n, int n_loc, const int *__restrict__ counts,
+             const uint32_t *__restrict__ slice_ptr, const uint32_t *__restrict__ col,
+             const uint32_t *__restrict__ rev, const int *__restrict__ ghost_owner,
+             const int *__restrict__ perm, const double *__restrict__ gvec, size_t plane,
+             const double *__restrict__ fown, const double *__restrict__ eat,
+             double *__restrict__ eatom, double *__restrict__ forces,
+             double *__restrict__ partial_e) {
+    __shared__ double red[4];
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    double e = 0.0;
+    if (idx < n) {
+        double fx = fown[3 * (size_t)idx], fy = fown[3 * (size_t)idx + 1],
+               fz = fown[3 * (size_t)idx + 2];
+        const size_t base = (size_t)slice_ptr[idx >> 5] * 32u + (idx & 31);
+        const int cnt = counts[idx];
+        for (int k = 0; rev && k < cnt; ++k) {
+            const size_t ent = base + (size_t)k * 32u;
+            const uint32_t q = rev[ent];
+            if (q == 0xFFFFFFFFu) continue;
+            int o = (int)(col[ent] & TAB_COL_IDX_MASK);
+            if (o >= n_loc) o = ghost_owner[o - n_loc];
+            const size_t re = (size_t)slice_ptr[o >> 5] * 32u + (o & 31) + (size_t)q * 32u;
+            fx -= gvec[re];
+            fy -= gvec[plane + re];
+            fz -= gvec[2 * plane + re];
+        }
+        const int o = perm[idx];
+        if (forces) {
+            forces[3 * (size_t)o + 0] = fx;
+            forces[3 * (size_t)o + 1] = fy;
+            forces[3 * (size_t)o + 2] = fz;
+        }
+        e = eat[idx];
+        if (eatom) eatom[o] = e;
+    }
+    e = warp_sum(e);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = e;
+    __syncthreads();
+    if (threadIdx.x == 0) partial_e[(size_t)blockIdx.x] = red[0] + red[1] + red[2] + red[3];
+}
+
+// fixed-order final sums: energy from partial_e[nb_e], virial from partial[nb_v*8+1..6]
+__global__ void __launch_bounds__(256)
+k_sf_reduce(int nb_e, const double *__restrict__ partial_e, int nb_v,
+            const double *__restrict__ partial, double *__restrict__ energy,
+            double *__restrict__ virial) {
+    __shared__ double sm[256][7];
+    double a[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (int b = threadIdx.x; b < nb_e; b += 256) a[0] += partial_e[b];
+    for (int b = threadIdx.x; b < nb_v; b += 256)
+#pragma unroll
+        for (int q = 1; q < 7; ++q) a[q] += partial[(size_t)b * 8 + q];
+#pragma unroll
+    for (int q = 0; q < 7; ++q) sm[threadIdx.x][q] = a[q];
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s)
+#pragma unroll
+            for (int q = 0; q < 7; ++q) sm[threadIdx.x][q] += sm[threadIdx.x + s][q];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        if (energy) energy[0] = sm[0][0];
+        if (virial) {
+            const double xx = sm[0][1], yy = sm[0][2], zz = sm[0][3], yz = sm[0][4],
+                         xz = sm[0][5], xy = sm[0][6];
+            virial[0] = xx; virial[1] = xy; virial[2] = xz;
+            virial[3] = xy; virial[4] = yy; virial[5] = yz;
+            virial[6] = xz; virial[7] = yz; virial[8] = zz;
+        }
+    }
+}
+
+// sorted -> caller order copy of the descriptors
+__global__ void k_sf_export(int n, int dim, const int *__restrict__ perm,
+                            const double *__restrict__ G, double *__restrict__ out) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)n * dim) return;
+    const int idx = (int)(t / dim), k = (int)(t % dim);
+    out[(size_t)perm[idx] * dim + k] = G[t];
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+extern "C" int tab_atomic_create(tab_atomic **out, const tab_sf_desc *d,
+                                 const tab_mlp_desc *mlps) {
+    if (!out || !d || !mlps || d->n_el < 1 || d->n_el > TAB_MAX_ELEMENTS) {
+        tab_set_error("tab_atomic_create: bad argument");
+        return TAB_EINVAL;
+    }
+    if (d->n_r < 0 || d->n_r > SF_MAX_R || d->n_a < 0 || d->n_a > SF_MAX_A) {
+        tab_set_error("tab_atomic_create: too many symmetry-function parameter sets");
+        return TAB_EUNSUPPORTED;
+    }
+    tab_atomic *m = new tab_atomic();
+    SfDev &sf = m->sf;
+    memset(&sf, 0, sizeof(sf));
+    sf.n_el = m->n_el = d->n_el;
+    sf.n_r = d->n_r;
+    sf.n_a = d->angular ? d->n_a : 0;
+    sf.angular = d->angular ? 1 : 0;
+    sf.cutoff = d->cutoff;
+    sf.rc = d->rc;
+    sf.acut = d->angular ? d->acut : d->rc;
+    for (int k = 0; k < d->n_r; ++k) {
+        sf.eta[k] = d->eta[k];
+        sf.omega[k] = d->omega[k];
+    }
+    for (int k = 0; k < sf.n_a; ++k) {
+        sf.beta[k] = d->beta[k];
+        sf.gamma[k] = d->gamma[k];
+        sf.zeta[k] = d->zeta[k];
+    }
+    sf.d_r = sf.n_el * sf.n_r;
+    sf.dim = sf.d_r + (sf.angular ? sf.n_el * (sf.n_el + 1) / 2 * sf.n_a : 0);
+    // pack the MLP blobs
+    size_t total = 0;
+    for (int e = 0; e < d->n_el; ++e) {
+        const tab_mlp_desc &q = mlps[e];
+        if (q.n_layers < 1 || q.n_layers > MLP_MAX_LAYERS || q.sizes[0] != sf.dim ||
+            q.sizes[q.n_layers] != 1) {
+            tab_set_error("tab_atomic_create: element %d: bad layer layout "
+                          "(input must be %d wide, output 1)", e, sf.dim);
+            delete m;
+            return TAB_EINVAL;
+        }
+        for (int l = 0; l < q.n_layers; ++l) {
+            if (q.sizes[l] > MLP_MAX_WIDTH || q.sizes[l + 1] > MLP_MAX_WIDTH) {
+                tab_set_error("tab_atomic_create: layer wider than %d", MLP_MAX_WIDTH);
+                delete m;
+                return TAB_EUNSUPPORTED;
+            }
+            total += (size_t)q.sizes[l] * q.sizes[l + 1] + q.sizes[l + 1];
+        }
+        total += 2 * (size_t)sf.dim;
+    }
+    double *host = new double[total + TAB_MAX_ELEMENTS * sizeof(MlpDev) / 8 + 8];
+    size_t off = 0;
+    for (int e = 0; e < d->n_el; ++e) {
+        const tab_mlp_desc &q = mlps[e];
+        MlpDev &M = m->mlp[e];
+        memset(&M, 0, sizeof(M));
+        M.n_layers = q.n_layers;
+        M.act = q.activation;
+        M.resnet = q.use_resnet_dt;
+        M.has_out_bias = q.output_bias;
+        M.has_minmax = (q.xlo && q.xhi) ? 1 : 0;
+        for (int l = 0; l < q.n_layers; ++l) {
+            const int ni = q.sizes[l], no = q.sizes[l + 1];
+            M.in[l] = ni;
+            M.out[l] = no;
+            M.w_off[l] = (long long)off;
+            memcpy(host + off, q.weights[l], sizeof(double) * ni * no);
+            off += (size_t)ni * no;
+            M.b_off[l] = (long long)off;
+            if (q.biases[l]) memcpy(host + off, q.biases[l], sizeof(double) * no);
+            else memset(host + off, 0, sizeof(double) * no);
+            off += no;
+        }
+        M.xlo_off = (long long)off;
+        if (M.has_minmax) memcpy(host + off, q.xlo, sizeof(double) * sf.dim);
+        off += sf.dim;
+        M.xhi_off = (long long)off;
+        if (M.has_minmax) memcpy(host + off, q.xhi, sizeof(double) * sf.dim);
+        off += sf.dim;
+    }
+    // MlpDev table appended (8-byte aligned)
+    const size_t mlp_off = off;
+    memcpy(host + off, m->mlp, sizeof(MlpDev) * d->n_el);
+    const size_t bytes = off * 8 + sizeof(MlpDev) * d->n_el;
+    int rc = m->blob.ensure(bytes);
+    if (rc == TAB_OK) {
+        cudaError_t e = cudaMemcpy(m->blob.p, host, bytes, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            tab_set_error("tab_atomic_create: cudaMemcpy -> %s", cudaGetErrorString(e));
+            rc = TAB_ECUDA;
+        }
+    }
+    delete[] host;
+    if (rc != TAB_OK) {
+        m->blob.release();
+        delete m;
+        return rc;
+    }
+    m->mlp_table_off = mlp_off;
+    *out = m;
+    return TAB_OK;
+}
+
+extern "C" int tab_atomic_free(tab_atomic *m) {
+    if (!m) return TAB_OK;
+    DevBuf *bufs[] = {&m->blob, &m->G, &m->dEdG, &m->eat, &m->gvec, &m->fown};
+    for (DevBuf *b : bufs) b->release();
+    delete m;
+    return TAB_OK;
+}
+
+extern "C" int tab_atomic_dim(const tab_atomic *m) { return m ? m->sf.dim : 0; }
+
+template <typename Real>
+static int atomic_run(tab_atomic *m, tab_nbr *nbr, double *d_energy, double *d_eatom,
+                      double *d_forces, double *d_virial, double *d_desc,
+                      cudaStream_t st) {
+    const int n = nbr->n;
+    const SfDev &sf = m->sf;
+    if (nbr->n_halo > 0) {
+        tab_set_error("AtomicNN with halo atoms (domain decomposition) is not supported");
+        return TAB_EUNSUPPORTED;
+    }
+    if (nbr->n_types > sf.n_el) {
+        tab_set_error("structure holds element index %d, model has %d elements",
+                      nbr->n_types - 1, sf.n_el);
+        return TAB_EINVAL;
+    }
+    const double need_rc = sf.angular && sf.acut > sf.rc ? sf.acut : sf.rc;
+    if (nbr->grid.rc + 1e-12 < need_rc) {
+        tab_set_error("neighbour lists were built with rc=%g < model cutoff %g",
+                      nbr->grid.rc, need_rc);
+        return TAB_ESTATE;
+    }
+    const int row_cap = nbr->nnl_max > 0 ? nbr->nnl_max : 1;
+    const size_t smem_row = (size_t)SF_WARPS * row_cap * ROW_W * sizeof(double);
+    if (smem_row > 200 * 1024) {
+        tab_set_error("neighbour rows of %d entries exceed the shared-memory budget", row_cap);
+        return TAB_EUNSUPPORTED;
+    }
+    const size_t smem_mlp = (size_t)SF_WARPS * (2 * MLP_MAX_LAYERS + 2) * MLP_MAX_WIDTH *
+                            sizeof(double);
+    static bool attr_done[2] = {false, false};
+    const int ai = sizeof(Real) == 8 ? 0 : 1;
+    if (!attr_done[ai]) {
+        TAB_CUDA(cudaFuncSetAttribute(k_sf_forward<Real>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        TAB_CUDA(cudaFuncSetAttribute(k_sf_backward<Real>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        TAB_CUDA(cudaFuncSetAttribute(k_mlp<Real>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        attr_done[ai] = true;
+    }
+    const int nblk = (n + SF_WARPS - 1) / SF_WARPS;
+    const int nblk_c = (n + 127) / 128;
+    TAB_TRY(m->G.ensure(sizeof(double) * (size_t)n * sf.dim));
+    TAB_TRY(m->dEdG.ensure(sizeof(double) * (size_t)n * sf.dim));
+    TAB_TRY(m->eat.ensure(sizeof(double) * (size_t)n));
+    TAB_TRY(m->fown.ensure(sizeof(double) * 3 * (size_t)n));
+    TAB_TRY(nbr->partial.ensure(sizeof(double) * (8 * (size_t)nblk + nblk_c + 8)));
+    const Atom4 *atoms = nbr->atoms.as<Atom4>();
+    k_sf_forward<Real><<<nblk, SF_WARPS * 32, smem_row, st>>>(
+        n, sf, nbr->n_types, row_cap, atoms, nbr->types_ext.as<uint8_t>(),
+        nbr->counts.as<int>(), nbr->tcounts.as<int>(), nbr->slice_ptr.as<uint32_t>(),
+        nbr->col.as<uint32_t>(), m->G.as<double>());
+    TAB_LAUNCH_CHECK();
+    if (d_desc) {
+        const size_t tot = (size_t)n * sf.dim;
+        k_sf_export<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(
+            n, sf.dim, nbr->perm.as<int>(), m->G.as<double>(), d_desc);
+        TAB_LAUNCH_CHECK();
+        if (!d_energy && !d_eatom && !d_forces && !d_virial) return TAB_OK;
+    }
+    const double *blob = m->blob.as<double>();
+    const MlpDev *mlps = reinterpret_cast<const MlpDev *>(blob + m->mlp_table_off);
+    k_mlp<Real><<<nblk, SF_WARPS * 32, smem_mlp, st>>>(
+        n, sf.dim, nbr->types_ext.as<uint8_t>(), mlps, blob, m->G.as<double>(),
+        m->eat.as<double>(), m->dEdG.as<double>());
+    TAB_LAUNCH_CHECK();
+    const size_t plane = (size_t)nbr->ell_rows * 32;
+    double *partial = nbr->partial.as<double>();
+    double *partial_e = partial + 8 * (size_t)nblk;
+    const bool need_grad = d_forces || d_virial;
+    if (need_grad) {
+        TAB_TRY(tab_nbr_ensure_reverse(nbr, st));
+        TAB_TRY(m->gvec.ensure(sizeof(double) * 3 * (plane + 32)));
+        k_sf_backward<Real><<<nblk, SF_WARPS * 32, smem_row, st>>>(
+            n, sf, nbr->n_types, row_cap, atoms, nbr->types_ext.as<uint8_t>(),
+            nbr->counts.as<int>(), nbr->tcounts.as<int>(), nbr->slice_ptr.as<uint32_t>(),
+            nbr->col.as<uint32_t>(), m->dEdG.as<double>(), m->gvec.as<double>(), plane,
+            m->fown.as<double>(), partial);
+        TAB_LAUNCH_CHECK();
+    }
+    k_sf_collect<<<nblk_c, 128, 0, st>>>(
+        n, nbr->n_loc, nbr->counts.as<int>(), nbr->slice_ptr.as<uint32_t>(),
+        nbr->col.as<uint32_t>(), need_grad ? nbr->rev.as<uint32_t>() : nullptr,
+        nbr->ghost_owner.as<int>(), nbr->perm.as<int>(), m->gvec.as<double>(), plane,
+        m->fown.as<double>(), m->eat.as<double>(), d_eatom, need_grad ? d_forces : nullptr,
+        partial_e);
+    TAB_LAUNCH_CHECK();
+    k_sf_reduce<<<1, 256, 0, st>>>(nblk_c, partial_e, need_grad ? nblk : 0, partial, d_energy,
+                                  need_grad ? d_virial : nullptr);
+    TAB_LAUNCH_CHECK();
+    return TAB_OK;
+}
+
+extern "C" int tab_atomic_eval(tab_atomic *m, tab_nbr *nbr, int32_t precision,
+                               double *d_energy, double *d_eatom, double *d_forces,
+                               double *d_virial, void *stream) {
+    if (!m || !nbr) {
+        tab_set_error("tab_atomic_eval: null handle");
+        return TAB_EINVAL;
+    }
+    if (!nbr->built) {
+        tab_set_error("tab_atomic_eval before tab_nbr_build");
+        return TAB_ESTATE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (precision == TAB_PRECISION_HIGH)
+        return atomic_run<double>(m, nbr, d_energy, d_eatom, d_forces, d_virial, nullptr, st);
+    return atomic_run<float>(m, nbr, d_energy, d_eatom, d_forces, d_virial, nullptr, st);
+}
+
+extern "C" int tab_atomic_descriptors(tab_atomic *m, tab_nbr *nbr, int32_t precision,
+                                      double *d_desc, void *stream) {
+    if (!m || !nbr || !d_desc) return TAB_EINVAL;
+    if (!nbr->built) return TAB_ESTATE;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (precision == TAB_PRECISION_HIGH)
+        return atomic_run<double>(m, nbr, nullptr, nullptr, nullptr, nullptr, d_desc, st);
+    return atomic_run<float>(m, nbr, nullptr, nullptr, nullptr, nullptr, d_desc, st);
+}

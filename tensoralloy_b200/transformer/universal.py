@@ -152,7 +152,10 @@ class UniversalTransformer:
         d_pos = torch.as_tensor(np.ascontiguousarray(atoms.positions, dtype=np.float64)
                                 ).to('cuda', non_blocking=True)
         d_types = torch.as_tensor(types).to('cuda', non_blocking=True)
-        self._nbr.build(d_pos, d_types, cell, pbc, rc or self._rcut)
+        if rc is None:
+            rc = max(self._rcut, self._acut) if (self._angular and self._acut) \
+                else self._rcut
+        self._nbr.build(d_pos, d_types, cell, pbc, rc)
         real_cell = np.asarray(atoms.get_cell(complete=True), dtype=np.float64)
         return DeviceFeatures(atoms, self.get_vap_transformer(atoms), types,
                               self._nbr, d_pos, real_cell.reshape(3, 3),

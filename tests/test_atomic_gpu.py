@@ -1,0 +1,123 @@
+"""AtomicNN (Behler G2 + G4 + per-element MLP) on the GPU vs the oracle and the
+reference's AMP golden.  Tolerances: BASELINE.json north_star (1e-10 eV/atom,
+1e-8 eV/A float64; 1e-5 relative float32)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import atomic as oat
+from tensoralloy_b200.atoms import Atoms, bulk_fcc
+from tensoralloy_b200.calculator import TensorAlloyCalculator
+from tensoralloy_b200.nn.atomic import AtomicNN, SymmetryFunction
+from tensoralloy_b200.precision import precision_scope
+from tensoralloy_b200.transformer import UniversalTransformer
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), 'golden')
+
+PD3O2 = Atoms('Pd3O2', pbc=[True, True, False],
+              cell=[[7.78, 0., 0.], [0., 5.50129076, 0.], [0., 0., 15.37532269]],
+              positions=[[3.89, 0., 8.37532269], [0., 2.75064538, 8.37532269],
+                         [3.89, 2.75064538, 8.37532269], [5.835, 1.37532269, 8.5],
+                         [5.835, 7.12596807, 8.]])
+
+
+def test_descriptors_match_amp_golden():
+    # nn/atomic/tests/test_sf.py:666-691 (tolerance 1e-12)
+    amp = np.load(os.path.join(GOLD, 'amp_Pd3O2.npz'))['g']
+    with precision_scope('high'):
+        clf = UniversalTransformer(['O', 'Pd'], rcut=6.5, angular=True, periodic=True)
+        nn = AtomicNN(['O', 'Pd'], SymmetryFunction(['O', 'Pd']))
+        nn.attach_transformer(clf)
+        g = nn.get_descriptors(clf.get_constant_features(PD3O2))
+    assert np.abs(g[3:5] - amp[3:5, 0:20]).max() < 1e-12
+    assert np.abs(g[0:3] - amp[0:3, 20:40]).max() < 1e-12
+
+
+def _compare(atoms, elements, rc, acut=None, angular=True, sf_kwargs=None,
+             nn_kwargs=None, seed=611, tol_e=1e-10, tol_f=1e-8, out_scale=0.02):
+    sf_kwargs = sf_kwargs or {}
+    nn_kwargs = nn_kwargs or {}
+    with precision_scope('high'):
+        clf = UniversalTransformer(elements, rcut=rc, acut=acut, angular=angular)
+        nn = AtomicNN(elements, SymmetryFunction(elements, **sf_kwargs),
+                      export_properties=('energy', 'forces', 'stress'), **nn_kwargs)
+        nn.attach_transformer(clf)
+        nn.initialize_variables(seed=seed)
+        # random he_normal weights on raw descriptors give |E| ~ 100 eV/atom; bring
+        # the model to a physical scale (|E| ~ eV/atom) so that the absolute
+        # tolerances of the north star are meaningful
+        for el in nn.elements:
+            key = f"Atomic/{el}/Output/kernel"
+            nn.set_variable(key, nn.get_variable(key) * out_scale)
+        if nn_kwargs.get('minmax_scale', True):
+            rng = np.random.default_rng(seed + 1)
+            dim = nn._dim()
+            for el in nn.elements:
+                lo = rng.random(dim) * 0.1
+                nn.set_variable(f"Atomic/{el}/xlo", lo.reshape(1, 1, -1))
+                nn.set_variable(f"Atomic/{el}/xhi", (lo + 1.0 + 5 * rng.random(dim)
+                                                     ).reshape(1, 1, -1))
+        calc = TensorAlloyCalculator(nn)
+        calc.calculate(atoms, properties=['energy', 'forces', 'stress'])
+        e, f, s = calc.results['energy'], calc.get_forces(atoms), calc.get_stress(atoms)
+        ea = calc.get_atomic(atoms)
+    params, minmax = {}, {}
+    for el in nn.elements:
+        p = nn.mlp_params(el)
+        params[el] = p
+        minmax[el] = (p['xlo'], p['xhi']) if p['xlo'] is not None else None
+    oracle_sf = {}
+    sfd = nn.descriptor.as_dict()
+    for k in ('eta', 'omega', 'beta', 'gamma', 'zeta'):
+        oracle_sf[k] = tuple(sfd[k])
+    oracle_sf['cutoff'] = sfd['cutoff_function']
+    ref = oat.atomic_evaluate(elements, atoms.get_chemical_symbols(), atoms.positions,
+                              atoms.cell, atoms.pbc, rc, params, sf=oracle_sf,
+                              acut=acut, angular=angular, minmax=minmax)
+    n = len(atoms)
+    print('E/atom', ref['energy'] / n, 'dE/atom', abs(e - ref['energy']) / n,
+          'dF', np.abs(f - ref['forces']).max(), 'Fmax', np.abs(ref['forces']).max(),
+          'dS', np.abs(s - ref['stress']).max())
+    assert abs(e - ref['energy']) / n < tol_e
+    assert np.abs(ea - ref['energy/atom']).max() < tol_e * 10
+    assert np.abs(f - ref['forces']).max() < tol_f
+    assert np.abs(s - ref['stress']).max() < tol_f
+    # float32 'medium'
+    with precision_scope('medium'):
+        calc32 = TensorAlloyCalculator(nn)
+        calc32.calculate(atoms, properties=['energy', 'forces'])
+        e32, f32 = calc32.results['energy'], calc32.get_forces(atoms)
+    assert abs(e32 - ref['energy']) <= 2e-5 * max(abs(ref['energy']), 1.0)
+    fscale = max(np.abs(ref['forces']).max(), 1e-2)
+    assert np.abs(f32 - ref['forces']).max() <= 1e-3 * fscale
+    return ref
+
+
+def test_be_liquid_g2_g4_mlp():
+    d = np.load(os.path.join(GOLD, 'Be_liquid_4000K.npz'))
+    # frame 0 is a perfect crystal (zero forces); frames 1, 2 are the liquid
+    atoms = Atoms(list(d['symbols']), d['positions'][2], d['cells'][2], True)
+    ref = _compare(atoms, ['Be'], 5.0, nn_kwargs=dict(minmax_scale=False))
+    assert np.abs(ref['forces']).max() > 0.1      # the comparison is not vacuous
+    atoms = Atoms(list(d['symbols']), d['positions'][1], d['cells'][1], True)
+    _compare(atoms, ['Be'], 5.0, nn_kwargs=dict(minmax_scale=True, use_resnet_dt=True,
+                                                hidden_sizes=[32, 32],
+                                                activation='tanh'))
+
+
+def test_two_elements_radial_and_angular():
+    base = bulk_fcc('Ni', 3.6, (2, 2, 2))
+    rng = np.random.default_rng(5)
+    sym = ['Mo' if x < 0.4 else 'Ni' for x in rng.random(len(base))]
+    atoms = Atoms(sym, base.positions + rng.normal(scale=0.1, size=base.positions.shape),
+                  base.cell, True)
+    _compare(atoms, ['Mo', 'Ni'], 4.6, angular=False,
+             nn_kwargs=dict(atomic_static_energy={'Mo': -1.5, 'Ni': -0.7}))
+    _compare(atoms, ['Mo', 'Ni'], 4.6, acut=4.0, angular=True,
+             sf_kwargs=dict(cutoff_function='polynomial', zeta=[1.0, 2.5]),
+             nn_kwargs=dict(activation='squareplus'))
+    # mixed periodicity + atoms outside the cell, three species
+    _compare(PD3O2, ['O', 'Pd'], 6.5)
