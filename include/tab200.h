@@ -176,6 +176,11 @@ int tab_eam_pass2(tab_model *model, tab_nbr *nbr, int32_t precision,
                   const double *d_fprime_halo, double *d_energy, double *d_eatom,
                   double *d_forces, double *d_virial, void *stream);
 
+/* Analytic Hessian d2E/dR_a dR_b of an EAM / FS model (float64 only):
+ * d_hessian [n,3,n,3] in caller atom order.  Replaces tf.hessians(E, R) of
+ * BasicNN._get_hessian_op (nn/basic.py:410-421). */
+int tab_eam_hessian(tab_model *model, tab_nbr *nbr, double *d_hessian, void *stream);
+
 /* Host-buffer convenience: H2D of positions (+types), neighbour build, eval,
  * D2H of the results -- the whole of TensorAlloyCalculator.calculate
  * (calculator.py:335-370) in one call.  Host buffers should be pinned for full

@@ -87,7 +87,7 @@ EXPORTS = [
     'tab_nbr_update',
     'tab_nbr_sizes', 'tab_nbr_counts', 'tab_nbr_export',
     'tab_eam_create', 'tab_model_free', 'tab_eam_eval', 'tab_eam_pass1',
-    'tab_eam_pass2', 'tab_eam_compute_host',
+    'tab_eam_pass2', 'tab_eam_hessian', 'tab_eam_compute_host',
     'tab_atomic_create', 'tab_atomic_free', 'tab_atomic_dim', 'tab_atomic_eval',
     'tab_atomic_descriptors',
     'tab_launch_count', 'tab_launch_count_reset',
@@ -129,6 +129,7 @@ def lib():
     L.tab_eam_eval.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]
     L.tab_eam_pass1.argtypes = [vp, vp, i32, vp, vp]
     L.tab_eam_pass2.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, vp]
+    L.tab_eam_hessian.argtypes = [vp, vp, vp, vp]
     L.tab_eam_compute_host.argtypes = [vp, vp, i32, i32, vp, vp,
                                        C.POINTER(dbl), C.POINTER(i32), dbl, i32,
                                        vp, vp, vp, vp, vp]
@@ -295,6 +296,15 @@ class EamModel:
                                   _ptr(fprime_halo), _ptr(energy), _ptr(eatom),
                                   _ptr(forces), _ptr(virial), _stream()),
               'tab_eam_pass2')
+
+    def hessian(self, nbr):
+        """Dense [n,3,n,3] float64 Hessian (caller atom order) on the device."""
+        import torch
+        n = nbr.n
+        H = torch.empty((n, 3, n, 3), dtype=torch.float64, device='cuda')
+        check(lib().tab_eam_hessian(self._h, nbr.handle, _ptr(H), _stream()),
+              'tab_eam_hessian')
+        return H
 
     def compute_host(self, nbr, precision, h_pos, h_types, cell, pbc, rc, rebuild,
                      h_energy, h_eatom, h_forces, h_virial):

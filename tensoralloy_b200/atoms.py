@@ -155,3 +155,15 @@ def fcc_positions(a, nx, ny, nz, dtype=np.float64):
     pos = (cells[:, None, :] + base[None, :, :]).reshape(-1, 3) * a
     cell = np.diag([nx * a, ny * a, nz * a]).astype(dtype)
     return pos, cell
+
+
+def bulk_hcp(symbol, a, c, repeat=(1, 1, 1)):
+    """hcp primitive cell (2 atoms) repeated; stand-in for
+    `ase.build.bulk(symbol, 'hcp', a=a, c=c) * repeat` (the Be crystal of the
+    reference's nn/constraint/data.py:42-50)."""
+    cell = np.array([[a, 0.0, 0.0],
+                     [-0.5 * a, 0.5 * np.sqrt(3.0) * a, 0.0],
+                     [0.0, 0.0, c]])
+    scaled = np.array([[0.0, 0.0, 0.0], [1.0 / 3.0, 2.0 / 3.0, 0.5]])
+    atoms = Atoms([symbol] * 2, scaled @ cell, cell, True)
+    return atoms.repeat(repeat)

@@ -582,6 +582,18 @@ extern "C" int tab_eam_create(tab_model **out, int32_t kind, int32_t n_el,
     return TAB_OK;
 }
 
+// accessor for hessian.cu (tab_model is private to this file)
+int tab_eam_tables(tab_model *m, const tab_fn **rho, const tab_fn **phi,
+                   const tab_fn **embed, int *n_el, int *kind) {
+    const int nn = m->n_el * m->n_el;
+    *rho = m->tables.as<tab_fn>();
+    *phi = *rho + nn;
+    *embed = *rho + 2 * nn;
+    *n_el = m->n_el;
+    *kind = m->kind;
+    return TAB_OK;
+}
+
 extern "C" int tab_model_free(tab_model *m) {
     if (!m) return TAB_OK;
     m->tables.release();

@@ -151,3 +151,14 @@ class EamNN(BasicNN):
         if want_virial:
             raw['virial'] = scal[1:10].reshape(3, 3).copy()
         return raw
+
+    def _hessian(self, features):
+        """[Nvap, 3, Nvap, 3] Hessian in GSL order incl. the virtual atom, the
+        layout of the reference's `Output/Hessian` op (basic.py:410-421)."""
+        H = self._device_model().hessian(features.nbr).cpu().numpy()
+        vap = features.vap
+        nv = vap.max_vap_natoms
+        idx = vap.local_to_gsl_array[1:]
+        out = np.zeros((nv, 3, nv, 3), dtype=np.float64)
+        out[np.ix_(idx, range(3), idx, range(3))] = H
+        return out

@@ -189,3 +189,37 @@ def test_adp_dipole_quadrupole():
     atoms = Atoms(sym, atoms.positions, atoms.cell, True)
     _calc_compare(AdpNN(['Mo', 'Ni'], custom_potentials=cp2), atoms, None, 'adp', 6.0,
                   fns=fns)
+
+
+def test_elastic_constants_known_answers():
+    """zjw04 Ni fcc, rc 6.0: C11 = 247, C12 = 147, C44 = 125 GPa (+-1), the values
+    asserted by the reference in nn/constraint/tests/test_elastic.py:49-56
+    (246.61 / 147.15 / 124.72 in tests/test_calculator.py:101-108).  Obtained here
+    by central finite differences of the GPU stress under homogeneous strain:
+    pins the sign and units of the virial / stress."""
+    from tensoralloy_b200.atoms import GPa
+    from tensoralloy_b200.calculator import TensorAlloyCalculator
+    from tensoralloy_b200.nn.eam import EamAlloyNN
+    from tensoralloy_b200.precision import precision_scope
+    from tensoralloy_b200.transformer import UniversalTransformer
+    with precision_scope('high'):
+        nn = EamAlloyNN(['Ni'], custom_potentials='zjw04',
+                        export_properties=['energy', 'forces', 'stress'])
+        nn.attach_transformer(UniversalTransformer(['Ni'], rcut=6.0))
+        calc = TensorAlloyCalculator(nn)
+        base = bulk_fcc('Ni', 3.52, (3, 3, 3))
+
+        def stress(eps):
+            a = base.copy()
+            F = np.eye(3) + eps
+            a.set_cell(base.cell @ F, scale_atoms=True)
+            return calc.get_stress(a, voigt=False)
+
+        h = 1e-4
+        e = np.zeros((3, 3)); e[0, 0] = h
+        d = (stress(e) - stress(-e)) / (2 * h) / GPa
+        c11, c12 = d[0, 0], d[1, 1]
+        e = np.zeros((3, 3)); e[1, 2] = e[2, 1] = h / 2
+        d = (stress(e) - stress(-e)) / (2 * h) / GPa
+        c44 = d[1, 2]
+    assert abs(c11 - 246.61) < 0.5 and abs(c12 - 147.15) < 0.5 and abs(c44 - 124.72) < 0.5
