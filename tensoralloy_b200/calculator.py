@@ -236,7 +236,8 @@ class TensorAlloyCalculator(_AseCalculator):
                 if prop not in self.implemented_properties:
                     raise KeyError(prop)
             features = self._transformer.get_constant_features(atoms)
-            want_stress = bool({'stress', 'total_pressure', 'elastic'} & properties)
+            want_stress = bool({'stress', 'total_pressure', 'elastic', 'total_stress'}
+                               & properties)
             want_forces = 'forces' in properties or want_stress
             raw = self._nn._evaluate(features, want_forces, want_stress, True)
             if 'hessian' in properties:
@@ -249,5 +250,12 @@ class TensorAlloyCalculator(_AseCalculator):
             pred = self._nn._finalize(raw, features, wanted)
             if 'elastic' in raw:
                 pred['elastic'] = raw['elastic']
+            # property names of legacy exports (Metadata/ops of api 1.0 files)
+            if 'atomic' in properties:
+                pred['atomic'] = pred['energy/atom']
+            if 'free_energy' in properties and 'free_energy' not in pred:
+                pred['free_energy'] = pred['energy']
+            if 'total_stress' in properties and 'virial' in pred:
+                pred['total_stress'] = pred['virial'] / features.volume
             self.results = pred
             self._ncalls += 1

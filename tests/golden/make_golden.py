@@ -11,6 +11,7 @@ Sources (all under /root/reference/test_files):
   amp_Pd3O2.npz               golden of nn/atomic/tests/test_sf.py:666-691
   crystals/Ni_fc2.npy         golden of nn/constraint/tests/test_fc2.py:30-54
   Be_liquid_4000K_TS.extxyz   config-2 geometry (3 x 128 Be atoms)
+  models/Mo.zhou04.pb         frozen GraphDef exported by the reference (model-file layout)
 """
 import shutil
 from pathlib import Path
@@ -76,6 +77,8 @@ def main():
         np.savez_compressed(OUT / (name.replace('.alloy.eam', '') + '_setfl.npz'), **d)
     shutil.copy(REF / 'amp_Pd3O2.npz', OUT / 'amp_Pd3O2.npz')
     shutil.copy(REF / 'crystals' / 'Ni_fc2.npy', OUT / 'Ni_fc2.npy')
+    # a frozen model exported by the reference (legacy metadata layout)
+    shutil.copy(REF / 'models' / 'Mo.zhou04.pb', OUT / 'Mo.zhou04.pb')
     frames = read_extxyz(REF / 'Be_liquid_4000K_TS.extxyz')
     np.savez_compressed(
         OUT / 'Be_liquid_4000K.npz',
