@@ -11,7 +11,7 @@ from pathlib import Path
 import numpy as np
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / 'csrc' / 'libtab200.so'
+LIB_PATH = Path(os.environ.get('TAB200_LIB', _HERE / 'csrc' / 'libtab200.so'))
 
 TAB_FN_MAX_PARAMS = 32
 PRECISION_HIGH = 0

@@ -42,7 +42,12 @@ struct Zhou1 {
     double fe, beta, lamda, re, A, alpha, kappa, B;   // re holds 1/r_eq
 };
 
-#define EAM_T 256
+#ifndef EAM_T
+#define EAM_T 128        // threads per block of the pair kernels (sweep: profiles/r01d)
+#endif
+#ifndef EAM_MINB
+#define EAM_MINB 4       // __launch_bounds__ min blocks per SM (register cap)
+#endif
 #define ADP_MAX_EL 3     // ADP keeps n_el x 9 moment accumulators in registers
 
 template <typename Real>
@@ -98,7 +103,7 @@ __device__ __forceinline__ void load_tables(tab_fn *s, const tab_fn *g, int coun
 // pass 1
 // ---------------------------------------------------------------------------
 template <typename Real, bool FAST>
-__global__ void __launch_bounds__(EAM_T)
+__global__ void __launch_bounds__(EAM_T, EAM_MINB)
 k_eam_rho(int n, const Atom4 *__restrict__ atoms,
           const uint8_t *__restrict__ types_ext, const int *__restrict__ counts,
           const uint32_t *__restrict__ slice_ptr, const uint32_t *__restrict__ col,
@@ -157,7 +162,7 @@ __global__ void k_spread_w(int n_owned, int n_loc, int n_ext,
 // pass 2
 // ---------------------------------------------------------------------------
 template <typename Real, bool FAST>
-__global__ void __launch_bounds__(EAM_T)
+__global__ void __launch_bounds__(EAM_T, EAM_MINB)
 k_eam_force(int n, const Atom4 *__restrict__ atoms,
             const uint8_t *__restrict__ types_ext, const int *__restrict__ counts,
             const uint32_t *__restrict__ slice_ptr, const uint32_t *__restrict__ col,
