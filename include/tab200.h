@@ -83,6 +83,12 @@ int tab_nbr_build_dd(tab_nbr *nbr, int32_t n_owned, int32_t n_halo,
                      const double *h_cell, const double *h_origin,
                      const int32_t *h_pbc, double rc, void *stream);
 
+/* Halo packing for the exchange of a spatial decomposition:
+ * d_dst[k, :] = d_src[d_idx[k], :] (+ h_shift for 3-column position rows; the
+ * sender applies the periodic shift).  d_idx: int64 row indices. */
+int tab_pack_rows(const double *d_src, const int64_t *d_idx, int32_t m, int32_t ncol,
+                  const double *h_shift, double *d_dst, void *stream);
+
 /* Keep the lists, refresh the positions (and optionally the cell): the MD step
  * between two rebuilds.  h_cell may be NULL (unchanged). */
 int tab_nbr_update(tab_nbr *nbr, const double *d_pos, const double *h_cell,

@@ -84,7 +84,7 @@ _lib = None
 EXPORTS = [
     'tab_version', 'tab_last_error',
     'tab_nbr_create', 'tab_nbr_free', 'tab_nbr_build', 'tab_nbr_build_dd',
-    'tab_nbr_update',
+    'tab_nbr_update', 'tab_pack_rows',
     'tab_nbr_sizes', 'tab_nbr_counts', 'tab_nbr_export',
     'tab_eam_create', 'tab_model_free', 'tab_eam_eval', 'tab_eam_pass1',
     'tab_eam_pass2', 'tab_eam_hessian', 'tab_eam_compute_host',
@@ -118,6 +118,7 @@ def lib():
     L.tab_nbr_build_dd.argtypes = [vp, i32, i32, vp, vp, C.POINTER(dbl),
                                    C.POINTER(dbl), C.POINTER(i32), dbl, vp]
     L.tab_nbr_update.argtypes = [vp, vp, C.POINTER(dbl), vp]
+    L.tab_pack_rows.argtypes = [vp, vp, i32, i32, C.POINTER(dbl), vp, vp]
     L.tab_nbr_sizes.argtypes = [vp, C.POINTER(i64), C.POINTER(i32),
                                 C.POINTER(i32)]
     L.tab_nbr_counts.argtypes = [vp, vp, vp]
@@ -176,6 +177,15 @@ def _ptr(t):
 def _stream():
     import torch
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def pack_rows(src, idx, dst, shift=None):
+    """dst[k] = src[idx[k]] (+ shift): one launch of the library's pack kernel."""
+    m = int(idx.shape[0])
+    ncol = int(src.shape[1]) if src.dim() == 2 else 1
+    sh = (C.c_double * 3)(*[float(x) for x in shift]) if shift is not None else None
+    check(lib().tab_pack_rows(_ptr(src), _ptr(idx), m, ncol, sh, _ptr(dst), _stream()),
+          'tab_pack_rows')
 
 
 class NeighborList:

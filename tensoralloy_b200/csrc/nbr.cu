@@ -836,3 +836,32 @@ int tab_nbr_ensure_reverse(tab_nbr *nbr, cudaStream_t st) {
     nbr->has_rev = true;
     return TAB_OK;
 }
+
+// ---------------------------------------------------------------------------
+// halo packing (domain decomposition): dst[k, :] = src[idx[k], :] (+ shift)
+// ---------------------------------------------------------------------------
+__global__ void k_pack_rows(int m, int ncol, const double *__restrict__ src,
+                            const long long *__restrict__ idx, double sx, double sy,
+                            double sz, int shifted, double *__restrict__ dst) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m * ncol) return;
+    const int k = t / ncol, c = t - k * ncol;
+    double v = src[(size_t)idx[k] * ncol + c];
+    if (shifted) v += c == 0 ? sx : (c == 1 ? sy : sz);
+    dst[t] = v;
+}
+
+extern "C" int tab_pack_rows(const double *d_src, const int64_t *d_idx, int32_t m,
+                             int32_t ncol, const double *h_shift, double *d_dst,
+                             void *stream) {
+    if (m <= 0) return TAB_OK;
+    if (!d_src || !d_idx || !d_dst || ncol < 1 || (h_shift && ncol != 3)) {
+        tab_set_error("tab_pack_rows: bad argument");
+        return TAB_EINVAL;
+    }
+    k_pack_rows<<<nblocks((long long)m * ncol, 256), 256, 0, (cudaStream_t)stream>>>(
+        m, ncol, d_src, (const long long *)d_idx, h_shift ? h_shift[0] : 0.0,
+        h_shift ? h_shift[1] : 0.0, h_shift ? h_shift[2] : 0.0, h_shift ? 1 : 0, d_dst);
+    TAB_LAUNCH_CHECK();
+    return TAB_OK;
+}

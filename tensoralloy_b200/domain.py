@@ -111,14 +111,17 @@ class SlabRank:
         self.ly, self.lz = ly, lz
         self.n_owned = int(len(pos_owned))
         self.h_pos = torch.from_numpy(np.ascontiguousarray(pos_owned)).pin_memory()
-        self.d_pos_owned = self.h_pos.to(device)
+        self._pos0 = self.h_pos.to(device)
         m_l, m_r = layout.send_masks(pos_owned[:, 0])
         self.idx_l = torch.from_numpy(np.flatnonzero(m_l)).to(device)
         self.idx_r = torch.from_numpy(np.flatnonzero(m_r)).to(device)
-        self.shift_l = torch.tensor([layout.shift_to_left, 0.0, 0.0],
-                                    dtype=torch.float64, device=device)
-        self.shift_r = torch.tensor([layout.shift_to_right, 0.0, 0.0],
-                                    dtype=torch.float64, device=device)
+        self.shift_l = [layout.shift_to_left, 0.0, 0.0]
+        self.shift_r = [layout.shift_to_right, 0.0, 0.0]
+        f64 = dict(dtype=torch.float64, device=device)
+        self.send_pos_l = torch.empty((len(self.idx_l), 3), **f64)
+        self.send_pos_r = torch.empty((len(self.idx_r), 3), **f64)
+        self.send_fp_l = torch.empty(len(self.idx_l), **f64)
+        self.send_fp_r = torch.empty(len(self.idx_r), **f64)
         self.nbr = _lib.NeighborList()
         self.n_from_l = self.n_from_r = 0
         self.d_pos_loc = None
@@ -135,6 +138,9 @@ class SlabRank:
         n_halo = n_from_left + n_from_right
         self.d_pos_loc = t.empty((self.n_owned + n_halo, 3), dtype=t.float64,
                                  device=self.device)
+        # the owned positions LIVE in the head of the local array (no copy per step)
+        self.d_pos_owned = self.d_pos_loc[:self.n_owned]
+        self.d_pos_owned.copy_(self._pos0)
         self.d_fp_halo = t.zeros(max(n_halo, 1), dtype=t.float64, device=self.device)
         o = self.n_owned
         self.recv_pos_l = self.d_pos_loc[o:o + n_from_left]
@@ -144,13 +150,14 @@ class SlabRank:
 
     def pack_positions(self):
         p = self.d_pos_owned
-        self.d_pos_loc[:self.n_owned].copy_(p)
-        return (p.index_select(0, self.idx_l) + self.shift_l,
-                p.index_select(0, self.idx_r) + self.shift_r)
+        self._lib.pack_rows(p, self.idx_l, self.send_pos_l, self.shift_l)
+        self._lib.pack_rows(p, self.idx_r, self.send_pos_r, self.shift_r)
+        return self.send_pos_l, self.send_pos_r
 
     def pack_fprime(self):
-        return (self.d_fp.index_select(0, self.idx_l),
-                self.d_fp.index_select(0, self.idx_r))
+        self._lib.pack_rows(self.d_fp, self.idx_l, self.send_fp_l)
+        self._lib.pack_rows(self.d_fp, self.idx_r, self.send_fp_r)
+        return self.send_fp_l, self.send_fp_r
 
     # -- kernels -------------------------------------------------------------
     def build(self):
@@ -211,7 +218,7 @@ class SlabDomain:
     def _exchange_positions(self):
         r = self.rank_state
         s_l, s_r = r.pack_positions()
-        self.comm.exchange(s_l.contiguous(), s_r.contiguous(), r.recv_pos_l, r.recv_pos_r)
+        self.comm.exchange(s_l, s_r, r.recv_pos_l, r.recv_pos_r)
 
     def _exchange_fprime(self):
         r = self.rank_state
