@@ -265,6 +265,19 @@ int tab_atomic_eval(tab_atomic *model, tab_nbr *nbr, int32_t precision,
 int tab_atomic_descriptors(tab_atomic *model, tab_nbr *nbr, int32_t precision,
                            double *d_desc, void *stream);
 
+/* Training support ("PyTorch custom ops where tensors cross into training").
+ * With c = dE/dG [n, dim] (caller order) the forces and the virial are LINEAR in c:
+ *   tab_atomic_forces : F = J(R)^T c , W = sum_p g_p (x) D_p        (the forward op)
+ *   tab_atomic_jvp    : T = d/dc [ sum_a F_a.u_a + sum_ab A_ab W_ab ]  (its transpose;
+ *                       d_u [n,3], d_A [9] on the device, d_out [n, dim])
+ * so a force / stress loss back-propagates to the network parameters through c --
+ * what the reference obtains from TF second-order autograd (nn/opt.py:132-157). */
+int tab_atomic_forces(tab_atomic *model, tab_nbr *nbr, int32_t precision,
+                      const double *d_dedg, double *d_forces, double *d_virial,
+                      void *stream);
+int tab_atomic_jvp(tab_atomic *model, tab_nbr *nbr, int32_t precision,
+                   const double *d_u, const double *d_A, double *d_out, void *stream);
+
 /* Per-kernel timing of tab_eam_eval with CUDA events recorded on the launching
  * stream (used by bench.py for the roofline figures; off by default).
  * tab_profile_read synchronises the device; ms[0..3] = mean milliseconds of the

@@ -89,7 +89,7 @@ EXPORTS = [
     'tab_eam_create', 'tab_model_free', 'tab_eam_eval', 'tab_eam_pass1',
     'tab_eam_pass2', 'tab_eam_hessian', 'tab_eam_compute_host',
     'tab_atomic_create', 'tab_atomic_free', 'tab_atomic_dim', 'tab_atomic_eval',
-    'tab_atomic_descriptors',
+    'tab_atomic_descriptors', 'tab_atomic_forces', 'tab_atomic_jvp',
     'tab_launch_count', 'tab_launch_count_reset',
     'tab_profile_enable', 'tab_profile_read',
 ]
@@ -139,6 +139,8 @@ def lib():
     L.tab_atomic_dim.argtypes = [vp]
     L.tab_atomic_eval.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]
     L.tab_atomic_descriptors.argtypes = [vp, vp, i32, vp, vp]
+    L.tab_atomic_forces.argtypes = [vp, vp, i32, vp, vp, vp, vp]
+    L.tab_atomic_jvp.argtypes = [vp, vp, i32, vp, vp, vp, vp]
     L.tab_profile_enable.argtypes = [i32]
     L.tab_profile_read.argtypes = [C.POINTER(dbl), C.POINTER(i32)]
     L.tab_launch_count.restype = i64
@@ -409,6 +411,15 @@ class AtomicModel:
         check(lib().tab_atomic_eval(self._h, nbr.handle, int(precision), _ptr(energy),
                                     _ptr(eatom), _ptr(forces), _ptr(virial),
                                     _stream()), 'tab_atomic_eval')
+
+    def forces_from_dedg(self, nbr, dedg, forces, virial, precision=PRECISION_HIGH):
+        check(lib().tab_atomic_forces(self._h, nbr.handle, int(precision), _ptr(dedg),
+                                      _ptr(forces), _ptr(virial), _stream()),
+              'tab_atomic_forces')
+
+    def jvp(self, nbr, u, A, out, precision=PRECISION_HIGH):
+        check(lib().tab_atomic_jvp(self._h, nbr.handle, int(precision), _ptr(u), _ptr(A),
+                                   _ptr(out), _stream()), 'tab_atomic_jvp')
 
     def descriptors(self, nbr, precision=PRECISION_HIGH):
         import torch

@@ -582,6 +582,148 @@ k_sf_reduce(int nb_e, const double *__restrict__ partial_e, int nb_v,
     }
 }
 
+
+// ---------------------------------------------------------------------------
+// JVP: T[i, f] = sum_{p in row i} dG_{i,f}/dD_p . dD_p  with the per-pair
+// displacement  dD_p = u_i - u_owner(j) + A D_p.
+// This is the transpose of the force/virial assembly
+//   F = J^T c  (forces), W = sum_p g_p (x) D_p   with c = dE/dG:
+//   d/dc [ sum_a F_a.u_a + sum_ab A_ab W_ab ] = T.
+// It is the backward of the force op in training (force / stress losses need
+// d(loss)/d(parameters) through dE/dG) -- the reference gets it from TF's
+// second-order autograd (nn/opt.py:132-157).
+// ---------------------------------------------------------------------------
+template <typename Real>
+__global__ void __launch_bounds__(SF_WARPS * 32)
+k_sf_jvp(int n, int n_loc, SfDev sf, int n_types, int row_cap,
+         const Atom4 *__restrict__ atoms, const uint8_t *__restrict__ types_ext,
+         const int *__restrict__ counts, const int *__restrict__ tcounts,
+         const uint32_t *__restrict__ slice_ptr, const uint32_t *__restrict__ col,
+         const int *__restrict__ ghost_owner, const double *__restrict__ u,
+         const double *__restrict__ A, double *__restrict__ T) {
+    extern __shared__ __align__(16) double smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int idx = blockIdx.x * SF_WARPS + warp;
+    if (idx >= n) return;
+    double *row = smem + (size_t)warp * row_cap * (ROW_W + 4);
+    double *dd = row + (size_t)row_cap * ROW_W;          // [row_cap][4]: dD_p
+    const int cnt = stage_row<Real>(sf, idx, lane, atoms, counts, slice_ptr, col, row);
+    {
+        const uint32_t *cp = col + ((size_t)slice_ptr[idx >> 5] * 32u + (idx & 31));
+        const double ux = u[3 * (size_t)idx], uy = u[3 * (size_t)idx + 1],
+                     uz = u[3 * (size_t)idx + 2];
+        for (int k = lane; k < cnt; k += 32) {
+            int j = (int)(cp[(size_t)k * 32u] & TAB_COL_IDX_MASK);
+            if (j >= n_loc) j = ghost_owner[j - n_loc];
+            const double *e = row + (size_t)k * ROW_W;
+            dd[k * 4 + 0] = ux - u[3 * (size_t)j] + A[0] * e[0] + A[1] * e[1] + A[2] * e[2];
+            dd[k * 4 + 1] = uy - u[3 * (size_t)j + 1] + A[3] * e[0] + A[4] * e[1] + A[5] * e[2];
+            dd[k * 4 + 2] = uz - u[3 * (size_t)j + 2] + A[6] * e[0] + A[7] * e[1] + A[8] * e[2];
+        }
+        __syncwarp();
+    }
+    const int ti = (int)types_ext[idx];
+    double *t = T + (size_t)idx * sf.dim;
+    const Real rc = (Real)sf.rc, rc2i = Real(1) / (rc * rc);
+    const Real ac2i = Real(1) / ((Real)sf.acut * (Real)sf.acut);
+    int seg[TAB_MAX_ELEMENTS + 1];
+    seg[0] = 0;
+    for (int s = 0; s < sf.n_el; ++s)
+        seg[s + 1] = seg[s] + (s < n_types ? tcounts[(size_t)idx * n_types + s] : 0);
+    // ---- G2
+    for (int s = 0; s < sf.n_el; ++s) {
+        const int term = radial_term(ti, s);
+        for (int tau = 0; tau < sf.n_r; ++tau) {
+            const Real eta = (Real)sf.eta[tau], om = (Real)sf.omega[tau];
+            Real acc = Real(0);
+            for (int k = seg[s] + lane; k < seg[s + 1]; k += 32) {
+                const double *e = row + k * ROW_W;
+                const Real r = (Real)e[3];
+                Real f, df;
+                cutoff_fn<Real>(sf.cutoff, r, rc, f, df);
+                const Real d = r - om;
+                const Real ex = Math<Real>::exp_(-eta * d * d * rc2i);
+                const Real g1 = ex * df - Real(2) * eta * d * rc2i * ex * f;
+                const Real proj = ((Real)e[0] * (Real)dd[k * 4] + (Real)e[1] * (Real)dd[k * 4 + 1] +
+                                   (Real)e[2] * (Real)dd[k * 4 + 2]) / r;
+                acc += g1 * proj;
+            }
+            const double tot = warp_sum((double)acc);
+            if (lane == 0) t[term * sf.n_r + tau] = tot;
+        }
+    }
+    if (!sf.angular) return;
+    // ---- G4
+    for (int a = 0; a < sf.n_el; ++a)
+        for (int b = a; b < sf.n_el; ++b) {
+            const int pt = pair_term(a, b, sf.n_el);
+            Real acc[SF_MAX_A];
+            for (int tau = 0; tau < sf.n_a; ++tau) acc[tau] = Real(0);
+            for (int p = seg[a]; p < seg[a + 1]; ++p) {
+                const double *ep = row + p * ROW_W;
+                const Real fp = (Real)ep[4], dfp = (Real)ep[5];
+                if (fp == Real(0)) continue;
+                const Real px = (Real)ep[0], py = (Real)ep[1], pz = (Real)ep[2],
+                           r1 = (Real)ep[3];
+                const Real s1 = (px * (Real)dd[p * 4] + py * (Real)dd[p * 4 + 1] +
+                                 pz * (Real)dd[p * 4 + 2]) / r1;
+                const int q0 = (a == b) ? p + 1 : seg[b];
+                for (int q = q0 + lane; q < seg[b + 1]; q += 32) {
+                    const double *eq = row + q * ROW_W;
+                    const Real fq = (Real)eq[4], dfq = (Real)eq[5];
+                    if (fq == Real(0)) continue;
+                    const Real qx = (Real)eq[0], qy = (Real)eq[1], qz = (Real)eq[2],
+                               r2 = (Real)eq[3];
+                    const Real jx = qx - px, jy = qy - py, jz = qz - pz;
+                    const Real r3 = sqrt(jx * jx + jy * jy + jz * jz + Math<Real>::eps());
+                    Real f3, df3;
+                    cutoff_fn<Real>(sf.cutoff, r3, (Real)sf.acut, f3, df3);
+                    if (f3 == Real(0)) continue;
+                    const Real s2 = (qx * (Real)dd[q * 4] + qy * (Real)dd[q * 4 + 1] +
+                                     qz * (Real)dd[q * 4 + 2]) / r2;
+                    const Real s3 = (jx * ((Real)dd[q * 4] - (Real)dd[p * 4]) +
+                                     jy * ((Real)dd[q * 4 + 1] - (Real)dd[p * 4 + 1]) +
+                                     jz * ((Real)dd[q * 4 + 2] - (Real)dd[p * 4 + 2])) / r3;
+                    const Real ss = r1 * r1 + r2 * r2 + r3 * r3;
+                    const Real lower = Real(2) * r1 * r2;
+                    const bool ok = lower != Real(0);
+                    const Real ct = ok ? (r1 * r1 + r2 * r2 - r3 * r3) / lower : Real(0);
+                    const Real dc1 = ok ? Real(1) / r2 - ct / r1 : Real(0);
+                    const Real dc2 = ok ? Real(1) / r1 - ct / r2 : Real(0);
+                    const Real dc3 = ok ? -r3 / (r1 * r2) : Real(0);
+                    const Real F3 = fp * fq * f3;
+                    // directional derivative of the geometry-only factors
+                    const Real dct = dc1 * s1 + dc2 * s2 + dc3 * s3;
+                    const Real dss = Real(2) * (r1 * s1 + r2 * s2 + r3 * s3);
+                    const Real dF3 = dfp * s1 * fq * f3 + fp * dfq * s2 * f3 + fp * fq * df3 * s3;
+                    for (int tau = 0; tau < sf.n_a; ++tau) {
+                        const Real z = (Real)sf.zeta[tau], gm = (Real)sf.gamma[tau],
+                                   be = (Real)sf.beta[tau];
+                        Real dP;
+                        const Real P = powz<Real>(Real(1) + gm * ct, z, dP);
+                        const Real E = Math<Real>::exp_(-be * ss * ac2i);
+                        acc[tau] += exp2(Real(1) - z) *
+                                    (dP * gm * dct * E * F3 - be * ac2i * dss * P * E * F3 +
+                                     P * E * dF3);
+                    }
+                }
+            }
+            for (int tau = 0; tau < sf.n_a; ++tau) {
+                const double tot = warp_sum((double)acc[tau]);
+                if (lane == 0) t[sf.d_r + pt * sf.n_a + tau] = tot;
+            }
+        }
+}
+
+// caller order <-> sorted order row permutations
+__global__ void k_rows_to_sorted(int n, int w, const int *__restrict__ perm,
+                                 const double *__restrict__ src, double *__restrict__ dst) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)n * w) return;
+    const int idx = (int)(t / w), k = (int)(t % w);
+    dst[t] = src[(size_t)perm[idx] * w + k];
+}
+
 // sorted -> caller order copy of the descriptors
 __global__ void k_sf_export(int n, int dim, const int *__restrict__ perm,
                             const double *__restrict__ G, double *__restrict__ out) {
@@ -827,4 +969,117 @@ extern "C" int tab_atomic_descriptors(tab_atomic *m, tab_nbr *nbr, int32_t preci
     if (precision == TAB_PRECISION_HIGH)
         return atomic_run<double>(m, nbr, nullptr, nullptr, nullptr, nullptr, d_desc, st);
     return atomic_run<float>(m, nbr, nullptr, nullptr, nullptr, nullptr, d_desc, st);
+}
+
+// ---------------------------------------------------------------------------
+// training entry points: force/virial as a linear operator of c = dE/dG
+// ---------------------------------------------------------------------------
+static int atomic_common_checks(tab_atomic *m, tab_nbr *nbr, const char *who) {
+    if (!m || !nbr) {
+        tab_set_error("%s: null handle", who);
+        return TAB_EINVAL;
+    }
+    if (!nbr->built) {
+        tab_set_error("%s before tab_nbr_build", who);
+        return TAB_ESTATE;
+    }
+    if (nbr->n_halo > 0) {
+        tab_set_error("%s: halo atoms are not supported", who);
+        return TAB_EUNSUPPORTED;
+    }
+    return TAB_OK;
+}
+
+template <typename Real>
+static int atomic_forces_from(tab_atomic *m, tab_nbr *nbr, const double *d_dedg,
+                              double *d_forces, double *d_virial, cudaStream_t st) {
+    const int n = nbr->n;
+    const SfDev &sf = m->sf;
+    const int row_cap = nbr->nnl_max > 0 ? nbr->nnl_max : 1;
+    const size_t smem_row = (size_t)SF_WARPS * row_cap * ROW_W * sizeof(double);
+    TAB_CUDA(cudaFuncSetAttribute(k_sf_backward<Real>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    const int nblk = (n + SF_WARPS - 1) / SF_WARPS, nblk_c = (n + 127) / 128;
+    TAB_TRY(m->dEdG.ensure(sizeof(double) * (size_t)n * sf.dim));
+    TAB_TRY(m->eat.ensure(sizeof(double) * (size_t)n));
+    TAB_TRY(m->fown.ensure(sizeof(double) * 3 * (size_t)n));
+    TAB_TRY(nbr->partial.ensure(sizeof(double) * (8 * (size_t)nblk + nblk_c + 8)));
+    TAB_TRY(tab_nbr_ensure_reverse(nbr, st));
+    const size_t plane = (size_t)nbr->ell_rows * 32;
+    TAB_TRY(m->gvec.ensure(sizeof(double) * 3 * (plane + 32)));
+    const size_t tot = (size_t)n * sf.dim;
+    k_rows_to_sorted<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(
+        n, sf.dim, nbr->perm.as<int>(), d_dedg, m->dEdG.as<double>());
+    TAB_LAUNCH_CHECK();
+    TAB_CUDA(cudaMemsetAsync(m->eat.p, 0, sizeof(double) * (size_t)n, st));
+    double *partial = nbr->partial.as<double>();
+    k_sf_backward<Real><<<nblk, SF_WARPS * 32, smem_row, st>>>(
+        n, sf, nbr->n_types, row_cap, nbr->atoms.as<Atom4>(), nbr->types_ext.as<uint8_t>(),
+        nbr->counts.as<int>(), nbr->tcounts.as<int>(), nbr->slice_ptr.as<uint32_t>(),
+        nbr->col.as<uint32_t>(), m->dEdG.as<double>(), m->gvec.as<double>(), plane,
+        m->fown.as<double>(), partial);
+    TAB_LAUNCH_CHECK();
+    k_sf_collect<<<nblk_c, 128, 0, st>>>(
+        n, nbr->n_loc, nbr->counts.as<int>(), nbr->slice_ptr.as<uint32_t>(),
+        nbr->col.as<uint32_t>(), nbr->rev.as<uint32_t>(), nbr->ghost_owner.as<int>(),
+        nbr->perm.as<int>(), m->gvec.as<double>(), plane, m->fown.as<double>(),
+        m->eat.as<double>(), nullptr, d_forces, partial + 8 * (size_t)nblk);
+    TAB_LAUNCH_CHECK();
+    k_sf_reduce<<<1, 256, 0, st>>>(0, nullptr, nblk, partial, nullptr, d_virial);
+    TAB_LAUNCH_CHECK();
+    return TAB_OK;
+}
+
+extern "C" int tab_atomic_forces(tab_atomic *m, tab_nbr *nbr, int32_t precision,
+                                 const double *d_dedg, double *d_forces,
+                                 double *d_virial, void *stream) {
+    TAB_TRY(atomic_common_checks(m, nbr, "tab_atomic_forces"));
+    if (!d_dedg) return TAB_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (precision == TAB_PRECISION_HIGH)
+        return atomic_forces_from<double>(m, nbr, d_dedg, d_forces, d_virial, st);
+    return atomic_forces_from<float>(m, nbr, d_dedg, d_forces, d_virial, st);
+}
+
+template <typename Real>
+static int atomic_jvp(tab_atomic *m, tab_nbr *nbr, const double *d_u, const double *d_A,
+                      double *d_out, cudaStream_t st) {
+    const int n = nbr->n;
+    const SfDev &sf = m->sf;
+    const int row_cap = nbr->nnl_max > 0 ? nbr->nnl_max : 1;
+    const size_t smem = (size_t)SF_WARPS * row_cap * (ROW_W + 4) * sizeof(double);
+    if (smem > 200 * 1024) {
+        tab_set_error("neighbour rows of %d entries exceed the shared-memory budget", row_cap);
+        return TAB_EUNSUPPORTED;
+    }
+    TAB_CUDA(cudaFuncSetAttribute(k_sf_jvp<Real>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    const int nblk = (n + SF_WARPS - 1) / SF_WARPS;
+    TAB_TRY(m->fown.ensure(sizeof(double) * 3 * (size_t)n));
+    TAB_TRY(m->G.ensure(sizeof(double) * (size_t)n * sf.dim));
+    // u to sorted order
+    k_rows_to_sorted<<<(unsigned)(((size_t)n * 3 + 255) / 256), 256, 0, st>>>(
+        n, 3, nbr->perm.as<int>(), d_u, m->fown.as<double>());
+    TAB_LAUNCH_CHECK();
+    k_sf_jvp<Real><<<nblk, SF_WARPS * 32, smem, st>>>(
+        n, nbr->n_loc, sf, nbr->n_types, row_cap, nbr->atoms.as<Atom4>(),
+        nbr->types_ext.as<uint8_t>(), nbr->counts.as<int>(), nbr->tcounts.as<int>(),
+        nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>(), nbr->ghost_owner.as<int>(),
+        m->fown.as<double>(), d_A, m->G.as<double>());
+    TAB_LAUNCH_CHECK();
+    const size_t tot = (size_t)n * sf.dim;
+    k_sf_export<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(
+        n, sf.dim, nbr->perm.as<int>(), m->G.as<double>(), d_out);
+    TAB_LAUNCH_CHECK();
+    return TAB_OK;
+}
+
+extern "C" int tab_atomic_jvp(tab_atomic *m, tab_nbr *nbr, int32_t precision,
+                              const double *d_u, const double *d_A, double *d_out,
+                              void *stream) {
+    TAB_TRY(atomic_common_checks(m, nbr, "tab_atomic_jvp"));
+    if (!d_u || !d_A || !d_out) return TAB_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (precision == TAB_PRECISION_HIGH) return atomic_jvp<double>(m, nbr, d_u, d_A, d_out, st);
+    return atomic_jvp<float>(m, nbr, d_u, d_A, d_out, st);
 }

@@ -1,0 +1,223 @@
+"""
+Training step of AtomicNN (energy + force + stress loss with parameter
+gradients) -- the hot part of the reference's `BasicNN.model_fn` in TRAIN mode
+(nn/basic.py:920-1015: build -> get_total_loss :446-631 -> get_train_op
+nn/opt.py:89-166), structure-parallel over the GPUs with one flat gradient
+all-reduce (the reference's MirroredStrategy with MEAN variable aggregation,
+train/distribute_utils.py:84-159, potentials.py:41, atomic.py:155).
+
+"PyTorch custom ops where tensors cross into training": the geometry work stays
+in libtab200 --
+    G        = descriptors (tab_atomic_descriptors; constant w.r.t. parameters)
+    F, W     = SfForce(dE/dG)     (tab_atomic_forces: linear in dE/dG)
+    backward = tab_atomic_jvp     (the transpose of that linear map)
+-- while the tiny per-element MLPs run in torch so that autograd provides
+dE/dG (create_graph) and the parameter gradients of the force / stress terms,
+which the reference obtains from TF second-order autograd.
+"""
+import numpy as np
+import torch
+
+from tensoralloy_b200 import _lib
+from tensoralloy_b200.nn import losses
+from tensoralloy_b200.precision import get_float_dtype
+
+VOIGT = ((0, 0), (1, 1), (2, 2), (1, 2), (0, 2), (0, 1))
+
+
+class SfForce(torch.autograd.Function):
+    """forces [n,3] and virial [3,3] of ONE structure from c = dE/dG [n, dim]."""
+
+    @staticmethod
+    def forward(ctx, dedg, model, nbr, precision):
+        n = dedg.shape[0]
+        c = dedg.detach().to(torch.float64).contiguous()
+        forces = torch.empty((n, 3), dtype=torch.float64, device=c.device)
+        virial = torch.empty(9, dtype=torch.float64, device=c.device)
+        model.forces_from_dedg(nbr, c, forces, virial, precision)
+        ctx.model, ctx.nbr, ctx.precision = model, nbr, precision
+        ctx.shape, ctx.dtype = dedg.shape, dedg.dtype
+        return forces.to(dedg.dtype), virial.reshape(3, 3).to(dedg.dtype)
+
+    @staticmethod
+    def backward(ctx, g_forces, g_virial):
+        u = g_forces.detach().to(torch.float64).contiguous()
+        A = g_virial.detach().to(torch.float64).contiguous().reshape(9)
+        out = torch.empty(ctx.shape, dtype=torch.float64, device=u.device)
+        ctx.model.jvp(ctx.nbr, u, A, out, ctx.precision)
+        return out.to(ctx.dtype), None, None, None
+
+
+def allreduce_mean_(params, dist, world):
+    """Average the gradients of `params` over the ranks with ONE flat-buffer
+    all-reduce (reference: MirroredStrategy + VariableAggregation.MEAN,
+    train/distribute_utils.py:84-159, nn/eam/potentials/potentials.py:41)."""
+    flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1)
+                      for p in params])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    flat /= world
+    off = 0
+    for p in params:
+        n = p.numel()
+        p.grad = flat[off:off + n].reshape(p.shape).clone()
+        off += n
+    return flat
+
+
+def _activation(name):
+    name = name.lower()
+    F = torch.nn.functional
+    table = {'softplus': F.softplus, 'tanh': torch.tanh, 'relu': torch.relu,
+             'leaky_relu': lambda x: F.leaky_relu(x, 0.2), 'sigmoid': torch.sigmoid,
+             'softsign': F.softsign, 'elu': F.elu,
+             'squareplus': lambda x: 0.5 * (x + torch.sqrt(x * x + 4.0))}
+    return table[name]
+
+
+class AtomicNNTrainer:
+    """Holds the structures of this rank (lists built once, descriptors cached:
+    the geometry does not change during training) and the torch parameters."""
+
+    def __init__(self, nn, device='cuda', loss_weights=None, per_atom_energy=True):
+        self.nn = nn
+        self.device = device
+        self.dt = get_float_dtype()
+        self.tdtype = torch.float64 if self.dt.name == 'float64' else torch.float32
+        self.model = nn._device_model()          # geometry side (weights unused)
+        self.elements = nn.elements
+        self.loss_weights = dict(energy=1.0, forces=1.0, stress=1.0)
+        self.loss_weights.update(loss_weights or {})
+        self.per_atom_energy = per_atom_energy
+        self.params = []        # flat list of leaf tensors
+        self.layers = {}        # el -> dict(W=[...], b=[...], out_b, xlo, xhi)
+        for el in self.elements:
+            p = nn.mlp_params(el)
+            W = [self._leaf(w) for w in p['weights']]
+            b = [self._leaf(v) if v is not None else None for v in p['biases']]
+            self.layers[el] = dict(
+                W=W, b=b, act=_activation(p['activation']), resnet=p['use_resnet_dt'],
+                xlo=None if p['xlo'] is None else torch.tensor(p['xlo'], dtype=self.tdtype,
+                                                               device=device),
+                xhi=None if p['xhi'] is None else torch.tensor(p['xhi'], dtype=self.tdtype,
+                                                               device=device))
+        self.structures = []
+
+    def _leaf(self, arr):
+        t = torch.tensor(np.asarray(arr), dtype=self.tdtype, device=self.device,
+                         requires_grad=True)
+        self.params.append(t)
+        return t
+
+    # -- data ------------------------------------------------------------------
+    def add_structure(self, atoms, energy, forces, stress):
+        """Builds the lists + descriptors of one structure (kept on the device)."""
+        clf = self.nn.transformer
+        types = clf.get_types(atoms)
+        nbr = _lib.NeighborList()
+        cell, pbc = clf._cell_and_pbc(atoms)
+        d_pos = torch.tensor(np.ascontiguousarray(atoms.positions), dtype=torch.float64,
+                             device=self.device)
+        d_types = torch.tensor(types, dtype=torch.int32, device=self.device)
+        nbr.build(d_pos, d_types, cell, pbc, self.nn.required_cutoff())
+        G = self.model.descriptors(nbr, self.dt.tab_precision).to(self.tdtype)
+        t = lambda a: torch.tensor(np.asarray(a), dtype=self.tdtype, device=self.device)
+        self.structures.append(dict(
+            nbr=nbr, G=G, types=torch.tensor(types, dtype=torch.long, device=self.device),
+            n=len(atoms), volume=float(atoms.get_volume()), energy=t(energy),
+            forces=t(forces), stress=t(stress)))
+
+    # -- model -------------------------------------------------------------------
+    def _mlp(self, el, x):
+        L = self.layers[el]
+        if L['xlo'] is not None:
+            den = L['xhi'] - L['xlo']
+            x = torch.where(den == 0, torch.zeros_like(x), (L['xhi'] - x) / den)
+        h = x
+        nh = len(L['W']) - 1
+        for k in range(nh):
+            y = L['act'](h @ L['W'][k] + L['b'][k])
+            if k and L['resnet'] and L['W'][k].shape[1] == L['W'][k - 1].shape[1]:
+                h = y + h
+            else:
+                h = y
+        out = h @ L['W'][nh]
+        if L['b'][nh] is not None:
+            out = out + L['b'][nh]
+        return out[:, 0]
+
+    def total_loss(self, want_forces=True, want_stress=True):
+        """Loss of this rank's structures (reference semantics: each replica
+        evaluates the loss of its own sub-batch)."""
+        S = self.structures
+        G_all = torch.cat([s['G'] for s in S]).detach().requires_grad_(True)
+        types_all = torch.cat([s['types'] for s in S])
+        sid = torch.cat([torch.full((s['n'],), k, dtype=torch.long, device=self.device)
+                         for k, s in enumerate(S)])
+        e_atom = torch.zeros(G_all.shape[0], dtype=self.tdtype, device=self.device)
+        for a, el in enumerate(self.elements):
+            sel = torch.nonzero(types_all == a).reshape(-1)
+            if sel.numel():
+                e_atom = e_atom.index_add(0, sel, self._mlp(el, G_all[sel]))
+        E = torch.zeros(len(S), dtype=self.tdtype, device=self.device).index_add(
+            0, sid, e_atom)
+        n_atoms = torch.tensor([s['n'] for s in S], device=self.device)
+        labels_e = torch.stack([s['energy'] for s in S])
+        w = self.loss_weights
+        loss = losses.energy_loss(labels_e, E, n_atoms, self.per_atom_energy, w['energy'])
+        parts = {'energy': loss.detach()}
+        if want_forces or want_stress:
+            dedg = torch.autograd.grad(E.sum(), G_all, create_graph=True)[0]
+            F_list, S_list = [], []
+            off = 0
+            for s in S:
+                f, W = SfForce.apply(dedg[off:off + s['n']], self.model, s['nbr'],
+                                     self.dt.tab_precision)
+                off += s['n']
+                F_list.append(f)
+                st = W / s['volume']
+                S_list.append(torch.stack([st[a, b] for a, b in VOIGT]))
+            if want_forces:
+                lf = losses.forces_loss(torch.cat([s['forces'] for s in S]),
+                                        torch.cat(F_list), w['forces'])
+                loss = loss + lf
+                parts['forces'] = lf.detach()
+            if want_stress:
+                ls = losses.stress_loss(torch.stack([s['stress'] for s in S]),
+                                        torch.stack(S_list), w['stress'])
+                loss = loss + ls
+                parts['stress'] = ls.detach()
+        return loss, parts
+
+    # -- one optimisation step ---------------------------------------------------
+    def gradients(self, want_forces=True, want_stress=True):
+        for p in self.params:
+            p.grad = None
+        loss, parts = self.total_loss(want_forces, want_stress)
+        loss.backward()
+        return loss.detach(), parts
+
+    def allreduce_gradients(self, dist, world):
+        allreduce_mean_(self.params, dist, world)
+
+    def train_step(self, optimizer, dist=None, world=1):
+        loss, parts = self.gradients()
+        if dist is not None and world > 1:
+            self.allreduce_gradients(dist, world)
+        optimizer.step()
+        return loss, parts
+
+    def sync_to_model(self):
+        """Write the trained parameters back into the AtomicNN variables."""
+        for el in self.elements:
+            L = self.layers[el]
+            nh = len(L['W']) - 1
+            for k in range(nh):
+                self.nn.set_variable(f"{self.nn.scope}/{el}/Conv1d{k + 1}/kernel",
+                                     L['W'][k].detach().cpu().numpy()[None])
+                self.nn.set_variable(f"{self.nn.scope}/{el}/Conv1d{k + 1}/bias",
+                                     L['b'][k].detach().cpu().numpy())
+            self.nn.set_variable(f"{self.nn.scope}/{el}/Output/kernel",
+                                 L['W'][nh].detach().cpu().numpy()[None])
+            if L['b'][nh] is not None:
+                self.nn.set_variable(f"{self.nn.scope}/{el}/Output/bias",
+                                     L['b'][nh].detach().cpu().numpy())

@@ -86,3 +86,39 @@ def test_ring_exchange_gloo(world):
     for rank, ok, total_ok in results:
         assert ok, f"rank {rank}: local neighbourhood differs from the global one"
         assert total_ok, "owned atoms do not partition the structure"
+
+
+def _grad_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from tensoralloy_b200.nn.atomic.training import allreduce_mean_
+        a = torch.zeros(3, 2, dtype=torch.float64, requires_grad=True)
+        b = torch.zeros(4, dtype=torch.float64, requires_grad=True)
+        a.grad = torch.full((3, 2), float(rank + 1), dtype=torch.float64)
+        b.grad = None if rank == 0 else torch.arange(4, dtype=torch.float64)
+        allreduce_mean_([a, b], dist, world)
+        q.put((rank, a.grad.tolist(), b.grad.tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_flat_gradient_allreduce_mean_gloo():
+    """Structure-parallel training: one flat all-reduce, MEAN aggregation
+    (train/distribute_utils.py:84-159; potentials.py:41)."""
+    world = 2
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_grad_worker, args=(r, world, port, q))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, ga, gb in results:
+        assert ga == [[1.5, 1.5]] * 3
+        assert gb == [0.0, 0.5, 1.0, 1.5]
