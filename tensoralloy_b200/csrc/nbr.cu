@@ -7,13 +7,14 @@
 // Pipeline (all on the caller's stream):
 //   k_bin          scaled coords -> owned-cell rank (+ wrap shift), histogram
 //   scan           cell_count -> cell_start
-//   k_scatter      atoms -> cell-sorted permutation (then k_sort_cells makes the
+//   k_scatter      atoms -> cell-sorted permutation (then k_rank_in_cell makes the
 //                  order inside a cell = caller index order: deterministic)
 //   k_gather_owned wrapped positions in sorted order -> Atom4 records
 //   k_ext_cells    extended (ghost-padded) cell table; ghost counts
 //   scan           ghost counts -> ghost starts
 //   k_fill_ghosts  ghost records = source record + S.h
-//   k_count        neighbours per atom, slice widths, nij, nnl_max
+//   k_count / k_nbr_warp<false>  neighbours per atom (thread- or warp-per-atom with
+//                  __ballot_sync compaction), k_slice_stats: slice widths, nij, nnl_max
 //   scan           slice widths -> slice_ptr
 //   k_fill         ELL entries, 32 atoms per slice, entry k of lane l at
 //                  col[(slice_ptr[s] + k) * 32 + l]  (coalesced for thread-per-atom
@@ -111,23 +112,20 @@ __global__ void k_scatter(int n, const int *__restrict__ cell_of,
     perm[cell_start[rank] + slot] = i;
 }
 
-// order inside a cell = ascending caller index (removes the atomics' race order)
-__global__ void k_sort_cells(int n_slots, const uint32_t *__restrict__ cell_start,
-                             const uint32_t *__restrict__ cell_count,
-                             int *__restrict__ perm) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n_slots) return;
-    const int cnt = (int)cell_count[c];
-    int *p = perm + cell_start[c];
-    for (int a = 1; a < cnt; ++a) {
-        const int v = p[a];
-        int b = a - 1;
-        while (b >= 0 && p[b] > v) {
-            p[b + 1] = p[b];
-            --b;
-        }
-        p[b + 1] = v;
-    }
+// order inside a cell = ascending caller index (removes the atomics' race order):
+// every atom counts the members of its cell with a smaller index -> its rank.
+__global__ void k_rank_in_cell(int n, const int *__restrict__ cell_of,
+                               const uint32_t *__restrict__ cell_start,
+                               const uint32_t *__restrict__ cell_count,
+                               const int *__restrict__ perm_in,
+                               int *__restrict__ perm_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c = cell_of[i];
+    const uint32_t start = cell_start[c], cnt = cell_count[c];
+    uint32_t rank = 0;
+    for (uint32_t k = 0; k < cnt; ++k) rank += perm_in[start + k] < i ? 1u : 0u;
+    perm_out[start + rank] = i;
 }
 
 __global__ void k_gather_owned(int n, const double *__restrict__ pos,
@@ -328,42 +326,30 @@ __device__ __forceinline__ void for_each_neighbor(
     }
 }
 
+// ---- thread-per-atom variants (large systems: lanes = the 32 atoms of a slice,
+//      candidate loads are warp-wide broadcasts)
 __global__ void __launch_bounds__(128)
 k_count(int n, Grid g, ExactCtx x, const int *__restrict__ cell_of,
         const Atom4 *__restrict__ atoms, const uint4 *__restrict__ ext_tab,
         const uint8_t *__restrict__ types_ext, int n_types,
-        int *__restrict__ counts, int *__restrict__ tcounts,
-        uint32_t *__restrict__ slice_w, unsigned long long *__restrict__ stats) {
+        int *__restrict__ counts, int *__restrict__ tcounts) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
     int cnt = 0;
-    if (idx < n) {
-        const int rank = cell_of[x.perm[idx]];
-        if (n_types > 1) {
-            int tc[TAB_MAX_ELEMENTS];
-            for (int t = 0; t < n_types; ++t) tc[t] = 0;
-            for_each_neighbor(g, x, idx, rank, atoms, ext_tab, [&](int j) {
-                ++cnt;
-                ++tc[types_ext[j]];
-            });
-            for (int t = 0; t < n_types; ++t) tcounts[(size_t)idx * n_types + t] = tc[t];
-        } else {
-            for_each_neighbor(g, x, idx, rank, atoms, ext_tab, [&](int) { ++cnt; });
-            tcounts[idx] = cnt;
-        }
-        counts[idx] = cnt;
+    const int rank = cell_of[x.perm[idx]];
+    if (n_types > 1) {
+        int tc[TAB_MAX_ELEMENTS];
+        for (int t = 0; t < n_types; ++t) tc[t] = 0;
+        for_each_neighbor(g, x, idx, rank, atoms, ext_tab, [&](int j) {
+            ++cnt;
+            ++tc[types_ext[j]];
+        });
+        for (int t = 0; t < n_types; ++t) tcounts[(size_t)idx * n_types + t] = tc[t];
+    } else {
+        for_each_neighbor(g, x, idx, rank, atoms, ext_tab, [&](int) { ++cnt; });
+        tcounts[idx] = cnt;
     }
-    // slice width = warp max, nij = sum, nnl_max = max
-    int mx = cnt, sum = cnt;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
-        sum += __shfl_xor_sync(0xffffffffu, sum, d);
-    }
-    if ((threadIdx.x & 31) == 0 && idx < n) {
-        slice_w[idx >> 5] = (uint32_t)mx;
-        atomicAdd(&stats[0], (unsigned long long)sum);
-        atomicMax(&stats[1], (unsigned long long)mx);
-    }
+    counts[idx] = cnt;
 }
 
 __global__ void __launch_bounds__(128)
@@ -403,6 +389,132 @@ k_fill(int n, Grid g, ExactCtx x, const int *__restrict__ cell_of,
     }
     const uint32_t w = slice_w[s];
     for (; k < w; ++k) base[(size_t)k * 32u] = TAB_COL_PAD;
+}
+
+// ---- warp-per-atom variants (small systems: the 32 lanes test 32 candidates at a
+//      time, __ballot_sync compaction keeps the deterministic candidate order).
+//      FILL = false: count only.
+template <bool FILL>
+__global__ void __launch_bounds__(128)
+k_nbr_warp(int n, Grid g, ExactCtx x, const int *__restrict__ cell_of,
+           const Atom4 *__restrict__ atoms, const uint8_t *__restrict__ types_ext,
+           const uint4 *__restrict__ ext_tab, int n_types, int *__restrict__ counts,
+           int *__restrict__ tcounts, const uint32_t *__restrict__ slice_w,
+           const uint32_t *__restrict__ slice_ptr, uint32_t *__restrict__ col) {
+    const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (idx >= n) return;
+    const uint32_t lt = (1u << lane) - 1u;
+    int cx, cy, cz;
+    owned_unrank(g, cell_of[x.perm[idx]], cx, cy, cz);
+    const Atom4 me = atoms[idx];
+    const double tol = 1e-9 * g.rc2;
+    uint32_t off[TAB_MAX_ELEMENTS];
+    uint32_t total = 0;
+    if (FILL) {
+        uint32_t run = 0;
+        for (int t = 0; t < n_types; ++t) {
+            off[t] = run;
+            run += (uint32_t)tcounts[(size_t)idx * n_types + t];
+        }
+    } else {
+        for (int t = 0; t < n_types; ++t) off[t] = 0;
+    }
+    uint32_t *base = FILL ? col + ((size_t)slice_ptr[idx >> 5] * 32u + (idx & 31)) : nullptr;
+    for (int dz = -g.sr[2]; dz <= g.sr[2]; ++dz) {
+        const int ez = cz + dz;
+        if (!g.pbc[2] && (ez < 0 || ez >= g.nb[2])) continue;
+        for (int dy = -g.sr[1]; dy <= g.sr[1]; ++dy) {
+            const int ey = cy + dy;
+            if (!g.pbc[1] && (ey < 0 || ey >= g.nb[1])) continue;
+            for (int dx = -g.sr[0]; dx <= g.sr[0]; ++dx) {
+                const int ex = cx + dx;
+                if (!g.pbc[0] && (ex < 0 || ex >= g.nb[0])) continue;
+                const int lin = ((ez + g.g[2]) * g.ne[1] + (ey + g.g[1])) * g.ne[0] +
+                                (ex + g.g[0]);
+                const uint4 t4 = ext_tab[lin];
+#pragma unroll
+                for (int part = 0; part < 2; ++part) {
+                    const uint32_t start = part ? t4.z : t4.x;
+                    const uint32_t cnt = part ? t4.w : t4.y;
+                    for (uint32_t k0 = 0; k0 < cnt; k0 += 32) {
+                        const uint32_t k = k0 + lane;
+                        bool in = false;
+                        int j = 0;
+                        if (k < cnt) {
+                            j = (int)(start + k);
+                            if (j != idx) {
+                                const Atom4 a = atoms[j];
+                                const double ddx = a.x - me.x, ddy = a.y - me.y,
+                                             ddz = a.z - me.z;
+                                const double d2 = ddx * ddx + ddy * ddy + ddz * ddz;
+                                in = d2 < g.rc2;
+                                if (fabs(d2 - g.rc2) <= tol) in = exact_inside(g, x, idx, j);
+                            }
+                        }
+                        const uint32_t t = in ? types_ext[j] : 0u;
+                        if (n_types == 1) {
+                            const uint32_t m = __ballot_sync(0xffffffffu, in);
+                            if (FILL && in)
+                                base[(size_t)(off[0] + __popc(m & lt)) * 32u] = (uint32_t)j;
+                            off[0] += __popc(m);
+                        } else {
+                            for (int s = 0; s < n_types; ++s) {
+                                const uint32_t m = __ballot_sync(0xffffffffu, in && t == (uint32_t)s);
+                                if (FILL && in && t == (uint32_t)s)
+                                    base[(size_t)(off[s] + __popc(m & lt)) * 32u] =
+                                        (uint32_t)j | (t << TAB_COL_TYPE_SHIFT);
+                                off[s] += __popc(m);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (!FILL) {
+        for (int t = 0; t < n_types; ++t) total += off[t];
+        if (lane == 0) {
+            counts[idx] = (int)total;
+            for (int t = 0; t < n_types; ++t) tcounts[(size_t)idx * n_types + t] = (int)off[t];
+        }
+    } else {
+        // pad the rest of this atom's column up to the slice width
+        const uint32_t w = slice_w[idx >> 5];
+        const uint32_t have = (uint32_t)counts[idx];
+        for (uint32_t k = have + lane; k < w; k += 32) base[(size_t)k * 32u] = TAB_COL_PAD;
+    }
+}
+
+// slice widths (max count of the 32 atoms of a slice), nij, nnl_max; pads the
+// columns of the non-existent atoms of the last slice
+__global__ void k_slice_stats(int n, const int *__restrict__ counts,
+                              uint32_t *__restrict__ slice_w,
+                              unsigned long long *__restrict__ stats) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int cnt = idx < n ? counts[idx] : 0;
+    int mx = cnt, sum = cnt;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+        sum += __shfl_xor_sync(0xffffffffu, sum, d);
+    }
+    if ((threadIdx.x & 31) == 0 && idx < n) {
+        slice_w[idx >> 5] = (uint32_t)mx;
+        atomicAdd(&stats[0], (unsigned long long)sum);
+        atomicMax(&stats[1], (unsigned long long)mx);
+    }
+}
+
+// columns of the padding lanes of the last (partial) slice
+__global__ void k_pad_tail(int n, const uint32_t *__restrict__ slice_w,
+                           const uint32_t *__restrict__ slice_ptr,
+                           uint32_t *__restrict__ col) {
+    const int lane = threadIdx.x & 31;
+    const int s = (n - 1) >> 5;
+    if (s * 32 + lane < n) return;
+    uint32_t *base = col + ((size_t)slice_ptr[s] * 32u + lane);
+    for (uint32_t k = 0; k < slice_w[s]; ++k) base[(size_t)k * 32u] = TAB_COL_PAD;
 }
 
 __global__ void k_scatter_counts(int n, const int *__restrict__ perm,
@@ -453,17 +565,19 @@ __global__ void k_export(int n, int n_loc, const int *__restrict__ perm,
 // gradient g_p = dE_i/dD_p is not symmetric in the pair (symmetry functions):
 //   F_i = sum_{p in row i} g_p - sum_{p in row i} g_rev(p).
 #define TAB_REV_NONE 0xFFFFFFFFu
+// one block per atom, one thread per row entry (the serial version took 2 ms for
+// a 128-atom structure: 90 x 90 dependent loads in a single thread)
 __global__ void __launch_bounds__(128)
 k_build_reverse(int n, int n_loc, const int *__restrict__ counts,
                 const uint32_t *__restrict__ slice_ptr,
                 const uint32_t *__restrict__ col, const int *__restrict__ ghost_owner,
                 const int *__restrict__ ghost_S, uint32_t *__restrict__ rev) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int idx = blockIdx.x;
     if (idx >= n) return;
     const size_t base = (size_t)slice_ptr[idx >> 5] * 32u + (idx & 31);
     const int cnt = counts[idx];
     const int zero = tab_pack_shift(0, 0, 0);
-    for (int k = 0; k < cnt; ++k) {
+    for (int k = threadIdx.x; k < cnt; k += blockDim.x) {
         const int j = (int)(col[base + (size_t)k * 32u] & TAB_COL_IDX_MASK);
         int o = j, S = zero;
         if (j >= n_loc) {
@@ -666,14 +780,15 @@ extern "C" int tab_nbr_build_dd(tab_nbr *nbr, int32_t n_owned, int32_t n_halo,
     TAB_TRY(tab_scan_exclusive_u32(nbr->cell_count.as<uint32_t>(),
                                    nbr->cell_start.as<uint32_t>(), slots2, nullptr,
                                    nbr->scan_tmp, st));
+    TAB_TRY(nbr->row_ptr.ensure(sizeof(int) * (size_t)n_loc));      // scratch: raw order
     k_scatter<<<nblocks(n_loc, 256), 256, 0, st>>>(n_loc, nbr->cell_of.as<int>(),
                                                    nbr->cell_start.as<uint32_t>(),
                                                    nbr->cell_fill.as<uint32_t>(),
-                                                   nbr->perm.as<int>());
+                                                   nbr->row_ptr.as<int>());
     TAB_LAUNCH_CHECK();
-    k_sort_cells<<<nblocks(slots2, 128), 128, 0, st>>>(
-        slots2, nbr->cell_start.as<uint32_t>(), nbr->cell_count.as<uint32_t>(),
-        nbr->perm.as<int>());
+    k_rank_in_cell<<<nblocks(n_loc, 256), 256, 0, st>>>(
+        n_loc, nbr->cell_of.as<int>(), nbr->cell_start.as<uint32_t>(),
+        nbr->cell_count.as<uint32_t>(), nbr->row_ptr.as<int>(), nbr->perm.as<int>());
     TAB_LAUNCH_CHECK();
 
     // ghost bookkeeping -> n_ghost (one small read-back)
@@ -727,12 +842,23 @@ extern "C" int tab_nbr_build_dd(tab_nbr *nbr, int32_t n_owned, int32_t n_halo,
     x.ghost_S = nbr->ghost_S.as<int>();
     x.n_loc = n_loc;
     const int nthreads = nbr->n_slices * 32;
+    // small systems: one warp per atom (parallelism); large: one thread per atom
+    const bool warp_mode = n_loc <= 20000;
     TAB_TRY(nbr->tcounts.ensure(sizeof(int) * (size_t)n * nbr->n_types));
-    k_count<<<nblocks(nthreads, 128), 128, 0, st>>>(
-        n, g, x, nbr->cell_of.as<int>(), nbr->atoms.as<Atom4>(),
-        nbr->ext_tab.as<uint4>(), nbr->types_ext.as<uint8_t>(), nbr->n_types,
-        nbr->counts.as<int>(), nbr->tcounts.as<int>(), nbr->slice_w.as<uint32_t>(),
-        d_stats);
+    if (warp_mode) {
+        k_nbr_warp<false><<<nblocks((long long)n * 32, 128), 128, 0, st>>>(
+            n, g, x, nbr->cell_of.as<int>(), nbr->atoms.as<Atom4>(),
+            nbr->types_ext.as<uint8_t>(), nbr->ext_tab.as<uint4>(), nbr->n_types,
+            nbr->counts.as<int>(), nbr->tcounts.as<int>(), nullptr, nullptr, nullptr);
+    } else {
+        k_count<<<nblocks(n, 128), 128, 0, st>>>(
+            n, g, x, nbr->cell_of.as<int>(), nbr->atoms.as<Atom4>(),
+            nbr->ext_tab.as<uint4>(), nbr->types_ext.as<uint8_t>(), nbr->n_types,
+            nbr->counts.as<int>(), nbr->tcounts.as<int>());
+    }
+    TAB_LAUNCH_CHECK();
+    k_slice_stats<<<nblocks(nthreads, 128), 128, 0, st>>>(
+        n, nbr->counts.as<int>(), nbr->slice_w.as<uint32_t>(), d_stats);
     TAB_LAUNCH_CHECK();
     TAB_TRY(tab_scan_exclusive_u32(nbr->slice_w.as<uint32_t>(),
                                    nbr->slice_ptr.as<uint32_t>(), nbr->n_slices,
@@ -748,12 +874,27 @@ extern "C" int tab_nbr_build_dd(tab_nbr *nbr, int32_t n_owned, int32_t n_halo,
         return TAB_EUNSUPPORTED;
     }
     TAB_TRY(nbr->col.ensure(sizeof(uint32_t) * 32 * (size_t)(nbr->ell_rows + 1)));
-    k_fill<<<nblocks(nthreads, 128), 128, 0, st>>>(
-        n, g, x, nbr->cell_of.as<int>(), nbr->atoms.as<Atom4>(),
-        nbr->types_ext.as<uint8_t>(), nbr->ext_tab.as<uint4>(), nbr->n_types,
-        nbr->tcounts.as<int>(), nbr->slice_w.as<uint32_t>(),
-        nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>());
-    TAB_LAUNCH_CHECK();
+    if (warp_mode) {
+        k_nbr_warp<true><<<nblocks((long long)n * 32, 128), 128, 0, st>>>(
+            n, g, x, nbr->cell_of.as<int>(), nbr->atoms.as<Atom4>(),
+            nbr->types_ext.as<uint8_t>(), nbr->ext_tab.as<uint4>(), nbr->n_types,
+            nbr->counts.as<int>(), nbr->tcounts.as<int>(), nbr->slice_w.as<uint32_t>(),
+            nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>());
+        TAB_LAUNCH_CHECK();
+        if (n & 31) {
+            k_pad_tail<<<1, 32, 0, st>>>(n, nbr->slice_w.as<uint32_t>(),
+                                         nbr->slice_ptr.as<uint32_t>(),
+                                         nbr->col.as<uint32_t>());
+            TAB_LAUNCH_CHECK();
+        }
+    } else {
+        k_fill<<<nblocks(nthreads, 128), 128, 0, st>>>(
+            n, g, x, nbr->cell_of.as<int>(), nbr->atoms.as<Atom4>(),
+            nbr->types_ext.as<uint8_t>(), nbr->ext_tab.as<uint4>(), nbr->n_types,
+            nbr->tcounts.as<int>(), nbr->slice_w.as<uint32_t>(),
+            nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>());
+        TAB_LAUNCH_CHECK();
+    }
     nbr->built = true;
     return TAB_OK;
 }
@@ -828,7 +969,7 @@ extern "C" int tab_nbr_export(const tab_nbr *cnbr, int32_t *d_i, int32_t *d_j,
 int tab_nbr_ensure_reverse(tab_nbr *nbr, cudaStream_t st) {
     if (nbr->has_rev) return TAB_OK;
     TAB_TRY(nbr->rev.ensure(sizeof(uint32_t) * 32 * (size_t)(nbr->ell_rows + 1)));
-    k_build_reverse<<<nblocks(nbr->n, 128), 128, 0, st>>>(
+    k_build_reverse<<<nbr->n, 128, 0, st>>>(
         nbr->n, nbr->n_loc, nbr->counts.as<int>(), nbr->slice_ptr.as<uint32_t>(),
         nbr->col.as<uint32_t>(), nbr->ghost_owner.as<int>(), nbr->ghost_S.as<int>(),
         nbr->rev.as<uint32_t>());

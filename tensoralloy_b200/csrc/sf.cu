@@ -12,14 +12,15 @@
 //   nn/basic.py:276-331        F = -dE/dR, virial (TF autograd -> analytic backward)
 //
 // Structure (all atomic-free, deterministic):
-//   k_sf_forward   warp per centre atom; its neighbour row (species-sorted) is staged
-//                  in shared memory; lanes stride over neighbours (G2) and over the
-//                  second index of the j<k pairs (G4); warp-shuffle reduction.
+//   k_sf_forward   block (128 threads) per centre atom; its neighbour row
+//                  (species-sorted) is staged in shared memory; threads stride over
+//                  neighbours (G2) and over the second index of the j<k pairs (G4);
+//                  fixed-order block reduction.
 //   k_mlp          warp per atom: forward + backward through the element's MLP,
 //                  giving E_i and dE_i/dG_i.
-//   k_sf_backward  warp per centre atom: E_i depends on the D vectors of row i only,
+//   k_sf_backward  block per centre atom: E_i depends on the D vectors of row i only,
 //                  so g_p = dE_i/dD_p is computed for every entry p of the row by the
-//                  lane that owns p (each unordered triple is visited from both of
+//                  thread that owns p (each unordered triple is visited from both of
 //                  its legs -> no reduction, no atomics); g_p is stored per entry,
 //                  sum_p g_p and sum_p g_p (x) D_p are accumulated on the fly.
 //   k_sf_collect   thread per atom: F_i = sum_p g_p - sum_p g_rev(p)  (reverse-pair
@@ -28,7 +29,9 @@
 
 #define SF_MAX_R 32      // radial parameter sets
 #define SF_MAX_A 32      // angular parameter sets
-#define SF_WARPS 4       // warps (= atoms) per block
+#define SF_WARPS 4       // warps per block of the geometry kernels: ONE ATOM PER BLOCK
+#define SF_TPA (SF_WARPS * 32)   // threads cooperating on one centre atom
+#define MLP_WARPS 1      // k_mlp: one warp (= one atom) per block
 #define MLP_MAX_LAYERS 8
 #define MLP_MAX_WIDTH 256
 
@@ -100,7 +103,7 @@ __device__ __forceinline__ Real powz(Real base, Real z, Real &dpow) {
 #define ROW_W 8
 
 template <typename Real>
-__device__ __forceinline__ int stage_row(const SfDev &sf, int idx, int lane,
+__device__ __forceinline__ int stage_row(const SfDev &sf, int idx, int lane, int nthr,
                                          const Atom4 *__restrict__ atoms,
                                          const int *__restrict__ counts,
                                          const uint32_t *__restrict__ slice_ptr,
@@ -109,7 +112,7 @@ __device__ __forceinline__ int stage_row(const SfDev &sf, int idx, int lane,
     const Atom4 me = atoms[idx];
     const int cnt = counts[idx];
     const uint32_t *cp = col + ((size_t)slice_ptr[idx >> 5] * 32u + (idx & 31));
-    for (int k = lane; k < cnt; k += 32) {
+    for (int k = lane; k < cnt; k += nthr) {
         const uint32_t c = cp[(size_t)k * 32u];
         const Atom4 a = atoms[c & TAB_COL_IDX_MASK];
         const double dx = a.x - me.x, dy = a.y - me.y, dz = a.z - me.z;
@@ -126,8 +129,21 @@ __device__ __forceinline__ int stage_row(const SfDev &sf, int idx, int lane,
         e[5] = df;
         e[6] = (double)(c >> TAB_COL_TYPE_SHIFT);
     }
-    __syncwarp();
+    __syncthreads();
     return cnt;
+}
+
+// sum over the SF_TPA threads of a block, result on every thread; fixed order
+__device__ __forceinline__ double block_sum(double v, double *red) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < SF_WARPS; ++w) t += red[w];
+    __syncthreads();
+    return t;
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -157,11 +173,12 @@ k_sf_forward(int n, SfDev sf, int n_types, int row_cap,
              const uint32_t *__restrict__ slice_ptr, const uint32_t *__restrict__ col,
              double *__restrict__ G) {
     extern __shared__ __align__(16) double smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int idx = blockIdx.x * SF_WARPS + warp;
+    __shared__ double red[SF_WARPS];
+    const int lane = threadIdx.x;           // thread index inside the atom's block
+    const int idx = blockIdx.x;
     if (idx >= n) return;
-    double *row = smem + (size_t)warp * row_cap * ROW_W;
-    const int cnt = stage_row<Real>(sf, idx, lane, atoms, counts, slice_ptr, col, row);
+    double *row = smem;
+    const int cnt = stage_row<Real>(sf, idx, lane, SF_TPA, atoms, counts, slice_ptr, col, row);
     const int ti = (int)types_ext[idx];
     double *g = G + (size_t)idx * sf.dim;
     const Real rc = (Real)sf.rc, rc2i = Real(1) / (rc * rc);
@@ -178,14 +195,14 @@ k_sf_forward(int n, SfDev sf, int n_types, int row_cap,
         for (int tau = 0; tau < sf.n_r; ++tau) {
             const Real eta = (Real)sf.eta[tau], om = (Real)sf.omega[tau];
             Real acc = Real(0);
-            for (int k = seg[t] + lane; k < seg[t + 1]; k += 32) {
+            for (int k = seg[t] + lane; k < seg[t + 1]; k += SF_TPA) {
                 const Real r = (Real)row[k * ROW_W + 3];
                 Real f, df;
                 cutoff_fn<Real>(sf.cutoff, r, rc, f, df);
                 const Real d = r - om;
                 acc += Math<Real>::exp_(-eta * d * d * rc2i) * f;
             }
-            const double tot = warp_sum((double)acc);
+            const double tot = block_sum((double)acc, red);
             if (lane == 0) g[term * sf.n_r + tau] = tot;
         }
     }
@@ -203,7 +220,7 @@ k_sf_forward(int n, SfDev sf, int n_types, int row_cap,
                 const Real px = (Real)ep[0], py = (Real)ep[1], pz = (Real)ep[2],
                            r1 = (Real)ep[3];
                 const int q0 = (a == b) ? p + 1 : seg[b];
-                for (int q = q0 + lane; q < seg[b + 1]; q += 32) {
+                for (int q = q0 + lane; q < seg[b + 1]; q += SF_TPA) {
                     const double *eq = row + q * ROW_W;
                     const Real fq = (Real)eq[4];
                     if (fq == Real(0)) continue;
@@ -219,17 +236,20 @@ k_sf_forward(int n, SfDev sf, int n_types, int row_cap,
                     const Real ct = lower != Real(0)
                                         ? (r1 * r1 + r2 * r2 - r3 * r3) / lower : Real(0);
                     const Real fc = fp * (fq * f3);
+                    Real E = Real(0);
                     for (int tau = 0; tau < sf.n_a; ++tau) {
                         Real dp;
                         const Real z = (Real)sf.zeta[tau];
                         const Real pw = powz<Real>(Real(1) + (Real)sf.gamma[tau] * ct, z, dp);
-                        acc[tau] += pw * (Math<Real>::exp_(-(Real)sf.beta[tau] * s2 * ac2i) * fc) *
-                                    exp2(Real(1) - z);
+                        // the exponential depends on beta only (grid: beta outermost)
+                        if (tau == 0 || sf.beta[tau] != sf.beta[tau - 1])
+                            E = Math<Real>::exp_(-(Real)sf.beta[tau] * s2 * ac2i);
+                        acc[tau] += pw * (E * fc) * exp2(Real(1) - z);
                     }
                 }
             }
             for (int tau = 0; tau < sf.n_a; ++tau) {
-                const double tot = warp_sum((double)acc[tau]);
+                const double tot = block_sum((double)acc[tau], red);
                 if (lane == 0) g[sf.d_r + pt * sf.n_a + tau] = tot;
             }
         }
@@ -284,13 +304,13 @@ __device__ __forceinline__ Real act_fn(int kind, Real z, Real &d) {
 // shared layout per warp: h[L][MLP_MAX_WIDTH] activations, dz[L][MLP_MAX_WIDTH]
 // activation derivatives, x[dim] inputs, delta/ delta2 scratch
 template <typename Real>
-__global__ void __launch_bounds__(SF_WARPS * 32)
+__global__ void __launch_bounds__(MLP_WARPS * 32)
 k_mlp(int n, int dim, const uint8_t *__restrict__ types_ext, const MlpDev *__restrict__ mlps,
       const double *__restrict__ blob, const double *__restrict__ G,
       double *__restrict__ eat, double *__restrict__ dEdG) {
     extern __shared__ __align__(16) double smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int idx = blockIdx.x * SF_WARPS + warp;
+    const int idx = blockIdx.x * MLP_WARPS + warp;
     if (idx >= n) return;
     const MlpDev &M = mlps[types_ext[idx]];
     const int L = M.n_layers;        // last one = output layer (no activation)
@@ -382,13 +402,13 @@ k_sf_backward(int n, SfDev sf, int n_types, int row_cap,
               const double *__restrict__ dEdG, double *__restrict__ gvec,
               size_t plane, double *__restrict__ fown, double *__restrict__ partial) {
     extern __shared__ __align__(16) double smem[];
-    __shared__ double red[SF_WARPS][6];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int idx = blockIdx.x * SF_WARPS + warp;
+    __shared__ double red[SF_WARPS];
+    const int lane = threadIdx.x;
+    const int idx = blockIdx.x;
     double vir[6] = {0, 0, 0, 0, 0, 0};
-    if (idx < n) {
-        double *row = smem + (size_t)warp * row_cap * ROW_W;
-        const int cnt = stage_row<Real>(sf, idx, lane, atoms, counts, slice_ptr, col, row);
+    {
+        double *row = smem;
+        const int cnt = stage_row<Real>(sf, idx, lane, SF_TPA, atoms, counts, slice_ptr, col, row);
         const int ti = (int)types_ext[idx];
         const double *c = dEdG + (size_t)idx * sf.dim;
         const Real rc = (Real)sf.rc, rc2i = Real(1) / (rc * rc);
@@ -399,7 +419,7 @@ k_sf_backward(int n, SfDev sf, int n_types, int row_cap,
             seg[t + 1] = seg[t] + (t < n_types ? tcounts[(size_t)idx * n_types + t] : 0);
         const size_t ebase = (size_t)slice_ptr[idx >> 5] * 32u + (idx & 31);
         double fx = 0, fy = 0, fz = 0;
-        for (int a = lane; a < cnt; a += 32) {
+        for (int a = lane; a < cnt; a += SF_TPA) {
             const double *ea = row + a * ROW_W;
             const Real ax = (Real)ea[0], ay = (Real)ea[1], az = (Real)ea[2], ra = (Real)ea[3];
             const Real fa = (Real)ea[4], dfa = (Real)ea[5];
@@ -445,14 +465,15 @@ k_sf_backward(int n, SfDev sf, int n_types, int row_cap,
                     const Real dct_da = lower != Real(0) ? Real(1) / rb - ct / ra : Real(0);
                     const Real dct_dab = lower != Real(0) ? -rab / (ra * rb) : Real(0);
                     const Real F3 = fa * fb * fab;
-                    Real va = Real(0), vab = Real(0);
+                    Real va = Real(0), vab = Real(0), E = Real(0);
                     for (int tau = 0; tau < sf.n_a; ++tau) {
                         const Real z = (Real)sf.zeta[tau], gm = (Real)sf.gamma[tau],
                                    be = (Real)sf.beta[tau];
                         Real dP;
                         const Real P = powz<Real>(Real(1) + gm * ct, z, dP);
                         dP *= gm;
-                        const Real E = Math<Real>::exp_(-be * s2 * ac2i);
+                        if (tau == 0 || sf.beta[tau] != sf.beta[tau - 1])
+                            E = Math<Real>::exp_(-be * s2 * ac2i);
                         const Real K = exp2(Real(1) - z) * (Real)cc[tau];
                         const Real PE = P * E;
                         va += K * (dP * dct_da * E * F3 - Real(2) * be * ra * ac2i * PE * F3 +
@@ -485,9 +506,9 @@ k_sf_backward(int n, SfDev sf, int n_types, int row_cap,
             vir[4] += 0.5 * (double)(gx * az + gz * ax);
             vir[5] += 0.5 * (double)(gx * ay + gy * ax);
         }
-        fx = warp_sum(fx);
-        fy = warp_sum(fy);
-        fz = warp_sum(fz);
+        fx = block_sum(fx, red);
+        fy = block_sum(fy, red);
+        fz = block_sum(fz, red);
         if (lane == 0) {
             fown[3 * (size_t)idx + 0] = fx;
             fown[3 * (size_t)idx + 1] = fy;
@@ -496,14 +517,8 @@ k_sf_backward(int n, SfDev sf, int n_types, int row_cap,
     }
 #pragma unroll
     for (int q = 0; q < 6; ++q) {
-        const double v = warp_sum(vir[q]);
-        if (lane == 0) red[warp][q] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x < 6) {
-        double v = 0;
-        for (int w = 0; w < SF_WARPS; ++w) v += red[w][threadIdx.x];
-        partial[(size_t)blockIdx.x * 8 + 1 + threadIdx.x] = v;
+        const double v = block_sum(vir[q], red);
+        if (lane == 0) partial[(size_t)blockIdx.x * 8 + 1 + q] = v;
     }
 }
 
@@ -602,17 +617,18 @@ k_sf_jvp(int n, int n_loc, SfDev sf, int n_types, int row_cap,
          const int *__restrict__ ghost_owner, const double *__restrict__ u,
          const double *__restrict__ A, double *__restrict__ T) {
     extern __shared__ __align__(16) double smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int idx = blockIdx.x * SF_WARPS + warp;
+    __shared__ double red[SF_WARPS];
+    const int lane = threadIdx.x;
+    const int idx = blockIdx.x;
     if (idx >= n) return;
-    double *row = smem + (size_t)warp * row_cap * (ROW_W + 4);
+    double *row = smem;
     double *dd = row + (size_t)row_cap * ROW_W;          // [row_cap][4]: dD_p
-    const int cnt = stage_row<Real>(sf, idx, lane, atoms, counts, slice_ptr, col, row);
+    const int cnt = stage_row<Real>(sf, idx, lane, SF_TPA, atoms, counts, slice_ptr, col, row);
     {
         const uint32_t *cp = col + ((size_t)slice_ptr[idx >> 5] * 32u + (idx & 31));
         const double ux = u[3 * (size_t)idx], uy = u[3 * (size_t)idx + 1],
                      uz = u[3 * (size_t)idx + 2];
-        for (int k = lane; k < cnt; k += 32) {
+        for (int k = lane; k < cnt; k += SF_TPA) {
             int j = (int)(cp[(size_t)k * 32u] & TAB_COL_IDX_MASK);
             if (j >= n_loc) j = ghost_owner[j - n_loc];
             const double *e = row + (size_t)k * ROW_W;
@@ -620,7 +636,7 @@ k_sf_jvp(int n, int n_loc, SfDev sf, int n_types, int row_cap,
             dd[k * 4 + 1] = uy - u[3 * (size_t)j + 1] + A[3] * e[0] + A[4] * e[1] + A[5] * e[2];
             dd[k * 4 + 2] = uz - u[3 * (size_t)j + 2] + A[6] * e[0] + A[7] * e[1] + A[8] * e[2];
         }
-        __syncwarp();
+        __syncthreads();
     }
     const int ti = (int)types_ext[idx];
     double *t = T + (size_t)idx * sf.dim;
@@ -636,7 +652,7 @@ k_sf_jvp(int n, int n_loc, SfDev sf, int n_types, int row_cap,
         for (int tau = 0; tau < sf.n_r; ++tau) {
             const Real eta = (Real)sf.eta[tau], om = (Real)sf.omega[tau];
             Real acc = Real(0);
-            for (int k = seg[s] + lane; k < seg[s + 1]; k += 32) {
+            for (int k = seg[s] + lane; k < seg[s + 1]; k += SF_TPA) {
                 const double *e = row + k * ROW_W;
                 const Real r = (Real)e[3];
                 Real f, df;
@@ -648,7 +664,7 @@ k_sf_jvp(int n, int n_loc, SfDev sf, int n_types, int row_cap,
                                    (Real)e[2] * (Real)dd[k * 4 + 2]) / r;
                 acc += g1 * proj;
             }
-            const double tot = warp_sum((double)acc);
+            const double tot = block_sum((double)acc, red);
             if (lane == 0) t[term * sf.n_r + tau] = tot;
         }
     }
@@ -668,7 +684,7 @@ k_sf_jvp(int n, int n_loc, SfDev sf, int n_types, int row_cap,
                 const Real s1 = (px * (Real)dd[p * 4] + py * (Real)dd[p * 4 + 1] +
                                  pz * (Real)dd[p * 4 + 2]) / r1;
                 const int q0 = (a == b) ? p + 1 : seg[b];
-                for (int q = q0 + lane; q < seg[b + 1]; q += 32) {
+                for (int q = q0 + lane; q < seg[b + 1]; q += SF_TPA) {
                     const double *eq = row + q * ROW_W;
                     const Real fq = (Real)eq[4], dfq = (Real)eq[5];
                     if (fq == Real(0)) continue;
@@ -696,12 +712,14 @@ k_sf_jvp(int n, int n_loc, SfDev sf, int n_types, int row_cap,
                     const Real dct = dc1 * s1 + dc2 * s2 + dc3 * s3;
                     const Real dss = Real(2) * (r1 * s1 + r2 * s2 + r3 * s3);
                     const Real dF3 = dfp * s1 * fq * f3 + fp * dfq * s2 * f3 + fp * fq * df3 * s3;
+                    Real E = Real(0);
                     for (int tau = 0; tau < sf.n_a; ++tau) {
                         const Real z = (Real)sf.zeta[tau], gm = (Real)sf.gamma[tau],
                                    be = (Real)sf.beta[tau];
                         Real dP;
                         const Real P = powz<Real>(Real(1) + gm * ct, z, dP);
-                        const Real E = Math<Real>::exp_(-be * ss * ac2i);
+                        if (tau == 0 || sf.beta[tau] != sf.beta[tau - 1])
+                            E = Math<Real>::exp_(-be * ss * ac2i);
                         acc[tau] += exp2(Real(1) - z) *
                                     (dP * gm * dct * E * F3 - be * ac2i * dss * P * E * F3 +
                                      P * E * dF3);
@@ -709,7 +727,7 @@ k_sf_jvp(int n, int n_loc, SfDev sf, int n_types, int row_cap,
                 }
             }
             for (int tau = 0; tau < sf.n_a; ++tau) {
-                const double tot = warp_sum((double)acc[tau]);
+                const double tot = block_sum((double)acc[tau], red);
                 if (lane == 0) t[sf.d_r + pt * sf.n_a + tau] = tot;
             }
         }
@@ -873,12 +891,12 @@ static int atomic_run(tab_atomic *m, tab_nbr *nbr, double *d_energy, double *d_e
         return TAB_ESTATE;
     }
     const int row_cap = nbr->nnl_max > 0 ? nbr->nnl_max : 1;
-    const size_t smem_row = (size_t)SF_WARPS * row_cap * ROW_W * sizeof(double);
+    const size_t smem_row = (size_t)row_cap * ROW_W * sizeof(double);
     if (smem_row > 200 * 1024) {
         tab_set_error("neighbour rows of %d entries exceed the shared-memory budget", row_cap);
         return TAB_EUNSUPPORTED;
     }
-    const size_t smem_mlp = (size_t)SF_WARPS * (2 * MLP_MAX_LAYERS + 2) * MLP_MAX_WIDTH *
+    const size_t smem_mlp = (size_t)MLP_WARPS * (2 * MLP_MAX_LAYERS + 2) * MLP_MAX_WIDTH *
                             sizeof(double);
     static bool attr_done[2] = {false, false};
     const int ai = sizeof(Real) == 8 ? 0 : 1;
@@ -891,7 +909,8 @@ static int atomic_run(tab_atomic *m, tab_nbr *nbr, double *d_energy, double *d_e
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         attr_done[ai] = true;
     }
-    const int nblk = (n + SF_WARPS - 1) / SF_WARPS;
+    const int nblk = n;                       // one block per atom
+    const int nblk_m = (n + MLP_WARPS - 1) / MLP_WARPS;
     const int nblk_c = (n + 127) / 128;
     TAB_TRY(m->G.ensure(sizeof(double) * (size_t)n * sf.dim));
     TAB_TRY(m->dEdG.ensure(sizeof(double) * (size_t)n * sf.dim));
@@ -913,7 +932,7 @@ static int atomic_run(tab_atomic *m, tab_nbr *nbr, double *d_energy, double *d_e
     }
     const double *blob = m->blob.as<double>();
     const MlpDev *mlps = reinterpret_cast<const MlpDev *>(blob + m->mlp_table_off);
-    k_mlp<Real><<<nblk, SF_WARPS * 32, smem_mlp, st>>>(
+    k_mlp<Real><<<nblk_m, MLP_WARPS * 32, smem_mlp, st>>>(
         n, sf.dim, nbr->types_ext.as<uint8_t>(), mlps, blob, m->G.as<double>(),
         m->eat.as<double>(), m->dEdG.as<double>());
     TAB_LAUNCH_CHECK();
@@ -996,10 +1015,10 @@ static int atomic_forces_from(tab_atomic *m, tab_nbr *nbr, const double *d_dedg,
     const int n = nbr->n;
     const SfDev &sf = m->sf;
     const int row_cap = nbr->nnl_max > 0 ? nbr->nnl_max : 1;
-    const size_t smem_row = (size_t)SF_WARPS * row_cap * ROW_W * sizeof(double);
+    const size_t smem_row = (size_t)row_cap * ROW_W * sizeof(double);
     TAB_CUDA(cudaFuncSetAttribute(k_sf_backward<Real>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    const int nblk = (n + SF_WARPS - 1) / SF_WARPS, nblk_c = (n + 127) / 128;
+    const int nblk = n, nblk_c = (n + 127) / 128;
     TAB_TRY(m->dEdG.ensure(sizeof(double) * (size_t)n * sf.dim));
     TAB_TRY(m->eat.ensure(sizeof(double) * (size_t)n));
     TAB_TRY(m->fown.ensure(sizeof(double) * 3 * (size_t)n));
@@ -1047,14 +1066,14 @@ static int atomic_jvp(tab_atomic *m, tab_nbr *nbr, const double *d_u, const doub
     const int n = nbr->n;
     const SfDev &sf = m->sf;
     const int row_cap = nbr->nnl_max > 0 ? nbr->nnl_max : 1;
-    const size_t smem = (size_t)SF_WARPS * row_cap * (ROW_W + 4) * sizeof(double);
+    const size_t smem = (size_t)row_cap * (ROW_W + 4) * sizeof(double);
     if (smem > 200 * 1024) {
         tab_set_error("neighbour rows of %d entries exceed the shared-memory budget", row_cap);
         return TAB_EUNSUPPORTED;
     }
     TAB_CUDA(cudaFuncSetAttribute(k_sf_jvp<Real>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    const int nblk = (n + SF_WARPS - 1) / SF_WARPS;
+    const int nblk = n;
     TAB_TRY(m->fown.ensure(sizeof(double) * 3 * (size_t)n));
     TAB_TRY(m->G.ensure(sizeof(double) * (size_t)n * sf.dim));
     // u to sorted order
