@@ -225,6 +225,8 @@ class NeighborList:
         """Domain-decomposed build: d_pos = owned atoms then halo atoms."""
         import torch
         assert d_pos.is_cuda and d_pos.dtype == torch.float64 and d_pos.is_contiguous()
+        if d_types is not None:
+            assert d_types.is_cuda and d_types.dtype == torch.int32
         n_loc = int(d_pos.shape[0])
         self.n = int(n_owned)
         org = (C.c_double * 3)(*[float(x) for x in origin])

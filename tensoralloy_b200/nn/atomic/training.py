@@ -114,11 +114,12 @@ class AtomicNNTrainer:
         clf = self.nn.transformer
         types = clf.get_types(atoms)
         nbr = _lib.NeighborList()
-        cell, pbc = clf._cell_and_pbc(atoms)
+        cell, pbc, origin = clf._cell_and_pbc(atoms)
         d_pos = torch.tensor(np.ascontiguousarray(atoms.positions), dtype=torch.float64,
                              device=self.device)
         d_types = torch.tensor(types, dtype=torch.int32, device=self.device)
-        nbr.build(d_pos, d_types, cell, pbc, self.nn.required_cutoff())
+        nbr.build_dd(d_pos, d_types, len(types), cell, origin, pbc,
+                     self.nn.required_cutoff())
         G = self.model.descriptors(nbr, self.dt.tab_precision).to(self.tdtype)
         t = lambda a: torch.tensor(np.asarray(a), dtype=self.tdtype, device=self.device)
         self.structures.append(dict(

@@ -153,3 +153,40 @@ class BasicNN:
         if 'hessian' in raw:
             pred['hessian'] = raw['hessian'].astype(dtype)
         return pred
+
+    def _hessian(self, features):
+        raise NotImplementedError(
+            f"{self.__class__.__name__} has no analytic Hessian kernel yet")
+
+    def _elastic(self, features):
+        """Elastic constant tensor [6,6] in GPa with the reference's definition
+        (nn/constraint/elastic.py:24-91):
+            C_ijkl = [ (d virial_ij / d h)^T h ]_kl / V / GPa
+        where the derivative w.r.t. the lattice h is taken at FIXED Cartesian
+        positions (only the periodic-image shifts S.h move) -- exact for
+        one-atom primitive cells, which is how the reference uses it.  The
+        derivative is a central difference of the GPU virial over the 9 lattice
+        components (lists and shifts kept, `tab_nbr_update`)."""
+        h0 = np.array(features.cell, dtype=np.float64)
+        vol = features.volume
+        nbr, d_pos = features.nbr, features.d_pos
+        step = 1e-5
+        dW = np.zeros((3, 3, 3, 3))
+        try:
+            for m in range(3):
+                for k in range(3):
+                    w = []
+                    for sgn in (+1.0, -1.0):
+                        h = h0.copy()
+                        h[m, k] += sgn * step
+                        nbr.update(d_pos, h)
+                        w.append(self._evaluate(features, False, True, False)['virial'])
+                    dW[:, :, m, k] = (w[0] - w[1]) / (2.0 * step)
+        finally:
+            nbr.update(d_pos, h0)
+        C = np.einsum('ijmk,ml->ijkl', dW, h0) / vol / GPa
+        out = np.zeros((6, 6))
+        for vi, (i, j) in enumerate(VOIGT):
+            for vj, (k, l) in enumerate(VOIGT):
+                out[vi, vj] = C[i, j, k, l]
+        return out

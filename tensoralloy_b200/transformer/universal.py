@@ -133,14 +133,19 @@ class UniversalTransformer:
 
     # -- device path ----------------------------------------------------------
     def _cell_and_pbc(self, atoms):
+        """Binning frame handed to the library: (cell, pbc, origin).  Periodic
+        structures use their own cell; non-periodic directions (or a missing
+        cell) get a bounding extent with its own origin -- only the binning frame
+        changes, S stays 0 along non-periodic directions."""
         cell = np.asarray(atoms.get_cell(complete=True), dtype=np.float64).reshape(3, 3)
         pbc = np.asarray(atoms.get_pbc(), dtype=bool).reshape(3)
         if not self._periodic:
             pbc = np.zeros(3, dtype=bool)
+        origin = np.zeros(3)
         if abs(np.linalg.det(cell)) < 1e-12 or not pbc.all():
-            cell, shift = _bounding_cell(np.asarray(atoms.positions), cell, pbc,
-                                         self._rcut)
-        return cell, pbc
+            cell, origin = _bounding_cell(np.asarray(atoms.positions), cell, pbc,
+                                          max(self._rcut, self._acut or 0.0))
+        return cell, pbc, origin
 
     def get_device_features(self, atoms, rc=None) -> DeviceFeatures:
         """Build the GPU neighbour lists of `atoms` (replaces get_feed_dict)."""
@@ -148,14 +153,14 @@ class UniversalTransformer:
         if self._nbr is None:
             self._nbr = _lib.NeighborList()
         types = self.get_types(atoms)
-        cell, pbc = self._cell_and_pbc(atoms)
+        cell, pbc, origin = self._cell_and_pbc(atoms)
         d_pos = torch.as_tensor(np.ascontiguousarray(atoms.positions, dtype=np.float64)
                                 ).to('cuda', non_blocking=True)
         d_types = torch.as_tensor(types).to('cuda', non_blocking=True)
         if rc is None:
             rc = max(self._rcut, self._acut) if (self._angular and self._acut) \
                 else self._rcut
-        self._nbr.build(d_pos, d_types, cell, pbc, rc)
+        self._nbr.build_dd(d_pos, d_types, len(types), cell, origin, pbc, rc)
         real_cell = np.asarray(atoms.get_cell(complete=True), dtype=np.float64)
         return DeviceFeatures(atoms, self.get_vap_transformer(atoms), types,
                               self._nbr, d_pos, real_cell.reshape(3, 3),
@@ -231,27 +236,27 @@ class UniversalTransformer:
 
 
 def _bounding_cell(positions, cell, pbc, rc):
-    """For non-periodic directions (or a missing cell) use an orthogonal-to-the-
-    -rest bounding extent so that the cell list has a frame to bin in.  Only the
-    binning frame changes; S stays 0 along non-periodic directions."""
+    """Frame for structures that are not periodic in every direction.  Along a
+    periodic direction the lattice vector is kept; along a non-periodic one the
+    frame spans the atoms (plus a margin) starting at `origin`."""
     cell = np.array(cell, dtype=np.float64)
-    out = cell.copy()
     pos = np.asarray(positions, dtype=np.float64)
+    out = cell.copy()
+    origin = np.zeros(3)
     if not pbc.any():
-        lo = pos.min(axis=0) - 1.0
-        hi = pos.max(axis=0) + 1.0
-        ext = np.maximum(hi - lo, 2.0 * rc + 2.0)
-        # the library bins with scaled = pos @ inv(cell); an origin shift is not
-        # needed because non-periodic bins are clipped to the box edges
-        return np.diag(ext + np.abs(lo) + np.abs(hi)), lo
+        lo = pos.min(axis=0) - 0.5
+        hi = pos.max(axis=0) + 0.5
+        return np.diag(np.maximum(hi - lo, 1.0)), lo
     for k in range(3):
-        if not pbc[k] and not np.any(cell[k]):
+        if pbc[k]:
+            continue
+        v = cell[k]
+        if not np.any(v):
             others = [cell[m] for m in range(3) if m != k and np.any(cell[m])]
-            if len(others) == 2:
-                v = np.cross(others[0], others[1])
-            else:
-                v = np.eye(3)[k]
-            v = v / np.linalg.norm(v)
-            span = np.ptp(pos @ v) + 2.0 * rc + 2.0
-            out[k] = v * max(span, 1.0)
-    return out, np.zeros(3)
+            v = np.cross(others[0], others[1]) if len(others) == 2 else np.eye(3)[k]
+        v = v / np.linalg.norm(v)
+        proj = pos @ v
+        lo, hi = proj.min() - 0.5, proj.max() + 0.5
+        out[k] = v * max(hi - lo, 1.0)
+        origin = origin + v * lo
+    return out, origin
