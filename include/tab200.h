@@ -138,6 +138,10 @@ int tab_nbr_export(const tab_nbr *nbr, int32_t *d_i, int32_t *d_j, int32_t *d_S,
 #define TAB_FN_GRIMES_PHI    13   /* grimmes.py:41-60     p = A,rho,C,D,gamma,r0 */
 #define TAB_FN_MISHIN_EMBED  14   /* mishin.py:196-260    p = s1..s7,eps */
 #define TAB_FN_MISHIN_POLAR  15   /* mishin.py:262-315, generic.py:52-84  p = p1,p2,p3,rc,h */
+#define TAB_FN_SPLINE        16   /* cubic spline table (io/lammps.py:60-72 Spline; the
+                                     reference's missing extension/interp CubicInterpolator):
+                                     aux = offset (in intervals) into the model's
+                                     coefficient pool, p = x0, 1/dx, n_intervals */
 #define TAB_FN_MAX_PARAMS    32
 
 typedef struct tab_fn {
@@ -157,6 +161,11 @@ int tab_eam_create(tab_model **out, int32_t kind, int32_t n_el,
                    const tab_fn *rho, const tab_fn *phi, const tab_fn *embed,
                    const tab_fn *dipole, const tab_fn *quadrupole);
 int tab_model_free(tab_model *model);
+
+/* Attach the spline coefficient pool used by TAB_FN_SPLINE entries: interval k of a
+ * table holds 4 doubles (c0, c1, c2, c3) of  f(x) = c0 + c1 t + c2 t^2 + c3 t^3,
+ * t = x - (x0 + k dx).  h_coeffs: [n_intervals_total * 4] host doubles. */
+int tab_eam_set_splines(tab_model *model, const double *h_coeffs, int64_t n_doubles);
 
 /* One E + F + virial evaluation on the lists held by `nbr`.
  *   d_energy : [1]   total energy (eV)                      basic.py:742-787

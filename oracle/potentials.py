@@ -343,6 +343,52 @@ class MishinH(Potential):
         return mishin_polar(r, P('q1'), P('q2'), P('q3'), P('rc'), P('h'))
 
 
+class SplineTable(Potential):
+    """Natural cubic splines over setfl / ADP tables: io/lammps.py:60-221 `Spline`
+    (+ the CubicInterpolator the reference imports from the missing
+    extension/interp package).  Coefficients from scipy
+    CubicSpline(bc_type='natural'); evaluation in torch so autograd differentiates
+    the piecewise polynomial.  `tables`: dict kind -> key -> (x0, dx, y)."""
+    name = 'spline'
+
+    def __init__(self, tables, dtype=torch.float64):
+        self.dtype = dtype
+        self.params = {}
+        self._c = {}
+        from scipy.interpolate import CubicSpline
+        import numpy as np
+        for kind, group in tables.items():
+            for key, (x0, dx, y) in group.items():
+                x = x0 + dx * np.arange(len(y))
+                cs = CubicSpline(x, np.asarray(y, dtype=np.float64), bc_type='natural')
+                self._c[(kind, key)] = (x0, dx, torch.tensor(cs.c.copy(), dtype=dtype))
+
+    def _eval(self, kind, key, x):
+        if (kind, key) not in self._c:
+            a, b = _elements_of(key) if len(_elements_of(key)) == 2 else (key, None)
+            key = b + a
+        x0, dx, c = self._c[(kind, key)]
+        n = c.shape[1]
+        k = torch.clamp(torch.floor((x.detach() - x0) / dx).long(), 0, n - 1)
+        t = x - (x0 + k.to(x.dtype) * dx)
+        return ((c[0, k] * t + c[1, k]) * t + c[2, k]) * t + c[3, k]
+
+    def rho(self, r, element):
+        return self._eval('rho', _elements_of(element)[-1], r)
+
+    def phi(self, r, term):
+        return self._eval('phi', term, r)
+
+    def embed(self, rho, element):
+        return self._eval('embed', element, rho)
+
+    def dipole(self, r, term):
+        return self._eval('dipole', term, r)
+
+    def quadrupole(self, r, term):
+        return self._eval('quadrupole', term, r)
+
+
 REGISTRY = {
     'zjw04': Zjw04, 'zjw04xc': Zjw04xc, 'zjw04uxc': Zjw04uxc,
     'zjw04xcp': Zjw04xcp, 'sutton90': AgSutton90, 'Be/1': AgrawalBe,

@@ -34,6 +34,7 @@ FN_GRIMES_RHO = 12
 FN_GRIMES_PHI = 13
 FN_MISHIN_EMBED = 14
 FN_MISHIN_POLAR = 15
+FN_SPLINE = 16
 
 
 class TabFn(C.Structure):
@@ -86,7 +87,7 @@ EXPORTS = [
     'tab_nbr_create', 'tab_nbr_free', 'tab_nbr_build', 'tab_nbr_build_dd',
     'tab_nbr_update', 'tab_pack_rows',
     'tab_nbr_sizes', 'tab_nbr_counts', 'tab_nbr_export',
-    'tab_eam_create', 'tab_model_free', 'tab_eam_eval', 'tab_eam_pass1',
+    'tab_eam_create', 'tab_eam_set_splines', 'tab_model_free', 'tab_eam_eval', 'tab_eam_pass1',
     'tab_eam_pass2', 'tab_eam_hessian', 'tab_eam_compute_host',
     'tab_atomic_create', 'tab_atomic_free', 'tab_atomic_dim', 'tab_atomic_eval',
     'tab_atomic_descriptors', 'tab_atomic_forces', 'tab_atomic_jvp',
@@ -126,6 +127,7 @@ def lib():
     L.tab_eam_create.argtypes = [pp, i32, i32, C.POINTER(TabFn),
                                  C.POINTER(TabFn), C.POINTER(TabFn),
                                  C.POINTER(TabFn), C.POINTER(TabFn)]
+    L.tab_eam_set_splines.argtypes = [vp, C.POINTER(dbl), i64]
     L.tab_model_free.argtypes = [vp]
     L.tab_eam_eval.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]
     L.tab_eam_pass1.argtypes = [vp, vp, i32, vp, vp]
@@ -281,6 +283,12 @@ class EamModel:
                                    *self._keep), 'tab_eam_create')
         self.n_el = n_el
         self.kind = kind
+
+    def set_splines(self, coeffs):
+        """coeffs: float64 array [n_intervals_total, 4] (c0, c1, c2, c3)."""
+        a = np.ascontiguousarray(np.asarray(coeffs, dtype=np.float64).reshape(-1))
+        check(lib().tab_eam_set_splines(self._h, a.ctypes.data_as(C.POINTER(C.c_double)),
+                                        int(a.size)), 'tab_eam_set_splines')
 
     def __del__(self):
         try:

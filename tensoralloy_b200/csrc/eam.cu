@@ -25,6 +25,7 @@ struct EamDev {
     const tab_fn *rho;     // [n_el*n_el] centre a, neighbour b
     const tab_fn *phi;     // [n_el*n_el]
     const tab_fn *embed;   // [n_el]
+    const double *pool;    // spline coefficient pool (TAB_FN_SPLINE) or NULL
 };
 
 struct tab_model {
@@ -34,6 +35,7 @@ struct tab_model {
     bool zhou1 = false;    // single element, all-zjw04: shared-exponential fast path
     double zp[8];          // fe, beta, lamda, 1/re, A, alpha, kappa, B
     DevBuf tables;         // tab_fn [2*n_el*n_el + n_el (+ 2*n_el*n_el)]
+    DevBuf pool;           // spline coefficients
     tab_fn embed0;         // host copy (fast path epilogue parameters)
 };
 
@@ -131,13 +133,13 @@ k_eam_rho(int n, const Atom4 *__restrict__ atoms,
             zhou_exp<Real>(r, (Real)z.fe, (Real)z.beta, (Real)z.lamda, (Real)z.re, f, df);
         } else {
             const int tj = (int)(c >> TAB_COL_TYPE_SHIFT);
-            eval_pair_fn<Real>(tabs[ti * m.n_el + tj], r, f, df);
+            eval_pair_fn<Real>(tabs[ti * m.n_el + tj], r, f, df, m.pool);
         }
         rho += f;
     }
     Real F, dF;
     if (FAST) eval_embed_fn<Real>(embed0, rho, F, dF);
-    else eval_embed_fn<Real>(tabs[2 * nn + ti], rho, F, dF);
+    else eval_embed_fn<Real>(tabs[2 * nn + ti], rho, F, dF, m.pool);
     fprime[idx] = (double)dF;
     fembed[idx] = (double)F;
     if (fprime_caller) fprime_caller[perm[idx]] = (double)dF;
@@ -202,10 +204,10 @@ k_eam_force(int n, const Atom4 *__restrict__ atoms,
             } else {
                 const int tj = (int)(c >> TAB_COL_TYPE_SHIFT);
                 Real rij, drij, rji, drji;
-                eval_pair_fn<Real>(tabs[ti * m.n_el + tj], r, rij, drij);
+                eval_pair_fn<Real>(tabs[ti * m.n_el + tj], r, rij, drij, m.pool);
                 if (ti == tj) drji = drij;
-                else eval_pair_fn<Real>(tabs[tj * m.n_el + ti], r, rji, drji);
-                eval_pair_fn<Real>(tabs[nn + ti * m.n_el + tj], r, phi, dphi);
+                else eval_pair_fn<Real>(tabs[tj * m.n_el + ti], r, rji, drji, m.pool);
+                eval_pair_fn<Real>(tabs[nn + ti * m.n_el + tj], r, phi, dphi, m.pool);
                 der = fpi * drij + fpj * drji + dphi;
             }
             const Real s = der * rinv;
@@ -293,9 +295,9 @@ k_adp_rho(int n, const Atom4 *__restrict__ atoms,
         Real dx, dy, dz, r, rinv, f, df, u, du, w, dw;
         pair_r<Real>(me, a, dx, dy, dz, r, rinv);
         const int tj = (int)(c >> TAB_COL_TYPE_SHIFT);
-        eval_pair_fn<Real>(tabs[ti * m.n_el + tj], r, f, df);
-        eval_pair_fn<Real>(t_dip[ti * m.n_el + tj], r, u, du);
-        eval_pair_fn<Real>(t_quad[ti * m.n_el + tj], r, w, dw);
+        eval_pair_fn<Real>(tabs[ti * m.n_el + tj], r, f, df, m.pool);
+        eval_pair_fn<Real>(t_dip[ti * m.n_el + tj], r, u, du, m.pool);
+        eval_pair_fn<Real>(t_quad[ti * m.n_el + tj], r, w, dw, m.pool);
         rho += f;
 #pragma unroll
         for (int t = 0; t < ADP_MAX_EL; ++t) {
@@ -313,7 +315,7 @@ k_adp_rho(int n, const Atom4 *__restrict__ atoms,
         }
     }
     Real F, dF;
-    eval_embed_fn<Real>(tabs[2 * nn + ti], rho, F, dF);
+    eval_embed_fn<Real>(tabs[2 * nn + ti], rho, F, dF, m.pool);
     Real eadp = Real(0);
 #pragma unroll
     for (int t = 0; t < ADP_MAX_EL; ++t) {
@@ -380,12 +382,12 @@ k_adp_force(int n, const Atom4 *__restrict__ atoms,
             const int tj = (int)(c >> TAB_COL_TYPE_SHIFT);
             const Real fpj = (Real)a.w;
             Real rij, drij, rji, drji, phi, dphi, u, du, w, dw;
-            eval_pair_fn<Real>(tabs[ti * m.n_el + tj], r, rij, drij);
+            eval_pair_fn<Real>(tabs[ti * m.n_el + tj], r, rij, drij, m.pool);
             if (ti == tj) drji = drij;
-            else eval_pair_fn<Real>(tabs[tj * m.n_el + ti], r, rji, drji);
-            eval_pair_fn<Real>(tabs[nn + ti * m.n_el + tj], r, phi, dphi);
-            eval_pair_fn<Real>(t_dip[ti * m.n_el + tj], r, u, du);
-            eval_pair_fn<Real>(t_quad[ti * m.n_el + tj], r, w, dw);
+            else eval_pair_fn<Real>(tabs[tj * m.n_el + ti], r, rji, drji, m.pool);
+            eval_pair_fn<Real>(tabs[nn + ti * m.n_el + tj], r, phi, dphi, m.pool);
+            eval_pair_fn<Real>(t_dip[ti * m.n_el + tj], r, u, du, m.pool);
+            eval_pair_fn<Real>(t_quad[ti * m.n_el + tj], r, w, dw, m.pool);
             // EAM part, symmetric in the pair
             const Real s = (fpi * drij + fpj * drji + dphi) * rinv;
             Real gx = s * dx, gy = s * dy, gz = s * dz;
@@ -599,9 +601,24 @@ int tab_eam_tables(tab_model *m, const tab_fn **rho, const tab_fn **phi,
     return TAB_OK;
 }
 
+extern "C" int tab_eam_set_splines(tab_model *m, const double *h_coeffs,
+                                   int64_t n_doubles) {
+    if (!m || !h_coeffs || n_doubles <= 0) {
+        tab_set_error("tab_eam_set_splines: bad argument");
+        return TAB_EINVAL;
+    }
+    TAB_TRY(m->pool.ensure(sizeof(double) * (size_t)n_doubles));
+    TAB_CUDA(cudaMemcpy(m->pool.p, h_coeffs, sizeof(double) * (size_t)n_doubles,
+                        cudaMemcpyHostToDevice));
+    return TAB_OK;
+}
+
+const double *tab_eam_pool(tab_model *m) { return m->pool.as<double>(); }
+
 extern "C" int tab_model_free(tab_model *m) {
     if (!m) return TAB_OK;
     m->tables.release();
+    m->pool.release();
     delete m;
     return TAB_OK;
 }
@@ -670,6 +687,7 @@ static int eam_prepare(tab_model *m, tab_nbr *nbr, bool fast, EamLaunch &L) {
     L.dev.rho = m->tables.as<tab_fn>();
     L.dev.phi = L.dev.rho + nn;
     L.dev.embed = L.dev.rho + 2 * nn;
+    L.dev.pool = m->pool.as<double>();
     memcpy(&L.z, m->zp, sizeof(L.z));
     L.smem = fast ? 0 : (size_t)(2 * nn + m->n_el) * sizeof(tab_fn);
     return TAB_OK;

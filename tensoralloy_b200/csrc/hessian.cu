@@ -88,9 +88,24 @@ __device__ inline D2 v_morse(D2 r, double d, double g, double r0) {
     return D2(d) * (e * e - D2(2.0) * e);
 }
 
+__device__ inline D2 spline_d2(const tab_fn &fn, const double *pool, D2 x) {
+    const double t = (x.v - fn.p[0]) * fn.p[1];
+    int k = (int)floor(t);
+    const int last = (int)fn.p[2] - 1;
+    k = k < 0 ? 0 : (k > last ? last : k);
+    const double *c = pool + ((size_t)fn.aux + k) * 4;
+    const double d = x.v - (fn.p[0] + (double)k / fn.p[1]);
+    return chain(x, ((c[3] * d + c[2]) * d + c[1]) * d + c[0],
+                 (3.0 * c[3] * d + 2.0 * c[2]) * d + c[1], 6.0 * c[3] * d + 2.0 * c[2]);
+}
+
+__device__ const double *g_hess_pool = nullptr;   // set per launch (single stream use)
+
 __device__ inline D2 eval_pair_d2(const tab_fn &fn, D2 r) {
     const double *p = fn.p;
     switch (fn.kind) {
+    case TAB_FN_SPLINE:
+        return spline_d2(fn, g_hess_pool, r);
     case TAB_FN_ZHOU_RHO:
         return v_zhou(r, p[0], p[1], p[2], p[3]);
     case TAB_FN_ZHOU_PHI:
@@ -164,6 +179,8 @@ __device__ inline D2 v_zhou_embed(const double *p, bool blended, D2 rho) {
 __device__ inline D2 eval_embed_d2(const tab_fn &fn, D2 rho) {
     const double *p = fn.p;
     switch (fn.kind) {
+    case TAB_FN_SPLINE:
+        return spline_d2(fn, g_hess_pool, rho);
     case TAB_FN_ZHOU_EMBED:
         return v_zhou_embed(p, false, rho);
     case TAB_FN_ZHOU_EMBED_XC:
@@ -365,6 +382,7 @@ struct tab_model_view {      // layout prefix of tab_model (eam.cu)
 };
 int tab_eam_tables(tab_model *m, const tab_fn **rho, const tab_fn **phi,
                    const tab_fn **embed, int *n_el, int *kind);   // eam.cu
+const double *tab_eam_pool(tab_model *m);                          // eam.cu
 
 extern "C" int tab_eam_hessian(tab_model *m, tab_nbr *nbr, double *d_hessian,
                                void *stream) {
@@ -400,6 +418,9 @@ extern "C" int tab_eam_hessian(tab_model *m, tab_nbr *nbr, double *d_hessian,
     const int n = nbr->n;
     TAB_TRY(nbr->rho.ensure(sizeof(double) * 2 * (size_t)n));
     double *fp = nbr->rho.as<double>(), *fpp = fp + n;
+    const double *pool = tab_eam_pool(m);
+    TAB_CUDA(cudaMemcpyToSymbolAsync(g_hess_pool, &pool, sizeof(pool), 0,
+                                     cudaMemcpyHostToDevice, st));
     TAB_CUDA(cudaMemsetAsync(d_hessian, 0, sizeof(double) * 9 * (size_t)n * n, st));
     k_hess_rho<<<(n + 127) / 128, 128, 0, st>>>(c, fp, fpp);
     TAB_LAUNCH_CHECK();

@@ -148,11 +148,31 @@ __device__ __forceinline__ void zhou_embed(const double *p, bool blended, Real r
 // NOTE: tab_eam_create stores 1/r_eq in the r_eq slots of the device tables.
 // One table entry -> value and d/dr.  The switch is warp-uniform for
 // single-species systems and cheap next to the transcendental work otherwise.
+// cubic spline table: value and derivative; out-of-range arguments use the edge
+// interval's polynomial (LAMMPS clamps the same way)
+template <typename Real>
+__device__ __forceinline__ void spline_eval(const tab_fn &fn, const double *__restrict__ pool,
+                                            Real x, Real &f, Real &df) {
+    const double t = ((double)x - fn.p[0]) * fn.p[1];
+    int k = (int)floor(t);
+    const int last = (int)fn.p[2] - 1;
+    k = k < 0 ? 0 : (k > last ? last : k);
+    const double *c = pool + ((size_t)fn.aux + k) * 4;
+    const Real d = (Real)((double)x - (fn.p[0] + (double)k / fn.p[1]));
+    const Real c0 = (Real)c[0], c1 = (Real)c[1], c2 = (Real)c[2], c3 = (Real)c[3];
+    f = ((c3 * d + c2) * d + c1) * d + c0;
+    df = (Real(3) * c3 * d + Real(2) * c2) * d + c1;
+}
+
 template <typename Real>
 __device__ __forceinline__ void eval_pair_fn(const tab_fn &fn, Real r, Real &f,
-                                             Real &df) {
+                                             Real &df,
+                                             const double *__restrict__ pool = nullptr) {
     const double *p = fn.p;
     switch (fn.kind) {
+    case TAB_FN_SPLINE:
+        spline_eval<Real>(fn, pool, r, f, df);
+        break;
     case TAB_FN_ZHOU_RHO:   // zjw04.py:245-277
         zhou_exp<Real>(r, (Real)p[0], (Real)p[1], (Real)p[2], (Real)p[3], f, df);
         break;
@@ -265,8 +285,12 @@ __device__ __forceinline__ void eval_pair_fn(const tab_fn &fn, Real r, Real &f,
 
 template <typename Real>
 __device__ __forceinline__ void eval_embed_fn(const tab_fn &fn, Real rho, Real &F,
-                                              Real &dF) {
+                                              Real &dF,
+                                              const double *__restrict__ pool = nullptr) {
     switch (fn.kind) {
+    case TAB_FN_SPLINE:
+        spline_eval<Real>(fn, pool, rho, F, dF);
+        break;
     case TAB_FN_ZHOU_EMBED:
         zhou_embed<Real>(fn.p, false, rho, F, dF);
         break;

@@ -52,8 +52,10 @@ class EamNN(BasicNN):
 
     @staticmethod
     def _check_fn_avail(name: str):
-        name = name.lower()
-        return name == "nn" or name in available_potentials
+        if name.startswith("spline@"):
+            return True
+        return name.lower() == "nn" or name in available_potentials or \
+            name.lower() in available_potentials
 
     def _setup_kbody_terms(self):
         kbody_terms = get_kbody_terms(self._elements, angular=False)[1]
@@ -101,6 +103,11 @@ class EamNN(BasicNN):
             raise NotImplementedError(
                 "'nn' (MLP-parametrised) EAM functions are not available in "
                 "libtab200 yet")
+        if name.startswith("spline@"):
+            if name not in self._empirical_functions:
+                from tensoralloy_b200.nn.eam.potentials.spline import SplinePotential
+                self._empirical_functions[name] = SplinePotential(name[len("spline@"):])
+            return self._empirical_functions[name]
         return self._empirical_functions[name]
 
     def _device_model(self):
@@ -122,8 +129,25 @@ class EamNN(BasicNN):
                     key = "".join(sorted([a, b])) if a != b else f"{a}{a}"
                     dipole.append(self._fn_of(key, 'dipole').dipole(key))
                     quadrupole.append(self._fn_of(key, 'quadrupole').quadrupole(key))
+        # tabulated functions: one coefficient pool per model; rebase the offsets
+        splines = [f for k, f in self._empirical_functions.items()
+                   if k.startswith("spline@")]
+        base = 0
+        pools = []
+        for sp in splines:
+            pool = sp.pool()
+            if base:
+                for fns in (rho, phi, embed, dipole or [], quadrupole or []):
+                    for fn in fns:
+                        if fn.kind == _lib.FN_SPLINE and getattr(fn, '_owner', None) is sp:
+                            fn.aux += base
+            pools.append(pool)
+            base += len(pool)
         self._model = _lib.EamModel(self.kind, len(els), rho, phi, embed, dipole,
                                     quadrupole)
+        if pools and base:
+            import numpy as _np
+            self._model.set_splines(_np.concatenate(pools))
         return self._model
 
     def _evaluate(self, features, want_forces, want_virial, want_atomic):
