@@ -41,6 +41,7 @@ struct SfDev {
     double rc, acut;
     double eta[SF_MAX_R], omega[SF_MAX_R];
     double beta[SF_MAX_A], gamma[SF_MAX_A], zeta[SF_MAX_A];
+    double outer[SF_MAX_A];                // 2^(1 - zeta)
 };
 
 struct MlpDev {
@@ -74,8 +75,10 @@ __device__ __forceinline__ void cutoff_fn(int kind, Real r, Real rc, Real &f, Re
     const Real x = r / rc;
     if (kind == 0) {
         const Real a = x * Real(3.14159265358979323846);
-        f = Real(0.5) * (cos(a) + Real(1));
-        df = Real(-0.5) * sin(a) * Real(3.14159265358979323846) / rc;
+        Real sn, cs;
+        sincos(a, &sn, &cs);
+        f = Real(0.5) * (cs + Real(1));
+        df = Real(-0.5) * sn * Real(3.14159265358979323846) / rc;
     } else {
         const Real x2 = x * x, x4 = x2 * x2, x5 = x4 * x;
         f = Real(1) + Real(5) * x5 * x - Real(6) * x5;        // 1 + g x^(g+1) - (g+1) x^g, g=5
@@ -213,18 +216,37 @@ k_sf_forward(int n, SfDev sf, int n_types, int row_cap,
             const int pt = pair_term(a, b, sf.n_el);
             Real acc[SF_MAX_A];
             for (int tau = 0; tau < sf.n_a; ++tau) acc[tau] = Real(0);
-            for (int p = seg[a]; p < seg[a + 1]; ++p) {
-                const double *ep = row + p * ROW_W;
-                const Real fp = (Real)ep[4];
-                if (fp == Real(0)) continue;
-                const Real px = (Real)ep[0], py = (Real)ep[1], pz = (Real)ep[2],
-                           r1 = (Real)ep[3];
-                const int q0 = (a == b) ? p + 1 : seg[b];
-                for (int q = q0 + lane; q < seg[b + 1]; q += SF_TPA) {
+            // flattened pair index: a == b -> strict upper triangle of the segment,
+            // a < b -> the full na x nb rectangle; threads stride over it
+            const int na = seg[a + 1] - seg[a], nb = seg[b + 1] - seg[b];
+            const long long npairs = (a == b) ? (long long)na * (na - 1) / 2
+                                              : (long long)na * nb;
+            for (long long t = lane; t < npairs; t += SF_TPA) {
+                int p, q;
+                if (a == b) {
+                    // row-major upper triangle: solve for the row
+                    const double nn1 = (double)na - 0.5;
+                    int i = (int)floor(nn1 - sqrt(nn1 * nn1 - 2.0 * (double)t));
+                    long long start = (long long)i * (2 * na - i - 1) / 2;
+                    if (start > t) { --i; start = (long long)i * (2 * na - i - 1) / 2; }
+                    else if (start + (na - i - 1) <= t) { start += na - i - 1; ++i; }
+                    p = seg[a] + i;
+                    q = p + 1 + (int)(t - start);
+                } else {
+                    p = seg[a] + (int)(t / nb);
+                    q = seg[b] + (int)(t % nb);
+                }
+                {
+                    const double *ep = row + p * ROW_W;
+                    const Real fp = (Real)ep[4];
+                    if (fp == Real(0)) continue;
+                    const Real px = (Real)ep[0], py = (Real)ep[1], pz = (Real)ep[2],
+                               r1 = (Real)ep[3];
                     const double *eq = row + q * ROW_W;
                     const Real fq = (Real)eq[4];
                     if (fq == Real(0)) continue;
                     const Real r2 = (Real)eq[3];
+
                     const Real jx = (Real)eq[0] - px, jy = (Real)eq[1] - py,
                                jz = (Real)eq[2] - pz;
                     const Real r3 = sqrt(jx * jx + jy * jy + jz * jz + Math<Real>::eps());
@@ -244,7 +266,7 @@ k_sf_forward(int n, SfDev sf, int n_types, int row_cap,
                         // the exponential depends on beta only (grid: beta outermost)
                         if (tau == 0 || sf.beta[tau] != sf.beta[tau - 1])
                             E = Math<Real>::exp_(-(Real)sf.beta[tau] * s2 * ac2i);
-                        acc[tau] += pw * (E * fc) * exp2(Real(1) - z);
+                        acc[tau] += pw * (E * fc) * (Real)sf.outer[tau];
                     }
                 }
             }
@@ -419,30 +441,19 @@ k_sf_backward(int n, SfDev sf, int n_types, int row_cap,
             seg[t + 1] = seg[t] + (t < n_types ? tcounts[(size_t)idx * n_types + t] : 0);
         const size_t ebase = (size_t)slice_ptr[idx >> 5] * 32u + (idx & 31);
         double fx = 0, fy = 0, fz = 0;
-        for (int a = lane; a < cnt; a += SF_TPA) {
-            const double *ea = row + a * ROW_W;
+        // 4 sub-threads per row entry a: each covers every 4th partner b, the four
+        // partial sums are combined with two shuffles (fixed order)
+        const int sub = lane & 3;
+        for (int a0 = 0; a0 < cnt; a0 += SF_TPA / 4) {
+            const int a = a0 + (lane >> 2);
+            const bool valid = a < cnt;
+            const double *ea = row + (valid ? a : 0) * ROW_W;
             const Real ax = (Real)ea[0], ay = (Real)ea[1], az = (Real)ea[2], ra = (Real)ea[3];
             const Real fa = (Real)ea[4], dfa = (Real)ea[5];
             const int ta = (int)ea[6];
-            // ---- G2 part
-            Real s_r = Real(0);                       // dE/dr_a
-            {
-                Real f, df;
-                cutoff_fn<Real>(sf.cutoff, ra, rc, f, df);
-                const int term = radial_term(ti, ta);
-                for (int tau = 0; tau < sf.n_r; ++tau) {
-                    const Real eta = (Real)sf.eta[tau], d = ra - (Real)sf.omega[tau];
-                    const Real e = Math<Real>::exp_(-eta * d * d * rc2i);
-                    s_r += (Real)c[term * sf.n_r + tau] *
-                           (e * df - Real(2) * eta * d * rc2i * e * f);
-                }
-            }
-            Real gx = s_r * ax / ra, gy = s_r * ay / ra, gz = s_r * az / ra;
-            // ---- G4 part: all other legs b of the triples (i; a, b)
-            if (sf.angular && fa != Real(0)) {
-                Real sa = Real(0);          // sum dV/dr_a
-                Real wx = 0, wy = 0, wz = 0;   // sum dV/dr_ab * (D_a - D_b)/r_ab
-                for (int b = 0; b < cnt; ++b) {
+            Real sa = Real(0), wx = Real(0), wy = Real(0), wz = Real(0);
+            if (valid && sf.angular && fa != Real(0)) {
+                for (int b = sub; b < cnt; b += 4) {
                     if (b == a) continue;
                     const double *eb = row + b * ROW_W;
                     const Real fb = (Real)eb[4];
@@ -474,7 +485,7 @@ k_sf_backward(int n, SfDev sf, int n_types, int row_cap,
                         dP *= gm;
                         if (tau == 0 || sf.beta[tau] != sf.beta[tau - 1])
                             E = Math<Real>::exp_(-be * s2 * ac2i);
-                        const Real K = exp2(Real(1) - z) * (Real)cc[tau];
+                        const Real K = (Real)sf.outer[tau] * (Real)cc[tau];
                         const Real PE = P * E;
                         va += K * (dP * dct_da * E * F3 - Real(2) * be * ra * ac2i * PE * F3 +
                                    PE * dfa * fb * fab);
@@ -487,11 +498,31 @@ k_sf_backward(int n, SfDev sf, int n_types, int row_cap,
                     wy += q * jy;
                     wz += q * jz;
                 }
-                const Real q = sa / ra;
-                gx += q * ax + wx;
-                gy += q * ay + wy;
-                gz += q * az + wz;
             }
+            // combine the 4 sub-threads (all lanes take part in the shuffles)
+#pragma unroll
+            for (int d = 1; d <= 2; d <<= 1) {
+                sa += __shfl_xor_sync(0xffffffffu, sa, d);
+                wx += __shfl_xor_sync(0xffffffffu, wx, d);
+                wy += __shfl_xor_sync(0xffffffffu, wy, d);
+                wz += __shfl_xor_sync(0xffffffffu, wz, d);
+            }
+            if (!valid || sub != 0) continue;
+            // ---- G2 part
+            Real s_r = Real(0);                       // dE/dr_a
+            {
+                Real f, df;
+                cutoff_fn<Real>(sf.cutoff, ra, rc, f, df);
+                const int term = radial_term(ti, ta);
+                for (int tau = 0; tau < sf.n_r; ++tau) {
+                    const Real eta = (Real)sf.eta[tau], d = ra - (Real)sf.omega[tau];
+                    const Real e = Math<Real>::exp_(-eta * d * d * rc2i);
+                    s_r += (Real)c[term * sf.n_r + tau] *
+                           (e * df - Real(2) * eta * d * rc2i * e * f);
+                }
+            }
+            const Real q = (s_r + sa) / ra;
+            const Real gx = q * ax + wx, gy = q * ay + wy, gz = q * az + wz;
             const size_t e = ebase + (size_t)a * 32u;
             gvec[e] = (double)gx;
             gvec[plane + e] = (double)gy;
@@ -522,7 +553,8 @@ k_sf_backward(int n, SfDev sf, int n_types, int row_cap,
     }
 }
 
-// F_i = sum_p g_p - sum_p g_rev(p); per-atom energies to caller order; energy partials
+// F_i = sum_p g_p - sum_p g_rev(p); per-atom energies to caller order; energy
+// partials.  One warp per atom (lanes stride over the row), 4 atoms per block.
 __global__ void __launch_bounds__(128)
 k_sf_collect(int n, int n_loc, const int *__restrict__ counts,
              const uint32_t *__restrict__ slice_ptr, const uint32_t *__restrict__ col,
@@ -532,14 +564,14 @@ k_sf_collect(int n, int n_loc, const int *__restrict__ counts,
              double *__restrict__ eatom, double *__restrict__ forces,
              double *__restrict__ partial_e) {
     __shared__ double red[4];
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int idx = blockIdx.x * 4 + warp;
     double e = 0.0;
     if (idx < n) {
-        double fx = fown[3 * (size_t)idx], fy = fown[3 * (size_t)idx + 1],
-               fz = fown[3 * (size_t)idx + 2];
+        double fx = 0.0, fy = 0.0, fz = 0.0;
         const size_t base = (size_t)slice_ptr[idx >> 5] * 32u + (idx & 31);
         const int cnt = counts[idx];
-        for (int k = 0; rev && k < cnt; ++k) {
+        for (int k = lane; rev && k < cnt; k += 32) {
             const size_t ent = base + (size_t)k * 32u;
             const uint32_t q = rev[ent];
             if (q == 0xFFFFFFFFu) continue;
@@ -550,17 +582,21 @@ k_sf_collect(int n, int n_loc, const int *__restrict__ counts,
             fy -= gvec[plane + re];
             fz -= gvec[2 * plane + re];
         }
-        const int o = perm[idx];
-        if (forces) {
-            forces[3 * (size_t)o + 0] = fx;
-            forces[3 * (size_t)o + 1] = fy;
-            forces[3 * (size_t)o + 2] = fz;
+        fx = warp_sum(fx);
+        fy = warp_sum(fy);
+        fz = warp_sum(fz);
+        if (lane == 0) {
+            const int o = perm[idx];
+            if (forces) {
+                forces[3 * (size_t)o + 0] = fx + fown[3 * (size_t)idx];
+                forces[3 * (size_t)o + 1] = fy + fown[3 * (size_t)idx + 1];
+                forces[3 * (size_t)o + 2] = fz + fown[3 * (size_t)idx + 2];
+            }
+            e = eat[idx];
+            if (eatom) eatom[o] = e;
         }
-        e = eat[idx];
-        if (eatom) eatom[o] = e;
     }
-    e = warp_sum(e);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = e;
+    if (lane == 0) red[warp] = e;
     __syncthreads();
     if (threadIdx.x == 0) partial_e[(size_t)blockIdx.x] = red[0] + red[1] + red[2] + red[3];
 }
@@ -720,7 +756,7 @@ k_sf_jvp(int n, int n_loc, SfDev sf, int n_types, int row_cap,
                         const Real P = powz<Real>(Real(1) + gm * ct, z, dP);
                         if (tau == 0 || sf.beta[tau] != sf.beta[tau - 1])
                             E = Math<Real>::exp_(-be * ss * ac2i);
-                        acc[tau] += exp2(Real(1) - z) *
+                        acc[tau] += (Real)sf.outer[tau] *
                                     (dP * gm * dct * E * F3 - be * ac2i * dss * P * E * F3 +
                                      P * E * dF3);
                     }
@@ -782,6 +818,7 @@ extern "C" int tab_atomic_create(tab_atomic **out, const tab_sf_desc *d,
         sf.beta[k] = d->beta[k];
         sf.gamma[k] = d->gamma[k];
         sf.zeta[k] = d->zeta[k];
+        sf.outer[k] = pow(2.0, 1.0 - d->zeta[k]);
     }
     sf.d_r = sf.n_el * sf.n_r;
     sf.dim = sf.d_r + (sf.angular ? sf.n_el * (sf.n_el + 1) / 2 * sf.n_a : 0);
@@ -911,7 +948,7 @@ static int atomic_run(tab_atomic *m, tab_nbr *nbr, double *d_energy, double *d_e
     }
     const int nblk = n;                       // one block per atom
     const int nblk_m = (n + MLP_WARPS - 1) / MLP_WARPS;
-    const int nblk_c = (n + 127) / 128;
+    const int nblk_c = (n + 3) / 4;
     TAB_TRY(m->G.ensure(sizeof(double) * (size_t)n * sf.dim));
     TAB_TRY(m->dEdG.ensure(sizeof(double) * (size_t)n * sf.dim));
     TAB_TRY(m->eat.ensure(sizeof(double) * (size_t)n));
@@ -1018,7 +1055,7 @@ static int atomic_forces_from(tab_atomic *m, tab_nbr *nbr, const double *d_dedg,
     const size_t smem_row = (size_t)row_cap * ROW_W * sizeof(double);
     TAB_CUDA(cudaFuncSetAttribute(k_sf_backward<Real>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    const int nblk = n, nblk_c = (n + 127) / 128;
+    const int nblk = n, nblk_c = (n + 3) / 4;
     TAB_TRY(m->dEdG.ensure(sizeof(double) * (size_t)n * sf.dim));
     TAB_TRY(m->eat.ensure(sizeof(double) * (size_t)n));
     TAB_TRY(m->fown.ensure(sizeof(double) * 3 * (size_t)n));
