@@ -17,6 +17,8 @@
 //   pass 1: rho_i, F(rho_i), F'(rho_i)
 //   spread: Atom4.w <- F' for owned atoms and their ghost images
 //   pass 2: forces, per-atom energy, block-reduced energy and virial
+#include <stdlib.h>
+
 #include "potentials.cuh"
 
 struct EamDev {
@@ -91,7 +93,20 @@ struct RowIter {
         if (k + 1 < cnt) c_nx2 = cp[(size_t)(k + 1) * 32u];
         return true;
     }
+    // entry index of the element returned by the last next()
+    __device__ __forceinline__ int pos() const { return k - 1; }
 };
+
+// Per-pair cache between the two passes of the single-element zjw04 fast path:
+// pass 1 has to evaluate g(r) = exp(-beta (x-1)) / (1 + (x-lamda)^20) for rho anyway;
+// it also stores (g, dg/dr) per directed pair (ELL layout, 16 B, coalesced,
+// streaming) and pass 2 reads them back instead of repeating one of its two
+// exponentials.  The kernels are FP64-pipe bound and HBM has slack (profiles/r01d),
+// so 32 B of traffic per pair buys ~38 of ~113 FP64 instructions of pass 2.
+__device__ __forceinline__ void cache_store(double2 *p, double a, double b) {
+    __stcs(p, make_double2(a, b));
+}
+__device__ __forceinline__ double2 cache_load(const double2 *p) { return __ldcs(p); }
 
 __device__ __forceinline__ void load_tables(tab_fn *s, const tab_fn *g, int count) {
     const int words = count * (int)(sizeof(tab_fn) / 8);
@@ -104,14 +119,14 @@ __device__ __forceinline__ void load_tables(tab_fn *s, const tab_fn *g, int coun
 // ---------------------------------------------------------------------------
 // pass 1
 // ---------------------------------------------------------------------------
-template <typename Real, bool FAST>
+template <typename Real, bool FAST, bool CACHE>
 __global__ void __launch_bounds__(EAM_T, EAM_MINB)
 k_eam_rho(int n, const Atom4 *__restrict__ atoms,
           const uint8_t *__restrict__ types_ext, const int *__restrict__ counts,
           const uint32_t *__restrict__ slice_ptr, const uint32_t *__restrict__ col,
           const int *__restrict__ perm, EamDev m, Zhou1 z, tab_fn embed0,
           double *__restrict__ fprime, double *__restrict__ fembed,
-          double *__restrict__ fprime_caller) {
+          double *__restrict__ fprime_caller, double2 *__restrict__ pcache) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     tab_fn *tabs = reinterpret_cast<tab_fn *>(smem_raw);
     const int nn = m.n_el * m.n_el;
@@ -121,7 +136,8 @@ k_eam_rho(int n, const Atom4 *__restrict__ atoms,
     const Atom4 me = atoms[idx];
     const int ti = FAST ? 0 : (int)types_ext[idx];
     const int cnt = counts[idx];
-    const uint32_t *cp = col + ((size_t)slice_ptr[idx >> 5] * 32u + (idx & 31));
+    const size_t row0 = (size_t)slice_ptr[idx >> 5] * 32u + (idx & 31);
+    const uint32_t *cp = col + row0;
     Real rho = Real(0);
     RowIter it(cp, atoms, cnt);
     Atom4 a;
@@ -130,13 +146,16 @@ k_eam_rho(int n, const Atom4 *__restrict__ atoms,
         Real dx, dy, dz, r, rinv, f, df;
         pair_r<Real>(me, a, dx, dy, dz, r, rinv);
         if (FAST) {
-            zhou_exp<Real>(r, (Real)z.fe, (Real)z.beta, (Real)z.lamda, (Real)z.re, f, df);
+            // g with unit prefactor; rho = fe * sum g
+            zhou_exp<Real>(r, Real(1), (Real)z.beta, (Real)z.lamda, (Real)z.re, f, df);
+            if (CACHE) cache_store(pcache + row0 + (size_t)it.pos() * 32u, (double)f, (double)df);
         } else {
             const int tj = (int)(c >> TAB_COL_TYPE_SHIFT);
             eval_pair_fn<Real>(tabs[ti * m.n_el + tj], r, f, df, m.pool);
         }
         rho += f;
     }
+    if (FAST) rho *= (Real)z.fe;
     Real F, dF;
     if (FAST) eval_embed_fn<Real>(embed0, rho, F, dF);
     else eval_embed_fn<Real>(tabs[2 * nn + ti], rho, F, dF, m.pool);
@@ -163,14 +182,15 @@ __global__ void k_spread_w(int n_owned, int n_loc, int n_ext,
 // ---------------------------------------------------------------------------
 // pass 2
 // ---------------------------------------------------------------------------
-template <typename Real, bool FAST>
+template <typename Real, bool FAST, bool CACHE>
 __global__ void __launch_bounds__(EAM_T, EAM_MINB)
 k_eam_force(int n, const Atom4 *__restrict__ atoms,
             const uint8_t *__restrict__ types_ext, const int *__restrict__ counts,
             const uint32_t *__restrict__ slice_ptr, const uint32_t *__restrict__ col,
             const int *__restrict__ perm, EamDev m, Zhou1 z,
             const double *__restrict__ fembed, double *__restrict__ eatom,
-            double *__restrict__ forces, double *__restrict__ partial) {
+            double *__restrict__ forces, double *__restrict__ partial,
+            const double2 *__restrict__ pcache) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     tab_fn *tabs = reinterpret_cast<tab_fn *>(smem_raw);
     __shared__ double red[EAM_T / 32][7];
@@ -182,13 +202,16 @@ k_eam_force(int n, const Atom4 *__restrict__ atoms,
         const Atom4 me = atoms[idx];
         const int ti = FAST ? 0 : (int)types_ext[idx];
         const int cnt = counts[idx];
-        const uint32_t *cp = col + ((size_t)slice_ptr[idx >> 5] * 32u + (idx & 31));
+        const size_t row0 = (size_t)slice_ptr[idx >> 5] * 32u + (idx & 31);
+        const uint32_t *cp = col + row0;
         const Real fpi = (Real)me.w;
         Real fx = 0, fy = 0, fz = 0, ep = 0;
         Real vxx = 0, vyy = 0, vzz = 0, vyz = 0, vxz = 0, vxy = 0;
         RowIter it(cp, atoms, cnt);
         Atom4 a;
         uint32_t c;
+        double2 pc_nx = make_double2(0.0, 0.0);
+        if (CACHE && cnt > 0) pc_nx = cache_load(pcache + row0);
         while (it.next(a, c)) {
             Real dx, dy, dz, r, rinv;
             pair_r<Real>(me, a, dx, dy, dz, r, rinv);
@@ -197,7 +220,14 @@ k_eam_force(int n, const Atom4 *__restrict__ atoms,
             if (FAST) {
                 Real ga, dga, gb, dgb;
                 zhou_exp<Real>(r, Real(1), (Real)z.alpha, (Real)z.kappa, (Real)z.re, ga, dga);
-                zhou_exp<Real>(r, Real(1), (Real)z.beta, (Real)z.lamda, (Real)z.re, gb, dgb);
+                if (CACHE) {
+                    gb = (Real)pc_nx.x;
+                    dgb = (Real)pc_nx.y;
+                    if (it.pos() + 1 < cnt)
+                        pc_nx = cache_load(pcache + row0 + (size_t)(it.pos() + 1) * 32u);
+                } else {
+                    zhou_exp<Real>(r, Real(1), (Real)z.beta, (Real)z.lamda, (Real)z.re, gb, dgb);
+                }
                 phi = (Real)z.A * ga - (Real)z.B * gb;
                 dphi = (Real)z.A * dga - (Real)z.B * dgb;
                 der = (fpi + fpj) * ((Real)z.fe * dgb) + dphi;
@@ -693,18 +723,42 @@ static int eam_prepare(tab_model *m, tab_nbr *nbr, bool fast, EamLaunch &L) {
     return TAB_OK;
 }
 
+// The per-pair cache is OFF by default: measured on B200 (1 M atoms) it makes pass 1
+// slower (0.38 -> 0.56 ms, the 1.46 GB stream) by more than pass 2 gains (0.73 -> 0.71 ms;
+// that pass is co-limited by L1 gather wavefronts, not by FP64 alone).  TAB_EAM_PAIR_CACHE=1
+// enables it for experiments (profiles/README.md, round 1).
+static bool pair_cache_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char *e = getenv("TAB_EAM_PAIR_CACHE");
+        on = (e && e[0] == '1') ? 1 : 0;
+    }
+    return on == 1;
+}
+
 template <typename Real, bool FAST>
 static int eam_pass1(tab_model *m, tab_nbr *nbr, double *d_fprime_caller,
                      cudaStream_t st) {
     EamLaunch L;
     TAB_TRY(eam_prepare(m, nbr, FAST, L));
+    const bool cache = FAST && sizeof(Real) == 8 && pair_cache_enabled();
+    if (cache) TAB_TRY(nbr->pcache.ensure(sizeof(double2) * 32 * (size_t)(nbr->ell_rows + 1)));
+    nbr->pcache_valid = false;
     prof_mark(0, st);
-    k_eam_rho<Real, FAST><<<L.nblk, EAM_T, L.smem, st>>>(
-        nbr->n, nbr->atoms.as<Atom4>(), nbr->types_ext.as<uint8_t>(),
-        nbr->counts.as<int>(), nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>(),
-        nbr->perm.as<int>(), L.dev, L.z, m->embed0, L.fprime, L.fembed,
-        d_fprime_caller);
+    if (cache)
+        k_eam_rho<Real, FAST, FAST><<<L.nblk, EAM_T, L.smem, st>>>(
+            nbr->n, nbr->atoms.as<Atom4>(), nbr->types_ext.as<uint8_t>(),
+            nbr->counts.as<int>(), nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>(),
+            nbr->perm.as<int>(), L.dev, L.z, m->embed0, L.fprime, L.fembed,
+            d_fprime_caller, nbr->pcache.as<double2>());
+    else
+        k_eam_rho<Real, FAST, false><<<L.nblk, EAM_T, L.smem, st>>>(
+            nbr->n, nbr->atoms.as<Atom4>(), nbr->types_ext.as<uint8_t>(),
+            nbr->counts.as<int>(), nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>(),
+            nbr->perm.as<int>(), L.dev, L.z, m->embed0, L.fprime, L.fembed,
+            d_fprime_caller, nullptr);
     TAB_LAUNCH_CHECK();
+    nbr->pcache_valid = cache;
     prof_mark(1, st);
     return TAB_OK;
 }
@@ -724,11 +778,20 @@ static int eam_pass2(tab_model *m, tab_nbr *nbr, const double *d_fprime_halo,
         nbr->ghost_owner.as<int>(), nbr->atoms.as<Atom4>());
     TAB_LAUNCH_CHECK();
     prof_mark(2, st);
-    k_eam_force<Real, FAST><<<L.nblk, EAM_T, L.smem, st>>>(
-        nbr->n, nbr->atoms.as<Atom4>(), nbr->types_ext.as<uint8_t>(),
-        nbr->counts.as<int>(), nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>(),
-        nbr->perm.as<int>(), L.dev, L.z, L.fembed, d_eatom, d_forces,
-        nbr->partial.as<double>());
+    // pass 1 of the same evaluation left (g, g') per pair behind (positions unchanged
+    // in between: tab_nbr_update / tab_nbr_build invalidate)
+    if (FAST && sizeof(Real) == 8 && nbr->pcache_valid)
+        k_eam_force<Real, FAST, FAST><<<L.nblk, EAM_T, L.smem, st>>>(
+            nbr->n, nbr->atoms.as<Atom4>(), nbr->types_ext.as<uint8_t>(),
+            nbr->counts.as<int>(), nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>(),
+            nbr->perm.as<int>(), L.dev, L.z, L.fembed, d_eatom, d_forces,
+            nbr->partial.as<double>(), nbr->pcache.as<double2>());
+    else
+        k_eam_force<Real, FAST, false><<<L.nblk, EAM_T, L.smem, st>>>(
+            nbr->n, nbr->atoms.as<Atom4>(), nbr->types_ext.as<uint8_t>(),
+            nbr->counts.as<int>(), nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>(),
+            nbr->perm.as<int>(), L.dev, L.z, L.fembed, d_eatom, d_forces,
+            nbr->partial.as<double>(), nullptr);
     TAB_LAUNCH_CHECK();
     prof_mark(3, st);
     if (d_energy || d_virial) {

@@ -31,6 +31,7 @@
 // within 1e-9 relative of rc^2 are re-decided with exactly ASE's expression on
 // the caller's positions, so the list is bit-exact.
 #include <math.h>
+#include <stdlib.h>
 
 #include "tab_internal.h"
 
@@ -90,6 +91,9 @@ __global__ void k_bin(int n, int n_owned, const double *__restrict__ pos,
             b -= sh[k] * g.nb[k];
         } else {
             sh[k] = 0;
+            // atoms more than one bin outside a non-periodic frame: stats[4] (the
+            // tile kernel's distance form wants bounded coordinates)
+            if (b < -1 || b > g.nb[k]) atomicMax(&stats[4], 1ull);
             b = min(max(b, 0), g.nb[k] - 1);
         }
         c[k] = b;
@@ -486,6 +490,259 @@ k_nbr_warp(int n, Grid g, ExactCtx x, const int *__restrict__ cell_of,
     }
 }
 
+// ---- block-per-tile variant (large systems), SINGLE PASS.
+//      One block = one B x B x B tile of owned cells, one thread = one atom of the
+//      tile.  The candidates of the tile's neighbourhood box (tile cells +- sr) are
+//      staged ONCE per block in shared memory, cell by cell in ascending
+//      (ez, ey, ex) order; every lane then walks the cells of its own cell's
+//      neighbourhood and reads the candidates as shared-memory broadcasts.  Per-atom
+//      candidate order is identical to for_each_neighbor(), so the rows hold the
+//      same entries in the same order as the thread-per-atom kernels (which remain
+//      for odd geometries).
+//
+//      Hits are written straight into rows of a FIXED capacity `wcap` (row of atom
+//      idx, entry k at rows[((idx >> 5) * wcap + k) * 32 + (idx & 31)]) while they
+//      are counted; counting continues past the capacity, so the host can see an
+//      overflow (nnl_max > wcap) and repeat the launch with the exact width.  For a
+//      single species these rows ARE the list (slice_ptr[s] = s * wcap); with
+//      several species k_rows_by_species regroups them into compact slices.
+//
+//      Distance test: with p = candidate and m = centre, both relative to the box
+//      centre c,  d^2 - rc^2 = (|p|^2 - 2 p.m) - (rc^2 - |m|^2):  |p|^2 is staged,
+//      the right-hand side is a per-thread constant, so one candidate costs three
+//      DFMA and two DSETP.  Rounding of this form is O(1e-16 |p|^2) -- the host
+//      only selects the kernel when that is below a quarter of the 1e-9 rc^2 band
+//      inside which membership is re-decided with ASE's exact expression: a cell
+//      segment is first scanned speculatively (band candidates counted as hits);
+//      if any of its candidates fell into the band the segment is re-scanned with
+//      the exact test (rare: the band is ~1e-9 wide).
+#define NBT_THREADS 256
+#define NBT_CAP 1024      // staged candidates per window (36 B each)
+#define NBT_CELLS 256     // box cells whose table entries are cached per batch
+
+template <bool EXACT>
+__device__ __forceinline__ bool nbt_scan(int kbeg, int kend, const double2 *cxy,
+                                         const double2 *czp, const uint32_t *cen,
+                                         double m2x, double m2y, double m2z, double thr_hi,
+                                         double thr_lo, int idx, uint32_t wcap,
+                                         uint32_t *__restrict__ base, uint32_t &kk,
+                                         const Grid &g, const ExactCtx &x) {
+    bool near_any = false;
+#pragma unroll 4
+    for (int k = kbeg; k < kend; ++k) {
+        const double2 p = cxy[k], q = czp[k];
+        const uint32_t e = cen[k];
+        const double t = fma(q.x, m2z, fma(p.y, m2y, fma(p.x, m2x, q.y)));
+        // in = t < hi ; near = in && t > lo  (two DSETP, the second predicated on
+        // the first: nvcc alone emits three)
+        unsigned in_u, near_u;
+        asm("{\n\t.reg .pred p, q;\n\t"
+            "setp.lt.f64 p, %2, %3;\n\t"
+            "setp.gt.and.f64 q, %2, %4, p;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "selp.u32 %1, 1, 0, q;\n\t}"
+            : "=r"(in_u), "=r"(near_u)
+            : "d"(t), "d"(thr_hi), "d"(thr_lo));
+        bool in = in_u != 0u;
+        if (EXACT) {
+            if (near_u) in = exact_inside(g, x, idx, (int)(e & TAB_COL_IDX_MASK));
+        } else {
+            near_any |= near_u != 0u;
+        }
+        in = in && (int)(e & TAB_COL_IDX_MASK) != idx;
+        if (in && kk < wcap) base[(size_t)kk * 32u] = e;
+        kk += in ? 1u : 0u;
+    }
+    return near_any;
+}
+
+__global__ void __launch_bounds__(NBT_THREADS)
+k_nbr_tile(int n, Grid g, ExactCtx x, const Atom4 *__restrict__ atoms,
+           const uint8_t *__restrict__ types_ext,
+           const uint32_t *__restrict__ cell_start,
+           const uint32_t *__restrict__ cell_count,
+           const uint4 *__restrict__ ext_tab, uint32_t wcap,
+           int *__restrict__ counts, uint32_t *__restrict__ rows) {
+    __shared__ double2 cxy[NBT_CAP];        // x, y   (relative to the box centre)
+    __shared__ double2 czp[NBT_CAP];        // z, |p|^2
+    __shared__ uint32_t cen[NBT_CAP];       // entry = index | species << 28
+    __shared__ uint4 cell_tab[NBT_CELLS];   // {start_a, count_a, start_b, count_b}
+    __shared__ int cell_pc[NBT_CELLS];      // packed box coordinates of the cell
+    __shared__ int cell_off[NBT_CELLS + 1]; // candidate offset of the cell in the batch
+    __shared__ int warp_tot[NBT_THREADS / 32];
+    __shared__ uint32_t tile_start[B * B * B + 1];
+
+    const int tile = blockIdx.x;
+    const int tid = threadIdx.x;
+    if (tid < B * B * B) tile_start[tid] = cell_start[tile * (B * B * B) + tid];
+    if (tid == B * B * B - 1)
+        tile_start[B * B * B] = cell_start[tile * (B * B * B) + tid] +
+                                cell_count[tile * (B * B * B) + tid];
+    __syncthreads();
+    const int a0 = (int)tile_start[0], a1 = (int)tile_start[B * B * B];
+    if (a1 <= a0) return;
+
+    int t3[3];
+    t3[0] = tile % g.tl[0];
+    t3[1] = (tile / g.tl[0]) % g.tl[1];
+    t3[2] = tile / (g.tl[0] * g.tl[1]);
+    int b0[3], bn[3];
+    double ctr[3] = {g.origin[0], g.origin[1], g.origin[2]};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        int lo = t3[k] * B - g.sr[k];
+        int hi = min(t3[k] * B + B - 1, g.nb[k] - 1) + g.sr[k];
+        if (!g.pbc[k]) {
+            lo = max(lo, 0);
+            hi = min(hi, g.nb[k] - 1);
+        }
+        b0[k] = lo;
+        bn[k] = hi - lo + 1;
+        // box centre in scaled coordinates along k -> Cartesian
+        const double sc = 0.5 * (double)(lo + hi + 1) / (double)g.nb[k];
+        ctr[0] += sc * g.h[3 * k + 0];
+        ctr[1] += sc * g.h[3 * k + 1];
+        ctr[2] += sc * g.h[3 * k + 2];
+    }
+    const int box_cells = bn[0] * bn[1] * bn[2];
+    const double tol = 1e-9 * g.rc2;
+    const int sr0 = g.sr[0], sr1 = g.sr[1], sr2 = g.sr[2];
+
+    for (int chunk = a0; chunk < a1; chunk += NBT_THREADS) {
+        const int idx = chunk + tid;
+        const bool active = idx < a1;
+        int mx = 0, my = 0, mz = 0;       // my cell, relative to the box origin
+        double m2x = 0, m2y = 0, m2z = 0, thr_hi = 0, thr_lo = 0;
+        uint32_t *base = rows;
+        if (active) {
+            int l = -1;
+#pragma unroll
+            for (int q = 0; q < B * B * B; ++q) l += tile_start[q] <= (uint32_t)idx ? 1 : 0;
+            mx = t3[0] * B + l % B - b0[0];
+            my = t3[1] * B + (l / B) % B - b0[1];
+            mz = t3[2] * B + l / (B * B) - b0[2];
+            const Atom4 me = atoms[idx];
+            const double ux = me.x - ctr[0], uy = me.y - ctr[1], uz = me.z - ctr[2];
+            const double mm = ux * ux + uy * uy + uz * uz;
+            m2x = -2.0 * ux;
+            m2y = -2.0 * uy;
+            m2z = -2.0 * uz;
+            thr_hi = (g.rc2 + tol) - mm;
+            thr_lo = (g.rc2 - tol) - mm;
+            base = rows + ((size_t)(idx >> 5) * wcap * 32u + (idx & 31));
+        }
+        uint32_t kk = 0;                  // hits so far = next row slot
+
+        for (int batch = 0; batch < box_cells; batch += NBT_CELLS) {
+            const int batch_cells = min(NBT_CELLS, box_cells - batch);
+            __syncthreads();              // previous users of the tables / buffers are done
+            // every thread owns one box cell: table entry, packed coordinates, and an
+            // exclusive block scan of the candidate counts
+            int mine = 0;
+            if (tid < batch_cells) {
+                const int q = batch + tid;
+                const int qx = q % bn[0], qy = (q / bn[0]) % bn[1], qz = q / (bn[0] * bn[1]);
+                const uint4 t = ext_tab[((b0[2] + qz + g.g[2]) * g.ne[1] + (b0[1] + qy + g.g[1])) *
+                                            g.ne[0] + (b0[0] + qx + g.g[0])];
+                cell_tab[tid] = t;
+                cell_pc[tid] = qx | (qy << 8) | (qz << 16);
+                mine = (int)(t.y + t.w);
+            }
+            int incl = mine;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, d);
+                if ((tid & 31) >= d) incl += v;
+            }
+            if ((tid & 31) == 31) warp_tot[tid >> 5] = incl;
+            __syncthreads();
+            int wbase = 0;
+#pragma unroll
+            for (int w = 0; w < NBT_THREADS / 32; ++w) wbase += w < (tid >> 5) ? warp_tot[w] : 0;
+            cell_off[tid] = wbase + incl - mine;
+            if (tid == NBT_THREADS - 1) cell_off[NBT_CELLS] = wbase + incl;
+            __syncthreads();
+            const int total = cell_off[NBT_CELLS];
+
+            for (int w0 = 0; w0 < total; w0 += NBT_CAP) {
+                const int w1 = min(total, w0 + NBT_CAP);
+                if (w0 > 0) __syncthreads();          // the previous window has been consumed
+                // stage the window: one warp per cell
+                for (int c = tid >> 5; c < batch_cells; c += NBT_THREADS / 32) {
+                    const int c0 = cell_off[c];
+                    const uint4 t = cell_tab[c];
+                    const int lo = max(c0, w0), hi = min(c0 + (int)(t.y + t.w), w1);
+                    for (int u = lo + (tid & 31); u < hi; u += 32) {
+                        const int o = u - c0;
+                        const uint32_t j = o < (int)t.y ? t.x + (uint32_t)o
+                                                        : t.z + (uint32_t)(o - (int)t.y);
+                        const Atom4 a = atoms[j];
+                        const double px = a.x - ctr[0], py = a.y - ctr[1], pz = a.z - ctr[2];
+                        cxy[u - w0] = make_double2(px, py);
+                        czp[u - w0] = make_double2(pz, px * px + py * py + pz * pz);
+                        cen[u - w0] = j | ((uint32_t)types_ext[j] << TAB_COL_TYPE_SHIFT);
+                    }
+                }
+                __syncthreads();
+                if (active) {
+                    for (int c = 0; c < batch_cells; ++c) {
+                        const int pc = cell_pc[c];
+                        const int ddx = (pc & 255) - mx, ddy = ((pc >> 8) & 255) - my,
+                                  ddz = (pc >> 16) - mz;
+                        if (abs(ddx) > sr0 || abs(ddy) > sr1 || abs(ddz) > sr2) continue;
+                        const int kbeg = max(cell_off[c], w0) - w0;
+                        const int kend = min(cell_off[c + 1], w1) - w0;
+                        const uint32_t kk0 = kk;
+                        if (nbt_scan<false>(kbeg, kend, cxy, czp, cen, m2x, m2y, m2z, thr_hi,
+                                            thr_lo, idx, wcap, base, kk, g, x)) {
+                            kk = kk0;
+                            nbt_scan<true>(kbeg, kend, cxy, czp, cen, m2x, m2y, m2z, thr_hi,
+                                           thr_lo, idx, wcap, base, kk, g, x);
+                        }
+                    }
+                }
+            }
+        }
+        if (active) counts[idx] = (int)kk;
+    }
+}
+
+// several species: regroup the fixed-capacity rows of k_nbr_tile by neighbour
+// species (stable) into the compact slices; also produces the per-species counts.
+__global__ void __launch_bounds__(128)
+k_rows_by_species(int n, int n_types, uint32_t wcap, const int *__restrict__ counts,
+                  const uint32_t *__restrict__ rows, const uint32_t *__restrict__ slice_ptr,
+                  uint32_t *__restrict__ col, int *__restrict__ tcounts) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const uint32_t *src = rows + ((size_t)(idx >> 5) * wcap * 32u + (idx & 31));
+    uint32_t *dst = col + ((size_t)slice_ptr[idx >> 5] * 32u + (idx & 31));
+    const int cnt = counts[idx];
+    uint32_t off[TAB_MAX_ELEMENTS];
+    for (int t = 0; t < n_types; ++t) off[t] = 0;
+    for (int k = 0; k < cnt; ++k) ++off[src[(size_t)k * 32u] >> TAB_COL_TYPE_SHIFT];
+    uint32_t run = 0;
+    for (int t = 0; t < n_types; ++t) {
+        const uint32_t c = off[t];
+        tcounts[(size_t)idx * n_types + t] = (int)c;
+        off[t] = run;
+        run += c;
+    }
+    for (int k = 0; k < cnt; ++k) {
+        const uint32_t e = src[(size_t)k * 32u];
+        dst[(size_t)(off[e >> TAB_COL_TYPE_SHIFT]++) * 32u] = e;
+    }
+}
+
+// single species, fixed-capacity rows used in place: slice_ptr[s] = s * wcap
+__global__ void k_fixed_slices(int n, int n_slices, uint32_t wcap,
+                               const int *__restrict__ counts,
+                               uint32_t *__restrict__ slice_ptr, int *__restrict__ tcounts) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_slices) slice_ptr[i] = (uint32_t)i * wcap;
+    if (i < n) tcounts[i] = counts[i];
+}
+
 // slice widths (max count of the 32 atoms of a slice), nij, nnl_max; pads the
 // columns of the non-existent atoms of the last slice
 __global__ void k_slice_stats(int n, const int *__restrict__ counts,
@@ -704,7 +961,7 @@ extern "C" int tab_nbr_free(tab_nbr *nbr) {
                       &nbr->ext_tab, &nbr->gcount, &nbr->gstart,
                       &nbr->slice_w, &nbr->slice_ptr, &nbr->col, &nbr->scan_tmp,
                       &nbr->stats, &nbr->row_ptr, &nbr->rho, &nbr->partial, &nbr->adp,
-                      &nbr->tcounts, &nbr->rev};
+                      &nbr->tcounts, &nbr->rev, &nbr->pcache, &nbr->rows_tmp};
     for (DevBuf *b : bufs) b->release();
     delete nbr;
     return TAB_OK;
@@ -714,6 +971,7 @@ static inline int nblocks(long long n, int t) { return (int)((n + t - 1) / t); }
 
 static int refresh_positions(tab_nbr *nbr, const double *d_pos, cudaStream_t st) {
     const Grid &g = nbr->grid;
+    nbr->pcache_valid = false;
     k_gather_owned<<<nblocks(nbr->n_loc, 256), 256, 0, st>>>(
         nbr->n_loc, d_pos, nullptr, g, nbr->perm.as<int>(), nbr->s0.as<int>(),
         nbr->atoms.as<Atom4>(), nullptr);
@@ -745,6 +1003,7 @@ extern "C" int tab_nbr_build_dd(tab_nbr *nbr, int32_t n_owned, int32_t n_halo,
     }
     cudaStream_t st = (cudaStream_t)stream;
     nbr->built = false;
+    nbr->pcache_valid = false;
     Grid &g = nbr->grid;
     const int n = n_owned, n_loc = (int)n_loc_ll;
     TAB_TRY(setup_grid(g, n_loc, h_cell, h_origin, h_pbc, rc));
@@ -766,12 +1025,12 @@ extern "C" int tab_nbr_build_dd(tab_nbr *nbr, int32_t n_owned, int32_t n_halo,
     TAB_TRY(nbr->gstart.ensure(sizeof(uint32_t) * g.n_ecells));
     TAB_TRY(nbr->slice_w.ensure(sizeof(uint32_t) * nbr->n_slices));
     TAB_TRY(nbr->slice_ptr.ensure(sizeof(uint32_t) * nbr->n_slices));
-    TAB_TRY(nbr->stats.ensure(4 * sizeof(unsigned long long)));
+    TAB_TRY(nbr->stats.ensure(5 * sizeof(unsigned long long)));
     unsigned long long *d_stats = nbr->stats.as<unsigned long long>();
 
     TAB_CUDA(cudaMemsetAsync(nbr->cell_count.p, 0, sizeof(uint32_t) * slots2, st));
     TAB_CUDA(cudaMemsetAsync(nbr->cell_fill.p, 0, sizeof(uint32_t) * slots2, st));
-    TAB_CUDA(cudaMemsetAsync(d_stats, 0, 4 * sizeof(unsigned long long), st));
+    TAB_CUDA(cudaMemsetAsync(d_stats, 0, 5 * sizeof(unsigned long long), st));
 
     k_bin<<<nblocks(n_loc, 256), 256, 0, st>>>(n_loc, n, d_pos, d_types, g,
                                                nbr->cell_of.as<int>(), nbr->s0.as<int>(),
@@ -799,7 +1058,7 @@ extern "C" int tab_nbr_build_dd(tab_nbr *nbr, int32_t n_owned, int32_t n_halo,
     TAB_TRY(tab_scan_exclusive_u32(nbr->gcount.as<uint32_t>(),
                                    nbr->gstart.as<uint32_t>(), g.n_ecells, d_stats + 2,
                                    nbr->scan_tmp, st));
-    unsigned long long two[2] = {0, 0};   // [n_ghost, max type]
+    unsigned long long two[3] = {0, 0, 0};   // [n_ghost, max type, atoms far outside the frame]
     TAB_CUDA(cudaMemcpyAsync(two, d_stats + 2, sizeof(two), cudaMemcpyDeviceToHost, st));
     TAB_CUDA(cudaStreamSynchronize(st));
     const unsigned long long n_ghost = two[0];
@@ -842,9 +1101,98 @@ extern "C" int tab_nbr_build_dd(tab_nbr *nbr, int32_t n_owned, int32_t n_halo,
     x.ghost_S = nbr->ghost_S.as<int>();
     x.n_loc = n_loc;
     const int nthreads = nbr->n_slices * 32;
-    // small systems: one warp per atom (parallelism); large: one thread per atom
-    const bool warp_mode = n_loc <= 20000;
+    // small systems: one warp per atom (parallelism); large: one block per tile of
+    // cells, single pass (thread per atom with shared-memory candidate staging).
+    // (TAB_NBR_MODE=thread|tile|warp overrides, for A/B measurements)
+    bool warp_mode = n_loc <= 20000;
+    // tile kernel: box indices fit 8 bits, and the |p|^2 - 2 p.m form of d^2 keeps
+    // its rounding (~8 ulp of R^2, R = half diagonal of a tile's candidate box + one
+    // bin) below a quarter of the exact-recheck band 1e-9 rc^2
+    bool tile_ok = g.sr[0] <= 100 && g.sr[1] <= 100 && g.sr[2] <= 100 && two[2] == 0;
+    {
+        double R = 0.0;
+        for (int k = 0; k < 3; ++k) {
+            const double len = sqrt(g.h[3 * k] * g.h[3 * k] + g.h[3 * k + 1] * g.h[3 * k + 1] +
+                                    g.h[3 * k + 2] * g.h[3 * k + 2]);
+            R += 0.5 * len * (double)(B + 2 * g.sr[k] + 2) / (double)g.nb[k];
+        }
+        if (8.0 * 2.3e-16 * R * R > 0.25e-9 * g.rc2) tile_ok = false;
+    }
+    bool tile_mode = !warp_mode && tile_ok;
+    if (const char *env = getenv("TAB_NBR_MODE")) {
+        warp_mode = !strcmp(env, "warp");
+        tile_mode = !strcmp(env, "tile") && tile_ok;
+    }
+    const int n_tiles = g.n_slots / (B * B * B);
     TAB_TRY(nbr->tcounts.ensure(sizeof(int) * (size_t)n * nbr->n_types));
+    unsigned long long h_stats[3];
+
+    if (tile_mode) {
+        // row capacity: last build of this handle, else the mean density
+        const bool multi = nbr->n_types > 1;
+        uint32_t wcap;
+        if (nbr->wcap_hint > 0 && nbr->wcap_hint_n == n_loc) wcap = nbr->wcap_hint;
+        else {
+            const double vol = fabs(g.h[0] * (g.h[4] * g.h[8] - g.h[5] * g.h[7]) -
+                                    g.h[1] * (g.h[3] * g.h[8] - g.h[5] * g.h[6]) +
+                                    g.h[2] * (g.h[3] * g.h[7] - g.h[4] * g.h[6]));
+            const double expect = 4.18879 * rc * rc * rc * (double)n_loc / vol;
+            wcap = (uint32_t)fmin(expect * 1.25 + 16.0, 4096.0);
+        }
+        wcap = (wcap + 7u) & ~7u;
+        for (int attempt = 0;; ++attempt) {
+            const size_t row_words = (size_t)nbr->n_slices * wcap * 32u + 32u;
+            DevBuf &rows = multi ? nbr->rows_tmp : nbr->col;
+            TAB_TRY(rows.ensure(sizeof(uint32_t) * row_words));
+            k_nbr_tile<<<n_tiles, NBT_THREADS, 0, st>>>(
+                n, g, x, nbr->atoms.as<Atom4>(), nbr->types_ext.as<uint8_t>(),
+                nbr->cell_start.as<uint32_t>(), nbr->cell_count.as<uint32_t>(),
+                nbr->ext_tab.as<uint4>(), wcap, nbr->counts.as<int>(), rows.as<uint32_t>());
+            TAB_LAUNCH_CHECK();
+            k_slice_stats<<<nblocks(nthreads, 128), 128, 0, st>>>(
+                n, nbr->counts.as<int>(), nbr->slice_w.as<uint32_t>(), d_stats);
+            TAB_LAUNCH_CHECK();
+            if (multi)
+                TAB_TRY(tab_scan_exclusive_u32(nbr->slice_w.as<uint32_t>(),
+                                               nbr->slice_ptr.as<uint32_t>(), nbr->n_slices,
+                                               d_stats + 2, nbr->scan_tmp, st));
+            TAB_CUDA(cudaMemcpyAsync(h_stats, d_stats, sizeof(h_stats),
+                                     cudaMemcpyDeviceToHost, st));
+            TAB_CUDA(cudaStreamSynchronize(st));
+            if (h_stats[1] <= wcap) break;
+            if (attempt > 0) {
+                tab_set_error("tab_nbr_build: row capacity retry failed (%llu > %u)",
+                              h_stats[1], wcap);
+                return TAB_ESTATE;
+            }
+            wcap = ((uint32_t)h_stats[1] + 7u) & ~7u;      // exact width: counting never stops
+            TAB_CUDA(cudaMemsetAsync(d_stats, 0, 3 * sizeof(unsigned long long), st));
+        }
+        nbr->nij = (long long)h_stats[0];
+        nbr->nnl_max = (int)h_stats[1];
+        nbr->ell_rows = multi ? (long long)h_stats[2] : (long long)nbr->n_slices * wcap;
+        if (nbr->ell_rows > 0xffffffffLL) {
+            tab_set_error("neighbour table too large (%lld rows)", nbr->ell_rows);
+            return TAB_EUNSUPPORTED;
+        }
+        if (multi) {
+            TAB_TRY(nbr->col.ensure(sizeof(uint32_t) * 32 * (size_t)(nbr->ell_rows + 1)));
+            k_rows_by_species<<<nblocks(n, 128), 128, 0, st>>>(
+                n, nbr->n_types, wcap, nbr->counts.as<int>(), nbr->rows_tmp.as<uint32_t>(),
+                nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>(),
+                nbr->tcounts.as<int>());
+        } else {
+            k_fixed_slices<<<nblocks(max(n, nbr->n_slices), 256), 256, 0, st>>>(
+                n, nbr->n_slices, wcap, nbr->counts.as<int>(), nbr->slice_ptr.as<uint32_t>(),
+                nbr->tcounts.as<int>());
+        }
+        TAB_LAUNCH_CHECK();
+        nbr->wcap_hint = (uint32_t)(nbr->nnl_max + nbr->nnl_max / 8 + 8);
+        nbr->wcap_hint_n = n_loc;
+        nbr->built = true;
+        return TAB_OK;
+    }
+
     if (warp_mode) {
         k_nbr_warp<false><<<nblocks((long long)n * 32, 128), 128, 0, st>>>(
             n, g, x, nbr->cell_of.as<int>(), nbr->atoms.as<Atom4>(),
@@ -863,7 +1211,6 @@ extern "C" int tab_nbr_build_dd(tab_nbr *nbr, int32_t n_owned, int32_t n_halo,
     TAB_TRY(tab_scan_exclusive_u32(nbr->slice_w.as<uint32_t>(),
                                    nbr->slice_ptr.as<uint32_t>(), nbr->n_slices,
                                    d_stats + 2, nbr->scan_tmp, st));
-    unsigned long long h_stats[3];
     TAB_CUDA(cudaMemcpyAsync(h_stats, d_stats, sizeof(h_stats), cudaMemcpyDeviceToHost, st));
     TAB_CUDA(cudaStreamSynchronize(st));
     nbr->nij = (long long)h_stats[0];

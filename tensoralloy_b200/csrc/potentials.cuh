@@ -12,24 +12,21 @@
 // 1e-10 eV/atom parity tolerance.  float32: hardware approximations (the
 // 'medium' tolerance is 1e-5 relative).
 // ---------------------------------------------------------------------------
+// MUFU seeds carry >= 20 good bits (relative error e <= 2^-20); ONE third-order
+// step leaves e^3 ~ 1e-18, so a second Newton iteration is not needed.
 __device__ __forceinline__ double tab_rcp(double x) {
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    double e = fma(-x, y, 1.0);
-    y = fma(y, e, y);
-    e = fma(-x, y, 1.0);
-    return fma(y, e, y);
+    const double e = fma(-x, y, 1.0);          // 1/x = y / (1 - e) = y (1 + e + e^2 + ...)
+    return fma(y, fma(e, e, e), y);
 }
 
 // 1/sqrt(x) for normal positive x
 __device__ __forceinline__ double tab_rsqrt(double x) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    const double h = 0.5 * x;
-    double e = fma(-h * y, y, 0.5);
-    y = fma(y, e, y);
-    e = fma(-h * y, y, 0.5);
-    return fma(y, e, y);
+    const double e = fma(-x, y * y, 1.0);      // x^-1/2 = y (1 - e)^-1/2 = y (1 + e/2 + 3e^2/8 + ...)
+    return fma(y, e * fma(0.375, e, 0.5), y);
 }
 
 // exp(t) for t < 700 (t < -700 -> 0): n = rint(t log2 e), f = t - n ln2, degree-12 Taylor

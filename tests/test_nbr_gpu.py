@@ -80,3 +80,64 @@ def test_large_lattice_counts():
     rng = np.random.default_rng(611)
     pos = pos + rng.normal(scale=0.05, size=pos.shape)
     assert_same_list(pos, cell, [1, 1, 1], 6.5)
+
+
+# --- block-per-tile build (large systems) ------------------------------------
+# The tile kernel must produce the SAME rows, in the same order, as the
+# thread-per-atom kernels; TAB_NBR_MODE selects the kernel for A/B runs.
+def _export_mode(mode, pos, cell, pbc, rc, types=None, monkeypatch=None):
+    monkeypatch.setenv('TAB_NBR_MODE', mode)
+    nl, i, j, S = gpu_list(pos, cell, pbc, rc, types)
+    return nl.sizes(), nl.counts().cpu().numpy(), i, j, S
+
+
+def _assert_modes_equal(pos, cell, pbc, rc, types, monkeypatch):
+    a = _export_mode('thread', pos, cell, pbc, rc, types, monkeypatch)
+    b = _export_mode('tile', pos, cell, pbc, rc, types, monkeypatch)
+    assert a[0] == b[0]
+    for u, v in zip(a[1:], b[1:]):
+        np.testing.assert_array_equal(u, v)      # same entries, same order
+
+
+def test_tile_kernel_matches_thread_kernel_fcc(monkeypatch):
+    pos, cell = fcc_positions(3.52, 21, 20, 19)      # odd bin counts: partial tiles
+    rng = np.random.default_rng(611)
+    pos = pos + rng.normal(scale=0.05, size=pos.shape)
+    _assert_modes_equal(pos, cell, [1, 1, 1], 6.5, None, monkeypatch)
+    # and against ASE's list
+    monkeypatch.setenv('TAB_NBR_MODE', 'tile')
+    assert_same_list(pos, cell, [1, 1, 1], 6.5)
+
+
+def test_tile_kernel_species_triclinic_mixed_pbc(monkeypatch):
+    rng = np.random.default_rng(9)
+    cell = np.array([[60.0, 0.0, 0.0], [11.0, 55.0, 0.0], [4.0, -7.0, 48.0]])
+    n = 14000
+    pos = rng.random((n, 3)) @ cell
+    types = rng.integers(0, 3, size=n)
+    for pbc in ([1, 1, 1], [1, 0, 1], [0, 0, 0]):
+        _assert_modes_equal(pos, cell, pbc, 5.0, types, monkeypatch)
+    monkeypatch.setenv('TAB_NBR_MODE', 'tile')
+    assert_same_list(pos[:3000] * 0.5, cell * 0.5, [1, 1, 0], 5.0)
+
+
+def test_tile_kernel_dense_cells_and_thin_box(monkeypatch):
+    # > NBT_CAP candidates per cell (segments are split) and > 256 atoms per tile
+    rng = np.random.default_rng(2)
+    cell = np.diag([16.0, 16.0, 16.0])
+    pos = rng.random((9000, 3)) @ cell             # 2.2 atoms / A^3
+    _assert_modes_equal(pos, cell, [1, 1, 1], 4.0, None, monkeypatch)
+    # a box thinner than the cutoff in y: search range > 1 bin along y
+    cell = np.diag([120.0, 5.0, 40.0])
+    pos = rng.random((3000, 3)) @ cell
+    _assert_modes_equal(pos, cell, [1, 1, 1], 6.0, rng.integers(0, 2, size=3000),
+                        monkeypatch)
+
+
+def test_tile_kernel_boundary_distances(monkeypatch):
+    # perfect lattice with rc exactly on a shell: the exact re-test decides
+    pos, cell = fcc_positions(3.52, 12, 12, 12)
+    rc = 3.52 * np.sqrt(2.0)                        # 4th shell distance
+    _assert_modes_equal(pos, cell, [1, 1, 1], rc, None, monkeypatch)
+    monkeypatch.setenv('TAB_NBR_MODE', 'tile')
+    assert_same_list(pos, cell, [1, 1, 1], rc)
