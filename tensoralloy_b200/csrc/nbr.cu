@@ -507,65 +507,83 @@ k_nbr_warp(int n, Grid g, ExactCtx x, const int *__restrict__ cell_of,
 //      single species these rows ARE the list (slice_ptr[s] = s * wcap); with
 //      several species k_rows_by_species regroups them into compact slices.
 //
-//      Distance test: with p = candidate and m = centre, both relative to the box
-//      centre c,  d^2 - rc^2 = (|p|^2 - 2 p.m) - (rc^2 - |m|^2):  |p|^2 is staged,
-//      the right-hand side is a per-thread constant, so one candidate costs three
-//      DFMA and two DSETP.  Rounding of this form is O(1e-16 |p|^2) -- the host
-//      only selects the kernel when that is below a quarter of the 1e-9 rc^2 band
-//      inside which membership is re-decided with ASE's exact expression: a cell
-//      segment is first scanned speculatively (band candidates counted as hits);
-//      if any of its candidates fell into the band the segment is re-scanned with
-//      the exact test (rare: the band is ~1e-9 wide).
+//      Distance test = float32 PRE-FILTER + exact float64 decision.  A candidate is
+//      staged as one 16-byte record (x, y, z relative to the box centre, rounded to
+//      float32, + the entry bits), so a test is one LDS.128, six FP32 operations and
+//      two FSETP.  The float32 d^2 differs from the true d^2 by less than `band`
+//      (host-computed from the box size); candidates with |d^2 - rc^2| < band are
+//      undecidable in float32: the cell segment they belong to is re-scanned by
+//      nbt_scan_exact, which repeats the float64 test of for_each_neighbor()
+//      (including ASE's exact expression within 1e-9 rc^2).  The band is ~1e-4 A^2
+//      wide, so re-scans touch ~0.1 % of the segments of a random structure.
 #define NBT_THREADS 256
-#define NBT_CAP 1024      // staged candidates per window (36 B each)
+#define NBT_CAP 2048      // staged candidates per window (16 B each)
 #define NBT_CELLS 256     // box cells whose table entries are cached per batch
 
-template <bool EXACT>
-__device__ __forceinline__ bool nbt_scan(int kbeg, int kend, const double2 *cxy,
-                                         const double2 *czp, const uint32_t *cen,
-                                         double m2x, double m2y, double m2z, double thr_hi,
-                                         double thr_lo, int idx, uint32_t wcap,
-                                         uint32_t *__restrict__ base, uint32_t &kk,
-                                         const Grid &g, const ExactCtx &x) {
-    bool near_any = false;
+// Speculative scan of one cell segment: band candidates count as hits; returns
+// true when any candidate fell into the band (the caller then restores kk and
+// repeats the segment with nbt_scan_exact).  The caller guarantees room for the
+// whole segment in the row.  The decision step is written in PTX so that it stays
+// branch-free: 2 FSETP (the second predicated on the first), the self-exclusion,
+// a predicated store and a predicated pointer bump.
+__device__ __forceinline__ bool nbt_scan(int kbeg, int kend, const float4 *cand, float mx,
+                                         float my, float mz, float thr_hi, float thr_lo,
+                                         uint32_t e_self, uint32_t *__restrict__ base,
+                                         uint32_t &kk) {
+    uint32_t near_any = 0;
+    uint32_t *ptr = base + (size_t)kk * 32u;
 #pragma unroll 4
     for (int k = kbeg; k < kend; ++k) {
-        const double2 p = cxy[k], q = czp[k];
-        const uint32_t e = cen[k];
-        const double t = fma(q.x, m2z, fma(p.y, m2y, fma(p.x, m2x, q.y)));
-        // in = t < hi ; near = in && t > lo  (two DSETP, the second predicated on
-        // the first: nvcc alone emits three)
-        unsigned in_u, near_u;
-        asm("{\n\t.reg .pred p, q;\n\t"
-            "setp.lt.f64 p, %2, %3;\n\t"
-            "setp.gt.and.f64 q, %2, %4, p;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "selp.u32 %1, 1, 0, q;\n\t}"
-            : "=r"(in_u), "=r"(near_u)
-            : "d"(t), "d"(thr_hi), "d"(thr_lo));
-        bool in = in_u != 0u;
-        if (EXACT) {
-            if (near_u) in = exact_inside(g, x, idx, (int)(e & TAB_COL_IDX_MASK));
-        } else {
-            near_any |= near_u != 0u;
-        }
-        in = in && (int)(e & TAB_COL_IDX_MASK) != idx;
+        const float4 c = cand[k];
+        const float dx = c.x - mx, dy = c.y - my, dz = c.z - mz;
+        const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p, q;\n\t"
+            "setp.lt.f32 p, %2, %3;\n\t"             // inside (band included)
+            "setp.gt.and.f32 q, %2, %4, p;\n\t"      // ... and in the band
+            "@q mov.u32 %1, 1;\n\t"
+            "setp.ne.and.u32 p, %5, %6, p;\n\t"      // not the centre itself
+            "@p st.global.u32 [%0], %5;\n\t"
+            "@p add.u64 %0, %0, 128;\n\t"
+            "}"
+            : "+l"(ptr), "+r"(near_any)
+            : "f"(d2), "f"(thr_hi), "f"(thr_lo), "r"(__float_as_uint(c.w)), "r"(e_self)
+            : "memory");
+    }
+    kk = (uint32_t)((ptr - base) >> 5);
+    return near_any != 0u;
+}
+
+// float64 re-scan of a segment: exactly the test of for_each_neighbor()
+__device__ __noinline__ void nbt_scan_exact(int kbeg, int kend, const float4 *cand,
+                                            const Atom4 *__restrict__ atoms, int idx,
+                                            uint32_t wcap, uint32_t *__restrict__ base,
+                                            uint32_t &kk, const Grid &g, const ExactCtx &x) {
+    const Atom4 me = atoms[idx];
+    const double tol = 1e-9 * g.rc2;
+    for (int k = kbeg; k < kend; ++k) {
+        const uint32_t e = __float_as_uint(cand[k].w);
+        const int j = (int)(e & TAB_COL_IDX_MASK);
+        if (j == idx) continue;
+        const Atom4 a = atoms[j];
+        const double ddx = a.x - me.x, ddy = a.y - me.y, ddz = a.z - me.z;
+        const double d2 = ddx * ddx + ddy * ddy + ddz * ddz;
+        bool in = d2 < g.rc2;
+        if (fabs(d2 - g.rc2) <= tol) in = exact_inside(g, x, idx, j);
         if (in && kk < wcap) base[(size_t)kk * 32u] = e;
         kk += in ? 1u : 0u;
     }
-    return near_any;
 }
 
-__global__ void __launch_bounds__(NBT_THREADS)
+__global__ void __launch_bounds__(NBT_THREADS, 4)
 k_nbr_tile(int n, Grid g, ExactCtx x, const Atom4 *__restrict__ atoms,
            const uint8_t *__restrict__ types_ext,
            const uint32_t *__restrict__ cell_start,
            const uint32_t *__restrict__ cell_count,
-           const uint4 *__restrict__ ext_tab, uint32_t wcap,
+           const uint4 *__restrict__ ext_tab, uint32_t wcap, float band,
            int *__restrict__ counts, uint32_t *__restrict__ rows) {
-    __shared__ double2 cxy[NBT_CAP];        // x, y   (relative to the box centre)
-    __shared__ double2 czp[NBT_CAP];        // z, |p|^2
-    __shared__ uint32_t cen[NBT_CAP];       // entry = index | species << 28
+    __shared__ float4 cand[NBT_CAP];        // x, y, z relative to the box centre; entry bits
     __shared__ uint4 cell_tab[NBT_CELLS];   // {start_a, count_a, start_b, count_b}
     __shared__ int cell_pc[NBT_CELLS];      // packed box coordinates of the cell
     __shared__ int cell_off[NBT_CELLS + 1]; // candidate offset of the cell in the batch
@@ -605,16 +623,18 @@ k_nbr_tile(int n, Grid g, ExactCtx x, const Atom4 *__restrict__ atoms,
         ctr[2] += sc * g.h[3 * k + 2];
     }
     const int box_cells = bn[0] * bn[1] * bn[2];
-    const double tol = 1e-9 * g.rc2;
     const int sr0 = g.sr[0], sr1 = g.sr[1], sr2 = g.sr[2];
+    const float thr_hi = (float)g.rc2 + band, thr_lo = (float)g.rc2 - band;
 
     for (int chunk = a0; chunk < a1; chunk += NBT_THREADS) {
         const int idx = chunk + tid;
         const bool active = idx < a1;
         int mx = 0, my = 0, mz = 0;       // my cell, relative to the box origin
-        double m2x = 0, m2y = 0, m2z = 0, thr_hi = 0, thr_lo = 0;
+        float fx = 0.f, fy = 0.f, fz = 0.f;
         uint32_t *base = rows;
+        uint32_t e_self = 0;
         if (active) {
+            e_self = (uint32_t)idx | ((uint32_t)types_ext[idx] << TAB_COL_TYPE_SHIFT);
             int l = -1;
 #pragma unroll
             for (int q = 0; q < B * B * B; ++q) l += tile_start[q] <= (uint32_t)idx ? 1 : 0;
@@ -622,13 +642,9 @@ k_nbr_tile(int n, Grid g, ExactCtx x, const Atom4 *__restrict__ atoms,
             my = t3[1] * B + (l / B) % B - b0[1];
             mz = t3[2] * B + l / (B * B) - b0[2];
             const Atom4 me = atoms[idx];
-            const double ux = me.x - ctr[0], uy = me.y - ctr[1], uz = me.z - ctr[2];
-            const double mm = ux * ux + uy * uy + uz * uz;
-            m2x = -2.0 * ux;
-            m2y = -2.0 * uy;
-            m2z = -2.0 * uz;
-            thr_hi = (g.rc2 + tol) - mm;
-            thr_lo = (g.rc2 - tol) - mm;
+            fx = (float)(me.x - ctr[0]);      // same rounding as the staged record
+            fy = (float)(me.y - ctr[1]);
+            fz = (float)(me.z - ctr[2]);
             base = rows + ((size_t)(idx >> 5) * wcap * 32u + (idx & 31));
         }
         uint32_t kk = 0;                  // hits so far = next row slot
@@ -677,10 +693,9 @@ k_nbr_tile(int n, Grid g, ExactCtx x, const Atom4 *__restrict__ atoms,
                         const uint32_t j = o < (int)t.y ? t.x + (uint32_t)o
                                                         : t.z + (uint32_t)(o - (int)t.y);
                         const Atom4 a = atoms[j];
-                        const double px = a.x - ctr[0], py = a.y - ctr[1], pz = a.z - ctr[2];
-                        cxy[u - w0] = make_double2(px, py);
-                        czp[u - w0] = make_double2(pz, px * px + py * py + pz * pz);
-                        cen[u - w0] = j | ((uint32_t)types_ext[j] << TAB_COL_TYPE_SHIFT);
+                        const uint32_t e = j | ((uint32_t)types_ext[j] << TAB_COL_TYPE_SHIFT);
+                        cand[u - w0] = make_float4((float)(a.x - ctr[0]), (float)(a.y - ctr[1]),
+                                                   (float)(a.z - ctr[2]), __uint_as_float(e));
                     }
                 }
                 __syncthreads();
@@ -693,11 +708,12 @@ k_nbr_tile(int n, Grid g, ExactCtx x, const Atom4 *__restrict__ atoms,
                         const int kbeg = max(cell_off[c], w0) - w0;
                         const int kend = min(cell_off[c + 1], w1) - w0;
                         const uint32_t kk0 = kk;
-                        if (nbt_scan<false>(kbeg, kend, cxy, czp, cen, m2x, m2y, m2z, thr_hi,
-                                            thr_lo, idx, wcap, base, kk, g, x)) {
+                        // fast path needs room for the whole segment (rows have slack)
+                        if (kk + (uint32_t)(kend - kbeg) > wcap ||
+                            nbt_scan(kbeg, kend, cand, fx, fy, fz, thr_hi, thr_lo, e_self, base,
+                                     kk)) {
                             kk = kk0;
-                            nbt_scan<true>(kbeg, kend, cxy, czp, cen, m2x, m2y, m2z, thr_hi,
-                                           thr_lo, idx, wcap, base, kk, g, x);
+                            nbt_scan_exact(kbeg, kend, cand, atoms, idx, wcap, base, kk, g, x);
                         }
                     }
                 }
@@ -1105,10 +1121,12 @@ extern "C" int tab_nbr_build_dd(tab_nbr *nbr, int32_t n_owned, int32_t n_halo,
     // cells, single pass (thread per atom with shared-memory candidate staging).
     // (TAB_NBR_MODE=thread|tile|warp overrides, for A/B measurements)
     bool warp_mode = n_loc <= 20000;
-    // tile kernel: box indices fit 8 bits, and the |p|^2 - 2 p.m form of d^2 keeps
-    // its rounding (~8 ulp of R^2, R = half diagonal of a tile's candidate box + one
-    // bin) below a quarter of the exact-recheck band 1e-9 rc^2
+    // tile kernel: box indices fit 8 bits; float32 pre-filter band from the largest
+    // staged coordinate R (half extent of a tile's candidate box + one bin):
+    //   |d2_f32 - d2| <= 2 sqrt(3) rc (2 R + rc) eps + 4 rc^2 eps,  eps = 2^-24
+    // (doubled for safety).  A band wider than 1e-3 rc^2 would re-scan too often.
     bool tile_ok = g.sr[0] <= 100 && g.sr[1] <= 100 && g.sr[2] <= 100 && two[2] == 0;
+    float band = 0.f;
     {
         double R = 0.0;
         for (int k = 0; k < 3; ++k) {
@@ -1116,7 +1134,10 @@ extern "C" int tab_nbr_build_dd(tab_nbr *nbr, int32_t n_owned, int32_t n_halo,
                                     g.h[3 * k + 2] * g.h[3 * k + 2]);
             R += 0.5 * len * (double)(B + 2 * g.sr[k] + 2) / (double)g.nb[k];
         }
-        if (8.0 * 2.3e-16 * R * R > 0.25e-9 * g.rc2) tile_ok = false;
+        const double eps = 5.97e-8;
+        const double bw = 2.0 * (2.0 * 1.7321 * rc * (2.0 * R + rc) * eps + 4.0 * g.rc2 * eps);
+        if (bw > 1e-3 * g.rc2) tile_ok = false;
+        band = (float)bw;
     }
     bool tile_mode = !warp_mode && tile_ok;
     if (const char *env = getenv("TAB_NBR_MODE")) {
@@ -1147,7 +1168,8 @@ extern "C" int tab_nbr_build_dd(tab_nbr *nbr, int32_t n_owned, int32_t n_halo,
             k_nbr_tile<<<n_tiles, NBT_THREADS, 0, st>>>(
                 n, g, x, nbr->atoms.as<Atom4>(), nbr->types_ext.as<uint8_t>(),
                 nbr->cell_start.as<uint32_t>(), nbr->cell_count.as<uint32_t>(),
-                nbr->ext_tab.as<uint4>(), wcap, nbr->counts.as<int>(), rows.as<uint32_t>());
+                nbr->ext_tab.as<uint4>(), wcap, band, nbr->counts.as<int>(),
+                rows.as<uint32_t>());
             TAB_LAUNCH_CHECK();
             k_slice_stats<<<nblocks(nthreads, 128), 128, 0, st>>>(
                 n, nbr->counts.as<int>(), nbr->slice_w.as<uint32_t>(), d_stats);
@@ -1187,7 +1209,7 @@ extern "C" int tab_nbr_build_dd(tab_nbr *nbr, int32_t n_owned, int32_t n_halo,
                 nbr->tcounts.as<int>());
         }
         TAB_LAUNCH_CHECK();
-        nbr->wcap_hint = (uint32_t)(nbr->nnl_max + nbr->nnl_max / 8 + 8);
+        nbr->wcap_hint = (uint32_t)(nbr->nnl_max + nbr->nnl_max / 8 + 24);
         nbr->wcap_hint_n = n_loc;
         nbr->built = true;
         return TAB_OK;
