@@ -30,20 +30,35 @@ struct EamDev {
     const double *pool;    // spline coefficient pool (TAB_FN_SPLINE) or NULL
 };
 
+// single-element zjw04: rho and the B term of phi share one exponential
+struct Zhou1 {
+    double fe, beta, lamda, re, A, alpha, kappa, B;   // re holds 1/r_eq
+    // float64 fast path: folded terms (potentials.cuh, ZTerm)
+    ZTerm t_rho;        // fe exp(-beta (x-1)) / (1 + (x-lamda)^20)
+    ZTerm t_a;          // A  exp(-alpha (x-1)) / (1 + (x-kappa)^20)
+    ZTerm t_b;          // B  exp(-beta (x-1)) / (1 + (x-lamda)^20)
+    double fe_over_B;
+};
+
+static void zterm_fold(ZTerm &t, double a, double b, double c, double re) {
+    t.nb = -b;
+    t.c = b + log(a);
+    t.kappa = c;
+    t.c20 = 20.0 / (re * re);
+    t.k20 = -20.0 * c / re;
+    t.nb_re = -b / re;
+}
+
 struct tab_model {
     int family = 0;        // 0 = EAM
     int kind = 0;
     int n_el = 0;
     bool zhou1 = false;    // single element, all-zjw04: shared-exponential fast path
-    double zp[8];          // fe, beta, lamda, 1/re, A, alpha, kappa, B
+    Zhou1 z1;              // fe, beta, lamda, 1/re, A, alpha, kappa, B + folded terms
+    bool z1_folded = false;   // prefactors positive: the folded float64 terms are usable
     DevBuf tables;         // tab_fn [2*n_el*n_el + n_el (+ 2*n_el*n_el)]
     DevBuf pool;           // spline coefficients
     tab_fn embed0;         // host copy (fast path epilogue parameters)
-};
-
-// single-element zjw04: rho and the B term of phi share one exponential
-struct Zhou1 {
-    double fe, beta, lamda, re, A, alpha, kappa, B;   // re holds 1/r_eq
 };
 
 #ifndef EAM_T
@@ -52,6 +67,10 @@ struct Zhou1 {
 #ifndef EAM_MINB
 #define EAM_MINB 4       // __launch_bounds__ min blocks per SM (register cap)
 #endif
+#ifndef EAM_FORCE_UNROLL
+#define EAM_FORCE_UNROLL 1   // pairs per iteration of the force loop (ILP vs registers)
+#endif
+constexpr int kForceUnroll = EAM_FORCE_UNROLL;
 #define ADP_MAX_EL 3     // ADP keeps n_el x 9 moment accumulators in registers
 
 template <typename Real>
@@ -146,16 +165,23 @@ k_eam_rho(int n, const Atom4 *__restrict__ atoms,
         Real dx, dy, dz, r, rinv, f, df;
         pair_r<Real>(me, a, dx, dy, dz, r, rinv);
         if (FAST) {
-            // g with unit prefactor; rho = fe * sum g
-            zhou_exp<Real>(r, Real(1), (Real)z.beta, (Real)z.lamda, (Real)z.re, f, df);
-            if (CACHE) cache_store(pcache + row0 + (size_t)it.pos() * 32u, (double)f, (double)df);
+            if (sizeof(Real) == 8 && !CACHE) {
+                double f8, d8;      // folded float64 term, fe inside the exponent
+                zterm_eval<false>((double)r, (double)r * z.re, z.t_rho, f8, d8);
+                f = (Real)f8;
+            } else {
+                // g with unit prefactor; rho = fe * sum g
+                zhou_exp<Real>(r, Real(1), (Real)z.beta, (Real)z.lamda, (Real)z.re, f, df);
+                if (CACHE)
+                    cache_store(pcache + row0 + (size_t)it.pos() * 32u, (double)f, (double)df);
+            }
         } else {
             const int tj = (int)(c >> TAB_COL_TYPE_SHIFT);
             eval_pair_fn<Real>(tabs[ti * m.n_el + tj], r, f, df, m.pool);
         }
         rho += f;
     }
-    if (FAST) rho *= (Real)z.fe;
+    if (FAST && !(sizeof(Real) == 8 && !CACHE)) rho *= (Real)z.fe;
     Real F, dF;
     if (FAST) eval_embed_fn<Real>(embed0, rho, F, dF);
     else eval_embed_fn<Real>(tabs[2 * nn + ti], rho, F, dF, m.pool);
@@ -212,12 +238,22 @@ k_eam_force(int n, const Atom4 *__restrict__ atoms,
         uint32_t c;
         double2 pc_nx = make_double2(0.0, 0.0);
         if (CACHE && cnt > 0) pc_nx = cache_load(pcache + row0);
+#pragma unroll kForceUnroll
         while (it.next(a, c)) {
             Real dx, dy, dz, r, rinv;
             pair_r<Real>(me, a, dx, dy, dz, r, rinv);
             const Real fpj = (Real)a.w;
             Real phi, dphi, der;   // der = dE/dr of the undirected pair seen from i
-            if (FAST) {
+            if (FAST && sizeof(Real) == 8 && !CACHE) {
+                // folded float64 terms: A and B inside the exponents
+                const double x = (double)r * z.re;
+                double ga, dga, gb, dgb;
+                zterm_eval<true>((double)r, x, z.t_a, ga, dga);
+                zterm_eval<true>((double)r, x, z.t_b, gb, dgb);
+                phi = (Real)(ga - gb);
+                dphi = (Real)(dga - dgb);
+                der = (Real)fma(((double)fpi + (double)fpj) * z.fe_over_B, dgb, (double)dphi);
+            } else if (FAST) {
                 Real ga, dga, gb, dgb;
                 zhou_exp<Real>(r, Real(1), (Real)z.alpha, (Real)z.kappa, (Real)z.re, ga, dga);
                 if (CACHE) {
@@ -606,14 +642,23 @@ extern "C" int tab_eam_create(tab_model **out, int32_t kind, int32_t n_el,
         rho[0].p[1] == phi[0].p[4] && rho[0].p[2] == phi[0].p[5] &&
         rho[0].p[3] == phi[0].p[6]) {
         m->zhou1 = true;
-        m->zp[0] = rho[0].p[0];   // f_eq
-        m->zp[1] = rho[0].p[1];   // beta
-        m->zp[2] = rho[0].p[2];   // lamda
-        m->zp[3] = 1.0 / rho[0].p[3];   // 1 / r_eq
-        m->zp[4] = phi[0].p[0];   // A
-        m->zp[5] = phi[0].p[1];   // alpha
-        m->zp[6] = phi[0].p[2];   // kappa
-        m->zp[7] = phi[0].p[3];   // B
+        Zhou1 &z = m->z1;
+        const double re = rho[0].p[3];
+        z.fe = rho[0].p[0];       // f_eq
+        z.beta = rho[0].p[1];
+        z.lamda = rho[0].p[2];
+        z.re = 1.0 / re;          // 1 / r_eq
+        z.A = phi[0].p[0];
+        z.alpha = phi[0].p[1];
+        z.kappa = phi[0].p[2];
+        z.B = phi[0].p[3];
+        m->z1_folded = z.fe > 0.0 && z.A > 0.0 && z.B > 0.0 && re > 0.0;
+        if (m->z1_folded) {
+            zterm_fold(z.t_rho, z.fe, z.beta, z.lamda, re);
+            zterm_fold(z.t_a, z.A, z.alpha, z.kappa, re);
+            zterm_fold(z.t_b, z.B, z.beta, z.lamda, re);
+            z.fe_over_B = z.fe / z.B;
+        }
     }
     *out = m;
     return TAB_OK;
@@ -718,7 +763,7 @@ static int eam_prepare(tab_model *m, tab_nbr *nbr, bool fast, EamLaunch &L) {
     L.dev.phi = L.dev.rho + nn;
     L.dev.embed = L.dev.rho + 2 * nn;
     L.dev.pool = m->pool.as<double>();
-    memcpy(&L.z, m->zp, sizeof(L.z));
+    L.z = m->z1;
     L.smem = fast ? 0 : (size_t)(2 * nn + m->n_el) * sizeof(tab_fn);
     return TAB_OK;
 }
@@ -859,10 +904,19 @@ static int adp_pass2(tab_model *m, tab_nbr *nbr, double *d_energy, double *d_eat
     return TAB_OK;
 }
 
+// the float64 fast path folds prefactors into exponents and drops the underflow guard
+static bool zhou1_f64_ok(const tab_model *m, const tab_nbr *nbr) {
+    if (!m->zhou1 || !m->z1_folded) return false;
+    const double xmax = nbr->grid.rc * m->z1.re;
+    const double bmax = m->z1.alpha > m->z1.beta ? m->z1.alpha : m->z1.beta;
+    return bmax * (xmax + 1.0) < 600.0;
+}
+
 #define EAM_DISPATCH(FN, ...)                                                        \
     do {                                                                             \
         if (precision == TAB_PRECISION_HIGH)                                         \
-            return m->zhou1 ? FN<double, true>(__VA_ARGS__) : FN<double, false>(__VA_ARGS__); \
+            return zhou1_f64_ok(m, nbr) ? FN<double, true>(__VA_ARGS__)              \
+                                        : FN<double, false>(__VA_ARGS__);            \
         if (precision == TAB_PRECISION_MEDIUM)                                       \
             return m->zhou1 ? FN<float, true>(__VA_ARGS__) : FN<float, false>(__VA_ARGS__);   \
         tab_set_error("unknown precision %d", precision);                            \

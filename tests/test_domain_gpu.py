@@ -58,3 +58,10 @@ def test_update_without_rebuild():
                             ['Ni'] * len(pos), pos2, cell, [1, 1, 1], 6.5, nl=old)
     assert abs(e.item() - ref['energy']) / len(pos) < 1e-10
     assert np.abs(f.cpu().numpy() - ref['forces']).max() < 1e-8
+
+
+def test_slabs_with_tile_build(monkeypatch):
+    # the same decomposition with the block-per-tile list build (halo atoms are the
+    # second group of every cell)
+    monkeypatch.setenv('TAB_NBR_MODE', 'tile')
+    test_slabs_match_single_domain(2)

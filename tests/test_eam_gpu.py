@@ -223,3 +223,34 @@ def test_elastic_constants_known_answers():
         d = (stress(e) - stress(-e)) / (2 * h) / GPa
         c44 = d[1, 2]
     assert abs(c11 - 246.61) < 0.5 and abs(c12 - 147.15) < 0.5 and abs(c44 - 124.72) < 0.5
+
+
+# --- lists from the block-per-tile build (large systems; forced here on small ones) ---
+def test_tile_lists_feed_the_eam_passes(monkeypatch):
+    atoms = bulk_fcc('Ni', 3.52, (8, 7, 6))           # 1344 atoms, odd bin counts
+    rng = np.random.default_rng(611)
+    pos = atoms.positions + rng.normal(scale=0.05, size=atoms.positions.shape)
+    sym = atoms.get_chemical_symbols()
+    monkeypatch.setenv('TAB_NBR_MODE', 'tile')
+    compare('zjw04', ['Ni'], sym, pos, atoms.cell, [1, 1, 1], 6.5)
+    # non-periodic slab (vacuum along z) and a two-species system (regrouped rows)
+    cell = atoms.cell.copy()
+    cell[2, 2] += 12.0
+    compare('zjw04', ['Ni'], sym, pos, cell, [1, 1, 0], 6.5)
+    sym2 = ['Mo' if x < 0.5 else 'Ni' for x in rng.random(len(pos))]
+    compare('zjw04', ['Mo', 'Ni'], sym2, pos, atoms.cell, [1, 1, 1], 6.5)
+
+
+def test_tile_lists_large_lattice(monkeypatch):
+    # default dispatch at 32 000 atoms (tile build) vs the thread-per-atom build:
+    # same rows in the same order -> identical results
+    from tensoralloy_b200.atoms import fcc_positions
+    pos, cell = fcc_positions(3.52, 20, 20, 20)
+    pos = pos + np.random.default_rng(611).normal(scale=0.05, size=pos.shape)
+    sym = ['Ni'] * len(pos)
+    e1, ea1, f1, v1 = gpu_eam('zjw04', ['Ni'], sym, pos, cell, [1, 1, 1], 6.5)
+    monkeypatch.setenv('TAB_NBR_MODE', 'thread')
+    e0, ea0, f0, v0 = gpu_eam('zjw04', ['Ni'], sym, pos, cell, [1, 1, 1], 6.5)
+    assert e1 == e0
+    np.testing.assert_array_equal(f1, f0)
+    np.testing.assert_array_equal(ea1, ea0)

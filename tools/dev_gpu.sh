@@ -1,4 +1,8 @@
 mkdir -p gpurun_out
-python -m pytest tests/test_nbr_gpu.py tests/test_domain_gpu.py tests/test_eam_gpu.py tests/test_atomic_gpu.py -m gpu -x -q 2>&1 | tail -8
-for mode in tile; do TAB_NBR_MODE=$mode python tools/e2e_breakdown.py 63 3 | tail -1; done
-TAB_NBR_MODE=tile ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_build_tile.csv python tools/e2e_breakdown.py 63 2 > /dev/null 2>&1
+for v in base estrin estrin_t64 estrin_t256 unroll2 estrin_u2 minb5 estrin_minb5; do
+TAB200_LIB=$PWD/build/variants/lib_$v.so python bench.py --steps 20 --warmup 5 --no-cpu-baseline --e2e-steps 2 2>/dev/null | python -c "
+import sys,json
+for l in sys.stdin:
+    if l.startswith('{'):
+        d=json.loads(l); k=d['roofline']['kernel_ms']; print('$v', 'step %.4f'%d['ms_per_step'], 'rho %.4f force %.4f'%(k['rho_pass'],k['force_pass']))
+"; done
