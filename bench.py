@@ -228,8 +228,8 @@ def run_ours(args):
     if rank == 0:
         _build.build_library(force=False)
     torch.cuda.set_device(local_rank)
-    if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
-        os.environ['NCCL_DEBUG'] = 'WARN'     # keep stdout to the one JSON line
+    # keep stdout to the one JSON line: whatever NCCL logs goes to stderr
+    os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
         dist.barrier()
@@ -260,11 +260,29 @@ def run_ours(args):
     for _ in range(args.warmup):
         runner.step()
     barrier()
+    graphed = False
+    if world > 1:
+        # per-kernel event timing and the launch count need eager launches: take them
+        # from a few untimed steps, then capture the step in a CUDA graph
+        _lib.profile_enable(True)
+        _lib.lib().tab_launch_count_reset()
+        for _ in range(3):
+            runner.step()
+        barrier()
+        launches_per_step = int(_lib.lib().tab_launch_count()) // 3
+        kernel_ms, calls = _lib.profile_read()
+        _lib.profile_enable(False)
+        if not args.no_graph:
+            graphed = runner.enable_graph()
+            for _ in range(args.warmup):
+                runner.step()
+            barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    _lib.profile_enable(True)
-    _lib.lib().tab_launch_count_reset()
+    if world == 1:
+        _lib.profile_enable(True)
+        _lib.lib().tab_launch_count_reset()
     ev0 = torch.cuda.Event(enable_timing=True)
     ev1 = torch.cuda.Event(enable_timing=True)
     barrier()
@@ -273,10 +291,13 @@ def run_ours(args):
         runner.step()
     ev1.record()
     barrier()
-    launches = int(_lib.lib().tab_launch_count())
     ms = ev0.elapsed_time(ev1)
-    kernel_ms, calls = _lib.profile_read()
-    _lib.profile_enable(False)
+    if world == 1:
+        launches = int(_lib.lib().tab_launch_count())
+        kernel_ms, calls = _lib.profile_read()
+        _lib.profile_enable(False)
+    else:
+        launches = launches_per_step * args.steps
     t = torch.tensor([ms], dtype=torch.float64, device='cuda')
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -358,11 +379,13 @@ def run_ours(args):
                 "sample": f"oracle (torch-float64 CPU restatement of the reference) "
                           f"on Ni fcc {args.ref_cells}^3 = {n_cpu} atoms, neighbour "
                           f"list + E+F+virial; E+F+virial alone {ev:.3e} atom-evals/s"}
-        print(json.dumps(line))
+        result_line = json.dumps(line)
+    else:
+        result_line = None
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    return 0
+    return result_line
 
 
 class SingleGpu:
@@ -407,6 +430,24 @@ class SingleGpu:
                                 self.h_f, self.h_v)
 
 
+class StdoutGuard:
+    """stdout must carry exactly ONE line (the JSON): libraries that print to
+    file descriptor 1 (NCCL's version banner, ...) are sent to stderr while the
+    benchmark runs; the descriptor is restored for the final print."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self._saved, 1)
+        os.close(self._saved)
+        return False
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -421,12 +462,18 @@ def main():
     ap.add_argument('--scaling', default='strong', choices=['strong', 'weak'])
     ap.add_argument('--e2e-steps', type=int, default=10)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true',
+                    help='N > 1: launch the step eagerly instead of as one CUDA graph')
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == 'reference':
         return run_reference(args)
-    return run_ours(args)
+    with StdoutGuard():
+        line = run_ours(args)
+    if line is not None:
+        print(line, flush=True)
+    return 0
 
 
 if __name__ == '__main__':

@@ -89,6 +89,18 @@ int tab_nbr_build_dd(tab_nbr *nbr, int32_t n_owned, int32_t n_halo,
 int tab_pack_rows(const double *d_src, const int64_t *d_idx, int32_t m, int32_t ncol,
                   const double *h_shift, double *d_dst, void *stream);
 
+/* Building blocks of a small all-reduce over NVLink peer memory (the 10-double
+ * [E, virial] sum of the spatial decomposition; the reference has no such step):
+ *   tab_peer_put   stores d_src[0..n) into slot `slot` (n doubles wide) of EACH of the
+ *                  n_peers buffers whose device addresses are listed in d_peer_ptrs
+ *                  (device array; the buffers are peer-mapped, e.g. torch symmetric
+ *                  memory) -- one kernel, the stores travel over NVLink;
+ *   tab_sum_slots  d_out[q] = sum_s d_slots[s * n + q]  (after a cross-rank barrier). */
+int tab_peer_put(const double *d_src, int32_t n, const uint64_t *d_peer_ptrs,
+                 int32_t n_peers, int32_t slot, void *stream);
+int tab_sum_slots(const double *d_slots, int32_t n_slots, int32_t n, double *d_out,
+                  void *stream);
+
 /* Keep the lists, refresh the positions (and optionally the cell): the MD step
  * between two rebuilds.  h_cell may be NULL (unchanged). */
 int tab_nbr_update(tab_nbr *nbr, const double *d_pos, const double *h_cell,

@@ -85,7 +85,7 @@ _lib = None
 EXPORTS = [
     'tab_version', 'tab_last_error',
     'tab_nbr_create', 'tab_nbr_free', 'tab_nbr_build', 'tab_nbr_build_dd',
-    'tab_nbr_update', 'tab_pack_rows',
+    'tab_nbr_update', 'tab_pack_rows', 'tab_peer_put', 'tab_sum_slots',
     'tab_nbr_sizes', 'tab_nbr_counts', 'tab_nbr_export',
     'tab_eam_create', 'tab_eam_set_splines', 'tab_model_free', 'tab_eam_eval', 'tab_eam_pass1',
     'tab_eam_pass2', 'tab_eam_hessian', 'tab_eam_compute_host',
@@ -120,6 +120,8 @@ def lib():
                                    C.POINTER(dbl), C.POINTER(i32), dbl, vp]
     L.tab_nbr_update.argtypes = [vp, vp, C.POINTER(dbl), vp]
     L.tab_pack_rows.argtypes = [vp, vp, i32, i32, C.POINTER(dbl), vp, vp]
+    L.tab_peer_put.argtypes = [vp, i32, vp, i32, i32, vp]
+    L.tab_sum_slots.argtypes = [vp, i32, i32, vp, vp]
     L.tab_nbr_sizes.argtypes = [vp, C.POINTER(i64), C.POINTER(i32),
                                 C.POINTER(i32)]
     L.tab_nbr_counts.argtypes = [vp, vp, vp]
@@ -190,6 +192,17 @@ def pack_rows(src, idx, dst, shift=None):
     sh = (C.c_double * 3)(*[float(x) for x in shift]) if shift is not None else None
     check(lib().tab_pack_rows(_ptr(src), _ptr(idx), m, ncol, sh, _ptr(dst), _stream()),
           'tab_pack_rows')
+
+
+def peer_put(src, peer_ptrs, slot):
+    """src[0..n) -> slot `slot` of every peer buffer (device int64 array of addresses)."""
+    check(lib().tab_peer_put(_ptr(src), int(src.numel()), _ptr(peer_ptrs),
+                             int(peer_ptrs.numel()), int(slot), _stream()), 'tab_peer_put')
+
+
+def sum_slots(slots, n_slots, out):
+    check(lib().tab_sum_slots(_ptr(slots), int(n_slots), int(out.numel()), _ptr(out),
+                              _stream()), 'tab_sum_slots')
 
 
 class NeighborList:

@@ -1395,3 +1395,47 @@ extern "C" int tab_pack_rows(const double *d_src, const int64_t *d_idx, int32_t 
     TAB_LAUNCH_CHECK();
     return TAB_OK;
 }
+
+// ---------------------------------------------------------------------------
+// small all-reduce over peer memory (see include/tab200.h)
+// ---------------------------------------------------------------------------
+__global__ void k_peer_put(int n, int n_peers, int slot, const double *__restrict__ src,
+                           const unsigned long long *__restrict__ peer_ptrs) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * n_peers) return;
+    const int p = t / n, q = t - p * n;
+    double *dst = reinterpret_cast<double *>(peer_ptrs[p]);
+    dst[(size_t)slot * n + q] = src[q];
+}
+
+__global__ void k_sum_slots(int n_slots, int n, const double *__restrict__ slots,
+                            double *__restrict__ out) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    double v = 0.0;
+    for (int s = 0; s < n_slots; ++s) v += slots[(size_t)s * n + q];   // fixed order
+    out[q] = v;
+}
+
+extern "C" int tab_peer_put(const double *d_src, int32_t n, const uint64_t *d_peer_ptrs,
+                            int32_t n_peers, int32_t slot, void *stream) {
+    if (!d_src || !d_peer_ptrs || n <= 0 || n_peers <= 0 || slot < 0) {
+        tab_set_error("tab_peer_put: bad argument");
+        return TAB_EINVAL;
+    }
+    k_peer_put<<<nblocks((long long)n * n_peers, 128), 128, 0, (cudaStream_t)stream>>>(
+        n, n_peers, slot, d_src, (const unsigned long long *)d_peer_ptrs);
+    TAB_LAUNCH_CHECK();
+    return TAB_OK;
+}
+
+extern "C" int tab_sum_slots(const double *d_slots, int32_t n_slots, int32_t n,
+                             double *d_out, void *stream) {
+    if (!d_slots || !d_out || n <= 0 || n_slots <= 0) {
+        tab_set_error("tab_sum_slots: bad argument");
+        return TAB_EINVAL;
+    }
+    k_sum_slots<<<nblocks(n, 128), 128, 0, (cudaStream_t)stream>>>(n_slots, n, d_slots, d_out);
+    TAB_LAUNCH_CHECK();
+    return TAB_OK;
+}

@@ -19,9 +19,15 @@ multi-GPU path of SURVEY.md 8(e):
   With FULL neighbour lists an owned atom never needs a ghost's force, only its
   position and F'(rho): no reverse communication.
 
-`DistComm` drives the exchange over torch.distributed (NCCL on GPUs, gloo in the
-CPU tests); `run_loopback` runs every rank inside one process to test the whole
-pipeline on a single GPU.
+`PeerComm` is the NVLink path: every rank's local position / F' arrays live in
+torch symmetric memory, the pack kernels of a rank store STRAIGHT into its ring
+neighbours' receive regions over NVLink (pack + send are one kernel, no staging
+buffer, no NCCL call) and a device-side barrier orders the steps; the 10-double
+reduction is a one-shot all-reduce over the same peer mappings.  `DistComm` is
+the fallback over torch.distributed point-to-point (NCCL on GPUs, gloo in the CPU
+tests).  The resident-list step is captured once in a CUDA graph (`enable_graph`),
+so a step is ONE launch per rank.  `run_loopback` runs every rank inside one
+process to test the whole pipeline on a single GPU.
 """
 import numpy as np
 
@@ -96,6 +102,84 @@ class DistComm:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
 
 
+class PeerComm:
+    """Halo exchange by direct stores into the neighbours' memory (NVLink / NVSwitch
+    peer mappings from torch symmetric memory).
+
+    One flat float64 symmetric buffer per rank, same capacity everywhere:
+        [ positions of owned | from-left | from-right atoms  (3 doubles each) ]
+        [ F' of from-left | from-right atoms ]
+    and a 16-double symmetric buffer for [E, virial(9)].  `dst_*` are views of the
+    NEIGHBOURS' buffers: the region of the left neighbour that holds what it
+    receives from its right (= me), and vice versa.
+    """
+
+    def __init__(self, layout, n_owned, n_send_left, n_send_right, device):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.torch, self.dist, self.layout = torch, dist, layout
+        world, rank = layout.world, layout.rank
+        # what each rank owns / receives: from-left of r = send-right of r-1, ...
+        mine = torch.tensor([n_owned, n_send_left, n_send_right], dtype=torch.int64,
+                            device=device)
+        table = [torch.zeros(3, dtype=torch.int64, device=device) for _ in range(world)]
+        dist.all_gather(table, mine)
+        table = [t.tolist() for t in table]
+        owned = [t[0] for t in table]
+        from_l = [table[(r - 1) % world][2] for r in range(world)]
+        from_r = [table[(r + 1) % world][1] for r in range(world)]
+        rows_cap = max(owned[r] + from_l[r] + from_r[r] for r in range(world))
+        halo_cap = max(from_l[r] + from_r[r] for r in range(world))
+        self.n_from_l, self.n_from_r = from_l[rank], from_r[rank]
+        self.off_fp = 3 * rows_cap
+        total = self.off_fp + max(halo_cap, 1)
+        group = dist.group.WORLD
+        self.group_name = group.group_name
+        self.buf = symm.empty(total, dtype=torch.float64, device=device)
+        self.buf.zero_()
+        self.hdl = symm.rendezvous(self.buf, group)
+        # all-reduce of [E, virial]: slot r of every rank's `red_all` is written by rank r
+        self.red_all = symm.empty(16 * world, dtype=torch.float64, device=device)
+        self.red_all.zero_()
+        self.red_hdl = symm.rendezvous(self.red_all, group)
+        self.red_ptrs = torch.tensor([int(p) for p in self.red_hdl.buffer_ptrs],
+                                     dtype=torch.int64, device=device)
+        self.red = torch.zeros(16, dtype=torch.float64, device=device)      # my partial sums
+        self.red_out = torch.zeros(16, dtype=torch.float64, device=device)
+        lay = layout
+        L, R = lay.left, lay.right
+        f64 = torch.float64
+        # my views
+        rows = owned[rank] + self.n_from_l + self.n_from_r
+        self.pos_loc = self.buf[:3 * rows].view(rows, 3)
+        n_halo = self.n_from_l + self.n_from_r
+        self.fp_halo = self.buf[self.off_fp:self.off_fp + max(n_halo, 1)]
+        # neighbours' receive regions
+        self.dst_pos_l = self.hdl.get_buffer(L, (n_send_left, 3), f64,
+                                             3 * (owned[L] + from_l[L]))
+        self.dst_pos_r = self.hdl.get_buffer(R, (n_send_right, 3), f64, 3 * owned[R])
+        self.dst_fp_l = self.hdl.get_buffer(L, (n_send_left,), f64, self.off_fp + from_l[L])
+        self.dst_fp_r = self.hdl.get_buffer(R, (n_send_right,), f64, self.off_fp)
+        torch.cuda.synchronize()
+        dist.barrier()
+
+    def fence(self, channel):
+        """All ranks have issued (and completed) the stores before this point."""
+        self.hdl.barrier(channel=channel)
+
+    def allreduce_sum(self):
+        """self.red summed over the ranks -> self.red_out: one kernel stores my 16
+        doubles into my slot of EVERY rank's buffer over NVLink, a device barrier,
+        one kernel sums the slots in rank order (deterministic, identical on all
+        ranks).  (torch's one-shot symmetric all-reduce has no float64 kernel.)"""
+        from tensoralloy_b200 import _lib
+        _lib.peer_put(self.red, self.red_ptrs, self.layout.rank)
+        self.red_hdl.barrier(channel=2)
+        _lib.sum_slots(self.red_all, self.layout.world, self.red_out)
+        return self.red_out
+
+
 class SlabRank:
     """Device state and kernels of ONE rank (comm-agnostic)."""
 
@@ -132,32 +216,45 @@ class SlabRank:
         self.h_f = torch.zeros((self.n_owned, 3), dtype=torch.float64).pin_memory()
 
     # -- halo bookkeeping ----------------------------------------------------
-    def set_halo_counts(self, n_from_left, n_from_right):
+    def set_halo_counts(self, n_from_left, n_from_right, pos_loc=None, fp_halo=None,
+                        out=None):
+        """`pos_loc` / `fp_halo` / `out`: externally owned storage (the symmetric
+        buffers of PeerComm) instead of private allocations."""
         t = self.torch
         self.n_from_l, self.n_from_r = n_from_left, n_from_right
         n_halo = n_from_left + n_from_right
-        self.d_pos_loc = t.empty((self.n_owned + n_halo, 3), dtype=t.float64,
-                                 device=self.device)
+        self.d_pos_loc = pos_loc if pos_loc is not None else \
+            t.empty((self.n_owned + n_halo, 3), dtype=t.float64, device=self.device)
         # the owned positions LIVE in the head of the local array (no copy per step)
         self.d_pos_owned = self.d_pos_loc[:self.n_owned]
         self.d_pos_owned.copy_(self._pos0)
-        self.d_fp_halo = t.zeros(max(n_halo, 1), dtype=t.float64, device=self.device)
+        self.d_fp_halo = fp_halo if fp_halo is not None else \
+            t.zeros(max(n_halo, 1), dtype=t.float64, device=self.device)
+        if out is not None:
+            self.d_out = out
         o = self.n_owned
         self.recv_pos_l = self.d_pos_loc[o:o + n_from_left]
         self.recv_pos_r = self.d_pos_loc[o + n_from_left:]
         self.recv_fp_l = self.d_fp_halo[:n_from_left]
         self.recv_fp_r = self.d_fp_halo[n_from_left:n_halo]
 
-    def pack_positions(self):
+    def pack_positions(self, dst_l=None, dst_r=None):
+        """Gather (+ periodic shift) the boundary atoms' positions into `dst_*`
+        (default: the private send buffers; PeerComm passes the neighbours'
+        receive regions, so the pack kernel IS the send)."""
+        dst_l = self.send_pos_l if dst_l is None else dst_l
+        dst_r = self.send_pos_r if dst_r is None else dst_r
         p = self.d_pos_owned
-        self._lib.pack_rows(p, self.idx_l, self.send_pos_l, self.shift_l)
-        self._lib.pack_rows(p, self.idx_r, self.send_pos_r, self.shift_r)
-        return self.send_pos_l, self.send_pos_r
+        self._lib.pack_rows(p, self.idx_l, dst_l, self.shift_l)
+        self._lib.pack_rows(p, self.idx_r, dst_r, self.shift_r)
+        return dst_l, dst_r
 
-    def pack_fprime(self):
-        self._lib.pack_rows(self.d_fp, self.idx_l, self.send_fp_l)
-        self._lib.pack_rows(self.d_fp, self.idx_r, self.send_fp_r)
-        return self.send_fp_l, self.send_fp_r
+    def pack_fprime(self, dst_l=None, dst_r=None):
+        dst_l = self.send_fp_l if dst_l is None else dst_l
+        dst_r = self.send_fp_r if dst_r is None else dst_r
+        self._lib.pack_rows(self.d_fp, self.idx_l, dst_l)
+        self._lib.pack_rows(self.d_fp, self.idx_r, dst_r)
+        return dst_l, dst_r
 
     # -- kernels -------------------------------------------------------------
     def build(self):
@@ -198,9 +295,30 @@ class SlabDomain:
         self.rank_state = SlabRank(model, self.layout, owned, ly, lz, precision, device)
         self.comm = DistComm(self.layout)
         self.scaling = scaling
+        self.graph = None
         r = self.rank_state
-        n_l, n_r = self.comm.exchange_counts(len(r.idx_l), len(r.idx_r), device)
-        r.set_halo_counts(n_l, n_r)
+        self.peer = None
+        import os
+        if device == 'cuda' and os.environ.get('TAB_DD_PEER', '1') != '0':
+            try:
+                self.peer = PeerComm(self.layout, r.n_owned, len(r.idx_l), len(r.idx_r),
+                                     device)
+            except Exception as exc:      # no peer mappings: NCCL point-to-point
+                self.peer = None
+                self.peer_error = f"{type(exc).__name__}: {exc}"
+        # every rank must take the same path
+        import torch
+        flag = torch.tensor([1 if self.peer is not None else 0], device=device)
+        self.comm.dist.all_reduce(flag, op=self.comm.dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            self.peer = None
+        if self.peer is not None:
+            pc = self.peer
+            r.set_halo_counts(pc.n_from_l, pc.n_from_r, pos_loc=pc.pos_loc,
+                              fp_halo=pc.fp_halo, out=pc.red)
+        else:
+            n_l, n_r = self.comm.exchange_counts(len(r.idx_l), len(r.idx_r), device)
+            r.set_halo_counts(n_l, n_r)
         self._exchange_positions()
         r.build()
         self.n_local = r.n_owned
@@ -210,29 +328,83 @@ class SlabDomain:
 
     def describe(self):
         lay = self.layout
+        how = ("pack kernels store into the ring neighbours' symmetric memory over "
+               "NVLink + device barrier (positions, F'), one-shot peer all-reduce of 10 "
+               "doubles") if self.peer is not None else \
+              "2 NCCL ring exchanges (positions, F') + one 10-double all-reduce per step"
         return (f"1-D slabs along x, {lay.world} ranks x {self.n_local} owned atoms "
-                f"(this rank), halo = rc = {lay.rc} A, 2 NCCL ring exchanges "
-                f"(positions, F') + one 10-double all-reduce per step; "
+                f"(this rank), halo = rc = {lay.rc} A, {how}; "
+                f"{'CUDA-graph step; ' if self.graph is not None else ''}"
                 f"{self.scaling} scaling")
 
     def _exchange_positions(self):
         r = self.rank_state
+        if self.peer is not None:
+            r.pack_positions(self.peer.dst_pos_l, self.peer.dst_pos_r)
+            self.peer.fence(0)
+            return
         s_l, s_r = r.pack_positions()
         self.comm.exchange(s_l, s_r, r.recv_pos_l, r.recv_pos_r)
 
     def _exchange_fprime(self):
         r = self.rank_state
+        if self.peer is not None:
+            r.pack_fprime(self.peer.dst_fp_l, self.peer.dst_fp_r)
+            self.peer.fence(1)
+            return
         s_l, s_r = r.pack_fprime()
         self.comm.exchange(s_l, s_r, r.recv_fp_l, r.recv_fp_r)
 
-    def step(self):
+    def _reduce(self):
+        r = self.rank_state
+        if self.peer is not None:
+            self.peer.allreduce_sum()
+        else:
+            self.comm.allreduce_sum(r.d_out[:10])
+
+    def _totals(self):
+        return self.peer.red_out if self.peer is not None else self.rank_state.d_out
+
+    def _step_body(self):
         r = self.rank_state
         self._exchange_positions()
         r.update()
         r.pass1()
         self._exchange_fprime()
         r.pass2()
-        self.comm.allreduce_sum(r.d_out[:10])
+        self._reduce()
+
+    def enable_graph(self, warmup=3):
+        """Capture the resident-list step (kernels, peer stores, barriers, reduction)
+        in one CUDA graph.  Returns True when the capture worked."""
+        import torch
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(warmup):
+                    self._step_body()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._step_body()
+            self.graph = g
+        except Exception as exc:
+            self.graph = None
+            self.graph_error = f"{type(exc).__name__}: {exc}"
+        # all ranks or none (a mixed ring would deadlock in the barriers)
+        flag = torch.tensor([1 if self.graph is not None else 0], device='cuda')
+        self.comm.dist.all_reduce(flag, op=self.comm.dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            self.graph = None
+        return self.graph is not None
+
+    def step(self):
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._step_body()
 
     def step_e2e(self):
         """Host positions in, host forces / energy / virial out, lists rebuilt."""
@@ -243,14 +415,14 @@ class SlabDomain:
         r.pass1()
         self._exchange_fprime()
         r.pass2()
-        self.comm.allreduce_sum(r.d_out[:10])
+        self._reduce()
         r.h_f.copy_(r.d_f, non_blocking=True)
-        r.h_out.copy_(r.d_out, non_blocking=True)
+        r.h_out.copy_(self._totals(), non_blocking=True)
         r.torch.cuda.synchronize()
 
     def results(self):
         r = self.rank_state
-        out = r.d_out.cpu().numpy()
+        out = self._totals().cpu().numpy()
         return out[0], r.d_f.cpu().numpy(), out[1:10].reshape(3, 3)
 
 

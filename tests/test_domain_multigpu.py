@@ -1,0 +1,26 @@
+"""Slab decomposition across REAL GPUs (needs >= 2 devices; skipped otherwise):
+NVLink peer-memory halo exchange, CUDA-graph step and the e2e call, each rank
+checked against a single-GPU evaluation (tools/dd_check.py under torchrun)."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2,
+                    reason="needs two GPUs")
+@pytest.mark.parametrize("peer", ["1", "0"])
+def test_two_rank_slabs(peer):
+    env = dict(os.environ, TAB_DD_PEER=peer)
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1',
+           '--nproc-per-node', '2', '--master-addr', '127.0.0.1', '--master-port',
+           '29541' if peer == '1' else '29542', os.path.join(ROOT, 'tools', 'dd_check.py'),
+           '8']
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert 'FAIL' not in res.stdout
