@@ -25,6 +25,8 @@
 //                  sum_p g_p and sum_p g_p (x) D_p are accumulated on the fly.
 //   k_sf_collect   thread per atom: F_i = sum_p g_p - sum_p g_rev(p)  (reverse-pair
 //                  index built once per list, nbr.cu:k_build_reverse).
+#include <stdlib.h>
+
 #include "potentials.cuh"
 
 #define SF_MAX_R 32      // radial parameter sets
@@ -53,10 +55,15 @@ struct MlpDev {
     long long xlo_off, xhi_off;
 };
 
+#include "mlp_tc.cuh"
+
 struct tab_atomic {
     SfDev sf;
     int n_el;
     MlpDev mlp[TAB_MAX_ELEMENTS];
+    bool tc_ok = false;      // every element's network fits the tensor-core kernel
+    DevBuf tc_nets;          // MlpTcDev [n_el]
+    DevBuf tc_status;        // int: set by k_mlp_tc when an MMA barrier timed out
     DevBuf blob;        // double: weights, biases, xlo, xhi of every element + MlpDev table
     size_t mlp_table_off = 0;   // offset (in doubles) of the MlpDev table inside blob
     DevBuf G, dEdG, eat, gvec, fown;
@@ -892,13 +899,53 @@ extern "C" int tab_atomic_create(tab_atomic **out, const tab_sf_desc *d,
         return rc;
     }
     m->mlp_table_off = mlp_off;
+    // tensor-core variant (mlp_tc.cuh): two hidden layers, D <= 64, H1 <= 64, H2 <= 32,
+    // no ResNet link
+    {
+        MlpTcDev nets[TAB_MAX_ELEMENTS];
+        bool ok = true;
+        auto pad16 = [](int v) { return (v + 15) & ~15; };
+        for (int e = 0; e < m->n_el && ok; ++e) {
+            const MlpDev &q = m->mlp[e];
+            if (q.n_layers != 3 || q.resnet || q.in[0] > 64 || q.out[0] > 64 || q.out[1] > 32 ||
+                q.out[2] != 1) {
+                ok = false;
+                break;
+            }
+            MlpTcDev &t = nets[e];
+            t.dim = q.in[0];
+            t.dp = pad16(q.in[0]);
+            t.h1 = q.out[0];
+            t.h1p = pad16(q.out[0]);
+            t.h2 = q.out[1];
+            t.h2p = pad16(q.out[1]);
+            t.act = q.act;
+            t.has_out_bias = q.has_out_bias;
+            t.has_minmax = q.has_minmax;
+            t.w1 = q.w_off[0];
+            t.b1 = q.b_off[0];
+            t.w2 = q.w_off[1];
+            t.b2 = q.b_off[1];
+            t.w3 = q.w_off[2];
+            t.b3 = q.b_off[2];
+            t.xlo = q.xlo_off;
+            t.xhi = q.xhi_off;
+        }
+        if (ok && m->tc_nets.ensure(sizeof(MlpTcDev) * m->n_el) == TAB_OK &&
+            m->tc_status.ensure(sizeof(int)) == TAB_OK &&
+            cudaMemcpy(m->tc_nets.p, nets, sizeof(MlpTcDev) * m->n_el,
+                       cudaMemcpyHostToDevice) == cudaSuccess &&
+            cudaMemset(m->tc_status.p, 0, sizeof(int)) == cudaSuccess)
+            m->tc_ok = true;
+    }
     *out = m;
     return TAB_OK;
 }
 
 extern "C" int tab_atomic_free(tab_atomic *m) {
     if (!m) return TAB_OK;
-    DevBuf *bufs[] = {&m->blob, &m->G, &m->dEdG, &m->eat, &m->gvec, &m->fown};
+    DevBuf *bufs[] = {&m->blob, &m->G, &m->dEdG, &m->eat, &m->gvec, &m->fown, &m->tc_nets,
+                      &m->tc_status};
     for (DevBuf *b : bufs) b->release();
     delete m;
     return TAB_OK;
@@ -969,9 +1016,32 @@ static int atomic_run(tab_atomic *m, tab_nbr *nbr, double *d_energy, double *d_e
     }
     const double *blob = m->blob.as<double>();
     const MlpDev *mlps = reinterpret_cast<const MlpDev *>(blob + m->mlp_table_off);
-    k_mlp<Real><<<nblk_m, MLP_WARPS * 32, smem_mlp, st>>>(
-        n, sf.dim, nbr->types_ext.as<uint8_t>(), mlps, blob, m->G.as<double>(),
-        m->eat.as<double>(), m->dEdG.as<double>());
+    // 'medium' precision, enough atoms to fill tiles: the MLP runs on the tensor cores
+    // (TAB_MLP_TC=0 forces the warp-per-atom kernel, TAB_MLP_TC=1 forces the tensor
+    // cores for any size, for tests)
+    bool use_tc = sizeof(Real) == 4 && m->tc_ok && n >= 4096;
+    if (const char *env = getenv("TAB_MLP_TC")) {
+        if (env[0] == '0') use_tc = false;
+        if (env[0] == '1') use_tc = sizeof(Real) == 4 && m->tc_ok;
+    }
+    if (use_tc) {
+        static bool tc_attr = false;
+        if (!tc_attr) {
+            TAB_CUDA(cudaFuncSetAttribute(k_mlp_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          TC_SMEM_BYTES));
+            tc_attr = true;
+        }
+        const int n_tiles = (n + TC_ROWS - 1) / TC_ROWS;
+        dim3 grid((unsigned)(n_tiles < 148 ? n_tiles : 148), (unsigned)m->n_el);
+        k_mlp_tc<<<grid, TC_ROWS, TC_SMEM_BYTES, st>>>(
+            n, sf.dim, nbr->types_ext.as<uint8_t>(), m->tc_nets.as<MlpTcDev>(), blob,
+            m->G.as<double>(), m->eat.as<double>(), m->dEdG.as<double>(),
+            m->tc_status.as<int>());
+    } else {
+        k_mlp<Real><<<nblk_m, MLP_WARPS * 32, smem_mlp, st>>>(
+            n, sf.dim, nbr->types_ext.as<uint8_t>(), mlps, blob, m->G.as<double>(),
+            m->eat.as<double>(), m->dEdG.as<double>());
+    }
     TAB_LAUNCH_CHECK();
     const size_t plane = (size_t)nbr->ell_rows * 32;
     double *partial = nbr->partial.as<double>();

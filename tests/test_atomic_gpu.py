@@ -121,3 +121,62 @@ def test_two_elements_radial_and_angular():
              nn_kwargs=dict(activation='squareplus'))
     # mixed periodicity + atoms outside the cell, three species
     _compare(PD3O2, ['O', 'Pd'], 6.5)
+
+
+# --- the MLP on the tensor cores (tcgen05, 'medium' precision; mlp_tc.cuh) -------------
+def _medium(nn, atoms, tc, monkeypatch):
+    monkeypatch.setenv('TAB_MLP_TC', tc)
+    with precision_scope('medium'):
+        calc = TensorAlloyCalculator(nn)
+        calc.calculate(atoms, properties=['energy', 'forces', 'stress'])
+        return (calc.results['energy'], calc.get_forces(atoms).copy(),
+                calc.get_stress(atoms).copy(), calc.get_atomic(atoms).copy())
+
+
+@pytest.mark.parametrize("case", ["be_default", "moni_minmax_bias", "be_tanh_small"])
+def test_mlp_on_tensor_cores(case, monkeypatch):
+    d = np.load(os.path.join(GOLD, 'Be_liquid_4000K.npz'))
+    if case == "moni_minmax_bias":
+        base = bulk_fcc('Ni', 3.6, (3, 3, 3))
+        rng = np.random.default_rng(5)
+        sym = ['Mo' if x < 0.4 else 'Ni' for x in rng.random(len(base))]
+        atoms = Atoms(sym, base.positions + rng.normal(scale=0.1, size=base.positions.shape),
+                      base.cell, True)
+        elements, rc, kw = ['Mo', 'Ni'], 4.6, dict(
+            atomic_static_energy={'Mo': -1.5, 'Ni': -0.7}, minmax_scale=True)
+    else:
+        atoms = Atoms(list(d['symbols']), d['positions'][2], d['cells'][2], True)
+        elements, rc = ['Be'], 5.0
+        kw = dict(minmax_scale=False) if case == "be_default" else \
+            dict(minmax_scale=False, hidden_sizes=[48, 16], activation='tanh')
+    # oracle parity in both precisions with the tensor-core kernel forced on
+    monkeypatch.setenv('TAB_MLP_TC', '1')
+    ref = _compare(atoms, elements, rc, acut=4.0 if len(elements) > 1 else None,
+                   nn_kwargs=kw)
+    # and directly against the warp-per-atom float32 kernel on the same model
+    with precision_scope('high'):
+        clf = UniversalTransformer(elements, rcut=rc, acut=4.0 if len(elements) > 1 else None,
+                                   angular=True)
+        nn = AtomicNN(elements, SymmetryFunction(elements),
+                      export_properties=('energy', 'forces', 'stress'), **kw)
+        nn.attach_transformer(clf)
+        nn.initialize_variables(seed=611)
+        for el in nn.elements:
+            key = f"Atomic/{el}/Output/kernel"
+            nn.set_variable(key, nn.get_variable(key) * 0.02)
+        if kw.get('minmax_scale', True):
+            rng = np.random.default_rng(612)
+            for el in nn.elements:
+                lo = rng.random(nn._dim()) * 0.1
+                nn.set_variable(f"Atomic/{el}/xlo", lo.reshape(1, 1, -1))
+                nn.set_variable(f"Atomic/{el}/xhi",
+                                (lo + 1.0 + 5 * rng.random(nn._dim())).reshape(1, 1, -1))
+    e1, f1, s1, a1 = _medium(nn, atoms, '1', monkeypatch)
+    e0, f0, s0, a0 = _medium(nn, atoms, '0', monkeypatch)
+    n = len(atoms)
+    print(case, 'dE/N', abs(e1 - e0) / n, 'dEatom', np.abs(a1 - a0).max(),
+          'dF', np.abs(f1 - f0).max(), 'Fmax', np.abs(f0).max())
+    assert np.abs(a1 - a0).max() <= 2e-5 * max(np.abs(a0).max(), 1.0)
+    assert np.abs(f1 - f0).max() <= 2e-5 * max(np.abs(f0).max(), 1e-2)
+    assert np.abs(s1 - s0).max() <= 2e-5 * max(np.abs(s0).max(), 1e-4)
+    assert np.abs(f0).max() > 1e-3                  # not vacuous
