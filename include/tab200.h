@@ -246,6 +246,11 @@ typedef struct tab_atomic tab_atomic;
  * the (beta, gamma, zeta) triples (beta outer, gamma, zeta inner) -- sf.py:47-51.
  * Feature layout of a centre of element c: G2 blocks of the terms
  * [cc, c-x1, ...] then G4 blocks of c+(sorted pair j<=k) -- utils.py:262-286. */
+#define TAB_RADIAL_SF      0
+#define TAB_RADIAL_MORSE   1
+#define TAB_RADIAL_DENSITY 2
+#define TAB_RADIAL_PEXP    3
+
 typedef struct tab_sf_desc {
     int32_t n_el;
     int32_t cutoff;           /* TAB_CUTOFF_* */
@@ -254,6 +259,19 @@ typedef struct tab_sf_desc {
     double  rc, acut;
     const double *eta, *omega;             /* [n_r] */
     const double *beta, *gamma, *zeta;     /* [n_a] */
+    /* GenericRadialAtomicPotential, legacy mode (nn/atomic/grap.py:121-466): the
+     * radial family and its multipole moments.  Parameters 1, 2 of set tau live in
+     * eta[tau], omega[tau], parameter 3 in p3[tau]:
+     *   TAB_RADIAL_SF      exp(-eta (r-omega)^2 / rc^2)          (= Behler G2)
+     *   TAB_RADIAL_MORSE   D [e^{-2g(r-r0)} - 2 e^{-g(r-r0)}]    (D, gamma, r0)
+     *   TAB_RADIAL_DENSITY A exp(-beta (r/re - 1))               (A, beta, re)
+     *   TAB_RADIAL_PEXP    exp(-(r/rl)^pl)                       (rl, pl)
+     * moments[0..n_moments): subset of {0, 1, 2}; feature layout per term:
+     * [tau][moment].  n_moments == 0 means {0} (plain symmetry functions). */
+    int32_t radial_kind;
+    int32_t n_moments;
+    int32_t moments[3];
+    const double *p3;                      /* [n_r] or NULL */
 } tab_sf_desc;
 
 /* One element's MLP: sizes[0] = descriptor length, sizes[n_layers] = 1;

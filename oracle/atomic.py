@@ -147,6 +147,64 @@ def descriptors(elements, types, R, cell, i, j, S, rc, acut=None, angular=True,
     return G
 
 
+def grap_descriptors(elements, types, R, cell, i, j, S, rc, algorithm, grid, moments,
+                     cutoff='cosine'):
+    """Legacy-mode GenericRadialAtomicPotential descriptors (nn/atomic/grap.py:384-466,
+    algorithms :121-234, generic.py:15-30,87-100,120-168).  grid: list of parameter
+    tuples in the algorithm's key order (sf: eta, omega; morse: D, gamma, r0; density:
+    A, beta, re; pexp: rl, pl).  Layout per radial term: [tau][moment]."""
+    elements = sorted(elements)
+    n, nel = R.shape[0], len(elements)
+    dtype = R.dtype
+    fcut = _cut(cutoff)
+    moments = sorted(set(moments))
+    n_r, n_m = len(grid), len(moments)
+    ti, tj = torch.as_tensor(i), torch.as_tensor(j)
+    Dij = R[tj] - R[ti] + torch.as_tensor(S).to(dtype) @ cell
+    rij = torch.sqrt((Dij * Dij).sum(-1) + EPS[dtype])
+    types_t = torch.as_tensor(types)
+    ci, cj = types_t[ti], types_t[tj]
+    tidx = torch.where(ci == cj, torch.zeros_like(ci), cj - (cj > ci).long() + 1)
+    fc = fcut(rij, rc)
+    u = Dij / rij[:, None]                       # div_no_nan: r > 0 for real pairs
+    cols = []
+    for tau, prm in enumerate(grid):
+        if algorithm == 'sf':
+            v = torch.exp(-prm[0] * (rij - prm[1]) ** 2 / rc ** 2)
+        elif algorithm == 'morse':
+            d, g, r0 = prm
+            v = d * (torch.exp(-2.0 * g * (rij - r0)) - 2.0 * torch.exp(-g * (rij - r0)))
+        elif algorithm == 'density':
+            a, b, re = prm
+            v = a * torch.exp(-b * (rij / re - 1.0))
+        elif algorithm == 'pexp':
+            rl, pl = prm
+            v = torch.exp(-(rij / rl) ** pl)
+        else:
+            raise ValueError(algorithm)
+        w = v * fc
+        for m in moments:
+            # accumulate per (centre, term): index = centre * nel + term
+            key = ti * nel + tidx
+            if m == 0:
+                acc = torch.zeros(n * nel, dtype=dtype).index_add(0, key, w)
+                val = acc
+            elif m == 1:
+                acc = torch.zeros(n * nel, 3, dtype=dtype).index_add(0, key, w[:, None] * u)
+                val = (acc * acc).sum(-1)
+            else:
+                uu = u[:, :, None] * u[:, None, :]
+                acc = torch.zeros(n * nel, 3, 3, dtype=dtype).index_add(
+                    0, key, w[:, None, None] * uu)
+                val = (acc * acc).sum((-1, -2))
+            cols.append((tau, moments.index(m), val.reshape(n, nel)))
+    G = torch.zeros(n, nel * n_r * n_m, dtype=dtype)
+    for tau, mi, val in cols:
+        for term in range(nel):
+            G[:, (term * n_r + tau) * n_m + mi] = val[:, term]
+    return G
+
+
 def activation(name):
     name = name.lower()
     if name == 'softplus':
@@ -187,7 +245,7 @@ def mlp(x, weights, biases, act, use_resnet_dt=False, out_bias=None):
 
 def atomic_evaluate(elements, symbols, positions, cell, pbc, rc, params, sf=None,
                     acut=None, angular=True, dtype=torch.float64, hessian=False,
-                    minmax=None):
+                    minmax=None, grap=None):
     """Full oracle call for AtomicNN + SymmetryFunction.
     params[el] = dict(weights=[...], biases=[...], out_bias=float or None,
                       activation=str, use_resnet_dt=bool)
@@ -205,8 +263,13 @@ def atomic_evaluate(elements, symbols, positions, cell, pbc, rc, params, sf=None
     types = np.array([elements.index(s) for s in symbols])
 
     def energy_fn(R, h):
-        G = descriptors(elements, types, R, h, nl[0], nl[1], nl[2], rc, acut_eff,
-                        angular, ang_list=ang, **sf)
+        if grap is not None:
+            G = grap_descriptors(elements, types, R, h, nl[0], nl[1], nl[2], rc,
+                                 grap['algorithm'], grap['grid'], grap['moments'],
+                                 grap.get('cutoff', 'cosine'))
+        else:
+            G = descriptors(elements, types, R, h, nl[0], nl[1], nl[2], rc, acut_eff,
+                            angular, ang_list=ang, **sf)
         e_atom = torch.zeros(R.shape[0], dtype=R.dtype)
         for a, el in enumerate(elements):
             sel = torch.nonzero(torch.as_tensor(types == a)).reshape(-1)

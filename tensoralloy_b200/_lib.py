@@ -64,7 +64,12 @@ class TabSfDesc(C.Structure):
                 ('n_r', C.c_int32), ('n_a', C.c_int32),
                 ('rc', C.c_double), ('acut', C.c_double),
                 ('eta', _DP), ('omega', _DP), ('beta', _DP), ('gamma', _DP),
-                ('zeta', _DP)]
+                ('zeta', _DP),
+                ('radial_kind', C.c_int32), ('n_moments', C.c_int32),
+                ('moments', C.c_int32 * 3), ('p3', _DP)]
+
+
+RADIAL_KINDS = {'sf': 0, 'morse': 1, 'density': 2, 'pexp': 3}
 
 
 class TabMlpDesc(C.Structure):
@@ -374,7 +379,10 @@ class AtomicModel:
               output_bias=bool, xlo=np or None, xhi=np or None)
     """
 
-    def __init__(self, n_el, rc, acut, radial, angular, cutoff, mlps):
+    def __init__(self, n_el, rc, acut, radial, angular, cutoff, mlps,
+                 radial_kind='sf', moments=(0,)):
+        """radial: list of parameter tuples (2 or 3 values per set, see
+        include/tab200.h: tab_sf_desc); moments: GRAP multipole moments."""
         self._keep = []
 
         def darr(vals):
@@ -392,6 +400,12 @@ class AtomicModel:
         sf.acut = float(acut if acut is not None else rc)
         sf.eta = darr([r[0] for r in radial])
         sf.omega = darr([r[1] for r in radial])
+        sf.p3 = darr([r[2] if len(r) > 2 else 0.0 for r in radial])
+        sf.radial_kind = RADIAL_KINDS[radial_kind]
+        moments = sorted(set(int(x) for x in moments))
+        sf.n_moments = len(moments)
+        for k, mm in enumerate(moments):
+            sf.moments[k] = mm
         ang = angular or []
         sf.beta = darr([a[0] for a in ang] or [0.0])
         sf.gamma = darr([a[1] for a in ang] or [0.0])

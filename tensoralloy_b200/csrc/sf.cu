@@ -39,9 +39,13 @@
 
 struct SfDev {
     int n_el, n_r, n_a, angular, cutoff;   // cutoff: 0 cosine, 1 polynomial(gamma=5)
-    int d_r, dim;                          // d_r = n_el*n_r ; dim = full descriptor length
+    int d_r, dim;                          // d_r = n_el*n_r*n_mom ; dim = full descriptor length
+    // radial family (GRAP, nn/atomic/grap.py): 0 sf (= Behler G2), 1 morse, 2 density,
+    // 3 pexp; moments = subset of {0, 1, 2} in ascending order (legacy-mode layout:
+    // per term, per tau, per moment)
+    int rad_kind, n_mom, mom[3], has_m1, has_m2;
     double rc, acut;
-    double eta[SF_MAX_R], omega[SF_MAX_R];
+    double eta[SF_MAX_R], omega[SF_MAX_R], p3[SF_MAX_R];   // parameters 1, 2, 3 per set
     double beta[SF_MAX_A], gamma[SF_MAX_A], zeta[SF_MAX_A];
     double outer[SF_MAX_A];                // 2^(1 - zeta)
 };
@@ -67,6 +71,7 @@ struct tab_atomic {
     DevBuf blob;        // double: weights, biases, xlo, xhi of every element + MlpDev table
     size_t mlp_table_off = 0;   // offset (in doubles) of the MlpDev table inside blob
     DevBuf G, dEdG, eat, gvec, fown;
+    DevBuf mom;         // GRAP moment sums [n, n_el, n_r, GRAP_MOM_W] (forward -> backward)
 };
 
 // ---------------------------------------------------------------------------
@@ -107,6 +112,51 @@ __device__ __forceinline__ Real powz(Real base, Real z, Real &dpow) {
     dpow = (base != Real(0)) ? z * p / base : Real(0);
     return p;
 }
+
+// radial functions of the GRAP family, value and d/dr BEFORE the cutoff factor
+// (grap.py:121-234; generic.py:15-30,87-100,120-168):
+//   sf      exp(-eta (r - omega)^2 / rc^2)            (eta, omega)   = Behler G2
+//   morse   D [e^{-2 g (r - r0)} - 2 e^{-g (r - r0)}]  (D, gamma, r0)
+//   density A exp(-beta (r / re - 1))                  (A, beta, re)
+//   pexp    exp(-(r / rl)^pl)                          (rl, pl)
+template <typename Real>
+__device__ __forceinline__ void rad_fn(const SfDev &sf, int tau, Real r, Real rc2i, Real &v,
+                                       Real &dv) {
+    const Real a = (Real)sf.eta[tau], b = (Real)sf.omega[tau];
+    switch (sf.rad_kind) {
+    case 0: {
+        const Real d = r - b;
+        v = Math<Real>::exp_(-a * d * d * rc2i);
+        dv = Real(-2) * a * d * rc2i * v;
+        break;
+    }
+    case 1: {
+        const Real e1 = Math<Real>::exp_(-b * (r - (Real)sf.p3[tau]));
+        v = a * (e1 * e1 - Real(2) * e1);
+        dv = Real(-2) * a * b * (e1 * e1 - e1);
+        break;
+    }
+    case 2: {
+        const Real re = (Real)sf.p3[tau];
+        v = a * Math<Real>::exp_(-b * (r / re - Real(1)));
+        dv = -b / re * v;
+        break;
+    }
+    default: {
+        const Real x = r / a;
+        Real xp1;                                    // x^(pl-1)
+        if (b == Real(1)) xp1 = Real(1);
+        else if (b == Real(2)) xp1 = x;
+        else if (b == Real(3)) xp1 = x * x;
+        else xp1 = Math<Real>::pow_(x, b - Real(1));
+        v = Math<Real>::exp_(-xp1 * x);
+        dv = -b * xp1 / a * v;
+    }
+    }
+}
+
+// moment sums of one (centre, term, tau): S0, Mx My Mz, Qxx Qyy Qzz Qyz Qxz Qxy
+#define GRAP_MOM_W 10
 
 // shared-memory row layout per warp: 8 doubles per neighbour
 //   0..2 D, 3 r, 4 fc(r; acut), 5 dfc(r; acut)/dr, 6 type (as double), 7 unused
@@ -181,7 +231,7 @@ k_sf_forward(int n, SfDev sf, int n_types, int row_cap,
              const Atom4 *__restrict__ atoms, const uint8_t *__restrict__ types_ext,
              const int *__restrict__ counts, const int *__restrict__ tcounts,
              const uint32_t *__restrict__ slice_ptr, const uint32_t *__restrict__ col,
-             double *__restrict__ G) {
+             double *__restrict__ G, double *__restrict__ mom) {
     extern __shared__ __align__(16) double smem[];
     __shared__ double red[SF_WARPS];
     const int lane = threadIdx.x;           // thread index inside the atom's block
@@ -199,21 +249,56 @@ k_sf_forward(int n, SfDev sf, int n_types, int row_cap,
     for (int t = 0; t < sf.n_el; ++t)
         seg[t + 1] = seg[t] + (t < n_types ? tcounts[(size_t)idx * n_types + t] : 0);
     (void)cnt;
-    // ---- G2
+    // ---- radial part: G2, or the GRAP family with multipole moments (grap.py:384-466)
+    //      m = 0: sum_j w ;  m = 1: sum_a (sum_j w d_a / r)^2 ;
+    //      m = 2: sum_ab (sum_j w d_a d_b / r^2)^2 ,   w = f(r) fc(r)
     for (int t = 0; t < sf.n_el; ++t) {
         const int term = radial_term(ti, t);
         for (int tau = 0; tau < sf.n_r; ++tau) {
-            const Real eta = (Real)sf.eta[tau], om = (Real)sf.omega[tau];
-            Real acc = Real(0);
+            Real acc[GRAP_MOM_W];
+#pragma unroll
+            for (int q = 0; q < GRAP_MOM_W; ++q) acc[q] = Real(0);
             for (int k = seg[t] + lane; k < seg[t + 1]; k += SF_TPA) {
-                const Real r = (Real)row[k * ROW_W + 3];
-                Real f, df;
+                const double *e = row + k * ROW_W;
+                const Real r = (Real)e[3];
+                Real f, df, v, dv;
                 cutoff_fn<Real>(sf.cutoff, r, rc, f, df);
-                const Real d = r - om;
-                acc += Math<Real>::exp_(-eta * d * d * rc2i) * f;
+                rad_fn<Real>(sf, tau, r, rc2i, v, dv);
+                const Real w = v * f;
+                acc[0] += w;
+                if (sf.has_m1 || sf.has_m2) {
+                    const Real ri = r != Real(0) ? Real(1) / r : Real(0);   // div_no_nan
+                    const Real ux = (Real)e[0] * ri, uy = (Real)e[1] * ri, uz = (Real)e[2] * ri;
+                    acc[1] += w * ux;
+                    acc[2] += w * uy;
+                    acc[3] += w * uz;
+                    acc[4] += w * ux * ux;
+                    acc[5] += w * uy * uy;
+                    acc[6] += w * uz * uz;
+                    acc[7] += w * uy * uz;
+                    acc[8] += w * ux * uz;
+                    acc[9] += w * ux * uy;
+                }
             }
-            const double tot = block_sum((double)acc, red);
-            if (lane == 0) g[term * sf.n_r + tau] = tot;
+            double tot[GRAP_MOM_W];
+            const int nsum = (sf.has_m1 || sf.has_m2) ? GRAP_MOM_W : 1;
+            for (int q = 0; q < nsum; ++q) tot[q] = block_sum((double)acc[q], red);
+            if (lane == 0) {
+                double *gg = g + (size_t)(term * sf.n_r + tau) * sf.n_mom;
+                for (int mi = 0; mi < sf.n_mom; ++mi) {
+                    const int mm = sf.mom[mi];
+                    if (mm == 0) gg[mi] = tot[0];
+                    else if (mm == 1) gg[mi] = tot[1] * tot[1] + tot[2] * tot[2] + tot[3] * tot[3];
+                    else
+                        gg[mi] = tot[4] * tot[4] + tot[5] * tot[5] + tot[6] * tot[6] +
+                                 2.0 * (tot[7] * tot[7] + tot[8] * tot[8] + tot[9] * tot[9]);
+                }
+                if (mom && nsum > 1) {
+                    double *mo = mom + ((size_t)idx * sf.n_el * sf.n_r + term * sf.n_r + tau) *
+                                           GRAP_MOM_W;
+                    for (int q = 0; q < GRAP_MOM_W; ++q) mo[q] = tot[q];
+                }
+            }
         }
     }
     if (!sf.angular) return;
@@ -429,7 +514,8 @@ k_sf_backward(int n, SfDev sf, int n_types, int row_cap,
               const int *__restrict__ counts, const int *__restrict__ tcounts,
               const uint32_t *__restrict__ slice_ptr, const uint32_t *__restrict__ col,
               const double *__restrict__ dEdG, double *__restrict__ gvec,
-              size_t plane, double *__restrict__ fown, double *__restrict__ partial) {
+              size_t plane, double *__restrict__ fown, double *__restrict__ partial,
+              const double *__restrict__ mom) {
     extern __shared__ __align__(16) double smem[];
     __shared__ double red[SF_WARPS];
     const int lane = threadIdx.x;
@@ -438,6 +524,7 @@ k_sf_backward(int n, SfDev sf, int n_types, int row_cap,
     {
         double *row = smem;
         const int cnt = stage_row<Real>(sf, idx, lane, SF_TPA, atoms, counts, slice_ptr, col, row);
+        const double *mo_atom = mom ? mom + (size_t)idx * sf.n_el * sf.n_r * GRAP_MOM_W : nullptr;
         const int ti = (int)types_ext[idx];
         const double *c = dEdG + (size_t)idx * sf.dim;
         const Real rc = (Real)sf.rc, rc2i = Real(1) / (rc * rc);
@@ -515,17 +602,51 @@ k_sf_backward(int n, SfDev sf, int n_types, int row_cap,
                 wz += __shfl_xor_sync(0xffffffffu, wz, d);
             }
             if (!valid || sub != 0) continue;
-            // ---- G2 part
+            // ---- radial part (G2 / GRAP moments)
             Real s_r = Real(0);                       // dE/dr_a
             {
                 Real f, df;
                 cutoff_fn<Real>(sf.cutoff, ra, rc, f, df);
                 const int term = radial_term(ti, ta);
+                const Real ri = ra != Real(0) ? Real(1) / ra : Real(0);
+                const Real ux = ax * ri, uy = ay * ri, uz = az * ri;
                 for (int tau = 0; tau < sf.n_r; ++tau) {
-                    const Real eta = (Real)sf.eta[tau], d = ra - (Real)sf.omega[tau];
-                    const Real e = Math<Real>::exp_(-eta * d * d * rc2i);
-                    s_r += (Real)c[term * sf.n_r + tau] *
-                           (e * df - Real(2) * eta * d * rc2i * e * f);
+                    Real v, dv;
+                    rad_fn<Real>(sf, tau, ra, rc2i, v, dv);
+                    const Real w = v * f, dw = dv * f + v * df;
+                    const double *cc = c + (size_t)(term * sf.n_r + tau) * sf.n_mom;
+                    const double *mo = mo_atom ? mo_atom + (size_t)(term * sf.n_r + tau) *
+                                                               GRAP_MOM_W : nullptr;
+                    for (int mi = 0; mi < sf.n_mom; ++mi) {
+                        const int mm = sf.mom[mi];
+                        const Real ck = (Real)cc[mi];
+                        if (mm == 0) {
+                            s_r += ck * dw;
+                        } else if (mm == 1) {
+                            // G = |M|^2, M = sum w u:  dG/dD = 2 [ (dw - w/r)(M.u) u + (w/r) M ]
+                            const Real Mx = (Real)mo[1], My = (Real)mo[2], Mz = (Real)mo[3];
+                            const Real mu = Mx * ux + My * uy + Mz * uz;
+                            const Real wr = w * ri;
+                            s_r += Real(2) * ck * (dw - wr) * mu;
+                            wx += Real(2) * ck * wr * Mx;
+                            wy += Real(2) * ck * wr * My;
+                            wz += Real(2) * ck * wr * Mz;
+                        } else {
+                            // G = sum_ab Q_ab^2, Q = sum w u (x) u:
+                            //   dG/dD = 2 [ (dw - 2 w/r)(u.Q.u) u + 2 (w/r) Q.u ]
+                            const Real Qxx = (Real)mo[4], Qyy = (Real)mo[5], Qzz = (Real)mo[6],
+                                       Qyz = (Real)mo[7], Qxz = (Real)mo[8], Qxy = (Real)mo[9];
+                            const Real qx = Qxx * ux + Qxy * uy + Qxz * uz;
+                            const Real qy = Qxy * ux + Qyy * uy + Qyz * uz;
+                            const Real qz = Qxz * ux + Qyz * uy + Qzz * uz;
+                            const Real uqu = qx * ux + qy * uy + qz * uz;
+                            const Real wr = w * ri;
+                            s_r += Real(2) * ck * (dw - Real(2) * wr) * uqu;
+                            wx += Real(4) * ck * wr * qx;
+                            wy += Real(4) * ck * wr * qy;
+                            wz += Real(4) * ck * wr * qz;
+                        }
+                    }
                 }
             }
             const Real q = (s_r + sa) / ra;
@@ -820,6 +941,24 @@ extern "C" int tab_atomic_create(tab_atomic **out, const tab_sf_desc *d,
     for (int k = 0; k < d->n_r; ++k) {
         sf.eta[k] = d->eta[k];
         sf.omega[k] = d->omega[k];
+        sf.p3[k] = d->p3 ? d->p3[k] : 0.0;
+    }
+    sf.rad_kind = d->radial_kind;
+    sf.n_mom = d->n_moments > 0 ? d->n_moments : 1;
+    if (sf.rad_kind < 0 || sf.rad_kind > 3 || sf.n_mom > 3) {
+        tab_set_error("tab_atomic_create: unknown radial family / moments");
+        delete m;
+        return TAB_EINVAL;
+    }
+    for (int k = 0; k < sf.n_mom; ++k) {
+        sf.mom[k] = d->n_moments > 0 ? d->moments[k] : 0;
+        if (sf.mom[k] < 0 || sf.mom[k] > 2) {
+            tab_set_error("tab_atomic_create: moment %d is not supported (0, 1, 2)", sf.mom[k]);
+            delete m;
+            return TAB_EUNSUPPORTED;
+        }
+        if (sf.mom[k] == 1) sf.has_m1 = 1;
+        if (sf.mom[k] == 2) sf.has_m2 = 1;
     }
     for (int k = 0; k < sf.n_a; ++k) {
         sf.beta[k] = d->beta[k];
@@ -827,7 +966,7 @@ extern "C" int tab_atomic_create(tab_atomic **out, const tab_sf_desc *d,
         sf.zeta[k] = d->zeta[k];
         sf.outer[k] = pow(2.0, 1.0 - d->zeta[k]);
     }
-    sf.d_r = sf.n_el * sf.n_r;
+    sf.d_r = sf.n_el * sf.n_r * sf.n_mom;
     sf.dim = sf.d_r + (sf.angular ? sf.n_el * (sf.n_el + 1) / 2 * sf.n_a : 0);
     // pack the MLP blobs
     size_t total = 0;
@@ -945,7 +1084,7 @@ extern "C" int tab_atomic_create(tab_atomic **out, const tab_sf_desc *d,
 extern "C" int tab_atomic_free(tab_atomic *m) {
     if (!m) return TAB_OK;
     DevBuf *bufs[] = {&m->blob, &m->G, &m->dEdG, &m->eat, &m->gvec, &m->fown, &m->tc_nets,
-                      &m->tc_status};
+                      &m->tc_status, &m->mom};
     for (DevBuf *b : bufs) b->release();
     delete m;
     return TAB_OK;
@@ -1002,10 +1141,14 @@ static int atomic_run(tab_atomic *m, tab_nbr *nbr, double *d_energy, double *d_e
     TAB_TRY(m->fown.ensure(sizeof(double) * 3 * (size_t)n));
     TAB_TRY(nbr->partial.ensure(sizeof(double) * (8 * (size_t)nblk + nblk_c + 8)));
     const Atom4 *atoms = nbr->atoms.as<Atom4>();
+    const bool grap_moments = sf.has_m1 || sf.has_m2;
+    if (grap_moments)
+        TAB_TRY(m->mom.ensure(sizeof(double) * (size_t)n * sf.n_el * sf.n_r * GRAP_MOM_W));
     k_sf_forward<Real><<<nblk, SF_WARPS * 32, smem_row, st>>>(
         n, sf, nbr->n_types, row_cap, atoms, nbr->types_ext.as<uint8_t>(),
         nbr->counts.as<int>(), nbr->tcounts.as<int>(), nbr->slice_ptr.as<uint32_t>(),
-        nbr->col.as<uint32_t>(), m->G.as<double>());
+        nbr->col.as<uint32_t>(), m->G.as<double>(),
+        grap_moments ? m->mom.as<double>() : nullptr);
     TAB_LAUNCH_CHECK();
     if (d_desc) {
         const size_t tot = (size_t)n * sf.dim;
@@ -1054,7 +1197,7 @@ static int atomic_run(tab_atomic *m, tab_nbr *nbr, double *d_energy, double *d_e
             n, sf, nbr->n_types, row_cap, atoms, nbr->types_ext.as<uint8_t>(),
             nbr->counts.as<int>(), nbr->tcounts.as<int>(), nbr->slice_ptr.as<uint32_t>(),
             nbr->col.as<uint32_t>(), m->dEdG.as<double>(), m->gvec.as<double>(), plane,
-            m->fown.as<double>(), partial);
+            m->fown.as<double>(), partial, grap_moments ? m->mom.as<double>() : nullptr);
         TAB_LAUNCH_CHECK();
     }
     k_sf_collect<<<nblk_c, 128, 0, st>>>(
@@ -1105,6 +1248,11 @@ static int atomic_common_checks(tab_atomic *m, tab_nbr *nbr, const char *who) {
         tab_set_error("%s: null handle", who);
         return TAB_EINVAL;
     }
+    if (m->sf.rad_kind != 0 || m->sf.n_mom != 1 || m->sf.mom[0] != 0) {
+        tab_set_error("%s: the training operators cover the symmetry-function descriptor "
+                      "only (GRAP families / moments: inference)", who);
+        return TAB_EUNSUPPORTED;
+    }
     if (!nbr->built) {
         tab_set_error("%s before tab_nbr_build", who);
         return TAB_ESTATE;
@@ -1143,7 +1291,7 @@ static int atomic_forces_from(tab_atomic *m, tab_nbr *nbr, const double *d_dedg,
         n, sf, nbr->n_types, row_cap, nbr->atoms.as<Atom4>(), nbr->types_ext.as<uint8_t>(),
         nbr->counts.as<int>(), nbr->tcounts.as<int>(), nbr->slice_ptr.as<uint32_t>(),
         nbr->col.as<uint32_t>(), m->dEdG.as<double>(), m->gvec.as<double>(), plane,
-        m->fown.as<double>(), partial);
+        m->fown.as<double>(), partial, nullptr);
     TAB_LAUNCH_CHECK();
     k_sf_collect<<<nblk_c, 128, 0, st>>>(
         n, nbr->n_loc, nbr->counts.as<int>(), nbr->slice_ptr.as<uint32_t>(),

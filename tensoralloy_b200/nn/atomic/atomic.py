@@ -39,10 +39,13 @@ class AtomicNN(BasicNN):
         self._fixed_atomic_static_energy = fixed_atomic_static_energy
         if isinstance(descriptor, dict):
             d = dict(descriptor)
-            d.pop('class', None)
-            d.pop('@class', None)
+            cls = d.pop('@class', d.pop('class', 'SymmetryFunction'))
             d.pop('@module', None)
-            descriptor = SymmetryFunction(**d)
+            if cls == 'GenericRadialAtomicPotential':
+                from tensoralloy_b200.nn.atomic.grap import GenericRadialAtomicPotential
+                descriptor = GenericRadialAtomicPotential(**d)
+            else:
+                descriptor = SymmetryFunction(**d)
         if descriptor is None:
             descriptor = SymmetryFunction(self._elements)
         self._descriptor = descriptor
@@ -138,7 +141,8 @@ class AtomicNN(BasicNN):
         self._model = _lib.AtomicModel(
             len(self._elements), clf.rcut, clf.acut,
             sf.radial_sets(), sf.angular_sets() if clf.angular else None,
-            sf.cutoff_function, [self.mlp_params(el) for el in self._elements])
+            sf.cutoff_function, [self.mlp_params(el) for el in self._elements],
+            radial_kind=sf.radial_kind(), moments=sf.moments())
         return self._model
 
     def required_cutoff(self):

@@ -1,0 +1,110 @@
+"""
+GenericRadialAtomicPotential (GRAP) descriptor, legacy mode -- mirror of the
+reference's tensoralloy/nn/atomic/grap.py (constructor :236-269, `as_dict`
+:306-322, algorithms :121-234, legacy descriptor functions :384-466).
+
+For every radial k-body term `c-x` of a centre of element c, every parameter set
+tau of the chosen algorithm f_tau(r) and every requested multipole moment:
+
+    m = 0   sum_j f(r_ij) fc(r_ij)
+    m = 1   sum_a  ( sum_j f fc d_a / r )^2              a in x, y, z
+    m = 2   sum_ab ( sum_j f fc d_a d_b / r^2 )^2        all 9 (a, b)
+
+laid out per term as [tau][moment] (grap.py:419-457), terms in
+`kbody_terms_for_element[c]` order.  The arithmetic runs on the GPU
+(csrc/sf.cu: rad_fn, k_sf_forward, k_sf_backward); the new ("T_dm / M_dnac")
+mode of the reference produces the same numbers for moments <= 2
+(nn/atomic/tests/test_grap.py:152-200) and its `nn` algorithm / moment 3 are
+not built.
+"""
+import numpy as np
+
+ALGORITHMS = {            # name -> required keys, in the order the kernel expects
+    'sf': ('eta', 'omega'),
+    'morse': ('D', 'gamma', 'r0'),
+    'density': ('A', 'beta', 're'),
+    'pexp': ('rl', 'pl'),
+}
+
+
+def _parameter_grid(params, keys, method):
+    """grap.py:45-72: 'cross' = sklearn ParameterGrid (sorted keys, last key
+    fastest), 'pair' = zip."""
+    if method == 'pair':
+        sizes = {len(params[k]) for k in keys}
+        if len(sizes) > 1:
+            raise ValueError("Hyperparameters must have the same length for gen:pair")
+        return [{k: float(params[k][i]) for k in keys} for i in range(sizes.pop())]
+    grid = [{}]
+    for k in sorted(keys):
+        grid = [dict(g, **{k: float(v)}) for g in grid for v in params[k]]
+    return grid
+
+
+class GenericRadialAtomicPotential:
+    def __init__(self, elements, algorithm='sf', parameters=None,
+                 param_space_method='pair', moment_tensors=0,
+                 cutoff_function='cosine', symmetric=False, legacy_mode=True,
+                 h_abck_modifier=None):
+        if algorithm not in ALGORITHMS:
+            raise ValueError(f"GRAP: algorithm '{algorithm}' is not implemented")
+        if param_space_method not in ('cross', 'pair'):
+            raise ValueError("param_space_method must be 'cross' or 'pair'")
+        if isinstance(moment_tensors, int):
+            moment_tensors = [moment_tensors]
+        moment_tensors = sorted(set(int(m) for m in moment_tensors))
+        if any(m not in (0, 1, 2) for m in moment_tensors):
+            raise ValueError("GRAP: moments 0, 1, 2 are supported")
+        keys = ALGORITHMS[algorithm]
+        if parameters is None:
+            parameters = {'eta': [0.05, 4.0, 20.0, 80.0], 'omega': [0.0] * 4} \
+                if algorithm == 'sf' else None
+        for k in keys:
+            if parameters is None or k not in parameters or len(parameters[k]) < 1:
+                raise ValueError(f"GRAP/{algorithm}: parameter '{k}' is required")
+        self._elements = sorted(list(elements))
+        self._algorithm = algorithm
+        self._parameters = {k: [float(x) for x in parameters[k]] for k in keys}
+        self._param_space_method = param_space_method
+        self._grid = _parameter_grid(self._parameters, keys, param_space_method)
+        self._moment_tensors = moment_tensors
+        self._cutoff_function = cutoff_function
+        self._symmetric = symmetric
+        self._legacy_mode = legacy_mode
+
+    name = property(lambda self: "GRAP")
+    elements = property(lambda self: self._elements)
+    cutoff_function = property(lambda self: self._cutoff_function)
+    algorithm = property(lambda self: self._algorithm)
+    moment_tensors = property(lambda self: self._moment_tensors)
+    max_moment = property(lambda self: max(self._moment_tensors))
+    grid = property(lambda self: self._grid)
+
+    def as_dict(self):
+        return {"@class": self.__class__.__name__,
+                "@module": "tensoralloy.nn.atomic.grap",
+                "elements": self._elements, "algorithm": self._algorithm,
+                "parameters": self._parameters,
+                "param_space_method": self._param_space_method,
+                "moment_tensors": self._moment_tensors,
+                "cutoff_function": self._cutoff_function,
+                "symmetric": self._symmetric, "legacy_mode": self._legacy_mode}
+
+    # -- what the device model consumes ---------------------------------------
+    def radial_kind(self):
+        return self._algorithm
+
+    def radial_sets(self):
+        keys = ALGORITHMS[self._algorithm]
+        return [tuple(row[k] for k in keys) for row in self._grid]
+
+    def angular_sets(self):
+        return None
+
+    def moments(self):
+        return tuple(self._moment_tensors)
+
+    def dimension(self, angular=False):
+        if angular:
+            raise ValueError("GRAP is a radial descriptor: use angular=False")
+        return len(self._elements) * len(self._grid) * len(self._moment_tensors)

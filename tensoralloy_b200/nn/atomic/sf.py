@@ -41,6 +41,12 @@ class SymmetryFunction:
                 "beta": self._beta.tolist(),
                 "cutoff_function": self._cutoff_function}
 
+    def radial_kind(self):
+        return 'sf'
+
+    def moments(self):
+        return (0,)
+
     def radial_sets(self):
         return [(p['eta'], p['omega']) for p in self._radial_parameters]
 

@@ -180,3 +180,75 @@ def test_mlp_on_tensor_cores(case, monkeypatch):
     assert np.abs(f1 - f0).max() <= 2e-5 * max(np.abs(f0).max(), 1e-2)
     assert np.abs(s1 - s0).max() <= 2e-5 * max(np.abs(s0).max(), 1e-4)
     assert np.abs(f0).max() > 1e-3                  # not vacuous
+
+
+# --- GenericRadialAtomicPotential (GRAP), legacy mode: nn/atomic/grap.py:384-466 --------
+def _grap_compare(atoms, elements, rc, algorithm, parameters, moments, method='pair',
+                  cutoff='cosine', nn_kwargs=None, seed=611):
+    from tensoralloy_b200.nn.atomic import GenericRadialAtomicPotential
+    nn_kwargs = nn_kwargs or dict(minmax_scale=False)
+    with precision_scope('high'):
+        clf = UniversalTransformer(elements, rcut=rc, angular=False)
+        desc = GenericRadialAtomicPotential(elements, algorithm=algorithm,
+                                            parameters=parameters,
+                                            param_space_method=method,
+                                            moment_tensors=moments, cutoff_function=cutoff)
+        nn = AtomicNN(elements, desc, export_properties=('energy', 'forces', 'stress'),
+                      **nn_kwargs)
+        nn.attach_transformer(clf)
+        nn.initialize_variables(seed=seed)
+        for el in nn.elements:
+            key = f"Atomic/{el}/Output/kernel"
+            nn.set_variable(key, nn.get_variable(key) * 0.05)
+        calc = TensorAlloyCalculator(nn)
+        calc.calculate(atoms, properties=['energy', 'forces', 'stress'])
+        e, f, s = calc.results['energy'], calc.get_forces(atoms), calc.get_stress(atoms)
+        g = nn.get_descriptors(clf.get_constant_features(atoms))
+    params = {el: nn.mlp_params(el) for el in nn.elements}
+    grap = dict(algorithm=algorithm, grid=desc.radial_sets(), moments=desc.moments(),
+                cutoff=cutoff)
+    ref = oat.atomic_evaluate(elements, atoms.get_chemical_symbols(), atoms.positions,
+                              atoms.cell, atoms.pbc, rc, params, angular=False, grap=grap)
+    # descriptors themselves
+    import torch as _t
+    from oracle import neighbor as onl
+    nl = onl.neighbor_list(atoms.positions, atoms.cell, atoms.pbc, rc)
+    types = np.array([sorted(elements).index(x) for x in atoms.get_chemical_symbols()])
+    G = oat.grap_descriptors(elements, types, _t.tensor(atoms.positions),
+                             _t.tensor(np.asarray(atoms.cell)), nl[0], nl[1], nl[2], rc,
+                             algorithm, desc.radial_sets(), desc.moments(), cutoff).numpy()
+    n = len(atoms)
+    print(algorithm, moments, 'dG', np.abs(g - G).max(), 'dE/N', abs(e - ref['energy']) / n,
+          'dF', np.abs(f - ref['forces']).max(), 'Fmax', np.abs(ref['forces']).max())
+    assert np.abs(g - G).max() < 1e-10 * max(1.0, np.abs(G).max())
+    assert abs(e - ref['energy']) / n < 1e-10
+    assert np.abs(f - ref['forces']).max() < 1e-8
+    assert np.abs(s - ref['stress']).max() < 1e-8
+    with precision_scope('medium'):
+        calc32 = TensorAlloyCalculator(nn)
+        calc32.calculate(atoms, properties=['energy', 'forces'])
+        e32, f32 = calc32.results['energy'], calc32.get_forces(atoms)
+    assert abs(e32 - ref['energy']) <= 2e-5 * max(abs(ref['energy']), 1.0)
+    assert np.abs(f32 - ref['forces']).max() <= 1e-3 * max(np.abs(ref['forces']).max(), 1e-2)
+    return ref
+
+
+def test_grap_families_and_moments():
+    d = np.load(os.path.join(GOLD, 'Be_liquid_4000K.npz'))
+    be = Atoms(list(d['symbols']), d['positions'][2], d['cells'][2], True)
+    # sf algorithm, moment 0 only == the G2 block of the symmetry functions
+    _grap_compare(be, ['Be'], 5.0, 'sf', dict(eta=[0.05, 4.0, 20.0], omega=[0.0, 0.5, 1.0]),
+                  [0])
+    # all three moments, each family (generic.py:15-30,87-100,120-168)
+    _grap_compare(be, ['Be'], 5.0, 'pexp', dict(rl=[1.0, 1.5, 2.0, 2.5], pl=[1.0, 2.0, 3.0, 2.5]),
+                  [0, 1, 2])
+    _grap_compare(be, ['Be'], 5.0, 'morse', dict(D=[0.5, 1.0], gamma=[1.2, 0.8], r0=[2.2, 2.6]),
+                  [0, 2], cutoff='polynomial')
+    ref = _grap_compare(be, ['Be'], 5.0, 'density', dict(A=[1.0, 2.0], beta=[3.0, 5.0],
+                                                        re=[2.2, 2.4]),
+                        [1, 2], method='cross')
+    assert np.abs(ref['forces']).max() > 1e-3
+    # two species, mixed periodicity, min-max normalisation and static energies
+    _grap_compare(PD3O2, ['O', 'Pd'], 6.5, 'pexp', dict(rl=[1.5, 2.5], pl=[2.0, 3.0]), [0, 1, 2],
+                  nn_kwargs=dict(minmax_scale=False,
+                                 atomic_static_energy={'O': -1.0, 'Pd': -2.0}))
