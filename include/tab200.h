@@ -154,6 +154,11 @@ int tab_nbr_export(const tab_nbr *nbr, int32_t *d_i, int32_t *d_j, int32_t *d_S,
                                      reference's missing extension/interp CubicInterpolator):
                                      aux = offset (in intervals) into the model's
                                      coefficient pool, p = x0, 1/dx, n_intervals */
+#define TAB_FN_MLP           17   /* 'nn' function (eam.py:174-190): MLP of the scalar
+                                     argument, hidden layers with bias + activation, linear
+                                     output without bias.  p = n_hidden (<= 4), TAB_ACT_*,
+                                     widths (<= 64); weights in the coefficient pool at
+                                     4*aux doubles: [w0, b0][W1, b1]...[w_out], W in-major */
 #define TAB_FN_MAX_PARAMS    32
 
 typedef struct tab_fn {
@@ -174,7 +179,7 @@ int tab_eam_create(tab_model **out, int32_t kind, int32_t n_el,
                    const tab_fn *dipole, const tab_fn *quadrupole);
 int tab_model_free(tab_model *model);
 
-/* Attach the spline coefficient pool used by TAB_FN_SPLINE entries: interval k of a
+/* Attach the coefficient pool used by TAB_FN_SPLINE (and TAB_FN_MLP) entries: interval k of a
  * table holds 4 doubles (c0, c1, c2, c3) of  f(x) = c0 + c1 t + c2 t^2 + c3 t^3,
  * t = x - (x0 + k dx).  h_coeffs: [n_intervals_total * 4] host doubles. */
 int tab_eam_set_splines(tab_model *model, const double *h_coeffs, int64_t n_doubles);

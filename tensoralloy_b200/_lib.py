@@ -35,6 +35,7 @@ FN_GRIMES_PHI = 13
 FN_MISHIN_EMBED = 14
 FN_MISHIN_POLAR = 15
 FN_SPLINE = 16
+FN_MLP = 17
 
 
 class TabFn(C.Structure):

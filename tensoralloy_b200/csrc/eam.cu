@@ -54,6 +54,7 @@ struct tab_model {
     int kind = 0;
     int n_el = 0;
     bool zhou1 = false;    // single element, all-zjw04: shared-exponential fast path
+    bool has_mlp_fn = false;   // some function is an 'nn' MLP (no analytic Hessian)
     Zhou1 z1;              // fe, beta, lamda, 1/re, A, alpha, kappa, B + folded terms
     bool z1_folded = false;   // prefactors positive: the folded float64 terms are usable
     DevBuf tables;         // tab_fn [2*n_el*n_el + n_el (+ 2*n_el*n_el)]
@@ -617,6 +618,21 @@ extern "C" int tab_eam_create(tab_model **out, int32_t kind, int32_t n_el,
     // device representation: the r_eq slots hold 1/r_eq (potentials.cuh)
     for (size_t k = 0; k < count; ++k) {
         tab_fn &f = host[k];
+        if (f.kind == TAB_FN_MLP) {
+            m->has_mlp_fn = true;
+            const int nh = (int)f.p[0];
+            bool bad = nh < 1 || nh > TAB_MLP_FN_MAXL;
+            for (int l = 0; !bad && l < nh; ++l)
+                bad = f.p[2 + l] < 1 || f.p[2 + l] > TAB_MLP_FN_MAXW;
+            if (bad) {
+                tab_set_error("tab_eam_create: 'nn' function with %d hidden layers / a layer "
+                              "wider than %d", nh, TAB_MLP_FN_MAXW);
+                delete[] host;
+                m->tables.release();
+                delete m;
+                return TAB_EUNSUPPORTED;
+            }
+        }
         if (f.kind == TAB_FN_ZHOU_RHO) f.p[3] = 1.0 / f.p[3];
         else if (f.kind == TAB_FN_ZHOU_PHI) f.p[6] = 1.0 / f.p[6];
         else if (f.kind == TAB_FN_ZHOU_PHI_MIX) {
@@ -667,6 +683,10 @@ extern "C" int tab_eam_create(tab_model **out, int32_t kind, int32_t n_el,
 // accessor for hessian.cu (tab_model is private to this file)
 int tab_eam_tables(tab_model *m, const tab_fn **rho, const tab_fn **phi,
                    const tab_fn **embed, int *n_el, int *kind) {
+    if (m->has_mlp_fn) {
+        tab_set_error("analytic Hessian: 'nn' (MLP) functions carry no second derivative");
+        return TAB_EUNSUPPORTED;
+    }
     const int nn = m->n_el * m->n_el;
     *rho = m->tables.as<tab_fn>();
     *phi = *rho + nn;

@@ -197,6 +197,102 @@ __device__ __forceinline__ void zhou_embed(const double *p, bool blended, Real r
     dF = dc1 * y1 + c1 * d1 + dc2 * y2 + c2 * d2 + dc3 * y3 + c3 * d3;
 }
 
+// ---------------------------------------------------------------------------
+// 'nn' functions (eam.py:174-190 -> convolution1x1 on a scalar): y = MLP(x) with
+// hidden layers (bias + activation) and a linear output unit without bias.  Value
+// and dy/dx by forward-mode differentiation.  Weights live in the model's pool at
+// pool + 4*aux:  layer 0: w[h0], b[h0];  layer l: W[h_{l-1} x h_l] (in-major), b[h_l];
+// output: w[h_last].   p = n_hidden, activation id, h0, h1, ...
+// ---------------------------------------------------------------------------
+#define TAB_MLP_FN_MAXW 64
+#define TAB_MLP_FN_MAXL 4
+
+template <typename Real>
+__device__ __forceinline__ Real mlp_fn_act(int kind, Real z, Real &d) {
+    switch (kind) {
+    case 0: {   // softplus
+        const Real e = Math<Real>::exp_(-fabs(z));
+        d = z >= Real(0) ? Real(1) / (Real(1) + e) : e / (Real(1) + e);
+        return (z > Real(0) ? z : Real(0)) + Math<Real>::log_(Real(1) + e);
+    }
+    case 1: {   // tanh
+        const Real t = tanh(z);
+        d = Real(1) - t * t;
+        return t;
+    }
+    case 2:
+        d = z > Real(0) ? Real(1) : Real(0);
+        return z > Real(0) ? z : Real(0);
+    case 3:
+        d = z > Real(0) ? Real(1) : Real(0.2);
+        return z > Real(0) ? z : Real(0.2) * z;
+    case 4: {
+        const Real sg = Real(1) / (Real(1) + Math<Real>::exp_(-z));
+        d = sg * (Real(1) - sg);
+        return sg;
+    }
+    case 5: {
+        const Real q = Real(1) + fabs(z);
+        d = Real(1) / (q * q);
+        return z / q;
+    }
+    case 6: {
+        const Real e = Math<Real>::exp_(z);
+        d = z > Real(0) ? Real(1) : e;
+        return z > Real(0) ? z : e - Real(1);
+    }
+    default: {
+        const Real sq = Math<Real>::sqrt_(z * z + Real(4));
+        d = Real(0.5) * (Real(1) + z / sq);
+        return Real(0.5) * (z + sq);
+    }
+    }
+}
+
+template <typename Real>
+__device__ __noinline__ void mlp_fn_eval(const tab_fn &fn, const double *__restrict__ pool,
+                                         Real x, Real &f, Real &df) {
+    const int nh = (int)fn.p[0], act = (int)fn.p[1];
+    const double *w = pool + (size_t)fn.aux * 4;
+    Real h[TAB_MLP_FN_MAXW], dh[TAB_MLP_FN_MAXW], g[TAB_MLP_FN_MAXW], dg[TAB_MLP_FN_MAXW];
+    int n0 = (int)fn.p[2];
+    for (int o = 0; o < n0; ++o) {
+        const Real wo = (Real)w[o];
+        Real d;
+        h[o] = mlp_fn_act<Real>(act, wo * x + (Real)w[n0 + o], d);
+        dh[o] = d * wo;
+    }
+    w += 2 * n0;
+    for (int l = 1; l < nh; ++l) {
+        const int n1 = (int)fn.p[2 + l];
+        const double *b = w + (size_t)n0 * n1;
+        for (int o = 0; o < n1; ++o) {
+            Real z = (Real)b[o], dz = Real(0);
+            for (int k = 0; k < n0; ++k) {
+                const Real wk = (Real)w[(size_t)k * n1 + o];
+                z += h[k] * wk;
+                dz += dh[k] * wk;
+            }
+            Real d;
+            g[o] = mlp_fn_act<Real>(act, z, d);
+            dg[o] = d * dz;
+        }
+        for (int o = 0; o < n1; ++o) {
+            h[o] = g[o];
+            dh[o] = dg[o];
+        }
+        w = b + n1;
+        n0 = n1;
+    }
+    Real y = Real(0), dy = Real(0);
+    for (int k = 0; k < n0; ++k) {
+        y += h[k] * (Real)w[k];
+        dy += dh[k] * (Real)w[k];
+    }
+    f = y;
+    df = dy;
+}
+
 // NOTE: tab_eam_create stores 1/r_eq in the r_eq slots of the device tables.
 // One table entry -> value and d/dr.  The switch is warp-uniform for
 // single-species systems and cheap next to the transcendental work otherwise.
@@ -224,6 +320,9 @@ __device__ __forceinline__ void eval_pair_fn(const tab_fn &fn, Real r, Real &f,
     switch (fn.kind) {
     case TAB_FN_SPLINE:
         spline_eval<Real>(fn, pool, r, f, df);
+        break;
+    case TAB_FN_MLP:
+        mlp_fn_eval<Real>(fn, pool, r, f, df);
         break;
     case TAB_FN_ZHOU_RHO:   // zjw04.py:245-277
         zhou_exp<Real>(r, (Real)p[0], (Real)p[1], (Real)p[2], (Real)p[3], f, df);
@@ -342,6 +441,9 @@ __device__ __forceinline__ void eval_embed_fn(const tab_fn &fn, Real rho, Real &
     switch (fn.kind) {
     case TAB_FN_SPLINE:
         spline_eval<Real>(fn, pool, rho, F, dF);
+        break;
+    case TAB_FN_MLP:
+        mlp_fn_eval<Real>(fn, pool, rho, F, dF);
         break;
     case TAB_FN_ZHOU_EMBED:
         zhou_embed<Real>(fn.p, false, rho, F, dF);

@@ -34,6 +34,15 @@ class EamNN(BasicNN):
         self._potentials = self._setup_potentials(custom_potentials)
         self._empirical_functions = {
             key: cls() for key, cls in available_potentials.items()}
+        # 'nn' functions (eam.py:174-190): one MLP per (section, function)
+        from tensoralloy_b200.nn.eam.potentials.nn import NNFunctions
+        self._nn = NNFunctions(self.scope, self._activation)
+        for section, fns in self._potentials.items():
+            for fn, name in fns.items():
+                if name == 'nn':
+                    self._nn.declare(fn, section, self._hidden_sizes[section][fn])
+        self._nn.initialize(np.random.default_rng(Defaults.seed))
+        self._empirical_functions['nn'] = self._nn
         self._model = None
         self._out = None
         assert self._kbody_terms and self._unique_kbody_terms
@@ -73,8 +82,21 @@ class EamNN(BasicNN):
         self._kbody_terms = kbody_terms
 
     # -- variables ---------------------------------------------------------
+    def initialize_variables(self, seed=Defaults.seed):
+        """he_normal kernels / zero biases of the 'nn' functions (init_ops.py:81-123)."""
+        self._nn.initialize(np.random.default_rng(seed))
+        self._model = None
+
+    @property
+    def variables(self):
+        """The trainable 'nn' variables by reference name."""
+        return self._nn.variables()
+
     def get_variable(self, name):
-        """Value of `EAM/Shared/<section>/<param>` (potentials.py:171-200)."""
+        """Value of `EAM/Shared/<section>/<param>` (potentials.py:171-200) or of an
+        'nn' kernel / bias."""
+        if self._nn.owns(name):
+            return self._nn.variables()[name]
         scope, shared, section, key = name.split('/')
         for fn in self._empirical_functions.values():
             if section in fn.params and key in fn.params[section]:
@@ -85,6 +107,10 @@ class EamNN(BasicNN):
         """Set one shared variable (e.g. a Const node of a frozen .pb).  Shared
         variables are keyed by section/param only (potentials.py:171-200), so
         the value is applied to every registered potential unless one is named."""
+        if self._nn.owns(name):
+            self._nn.set_variable(name, value)
+            self._model = None
+            return
         parts = name.split('/')
         section, key = parts[-2], parts[-1]
         for pname, fn in self._empirical_functions.items():
@@ -100,9 +126,7 @@ class EamNN(BasicNN):
     def _fn_of(self, section, key):
         name = self._potentials[section][key]
         if name == 'nn':
-            raise NotImplementedError(
-                "'nn' (MLP-parametrised) EAM functions are not available in "
-                "libtab200 yet")
+            return self._nn
         if name.startswith("spline@"):
             if name not in self._empirical_functions:
                 from tensoralloy_b200.nn.eam.potentials.spline import SplinePotential
@@ -129,18 +153,22 @@ class EamNN(BasicNN):
                     key = "".join(sorted([a, b])) if a != b else f"{a}{a}"
                     dipole.append(self._fn_of(key, 'dipole').dipole(key))
                     quadrupole.append(self._fn_of(key, 'quadrupole').quadrupole(key))
-        # tabulated functions: one coefficient pool per model; rebase the offsets
+        # tabulated and 'nn' functions: one coefficient pool per model (units of 4
+        # doubles); rebase the offsets of every provider after the first
         splines = [f for k, f in self._empirical_functions.items()
-                   if k.startswith("spline@")]
+                   if k.startswith("spline@") or k == 'nn']
         base = 0
         pools = []
         for sp in splines:
             pool = sp.pool()
+            if not len(pool):
+                continue
             if base:
                 for fns in (rho, phi, embed, dipole or [], quadrupole or []):
                     for fn in fns:
-                        if fn.kind == _lib.FN_SPLINE and getattr(fn, '_owner', None) is sp:
+                        if getattr(fn, '_owner', None) is sp and not getattr(fn, '_rebased', False):
                             fn.aux += base
+                            fn._rebased = True
             pools.append(pool)
             base += len(pool)
         self._model = _lib.EamModel(self.kind, len(els), rho, phi, embed, dipole,

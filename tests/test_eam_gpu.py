@@ -254,3 +254,93 @@ def test_tile_lists_large_lattice(monkeypatch):
     assert e1 == e0
     np.testing.assert_array_equal(f1, f0)
     np.testing.assert_array_equal(ea1, ea0)
+
+
+# --- 'nn' functions (eam.py:174-190): MLP-parametrised rho / phi / embed / u / w ---------
+def _nn_oracle_fns(nn, elements):
+    """Oracle callables for the functions of `nn` that are 'nn' (torch MLP with the
+    model's weights); the others stay with the named empirical potential."""
+    from oracle import atomic as oat
+    provider = nn._nn
+
+    def make(fn, key):
+        arrays = provider.weights(fn, key)
+        W = [torch.tensor(a) for a in arrays[0:-1:2]] + [torch.tensor(arrays[-1])]
+        b = [torch.tensor(a) for a in arrays[1:-1:2]]
+        return lambda x: oat.mlp(x[:, None], W, b, nn._activation)
+
+    fns = {}
+    pots = nn.potentials
+    zj = opot.get_potential('zjw04')
+
+    def dispatch(fn, base):
+        def call(x, key):
+            if fn in ('rho', 'embed'):
+                section = key[-2:] if (fn == 'rho' and nn.tag == 'fs') else key
+                if fn == 'rho' and nn.tag != 'fs':
+                    section = key
+            else:
+                section = key
+            name = pots[section][fn]
+            if name == 'nn':
+                return make(fn, section)(x)
+            return getattr(zj, base)(x, key)
+        return call
+
+    for fn in ('rho', 'phi', 'embed', 'dipole', 'quadrupole'):
+        fns[fn] = dispatch(fn, fn)
+    return fns
+
+
+@pytest.mark.parametrize("case", ["all_nn", "mixed", "adp_nn"])
+def test_nn_parametrised_functions(case):
+    from tensoralloy_b200.atoms import Atoms
+    from tensoralloy_b200.calculator import TensorAlloyCalculator
+    from tensoralloy_b200.nn.eam import AdpNN, EamAlloyNN
+    from tensoralloy_b200.precision import precision_scope
+    from tensoralloy_b200.transformer import UniversalTransformer
+    base = bulk_fcc('Ni', 3.6, (3, 3, 3))
+    rng = np.random.default_rng(7)
+    sym = ['Mo' if x < 0.4 else 'Ni' for x in rng.random(len(base))]
+    atoms = Atoms(sym, base.positions + rng.normal(scale=0.08, size=base.positions.shape),
+                  base.cell, True)
+    elements = ['Mo', 'Ni']
+    with precision_scope('high'):
+        if case == "all_nn":
+            nn = EamAlloyNN(elements, hidden_sizes=[16, 8])          # every function 'nn'
+        elif case == "mixed":
+            nn = EamAlloyNN(elements, custom_potentials={
+                'Ni': {'rho': 'zjw04', 'embed': 'nn'}, 'Mo': {'rho': 'nn', 'embed': 'zjw04'},
+                'MoNi': {'phi': 'nn'}, 'NiNi': {'phi': 'zjw04'}, 'MoMo': {'phi': 'zjw04'}},
+                hidden_sizes={'Ni': {'embed': [24]}, 'Mo': {'rho': [12, 12, 6]},
+                              'MoNi': {'phi': [32, 16]}})
+        else:
+            nn = AdpNN(elements, custom_potentials={
+                'Ni': {'rho': 'zjw04', 'embed': 'zjw04'}, 'Mo': {'rho': 'zjw04', 'embed': 'zjw04'},
+                'MoNi': {'phi': 'zjw04', 'dipole': 'nn', 'quadrupole': 'nn'},
+                'NiNi': {'phi': 'zjw04', 'dipole': 'nn', 'quadrupole': 'nn'},
+                'MoMo': {'phi': 'zjw04', 'dipole': 'nn', 'quadrupole': 'nn'}},
+                hidden_sizes=[8, 8])
+        nn.attach_transformer(UniversalTransformer(elements, rcut=5.0))
+        nn.initialize_variables(seed=3)
+        for name, value in list(nn.variables.items()):
+            if name.endswith('Output/kernel'):
+                nn.set_variable(name, value * (0.02 if case == "adp_nn" else 0.2))
+        calc = TensorAlloyCalculator(nn)
+        calc.calculate(atoms, properties=['energy', 'forces', 'stress'])
+        e, f, s = calc.results['energy'], calc.get_forces(atoms), calc.get_stress(atoms)
+    kind = 'adp' if case == "adp_nn" else 'alloy'
+    ref = oeam.eam_evaluate(opot.get_potential('zjw04'), kind, elements, sym,
+                            atoms.positions, atoms.cell, [1, 1, 1], 5.0,
+                            fns=_nn_oracle_fns(nn, elements))
+    n = len(atoms)
+    print(case, 'E/N', ref['energy'] / n, 'dE/N', abs(e - ref['energy']) / n, 'dF',
+          np.abs(f - ref['forces']).max(), 'Fmax', np.abs(ref['forces']).max())
+    assert abs(e - ref['energy']) / n < 1e-10
+    assert np.abs(f - ref['forces']).max() < 1e-8
+    assert np.abs(s - ref['stress']).max() < 1e-8
+    assert np.abs(ref['forces']).max() > 1e-3
+    with precision_scope('medium'):
+        calc32 = TensorAlloyCalculator(nn)
+        calc32.calculate(atoms, properties=['energy', 'forces'])
+    assert abs(calc32.results['energy'] - ref['energy']) <= 2e-5 * max(abs(ref['energy']), 1.0)
