@@ -72,6 +72,13 @@ struct tab_model {
 #define EAM_FORCE_UNROLL 1   // pairs per iteration of the force loop (ILP vs registers)
 #endif
 constexpr int kForceUnroll = EAM_FORCE_UNROLL;
+// exp2 table size (log2) of the folded float64 zjw04 terms, per pass (potentials.cuh zexp)
+#ifndef ZEXP_RHO
+#define ZEXP_RHO 0
+#endif
+#ifndef ZEXP_FORCE
+#define ZEXP_FORCE 6
+#endif
 #define ADP_MAX_EL 3     // ADP keeps n_el x 9 moment accumulators in registers
 
 template <typename Real>
@@ -139,7 +146,7 @@ __device__ __forceinline__ void load_tables(tab_fn *s, const tab_fn *g, int coun
 // ---------------------------------------------------------------------------
 // pass 1
 // ---------------------------------------------------------------------------
-template <typename Real, bool FAST, bool CACHE>
+template <typename Real, bool FAST, bool CACHE, bool NN>
 __global__ void __launch_bounds__(EAM_T, EAM_MINB)
 k_eam_rho(int n, const Atom4 *__restrict__ atoms,
           const uint8_t *__restrict__ types_ext, const int *__restrict__ counts,
@@ -149,8 +156,10 @@ k_eam_rho(int n, const Atom4 *__restrict__ atoms,
           double *__restrict__ fprime_caller, double2 *__restrict__ pcache) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     tab_fn *tabs = reinterpret_cast<tab_fn *>(smem_raw);
+    __shared__ double s_etab[TAB_EXP_TAB];
     const int nn = m.n_el * m.n_el;
     if (!FAST) load_tables(tabs, m.rho, 2 * nn + m.n_el);
+    if (FAST && sizeof(Real) == 8 && !CACHE) load_exp2_tab<ZEXP_RHO>(s_etab);
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n) return;
     const Atom4 me = atoms[idx];
@@ -168,7 +177,7 @@ k_eam_rho(int n, const Atom4 *__restrict__ atoms,
         if (FAST) {
             if (sizeof(Real) == 8 && !CACHE) {
                 double f8, d8;      // folded float64 term, fe inside the exponent
-                zterm_eval<false>((double)r, (double)r * z.re, z.t_rho, f8, d8);
+                zterm_eval<false, ZEXP_RHO>((double)r, (double)r * z.re, z.t_rho, s_etab, f8, d8);
                 f = (Real)f8;
             } else {
                 // g with unit prefactor; rho = fe * sum g
@@ -178,14 +187,16 @@ k_eam_rho(int n, const Atom4 *__restrict__ atoms,
             }
         } else {
             const int tj = (int)(c >> TAB_COL_TYPE_SHIFT);
-            eval_pair_fn<Real>(tabs[ti * m.n_el + tj], r, f, df, m.pool);
+            eval_pair_fn<Real, NN>(tabs[ti * m.n_el + tj], r, f, df, m.pool);
         }
         rho += f;
     }
     if (FAST && !(sizeof(Real) == 8 && !CACHE)) rho *= (Real)z.fe;
     Real F, dF;
-    if (FAST) eval_embed_fn<Real>(embed0, rho, F, dF);
-    else eval_embed_fn<Real>(tabs[2 * nn + ti], rho, F, dF, m.pool);
+    // the fast path is all-zjw04 (tab_eam_create): call the embedding directly, the generic
+    // switch would drag the 'nn' function's local arrays into this kernel
+    if (FAST) zhou_embed<Real>(embed0.p, embed0.kind == TAB_FN_ZHOU_EMBED_XC, rho, F, dF);
+    else eval_embed_fn<Real, NN>(tabs[2 * nn + ti], rho, F, dF, m.pool);
     fprime[idx] = (double)dF;
     fembed[idx] = (double)F;
     if (fprime_caller) fprime_caller[perm[idx]] = (double)dF;
@@ -209,7 +220,7 @@ __global__ void k_spread_w(int n_owned, int n_loc, int n_ext,
 // ---------------------------------------------------------------------------
 // pass 2
 // ---------------------------------------------------------------------------
-template <typename Real, bool FAST, bool CACHE>
+template <typename Real, bool FAST, bool CACHE, bool NN>
 __global__ void __launch_bounds__(EAM_T, EAM_MINB)
 k_eam_force(int n, const Atom4 *__restrict__ atoms,
             const uint8_t *__restrict__ types_ext, const int *__restrict__ counts,
@@ -221,8 +232,10 @@ k_eam_force(int n, const Atom4 *__restrict__ atoms,
     extern __shared__ __align__(16) unsigned char smem_raw[];
     tab_fn *tabs = reinterpret_cast<tab_fn *>(smem_raw);
     __shared__ double red[EAM_T / 32][7];
+    __shared__ double s_etab[TAB_EXP_TAB];
     const int nn = m.n_el * m.n_el;
     if (!FAST) load_tables(tabs, m.rho, 2 * nn + m.n_el);
+    if (FAST && sizeof(Real) == 8 && !CACHE) load_exp2_tab<ZEXP_FORCE>(s_etab);
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     double acc[7] = {0, 0, 0, 0, 0, 0, 0};   // E, vxx, vyy, vzz, vyz, vxz, vxy
     if (idx < n) {
@@ -249,8 +262,8 @@ k_eam_force(int n, const Atom4 *__restrict__ atoms,
                 // folded float64 terms: A and B inside the exponents
                 const double x = (double)r * z.re;
                 double ga, dga, gb, dgb;
-                zterm_eval<true>((double)r, x, z.t_a, ga, dga);
-                zterm_eval<true>((double)r, x, z.t_b, gb, dgb);
+                zterm_eval<true, ZEXP_FORCE>((double)r, x, z.t_a, s_etab, ga, dga);
+                zterm_eval<true, ZEXP_FORCE>((double)r, x, z.t_b, s_etab, gb, dgb);
                 phi = (Real)(ga - gb);
                 dphi = (Real)(dga - dgb);
                 der = (Real)fma(((double)fpi + (double)fpj) * z.fe_over_B, dgb, (double)dphi);
@@ -271,10 +284,10 @@ k_eam_force(int n, const Atom4 *__restrict__ atoms,
             } else {
                 const int tj = (int)(c >> TAB_COL_TYPE_SHIFT);
                 Real rij, drij, rji, drji;
-                eval_pair_fn<Real>(tabs[ti * m.n_el + tj], r, rij, drij, m.pool);
+                eval_pair_fn<Real, NN>(tabs[ti * m.n_el + tj], r, rij, drij, m.pool);
                 if (ti == tj) drji = drij;
-                else eval_pair_fn<Real>(tabs[tj * m.n_el + ti], r, rji, drji, m.pool);
-                eval_pair_fn<Real>(tabs[nn + ti * m.n_el + tj], r, phi, dphi, m.pool);
+                else eval_pair_fn<Real, NN>(tabs[tj * m.n_el + ti], r, rji, drji, m.pool);
+                eval_pair_fn<Real, NN>(tabs[nn + ti * m.n_el + tj], r, phi, dphi, m.pool);
                 der = fpi * drij + fpj * drji + dphi;
             }
             const Real s = der * rinv;
@@ -331,7 +344,7 @@ k_eam_force(int n, const Atom4 *__restrict__ atoms,
 // Moments are stored per extended atom as [n_el][9] = mux muy muz lxx lyy lzz
 // lyz lxz lxy; pass 2 needs the neighbour's moments w.r.t. the centre's species.
 // ---------------------------------------------------------------------------
-template <typename Real>
+template <typename Real, bool NN>
 __global__ void __launch_bounds__(EAM_T)
 k_adp_rho(int n, const Atom4 *__restrict__ atoms,
           const uint8_t *__restrict__ types_ext, const int *__restrict__ counts,
@@ -362,9 +375,9 @@ k_adp_rho(int n, const Atom4 *__restrict__ atoms,
         Real dx, dy, dz, r, rinv, f, df, u, du, w, dw;
         pair_r<Real>(me, a, dx, dy, dz, r, rinv);
         const int tj = (int)(c >> TAB_COL_TYPE_SHIFT);
-        eval_pair_fn<Real>(tabs[ti * m.n_el + tj], r, f, df, m.pool);
-        eval_pair_fn<Real>(t_dip[ti * m.n_el + tj], r, u, du, m.pool);
-        eval_pair_fn<Real>(t_quad[ti * m.n_el + tj], r, w, dw, m.pool);
+        eval_pair_fn<Real, NN>(tabs[ti * m.n_el + tj], r, f, df, m.pool);
+        eval_pair_fn<Real, NN>(t_dip[ti * m.n_el + tj], r, u, du, m.pool);
+        eval_pair_fn<Real, NN>(t_quad[ti * m.n_el + tj], r, w, dw, m.pool);
         rho += f;
 #pragma unroll
         for (int t = 0; t < ADP_MAX_EL; ++t) {
@@ -382,7 +395,7 @@ k_adp_rho(int n, const Atom4 *__restrict__ atoms,
         }
     }
     Real F, dF;
-    eval_embed_fn<Real>(tabs[2 * nn + ti], rho, F, dF, m.pool);
+    eval_embed_fn<Real, NN>(tabs[2 * nn + ti], rho, F, dF, m.pool);
     Real eadp = Real(0);
 #pragma unroll
     for (int t = 0; t < ADP_MAX_EL; ++t) {
@@ -412,7 +425,7 @@ __global__ void k_adp_spread(int n_owned, int n_ext, int stride,
         moments[(size_t)e * stride + k] = moments[(size_t)o * stride + k];
 }
 
-template <typename Real>
+template <typename Real, bool NN>
 __global__ void __launch_bounds__(EAM_T)
 k_adp_force(int n, const Atom4 *__restrict__ atoms,
             const uint8_t *__restrict__ types_ext, const int *__restrict__ counts,
@@ -449,12 +462,12 @@ k_adp_force(int n, const Atom4 *__restrict__ atoms,
             const int tj = (int)(c >> TAB_COL_TYPE_SHIFT);
             const Real fpj = (Real)a.w;
             Real rij, drij, rji, drji, phi, dphi, u, du, w, dw;
-            eval_pair_fn<Real>(tabs[ti * m.n_el + tj], r, rij, drij, m.pool);
+            eval_pair_fn<Real, NN>(tabs[ti * m.n_el + tj], r, rij, drij, m.pool);
             if (ti == tj) drji = drij;
-            else eval_pair_fn<Real>(tabs[tj * m.n_el + ti], r, rji, drji, m.pool);
-            eval_pair_fn<Real>(tabs[nn + ti * m.n_el + tj], r, phi, dphi, m.pool);
-            eval_pair_fn<Real>(t_dip[ti * m.n_el + tj], r, u, du, m.pool);
-            eval_pair_fn<Real>(t_quad[ti * m.n_el + tj], r, w, dw, m.pool);
+            else eval_pair_fn<Real, NN>(tabs[tj * m.n_el + ti], r, rji, drji, m.pool);
+            eval_pair_fn<Real, NN>(tabs[nn + ti * m.n_el + tj], r, phi, dphi, m.pool);
+            eval_pair_fn<Real, NN>(t_dip[ti * m.n_el + tj], r, u, du, m.pool);
+            eval_pair_fn<Real, NN>(t_quad[ti * m.n_el + tj], r, w, dw, m.pool);
             // EAM part, symmetric in the pair
             const Real s = (fpi * drij + fpj * drji + dphi) * rinv;
             Real gx = s * dx, gy = s * dy, gz = s * dz;
@@ -810,14 +823,21 @@ static int eam_pass1(tab_model *m, tab_nbr *nbr, double *d_fprime_caller,
     if (cache) TAB_TRY(nbr->pcache.ensure(sizeof(double2) * 32 * (size_t)(nbr->ell_rows + 1)));
     nbr->pcache_valid = false;
     prof_mark(0, st);
+    // 'nn' functions (NN) exist only on the generic path; the pair cache only on the fast one
     if (cache)
-        k_eam_rho<Real, FAST, FAST><<<L.nblk, EAM_T, L.smem, st>>>(
+        k_eam_rho<Real, FAST, FAST, false><<<L.nblk, EAM_T, L.smem, st>>>(
             nbr->n, nbr->atoms.as<Atom4>(), nbr->types_ext.as<uint8_t>(),
             nbr->counts.as<int>(), nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>(),
             nbr->perm.as<int>(), L.dev, L.z, m->embed0, L.fprime, L.fembed,
             d_fprime_caller, nbr->pcache.as<double2>());
+    else if (!FAST && m->has_mlp_fn)
+        k_eam_rho<Real, false, false, true><<<L.nblk, EAM_T, L.smem, st>>>(
+            nbr->n, nbr->atoms.as<Atom4>(), nbr->types_ext.as<uint8_t>(),
+            nbr->counts.as<int>(), nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>(),
+            nbr->perm.as<int>(), L.dev, L.z, m->embed0, L.fprime, L.fembed,
+            d_fprime_caller, nullptr);
     else
-        k_eam_rho<Real, FAST, false><<<L.nblk, EAM_T, L.smem, st>>>(
+        k_eam_rho<Real, FAST, false, false><<<L.nblk, EAM_T, L.smem, st>>>(
             nbr->n, nbr->atoms.as<Atom4>(), nbr->types_ext.as<uint8_t>(),
             nbr->counts.as<int>(), nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>(),
             nbr->perm.as<int>(), L.dev, L.z, m->embed0, L.fprime, L.fembed,
@@ -846,13 +866,19 @@ static int eam_pass2(tab_model *m, tab_nbr *nbr, const double *d_fprime_halo,
     // pass 1 of the same evaluation left (g, g') per pair behind (positions unchanged
     // in between: tab_nbr_update / tab_nbr_build invalidate)
     if (FAST && sizeof(Real) == 8 && nbr->pcache_valid)
-        k_eam_force<Real, FAST, FAST><<<L.nblk, EAM_T, L.smem, st>>>(
+        k_eam_force<Real, FAST, FAST, false><<<L.nblk, EAM_T, L.smem, st>>>(
             nbr->n, nbr->atoms.as<Atom4>(), nbr->types_ext.as<uint8_t>(),
             nbr->counts.as<int>(), nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>(),
             nbr->perm.as<int>(), L.dev, L.z, L.fembed, d_eatom, d_forces,
             nbr->partial.as<double>(), nbr->pcache.as<double2>());
+    else if (!FAST && m->has_mlp_fn)
+        k_eam_force<Real, false, false, true><<<L.nblk, EAM_T, L.smem, st>>>(
+            nbr->n, nbr->atoms.as<Atom4>(), nbr->types_ext.as<uint8_t>(),
+            nbr->counts.as<int>(), nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>(),
+            nbr->perm.as<int>(), L.dev, L.z, L.fembed, d_eatom, d_forces,
+            nbr->partial.as<double>(), nullptr);
     else
-        k_eam_force<Real, FAST, false><<<L.nblk, EAM_T, L.smem, st>>>(
+        k_eam_force<Real, FAST, false, false><<<L.nblk, EAM_T, L.smem, st>>>(
             nbr->n, nbr->atoms.as<Atom4>(), nbr->types_ext.as<uint8_t>(),
             nbr->counts.as<int>(), nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>(),
             nbr->perm.as<int>(), L.dev, L.z, L.fembed, d_eatom, d_forces,
@@ -881,7 +907,8 @@ static int adp_pass1(tab_model *m, tab_nbr *nbr, cudaStream_t st) {
     L.smem = (size_t)(4 * nn + m->n_el) * sizeof(tab_fn);
     TAB_TRY(nbr->adp.ensure(sizeof(double) * (size_t)nbr->n_ext * stride));
     prof_mark(0, st);
-    k_adp_rho<Real><<<L.nblk, EAM_T, L.smem, st>>>(
+    auto kr = m->has_mlp_fn ? k_adp_rho<Real, true> : k_adp_rho<Real, false>;
+    kr<<<L.nblk, EAM_T, L.smem, st>>>(
         nbr->n, nbr->atoms.as<Atom4>(), nbr->types_ext.as<uint8_t>(),
         nbr->counts.as<int>(), nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>(),
         L.dev, L.fprime, L.fembed, nbr->adp.as<double>());
@@ -907,7 +934,8 @@ static int adp_pass2(tab_model *m, tab_nbr *nbr, double *d_energy, double *d_eat
         nbr->ghost_owner.as<int>(), nbr->atoms.as<Atom4>());
     TAB_LAUNCH_CHECK();
     prof_mark(2, st);
-    k_adp_force<Real><<<L.nblk, EAM_T, L.smem, st>>>(
+    auto kf = m->has_mlp_fn ? k_adp_force<Real, true> : k_adp_force<Real, false>;
+    kf<<<L.nblk, EAM_T, L.smem, st>>>(
         nbr->n, nbr->atoms.as<Atom4>(), nbr->types_ext.as<uint8_t>(),
         nbr->counts.as<int>(), nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>(),
         nbr->perm.as<int>(), L.dev, nbr->adp.as<double>(), L.fembed, d_eatom, d_forces,

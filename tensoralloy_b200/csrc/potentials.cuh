@@ -100,10 +100,9 @@ __device__ __forceinline__ void zhou_exp(Real r, Real a, Real b, Real c, Real in
 // denominator formed as 1 + u^16 u^4, and (20/re) u^19 built from
 // u' = (20/re) u = r (20/re^2) - 20 c/re, so that
 //   df/dr = f * ( -(20/re) u^19 q - b/re ).
-// 30 FP64 instructions for f and df (the generic zhou_exp above: 35); the
-// exponential uses a degree-11 minimax polynomial on |f| <= ln2/2 (approximation
-// error 1.4e-17) and no underflow guard -- the host only takes this path when
-// b (rc/re - 1) < 600.
+// 25 FP64 instructions for f and df (the generic zhou_exp above: 35); the
+// exponential is table driven (below) and has no underflow guard -- the host only
+// takes this path when b (rc/re - 1) < 600.
 // ---------------------------------------------------------------------------
 struct ZTerm {
     double nb;      // -b
@@ -114,32 +113,94 @@ struct ZTerm {
     double nb_re;   // -b / re
 };
 
-template <bool DERIV>
-__device__ __forceinline__ void zterm_eval(double r, double x, const ZTerm &p, double &f,
+// 2^(j/64), j = 0..63, correctly rounded (exp2 table of the folded float64 terms).
+// The kernels copy a stride of it to shared memory once per block.
+#define TAB_EXP_TAB 64
+__device__ const double c_exp2_tab[TAB_EXP_TAB] = {
+    0x1.0000000000000p+0, 0x1.02c9a3e778061p+0, 0x1.059b0d3158574p+0, 0x1.0874518759bc8p+0,
+    0x1.0b5586cf9890fp+0, 0x1.0e3ec32d3d1a2p+0, 0x1.11301d0125b51p+0, 0x1.1429aaea92de0p+0,
+    0x1.172b83c7d517bp+0, 0x1.1a35beb6fcb75p+0, 0x1.1d4873168b9aap+0, 0x1.2063b88628cd6p+0,
+    0x1.2387a6e756238p+0, 0x1.26b4565e27cddp+0, 0x1.29e9df51fdee1p+0, 0x1.2d285a6e4030bp+0,
+    0x1.306fe0a31b715p+0, 0x1.33c08b26416ffp+0, 0x1.371a7373aa9cbp+0, 0x1.3a7db34e59ff7p+0,
+    0x1.3dea64c123422p+0, 0x1.4160a21f72e2ap+0, 0x1.44e086061892dp+0, 0x1.486a2b5c13cd0p+0,
+    0x1.4bfdad5362a27p+0, 0x1.4f9b2769d2ca7p+0, 0x1.5342b569d4f82p+0, 0x1.56f4736b527dap+0,
+    0x1.5ab07dd485429p+0, 0x1.5e76f15ad2148p+0, 0x1.6247eb03a5585p+0, 0x1.6623882552225p+0,
+    0x1.6a09e667f3bcdp+0, 0x1.6dfb23c651a2fp+0, 0x1.71f75e8ec5f74p+0, 0x1.75feb564267c9p+0,
+    0x1.7a11473eb0187p+0, 0x1.7e2f336cf4e62p+0, 0x1.82589994cce13p+0, 0x1.868d99b4492edp+0,
+    0x1.8ace5422aa0dbp+0, 0x1.8f1ae99157736p+0, 0x1.93737b0cdc5e5p+0, 0x1.97d829fde4e50p+0,
+    0x1.9c49182a3f090p+0, 0x1.a0c667b5de565p+0, 0x1.a5503b23e255dp+0, 0x1.a9e6b5579fdbfp+0,
+    0x1.ae89f995ad3adp+0, 0x1.b33a2b84f15fbp+0, 0x1.b7f76f2fb5e47p+0, 0x1.bcc1e904bc1d2p+0,
+    0x1.c199bdd85529cp+0, 0x1.c67f12e57d14bp+0, 0x1.cb720dcef9069p+0, 0x1.d072d4a07897cp+0,
+    0x1.d5818dcfba487p+0, 0x1.da9e603db3285p+0, 0x1.dfc97337b9b5fp+0, 0x1.e502ee78b3ff6p+0,
+    0x1.ea4afa2a490dap+0, 0x1.efa1bee615a27p+0, 0x1.f50765b6e4540p+0, 0x1.fa7c1819e90d8p+0,
+};
+
+// LB = log2(table entries): 0 = no table (degree-11 polynomial on |fr| <= ln2/2),
+// 4 = 16 entries (one 128-byte shared-memory row: conflict-free for any index pattern,
+// degree 7), 5 = 32 entries (degree 6), 6 = 64 entries (degree 5).
+template <int LB>
+__device__ __forceinline__ void load_exp2_tab(double *s_tab) {
+    if (LB > 0) {
+        if (threadIdx.x < (1 << LB)) s_tab[threadIdx.x] = c_exp2_tab[threadIdx.x << (6 - LB)];
+        __syncthreads();
+    }
+}
+
+// exp(t) of the folded terms.  Table driven (LB > 0): t = (2^LB m + j) ln2/2^LB + fr,
+// |fr| <= ln2/2^(LB+1), exp(t) = 2^m * 2^(j/2^LB) * P(fr) with a Taylor polynomial whose
+// truncation error is < 2e-17 relative, the table entry by one 8-byte shared-memory load.
+template <int LB>
+__device__ __forceinline__ double zexp(double t, const double *__restrict__ etab) {
+    const double SHIFT = 6755399441055744.0;   // 1.5 * 2^52
+    constexpr double S = (double)(1 << LB);
+    const double zz = fma(t, S * 1.4426950408889634074, SHIFT);
+    const int n = __double2loint(zz);
+    const double nf = zz - SHIFT;
+    double fr = fma(nf, -6.93147180369123816490e-01 / S, t);
+    fr = fma(nf, -1.90821492927058770002e-10 / S, fr);
+    double e;
+    if (LB == 0) {
+        e = 2.511015364692893e-08;
+        e = fma(e, fr, 2.763279054211718e-07);
+        e = fma(e, fr, 2.7557240604663896e-06);
+        e = fma(e, fr, 2.4801485074105115e-05);
+        e = fma(e, fr, 0.00019841269890340666);
+        e = fma(e, fr, 0.0013888888952696516);
+        e = fma(e, fr, 0.00833333333331949);
+        e = fma(e, fr, 0.04166666666648666);
+        e = fma(e, fr, 0.1666666666666668);
+        e = fma(e, fr, 0.5000000000000019);
+        e = fma(e, fr, 1.0);
+        e = fma(e, fr, 1.0);   // (an Estrin split of this chain measured 4 % slower: +3 FP64 ops)
+    } else {
+        if (LB == 4) {
+            e = 1.98412698412698412698e-04;                 // 1/7!
+            e = fma(e, fr, 1.38888888888888888889e-03);     // 1/6!
+            e = fma(e, fr, 8.33333333333333333333e-03);     // 1/5!
+        } else if (LB == 5) {
+            e = 1.38888888888888888889e-03;
+            e = fma(e, fr, 8.33333333333333333333e-03);
+        } else {
+            e = 8.33333333333333333333e-03;
+        }
+        e = fma(e, fr, 4.16666666666666666667e-02);
+        e = fma(e, fr, 1.66666666666666666667e-01);
+        e = fma(e, fr, 0.5);
+        e = fma(e, fr, 1.0);
+        e = fma(e, fr, 1.0);
+        e *= etab[n & ((1 << LB) - 1)];
+    }
+    return __hiloint2double(__double2hiint(e) + ((n >> LB) << 20), __double2loint(e));
+}
+
+template <bool DERIV, int LB>
+__device__ __forceinline__ void zterm_eval(double r, double x, const ZTerm &p,
+                                           const double *__restrict__ etab, double &f,
                                            double &df) {
     const double u = x - p.kappa;
     const double u2 = u * u, u4 = u2 * u2, u8 = u4 * u4, u16 = u8 * u8;
     const double q = tab_rcp(fma(u16, u4, 1.0));
-    const double SHIFT = 6755399441055744.0;   // 1.5 * 2^52
-    const double t = fma(x, p.nb, p.c);
-    const double zz = fma(t, 1.4426950408889634074, SHIFT);
-    const int n = __double2loint(zz);
-    const double nf = zz - SHIFT;
-    double fr = fma(nf, -6.93147180369123816490e-01, t);
-    fr = fma(nf, -1.90821492927058770002e-10, fr);
-    double e = 2.511015364692893e-08;
-    e = fma(e, fr, 2.763279054211718e-07);
-    e = fma(e, fr, 2.7557240604663896e-06);
-    e = fma(e, fr, 2.4801485074105115e-05);
-    e = fma(e, fr, 0.00019841269890340666);
-    e = fma(e, fr, 0.0013888888952696516);
-    e = fma(e, fr, 0.00833333333331949);
-    e = fma(e, fr, 0.04166666666648666);
-    e = fma(e, fr, 0.1666666666666668);
-    e = fma(e, fr, 0.5000000000000019);
-    e = fma(e, fr, 1.0);
-    e = fma(e, fr, 1.0);   // (an Estrin split of this chain measured 4 % slower: +3 FP64 ops)
-    e = __hiloint2double(__double2hiint(e) + (n << 20), __double2loint(e));
+    const double e = zexp<LB>(fma(x, p.nb, p.c), etab);
     f = e * q;
     if (DERIV) {
         const double up = fma(r, p.c20, p.k20);
@@ -312,17 +373,20 @@ __device__ __forceinline__ void spline_eval(const tab_fn &fn, const double *__re
     df = (Real(3) * c3 * d + Real(2) * c2) * d + c1;
 }
 
-template <typename Real>
+// NN = the model holds 'nn' (MLP) functions: only then is mlp_fn_eval (local arrays, a
+// stack frame and ~2x the registers) compiled into the calling kernel.
+template <typename Real, bool NN = false>
 __device__ __forceinline__ void eval_pair_fn(const tab_fn &fn, Real r, Real &f,
                                              Real &df,
                                              const double *__restrict__ pool = nullptr) {
     const double *p = fn.p;
+    if (NN && fn.kind == TAB_FN_MLP) {
+        mlp_fn_eval<Real>(fn, pool, r, f, df);
+        return;
+    }
     switch (fn.kind) {
     case TAB_FN_SPLINE:
         spline_eval<Real>(fn, pool, r, f, df);
-        break;
-    case TAB_FN_MLP:
-        mlp_fn_eval<Real>(fn, pool, r, f, df);
         break;
     case TAB_FN_ZHOU_RHO:   // zjw04.py:245-277
         zhou_exp<Real>(r, (Real)p[0], (Real)p[1], (Real)p[2], (Real)p[3], f, df);
@@ -434,16 +498,17 @@ __device__ __forceinline__ void eval_pair_fn(const tab_fn &fn, Real r, Real &f,
     }
 }
 
-template <typename Real>
+template <typename Real, bool NN = false>
 __device__ __forceinline__ void eval_embed_fn(const tab_fn &fn, Real rho, Real &F,
                                               Real &dF,
                                               const double *__restrict__ pool = nullptr) {
+    if (NN && fn.kind == TAB_FN_MLP) {
+        mlp_fn_eval<Real>(fn, pool, rho, F, dF);
+        return;
+    }
     switch (fn.kind) {
     case TAB_FN_SPLINE:
         spline_eval<Real>(fn, pool, rho, F, dF);
-        break;
-    case TAB_FN_MLP:
-        mlp_fn_eval<Real>(fn, pool, rho, F, dF);
         break;
     case TAB_FN_ZHOU_EMBED:
         zhou_embed<Real>(fn.p, false, rho, F, dF);
