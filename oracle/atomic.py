@@ -293,3 +293,95 @@ def atomic_evaluate(elements, symbols, positions, cell, pbc, rc, params, sf=None
 
     return evaluate(energy_fn, torch.tensor(positions, dtype=dtype),
                     torch.tensor(cell, dtype=dtype), hessian=hessian)
+
+
+def td_heads(x, T, p, dtype):
+    """nn/atomic/finite_temperature.py:211-304 for the atoms of ONE element.
+    x [n, D] descriptors (already min-max scaled), T scalar electron temperature,
+    p = dict(H=..., S=..., U=...) of mlp parameter dicts + 'algo' + 'special'.
+    Returns per-atom (U, S, F = U - T S)."""
+    def net(q, inp, squeeze=True):
+        W = [torch.as_tensor(w, dtype=dtype) for w in q['weights']]
+        b = [None if v is None else torch.as_tensor(v, dtype=dtype) for v in q['biases']]
+        ob = q.get('out_bias')
+        ob = None if ob is None else torch.as_tensor(ob, dtype=dtype)
+        fn = activation(q.get('activation', 'softplus'))
+        h = inp
+        nh = len(W) - 1
+        for k in range(nh):
+            y = fn(h @ W[k] + b[k])
+            if k and q.get('use_resnet_dt', False) and W[k].shape[1] == W[k - 1].shape[1]:
+                h = y + h
+            else:
+                h = y
+        out = h @ W[nh]
+        if ob is not None:
+            out = out + ob
+        return out[:, 0] if squeeze else out
+    H = net(p['H'], x, squeeze=False)                       # :243-256 (linear output layer)
+    t = torch.full((x.shape[0], 1), float(T), dtype=dtype)
+    Ht = torch.cat([H, t], dim=1)                            # :92-118
+    Tv = t[:, 0]
+    if p.get('special') == 'Be':                             # special/beryllium.py:23-77
+        t2 = Tv * Tv
+        ft = torch.relu(1.0 - 1.45 * Tv) ** 2
+        base = -0.5718444 * t2 * ft + 0.83744317 * Tv + (-0.2110962) * (1.0 - ft)
+        S = base * torch.nn.functional.softplus(net(p['S'], Ht))
+    else:
+        S = net(p['S'], Ht)                                  # :120-166
+        if p.get('algo', 'default') == 'Sommerfeld':
+            S = S * Tv
+    U = net(p['U'], Ht)                                      # :168-209
+    return U, S, U - Tv * S                                  # :296-301
+
+
+def td_atomic_evaluate(elements, symbols, positions, cell, pbc, rc, params, etemperature,
+                       sf=None, acut=None, angular=True, dtype=torch.float64, minmax=None):
+    """Oracle call for TemperatureDependentAtomicNN: forces / stress derive from the
+    FREE energy (basic.py:190-202); also returns 'energy' (U), 'eentropy' (S),
+    'free_energy'."""
+    from oracle import neighbor
+    elements = sorted(elements)
+    sf = dict(sf or {})
+    positions = np.asarray(positions, dtype=np.float64)
+    cell = np.asarray(cell, dtype=np.float64).reshape(3, 3)
+    nl = neighbor.neighbor_list(positions, cell, pbc, rc)
+    acut_eff = acut if acut is not None else rc
+    ang = None
+    if angular and abs(acut_eff - rc) > 5e-3:
+        ang = neighbor.neighbor_list(positions, cell, pbc, acut_eff)[:3]
+    types = np.array([elements.index(s) for s in symbols])
+    keep = {}
+
+    def energy_fn(R, h):
+        G = descriptors(elements, types, R, h, nl[0], nl[1], nl[2], rc, acut_eff,
+                        angular, ang_list=ang, **sf)
+        n = R.shape[0]
+        U = torch.zeros(n, dtype=R.dtype)
+        S = torch.zeros(n, dtype=R.dtype)
+        F = torch.zeros(n, dtype=R.dtype)
+        for a, el in enumerate(elements):
+            sel = torch.nonzero(torch.as_tensor(types == a)).reshape(-1)
+            if not sel.numel():
+                continue
+            x = G[sel]
+            if minmax and minmax.get(el) is not None:
+                xlo, xhi = [torch.as_tensor(v, dtype=R.dtype) for v in minmax[el]]
+                den = xhi - xlo
+                x = torch.where(den == 0, torch.zeros_like(x), (xhi - x) / den)
+            u, s, f = td_heads(x, etemperature, params[el], R.dtype)
+            U = U.index_add(0, sel, u)
+            S = S.index_add(0, sel, s)
+            F = F.index_add(0, sel, f)
+        keep['U'], keep['S'] = U.detach(), S.detach()
+        return F.sum(), F
+
+    out = evaluate(energy_fn, torch.tensor(positions, dtype=dtype),
+                   torch.tensor(cell, dtype=dtype))
+    out['free_energy'] = out['energy']
+    out['free_energy/atom'] = out['energy/atom']
+    out['energy'] = keep['U'].sum().numpy()
+    out['energy/atom'] = keep['U'].numpy()
+    out['eentropy'] = keep['S'].sum().numpy()
+    out['eentropy/atom'] = keep['S'].numpy()
+    return out
