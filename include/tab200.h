@@ -101,6 +101,21 @@ int tab_peer_put(const double *d_src, int32_t n, const uint64_t *d_peer_ptrs,
 int tab_sum_slots(const double *d_slots, int32_t n_slots, int32_t n, double *d_out,
                   void *stream);
 
+/* Batch of independent structures in ONE handle ("structure-parallel batches"; replaces
+ * the padded [B, N+1, 3] / [B, nij_max, .] tensors of BatchUniversalTransformer,
+ * transformer/universal.py:921-1388, and the per-structure ASE neighbour lists behind them).
+ * Structure s owns atoms [h_offsets[s], h_offsets[s+1]) of d_pos / d_types; h_cells:
+ * [n_struct, 9]; h_pbc: [n_struct, 3].  Meant for small structures (~100 atoms): the
+ * candidates of an atom are all atoms and periodic images of its own structure.  Every
+ * evaluation entry point accepts a batch handle; per-atom outputs cover all atoms of the
+ * batch in caller order, and d_energy / d_virial become [n_struct] / [n_struct, 9]
+ * (tab_atomic_jvp: d_A [n_struct, 9]).  Not supported on batch handles: tab_nbr_update,
+ * tab_eam_hessian, the domain-decomposition passes. */
+int tab_nbr_build_batch(tab_nbr *nbr, int32_t n_struct, const int32_t *h_offsets,
+                        const double *d_pos, const int32_t *d_types, const double *h_cells,
+                        const int32_t *h_pbc, double rc, void *stream);
+int tab_nbr_batch_size(const tab_nbr *nbr);   /* 0 = single structure */
+
 /* Keep the lists, refresh the positions (and optionally the cell): the MD step
  * between two rebuilds.  h_cell may be NULL (unchanged). */
 int tab_nbr_update(tab_nbr *nbr, const double *d_pos, const double *h_cell,

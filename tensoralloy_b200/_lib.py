@@ -98,6 +98,7 @@ EXPORTS = [
     'tab_atomic_create', 'tab_atomic_free', 'tab_atomic_dim', 'tab_atomic_eval',
     'tab_atomic_descriptors', 'tab_atomic_forces', 'tab_atomic_jvp',
     'tab_launch_count', 'tab_launch_count_reset',
+    'tab_nbr_build_batch', 'tab_nbr_batch_size',
     'tab_profile_enable', 'tab_profile_read',
 ]
 
@@ -125,6 +126,9 @@ def lib():
     L.tab_nbr_build_dd.argtypes = [vp, i32, i32, vp, vp, C.POINTER(dbl),
                                    C.POINTER(dbl), C.POINTER(i32), dbl, vp]
     L.tab_nbr_update.argtypes = [vp, vp, C.POINTER(dbl), vp]
+    L.tab_nbr_build_batch.argtypes = [vp, i32, C.POINTER(i32), vp, vp, C.POINTER(dbl),
+                                      C.POINTER(i32), dbl, vp]
+    L.tab_nbr_batch_size.argtypes = [vp]
     L.tab_pack_rows.argtypes = [vp, vp, i32, i32, C.POINTER(dbl), vp, vp]
     L.tab_peer_put.argtypes = [vp, i32, vp, i32, i32, vp]
     L.tab_sum_slots.argtypes = [vp, i32, i32, vp, vp]
@@ -218,6 +222,7 @@ class NeighborList:
         self._h = C.c_void_p()
         check(lib().tab_nbr_create(C.byref(self._h)), 'tab_nbr_create')
         self.n = 0
+        self.n_struct = 0       # > 0: batch handle (build_batch)
 
     def __del__(self):
         try:
@@ -238,6 +243,7 @@ class NeighborList:
         if d_types is not None:
             assert d_types.is_cuda and d_types.dtype == torch.int32
         self.n = int(d_pos.shape[0])
+        self.n_struct = 0
         check(lib().tab_nbr_build(self._h, self.n, _ptr(d_pos), _ptr(d_types),
                                   _cell9(cell), _pbc3(pbc), float(rc), _stream()),
               'tab_nbr_build')
@@ -250,10 +256,33 @@ class NeighborList:
             assert d_types.is_cuda and d_types.dtype == torch.int32
         n_loc = int(d_pos.shape[0])
         self.n = int(n_owned)
+        self.n_struct = 0
         org = (C.c_double * 3)(*[float(x) for x in origin])
         check(lib().tab_nbr_build_dd(self._h, self.n, n_loc - self.n, _ptr(d_pos),
                                      _ptr(d_types), _cell9(cell), org, _pbc3(pbc),
                                      float(rc), _stream()), 'tab_nbr_build_dd')
+
+    def build_batch(self, d_pos, d_types, offsets, cells, pbcs, rc):
+        """Lists of a BATCH of structures in one handle (tab_nbr_build_batch).
+        d_pos [N,3] / d_types [N]: the structures' atoms back to back; offsets
+        [B+1]; cells [B,3,3]; pbcs [B,3]."""
+        import torch
+        assert d_pos.is_cuda and d_pos.dtype == torch.float64 and d_pos.is_contiguous()
+        if d_types is not None:
+            assert d_types.is_cuda and d_types.dtype == torch.int32
+        offsets = np.ascontiguousarray(offsets, dtype=np.int32)
+        nb = len(offsets) - 1
+        cells = np.ascontiguousarray(cells, dtype=np.float64).reshape(nb, 9)
+        pbcs = np.ascontiguousarray(np.asarray(pbcs).astype(bool), dtype=np.int32).reshape(nb, 3)
+        assert int(offsets[-1]) == int(d_pos.shape[0])
+        self.n = int(d_pos.shape[0])
+        self.n_struct = nb
+        self.offsets = offsets
+        check(lib().tab_nbr_build_batch(
+            self._h, nb, offsets.ctypes.data_as(C.POINTER(C.c_int32)), _ptr(d_pos),
+            _ptr(d_types), cells.ctypes.data_as(C.POINTER(C.c_double)),
+            pbcs.ctypes.data_as(C.POINTER(C.c_int32)), float(rc), _stream()),
+            'tab_nbr_build_batch')
 
     def update(self, d_pos, cell=None):
         c = _cell9(cell) if cell is not None else None

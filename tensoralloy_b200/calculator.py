@@ -224,6 +224,41 @@ class TensorAlloyCalculator(_AseCalculator):
     def reset_call_counter(self):
         self._ncalls = 0
 
+    def calculate_batch(self, images, properties=('energy', 'forces', 'stress')):
+        """Batched inference (BASELINE config 2: "batched E/F/stress inference"): the
+        structures of `images` share ONE neighbour handle and every kernel runs once over
+        the whole batch (`tab_nbr_build_batch`).  The reference has no calculator-level
+        batch call (its batches exist only inside the tf.data training pipeline,
+        universal.py:921-1388); this is the inference-side equivalent.  Returns one dict
+        per structure: 'energy', 'forces' [N,3] in the structure's own (ASE) atom order,
+        'stress' [6] Voigt eV/A^3, 'energy/atom' [N]."""
+        with precision_scope(self._fp_precision):
+            properties = set(properties)
+            for prop in properties:
+                if prop not in self.implemented_properties:
+                    raise KeyError(prop)
+            want_stress = bool({'stress', 'total_pressure'} & properties)
+            want_forces = 'forces' in properties or want_stress
+            batch = self._transformer.get_batch_features(images)
+            raws = self._nn.evaluate_batch(batch, want_forces, want_stress, True)
+            dtype = np.float64 if self._fp_precision == 'high' else np.float32
+            out = []
+            for s, raw in enumerate(raws):
+                res = {'energy': dtype(raw['energy']),
+                       'energy/atom': raw['energy/atom'].astype(dtype)}
+                if want_forces:
+                    res['forces'] = raw['forces'].astype(dtype)
+                if want_stress:
+                    stress = raw['virial'] / batch.volumes[s]
+                    res['virial'] = raw['virial'].astype(dtype)
+                    res['stress'] = np.array([stress[a, b] for a, b in
+                                              ((0, 0), (1, 1), (2, 2), (1, 2), (0, 2),
+                                               (0, 1))]).astype(dtype)
+                    res['total_pressure'] = dtype(np.trace(stress) / (-3.0 * GPa))
+                out.append(res)
+            self._ncalls += 1
+        return out
+
     # -- the hot call ---------------------------------------------------------
     def calculate(self, atoms=None, properties=('energy', 'forces'),
                   system_changes=all_changes, debug_mode=False, extra_ops=None):

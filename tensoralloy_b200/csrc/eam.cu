@@ -81,6 +81,20 @@ constexpr int kForceUnroll = EAM_FORCE_UNROLL;
 #endif
 #define ADP_MAX_EL 3     // ADP keeps n_el x 9 moment accumulators in registers
 
+// Block -> atoms of the pair kernels.  Single structure: block b owns atoms
+// [b T, (b+1) T).  Batch handles (tab_nbr_build_batch): blocks are cut at structure
+// boundaries (blk_first[b] .. blk_first[b+1]) so that a block's partial sums belong to
+// one structure.
+__device__ __forceinline__ bool block_atom(int n, const int *__restrict__ blk_first,
+                                           int &idx) {
+    if (blk_first) {
+        idx = blk_first[blockIdx.x] + (int)threadIdx.x;
+        return idx < blk_first[blockIdx.x + 1];
+    }
+    idx = blockIdx.x * blockDim.x + threadIdx.x;
+    return idx < n;
+}
+
 template <typename Real>
 __device__ __forceinline__ void pair_r(const Atom4 &me, const Atom4 &a, Real &dx,
                                        Real &dy, Real &dz, Real &r, Real &rinv) {
@@ -153,15 +167,16 @@ k_eam_rho(int n, const Atom4 *__restrict__ atoms,
           const uint32_t *__restrict__ slice_ptr, const uint32_t *__restrict__ col,
           const int *__restrict__ perm, EamDev m, Zhou1 z, tab_fn embed0,
           double *__restrict__ fprime, double *__restrict__ fembed,
-          double *__restrict__ fprime_caller, double2 *__restrict__ pcache) {
+          double *__restrict__ fprime_caller, double2 *__restrict__ pcache,
+          const int *__restrict__ blk_first) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     tab_fn *tabs = reinterpret_cast<tab_fn *>(smem_raw);
     __shared__ double s_etab[TAB_EXP_TAB];
     const int nn = m.n_el * m.n_el;
     if (!FAST) load_tables(tabs, m.rho, 2 * nn + m.n_el);
     if (FAST && sizeof(Real) == 8 && !CACHE) load_exp2_tab<ZEXP_RHO>(s_etab);
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n) return;
+    int idx;
+    if (!block_atom(n, blk_first, idx)) return;
     const Atom4 me = atoms[idx];
     const int ti = FAST ? 0 : (int)types_ext[idx];
     const int cnt = counts[idx];
@@ -228,7 +243,7 @@ k_eam_force(int n, const Atom4 *__restrict__ atoms,
             const int *__restrict__ perm, EamDev m, Zhou1 z,
             const double *__restrict__ fembed, double *__restrict__ eatom,
             double *__restrict__ forces, double *__restrict__ partial,
-            const double2 *__restrict__ pcache) {
+            const double2 *__restrict__ pcache, const int *__restrict__ blk_first) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     tab_fn *tabs = reinterpret_cast<tab_fn *>(smem_raw);
     __shared__ double red[EAM_T / 32][7];
@@ -236,9 +251,10 @@ k_eam_force(int n, const Atom4 *__restrict__ atoms,
     const int nn = m.n_el * m.n_el;
     if (!FAST) load_tables(tabs, m.rho, 2 * nn + m.n_el);
     if (FAST && sizeof(Real) == 8 && !CACHE) load_exp2_tab<ZEXP_FORCE>(s_etab);
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    int idx;
+    const bool active = block_atom(n, blk_first, idx);
     double acc[7] = {0, 0, 0, 0, 0, 0, 0};   // E, vxx, vyy, vzz, vyz, vxz, vxy
-    if (idx < n) {
+    if (active) {
         const Atom4 me = atoms[idx];
         const int ti = FAST ? 0 : (int)types_ext[idx];
         const int cnt = counts[idx];
@@ -350,14 +366,14 @@ k_adp_rho(int n, const Atom4 *__restrict__ atoms,
           const uint8_t *__restrict__ types_ext, const int *__restrict__ counts,
           const uint32_t *__restrict__ slice_ptr, const uint32_t *__restrict__ col,
           EamDev m, double *__restrict__ fprime, double *__restrict__ fembed,
-          double *__restrict__ moments) {
+          double *__restrict__ moments, const int *__restrict__ blk_first) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     tab_fn *tabs = reinterpret_cast<tab_fn *>(smem_raw);
     const int nn = m.n_el * m.n_el;
     load_tables(tabs, m.rho, 4 * nn + m.n_el);
     const tab_fn *t_dip = tabs + 2 * nn + m.n_el, *t_quad = t_dip + nn;
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n) return;
+    int idx;
+    if (!block_atom(n, blk_first, idx)) return;
     const Atom4 me = atoms[idx];
     const int ti = (int)types_ext[idx];
     const int cnt = counts[idx];
@@ -433,16 +449,17 @@ k_adp_force(int n, const Atom4 *__restrict__ atoms,
             const int *__restrict__ perm, EamDev m,
             const double *__restrict__ moments, const double *__restrict__ fembed,
             double *__restrict__ eatom, double *__restrict__ forces,
-            double *__restrict__ partial) {
+            double *__restrict__ partial, const int *__restrict__ blk_first) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     tab_fn *tabs = reinterpret_cast<tab_fn *>(smem_raw);
     __shared__ double red[EAM_T / 32][7];
     const int nn = m.n_el * m.n_el;
     load_tables(tabs, m.rho, 4 * nn + m.n_el);
     const tab_fn *t_dip = tabs + 2 * nn + m.n_el, *t_quad = t_dip + nn;
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    int idx;
+    const bool active = block_atom(n, blk_first, idx);
     double acc[7] = {0, 0, 0, 0, 0, 0, 0};
-    if (idx < n) {
+    if (active) {
         const Atom4 me = atoms[idx];
         const int ti = (int)types_ext[idx];
         const int cnt = counts[idx];
@@ -555,13 +572,22 @@ k_adp_force(int n, const Atom4 *__restrict__ atoms,
     }
 }
 
-// fixed-order final reduction: energy[0], virial[9]
+// fixed-order final reduction: energy[0], virial[9].  Batch handles: block s of the grid
+// reduces the partial rows [struct_blk[s], struct_blk[s+1]) into energy[s], virial[9 s..].
 __global__ void __launch_bounds__(256)
 k_reduce_partials(int nblk, const double *__restrict__ partial,
-                  double *__restrict__ energy, double *__restrict__ virial) {
+                  double *__restrict__ energy, double *__restrict__ virial,
+                  const int *__restrict__ struct_blk) {
     __shared__ double sm[256][7];
     double a[7] = {0, 0, 0, 0, 0, 0, 0};
-    for (int b = threadIdx.x; b < nblk; b += 256)
+    int b_lo = 0;
+    if (struct_blk) {
+        b_lo = struct_blk[blockIdx.x];
+        nblk = struct_blk[blockIdx.x + 1];
+        if (energy) energy += blockIdx.x;
+        if (virial) virial += 9 * (size_t)blockIdx.x;
+    }
+    for (int b = b_lo + threadIdx.x; b < nblk; b += 256)
 #pragma unroll
         for (int q = 0; q < 7; ++q) a[q] += partial[(size_t)b * 8 + q];
 #pragma unroll
@@ -780,11 +806,48 @@ struct EamLaunch {
     size_t smem;
     int nblk;
     double *fprime, *fembed;
+    const int *blk_first;    // batch handles: blocks cut at structure boundaries, else NULL
+    const int *struct_blk;
+    int n_red;               // grid of k_reduce_partials (1, or the number of structures)
 };
 
-static int eam_prepare(tab_model *m, tab_nbr *nbr, bool fast, EamLaunch &L) {
+// batch handles: the pair-kernel block table for blocks of EAM_T atoms (cached in nbr)
+static int ensure_batch_blocks(tab_nbr *nbr, cudaStream_t st) {
+    if (nbr->n_struct <= 0 || nbr->blk_T == EAM_T) return TAB_OK;
+    std::vector<int> first, sblk(nbr->n_struct + 1);
+    for (int s = 0; s < nbr->n_struct; ++s) {
+        sblk[s] = (int)first.size();
+        for (int a = nbr->h_struct_off[s]; a < nbr->h_struct_off[s + 1]; a += EAM_T)
+            first.push_back(a);
+    }
+    sblk[nbr->n_struct] = (int)first.size();
+    nbr->n_blk = (int)first.size();
+    first.push_back(nbr->h_struct_off[nbr->n_struct]);
+    TAB_TRY(nbr->blk_first.ensure(sizeof(int) * first.size()));
+    TAB_TRY(nbr->struct_blk.ensure(sizeof(int) * sblk.size()));
+    TAB_CUDA(cudaMemcpyAsync(nbr->blk_first.p, first.data(), sizeof(int) * first.size(),
+                             cudaMemcpyHostToDevice, st));
+    TAB_CUDA(cudaMemcpyAsync(nbr->struct_blk.p, sblk.data(), sizeof(int) * sblk.size(),
+                             cudaMemcpyHostToDevice, st));
+    TAB_CUDA(cudaStreamSynchronize(st));     // pageable host vectors
+    nbr->blk_T = EAM_T;
+    return TAB_OK;
+}
+
+static int eam_prepare(tab_model *m, tab_nbr *nbr, bool fast, EamLaunch &L,
+                       cudaStream_t st) {
     const int n = nbr->n;
     L.nblk = (n + EAM_T - 1) / EAM_T;
+    L.blk_first = nullptr;
+    L.struct_blk = nullptr;
+    L.n_red = 1;
+    if (nbr->n_struct > 0) {
+        TAB_TRY(ensure_batch_blocks(nbr, st));
+        L.nblk = nbr->n_blk;
+        L.blk_first = nbr->blk_first.as<int>();
+        L.struct_blk = nbr->struct_blk.as<int>();
+        L.n_red = nbr->n_struct;
+    }
     TAB_TRY(nbr->rho.ensure(sizeof(double) * 2 * (size_t)n));
     TAB_TRY(nbr->partial.ensure(sizeof(double) * 8 * (size_t)L.nblk));
     L.fprime = nbr->rho.as<double>();
@@ -818,7 +881,7 @@ template <typename Real, bool FAST>
 static int eam_pass1(tab_model *m, tab_nbr *nbr, double *d_fprime_caller,
                      cudaStream_t st) {
     EamLaunch L;
-    TAB_TRY(eam_prepare(m, nbr, FAST, L));
+    TAB_TRY(eam_prepare(m, nbr, FAST, L, st));
     const bool cache = FAST && sizeof(Real) == 8 && pair_cache_enabled();
     if (cache) TAB_TRY(nbr->pcache.ensure(sizeof(double2) * 32 * (size_t)(nbr->ell_rows + 1)));
     nbr->pcache_valid = false;
@@ -829,19 +892,19 @@ static int eam_pass1(tab_model *m, tab_nbr *nbr, double *d_fprime_caller,
             nbr->n, nbr->atoms.as<Atom4>(), nbr->types_ext.as<uint8_t>(),
             nbr->counts.as<int>(), nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>(),
             nbr->perm.as<int>(), L.dev, L.z, m->embed0, L.fprime, L.fembed,
-            d_fprime_caller, nbr->pcache.as<double2>());
+            d_fprime_caller, nbr->pcache.as<double2>(), L.blk_first);
     else if (!FAST && m->has_mlp_fn)
         k_eam_rho<Real, false, false, true><<<L.nblk, EAM_T, L.smem, st>>>(
             nbr->n, nbr->atoms.as<Atom4>(), nbr->types_ext.as<uint8_t>(),
             nbr->counts.as<int>(), nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>(),
             nbr->perm.as<int>(), L.dev, L.z, m->embed0, L.fprime, L.fembed,
-            d_fprime_caller, nullptr);
+            d_fprime_caller, nullptr, L.blk_first);
     else
         k_eam_rho<Real, FAST, false, false><<<L.nblk, EAM_T, L.smem, st>>>(
             nbr->n, nbr->atoms.as<Atom4>(), nbr->types_ext.as<uint8_t>(),
             nbr->counts.as<int>(), nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>(),
             nbr->perm.as<int>(), L.dev, L.z, m->embed0, L.fprime, L.fembed,
-            d_fprime_caller, nullptr);
+            d_fprime_caller, nullptr, L.blk_first);
     TAB_LAUNCH_CHECK();
     nbr->pcache_valid = cache;
     prof_mark(1, st);
@@ -853,7 +916,7 @@ static int eam_pass2(tab_model *m, tab_nbr *nbr, const double *d_fprime_halo,
                      double *d_energy, double *d_eatom, double *d_forces,
                      double *d_virial, cudaStream_t st) {
     EamLaunch L;
-    TAB_TRY(eam_prepare(m, nbr, FAST, L));
+    TAB_TRY(eam_prepare(m, nbr, FAST, L, st));
     if (nbr->n_halo > 0 && !d_fprime_halo) {
         tab_set_error("tab_eam_pass2: halo atoms present but no halo F' given");
         return TAB_EINVAL;
@@ -870,24 +933,24 @@ static int eam_pass2(tab_model *m, tab_nbr *nbr, const double *d_fprime_halo,
             nbr->n, nbr->atoms.as<Atom4>(), nbr->types_ext.as<uint8_t>(),
             nbr->counts.as<int>(), nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>(),
             nbr->perm.as<int>(), L.dev, L.z, L.fembed, d_eatom, d_forces,
-            nbr->partial.as<double>(), nbr->pcache.as<double2>());
+            nbr->partial.as<double>(), nbr->pcache.as<double2>(), L.blk_first);
     else if (!FAST && m->has_mlp_fn)
         k_eam_force<Real, false, false, true><<<L.nblk, EAM_T, L.smem, st>>>(
             nbr->n, nbr->atoms.as<Atom4>(), nbr->types_ext.as<uint8_t>(),
             nbr->counts.as<int>(), nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>(),
             nbr->perm.as<int>(), L.dev, L.z, L.fembed, d_eatom, d_forces,
-            nbr->partial.as<double>(), nullptr);
+            nbr->partial.as<double>(), nullptr, L.blk_first);
     else
         k_eam_force<Real, FAST, false, false><<<L.nblk, EAM_T, L.smem, st>>>(
             nbr->n, nbr->atoms.as<Atom4>(), nbr->types_ext.as<uint8_t>(),
             nbr->counts.as<int>(), nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>(),
             nbr->perm.as<int>(), L.dev, L.z, L.fembed, d_eatom, d_forces,
-            nbr->partial.as<double>(), nullptr);
+            nbr->partial.as<double>(), nullptr, L.blk_first);
     TAB_LAUNCH_CHECK();
     prof_mark(3, st);
     if (d_energy || d_virial) {
-        k_reduce_partials<<<1, 256, 0, st>>>(L.nblk, nbr->partial.as<double>(), d_energy,
-                                             d_virial);
+        k_reduce_partials<<<L.n_red, 256, 0, st>>>(L.nblk, nbr->partial.as<double>(),
+                                                   d_energy, d_virial, L.struct_blk);
         TAB_LAUNCH_CHECK();
     }
     prof_mark(4, st);
@@ -898,7 +961,7 @@ static int eam_pass2(tab_model *m, tab_nbr *nbr, const double *d_fprime_halo,
 template <typename Real>
 static int adp_pass1(tab_model *m, tab_nbr *nbr, cudaStream_t st) {
     EamLaunch L;
-    TAB_TRY(eam_prepare(m, nbr, false, L));
+    TAB_TRY(eam_prepare(m, nbr, false, L, st));
     if (nbr->n_halo > 0) {
         tab_set_error("ADP with halo atoms (domain decomposition) is not supported");
         return TAB_EUNSUPPORTED;
@@ -911,7 +974,7 @@ static int adp_pass1(tab_model *m, tab_nbr *nbr, cudaStream_t st) {
     kr<<<L.nblk, EAM_T, L.smem, st>>>(
         nbr->n, nbr->atoms.as<Atom4>(), nbr->types_ext.as<uint8_t>(),
         nbr->counts.as<int>(), nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>(),
-        L.dev, L.fprime, L.fembed, nbr->adp.as<double>());
+        L.dev, L.fprime, L.fembed, nbr->adp.as<double>(), L.blk_first);
     TAB_LAUNCH_CHECK();
     if (nbr->n_ext > nbr->n) {
         k_adp_spread<<<(nbr->n_ext - nbr->n + 255) / 256, 256, 0, st>>>(
@@ -926,7 +989,7 @@ template <typename Real>
 static int adp_pass2(tab_model *m, tab_nbr *nbr, double *d_energy, double *d_eatom,
                      double *d_forces, double *d_virial, cudaStream_t st) {
     EamLaunch L;
-    TAB_TRY(eam_prepare(m, nbr, false, L));
+    TAB_TRY(eam_prepare(m, nbr, false, L, st));
     const int nn = m->n_el * m->n_el;
     L.smem = (size_t)(4 * nn + m->n_el) * sizeof(tab_fn);
     k_spread_w<<<(nbr->n_ext + 255) / 256, 256, 0, st>>>(
@@ -939,12 +1002,12 @@ static int adp_pass2(tab_model *m, tab_nbr *nbr, double *d_energy, double *d_eat
         nbr->n, nbr->atoms.as<Atom4>(), nbr->types_ext.as<uint8_t>(),
         nbr->counts.as<int>(), nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>(),
         nbr->perm.as<int>(), L.dev, nbr->adp.as<double>(), L.fembed, d_eatom, d_forces,
-        nbr->partial.as<double>());
+        nbr->partial.as<double>(), L.blk_first);
     TAB_LAUNCH_CHECK();
     prof_mark(3, st);
     if (d_energy || d_virial) {
-        k_reduce_partials<<<1, 256, 0, st>>>(L.nblk, nbr->partial.as<double>(), d_energy,
-                                             d_virial);
+        k_reduce_partials<<<L.n_red, 256, 0, st>>>(L.nblk, nbr->partial.as<double>(),
+                                                   d_energy, d_virial, L.struct_blk);
         TAB_LAUNCH_CHECK();
     }
     prof_mark(4, st);
@@ -1038,6 +1101,10 @@ extern "C" int tab_eam_compute_host(tab_model *m, tab_nbr *nbr, int32_t precisio
         return TAB_EINVAL;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    if (nbr->n_struct > 0 && !rebuild) {
+        tab_set_error("tab_eam_compute_host: the handle holds a batch; pass rebuild != 0");
+        return TAB_ESTATE;
+    }
     TAB_TRY(g_stage.pos.ensure(sizeof(double) * 3 * (size_t)n));
     TAB_TRY(g_stage.types.ensure(sizeof(int32_t) * (size_t)n));
     // out: energy[1] virial[9] (pad to 16) | forces[3n] | eatom[n]

@@ -398,6 +398,10 @@ extern "C" int tab_eam_hessian(tab_model *m, tab_nbr *nbr, double *d_hessian,
         tab_set_error("tab_eam_hessian: halo atoms (domain decomposition) not supported");
         return TAB_EUNSUPPORTED;
     }
+    if (nbr->n_struct > 0) {
+        tab_set_error("tab_eam_hessian: batch handles are not supported (one structure per call)");
+        return TAB_EUNSUPPORTED;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     HessCtx c;
     int kind = 0;

@@ -1040,6 +1040,7 @@ extern "C" int tab_nbr_build_dd(tab_nbr *nbr, int32_t n_owned, int32_t n_halo,
     cudaStream_t st = (cudaStream_t)stream;
     nbr->built = false;
     nbr->pcache_valid = false;
+    nbr->n_struct = 0;          // single structure (a batch handle may be reused)
     Grid &g = nbr->grid;
     const int n = n_owned, n_loc = (int)n_loc_ll;
     TAB_TRY(setup_grid(g, n_loc, h_cell, h_origin, h_pbc, rc));
@@ -1301,6 +1302,10 @@ extern "C" int tab_nbr_update(tab_nbr *nbr, const double *d_pos, const double *h
         tab_set_error("tab_nbr_update before tab_nbr_build");
         return TAB_ESTATE;
     }
+    if (nbr->n_struct > 0) {
+        tab_set_error("tab_nbr_update: batch handles are rebuilt, not refreshed");
+        return TAB_EUNSUPPORTED;
+    }
     if (h_cell) {
         double det;
         memcpy(nbr->grid.h, h_cell, 9 * sizeof(double));
@@ -1439,3 +1444,5 @@ extern "C" int tab_sum_slots(const double *d_slots, int32_t n_slots, int32_t n,
     TAB_LAUNCH_CHECK();
     return TAB_OK;
 }
+
+#include "nbr_batch.cuh"

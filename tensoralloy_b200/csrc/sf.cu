@@ -729,6 +729,44 @@ k_sf_collect(int n, int n_loc, const int *__restrict__ counts,
     if (threadIdx.x == 0) partial_e[(size_t)blockIdx.x] = red[0] + red[1] + red[2] + red[3];
 }
 
+// batch handles: one block per structure sums its atoms' energies (eat, sorted = caller
+// order) and the per-atom virial rows of k_sf_backward (partial[idx*8+1..6]) in fixed order
+__global__ void __launch_bounds__(128)
+k_sf_reduce_batch(const int *__restrict__ struct_off, const double *__restrict__ eat,
+                  const double *__restrict__ partial, double *__restrict__ energy,
+                  double *__restrict__ virial) {
+    __shared__ double sm[128][7];
+    const int s = blockIdx.x;
+    const int lo = struct_off[s], hi = struct_off[s + 1];
+    double a[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (int i = lo + threadIdx.x; i < hi; i += 128) {
+        if (eat) a[0] += eat[i];
+        if (partial)
+#pragma unroll
+            for (int q = 1; q < 7; ++q) a[q] += partial[(size_t)i * 8 + q];
+    }
+#pragma unroll
+    for (int q = 0; q < 7; ++q) sm[threadIdx.x][q] = a[q];
+    __syncthreads();
+    for (int w = 64; w > 0; w >>= 1) {
+        if (threadIdx.x < w)
+#pragma unroll
+            for (int q = 0; q < 7; ++q) sm[threadIdx.x][q] += sm[threadIdx.x + w][q];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        if (energy) energy[s] = sm[0][0];
+        if (virial) {
+            double *v = virial + 9 * (size_t)s;
+            const double xx = sm[0][1], yy = sm[0][2], zz = sm[0][3], yz = sm[0][4],
+                         xz = sm[0][5], xy = sm[0][6];
+            v[0] = xx; v[1] = xy; v[2] = xz;
+            v[3] = xy; v[4] = yy; v[5] = yz;
+            v[6] = xz; v[7] = yz; v[8] = zz;
+        }
+    }
+}
+
 // fixed-order final sums: energy from partial_e[nb_e], virial from partial[nb_v*8+1..6]
 __global__ void __launch_bounds__(256)
 k_sf_reduce(int nb_e, const double *__restrict__ partial_e, int nb_v,
@@ -779,12 +817,14 @@ k_sf_jvp(int n, int n_loc, SfDev sf, int n_types, int row_cap,
          const int *__restrict__ counts, const int *__restrict__ tcounts,
          const uint32_t *__restrict__ slice_ptr, const uint32_t *__restrict__ col,
          const int *__restrict__ ghost_owner, const double *__restrict__ u,
-         const double *__restrict__ A, double *__restrict__ T) {
+         const double *__restrict__ A, const int *__restrict__ struct_of,
+         double *__restrict__ T) {
     extern __shared__ __align__(16) double smem[];
     __shared__ double red[SF_WARPS];
     const int lane = threadIdx.x;
     const int idx = blockIdx.x;
     if (idx >= n) return;
+    if (struct_of) A += 9 * (size_t)struct_of[idx];     // batch: A [n_struct, 9]
     double *row = smem;
     double *dd = row + (size_t)row_cap * ROW_W;          // [row_cap][4]: dD_p
     const int cnt = stage_row<Real>(sf, idx, lane, SF_TPA, atoms, counts, slice_ptr, col, row);
@@ -1207,8 +1247,13 @@ static int atomic_run(tab_atomic *m, tab_nbr *nbr, double *d_energy, double *d_e
         m->fown.as<double>(), m->eat.as<double>(), d_eatom, need_grad ? d_forces : nullptr,
         partial_e);
     TAB_LAUNCH_CHECK();
-    k_sf_reduce<<<1, 256, 0, st>>>(nblk_c, partial_e, need_grad ? nblk : 0, partial, d_energy,
-                                  need_grad ? d_virial : nullptr);
+    if (nbr->n_struct > 0)
+        k_sf_reduce_batch<<<nbr->n_struct, 128, 0, st>>>(
+            nbr->struct_off.as<int>(), d_energy ? m->eat.as<double>() : nullptr,
+            need_grad ? partial : nullptr, d_energy, need_grad ? d_virial : nullptr);
+    else
+        k_sf_reduce<<<1, 256, 0, st>>>(nblk_c, partial_e, need_grad ? nblk : 0, partial,
+                                      d_energy, need_grad ? d_virial : nullptr);
     TAB_LAUNCH_CHECK();
     return TAB_OK;
 }
@@ -1299,7 +1344,11 @@ static int atomic_forces_from(tab_atomic *m, tab_nbr *nbr, const double *d_dedg,
         nbr->perm.as<int>(), m->gvec.as<double>(), plane, m->fown.as<double>(),
         m->eat.as<double>(), nullptr, d_forces, partial + 8 * (size_t)nblk);
     TAB_LAUNCH_CHECK();
-    k_sf_reduce<<<1, 256, 0, st>>>(0, nullptr, nblk, partial, nullptr, d_virial);
+    if (nbr->n_struct > 0)
+        k_sf_reduce_batch<<<nbr->n_struct, 128, 0, st>>>(nbr->struct_off.as<int>(), nullptr,
+                                                         partial, nullptr, d_virial);
+    else
+        k_sf_reduce<<<1, 256, 0, st>>>(0, nullptr, nblk, partial, nullptr, d_virial);
     TAB_LAUNCH_CHECK();
     return TAB_OK;
 }
@@ -1339,7 +1388,8 @@ static int atomic_jvp(tab_atomic *m, tab_nbr *nbr, const double *d_u, const doub
         n, nbr->n_loc, sf, nbr->n_types, row_cap, nbr->atoms.as<Atom4>(),
         nbr->types_ext.as<uint8_t>(), nbr->counts.as<int>(), nbr->tcounts.as<int>(),
         nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>(), nbr->ghost_owner.as<int>(),
-        m->fown.as<double>(), d_A, m->G.as<double>());
+        m->fown.as<double>(), d_A, nbr->n_struct > 0 ? nbr->struct_of.as<int>() : nullptr,
+        m->G.as<double>());
     TAB_LAUNCH_CHECK();
     const size_t tot = (size_t)n * sf.dim;
     k_sf_export<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(

@@ -26,23 +26,25 @@ VOIGT = ((0, 0), (1, 1), (2, 2), (1, 2), (0, 2), (0, 1))
 
 
 class SfForce(torch.autograd.Function):
-    """forces [n,3] and virial [3,3] of ONE structure from c = dE/dG [n, dim]."""
+    """forces [N,3] and virials [B,3,3] of a BATCH of structures (one neighbour handle,
+    `tab_nbr_build_batch`) from c = dE/dG [N, dim]: one kernel pass over all structures."""
 
     @staticmethod
     def forward(ctx, dedg, model, nbr, precision):
         n = dedg.shape[0]
+        nb = max(nbr.n_struct, 1)
         c = dedg.detach().to(torch.float64).contiguous()
         forces = torch.empty((n, 3), dtype=torch.float64, device=c.device)
-        virial = torch.empty(9, dtype=torch.float64, device=c.device)
+        virial = torch.empty(nb * 9, dtype=torch.float64, device=c.device)
         model.forces_from_dedg(nbr, c, forces, virial, precision)
         ctx.model, ctx.nbr, ctx.precision = model, nbr, precision
         ctx.shape, ctx.dtype = dedg.shape, dedg.dtype
-        return forces.to(dedg.dtype), virial.reshape(3, 3).to(dedg.dtype)
+        return forces.to(dedg.dtype), virial.reshape(nb, 3, 3).to(dedg.dtype)
 
     @staticmethod
     def backward(ctx, g_forces, g_virial):
         u = g_forces.detach().to(torch.float64).contiguous()
-        A = g_virial.detach().to(torch.float64).contiguous().reshape(9)
+        A = g_virial.detach().to(torch.float64).contiguous().reshape(-1)
         out = torch.empty(ctx.shape, dtype=torch.float64, device=u.device)
         ctx.model.jvp(ctx.nbr, u, A, out, ctx.precision)
         return out.to(ctx.dtype), None, None, None
@@ -101,6 +103,7 @@ class AtomicNNTrainer:
                 xhi=None if p['xhi'] is None else torch.tensor(p['xhi'], dtype=self.tdtype,
                                                                device=device))
         self.structures = []
+        self._batch = None
 
     def _leaf(self, arr):
         t = torch.tensor(np.asarray(arr), dtype=self.tdtype, device=self.device,
@@ -110,22 +113,35 @@ class AtomicNNTrainer:
 
     # -- data ------------------------------------------------------------------
     def add_structure(self, atoms, energy, forces, stress):
-        """Builds the lists + descriptors of one structure (kept on the device)."""
-        clf = self.nn.transformer
-        types = clf.get_types(atoms)
-        nbr = _lib.NeighborList()
-        cell, pbc, origin = clf._cell_and_pbc(atoms)
-        d_pos = torch.tensor(np.ascontiguousarray(atoms.positions), dtype=torch.float64,
-                             device=self.device)
-        d_types = torch.tensor(types, dtype=torch.int32, device=self.device)
-        nbr.build_dd(d_pos, d_types, len(types), cell, origin, pbc,
-                     self.nn.required_cutoff())
-        G = self.model.descriptors(nbr, self.dt.tab_precision).to(self.tdtype)
+        """Queue one labelled structure of this rank's sub-batch."""
         t = lambda a: torch.tensor(np.asarray(a), dtype=self.tdtype, device=self.device)
-        self.structures.append(dict(
-            nbr=nbr, G=G, types=torch.tensor(types, dtype=torch.long, device=self.device),
-            n=len(atoms), volume=float(atoms.get_volume()), energy=t(energy),
-            forces=t(forces), stress=t(stress)))
+        self.structures.append(dict(atoms=atoms, n=len(atoms),
+                                    volume=float(atoms.get_volume()), energy=t(energy),
+                                    forces=t(forces), stress=t(stress)))
+        self._batch = None
+
+    def _ensure_batch(self):
+        """Lists + descriptors of ALL queued structures in one device handle (kept: the
+        geometry does not change during training)."""
+        if self._batch is not None:
+            return self._batch
+        clf = self.nn.transformer
+        bf = clf.get_batch_features([s['atoms'] for s in self.structures],
+                                    rc=self.nn.required_cutoff(), nbr=_lib.NeighborList())
+        G = self.model.descriptors(bf.nbr, self.dt.tab_precision).to(self.tdtype)
+        dev = self.device
+        n_atoms = torch.tensor([s['n'] for s in self.structures], device=dev)
+        self._batch = dict(
+            nbr=bf.nbr, G=G, types=torch.as_tensor(bf.types, device=dev).long(),
+            sid=torch.repeat_interleave(torch.arange(len(self.structures), device=dev),
+                                        n_atoms),
+            n_atoms=n_atoms,
+            volume=torch.tensor([s['volume'] for s in self.structures], dtype=self.tdtype,
+                                device=dev),
+            energy=torch.stack([s['energy'] for s in self.structures]),
+            forces=torch.cat([s['forces'] for s in self.structures]),
+            stress=torch.stack([s['stress'] for s in self.structures]))
+        return self._batch
 
     # -- model -------------------------------------------------------------------
     def _mlp(self, el, x):
@@ -149,42 +165,31 @@ class AtomicNNTrainer:
     def total_loss(self, want_forces=True, want_stress=True):
         """Loss of this rank's structures (reference semantics: each replica
         evaluates the loss of its own sub-batch)."""
-        S = self.structures
-        G_all = torch.cat([s['G'] for s in S]).detach().requires_grad_(True)
-        types_all = torch.cat([s['types'] for s in S])
-        sid = torch.cat([torch.full((s['n'],), k, dtype=torch.long, device=self.device)
-                         for k, s in enumerate(S)])
+        B = self._ensure_batch()
+        nb = len(self.structures)
+        G_all = B['G'].detach().requires_grad_(True)
         e_atom = torch.zeros(G_all.shape[0], dtype=self.tdtype, device=self.device)
         for a, el in enumerate(self.elements):
-            sel = torch.nonzero(types_all == a).reshape(-1)
+            sel = torch.nonzero(B['types'] == a).reshape(-1)
             if sel.numel():
                 e_atom = e_atom.index_add(0, sel, self._mlp(el, G_all[sel]))
-        E = torch.zeros(len(S), dtype=self.tdtype, device=self.device).index_add(
-            0, sid, e_atom)
-        n_atoms = torch.tensor([s['n'] for s in S], device=self.device)
-        labels_e = torch.stack([s['energy'] for s in S])
+        E = torch.zeros(nb, dtype=self.tdtype, device=self.device).index_add(
+            0, B['sid'], e_atom)
         w = self.loss_weights
-        loss = losses.energy_loss(labels_e, E, n_atoms, self.per_atom_energy, w['energy'])
+        loss = losses.energy_loss(B['energy'], E, B['n_atoms'], self.per_atom_energy,
+                                  w['energy'])
         parts = {'energy': loss.detach()}
         if want_forces or want_stress:
             dedg = torch.autograd.grad(E.sum(), G_all, create_graph=True)[0]
-            F_list, S_list = [], []
-            off = 0
-            for s in S:
-                f, W = SfForce.apply(dedg[off:off + s['n']], self.model, s['nbr'],
-                                     self.dt.tab_precision)
-                off += s['n']
-                F_list.append(f)
-                st = W / s['volume']
-                S_list.append(torch.stack([st[a, b] for a, b in VOIGT]))
+            F, W = SfForce.apply(dedg, self.model, B['nbr'], self.dt.tab_precision)
             if want_forces:
-                lf = losses.forces_loss(torch.cat([s['forces'] for s in S]),
-                                        torch.cat(F_list), w['forces'])
+                lf = losses.forces_loss(B['forces'], F, w['forces'])
                 loss = loss + lf
                 parts['forces'] = lf.detach()
             if want_stress:
-                ls = losses.stress_loss(torch.stack([s['stress'] for s in S]),
-                                        torch.stack(S_list), w['stress'])
+                st = W / B['volume'][:, None, None]
+                voigt = torch.stack([st[:, a, b] for a, b in VOIGT], dim=1)
+                ls = losses.stress_loss(B['stress'], voigt, w['stress'])
                 loss = loss + ls
                 parts['stress'] = ls.detach()
         return loss, parts

@@ -154,6 +154,41 @@ class BasicNN:
             pred['hessian'] = raw['hessian'].astype(dtype)
         return pred
 
+    def evaluate_batch(self, batch, want_forces=True, want_virial=True,
+                       want_atomic=True):
+        """One pass of the kernels over a BATCH of structures
+        (`transformer.get_batch_features(images)`): energies [B], per-atom energies and
+        forces of all atoms (split per structure), virials [B,3,3].  Returns a list of
+        `_evaluate`-style dicts (caller atom order)."""
+        import torch
+        if self.is_finite_temperature:
+            raise NotImplementedError("batched evaluation of finite-temperature models")
+        model = self._device_model()
+        nb, n = batch.n_struct, batch.n_atoms
+        f64 = dict(dtype=torch.float64, device='cuda')
+        energy = torch.zeros(nb, **f64)
+        virial = torch.zeros((nb, 9), **f64) if want_virial else None
+        eatom = torch.zeros(n, **f64) if want_atomic else None
+        forces = torch.zeros((n, 3), **f64) if want_forces else None
+        model.eval(batch.nbr, get_float_dtype().tab_precision, energy=energy,
+                   eatom=eatom, forces=forces, virial=virial)
+        energy = energy.cpu().numpy()
+        virial = virial.cpu().numpy() if want_virial else None
+        eatom = eatom.cpu().numpy() if want_atomic else None
+        forces = forces.cpu().numpy() if want_forces else None
+        out = []
+        for s in range(nb):
+            lo, hi = int(batch.offsets[s]), int(batch.offsets[s + 1])
+            raw = {'energy': energy[s]}
+            if want_atomic:
+                raw['energy/atom'] = eatom[lo:hi]
+            if want_forces:
+                raw['forces'] = forces[lo:hi]
+            if want_virial:
+                raw['virial'] = virial[s].reshape(3, 3).copy()
+            out.append(raw)
+        return out
+
     def _hessian(self, features):
         raise NotImplementedError(
             f"{self.__class__.__name__} has no analytic Hessian kernel yet")

@@ -42,6 +42,33 @@ class DeviceFeatures:
         self.n_atoms = len(types)
 
 
+class BatchDeviceFeatures:
+    """A batch of independent structures on the device: ONE neighbour handle
+    (`tab_nbr_build_batch`) instead of the reference's padded batch tensors
+    (BatchUniversalTransformer, universal.py:921-1388)."""
+
+    def __init__(self, images, vaps, types, offsets, nbr, d_pos, cells, volumes):
+        self.images = images
+        self.vaps = vaps
+        self.types = types          # int32 [N] host, all structures back to back
+        self.offsets = offsets      # int32 [B+1]
+        self.nbr = nbr
+        self.d_pos = d_pos
+        self.cells = cells          # [B,3,3] the structures' own lattices
+        self.volumes = volumes      # [B]
+        self.n_struct = len(images)
+        self.n_atoms = int(offsets[-1])
+
+    def structure(self, s):
+        """Per-structure view with the attributes `BasicNN._finalize` reads."""
+        lo, hi = int(self.offsets[s]), int(self.offsets[s + 1])
+        f = DeviceFeatures.__new__(DeviceFeatures)
+        f.atoms, f.vap, f.types = self.images[s], self.vaps[s], self.types[lo:hi]
+        f.nbr, f.d_pos, f.cell = None, None, self.cells[s]
+        f.volume, f.pbc, f.n_atoms = float(self.volumes[s]), None, hi - lo
+        return f
+
+
 class UniversalTransformer:
     """See module docstring.  Signature: universal.py:243-244."""
 
@@ -72,6 +99,7 @@ class UniversalTransformer:
         self._use_computed_dists = use_computed_dists
         self._vap_transformers: Dict[str, VirtualAtomMap] = {}
         self._nbr = None
+        self._batch_nbr = None
         self._types_cache = (None, None)
 
     # -- reference properties (universal.py:323-445) -----------------------
@@ -165,6 +193,39 @@ class UniversalTransformer:
         return DeviceFeatures(atoms, self.get_vap_transformer(atoms), types,
                               self._nbr, d_pos, real_cell.reshape(3, 3),
                               float(atoms.get_volume()), pbc)
+
+    def get_batch_features(self, images, rc=None, nbr=None) -> BatchDeviceFeatures:
+        """Neighbour lists of a list of structures in one device handle: one H2D copy
+        of the concatenated positions / types, one `tab_nbr_build_batch`."""
+        import torch
+        if nbr is None:
+            if self._batch_nbr is None:
+                self._batch_nbr = _lib.NeighborList()
+            nbr = self._batch_nbr
+        types, cells, pbcs, real_cells, vols, vaps = [], [], [], [], [], []
+        offsets = np.zeros(len(images) + 1, dtype=np.int32)
+        for s, atoms in enumerate(images):
+            t = np.array(self.get_types(atoms), copy=True)
+            types.append(t)
+            cell, pbc, _origin = self._cell_and_pbc(atoms)
+            cells.append(cell)
+            pbcs.append(pbc)
+            real_cells.append(np.asarray(atoms.get_cell(complete=True),
+                                         dtype=np.float64).reshape(3, 3))
+            vols.append(float(atoms.get_volume()))
+            vaps.append(self.get_vap_transformer(atoms))
+            offsets[s + 1] = offsets[s] + len(t)
+        pos = np.concatenate([np.asarray(a.positions, dtype=np.float64).reshape(-1, 3)
+                              for a in images])
+        types = np.concatenate(types).astype(np.int32)
+        d_pos = torch.as_tensor(np.ascontiguousarray(pos)).to('cuda', non_blocking=True)
+        d_types = torch.as_tensor(types).to('cuda', non_blocking=True)
+        if rc is None:
+            rc = max(self._rcut, self._acut) if (self._angular and self._acut) \
+                else self._rcut
+        nbr.build_batch(d_pos, d_types, offsets, np.stack(cells), np.stack(pbcs), rc)
+        return BatchDeviceFeatures(list(images), vaps, types, offsets, nbr, d_pos,
+                                   np.stack(real_cells), np.asarray(vols))
 
     # -- reference wire format (universal.py:46-112,851-893) -------------------
     def get_np_feed_dict(self, atoms):
