@@ -337,6 +337,24 @@ int tab_atomic_forces(tab_atomic *model, tab_nbr *nbr, int32_t precision,
 int tab_atomic_jvp(tab_atomic *model, tab_nbr *nbr, int32_t precision,
                    const double *d_u, const double *d_A, double *d_out, void *stream);
 
+/* Pair-level training operators of the EAM / ADP family ("PyTorch custom ops where
+ * tensors cross into training").  The reference obtains d loss / d parameters of an energy
+ * + force + stress loss from TF second-order autograd over its padded pair tensors
+ * (nn/eam/eam.py:495-570, nn/basic.py:446-631, nn/opt.py:132-157).  Here the energy is a
+ * function of the directed pair vectors D_p (one per list entry, rows sorted by centre
+ * atom, tab_nbr_export order); the force / virial assembly is LINEAR in g_p = dE/dD_p:
+ *   tab_pairs_export : d_i, d_j [nij] int32 (caller indices, either may be NULL),
+ *                      d_D [nij,3] = R_j - R_i (+ image shift)
+ *   tab_pair_forces  : F_i = sum_{p in row i} g_p - sum_{p -> i} g_p   [n,3]
+ *                      W   = sum_p sym(g_p (x) D_p)   [9], batch handles [n_struct, 9]
+ *   tab_pair_jvp     : the transpose, t_p = u_i - u_j + sym(A) D_p     [nij,3]
+ * All arrays float64 on the device; single-structure and batch handles. */
+int tab_pairs_export(tab_nbr *nbr, int32_t *d_i, int32_t *d_j, double *d_D, void *stream);
+int tab_pair_forces(tab_nbr *nbr, const double *d_g, double *d_forces, double *d_virial,
+                    void *stream);
+int tab_pair_jvp(tab_nbr *nbr, const double *d_u, const double *d_A, double *d_t,
+                 void *stream);
+
 /* Per-kernel timing of tab_eam_eval with CUDA events recorded on the launching
  * stream (used by bench.py for the roofline figures; off by default).
  * tab_profile_read synchronises the device; ms[0..3] = mean milliseconds of the

@@ -84,7 +84,20 @@ class Potential:
         self.params = params if params is not None else self.defaults()
 
     def p(self, section, key):
+        leaves = getattr(self, 'leaves', None)
+        if leaves is not None:
+            if (section, key) not in leaves:
+                leaves[(section, key)] = torch.tensor(self.params[section][key],
+                                                      dtype=self.dtype, requires_grad=True)
+            return leaves[(section, key)]
         return torch.tensor(self.params[section][key], dtype=self.dtype)
+
+    def track_parameters(self):
+        """From now on every parameter is one shared leaf tensor (requires_grad): the
+        reference's shared trainable variables, potentials.py:171-200.  Returns the dict
+        (section, key) -> leaf, filled as the functions touch their parameters."""
+        self.leaves = {}
+        return self.leaves
 
     def defaults(self):
         raise NotImplementedError

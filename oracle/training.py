@@ -93,3 +93,56 @@ def loss_and_grads(elements, structures, params, rc, sf=None, acut=None, angular
     return (float(loss.detach()), {'energy': float(le.detach()),
                                    'forces': float(lf.detach()),
                                    'stress': float(ls.detach())}, out)
+
+
+def eam_loss_and_grads(kind, elements, structures, fns, leaves_fn, rc,
+                       weights=(1.0, 1.0, 1.0), eps=1e-14):
+    """Training-step loss of an EAM / ADP model and its parameter gradients by torch
+    double-backward on the CPU (reference: TF second-order autograd, nn/opt.py:132-157).
+    fns: dict of callables rho(r, key), phi(r, key), embed(rho, el)[, dipole, quadrupole]
+    closing over leaf tensors; leaves_fn() -> {name: leaf} AFTER the forward pass (shared
+    parameters are created lazily).  Returns (loss, parts, {name: grad})."""
+    from oracle import eam as oeam
+    elements = sorted(elements)
+    dtype = torch.float64
+    E_pred, E_lab, n_at, F_pred, F_lab, S_pred, S_lab = [], [], [], [], [], [], []
+    for s in structures:
+        pos = np.asarray(s['positions'], dtype=np.float64)
+        cell = np.asarray(s['cell'], dtype=np.float64)
+        nl = neighbor.neighbor_list(pos, cell, s['pbc'], rc)
+        types = torch.tensor([elements.index(x) for x in s['symbols']])
+        R = torch.tensor(pos, dtype=dtype, requires_grad=True)
+        h = torch.tensor(cell, dtype=dtype, requires_grad=True)
+        e_atom, _ = oeam.eam_atomic_energies(
+            None, kind, elements, types, R, h, torch.from_numpy(nl[0]),
+            torch.from_numpy(nl[1]), torch.from_numpy(nl[2]), True, fns=fns)
+        e = e_atom.sum()
+        dR, dh = torch.autograd.grad(e, (R, h), create_graph=True)
+        F = -dR
+        virial = -(F.t() @ R) + dh.t() @ h               # basic.py:306-317
+        stress = virial / abs(np.linalg.det(cell))
+        voigt = torch.stack([stress[0, 0], stress[1, 1], stress[2, 2],
+                             stress[1, 2], stress[0, 2], stress[0, 1]])
+        E_pred.append(e)
+        E_lab.append(float(s['energy']))
+        n_at.append(len(pos))
+        F_pred.append(F)
+        F_lab.append(torch.tensor(np.asarray(s['forces']), dtype=dtype))
+        S_pred.append(voigt)
+        S_lab.append(torch.tensor(np.asarray(s['stress']), dtype=dtype))
+    n = torch.tensor(n_at, dtype=dtype)
+
+    def rmse(x, y):
+        return torch.sqrt(torch.mean((x - y) ** 2) + eps)
+
+    le = rmse(torch.tensor(E_lab, dtype=dtype) / n, torch.stack(E_pred) / n)
+    lf = rmse(torch.cat(F_lab), torch.cat(F_pred))
+    ls = rmse(torch.stack(S_lab), torch.stack(S_pred))
+    loss = weights[0] * le + weights[1] * lf + weights[2] * ls
+    leaves = leaves_fn()
+    names = list(leaves)
+    grads = torch.autograd.grad(loss, [leaves[k] for k in names], allow_unused=True)
+    return (float(loss.detach()),
+            {'energy': float(le.detach()), 'forces': float(lf.detach()),
+             'stress': float(ls.detach())},
+            {k: (None if g is None else g.numpy()) for k, g in zip(names, grads)})

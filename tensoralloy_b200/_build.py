@@ -6,7 +6,7 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
 CSRC = ROOT / 'tensoralloy_b200' / 'csrc'
-SOURCES = ['scan.cu', 'nbr.cu', 'eam.cu', 'sf.cu', 'hessian.cu']
+SOURCES = ['scan.cu', 'nbr.cu', 'eam.cu', 'sf.cu', 'hessian.cu', 'pairs.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3',
               '-std=c++17', '-Xcompiler', '-fPIC', '-shared']
 

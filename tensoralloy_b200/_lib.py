@@ -99,6 +99,7 @@ EXPORTS = [
     'tab_atomic_descriptors', 'tab_atomic_forces', 'tab_atomic_jvp',
     'tab_launch_count', 'tab_launch_count_reset',
     'tab_nbr_build_batch', 'tab_nbr_batch_size',
+    'tab_pairs_export', 'tab_pair_forces', 'tab_pair_jvp',
     'tab_profile_enable', 'tab_profile_read',
 ]
 
@@ -129,6 +130,9 @@ def lib():
     L.tab_nbr_build_batch.argtypes = [vp, i32, C.POINTER(i32), vp, vp, C.POINTER(dbl),
                                       C.POINTER(i32), dbl, vp]
     L.tab_nbr_batch_size.argtypes = [vp]
+    L.tab_pairs_export.argtypes = [vp, vp, vp, vp, vp]
+    L.tab_pair_forces.argtypes = [vp, vp, vp, vp, vp]
+    L.tab_pair_jvp.argtypes = [vp, vp, vp, vp, vp]
     L.tab_pack_rows.argtypes = [vp, vp, i32, i32, C.POINTER(dbl), vp, vp]
     L.tab_peer_put.argtypes = [vp, i32, vp, i32, i32, vp]
     L.tab_sum_slots.argtypes = [vp, i32, i32, vp, vp]
@@ -311,6 +315,34 @@ class NeighborList:
         check(lib().tab_nbr_export(self._h, _ptr(i), _ptr(j), _ptr(S), _stream()),
               'tab_nbr_export')
         return i[:nij], j[:nij], S[:nij]
+
+
+def _nbr_pairs(self):
+    """(i, j, D) of every list entry: cuda int32 [nij] x 2 (caller indices), float64
+    [nij,3] pair vectors, rows sorted by i (tab_pairs_export)."""
+    import torch
+    nij = self.sizes()[0]
+    i = torch.empty(max(nij, 1), dtype=torch.int32, device='cuda')
+    j = torch.empty(max(nij, 1), dtype=torch.int32, device='cuda')
+    D = torch.empty((max(nij, 1), 3), dtype=torch.float64, device='cuda')
+    check(lib().tab_pairs_export(self._h, _ptr(i), _ptr(j), _ptr(D), _stream()),
+          'tab_pairs_export')
+    return i[:nij], j[:nij], D[:nij]
+
+
+def _nbr_pair_forces(self, g, forces, virial):
+    check(lib().tab_pair_forces(self._h, _ptr(g), _ptr(forces), _ptr(virial), _stream()),
+          'tab_pair_forces')
+
+
+def _nbr_pair_jvp(self, u, A, out):
+    check(lib().tab_pair_jvp(self._h, _ptr(u), _ptr(A), _ptr(out), _stream()),
+          'tab_pair_jvp')
+
+
+NeighborList.pairs = _nbr_pairs
+NeighborList.pair_forces = _nbr_pair_forces
+NeighborList.pair_jvp = _nbr_pair_jvp
 
 
 class EamModel:

@@ -34,6 +34,7 @@ class Atoms:
         if isinstance(symbols, str):
             symbols = _parse_formula(symbols)
         self._symbols = list(symbols)
+        self.numbers = np.array([atomic_numbers[s] for s in self._symbols], dtype=np.int64)
         self.positions = np.array(positions, dtype=np.float64).reshape(-1, 3)
         if len(self._symbols) != len(self.positions):
             raise ValueError("symbols and positions differ in length")
@@ -57,7 +58,7 @@ class Atoms:
         return list(self._symbols)
 
     def get_atomic_numbers(self):
-        return np.array([atomic_numbers[s] for s in self._symbols])
+        return self.numbers.copy()
 
     def get_positions(self):
         return self.positions.copy()

@@ -240,21 +240,27 @@ class TensorAlloyCalculator(_AseCalculator):
             want_stress = bool({'stress', 'total_pressure'} & properties)
             want_forces = 'forces' in properties or want_stress
             batch = self._transformer.get_batch_features(images)
-            raws = self._nn.evaluate_batch(batch, want_forces, want_stress, True)
+            raw = self._nn.evaluate_batch(batch, want_forces, want_stress, True)
             dtype = np.float64 if self._fp_precision == 'high' else np.float32
+            energy = raw['energy'].astype(dtype)
+            eatom = raw['energy/atom'].astype(dtype)
+            forces = raw['forces'].astype(dtype) if want_forces else None
+            if want_stress:
+                stress = raw['virial'] / batch.volumes[:, None, None]
+                virial = raw['virial'].astype(dtype)
+                voigt = stress[:, [0, 1, 2, 1, 0, 0], [0, 1, 2, 2, 2, 1]].astype(dtype)
+                pressure = (np.trace(stress, axis1=1, axis2=2) / (-3.0 * GPa)).astype(dtype)
+            off = batch.offsets
             out = []
-            for s, raw in enumerate(raws):
-                res = {'energy': dtype(raw['energy']),
-                       'energy/atom': raw['energy/atom'].astype(dtype)}
+            for s in range(batch.n_struct):
+                lo, hi = off[s], off[s + 1]
+                res = {'energy': energy[s], 'energy/atom': eatom[lo:hi]}
                 if want_forces:
-                    res['forces'] = raw['forces'].astype(dtype)
+                    res['forces'] = forces[lo:hi]
                 if want_stress:
-                    stress = raw['virial'] / batch.volumes[s]
-                    res['virial'] = raw['virial'].astype(dtype)
-                    res['stress'] = np.array([stress[a, b] for a, b in
-                                              ((0, 0), (1, 1), (2, 2), (1, 2), (0, 2),
-                                               (0, 1))]).astype(dtype)
-                    res['total_pressure'] = dtype(np.trace(stress) / (-3.0 * GPa))
+                    res['virial'] = virial[s]
+                    res['stress'] = voigt[s]
+                    res['total_pressure'] = pressure[s]
                 out.append(res)
             self._ncalls += 1
         return out

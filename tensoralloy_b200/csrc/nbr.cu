@@ -1041,6 +1041,7 @@ extern "C" int tab_nbr_build_dd(tab_nbr *nbr, int32_t n_owned, int32_t n_halo,
     nbr->built = false;
     nbr->pcache_valid = false;
     nbr->n_struct = 0;          // single structure (a batch handle may be reused)
+    nbr->has_row_ptr = false;
     Grid &g = nbr->grid;
     const int n = n_owned, n_loc = (int)n_loc_ll;
     TAB_TRY(setup_grid(g, n_loc, h_cell, h_origin, h_pbc, rc));

@@ -265,6 +265,7 @@ extern "C" int tab_nbr_build_batch(tab_nbr *nbr, int32_t n_struct, const int32_t
     nbr->built = false;
     nbr->pcache_valid = false;
     nbr->has_rev = false;
+    nbr->has_row_ptr = false;
     nbr->wcap_hint = 0;
     std::vector<BStruct> hs(n_struct);
     std::vector<int> h_struct_of((size_t)N);

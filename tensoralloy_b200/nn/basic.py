@@ -158,8 +158,8 @@ class BasicNN:
                        want_atomic=True):
         """One pass of the kernels over a BATCH of structures
         (`transformer.get_batch_features(images)`): energies [B], per-atom energies and
-        forces of all atoms (split per structure), virials [B,3,3].  Returns a list of
-        `_evaluate`-style dicts (caller atom order)."""
+        forces of all atoms of the batch back to back (caller order, split them with
+        `batch.offsets`), virials [B,3,3] -- float64 numpy arrays."""
         import torch
         if self.is_finite_temperature:
             raise NotImplementedError("batched evaluation of finite-temperature models")
@@ -172,22 +172,14 @@ class BasicNN:
         forces = torch.zeros((n, 3), **f64) if want_forces else None
         model.eval(batch.nbr, get_float_dtype().tab_precision, energy=energy,
                    eatom=eatom, forces=forces, virial=virial)
-        energy = energy.cpu().numpy()
-        virial = virial.cpu().numpy() if want_virial else None
-        eatom = eatom.cpu().numpy() if want_atomic else None
-        forces = forces.cpu().numpy() if want_forces else None
-        out = []
-        for s in range(nb):
-            lo, hi = int(batch.offsets[s]), int(batch.offsets[s + 1])
-            raw = {'energy': energy[s]}
-            if want_atomic:
-                raw['energy/atom'] = eatom[lo:hi]
-            if want_forces:
-                raw['forces'] = forces[lo:hi]
-            if want_virial:
-                raw['virial'] = virial[s].reshape(3, 3).copy()
-            out.append(raw)
-        return out
+        raw = {'energy': energy.cpu().numpy()}
+        if want_virial:
+            raw['virial'] = virial.cpu().numpy().reshape(nb, 3, 3)
+        if want_atomic:
+            raw['energy/atom'] = eatom.cpu().numpy()
+        if want_forces:
+            raw['forces'] = forces.cpu().numpy()
+        return raw
 
     def _hessian(self, features):
         raise NotImplementedError(

@@ -47,9 +47,11 @@ class BatchDeviceFeatures:
     (`tab_nbr_build_batch`) instead of the reference's padded batch tensors
     (BatchUniversalTransformer, universal.py:921-1388)."""
 
-    def __init__(self, images, vaps, types, offsets, nbr, d_pos, cells, volumes):
+    def __init__(self, images, vaps, types, offsets, nbr, d_pos, cells, volumes,
+                 transformer=None):
         self.images = images
-        self.vaps = vaps
+        self.vaps = vaps            # None: built on demand by structure()
+        self._transformer = transformer
         self.types = types          # int32 [N] host, all structures back to back
         self.offsets = offsets      # int32 [B+1]
         self.nbr = nbr
@@ -63,7 +65,9 @@ class BatchDeviceFeatures:
         """Per-structure view with the attributes `BasicNN._finalize` reads."""
         lo, hi = int(self.offsets[s]), int(self.offsets[s + 1])
         f = DeviceFeatures.__new__(DeviceFeatures)
-        f.atoms, f.vap, f.types = self.images[s], self.vaps[s], self.types[lo:hi]
+        vap = self.vaps[s] if self.vaps is not None else \
+            self._transformer.get_vap_transformer(self.images[s])
+        f.atoms, f.vap, f.types = self.images[s], vap, self.types[lo:hi]
         f.nbr, f.d_pos, f.cell = None, None, self.cells[s]
         f.volume, f.pbc, f.n_atoms = float(self.volumes[s]), None, hi - lo
         return f
@@ -100,6 +104,7 @@ class UniversalTransformer:
         self._vap_transformers: Dict[str, VirtualAtomMap] = {}
         self._nbr = None
         self._batch_nbr = None
+        self._zlut = None
         self._types_cache = (None, None)
 
     # -- reference properties (universal.py:323-445) -----------------------
@@ -196,36 +201,53 @@ class UniversalTransformer:
 
     def get_batch_features(self, images, rc=None, nbr=None) -> BatchDeviceFeatures:
         """Neighbour lists of a list of structures in one device handle: one H2D copy
-        of the concatenated positions / types, one `tab_nbr_build_batch`."""
+        of the concatenated positions / types, one `tab_nbr_build_batch`.  The host side
+        is vectorised over the batch (no per-atom Python work)."""
         import torch
         if nbr is None:
             if self._batch_nbr is None:
                 self._batch_nbr = _lib.NeighborList()
             nbr = self._batch_nbr
-        types, cells, pbcs, real_cells, vols, vaps = [], [], [], [], [], []
-        offsets = np.zeros(len(images) + 1, dtype=np.int32)
-        for s, atoms in enumerate(images):
-            t = np.array(self.get_types(atoms), copy=True)
-            types.append(t)
-            cell, pbc, _origin = self._cell_and_pbc(atoms)
-            cells.append(cell)
-            pbcs.append(pbc)
-            real_cells.append(np.asarray(atoms.get_cell(complete=True),
-                                         dtype=np.float64).reshape(3, 3))
-            vols.append(float(atoms.get_volume()))
-            vaps.append(self.get_vap_transformer(atoms))
-            offsets[s + 1] = offsets[s] + len(t)
-        pos = np.concatenate([np.asarray(a.positions, dtype=np.float64).reshape(-1, 3)
-                              for a in images])
-        types = np.concatenate(types).astype(np.int32)
+        nb = len(images)
+        lens = np.fromiter((len(a) for a in images), dtype=np.int64, count=nb)
+        offsets = np.zeros(nb + 1, dtype=np.int32)
+        np.cumsum(lens, out=offsets[1:])
+        numbers = np.concatenate([a.numbers for a in images])
+        types = self._z_lut()[numbers]
+        if (types < 0).any():
+            from tensoralloy_b200.atoms import chemical_symbols
+            bad = sorted({chemical_symbols[z] for z in np.unique(numbers[types < 0])})
+            raise ValueError(f"elements {bad} are not supported by this transformer")
+        pos = np.concatenate([a.positions for a in images]).astype(np.float64, copy=False)
+        real_cells = np.stack([np.asarray(a.cell, dtype=np.float64).reshape(3, 3)
+                               for a in images])
+        pbcs = np.stack([np.asarray(a.pbc, dtype=bool).reshape(3) for a in images])
+        if not self._periodic:
+            pbcs = np.zeros_like(pbcs)
+        det = np.linalg.det(real_cells)
+        cells = real_cells.copy()
+        rmax = max(self._rcut, self._acut or 0.0)
+        for s in np.flatnonzero((np.abs(det) < 1e-12) | ~pbcs.all(axis=1)):
+            lo, hi = offsets[s], offsets[s + 1]
+            cells[s], _ = _bounding_cell(pos[lo:hi], real_cells[s], pbcs[s], rmax)
         d_pos = torch.as_tensor(np.ascontiguousarray(pos)).to('cuda', non_blocking=True)
         d_types = torch.as_tensor(types).to('cuda', non_blocking=True)
         if rc is None:
             rc = max(self._rcut, self._acut) if (self._angular and self._acut) \
                 else self._rcut
-        nbr.build_batch(d_pos, d_types, offsets, np.stack(cells), np.stack(pbcs), rc)
-        return BatchDeviceFeatures(list(images), vaps, types, offsets, nbr, d_pos,
-                                   np.stack(real_cells), np.asarray(vols))
+        nbr.build_batch(d_pos, d_types, offsets, cells, pbcs, rc)
+        return BatchDeviceFeatures(list(images), None, types, offsets, nbr, d_pos,
+                                   real_cells, np.abs(det), transformer=self)
+
+    def _z_lut(self):
+        """atomic number -> element index of this transformer (-1 = unsupported)."""
+        if self._zlut is None:
+            from tensoralloy_b200.atoms import atomic_numbers
+            lut = np.full(128, -1, dtype=np.int32)
+            for k, el in enumerate(self._elements):
+                lut[atomic_numbers[el]] = k
+            self._zlut = lut
+        return self._zlut
 
     # -- reference wire format (universal.py:46-112,851-893) -------------------
     def get_np_feed_dict(self, atoms):

@@ -54,7 +54,7 @@ def c1():
             "ms_per_call": t * 1e3, "atom_evals_per_s": 256 / t, "dtype": "f64"}
 
 
-def c2(batch):
+def c2(batch, batched=False):
     d = np.load(os.path.join(ROOT, 'tests', 'golden', 'Be_liquid_4000K.npz'))
     rng = np.random.default_rng(1)
     frames = []
@@ -72,11 +72,35 @@ def c2(batch):
     def run():
         for a in frames:
             calc.calculate(a, ['energy', 'forces', 'stress'])
-    t = timed(run, 5, warm=2)
+    if not batched:
+        t = timed(run, 5, warm=2)
+        how = "sequential calculate() calls"
+    else:
+        t = timed(lambda: calc.calculate_batch(frames, ('energy', 'forces', 'stress')), 5,
+                  warm=2)
+        how = "ONE calculate_batch() call: H2D, batch list build, E+F+stress, D2H"
     return {"config": f"C2 AtomicNN G2+G4 (eta 4, beta 1, gamma 2, zeta 2) + MLP [64,32], "
-                      f"Be 128 atoms rc=acut=5.0, batch {batch} (sequential calls)",
+                      f"Be 128 atoms rc=acut=5.0, batch {batch} ({how})",
             "ms_per_batch": t * 1e3, "structures_per_s": batch / t,
             "atom_evals_per_s": batch * 128 / t, "dtype": "f64"}
+
+
+def c1_batch(batch=256):
+    rng = np.random.default_rng(611)
+    frames = []
+    for k in range(batch):
+        atoms = bulk_fcc('Ni', 3.52, (4, 4, 4))
+        atoms.positions += rng.normal(scale=0.05, size=atoms.positions.shape)
+        frames.append(atoms)
+    nn = EamAlloyNN(['Ni'], custom_potentials='zjw04',
+                    export_properties=['energy', 'forces', 'stress'])
+    nn.attach_transformer(UniversalTransformer(['Ni'], rcut=6.5))
+    calc = TensorAlloyCalculator(nn)
+    t = timed(lambda: calc.calculate_batch(frames, ('energy', 'forces', 'stress')), 5, warm=2)
+    return {"config": f"C1 x {batch}: EAM Ni fcc 4x4x4 (256 atoms) zjw04 rc 6.5, ONE "
+                      "calculate_batch() call (H2D, batch list build, E+F+stress, D2H)",
+            "ms_per_batch": t * 1e3, "structures_per_s": batch / t,
+            "atom_evals_per_s": batch * 256 / t, "dtype": "f64"}
 
 
 def c4(n_struct=32):
@@ -120,7 +144,8 @@ def c5():
 
 def main():
     with precision_scope('high'):
-        for fn in (c1, lambda: c2(1), lambda: c2(32), lambda: c2(256), c4, c5):
+        for fn in (c1, c1_batch, lambda: c2(1), lambda: c2(32), lambda: c2(32, True),
+                   lambda: c2(256, True), c4, lambda: c4(256), c5):
             print(json.dumps(fn()), flush=True)
 
 
