@@ -57,7 +57,7 @@ def make_lattice(cells, seed=SEED):
 
 def load_traffic(kernel):
     """DRAM bytes per launch of `kernel` from the committed ncu capture (or None)."""
-    path = os.path.join(ROOT, 'profiles', 'r01h_traffic.json')
+    path = os.path.join(ROOT, 'profiles', 'r01k_traffic.json')
     try:
         with open(path) as fp:
             return json.load(fp).get(kernel)
@@ -359,10 +359,11 @@ def run_ours(args):
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "kernel_ms": {"rho_pass": kernel_ms[0], "spread": kernel_ms[1],
                               "force_pass": kernel_ms[2], "reduce": kernel_ms[3]},
-                "fp64_pipe_active_pct_ncu": 71.0,
-                "note": "float64 analytic zjw04 is FP64-pipe bound (ncu: 71% of the "
-                        "FP64 pipe's cycles active at 93 FP64 instructions per pair, DRAM "
-                        "8%; profiles/r01h_*), not HBM bound; the HBM fraction is "
+                "fp64_pipe_active_pct_ncu": 64.9,
+                "note": "float64 analytic zjw04 is bound by the FP64 pipe and the L1 "
+                        "gather path together (ncu: FP64 pipe 65% of cycles active at 83 "
+                        "FP64 instructions per pair, L1 50%, DRAM 8%, DRAM bytes within 10% "
+                        "of algorithmic; profiles/r01k_*), not by HBM; the HBM fraction is "
                         "reported as BASELINE.json asks"},
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": runner.h2d_bytes,
