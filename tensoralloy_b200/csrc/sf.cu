@@ -77,6 +77,34 @@ struct tab_atomic {
 // ---------------------------------------------------------------------------
 // cutoff functions: value and derivative  (nn/cutoff.py:20-85)
 // ---------------------------------------------------------------------------
+// sin(pi x), cos(pi x) for x in [0, 1]: quadrant folding to |theta| <= pi/4 and the
+// fdlibm kernel polynomials (|error| < 3e-18); ~20 FP64 instructions instead of the ~90
+// of the library sincos -- the cutoff of r_jk is evaluated for every neighbour PAIR.
+__device__ __forceinline__ void sincospi_unit(double x, double &sn, double &cs) {
+    const int q = (int)(x * 2.0 + 0.5);                 // 0, 1, 2
+    const double th = (x - 0.5 * (double)q) * 3.14159265358979323846;
+    const double z = th * th;
+    double ps = 1.58969099521155010221e-10;
+    ps = fma(ps, z, -2.50507602534068634195e-08);
+    ps = fma(ps, z, 2.75573137070700676789e-06);
+    ps = fma(ps, z, -1.98412698298579493134e-04);
+    ps = fma(ps, z, 8.33333333332248946124e-03);
+    ps = fma(ps, z, -1.66666666666666324348e-01);
+    const double s0 = fma(th * z, ps, th);
+    double pc = -1.13596475577881948265e-11;
+    pc = fma(pc, z, 2.08757232129817482790e-09);
+    pc = fma(pc, z, -2.75573143513906633035e-07);
+    pc = fma(pc, z, 2.48015872894767294178e-05);
+    pc = fma(pc, z, -1.38888888888741095749e-03);
+    pc = fma(pc, z, 4.16666666666666019037e-02);
+    const double c0 = fma(z * z, pc, fma(-0.5, z, 1.0));
+    sn = q == 1 ? c0 : (q == 2 ? -s0 : s0);
+    cs = q == 1 ? -s0 : (q == 2 ? -c0 : c0);
+}
+__device__ __forceinline__ void sincospi_unit(float x, float &sn, float &cs) {
+    sincospif(x, &sn, &cs);
+}
+
 template <typename Real>
 __device__ __forceinline__ void cutoff_fn(int kind, Real r, Real rc, Real &f, Real &df) {
     if (r >= rc) {
@@ -84,17 +112,17 @@ __device__ __forceinline__ void cutoff_fn(int kind, Real r, Real rc, Real &f, Re
         df = Real(0);
         return;
     }
-    const Real x = r / rc;
+    const Real rci = Real(1) / rc;          // loop invariant at every call site
+    const Real x = r * rci;
     if (kind == 0) {
-        const Real a = x * Real(3.14159265358979323846);
         Real sn, cs;
-        sincos(a, &sn, &cs);
+        sincospi_unit(x, sn, cs);
         f = Real(0.5) * (cs + Real(1));
-        df = Real(-0.5) * sn * Real(3.14159265358979323846) / rc;
+        df = Real(-0.5) * sn * Real(3.14159265358979323846) * rci;
     } else {
         const Real x2 = x * x, x4 = x2 * x2, x5 = x4 * x;
         f = Real(1) + Real(5) * x5 * x - Real(6) * x5;        // 1 + g x^(g+1) - (g+1) x^g, g=5
-        df = (Real(30) * x5 - Real(30) * x4) / rc;
+        df = (Real(30) * x5 - Real(30) * x4) * rci;
     }
 }
 
@@ -159,7 +187,7 @@ __device__ __forceinline__ void rad_fn(const SfDev &sf, int tau, Real r, Real rc
 #define GRAP_MOM_W 10
 
 // shared-memory row layout per warp: 8 doubles per neighbour
-//   0..2 D, 3 r, 4 fc(r; acut), 5 dfc(r; acut)/dr, 6 type (as double), 7 unused
+//   0..2 D, 3 r, 4 fc(r; acut), 5 dfc(r; acut)/dr, 6 type (as double), 7 1/r (0 if r = 0)
 #define ROW_W 8
 
 template <typename Real>
@@ -188,6 +216,7 @@ __device__ __forceinline__ int stage_row(const SfDev &sf, int idx, int lane, int
         e[4] = f;
         e[5] = df;
         e[6] = (double)(c >> TAB_COL_TYPE_SHIFT);
+        e[7] = r != Real(0) ? (double)(Real(1) / r) : 0.0;     // div_no_nan
     }
     __syncthreads();
     return cnt;
@@ -341,14 +370,16 @@ k_sf_forward(int n, SfDev sf, int n_types, int row_cap,
 
                     const Real jx = (Real)eq[0] - px, jy = (Real)eq[1] - py,
                                jz = (Real)eq[2] - pz;
-                    const Real r3 = sqrt(jx * jx + jy * jy + jz * jz + Math<Real>::eps());
+                    const Real d3 = jx * jx + jy * jy + jz * jz + Math<Real>::eps();
+                    const Real r3 = d3 * Math<Real>::rsqrt_(d3);
                     Real f3, df3;
                     cutoff_fn<Real>(sf.cutoff, r3, (Real)sf.acut, f3, df3);
                     if (f3 == Real(0)) continue;
                     const Real s2 = r1 * r1 + r2 * r2 + r3 * r3;
-                    const Real lower = Real(2) * r1 * r2;
-                    const Real ct = lower != Real(0)
-                                        ? (r1 * r1 + r2 * r2 - r3 * r3) / lower : Real(0);
+                    // cos(theta) = (r1^2 + r2^2 - r3^2) / (2 r1 r2) with the row's 1/r
+                    // (zero when r = 0: divide_no_nan, sf.py:150)
+                    const Real ct = (r1 * r1 + r2 * r2 - r3 * r3) *
+                                    (Real(0.5) * (Real)ep[7] * (Real)eq[7]);
                     const Real fc = fp * (fq * f3);
                     Real E = Real(0);
                     for (int tau = 0; tau < sf.n_a; ++tau) {
@@ -543,7 +574,7 @@ k_sf_backward(int n, SfDev sf, int n_types, int row_cap,
             const bool valid = a < cnt;
             const double *ea = row + (valid ? a : 0) * ROW_W;
             const Real ax = (Real)ea[0], ay = (Real)ea[1], az = (Real)ea[2], ra = (Real)ea[3];
-            const Real fa = (Real)ea[4], dfa = (Real)ea[5];
+            const Real fa = (Real)ea[4], dfa = (Real)ea[5], ira = (Real)ea[7];
             const int ta = (int)ea[6];
             Real sa = Real(0), wx = Real(0), wy = Real(0), wz = Real(0);
             if (valid && sf.angular && fa != Real(0)) {
@@ -555,7 +586,9 @@ k_sf_backward(int n, SfDev sf, int n_types, int row_cap,
                     const Real rb = (Real)eb[3];
                     const Real jx = ax - (Real)eb[0], jy = ay - (Real)eb[1],
                                jz = az - (Real)eb[2];
-                    const Real rab = sqrt(jx * jx + jy * jy + jz * jz + Math<Real>::eps());
+                    const Real dab = jx * jx + jy * jy + jz * jz + Math<Real>::eps();
+                    const Real irab = Math<Real>::rsqrt_(dab);
+                    const Real rab = dab * irab;
                     Real fab, dfab;
                     cutoff_fn<Real>(sf.cutoff, rab, (Real)sf.acut, fab, dfab);
                     if (fab == Real(0)) continue;
@@ -564,11 +597,11 @@ k_sf_backward(int n, SfDev sf, int n_types, int row_cap,
                                             : pair_term(tb, ta, sf.n_el);
                     const double *cc = c + sf.d_r + pt * sf.n_a;
                     const Real s2 = ra * ra + rb * rb + rab * rab;
-                    const Real lower = Real(2) * ra * rb;
-                    const Real ct = lower != Real(0)
-                                        ? (ra * ra + rb * rb - rab * rab) / lower : Real(0);
-                    const Real dct_da = lower != Real(0) ? Real(1) / rb - ct / ra : Real(0);
-                    const Real dct_dab = lower != Real(0) ? -rab / (ra * rb) : Real(0);
+                    // reciprocals from the row (0 when r = 0: divide_no_nan)
+                    const Real irb = (Real)eb[7], iab2 = ira * irb;
+                    const Real ct = (ra * ra + rb * rb - rab * rab) * (Real(0.5) * iab2);
+                    const Real dct_da = iab2 != Real(0) ? irb - ct * ira : Real(0);
+                    const Real dct_dab = -rab * iab2;
                     const Real F3 = fa * fb * fab;
                     Real va = Real(0), vab = Real(0), E = Real(0);
                     for (int tau = 0; tau < sf.n_a; ++tau) {
@@ -587,7 +620,7 @@ k_sf_backward(int n, SfDev sf, int n_types, int row_cap,
                                     PE * fa * fb * dfab);
                     }
                     sa += va;
-                    const Real q = vab / rab;
+                    const Real q = vab * irab;
                     wx += q * jx;
                     wy += q * jy;
                     wz += q * jz;
@@ -608,7 +641,7 @@ k_sf_backward(int n, SfDev sf, int n_types, int row_cap,
                 Real f, df;
                 cutoff_fn<Real>(sf.cutoff, ra, rc, f, df);
                 const int term = radial_term(ti, ta);
-                const Real ri = ra != Real(0) ? Real(1) / ra : Real(0);
+                const Real ri = ira;
                 const Real ux = ax * ri, uy = ay * ri, uz = az * ri;
                 for (int tau = 0; tau < sf.n_r; ++tau) {
                     Real v, dv;
@@ -649,7 +682,7 @@ k_sf_backward(int n, SfDev sf, int n_types, int row_cap,
                     }
                 }
             }
-            const Real q = (s_r + sa) / ra;
+            const Real q = (s_r + sa) * ira;
             const Real gx = q * ax + wx, gy = q * ay + wy, gz = q * az + wz;
             const size_t e = ebase + (size_t)a * 32u;
             gvec[e] = (double)gx;
@@ -885,8 +918,9 @@ k_sf_jvp(int n, int n_loc, SfDev sf, int n_types, int row_cap,
                 if (fp == Real(0)) continue;
                 const Real px = (Real)ep[0], py = (Real)ep[1], pz = (Real)ep[2],
                            r1 = (Real)ep[3];
+                const Real ir1 = (Real)ep[7];
                 const Real s1 = (px * (Real)dd[p * 4] + py * (Real)dd[p * 4 + 1] +
-                                 pz * (Real)dd[p * 4 + 2]) / r1;
+                                 pz * (Real)dd[p * 4 + 2]) * ir1;
                 const int q0 = (a == b) ? p + 1 : seg[b];
                 for (int q = q0 + lane; q < seg[b + 1]; q += SF_TPA) {
                     const double *eq = row + q * ROW_W;
@@ -895,22 +929,25 @@ k_sf_jvp(int n, int n_loc, SfDev sf, int n_types, int row_cap,
                     const Real qx = (Real)eq[0], qy = (Real)eq[1], qz = (Real)eq[2],
                                r2 = (Real)eq[3];
                     const Real jx = qx - px, jy = qy - py, jz = qz - pz;
-                    const Real r3 = sqrt(jx * jx + jy * jy + jz * jz + Math<Real>::eps());
+                    const Real d3 = jx * jx + jy * jy + jz * jz + Math<Real>::eps();
+                    const Real ir3 = Math<Real>::rsqrt_(d3);
+                    const Real r3 = d3 * ir3;
                     Real f3, df3;
                     cutoff_fn<Real>(sf.cutoff, r3, (Real)sf.acut, f3, df3);
                     if (f3 == Real(0)) continue;
+                    const Real ir2 = (Real)eq[7];
                     const Real s2 = (qx * (Real)dd[q * 4] + qy * (Real)dd[q * 4 + 1] +
-                                     qz * (Real)dd[q * 4 + 2]) / r2;
+                                     qz * (Real)dd[q * 4 + 2]) * ir2;
                     const Real s3 = (jx * ((Real)dd[q * 4] - (Real)dd[p * 4]) +
                                      jy * ((Real)dd[q * 4 + 1] - (Real)dd[p * 4 + 1]) +
-                                     jz * ((Real)dd[q * 4 + 2] - (Real)dd[p * 4 + 2])) / r3;
+                                     jz * ((Real)dd[q * 4 + 2] - (Real)dd[p * 4 + 2])) * ir3;
                     const Real ss = r1 * r1 + r2 * r2 + r3 * r3;
-                    const Real lower = Real(2) * r1 * r2;
-                    const bool ok = lower != Real(0);
-                    const Real ct = ok ? (r1 * r1 + r2 * r2 - r3 * r3) / lower : Real(0);
-                    const Real dc1 = ok ? Real(1) / r2 - ct / r1 : Real(0);
-                    const Real dc2 = ok ? Real(1) / r1 - ct / r2 : Real(0);
-                    const Real dc3 = ok ? -r3 / (r1 * r2) : Real(0);
+                    const Real i12 = ir1 * ir2;
+                    const bool ok = i12 != Real(0);
+                    const Real ct = (r1 * r1 + r2 * r2 - r3 * r3) * (Real(0.5) * i12);
+                    const Real dc1 = ok ? ir2 - ct * ir1 : Real(0);
+                    const Real dc2 = ok ? ir1 - ct * ir2 : Real(0);
+                    const Real dc3 = -r3 * i12;
                     const Real F3 = fp * fq * f3;
                     // directional derivative of the geometry-only factors
                     const Real dct = dc1 * s1 + dc2 * s2 + dc3 * s3;
