@@ -1,0 +1,76 @@
+"""CPU checks of the oracle pieces that have no golden in the reference (they only build
+graphs there): the EAM training-step gradients against central finite differences of the
+oracle loss, and the temperature-dependent heads' algebra / variable names."""
+import numpy as np
+import torch
+
+from oracle import atomic as oat
+from oracle import potentials as opot
+from oracle import training as otr
+from tensoralloy_b200.atoms import bulk_fcc
+from tensoralloy_b200.nn.atomic import BeNN, SymmetryFunction, TemperatureDependentAtomicNN
+from tensoralloy_b200.transformer import UniversalTransformer
+
+
+def _structures():
+    rng = np.random.default_rng(2)
+    base = bulk_fcc('Ni', 3.55, (2, 2, 2))
+    sym = ['Mo' if x < 0.4 else 'Ni' for x in rng.random(len(base))]
+    pos = base.positions + rng.normal(scale=0.08, size=base.positions.shape)
+    return [dict(symbols=sym, positions=pos, cell=base.cell, pbc=[1, 1, 1],
+                 energy=-4.2 * len(base), forces=rng.normal(scale=0.2, size=pos.shape),
+                 stress=rng.normal(scale=0.01, size=6))]
+
+
+def test_eam_training_gradients_match_finite_differences():
+    structs = _structures()
+
+    def run(shift=None):
+        zj = opot.get_potential('zjw04')
+        leaves = zj.track_parameters()
+        if shift:
+            (sec, key), dv = shift
+            zj.params = {k: dict(v) for k, v in zj.params.items()}
+            zj.params[sec][key] = zj.params[sec][key] + dv
+        fns = {'rho': zj.rho, 'phi': zj.phi, 'embed': zj.embed}
+        return otr.eam_loss_and_grads('alloy', ['Mo', 'Ni'], structs, fns,
+                                      lambda: {f"{s}/{k}": t for (s, k), t in leaves.items()},
+                                      5.0)
+    loss, parts, grads = run()
+    assert np.isfinite(loss) and parts['forces'] > 0
+    for sec, key in (('Ni', 'A'), ('Mo', 'beta'), ('Ni', 'r_eq'), ('Mo', 'F1')):
+        h = 1e-6
+        lp = run(((sec, key), +h))[0]
+        lm = run(((sec, key), -h))[0]
+        fd = (lp - lm) / (2 * h)
+        g = float(grads[f"{sec}/{key}"])
+        assert abs(fd - g) < 2e-5 * max(1.0, abs(g)), (sec, key, fd, g)
+
+
+def test_td_heads_algebra_and_variable_names():
+    nn = TemperatureDependentAtomicNN(
+        ['Be'], SymmetryFunction(['Be']), hidden_sizes=[8, 8],
+        finite_temperature=dict(activation='tanh', layers=[12, 6], algo='Sommerfeld'))
+    nn.attach_transformer(UniversalTransformer(['Be'], rcut=5.0, angular=True))
+    nn.initialize_variables(seed=1)
+    names = set(nn.variables)
+    for head, layers in (('H', 1), ('S', 2), ('U', 2)):
+        for k in range(layers):
+            assert f"TD/Be/{head}/Conv1d{k + 1}/kernel" in names
+        assert f"TD/Be/{head}/Output/kernel" in names
+    assert nn.variables['TD/Be/H/Output/kernel'].shape[-1] == 6
+    assert nn.variables['TD/Be/S/Conv1d1/kernel'].shape[-2] == 7     # [H, T]
+    assert nn.is_finite_temperature and nn.variational_energy == 'free_energy'
+    assert nn.as_dict()['finite_temperature']['algo'] == 'Sommerfeld'
+    x = torch.rand(5, nn._dim(), dtype=torch.float64)
+    p = nn.td_params('Be')
+    U, S, F = oat.td_heads(x, 0.3, p, torch.float64)
+    assert torch.allclose(F, U - 0.3 * S)
+    p0 = dict(p, algo='default')
+    S0 = oat.td_heads(x, 0.3, p0, torch.float64)[1]
+    assert torch.allclose(S, 0.3 * S0)                                # Sommerfeld: S = T * net
+    be = BeNN(['Be'], SymmetryFunction(['Be']), hidden_sizes=[8])
+    be.attach_transformer(UniversalTransformer(['Be'], rcut=5.0, angular=True))
+    be.initialize_variables(seed=1)
+    assert 'TD/Be/S/Output/bias' not in be.variables               # beryllium.py:66
+    assert 'TD/Be/U/Output/bias' in be.variables
