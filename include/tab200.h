@@ -320,6 +320,21 @@ int tab_atomic_eval(tab_atomic *model, tab_nbr *nbr, int32_t precision,
                     double *d_energy, double *d_eatom, double *d_forces,
                     double *d_virial, void *stream);
 
+/* Spatial decomposition of AtomicNN.  The force on an owned atom i holds
+ * dE_j/dR_i of every centre j within rc, and with angular functions dE_j/dR_i needs the
+ * whole neighbourhood of j: the lists are built (tab_nbr_build_dd) with
+ *   "owned" group = the rank's own atoms followed by the INNER halo (atoms of other ranks
+ *                   within rc of the slab), whose descriptors / MLP / per-pair gradients are
+ *                   recomputed redundantly on this rank,
+ *   halo group    = the OUTER halo (rc .. 2 rc), positions only,
+ * so ONE position exchange per step suffices (no exchange of dE/dG or ghost forces).
+ * d_mask [n_owned_group] int32, caller order: 1 = own atom, 0 = inner halo.  d_energy /
+ * d_virial receive this rank's partial sums over the own atoms; d_forces / d_eatom
+ * [n_owned_group, .] are valid in the rows of the own atoms. */
+int tab_atomic_eval_dd(tab_atomic *model, tab_nbr *nbr, int32_t precision,
+                       const int32_t *d_mask, double *d_energy, double *d_eatom,
+                       double *d_forces, double *d_virial, void *stream);
+
 /* Raw descriptors, d_desc [n, dim] float64 in caller atom order. */
 int tab_atomic_descriptors(tab_atomic *model, tab_nbr *nbr, int32_t precision,
                            double *d_desc, void *stream);

@@ -99,7 +99,7 @@ EXPORTS = [
     'tab_atomic_descriptors', 'tab_atomic_forces', 'tab_atomic_jvp',
     'tab_launch_count', 'tab_launch_count_reset',
     'tab_nbr_build_batch', 'tab_nbr_batch_size',
-    'tab_pairs_export', 'tab_pair_forces', 'tab_pair_jvp',
+    'tab_pairs_export', 'tab_pair_forces', 'tab_pair_jvp', 'tab_atomic_eval_dd',
     'tab_profile_enable', 'tab_profile_read',
 ]
 
@@ -157,6 +157,7 @@ def lib():
     L.tab_atomic_dim.argtypes = [vp]
     L.tab_atomic_eval.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]
     L.tab_atomic_descriptors.argtypes = [vp, vp, i32, vp, vp]
+    L.tab_atomic_eval_dd.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, vp]
     L.tab_atomic_forces.argtypes = [vp, vp, i32, vp, vp, vp, vp]
     L.tab_atomic_jvp.argtypes = [vp, vp, i32, vp, vp, vp, vp]
     L.tab_profile_enable.argtypes = [i32]
@@ -510,6 +511,14 @@ class AtomicModel:
         check(lib().tab_atomic_eval(self._h, nbr.handle, int(precision), _ptr(energy),
                                     _ptr(eatom), _ptr(forces), _ptr(virial),
                                     _stream()), 'tab_atomic_eval')
+
+    def eval_dd(self, nbr, mask, precision=PRECISION_HIGH, energy=None, eatom=None,
+                forces=None, virial=None):
+        """Spatial decomposition: lists built with build_dd over [own | inner halo] +
+        outer halo; `mask` (cuda int32) marks the own atoms (tab_atomic_eval_dd)."""
+        check(lib().tab_atomic_eval_dd(self._h, nbr.handle, int(precision), _ptr(mask),
+                                       _ptr(energy), _ptr(eatom), _ptr(forces),
+                                       _ptr(virial), _stream()), 'tab_atomic_eval_dd')
 
     def forces_from_dedg(self, nbr, dedg, forces, virial, precision=PRECISION_HIGH):
         check(lib().tab_atomic_forces(self._h, nbr.handle, int(precision), _ptr(dedg),

@@ -800,6 +800,43 @@ k_sf_reduce_batch(const int *__restrict__ struct_off, const double *__restrict__
     }
 }
 
+// spatial decomposition: only the atoms with mask[caller index] != 0 (the rank's OWN atoms;
+// the other rows belong to the inner halo and are recomputed by their owner ranks) count
+// towards this rank's partial energy / virial
+__global__ void __launch_bounds__(256)
+k_sf_reduce_masked(int n, const int *__restrict__ perm, const int *__restrict__ mask,
+                   const double *__restrict__ eat, const double *__restrict__ partial,
+                   double *__restrict__ energy, double *__restrict__ virial) {
+    __shared__ double sm[256][7];
+    double a[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (int i = threadIdx.x; i < n; i += 256) {
+        if (!mask[perm[i]]) continue;
+        a[0] += eat[i];
+        if (partial)
+#pragma unroll
+            for (int q = 1; q < 7; ++q) a[q] += partial[(size_t)i * 8 + q];
+    }
+#pragma unroll
+    for (int q = 0; q < 7; ++q) sm[threadIdx.x][q] = a[q];
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (threadIdx.x < w)
+#pragma unroll
+            for (int q = 0; q < 7; ++q) sm[threadIdx.x][q] += sm[threadIdx.x + w][q];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        if (energy) energy[0] = sm[0][0];
+        if (virial) {
+            const double xx = sm[0][1], yy = sm[0][2], zz = sm[0][3], yz = sm[0][4],
+                         xz = sm[0][5], xy = sm[0][6];
+            virial[0] = xx; virial[1] = xy; virial[2] = xz;
+            virial[3] = xy; virial[4] = yy; virial[5] = yz;
+            virial[6] = xz; virial[7] = yz; virial[8] = zz;
+        }
+    }
+}
+
 // fixed-order final sums: energy from partial_e[nb_e], virial from partial[nb_v*8+1..6]
 __global__ void __launch_bounds__(256)
 k_sf_reduce(int nb_e, const double *__restrict__ partial_e, int nb_v,
@@ -1172,11 +1209,16 @@ extern "C" int tab_atomic_dim(const tab_atomic *m) { return m ? m->sf.dim : 0; }
 template <typename Real>
 static int atomic_run(tab_atomic *m, tab_nbr *nbr, double *d_energy, double *d_eatom,
                       double *d_forces, double *d_virial, double *d_desc,
-                      cudaStream_t st) {
+                      cudaStream_t st, const int *d_mask = nullptr) {
     const int n = nbr->n;
     const SfDev &sf = m->sf;
-    if (nbr->n_halo > 0) {
-        tab_set_error("AtomicNN with halo atoms (domain decomposition) is not supported");
+    if (nbr->n_halo > 0 && !d_mask && !d_desc) {
+        tab_set_error("AtomicNN on lists with halo atoms: use tab_atomic_eval_dd "
+                      "(the rows of the inner halo must be masked out of the sums)");
+        return TAB_EUNSUPPORTED;
+    }
+    if (d_mask && nbr->n_struct > 0) {
+        tab_set_error("tab_atomic_eval_dd: batch handles are not decomposed");
         return TAB_EUNSUPPORTED;
     }
     if (nbr->n_types > sf.n_el) {
@@ -1284,7 +1326,11 @@ static int atomic_run(tab_atomic *m, tab_nbr *nbr, double *d_energy, double *d_e
         m->fown.as<double>(), m->eat.as<double>(), d_eatom, need_grad ? d_forces : nullptr,
         partial_e);
     TAB_LAUNCH_CHECK();
-    if (nbr->n_struct > 0)
+    if (d_mask)
+        k_sf_reduce_masked<<<1, 256, 0, st>>>(n, nbr->perm.as<int>(), d_mask,
+                                             m->eat.as<double>(), need_grad ? partial : nullptr,
+                                             d_energy, need_grad ? d_virial : nullptr);
+    else if (nbr->n_struct > 0)
         k_sf_reduce_batch<<<nbr->n_struct, 128, 0, st>>>(
             nbr->struct_off.as<int>(), d_energy ? m->eat.as<double>() : nullptr,
             need_grad ? partial : nullptr, d_energy, need_grad ? d_virial : nullptr);
@@ -1310,6 +1356,24 @@ extern "C" int tab_atomic_eval(tab_atomic *m, tab_nbr *nbr, int32_t precision,
     if (precision == TAB_PRECISION_HIGH)
         return atomic_run<double>(m, nbr, d_energy, d_eatom, d_forces, d_virial, nullptr, st);
     return atomic_run<float>(m, nbr, d_energy, d_eatom, d_forces, d_virial, nullptr, st);
+}
+
+extern "C" int tab_atomic_eval_dd(tab_atomic *m, tab_nbr *nbr, int32_t precision,
+                                  const int32_t *d_mask, double *d_energy, double *d_eatom,
+                                  double *d_forces, double *d_virial, void *stream) {
+    if (!m || !nbr || !d_mask) {
+        tab_set_error("tab_atomic_eval_dd: null argument");
+        return TAB_EINVAL;
+    }
+    if (!nbr->built) {
+        tab_set_error("tab_atomic_eval_dd before tab_nbr_build_dd");
+        return TAB_ESTATE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (precision == TAB_PRECISION_HIGH)
+        return atomic_run<double>(m, nbr, d_energy, d_eatom, d_forces, d_virial, nullptr, st,
+                                  d_mask);
+    return atomic_run<float>(m, nbr, d_energy, d_eatom, d_forces, d_virial, nullptr, st, d_mask);
 }
 
 extern "C" int tab_atomic_descriptors(tab_atomic *m, tab_nbr *nbr, int32_t precision,
