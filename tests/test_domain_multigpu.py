@@ -24,3 +24,15 @@ def test_two_rank_slabs(peer):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert 'FAIL' not in res.stdout
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2,
+                    reason="needs two GPUs")
+def test_two_rank_atomic_nn_slabs():
+    """AtomicNN decomposition (2 rc halo, NCCL send/recv ring; tools/dd_atomic_check.py)."""
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1',
+           '--nproc-per-node', '2', '--master-addr', '127.0.0.1', '--master-port', '29543',
+           os.path.join(ROOT, 'tools', 'dd_atomic_check.py'), '12', '3']
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert 'FAIL' not in res.stdout
