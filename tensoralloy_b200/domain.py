@@ -378,6 +378,12 @@ class SlabDomain:
         """Capture the resident-list step (kernels, peer stores, barriers, reduction)
         in one CUDA graph.  Returns True when the capture worked."""
         import torch
+        if self.peer is None and self.layout.world > 1:
+            # NCCL point-to-point inside a stream capture is not robust (a capture that
+            # fails on one rank leaves the ring waiting): the fallback path runs eagerly
+            self.graph = None
+            self.graph_error = "graph capture needs the peer-memory path"
+            return False
         try:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())

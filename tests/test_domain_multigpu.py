@@ -21,7 +21,7 @@ def test_two_rank_slabs(peer):
            '--nproc-per-node', '2', '--master-addr', '127.0.0.1', '--master-port',
            '29541' if peer == '1' else '29542', os.path.join(ROOT, 'tools', 'dd_check.py'),
            '8']
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=env, cwd=ROOT)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert 'FAIL' not in res.stdout
 
@@ -33,6 +33,6 @@ def test_two_rank_atomic_nn_slabs():
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1',
            '--nproc-per-node', '2', '--master-addr', '127.0.0.1', '--master-port', '29543',
            os.path.join(ROOT, 'tools', 'dd_atomic_check.py'), '12', '3']
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=240, cwd=ROOT)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert 'FAIL' not in res.stdout
