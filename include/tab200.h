@@ -223,6 +223,17 @@ int tab_eam_pass2(tab_model *model, tab_nbr *nbr, int32_t precision,
                   const double *d_fprime_halo, double *d_energy, double *d_eatom,
                   double *d_forces, double *d_virial, void *stream);
 
+/* Spatial decomposition without a second exchange: lists built by tab_nbr_build_dd over
+ * [own atoms | inner halo (<= rc from the slab)] as the row-owning group + the outer halo
+ * (rc .. 2 rc); rho, F', ADP moments and forces of the inner halo are recomputed on this
+ * rank; d_mask [n_owned_group] (int32, caller order, 1 = own atom) keeps them out of the
+ * partial energy / virial.  This is the decomposition path of ADP (no moment exchange
+ * exists) and an alternative to tab_eam_pass1/pass2 for EAM / FS.  d_forces / d_eatom are
+ * valid in the rows of the own atoms. */
+int tab_eam_eval_dd(tab_model *model, tab_nbr *nbr, int32_t precision,
+                    const int32_t *d_mask, double *d_energy, double *d_eatom,
+                    double *d_forces, double *d_virial, void *stream);
+
 /* Analytic Hessian d2E/dR_a dR_b of an EAM / FS model (float64 only):
  * d_hessian [n,3,n,3] in caller atom order.  Replaces tf.hessians(E, R) of
  * BasicNN._get_hessian_op (nn/basic.py:410-421). */

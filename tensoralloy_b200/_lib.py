@@ -99,7 +99,7 @@ EXPORTS = [
     'tab_atomic_descriptors', 'tab_atomic_forces', 'tab_atomic_jvp',
     'tab_launch_count', 'tab_launch_count_reset',
     'tab_nbr_build_batch', 'tab_nbr_batch_size',
-    'tab_pairs_export', 'tab_pair_forces', 'tab_pair_jvp', 'tab_atomic_eval_dd',
+    'tab_pairs_export', 'tab_pair_forces', 'tab_pair_jvp', 'tab_atomic_eval_dd', 'tab_eam_eval_dd',
     'tab_profile_enable', 'tab_profile_read',
 ]
 
@@ -158,6 +158,7 @@ def lib():
     L.tab_atomic_eval.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]
     L.tab_atomic_descriptors.argtypes = [vp, vp, i32, vp, vp]
     L.tab_atomic_eval_dd.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, vp]
+    L.tab_eam_eval_dd.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, vp]
     L.tab_atomic_forces.argtypes = [vp, vp, i32, vp, vp, vp, vp]
     L.tab_atomic_jvp.argtypes = [vp, vp, i32, vp, vp, vp, vp]
     L.tab_profile_enable.argtypes = [i32]
@@ -388,6 +389,13 @@ class EamModel:
         check(lib().tab_eam_eval(self._h, nbr.handle, int(precision), _ptr(energy),
                                  _ptr(eatom), _ptr(forces), _ptr(virial),
                                  _stream()), 'tab_eam_eval')
+
+    def eval_dd(self, nbr, mask, precision=PRECISION_HIGH, energy=None, eatom=None,
+                forces=None, virial=None):
+        """Decomposed evaluation with recomputed inner-halo rows (tab_eam_eval_dd)."""
+        check(lib().tab_eam_eval_dd(self._h, nbr.handle, int(precision), _ptr(mask),
+                                    _ptr(energy), _ptr(eatom), _ptr(forces), _ptr(virial),
+                                    _stream()), 'tab_eam_eval_dd')
 
     def pass1(self, nbr, precision, fprime=None):
         check(lib().tab_eam_pass1(self._h, nbr.handle, int(precision), _ptr(fprime),

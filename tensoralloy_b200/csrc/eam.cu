@@ -229,7 +229,8 @@ __global__ void k_spread_w(int n_owned, int n_loc, int n_ext,
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_ext) return;
     const int o = e < n_loc ? e : ghost_owner[e - n_loc];
-    atoms[e].w = o < n_owned ? v[o] : halo_v[perm[o] - n_owned];
+    // halo_v == NULL (recompute mode): F' of the outer halo is never needed by an own atom
+    atoms[e].w = o < n_owned ? v[o] : (halo_v ? halo_v[perm[o] - n_owned] : 0.0);
 }
 
 // ---------------------------------------------------------------------------
@@ -243,7 +244,8 @@ k_eam_force(int n, const Atom4 *__restrict__ atoms,
             const int *__restrict__ perm, EamDev m, Zhou1 z,
             const double *__restrict__ fembed, double *__restrict__ eatom,
             double *__restrict__ forces, double *__restrict__ partial,
-            const double2 *__restrict__ pcache, const int *__restrict__ blk_first) {
+            const double2 *__restrict__ pcache, const int *__restrict__ blk_first,
+            const int *__restrict__ own_mask) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     tab_fn *tabs = reinterpret_cast<tab_fn *>(smem_raw);
     __shared__ double red[EAM_T / 32][7];
@@ -335,6 +337,10 @@ k_eam_force(int n, const Atom4 *__restrict__ atoms,
         acc[4] = 0.5 * (double)vyz;
         acc[5] = 0.5 * (double)vxz;
         acc[6] = 0.5 * (double)vxy;
+        // spatial decomposition with recomputed inner-halo rows: only own atoms count
+        if (own_mask && !own_mask[o])
+#pragma unroll
+            for (int q = 0; q < 7; ++q) acc[q] = 0.0;
     }
 #pragma unroll
     for (int q = 0; q < 7; ++q) {
@@ -430,13 +436,15 @@ k_adp_rho(int n, const Atom4 *__restrict__ atoms,
     fembed[idx] = (double)(F + eadp);
 }
 
-// moments of halo atoms are not exchanged yet: ADP runs single-domain only
-__global__ void k_adp_spread(int n_owned, int n_ext, int stride,
+// moments of the library's periodic images (records [n_loc, n_ext)) = their source atom's;
+// halo atoms [n, n_loc) keep zeros (decomposition: tab_eam_eval_dd recomputes the inner halo
+// as part of the row-owning group, the outer halo's moments are never read by an own atom)
+__global__ void k_adp_spread(int n_loc, int n_ext, int stride,
                              const int *__restrict__ ghost_owner,
                              double *__restrict__ moments) {
-    const int e = n_owned + blockIdx.x * blockDim.x + threadIdx.x;
+    const int e = n_loc + blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_ext) return;
-    const int o = ghost_owner[e - n_owned];
+    const int o = ghost_owner[e - n_loc];
     for (int k = 0; k < stride; ++k)
         moments[(size_t)e * stride + k] = moments[(size_t)o * stride + k];
 }
@@ -449,7 +457,8 @@ k_adp_force(int n, const Atom4 *__restrict__ atoms,
             const int *__restrict__ perm, EamDev m,
             const double *__restrict__ moments, const double *__restrict__ fembed,
             double *__restrict__ eatom, double *__restrict__ forces,
-            double *__restrict__ partial, const int *__restrict__ blk_first) {
+            double *__restrict__ partial, const int *__restrict__ blk_first,
+            const int *__restrict__ own_mask) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     tab_fn *tabs = reinterpret_cast<tab_fn *>(smem_raw);
     __shared__ double red[EAM_T / 32][7];
@@ -556,6 +565,9 @@ k_adp_force(int n, const Atom4 *__restrict__ atoms,
         acc[4] = (double)vyz;
         acc[5] = (double)vxz;
         acc[6] = (double)vxy;
+        if (own_mask && !own_mask[o])
+#pragma unroll
+            for (int q = 0; q < 7; ++q) acc[q] = 0.0;
     }
 #pragma unroll
     for (int q = 0; q < 7; ++q) {
@@ -914,10 +926,10 @@ static int eam_pass1(tab_model *m, tab_nbr *nbr, double *d_fprime_caller,
 template <typename Real, bool FAST>
 static int eam_pass2(tab_model *m, tab_nbr *nbr, const double *d_fprime_halo,
                      double *d_energy, double *d_eatom, double *d_forces,
-                     double *d_virial, cudaStream_t st) {
+                     double *d_virial, cudaStream_t st, const int *d_own_mask = nullptr) {
     EamLaunch L;
     TAB_TRY(eam_prepare(m, nbr, FAST, L, st));
-    if (nbr->n_halo > 0 && !d_fprime_halo) {
+    if (nbr->n_halo > 0 && !d_fprime_halo && !d_own_mask) {
         tab_set_error("tab_eam_pass2: halo atoms present but no halo F' given");
         return TAB_EINVAL;
     }
@@ -933,19 +945,19 @@ static int eam_pass2(tab_model *m, tab_nbr *nbr, const double *d_fprime_halo,
             nbr->n, nbr->atoms.as<Atom4>(), nbr->types_ext.as<uint8_t>(),
             nbr->counts.as<int>(), nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>(),
             nbr->perm.as<int>(), L.dev, L.z, L.fembed, d_eatom, d_forces,
-            nbr->partial.as<double>(), nbr->pcache.as<double2>(), L.blk_first);
+            nbr->partial.as<double>(), nbr->pcache.as<double2>(), L.blk_first, d_own_mask);
     else if (!FAST && m->has_mlp_fn)
         k_eam_force<Real, false, false, true><<<L.nblk, EAM_T, L.smem, st>>>(
             nbr->n, nbr->atoms.as<Atom4>(), nbr->types_ext.as<uint8_t>(),
             nbr->counts.as<int>(), nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>(),
             nbr->perm.as<int>(), L.dev, L.z, L.fembed, d_eatom, d_forces,
-            nbr->partial.as<double>(), nullptr, L.blk_first);
+            nbr->partial.as<double>(), nullptr, L.blk_first, d_own_mask);
     else
         k_eam_force<Real, FAST, false, false><<<L.nblk, EAM_T, L.smem, st>>>(
             nbr->n, nbr->atoms.as<Atom4>(), nbr->types_ext.as<uint8_t>(),
             nbr->counts.as<int>(), nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>(),
             nbr->perm.as<int>(), L.dev, L.z, L.fembed, d_eatom, d_forces,
-            nbr->partial.as<double>(), nullptr, L.blk_first);
+            nbr->partial.as<double>(), nullptr, L.blk_first, d_own_mask);
     TAB_LAUNCH_CHECK();
     prof_mark(3, st);
     if (d_energy || d_virial) {
@@ -959,16 +971,19 @@ static int eam_pass2(tab_model *m, tab_nbr *nbr, const double *d_fprime_halo,
 }
 
 template <typename Real>
-static int adp_pass1(tab_model *m, tab_nbr *nbr, cudaStream_t st) {
+static int adp_pass1(tab_model *m, tab_nbr *nbr, cudaStream_t st, bool recompute = false) {
     EamLaunch L;
     TAB_TRY(eam_prepare(m, nbr, false, L, st));
-    if (nbr->n_halo > 0) {
-        tab_set_error("ADP with halo atoms (domain decomposition) is not supported");
+    if (nbr->n_halo > 0 && !recompute) {
+        tab_set_error("ADP on lists with halo atoms: use tab_eam_eval_dd (inner-halo rows "
+                      "recomputed, no moment exchange)");
         return TAB_EUNSUPPORTED;
     }
     const int nn = m->n_el * m->n_el, stride = m->n_el * 9;
     L.smem = (size_t)(4 * nn + m->n_el) * sizeof(tab_fn);
     TAB_TRY(nbr->adp.ensure(sizeof(double) * (size_t)nbr->n_ext * stride));
+    if (nbr->n_halo > 0)     // outer-halo moments are never computed: keep them finite
+        TAB_CUDA(cudaMemsetAsync(nbr->adp.p, 0, sizeof(double) * (size_t)nbr->n_ext * stride, st));
     prof_mark(0, st);
     auto kr = m->has_mlp_fn ? k_adp_rho<Real, true> : k_adp_rho<Real, false>;
     kr<<<L.nblk, EAM_T, L.smem, st>>>(
@@ -976,9 +991,9 @@ static int adp_pass1(tab_model *m, tab_nbr *nbr, cudaStream_t st) {
         nbr->counts.as<int>(), nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>(),
         L.dev, L.fprime, L.fembed, nbr->adp.as<double>(), L.blk_first);
     TAB_LAUNCH_CHECK();
-    if (nbr->n_ext > nbr->n) {
-        k_adp_spread<<<(nbr->n_ext - nbr->n + 255) / 256, 256, 0, st>>>(
-            nbr->n, nbr->n_ext, stride, nbr->ghost_owner.as<int>(), nbr->adp.as<double>());
+    if (nbr->n_ext > nbr->n_loc) {
+        k_adp_spread<<<(nbr->n_ext - nbr->n_loc + 255) / 256, 256, 0, st>>>(
+            nbr->n_loc, nbr->n_ext, stride, nbr->ghost_owner.as<int>(), nbr->adp.as<double>());
         TAB_LAUNCH_CHECK();
     }
     prof_mark(1, st);
@@ -987,7 +1002,8 @@ static int adp_pass1(tab_model *m, tab_nbr *nbr, cudaStream_t st) {
 
 template <typename Real>
 static int adp_pass2(tab_model *m, tab_nbr *nbr, double *d_energy, double *d_eatom,
-                     double *d_forces, double *d_virial, cudaStream_t st) {
+                     double *d_forces, double *d_virial, cudaStream_t st,
+                     const int *d_own_mask = nullptr) {
     EamLaunch L;
     TAB_TRY(eam_prepare(m, nbr, false, L, st));
     const int nn = m->n_el * m->n_el;
@@ -1002,7 +1018,7 @@ static int adp_pass2(tab_model *m, tab_nbr *nbr, double *d_energy, double *d_eat
         nbr->n, nbr->atoms.as<Atom4>(), nbr->types_ext.as<uint8_t>(),
         nbr->counts.as<int>(), nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>(),
         nbr->perm.as<int>(), L.dev, nbr->adp.as<double>(), L.fembed, d_eatom, d_forces,
-        nbr->partial.as<double>(), L.blk_first);
+        nbr->partial.as<double>(), L.blk_first, d_own_mask);
     TAB_LAUNCH_CHECK();
     prof_mark(3, st);
     if (d_energy || d_virial) {
@@ -1082,6 +1098,35 @@ extern "C" int tab_eam_eval(tab_model *m, tab_nbr *nbr, int32_t precision,
     TAB_TRY(tab_eam_pass1(m, nbr, precision, nullptr, stream));
     return tab_eam_pass2(m, nbr, precision, nullptr, d_energy, d_eatom, d_forces,
                          d_virial, stream);
+}
+
+// Spatial decomposition WITHOUT a second exchange (see include/tab200.h): lists over
+// [own | inner halo] + outer halo, inner-halo rows recomputed, own_mask keeps them out of
+// the rank's energy / virial sums.  Serves ADP (whose F' + moment exchange is not built)
+// and is an alternative to tab_eam_pass1/pass2 for EAM / FS.
+extern "C" int tab_eam_eval_dd(tab_model *m, tab_nbr *nbr, int32_t precision,
+                               const int32_t *d_mask, double *d_energy, double *d_eatom,
+                               double *d_forces, double *d_virial, void *stream) {
+    TAB_TRY(check_handles(m, nbr, "tab_eam_eval_dd"));
+    if (!d_mask) {
+        tab_set_error("tab_eam_eval_dd: null mask");
+        return TAB_EINVAL;
+    }
+    if (nbr->n_struct > 0) {
+        tab_set_error("tab_eam_eval_dd: batch handles are not decomposed");
+        return TAB_EUNSUPPORTED;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (m->kind == TAB_EAM_ADP) {
+        if (precision == TAB_PRECISION_HIGH) {
+            TAB_TRY(adp_pass1<double>(m, nbr, st, true));
+            return adp_pass2<double>(m, nbr, d_energy, d_eatom, d_forces, d_virial, st, d_mask);
+        }
+        TAB_TRY(adp_pass1<float>(m, nbr, st, true));
+        return adp_pass2<float>(m, nbr, d_energy, d_eatom, d_forces, d_virial, st, d_mask);
+    }
+    TAB_TRY(tab_eam_pass1(m, nbr, precision, nullptr, stream));
+    EAM_DISPATCH(eam_pass2, m, nbr, nullptr, d_energy, d_eatom, d_forces, d_virial, st, d_mask);
 }
 
 // Host-buffer convenience: see include/tab200.h.

@@ -14,6 +14,10 @@ and ONE position exchange per step suffices.  The lists are built by `tab_nbr_bu
 [own | inner halo] as the row-owning group; `tab_atomic_eval_dd` masks the inner-halo rows
 out of the rank's energy / virial sums; [E, virial] is one 10-double all-reduce.
 
+The same scheme serves the EAM family through `tab_eam_eval_dd` (`EamModel.eval_dd`): it is
+the decomposition path of ADP, whose per-species moments would otherwise need their own
+exchange, and an alternative to the F' exchange of domain.py for EAM / FS.
+
 `AtomicSlabRank` is comm-agnostic (one rank's device state); `run_loopback` runs all ranks
 inside one process on one GPU (test harness); `AtomicSlabDomain` is the torch.distributed
 (NCCL send/recv ring) driver.

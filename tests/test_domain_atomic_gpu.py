@@ -53,6 +53,41 @@ def test_atomic_nn_slab_decomposition_matches_single_domain(world):
         assert np.abs(ea - ea0).max() < 1e-11
 
 
+@pytest.mark.parametrize("world", [2, 3])
+def test_adp_and_eam_recompute_decomposition(world):
+    """ADP (two species: per-term moments) and EAM through the same 2 rc / recompute path
+    (tab_eam_eval_dd): no F' or moment exchange."""
+    from tensoralloy_b200.nn.eam import AdpNN, EamAlloyNN
+    rng = np.random.default_rng(21)
+    base = bulk_fcc('Ni', 3.6, (11, 3, 3))
+    sym = ['Mo' if x < 0.45 else 'Ni' for x in rng.random(len(base))]
+    pos = base.positions + rng.normal(scale=0.08, size=base.positions.shape)
+    pos[:, 0] -= 0.777
+    atoms = Atoms(sym, pos, base.cell, True)
+    rc = 6.0
+    cp = {'Mo': {'rho': 'zjw04', 'embed': 'zjw04'}, 'Ni': {'rho': 'zjw04', 'embed': 'zjw04'},
+          'MoMo': {'phi': 'zjw04', 'dipole': 'mishinh', 'quadrupole': 'mishinh'},
+          'MoNi': {'phi': 'zjw04', 'dipole': 'mishinh', 'quadrupole': 'mishinh'},
+          'NiNi': {'phi': 'zjw04', 'dipole': 'mishinh', 'quadrupole': 'mishinh'}}
+    with precision_scope('high'):
+        for nn in (AdpNN(['Mo', 'Ni'], custom_potentials=cp,
+                         export_properties=('energy', 'forces', 'stress')),
+                   EamAlloyNN(['Mo', 'Ni'], custom_potentials='zjw04',
+                              export_properties=('energy', 'forces', 'stress'))):
+            nn.attach_transformer(UniversalTransformer(['Mo', 'Ni'], rcut=rc))
+            calc = TensorAlloyCalculator(nn)
+            calc.calculate(atoms, properties=['energy', 'forces', 'stress'])
+            e0, f0, w0 = calc.results['energy'], calc.get_forces(atoms), calc.results['virial']
+            types = nn.transformer.get_types(atoms)
+            e, f, w, _ = run_loopback(nn._device_model(), pos, types, np.asarray(atoms.cell),
+                                      rc, world, precision=0)
+            n = len(atoms)
+            assert abs(e - e0) / n < 1e-12, type(nn).__name__
+            assert np.abs(f - f0).max() < 1e-10, type(nn).__name__
+            assert np.abs(w - w0).max() / n < 1e-11, type(nn).__name__
+            assert np.abs(f0).max() > 1e-2
+
+
 def test_layout_rejects_too_narrow_slabs():
     with pytest.raises(ValueError):
         AtomicSlabLayout(20.0, 4, 0, 4.6)      # width 5 < 2 rc
