@@ -232,6 +232,8 @@ class TensorAlloyCalculator(_AseCalculator):
         universal.py:921-1388); this is the inference-side equivalent.  Returns one dict
         per structure: 'energy', 'forces' [N,3] in the structure's own (ASE) atom order,
         'stress' [6] Voigt eV/A^3, 'energy/atom' [N]."""
+        if self._nn.is_finite_temperature:
+            raise NotImplementedError("batched evaluation of finite-temperature models")
         with precision_scope(self._fp_precision):
             properties = set(properties)
             for prop in properties:
@@ -246,7 +248,8 @@ class TensorAlloyCalculator(_AseCalculator):
             eatom = raw['energy/atom'].astype(dtype)
             forces = raw['forces'].astype(dtype) if want_forces else None
             if want_stress:
-                stress = raw['virial'] / batch.volumes[:, None, None]
+                with np.errstate(divide='ignore', invalid='ignore'):   # clusters: V = 0
+                    stress = raw['virial'] / batch.volumes[:, None, None]
                 virial = raw['virial'].astype(dtype)
                 voigt = stress[:, [0, 1, 2, 1, 0, 0], [0, 1, 2, 2, 2, 1]].astype(dtype)
                 pressure = (np.trace(stress, axis1=1, axis2=2) / (-3.0 * GPa)).astype(dtype)

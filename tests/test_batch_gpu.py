@@ -197,3 +197,53 @@ def test_atomic_nn_two_species_batch():
                                  minmax_scale=False, hidden_sizes=[32, 32],
                                  export_properties=('energy', 'forces', 'stress'))),
         lambda: UniversalTransformer(['Mo', 'Ni'], rcut=4.6, acut=4.0, angular=True), images)
+
+
+def test_batch_edge_cases_and_errors():
+    """Ragged / degenerate inputs: a one-structure batch, an isolated atom (no neighbours),
+    a non-periodic cluster next to periodic crystals; error behaviour of the reference
+    (unsupported element -> ValueError, universal.py:280-282) and of the C ABI."""
+    with precision_scope('high'):
+        nn = EamAlloyNN(['Ni'], custom_potentials='zjw04',
+                        export_properties=('energy', 'forces', 'stress'))
+        nn.attach_transformer(UniversalTransformer(['Ni'], rcut=6.5))
+        calc = TensorAlloyCalculator(nn)
+        crystal = _rattled('Ni', 3.52, (3, 3, 3), 31)
+        lonely = Atoms(['Ni'], [[5.0, 5.0, 5.0]], np.diag([30.0, 30.0, 30.0]), True)
+        rng = np.random.default_rng(3)
+        cluster = Atoms(['Ni'] * 13, 2.2 * rng.normal(size=(13, 3)), np.zeros((3, 3)), False)
+        images = [crystal, lonely, cluster]
+        res = calc.calculate_batch(images, properties=('energy', 'forces', 'stress'))
+        for s, atoms in enumerate(images):
+            calc.calculate(atoms, properties=['energy', 'forces'])
+            assert abs(res[s]['energy'] - calc.results['energy']) < 1e-11 * max(1, len(atoms))
+            assert np.abs(res[s]['forces'] - calc.get_forces(atoms)).max() < 1e-11
+        assert np.abs(res[1]['forces']).max() == 0.0          # no neighbours at all
+        one = calc.calculate_batch([crystal], properties=('energy', 'forces'))
+        assert abs(one[0]['energy'] - res[0]['energy']) < 1e-11
+        with pytest.raises(ValueError):
+            calc.calculate_batch([crystal, Atoms(['Cu'], [[0, 0, 0]], np.eye(3) * 9, True)])
+        with pytest.raises(KeyError):
+            calc.calculate_batch([crystal], properties=('energy', 'dipole_moment'))
+    # C ABI: empty structure, update on a batch handle
+    nl = _lib.NeighborList()
+    pos = torch.tensor(crystal.positions, dtype=torch.float64, device='cuda')
+    with pytest.raises(_lib.TabError):
+        nl.build_batch(pos, None, np.array([0, 0, len(crystal)], dtype=np.int32),
+                       np.stack([crystal.cell, crystal.cell]), np.ones((2, 3), bool), 6.5)
+    nl.build_batch(pos, None, np.array([0, len(crystal)], dtype=np.int32),
+                   crystal.cell[None], np.ones((1, 3), bool), 6.5)
+    with pytest.raises(_lib.TabError):
+        nl.update(pos)
+
+
+def test_batch_rejects_finite_temperature_models():
+    from tensoralloy_b200.nn.atomic import TemperatureDependentAtomicNN
+    with precision_scope('high'):
+        nn = TemperatureDependentAtomicNN(['Be'], SymmetryFunction(['Be']), hidden_sizes=[8],
+                                          finite_temperature=dict(layers=[8, 4]))
+        nn.attach_transformer(UniversalTransformer(['Be'], rcut=5.0, angular=True))
+        d = np.load(os.path.join(GOLD, 'Be_liquid_4000K.npz'))
+        atoms = Atoms(list(d['symbols']), d['positions'][1], d['cells'][1], True)
+        with pytest.raises(NotImplementedError):
+            TensorAlloyCalculator(nn).calculate_batch([atoms])
