@@ -51,8 +51,15 @@ class Atoms:
         return len(self._symbols)
 
     def copy(self):
-        return Atoms(self._symbols, self.positions.copy(), self.cell.copy(),
-                     self.pbc.copy(), info=dict(self.info))
+        new = Atoms.__new__(Atoms)      # no per-atom symbol work
+        new._symbols = list(self._symbols)
+        new.numbers = self.numbers.copy()
+        new.positions = self.positions.copy()
+        new.cell = self.cell.copy()
+        new.pbc = self.pbc.copy()
+        new.info = dict(self.info)
+        new.calc = None
+        return new
 
     def get_chemical_symbols(self):
         return list(self._symbols)
