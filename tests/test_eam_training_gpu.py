@@ -146,3 +146,18 @@ def test_adp_all_nn_parameter_gradients():
                 scale = 0.02 if ('Dipole' in name or 'Quadrupole' in name) else 0.2
                 nn.set_variable(name, value * scale)
         _check(nn, 'adp', structs)
+
+
+def test_eam_fs_all_nn_parameter_gradients():
+    """Finnis-Sinclair: rho is a function of the ORDERED pair (fs.py:180-203)."""
+    from tensoralloy_b200.nn.eam import EamFsNN
+    structs = make_structures(2, seed=8)
+    with precision_scope('high'):
+        nn = EamFsNN(ELEMENTS, hidden_sizes=[8, 6],
+                     minimize_properties=('energy', 'forces', 'stress'))
+        nn.attach_transformer(UniversalTransformer(ELEMENTS, rcut=RC))
+        nn.initialize_variables(seed=9)
+        for name, value in list(nn.variables.items()):
+            if name.endswith('Output/kernel'):
+                nn.set_variable(name, value * 0.2)
+        _check(nn, 'fs', structs)
