@@ -156,26 +156,4 @@ class AtomicNN(BasicNN):
         return g.cpu().numpy()
 
     def _evaluate(self, features, want_forces, want_virial, want_atomic):
-        import torch
-        model = self._device_model()
-        n = features.n_atoms
-        if self._out is None or self._out['n'] != n:
-            self._out = {
-                'n': n,
-                'scal': torch.zeros(16, dtype=torch.float64, device='cuda'),
-                'eatom': torch.zeros(n, dtype=torch.float64, device='cuda'),
-                'forces': torch.zeros((n, 3), dtype=torch.float64, device='cuda')}
-        o = self._out
-        model.eval(features.nbr, get_float_dtype().tab_precision,
-                   energy=o['scal'][0:1], eatom=o['eatom'] if want_atomic else None,
-                   forces=o['forces'] if want_forces else None,
-                   virial=o['scal'][1:10] if want_virial else None)
-        scal = o['scal'].cpu().numpy()
-        raw = {'energy': scal[0]}
-        if want_atomic:
-            raw['energy/atom'] = o['eatom'].cpu().numpy()
-        if want_forces:
-            raw['forces'] = o['forces'].cpu().numpy()
-        if want_virial:
-            raw['virial'] = scal[1:10].reshape(3, 3).copy()
-        return raw
+        return self._evaluate_single(features, want_forces, want_virial, want_atomic)

@@ -154,31 +154,56 @@ class BasicNN:
             pred['hessian'] = raw['hessian'].astype(dtype)
         return pred
 
+    def _eval_flat(self, nbr, n, nb, want_forces, want_virial, want_atomic):
+        """Run `model.eval` with every output in ONE device buffer
+        [energy nb | virial 9 nb | E_atom n | forces 3 n] and bring it back with a single
+        device->host copy (one synchronisation per call instead of one per array)."""
+        import torch
+        model = self._device_model()
+        size = 10 * nb + 4 * n
+        buf = getattr(self, '_flat_out', None)
+        if buf is None or buf.numel() != size:
+            buf = torch.zeros(size, dtype=torch.float64, device='cuda')
+            self._flat_out = buf
+        o_v, o_e, o_f = nb, 10 * nb, 10 * nb + n
+        model.eval(nbr, get_float_dtype().tab_precision, energy=buf[0:nb],
+                   eatom=buf[o_e:o_f] if want_atomic else None,
+                   forces=buf[o_f:].view(n, 3) if want_forces else None,
+                   virial=buf[o_v:o_e] if want_virial else None)
+        host = buf.cpu().numpy()
+        return (host[0:nb], host[o_v:o_e].reshape(nb, 3, 3), host[o_e:o_f],
+                host[o_f:].reshape(n, 3))
+
     def evaluate_batch(self, batch, want_forces=True, want_virial=True,
                        want_atomic=True):
         """One pass of the kernels over a BATCH of structures
         (`transformer.get_batch_features(images)`): energies [B], per-atom energies and
         forces of all atoms of the batch back to back (caller order, split them with
         `batch.offsets`), virials [B,3,3] -- float64 numpy arrays."""
-        import torch
         if self.is_finite_temperature:
             raise NotImplementedError("batched evaluation of finite-temperature models")
-        model = self._device_model()
-        nb, n = batch.n_struct, batch.n_atoms
-        f64 = dict(dtype=torch.float64, device='cuda')
-        energy = torch.zeros(nb, **f64)
-        virial = torch.zeros((nb, 9), **f64) if want_virial else None
-        eatom = torch.zeros(n, **f64) if want_atomic else None
-        forces = torch.zeros((n, 3), **f64) if want_forces else None
-        model.eval(batch.nbr, get_float_dtype().tab_precision, energy=energy,
-                   eatom=eatom, forces=forces, virial=virial)
-        raw = {'energy': energy.cpu().numpy()}
+        e, w, ea, f = self._eval_flat(batch.nbr, batch.n_atoms, batch.n_struct,
+                                      want_forces, want_virial, want_atomic)
+        raw = {'energy': e}
         if want_virial:
-            raw['virial'] = virial.cpu().numpy().reshape(nb, 3, 3)
+            raw['virial'] = w
         if want_atomic:
-            raw['energy/atom'] = eatom.cpu().numpy()
+            raw['energy/atom'] = ea
         if want_forces:
-            raw['forces'] = forces.cpu().numpy()
+            raw['forces'] = f
+        return raw
+
+    def _evaluate_single(self, features, want_forces, want_virial, want_atomic):
+        """`_evaluate` of the models whose device handle has an `eval` entry point."""
+        e, w, ea, f = self._eval_flat(features.nbr, features.n_atoms, 1, want_forces,
+                                      want_virial, want_atomic)
+        raw = {'energy': e[0]}
+        if want_atomic:
+            raw['energy/atom'] = ea.copy()
+        if want_forces:
+            raw['forces'] = f.copy()
+        if want_virial:
+            raw['virial'] = w[0].copy()
         return raw
 
     def _hessian(self, features):
