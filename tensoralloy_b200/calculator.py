@@ -231,9 +231,8 @@ class TensorAlloyCalculator(_AseCalculator):
         batch call (its batches exist only inside the tf.data training pipeline,
         universal.py:921-1388); this is the inference-side equivalent.  Returns one dict
         per structure: 'energy', 'forces' [N,3] in the structure's own (ASE) atom order,
-        'stress' [6] Voigt eV/A^3, 'energy/atom' [N]."""
-        if self._nn.is_finite_temperature:
-            raise NotImplementedError("batched evaluation of finite-temperature models")
+        'stress' [6] Voigt eV/A^3, 'energy/atom' [N] (+ 'eentropy', 'free_energy' for
+        finite-temperature models, whose forces derive from the free energy)."""
         with precision_scope(self._fp_precision):
             properties = set(properties)
             for prop in properties:
@@ -250,14 +249,18 @@ class TensorAlloyCalculator(_AseCalculator):
             if want_stress:
                 with np.errstate(divide='ignore', invalid='ignore'):   # clusters: V = 0
                     stress = raw['virial'] / batch.volumes[:, None, None]
+                    pressure = (np.trace(stress, axis1=1, axis2=2) /
+                                (-3.0 * GPa)).astype(dtype)
                 virial = raw['virial'].astype(dtype)
                 voigt = stress[:, [0, 1, 2, 1, 0, 0], [0, 1, 2, 2, 2, 1]].astype(dtype)
-                pressure = (np.trace(stress, axis1=1, axis2=2) / (-3.0 * GPa)).astype(dtype)
             off = batch.offsets
             out = []
             for s in range(batch.n_struct):
                 lo, hi = off[s], off[s + 1]
                 res = {'energy': energy[s], 'energy/atom': eatom[lo:hi]}
+                for key in ('eentropy', 'free_energy'):      # finite-temperature models
+                    if key in raw:
+                        res[key] = dtype(raw[key][s])
                 if want_forces:
                     res['forces'] = forces[lo:hi]
                 if want_stress:

@@ -204,17 +204,18 @@ class TemperatureDependentAtomicNN(AtomicNN):
             S = S * T
         return S
 
-    def _evaluate(self, features, want_forces, want_virial, want_atomic):
+    def _run(self, nbr, types, t_atom, sid, nb, want_grad):
+        """Shared core of the single-structure and the batched evaluation.  t_atom: per-atom
+        electron temperature (cuda); sid: structure of each atom or None.  Returns per-atom
+        U, S, F (float64 numpy), per-structure sums, and forces / virials [nb, 9]."""
         import torch
         dt = get_float_dtype()
         tdtype = torch.float64 if dt.name == 'float64' else torch.float32
         model = self._device_model()
-        nbr = features.nbr
-        n = features.n_atoms
-        etemp = float(features.atoms.info.get('etemperature', 0.0))
+        n = int(types.shape[0])
         G = model.descriptors(nbr, dt.tab_precision).to(tdtype).requires_grad_(True)
-        types = torch.as_tensor(np.asarray(features.types), device='cuda').long()
         heads_all = self._torch_heads(tdtype)
+        t_atom = t_atom.to(tdtype)
         U = torch.zeros(n, dtype=tdtype, device='cuda')
         S = torch.zeros(n, dtype=tdtype, device='cuda')
         for a, el in enumerate(self._elements):
@@ -227,25 +228,65 @@ class TemperatureDependentAtomicNN(AtomicNN):
                 den = hd['xhi'] - hd['xlo']
                 x = torch.where(den == 0, torch.zeros_like(x), (hd['xhi'] - x) / den)
             H = self._net(hd['H'], x)
-            T = torch.full((x.shape[0],), etemp, dtype=tdtype, device='cuda')
+            T = t_atom[sel]
             Ht = torch.cat([H, T[:, None]], dim=1)
             U = U.index_add(0, sel, self._net(hd['U'], Ht)[:, 0])
             S = S.index_add(0, sel, self._entropy(hd, Ht, T))
-        F = U - etemp * S
-        raw = {}
-        if want_forces or want_virial:
+        F = U - t_atom * S
+        forces = virial = None
+        if want_grad:
             dedg = torch.autograd.grad(F.sum(), G)[0].to(torch.float64).contiguous()
             forces = torch.empty((n, 3), dtype=torch.float64, device='cuda')
-            virial = torch.empty(9, dtype=torch.float64, device='cuda')
+            virial = torch.empty(nb * 9, dtype=torch.float64, device='cuda')
             model.forces_from_dedg(nbr, dedg, forces, virial, dt.tab_precision)
-            if want_forces:
-                raw['forces'] = forces.cpu().numpy()
-            if want_virial:
-                raw['virial'] = virial.cpu().numpy().reshape(3, 3).copy()
-        U, S, F = (v.detach().to(torch.float64).cpu().numpy() for v in (U, S, F))
-        raw.update({'energy': U.sum(), 'eentropy': S.sum(), 'free_energy': F.sum()})
+        per_atom = torch.stack([U.detach(), S.detach(), F.detach()]).to(torch.float64)
+        if sid is None:
+            sums = per_atom.sum(dim=1, keepdim=True)
+        else:
+            sums = torch.zeros((3, nb), dtype=torch.float64, device='cuda').index_add(
+                1, sid, per_atom)
+        return (per_atom.cpu().numpy(), sums.cpu().numpy(),
+                None if forces is None else forces.cpu().numpy(),
+                None if virial is None else virial.cpu().numpy().reshape(nb, 3, 3))
+
+    def _evaluate(self, features, want_forces, want_virial, want_atomic):
+        import torch
+        n = features.n_atoms
+        etemp = float(features.atoms.info.get('etemperature', 0.0))
+        types = torch.as_tensor(np.asarray(features.types), device='cuda').long()
+        t_atom = torch.full((n,), etemp, dtype=torch.float64, device='cuda')
+        per_atom, sums, forces, virial = self._run(features.nbr, types, t_atom, None, 1,
+                                                   want_forces or want_virial)
+        raw = {'energy': sums[0, 0], 'eentropy': sums[1, 0], 'free_energy': sums[2, 0]}
+        if want_forces:
+            raw['forces'] = forces
+        if want_virial:
+            raw['virial'] = virial[0].copy()
         if want_atomic:
-            raw.update({'energy/atom': U, 'eentropy/atom': S, 'free_energy/atom': F})
+            raw.update({'energy/atom': per_atom[0], 'eentropy/atom': per_atom[1],
+                        'free_energy/atom': per_atom[2]})
+        return raw
+
+    def evaluate_batch(self, batch, want_forces=True, want_virial=True, want_atomic=True):
+        """Batched evaluation (one neighbour handle, `tab_nbr_build_batch`): every
+        structure carries its own electron temperature (`atoms.info['etemperature']`)."""
+        import torch
+        nb = batch.n_struct
+        lens = np.diff(batch.offsets)
+        sid = torch.as_tensor(np.repeat(np.arange(nb), lens), device='cuda').long()
+        temps = np.array([float(a.info.get('etemperature', 0.0)) for a in batch.images])
+        t_atom = torch.as_tensor(np.repeat(temps, lens), device='cuda')
+        types = torch.as_tensor(np.asarray(batch.types), device='cuda').long()
+        per_atom, sums, forces, virial = self._run(batch.nbr, types, t_atom, sid, nb,
+                                                   want_forces or want_virial)
+        raw = {'energy': sums[0], 'eentropy': sums[1], 'free_energy': sums[2]}
+        if want_forces:
+            raw['forces'] = forces
+        if want_virial:
+            raw['virial'] = virial
+        if want_atomic:
+            raw.update({'energy/atom': per_atom[0], 'eentropy/atom': per_atom[1],
+                        'free_energy/atom': per_atom[2]})
         return raw
 
     def _finalize(self, raw, features, properties):

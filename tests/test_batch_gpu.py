@@ -237,13 +237,33 @@ def test_batch_edge_cases_and_errors():
         nl.update(pos)
 
 
-def test_batch_rejects_finite_temperature_models():
-    from tensoralloy_b200.nn.atomic import TemperatureDependentAtomicNN
+def test_finite_temperature_batch_matches_single_calls():
+    from tensoralloy_b200.nn.atomic import BeNN, TemperatureDependentAtomicNN
+    d = np.load(os.path.join(GOLD, 'Be_liquid_4000K.npz'))
+    images = []
+    for k, temp in ((2, 0.34469373), (1, 0.2), (2, 0.05)):
+        a = Atoms(list(d['symbols']), d['positions'][k], d['cells'][k], True)
+        a.info['etemperature'] = temp
+        images.append(a)
+    props = ('energy', 'forces', 'stress', 'eentropy', 'free_energy')
     with precision_scope('high'):
-        nn = TemperatureDependentAtomicNN(['Be'], SymmetryFunction(['Be']), hidden_sizes=[8],
-                                          finite_temperature=dict(layers=[8, 4]))
-        nn.attach_transformer(UniversalTransformer(['Be'], rcut=5.0, angular=True))
-        d = np.load(os.path.join(GOLD, 'Be_liquid_4000K.npz'))
-        atoms = Atoms(list(d['symbols']), d['positions'][1], d['cells'][1], True)
-        with pytest.raises(NotImplementedError):
-            TensorAlloyCalculator(nn).calculate_batch([atoms])
+        for cls in (TemperatureDependentAtomicNN, BeNN):
+            nn = cls(['Be'], SymmetryFunction(['Be']), hidden_sizes=[16, 16],
+                     minmax_scale=False, export_properties=props,
+                     finite_temperature=dict(layers=[16, 8]))
+            nn.attach_transformer(UniversalTransformer(['Be'], rcut=5.0, angular=True))
+            nn.initialize_variables(seed=4)
+            for head in ('U', 'S'):
+                key = f"TD/Be/{head}/Output/kernel"
+                nn.set_variable(key, nn.get_variable(key) * 0.2)
+            key = "TD/Be/H/Conv1d1/kernel"
+            nn.set_variable(key, nn.get_variable(key) * 0.2)
+            calc = TensorAlloyCalculator(nn)
+            batch = calc.calculate_batch(images, properties=props)
+            for s, atoms in enumerate(images):
+                calc.calculate(atoms, properties=list(props))
+                for key in ('energy', 'eentropy', 'free_energy'):
+                    assert abs(batch[s][key] - calc.results[key]) < 1e-10, (cls.__name__, key)
+                assert np.abs(batch[s]['forces'] - calc.get_forces(atoms)).max() < 1e-11
+                assert np.abs(batch[s]['stress'] - calc.get_stress(atoms)).max() < 1e-11
+            assert abs(batch[0]['eentropy'] - batch[2]['eentropy']) > 1e-6   # T matters
