@@ -356,7 +356,10 @@ int tab_atomic_descriptors(tab_atomic *model, tab_nbr *nbr, int32_t precision,
  *   tab_atomic_jvp    : T = d/dc [ sum_a F_a.u_a + sum_ab A_ab W_ab ]  (its transpose;
  *                       d_u [n,3], d_A [9] on the device, d_out [n, dim])
  * so a force / stress loss back-propagates to the network parameters through c --
- * what the reference obtains from TF second-order autograd (nn/opt.py:132-157). */
+ * what the reference obtains from TF second-order autograd (nn/opt.py:132-157).  Symmetry
+ * functions and the GRAP families with moments 0, 1, 2 (the moment sums of the lists are
+ * recomputed inside the call); single-structure and batch handles (d_virial / d_A per
+ * structure). */
 int tab_atomic_forces(tab_atomic *model, tab_nbr *nbr, int32_t precision,
                       const double *d_dedg, double *d_forces, double *d_virial,
                       void *stream);

@@ -15,7 +15,7 @@ from oracle import neighbor
 
 
 def loss_and_grads(elements, structures, params, rc, sf=None, acut=None, angular=True,
-                   minmax=None, weights=(1.0, 1.0, 1.0), eps=1e-14):
+                   minmax=None, weights=(1.0, 1.0, 1.0), eps=1e-14, grap=None):
     """structures: list of dict(symbols, positions, cell, pbc, energy, forces, stress).
     params[el]: dict(weights=[np], biases=[np or None], activation, use_resnet_dt,
     out_bias).  Returns (loss, {el: ([dW...], [db...])})."""
@@ -38,8 +38,13 @@ def loss_and_grads(elements, structures, params, rc, sf=None, acut=None, angular
         types = np.array([elements.index(x) for x in s['symbols']])
         R = torch.tensor(pos, dtype=dtype, requires_grad=True)
         h = torch.tensor(cell, dtype=dtype, requires_grad=True)
-        G = oat.descriptors(elements, types, R, h, nl[0], nl[1], nl[2], rc,
-                            acut if acut else rc, angular, **sf)
+        if grap is not None:      # GenericRadialAtomicPotential (nn/atomic/grap.py:384-466)
+            G = oat.grap_descriptors(elements, types, R, h, nl[0], nl[1], nl[2], rc,
+                                     grap['algorithm'], grap['grid'], grap['moments'],
+                                     grap.get('cutoff', 'cosine'))
+        else:
+            G = oat.descriptors(elements, types, R, h, nl[0], nl[1], nl[2], rc,
+                                acut if acut else rc, angular, **sf)
         e = torch.zeros((), dtype=dtype)
         for a, el in enumerate(elements):
             sel = torch.nonzero(torch.as_tensor(types == a)).reshape(-1)

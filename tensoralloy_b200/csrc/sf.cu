@@ -888,7 +888,7 @@ k_sf_jvp(int n, int n_loc, SfDev sf, int n_types, int row_cap,
          const uint32_t *__restrict__ slice_ptr, const uint32_t *__restrict__ col,
          const int *__restrict__ ghost_owner, const double *__restrict__ u,
          const double *__restrict__ A, const int *__restrict__ struct_of,
-         double *__restrict__ T) {
+         const double *__restrict__ mom, double *__restrict__ T) {
     extern __shared__ __align__(16) double smem[];
     __shared__ double red[SF_WARPS];
     const int lane = threadIdx.x;
@@ -920,26 +920,65 @@ k_sf_jvp(int n, int n_loc, SfDev sf, int n_types, int row_cap,
     seg[0] = 0;
     for (int s = 0; s < sf.n_el; ++s)
         seg[s + 1] = seg[s] + (s < n_types ? tcounts[(size_t)idx * n_types + s] : 0);
-    // ---- G2
+    // ---- radial part: G2 or the GRAP families with multipole moments.  With
+    //      w = f(r) fc(r), u = D / r, s = u . dD and dD_perp = dD - s u:
+    //        m = 0:  dG = sum w' s
+    //        m = 1:  G = |M|^2,      dG = 2 M . dM,  dM = sum [w' s u + (w / r) dD_perp]
+    //        m = 2:  G = sum Q_ab^2, dG = 2 Q : dQ,
+    //                dQ = sum [w' s u (x) u + (w / r) (dD_perp (x) u + u (x) dD_perp)]
+    //      (M, Q = the moment sums of the forward pass, `mom`)
+    const bool grap = sf.has_m1 || sf.has_m2;
+    const double *mo_atom = (grap && mom) ? mom + (size_t)idx * sf.n_el * sf.n_r * GRAP_MOM_W
+                                          : nullptr;
     for (int s = 0; s < sf.n_el; ++s) {
         const int term = radial_term(ti, s);
         for (int tau = 0; tau < sf.n_r; ++tau) {
-            const Real eta = (Real)sf.eta[tau], om = (Real)sf.omega[tau];
-            Real acc = Real(0);
+            Real acc[GRAP_MOM_W];
+#pragma unroll
+            for (int q = 0; q < GRAP_MOM_W; ++q) acc[q] = Real(0);
             for (int k = seg[s] + lane; k < seg[s + 1]; k += SF_TPA) {
                 const double *e = row + k * ROW_W;
-                const Real r = (Real)e[3];
-                Real f, df;
+                const Real r = (Real)e[3], ri = (Real)e[7];
+                Real f, df, v, dv;
                 cutoff_fn<Real>(sf.cutoff, r, rc, f, df);
-                const Real d = r - om;
-                const Real ex = Math<Real>::exp_(-eta * d * d * rc2i);
-                const Real g1 = ex * df - Real(2) * eta * d * rc2i * ex * f;
-                const Real proj = ((Real)e[0] * (Real)dd[k * 4] + (Real)e[1] * (Real)dd[k * 4 + 1] +
-                                   (Real)e[2] * (Real)dd[k * 4 + 2]) / r;
-                acc += g1 * proj;
+                rad_fn<Real>(sf, tau, r, rc2i, v, dv);
+                const Real w = v * f, dw = dv * f + v * df;
+                const Real ux = (Real)e[0] * ri, uy = (Real)e[1] * ri, uz = (Real)e[2] * ri;
+                const Real dx = (Real)dd[k * 4], dy = (Real)dd[k * 4 + 1], dz = (Real)dd[k * 4 + 2];
+                const Real sp = ux * dx + uy * dy + uz * dz;
+                acc[0] += dw * sp;
+                if (grap) {
+                    const Real wr = w * ri;
+                    const Real px = dx - sp * ux, py = dy - sp * uy, pz = dz - sp * uz;
+                    const Real c1 = dw * sp;
+                    acc[1] += c1 * ux + wr * px;
+                    acc[2] += c1 * uy + wr * py;
+                    acc[3] += c1 * uz + wr * pz;
+                    acc[4] += c1 * ux * ux + Real(2) * wr * px * ux;
+                    acc[5] += c1 * uy * uy + Real(2) * wr * py * uy;
+                    acc[6] += c1 * uz * uz + Real(2) * wr * pz * uz;
+                    acc[7] += c1 * uy * uz + wr * (py * uz + pz * uy);
+                    acc[8] += c1 * ux * uz + wr * (px * uz + pz * ux);
+                    acc[9] += c1 * ux * uy + wr * (px * uy + py * ux);
+                }
             }
-            const double tot = block_sum((double)acc, red);
-            if (lane == 0) t[term * sf.n_r + tau] = tot;
+            double tot[GRAP_MOM_W];
+            const int nsum = grap ? GRAP_MOM_W : 1;
+            for (int q = 0; q < nsum; ++q) tot[q] = block_sum((double)acc[q], red);
+            if (lane == 0) {
+                double *tt = t + (size_t)(term * sf.n_r + tau) * sf.n_mom;
+                const double *mo = mo_atom ? mo_atom + (size_t)(term * sf.n_r + tau) * GRAP_MOM_W
+                                           : nullptr;
+                for (int mi = 0; mi < sf.n_mom; ++mi) {
+                    const int mm = sf.mom[mi];
+                    if (mm == 0) tt[mi] = tot[0];
+                    else if (mm == 1)
+                        tt[mi] = 2.0 * (mo[1] * tot[1] + mo[2] * tot[2] + mo[3] * tot[3]);
+                    else
+                        tt[mi] = 2.0 * (mo[4] * tot[4] + mo[5] * tot[5] + mo[6] * tot[6] +
+                                        2.0 * (mo[7] * tot[7] + mo[8] * tot[8] + mo[9] * tot[9]));
+                }
+            }
         }
     }
     if (!sf.angular) return;
@@ -1394,11 +1433,6 @@ static int atomic_common_checks(tab_atomic *m, tab_nbr *nbr, const char *who) {
         tab_set_error("%s: null handle", who);
         return TAB_EINVAL;
     }
-    if (m->sf.rad_kind != 0 || m->sf.n_mom != 1 || m->sf.mom[0] != 0) {
-        tab_set_error("%s: the training operators cover the symmetry-function descriptor "
-                      "only (GRAP families / moments: inference)", who);
-        return TAB_EUNSUPPORTED;
-    }
     if (!nbr->built) {
         tab_set_error("%s before tab_nbr_build", who);
         return TAB_ESTATE;
@@ -1407,6 +1441,30 @@ static int atomic_common_checks(tab_atomic *m, tab_nbr *nbr, const char *who) {
         tab_set_error("%s: halo atoms are not supported", who);
         return TAB_EUNSUPPORTED;
     }
+    return TAB_OK;
+}
+
+// GRAP moments 1 / 2: the backward and JVP kernels need the moment sums M, Q of the forward
+// pass for THESE lists (m->mom is per model, not per structure): recompute them.
+template <typename Real>
+static int forward_moments(tab_atomic *m, tab_nbr *nbr, cudaStream_t st) {
+    const SfDev &sf = m->sf;
+    const int n = nbr->n;
+    const int row_cap = nbr->nnl_max > 0 ? nbr->nnl_max : 1;
+    const size_t smem_row = (size_t)row_cap * ROW_W * sizeof(double);
+    if (smem_row > 200 * 1024) {
+        tab_set_error("neighbour rows of %d entries exceed the shared-memory budget", row_cap);
+        return TAB_EUNSUPPORTED;
+    }
+    TAB_CUDA(cudaFuncSetAttribute(k_sf_forward<Real>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    TAB_TRY(m->G.ensure(sizeof(double) * (size_t)n * sf.dim));
+    TAB_TRY(m->mom.ensure(sizeof(double) * (size_t)n * sf.n_el * sf.n_r * GRAP_MOM_W));
+    k_sf_forward<Real><<<n, SF_WARPS * 32, smem_row, st>>>(
+        n, sf, nbr->n_types, row_cap, nbr->atoms.as<Atom4>(), nbr->types_ext.as<uint8_t>(),
+        nbr->counts.as<int>(), nbr->tcounts.as<int>(), nbr->slice_ptr.as<uint32_t>(),
+        nbr->col.as<uint32_t>(), m->G.as<double>(), m->mom.as<double>());
+    TAB_LAUNCH_CHECK();
     return TAB_OK;
 }
 
@@ -1427,6 +1485,8 @@ static int atomic_forces_from(tab_atomic *m, tab_nbr *nbr, const double *d_dedg,
     TAB_TRY(tab_nbr_ensure_reverse(nbr, st));
     const size_t plane = (size_t)nbr->ell_rows * 32;
     TAB_TRY(m->gvec.ensure(sizeof(double) * 3 * (plane + 32)));
+    const bool grap_moments = sf.has_m1 || sf.has_m2;
+    if (grap_moments) TAB_TRY(forward_moments<Real>(m, nbr, st));
     const size_t tot = (size_t)n * sf.dim;
     k_rows_to_sorted<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(
         n, sf.dim, nbr->perm.as<int>(), d_dedg, m->dEdG.as<double>());
@@ -1437,7 +1497,7 @@ static int atomic_forces_from(tab_atomic *m, tab_nbr *nbr, const double *d_dedg,
         n, sf, nbr->n_types, row_cap, nbr->atoms.as<Atom4>(), nbr->types_ext.as<uint8_t>(),
         nbr->counts.as<int>(), nbr->tcounts.as<int>(), nbr->slice_ptr.as<uint32_t>(),
         nbr->col.as<uint32_t>(), m->dEdG.as<double>(), m->gvec.as<double>(), plane,
-        m->fown.as<double>(), partial, nullptr);
+        m->fown.as<double>(), partial, grap_moments ? m->mom.as<double>() : nullptr);
     TAB_LAUNCH_CHECK();
     k_sf_collect<<<nblk_c, 128, 0, st>>>(
         n, nbr->n_loc, nbr->counts.as<int>(), nbr->slice_ptr.as<uint32_t>(),
@@ -1479,6 +1539,8 @@ static int atomic_jvp(tab_atomic *m, tab_nbr *nbr, const double *d_u, const doub
     TAB_CUDA(cudaFuncSetAttribute(k_sf_jvp<Real>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     const int nblk = n;
+    const bool grap_moments = sf.has_m1 || sf.has_m2;
+    if (grap_moments) TAB_TRY(forward_moments<Real>(m, nbr, st));   // before G is reused as T
     TAB_TRY(m->fown.ensure(sizeof(double) * 3 * (size_t)n));
     TAB_TRY(m->G.ensure(sizeof(double) * (size_t)n * sf.dim));
     // u to sorted order
@@ -1490,7 +1552,7 @@ static int atomic_jvp(tab_atomic *m, tab_nbr *nbr, const double *d_u, const doub
         nbr->types_ext.as<uint8_t>(), nbr->counts.as<int>(), nbr->tcounts.as<int>(),
         nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>(), nbr->ghost_owner.as<int>(),
         m->fown.as<double>(), d_A, nbr->n_struct > 0 ? nbr->struct_of.as<int>() : nullptr,
-        m->G.as<double>());
+        grap_moments ? m->mom.as<double>() : nullptr, m->G.as<double>());
     TAB_LAUNCH_CHECK();
     const size_t tot = (size_t)n * sf.dim;
     k_sf_export<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(

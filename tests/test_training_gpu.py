@@ -75,3 +75,43 @@ def test_parameter_gradients_match_oracle():
         tr.sync_to_model()
         assert np.allclose(nn.mlp_params('Ni')['weights'][0],
                            tr.layers['Ni']['W'][0].detach().cpu().numpy())
+
+
+def test_grap_parameter_gradients_match_oracle():
+    """The default descriptor of the reference (GenericRadialAtomicPotential, legacy mode)
+    with multipole moments 0, 1, 2: force op + JVP kernel carry the moment terms."""
+    from tensoralloy_b200.nn.atomic import GenericRadialAtomicPotential
+    structs = make_structures(2, seed=5)
+    elements = ['Mo', 'Ni']
+    rc = 4.5
+    with precision_scope('high'):
+        desc = GenericRadialAtomicPotential(elements, algorithm='pexp',
+                                            parameters=dict(rl=[1.5, 2.5], pl=[2.0, 3.0]),
+                                            param_space_method='pair',
+                                            moment_tensors=[0, 1, 2])
+        nn = AtomicNN(elements, desc, hidden_sizes=[16, 16], activation='softplus',
+                      minmax_scale=False, minimize_properties=('energy', 'forces', 'stress'),
+                      export_properties=('energy', 'forces', 'stress'))
+        nn.attach_transformer(UniversalTransformer(elements, rcut=rc, angular=False))
+        nn.initialize_variables(seed=3)
+        for el in elements:
+            key = f"Atomic/{el}/Output/kernel"
+            nn.set_variable(key, nn.get_variable(key) * 0.05)
+        tr = AtomicNNTrainer(nn)
+        for s in structs:
+            tr.add_structure(s['atoms'], s['energy'], s['forces'], s['stress'])
+        loss, parts = tr.gradients()
+        params = {el: nn.mlp_params(el) for el in elements}
+        grap = dict(algorithm='pexp', grid=desc.radial_sets(), moments=desc.moments(),
+                    cutoff='cosine')
+        ref_loss, ref_parts, ref_g = otr.loss_and_grads(elements, structs, params, rc,
+                                                        angular=False, grap=grap)
+        assert abs(loss.item() - ref_loss) < 1e-9 * max(1.0, abs(ref_loss))
+        for key in ('energy', 'forces', 'stress'):
+            assert abs(parts[key].item() - ref_parts[key]) < 1e-9
+        for el in elements:
+            L = tr.layers[el]
+            for k, w in enumerate(L['W']):
+                g = w.grad.cpu().numpy()
+                r = ref_g[el][0][k]
+                assert np.abs(g - r).max() < 1e-8 * max(1.0, np.abs(r).max()), (el, k)
