@@ -151,3 +151,96 @@ def eam_loss_and_grads(kind, elements, structures, fns, leaves_fn, rc,
             {'energy': float(le.detach()), 'forces': float(lf.detach()),
              'stress': float(ls.detach())},
             {k: (None if g is None else g.numpy()) for k, g in zip(names, grads)})
+
+
+def td_loss_and_grads(elements, structures, params, rc, minimize, sf=None, acut=None,
+                      angular=True, minmax=None, eps=1e-14):
+    """Training-step loss of a temperature-dependent AtomicNN (finite_temperature.py:
+    211-304,338-366): energy losses for the properties of `minimize` among 'energy' (U),
+    'free_energy' (F), 'eentropy' (S), forces / stress from F.  params[el] = dict(H=, S=,
+    U=, algo=, special=) of mlp dicts (weights, biases, out_bias as arrays); structures carry
+    'etemperature', 'free_energy', 'eentropy'.  Returns (loss, parts, {name: grad}) with the
+    reference variable names TD/<El>/<head>/..."""
+    elements = sorted(elements)
+    dtype = torch.float64
+    leaves = {}
+    P = {}
+    for el in elements:
+        P[el] = dict(algo=params[el].get('algo', 'default'), special=params[el].get('special'))
+        for head in ('H', 'S', 'U'):
+            q = params[el][head]
+            base = f"TD/{el}/{head}"
+            W, b = [], []
+            for k, w in enumerate(q['weights'][:-1]):
+                W.append(torch.tensor(w, dtype=dtype, requires_grad=True))
+                b.append(torch.tensor(q['biases'][k], dtype=dtype, requires_grad=True))
+                leaves[f"{base}/Conv1d{k + 1}/kernel"] = W[-1]
+                leaves[f"{base}/Conv1d{k + 1}/bias"] = b[-1]
+            W.append(torch.tensor(q['weights'][-1], dtype=dtype, requires_grad=True))
+            leaves[f"{base}/Output/kernel"] = W[-1]
+            ob = None
+            if q.get('out_bias') is not None:
+                ob = torch.tensor(q['out_bias'], dtype=dtype, requires_grad=True)
+                leaves[f"{base}/Output/bias"] = ob
+            P[el][head] = dict(weights=W, biases=b + [None], out_bias=ob,
+                               activation=q.get('activation', 'softplus'),
+                               use_resnet_dt=q.get('use_resnet_dt', False))
+    pred = {'energy': [], 'free_energy': [], 'eentropy': []}
+    lab = {'energy': [], 'free_energy': [], 'eentropy': []}
+    n_at, F_pred, F_lab, S_pred, S_lab = [], [], [], [], []
+    sf = dict(sf or {})
+    for s in structures:
+        pos = np.asarray(s['positions'], dtype=np.float64)
+        cell = np.asarray(s['cell'], dtype=np.float64)
+        cut = max(rc, acut) if (angular and acut) else rc
+        nl = neighbor.neighbor_list(pos, cell, s['pbc'], cut)
+        types = np.array([elements.index(x) for x in s['symbols']])
+        R = torch.tensor(pos, dtype=dtype, requires_grad=True)
+        h = torch.tensor(cell, dtype=dtype, requires_grad=True)
+        G = oat.descriptors(elements, types, R, h, nl[0], nl[1], nl[2], rc,
+                            acut if acut else rc, angular, **sf)
+        tot = {k: torch.zeros((), dtype=dtype) for k in pred}
+        for a, el in enumerate(elements):
+            sel = torch.nonzero(torch.as_tensor(types == a)).reshape(-1)
+            if not sel.numel():
+                continue
+            x = G[sel]
+            if minmax and minmax.get(el) is not None:
+                xlo, xhi = [torch.as_tensor(v, dtype=dtype) for v in minmax[el]]
+                den = xhi - xlo
+                x = torch.where(den == 0, torch.zeros_like(x), (xhi - x) / den)
+            U, S, F = oat.td_heads(x, s['etemperature'], P[el], dtype)
+            tot['energy'] = tot['energy'] + U.sum()
+            tot['eentropy'] = tot['eentropy'] + S.sum()
+            tot['free_energy'] = tot['free_energy'] + F.sum()
+        dR, dh = torch.autograd.grad(tot['free_energy'], (R, h), create_graph=True)
+        Fo = -dR
+        virial = -(Fo.t() @ R) + dh.t() @ h
+        stress = virial / abs(np.linalg.det(cell))
+        S_pred.append(torch.stack([stress[0, 0], stress[1, 1], stress[2, 2],
+                                   stress[1, 2], stress[0, 2], stress[0, 1]]))
+        S_lab.append(torch.tensor(np.asarray(s['stress']), dtype=dtype))
+        F_pred.append(Fo)
+        F_lab.append(torch.tensor(np.asarray(s['forces']), dtype=dtype))
+        n_at.append(len(pos))
+        for k in pred:
+            pred[k].append(tot[k])
+            lab[k].append(float(s[k]))
+    n = torch.tensor(n_at, dtype=dtype)
+
+    def rmse(x, y):
+        return torch.sqrt(torch.mean((x - y) ** 2) + eps)
+
+    loss = torch.zeros((), dtype=dtype)
+    parts = {}
+    for k in ('energy', 'free_energy', 'eentropy'):
+        if k in minimize:
+            parts[k] = rmse(torch.tensor(lab[k], dtype=dtype) / n, torch.stack(pred[k]) / n)
+            loss = loss + parts[k]
+    parts['forces'] = rmse(torch.cat(F_lab), torch.cat(F_pred))
+    parts['stress'] = rmse(torch.stack(S_lab), torch.stack(S_pred))
+    loss = loss + parts['forces'] + parts['stress']
+    names = list(leaves)
+    grads = torch.autograd.grad(loss, [leaves[k] for k in names], allow_unused=True)
+    return (float(loss.detach()), {k: float(v.detach()) for k, v in parts.items()},
+            {k: (None if g is None else g.numpy()) for k, g in zip(names, grads)})

@@ -227,3 +227,122 @@ class AtomicNNTrainer:
             if L['b'][nh] is not None:
                 self.nn.set_variable(f"{self.nn.scope}/{el}/Output/bias",
                                      L['b'][nh].detach().cpu().numpy())
+
+
+class TemperatureDependentTrainer(AtomicNNTrainer):
+    """Training step of `TemperatureDependentAtomicNN` / `BeNN`
+    (nn/atomic/finite_temperature.py:211-304,338-366): the energy losses cover the
+    properties listed in `minimize_properties` among 'energy' (U), 'free_energy' (F = U - T S)
+    and 'eentropy' (S); forces and stress derive from the FREE energy (basic.py:190-202).
+    Geometry side as in `AtomicNNTrainer`: descriptors, force operator and its JVP are the
+    libtab200 kernels on one batch handle; the H / S / U heads run in torch."""
+
+    def __init__(self, nn, device='cuda', loss_weights=None, per_atom_energy=True):
+        self.nn = nn
+        self.device = device
+        self.dt = get_float_dtype()
+        self.tdtype = torch.float64 if self.dt.name == 'float64' else torch.float32
+        self.model = nn._device_model()
+        self.elements = nn.elements
+        self.loss_weights = dict(energy=1.0, free_energy=1.0, eentropy=1.0, forces=1.0,
+                                 stress=1.0)
+        self.loss_weights.update(loss_weights or {})
+        self.per_atom_energy = per_atom_energy
+        self.params = []
+        self.named = {}             # reference variable name -> leaf
+        self.heads = {}
+        for el in self.elements:
+            hd = {}
+            for head in ('H', 'S', 'U'):
+                p = nn.head_params(el, head)
+                base = f"{nn.scope}/{el}/{head}"
+                W, b = [], []
+                for k, w in enumerate(p['weights'][:-1]):
+                    W.append(self._named_leaf(f"{base}/Conv1d{k + 1}/kernel", w))
+                    b.append(self._named_leaf(f"{base}/Conv1d{k + 1}/bias", p['biases'][k]))
+                W.append(self._named_leaf(f"{base}/Output/kernel", p['weights'][-1]))
+                ob = None if p['out_bias'] is None else \
+                    self._named_leaf(f"{base}/Output/bias", p['out_bias'])
+                hd[head] = dict(W=W, b=b, ob=ob, act=p['activation'],
+                                resnet=p['use_resnet_dt'])
+            mm = nn.minmax(el)
+            t = lambda a: torch.tensor(np.asarray(a), dtype=self.tdtype, device=device)
+            hd['xlo'], hd['xhi'] = (t(mm[0]), t(mm[1])) if mm else (None, None)
+            self.heads[el] = hd
+        self.structures = []
+        self._batch = None
+
+    def _named_leaf(self, name, arr):
+        t = self._leaf(arr)
+        self.named[name] = t
+        return t
+
+    def add_structure(self, atoms, energy, forces, stress, free_energy=None, eentropy=None):
+        super().add_structure(atoms, energy, forces, stress)
+        t = lambda a: torch.tensor(float(a), dtype=self.tdtype, device=self.device)
+        s = self.structures[-1]
+        s['free_energy'] = t(energy if free_energy is None else free_energy)
+        s['eentropy'] = t(0.0 if eentropy is None else eentropy)
+        s['etemperature'] = float(atoms.info.get('etemperature', 0.0))
+
+    def total_loss(self, want_forces=True, want_stress=True):
+        B = self._ensure_batch()
+        S_ = self.structures
+        nb = len(S_)
+        if 't_atom' not in B:
+            temps = torch.tensor([s['etemperature'] for s in S_], dtype=self.tdtype,
+                                 device=self.device)
+            B['t_atom'] = temps[B['sid']]
+            B['free_energy'] = torch.stack([s['free_energy'] for s in S_])
+            B['eentropy'] = torch.stack([s['eentropy'] for s in S_])
+        G_all = B['G'].detach().requires_grad_(True)
+        n = G_all.shape[0]
+        z = lambda: torch.zeros(n, dtype=self.tdtype, device=self.device)
+        U, S = z(), z()
+        net = self.nn._net
+        for a, el in enumerate(self.elements):
+            sel = torch.nonzero(B['types'] == a).reshape(-1)
+            if not sel.numel():
+                continue
+            hd = self.heads[el]
+            x = G_all[sel]
+            if hd['xlo'] is not None:
+                den = hd['xhi'] - hd['xlo']
+                x = torch.where(den == 0, torch.zeros_like(x), (hd['xhi'] - x) / den)
+            T = B['t_atom'][sel]
+            Ht = torch.cat([net(hd['H'], x), T[:, None]], dim=1)
+            U = U.index_add(0, sel, net(hd['U'], Ht)[:, 0])
+            S = S.index_add(0, sel, self.nn._entropy(hd, Ht, T))
+        F = U - B['t_atom'] * S
+        seg = lambda v: torch.zeros(nb, dtype=self.tdtype, device=self.device).index_add(
+            0, B['sid'], v)
+        totals = {'energy': seg(U), 'eentropy': seg(S), 'free_energy': seg(F)}
+        w = self.loss_weights
+        loss = torch.zeros((), dtype=self.tdtype, device=self.device)
+        parts = {}
+        for prop in ('energy', 'free_energy', 'eentropy'):
+            if prop in self.nn.minimize_properties:
+                lp = losses.energy_loss(B[prop], totals[prop], B['n_atoms'],
+                                        self.per_atom_energy, w[prop])
+                loss = loss + lp
+                parts[prop] = lp.detach()
+        if want_forces or want_stress:
+            dedg = torch.autograd.grad(totals['free_energy'].sum(), G_all,
+                                       create_graph=True)[0]
+            Fo, W = SfForce.apply(dedg, self.model, B['nbr'], self.dt.tab_precision)
+            if want_forces:
+                lf = losses.forces_loss(B['forces'], Fo, w['forces'])
+                loss = loss + lf
+                parts['forces'] = lf.detach()
+            if want_stress:
+                st = W / B['volume'][:, None, None]
+                voigt = torch.stack([st[:, a, b] for a, b in VOIGT], dim=1)
+                ls = losses.stress_loss(B['stress'], voigt, w['stress'])
+                loss = loss + ls
+                parts['stress'] = ls.detach()
+        return loss, parts
+
+    def sync_to_model(self):
+        for name, t in self.named.items():
+            v = t.detach().cpu().numpy()
+            self.nn.set_variable(name, v[None] if name.endswith('/kernel') else v)

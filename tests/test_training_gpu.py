@@ -115,3 +115,67 @@ def test_grap_parameter_gradients_match_oracle():
                 g = w.grad.cpu().numpy()
                 r = ref_g[el][0][k]
                 assert np.abs(g - r).max() < 1e-8 * max(1.0, np.abs(r).max()), (el, k)
+
+
+@pytest.mark.parametrize("special", [False, True])
+def test_temperature_dependent_parameter_gradients_match_oracle(special):
+    """TemperatureDependentAtomicNN / BeNN: U, F = U - T S and S losses + forces and stress
+    of the free energy (finite_temperature.py:338-366, basic.py:190-202)."""
+    from tensoralloy_b200.nn.atomic import BeNN, TemperatureDependentAtomicNN
+    from tensoralloy_b200.nn.atomic.training import TemperatureDependentTrainer
+    rng = np.random.default_rng(11)
+    structs = []
+    for k in range(2):
+        base = bulk_fcc('Ni', 3.2 + 0.2 * k, (2, 2, 2))
+        sym = ['Be'] * len(base)
+        pos = base.positions + rng.normal(scale=0.1, size=base.positions.shape)
+        atoms = Atoms(sym, pos, base.cell, True)
+        atoms.info['etemperature'] = 0.1 + 0.2 * k
+        structs.append(dict(atoms=atoms, symbols=sym, positions=pos, cell=base.cell,
+                            pbc=[1, 1, 1], etemperature=atoms.info['etemperature'],
+                            energy=-3.0 * len(base), free_energy=-3.1 * len(base),
+                            eentropy=0.3 * len(base),
+                            forces=rng.normal(scale=0.3, size=pos.shape),
+                            stress=rng.normal(scale=0.01, size=6)))
+    minimize = ('energy', 'free_energy', 'eentropy', 'forces', 'stress')
+    with precision_scope('high'):
+        cls = BeNN if special else TemperatureDependentAtomicNN
+        nn = cls(['Be'], SymmetryFunction(['Be']), hidden_sizes=[12, 12], minmax_scale=False,
+                 activation='softplus', minimize_properties=minimize,
+                 export_properties=('energy', 'forces', 'stress'),
+                 finite_temperature=dict(activation='tanh', layers=[16, 8],
+                                         algo='default' if special else 'Sommerfeld'))
+        nn.attach_transformer(UniversalTransformer(['Be'], rcut=4.5, angular=True))
+        nn.initialize_variables(seed=2)
+        for head in ('U', 'S'):
+            key = f"TD/Be/{head}/Output/kernel"
+            nn.set_variable(key, nn.get_variable(key) * 0.2)
+        key = "TD/Be/H/Conv1d1/kernel"
+        nn.set_variable(key, nn.get_variable(key) * 0.2)
+        tr = TemperatureDependentTrainer(nn)
+        for s in structs:
+            tr.add_structure(s['atoms'], s['energy'], s['forces'], s['stress'],
+                             free_energy=s['free_energy'], eentropy=s['eentropy'])
+        loss, parts = tr.gradients()
+        ref_loss, ref_parts, ref_g = otr.td_loss_and_grads(
+            ['Be'], structs, {'Be': nn.td_params('Be')}, 4.5, minimize)
+        assert abs(loss.item() - ref_loss) < 1e-9 * max(1.0, abs(ref_loss))
+        for key, val in ref_parts.items():
+            assert abs(parts[key].item() - val) < 1e-9 * max(1.0, abs(val)), key
+        checked = 0
+        for name, r in ref_g.items():
+            assert name in tr.named, name
+            if r is None:
+                continue
+            g = tr.named[name].grad.cpu().numpy().reshape(r.shape)
+            assert np.abs(g - r).max() < 1e-8 * max(1.0, np.abs(r).max()), name
+            checked += 1
+        assert checked >= 10
+        opt = torch.optim.Adam(tr.params, lr=1e-3)
+        l0 = loss.item()
+        for _ in range(10):
+            l, _ = tr.train_step(opt)
+        assert l.item() < l0
+        tr.sync_to_model()
+        assert np.allclose(nn.get_variable('TD/Be/U/Output/kernel').reshape(-1),
+                           tr.named['TD/Be/U/Output/kernel'].detach().cpu().numpy().reshape(-1))
