@@ -161,3 +161,24 @@ def test_eam_fs_all_nn_parameter_gradients():
             if name.endswith('Output/kernel'):
                 nn.set_variable(name, value * 0.2)
         _check(nn, 'fs', structs)
+
+
+def test_eam_training_step_in_medium_precision():
+    structs = make_structures(2, seed=31)
+    out = {}
+    for prec in ('high', 'medium'):
+        with precision_scope(prec):
+            nn = EamAlloyNN(ELEMENTS, hidden_sizes=[8, 8],
+                            minimize_properties=('energy', 'forces', 'stress'))
+            nn.attach_transformer(UniversalTransformer(ELEMENTS, rcut=RC))
+            nn.initialize_variables(seed=3)
+            for name, value in list(nn.variables.items()):
+                if name.endswith('Output/kernel'):
+                    nn.set_variable(name, value * 0.2)
+            tr = EamTrainer(nn)
+            for s in structs:
+                tr.add_structure(s['atoms'], s['energy'], s['forces'], s['stress'])
+            loss, _ = tr.gradients()
+            assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in tr.params)
+            out[prec] = loss.item()
+    assert abs(out['medium'] - out['high']) < 1e-4 * abs(out['high'])

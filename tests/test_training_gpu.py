@@ -179,3 +179,29 @@ def test_temperature_dependent_parameter_gradients_match_oracle(special):
         tr.sync_to_model()
         assert np.allclose(nn.get_variable('TD/Be/U/Output/kernel').reshape(-1),
                            tr.named['TD/Be/U/Output/kernel'].detach().cpu().numpy().reshape(-1))
+
+
+def test_training_step_in_medium_precision():
+    """'medium' (float32, the reference's default precision): the same training step runs
+    with float32 kernels and float32 torch leaves; loss within 1e-4 relative of float64."""
+    structs = make_structures(2, seed=21)
+    elements = ['Mo', 'Ni']
+    out = {}
+    for prec in ('high', 'medium'):
+        with precision_scope(prec):
+            nn = AtomicNN(elements, SymmetryFunction(elements), hidden_sizes=[16, 16],
+                          minmax_scale=False,
+                          minimize_properties=('energy', 'forces', 'stress'))
+            nn.attach_transformer(UniversalTransformer(elements, rcut=4.5, angular=True))
+            nn.initialize_variables(seed=3)
+            for el in elements:
+                key = f"Atomic/{el}/Output/kernel"
+                nn.set_variable(key, nn.get_variable(key) * 0.05)
+            tr = AtomicNNTrainer(nn)
+            for s in structs:
+                tr.add_structure(s['atoms'], s['energy'], s['forces'], s['stress'])
+            loss, _ = tr.gradients()
+            assert tr.params[0].dtype == (torch.float64 if prec == 'high' else torch.float32)
+            assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in tr.params)
+            out[prec] = loss.item()
+    assert abs(out['medium'] - out['high']) < 1e-4 * abs(out['high'])
