@@ -36,3 +36,16 @@ def test_two_rank_atomic_nn_slabs():
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=240, cwd=ROOT)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert 'FAIL' not in res.stdout
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2,
+                    reason="needs two GPUs")
+def test_two_rank_structure_parallel_training():
+    """Config 4: per-rank sub-batches, one flat NCCL gradient all-reduce
+    (tools/train_check.py)."""
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1',
+           '--nproc-per-node', '2', '--master-addr', '127.0.0.1', '--master-port', '29544',
+           os.path.join(ROOT, 'tools', 'train_check.py'), '4']
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=240, cwd=ROOT)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert 'FAIL' not in res.stdout
