@@ -112,3 +112,46 @@ def test_product_never_imports_oracle():
             if f.endswith('.py'):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r'^\s*(from|import)\s+oracle\b', src, flags=re.M), f
+
+
+def test_atomic_slab_layout_geometry():
+    """2 rc halo of the AtomicNN / ADP decomposition (domain_atomic.py): send masks, the
+    inner / outer split and the binning frame."""
+    import pytest
+    from tensoralloy_b200.domain_atomic import AtomicSlabLayout
+    lay = AtomicSlabLayout(40.0, 2, 1, 4.0)           # slab [20, 40), halo 8
+    assert (lay.lo, lay.hi, lay.halo) == (20.0, 40.0, 8.0)
+    x = np.array([20.5, 27.9, 28.1, 31.9, 32.1, 39.9])
+    to_left, to_right = lay.send_masks(x)
+    assert to_left.tolist() == [True, True, False, False, False, False]
+    assert to_right.tolist() == [False, False, False, False, True, True]
+    assert lay.shift_to_right == -40.0 and lay.shift_to_left == 0.0   # last rank wraps right
+    cell, origin, pbc = lay.frame(10.0, 12.0)
+    assert pbc == [0, 1, 1] and origin[0] == 20.0 - 8.0 - 0.5
+    assert cell[0, 0] == 20.0 + 16.0 + 1.0 and cell[1, 1] == 10.0
+    with pytest.raises(ValueError):
+        AtomicSlabLayout(40.0, 8, 0, 4.0)             # width 5 < halo 8
+    AtomicSlabLayout(40.0, 1, 0, 30.0)                # a single rank is never too narrow
+
+
+def test_transformer_element_lookup_table():
+    from tensoralloy_b200.transformer import UniversalTransformer
+    clf = UniversalTransformer(['Ni', 'Mo'], rcut=5.0)
+    lut = clf._z_lut()
+    assert lut[42] == 0 and lut[28] == 1 and (np.delete(lut, [28, 42]) == -1).all()
+    atoms = Atoms(['Ni', 'Mo', 'Ni'], np.zeros((3, 3)), np.eye(3) * 5, True)
+    assert atoms.numbers.tolist() == [28, 42, 28]
+    assert lut[atoms.numbers].tolist() == clf.get_types(atoms).tolist() == [1, 0, 1]
+    b = atoms.copy()
+    b.positions[0, 0] = 1.0
+    assert atoms.positions[0, 0] == 0.0 and b.numbers is not atoms.numbers
+
+
+def test_phonon_masses_and_units():
+    from tensoralloy_b200.analysis.phonon import VaspToCm, VaspToTHz, get_masses
+    atoms = Atoms(['Ni', 'Be'], np.zeros((2, 3)), np.eye(3) * 5, True)
+    assert np.allclose(get_masses(atoms), [58.6934, 9.0121831])
+    # sqrt(eV / (amu A^2)) / (2 pi) in THz
+    ev, amu = 1.602176634e-19, 1.66053906660e-27
+    assert abs(VaspToTHz - np.sqrt(ev / amu) / 1e-10 / (2 * np.pi) / 1e12) < 1e-4
+    assert abs(VaspToCm / VaspToTHz - 33.356410) < 1e-6
