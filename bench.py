@@ -55,6 +55,10 @@ def make_lattice(cells, seed=SEED):
     return pos, cell
 
 
+# FP64 instructions per pair in the k_eam_force loop of the zjw04 fast path (SASS count)
+FP64_PER_PAIR = {'high': 83, 'medium': 0}
+
+
 def load_traffic(kernel):
     """DRAM bytes per launch of `kernel` from the committed ncu capture (or None)."""
     path = os.path.join(ROOT, 'profiles', 'r01k_traffic.json')
@@ -360,6 +364,17 @@ def run_ours(args):
                 "kernel_ms": {"rho_pass": kernel_ms[0], "spread": kernel_ms[1],
                               "force_pass": kernel_ms[2], "reduce": kernel_ms[3]},
                 "fp64_pipe_active_pct_ncu": 64.9,
+                # the binding compute limit next to the HBM figure: SASS-counted FP64
+                # instructions of the force loop (tools/sass_loop.py) x pairs / measured
+                # duration, against 64 FP64 lanes/clk/SM x 148 SMs x the sampled SM clock
+                "fp64": ({"instr_per_pair": FP64_PER_PAIR[args.precision],
+                          "achieved_ginstr_s": FP64_PER_PAIR[args.precision] * nij /
+                          (force_ms * 1e-3) / 1e9,
+                          "peak_ginstr_s": 64 * 148 * (clocks or {}).get('sm_mhz', 1965.0)
+                          * 1e6 / 1e9,
+                          "frac": FP64_PER_PAIR[args.precision] * nij / (force_ms * 1e-3) /
+                          (64 * 148 * (clocks or {}).get('sm_mhz', 1965.0) * 1e6)}
+                         if (force_ms > 0 and args.precision == 'high') else None),
                 "note": "float64 analytic zjw04 is bound by the FP64 pipe and the L1 "
                         "gather path together (ncu: FP64 pipe 65% of cycles active at 83 "
                         "FP64 instructions per pair, L1 50%, DRAM 8%, DRAM bytes within 10% "
