@@ -337,6 +337,7 @@ def run_ours(args):
         alg_bytes = 4.0 * nij + 64.0 * n_loc
         force_ms = kernel_ms[2]
         achieved = alg_bytes / (force_ms * 1e-3) / 1e9 if force_ms > 0 else None
+        sm_mhz = float((clocks or {}).get('sm_mhz') or 1965.0)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
@@ -370,10 +371,9 @@ def run_ours(args):
                 "fp64": ({"instr_per_pair": FP64_PER_PAIR[args.precision],
                           "achieved_ginstr_s": FP64_PER_PAIR[args.precision] * nij /
                           (force_ms * 1e-3) / 1e9,
-                          "peak_ginstr_s": 64 * 148 * (clocks or {}).get('sm_mhz', 1965.0)
-                          * 1e6 / 1e9,
+                          "peak_ginstr_s": 64 * 148 * sm_mhz * 1e6 / 1e9,
                           "frac": FP64_PER_PAIR[args.precision] * nij / (force_ms * 1e-3) /
-                          (64 * 148 * (clocks or {}).get('sm_mhz', 1965.0) * 1e6)}
+                          (64 * 148 * sm_mhz * 1e6)}
                          if (force_ms > 0 and args.precision == 'high') else None),
                 "note": "float64 analytic zjw04 is bound by the FP64 pipe and the L1 "
                         "gather path together (ncu: FP64 pipe 65% of cycles active at 83 "
