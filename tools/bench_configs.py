@@ -128,6 +128,32 @@ def c4(n_struct=32):
             "ms_per_step": t * 1e3, "structures_per_s": n_struct / t, "dtype": "f64"}
 
 
+def c4_adp(n_struct=256):
+    from tensoralloy_b200.nn.eam import AdpNN
+    from tensoralloy_b200.nn.eam.training import EamTrainer
+    rng = np.random.default_rng(0)
+    elements = ['Mo', 'Ni']
+    nn = AdpNN(elements, hidden_sizes=[32, 32],
+               minimize_properties=('energy', 'forces', 'stress'))
+    nn.attach_transformer(UniversalTransformer(elements, rcut=5.0))
+    nn.initialize_variables()
+    tr = EamTrainer(nn)
+    for _ in range(n_struct):
+        a = 3.3 + 0.4 * rng.random()
+        base = bulk_fcc('Ni', a, (3, 3, 3))
+        sym = ['Mo' if x < 0.4 else 'Ni' for x in rng.random(len(base))]
+        atoms = Atoms(sym, base.positions + rng.normal(scale=0.1, size=base.positions.shape),
+                      base.cell, True)
+        tr.add_structure(atoms, -4.0 * len(base), rng.normal(scale=0.3, size=(len(base), 3)),
+                         rng.normal(scale=0.01, size=6))
+    opt = torch.optim.Adam(tr.params, lr=1e-3)
+    t = timed(lambda: tr.train_step(opt), 5, warm=2)
+    return {"config": f"C4(ii) AdpNN training step, Mo-Ni, {n_struct} structures x 108 atoms, "
+                      f"phi / rho / embed / dipole / quadrupole as 'nn' MLPs [32,32], rc 5.0, "
+                      f"loss = E/atom + F + stress RMSE, Adam",
+            "ms_per_step": t * 1e3, "structures_per_s": n_struct / t, "dtype": "f64"}
+
+
 def c5():
     atoms = bulk_hcp('Be', 2.2644, 3.5673, (5, 5, 3))
     atoms.positions += np.random.default_rng(8).normal(scale=0.01,
@@ -145,7 +171,8 @@ def c5():
 def main():
     with precision_scope('high'):
         for fn in (c1, c1_batch, lambda: c2(1), lambda: c2(32), lambda: c2(32, True),
-                   lambda: c2(256, True), c4, lambda: c4(256), c5):
+                   lambda: c2(256, True), c4, lambda: c4(256), lambda: c4_adp(32),
+                   c4_adp, c5):
             print(json.dumps(fn()), flush=True)
 
 
