@@ -603,21 +603,38 @@ k_sf_backward(int n, SfDev sf, int n_types, int row_cap,
                     const Real dct_da = iab2 != Real(0) ? irb - ct * ira : Real(0);
                     const Real dct_dab = -rab * iab2;
                     const Real F3 = fa * fb * fab;
-                    Real va = Real(0), vab = Real(0), E = Real(0);
+                    // sum over the angular sets with the beta-independent factors pulled
+                    // out: for one beta group, with A0 = sum K P and A1 = sum K gamma P',
+                    //   d/dr_a  = E [F3 dct_da  A1 + A0 (fa' fb fab - 2 beta r_a  F3 / acut^2)]
+                    //   d/dr_ab = E [F3 dct_dab A1 + A0 (fa fb fab' - 2 beta r_ab F3 / acut^2)]
+                    // (the grid is beta-outermost, sf.py:49-51: one exponential per group)
+                    Real va = Real(0), vab = Real(0), E = Real(0), A0 = Real(0), A1 = Real(0);
+                    Real be_cur = Real(0);
+                    const Real ta_ = dfa * fb * fab, tab_ = fa * fb * dfab;
                     for (int tau = 0; tau < sf.n_a; ++tau) {
                         const Real z = (Real)sf.zeta[tau], gm = (Real)sf.gamma[tau],
                                    be = (Real)sf.beta[tau];
+                        if (tau == 0 || sf.beta[tau] != sf.beta[tau - 1]) {
+                            if (tau > 0) {
+                                const Real c0 = Real(-2) * be_cur * ac2i * F3;
+                                va += E * (F3 * dct_da * A1 + A0 * (ta_ + c0 * ra));
+                                vab += E * (F3 * dct_dab * A1 + A0 * (tab_ + c0 * rab));
+                            }
+                            E = Math<Real>::exp_(-be * s2 * ac2i);
+                            A0 = Real(0);
+                            A1 = Real(0);
+                            be_cur = be;
+                        }
                         Real dP;
                         const Real P = powz<Real>(Real(1) + gm * ct, z, dP);
-                        dP *= gm;
-                        if (tau == 0 || sf.beta[tau] != sf.beta[tau - 1])
-                            E = Math<Real>::exp_(-be * s2 * ac2i);
                         const Real K = (Real)sf.outer[tau] * (Real)cc[tau];
-                        const Real PE = P * E;
-                        va += K * (dP * dct_da * E * F3 - Real(2) * be * ra * ac2i * PE * F3 +
-                                   PE * dfa * fb * fab);
-                        vab += K * (dP * dct_dab * E * F3 - Real(2) * be * rab * ac2i * PE * F3 +
-                                    PE * fa * fb * dfab);
+                        A0 += K * P;
+                        A1 += K * (dP * gm);
+                    }
+                    {
+                        const Real c0 = Real(-2) * be_cur * ac2i * F3;
+                        va += E * (F3 * dct_da * A1 + A0 * (ta_ + c0 * ra));
+                        vab += E * (F3 * dct_dab * A1 + A0 * (tab_ + c0 * rab));
                     }
                     sa += va;
                     const Real q = vab * irab;
