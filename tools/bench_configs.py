@@ -168,12 +168,25 @@ def c5():
             "ms_per_call": t * 1e3, "dtype": "f64"}
 
 
+def medium():
+    """'medium' (float32 kernels, the reference's default precision) on the batch path."""
+    out = []
+    with precision_scope('medium'):
+        for fn in (c1_batch, lambda: c2(256, True)):
+            r = fn()
+            r['dtype'] = 'f32'
+            out.append(r)
+    return out
+
+
 def main():
     with precision_scope('high'):
         for fn in (c1, c1_batch, lambda: c2(1), lambda: c2(32), lambda: c2(32, True),
                    lambda: c2(256, True), c4, lambda: c4(256), lambda: c4_adp(32),
                    c4_adp, c5):
             print(json.dumps(fn()), flush=True)
+    for r in medium():
+        print(json.dumps(r), flush=True)
 
 
 if __name__ == '__main__':
