@@ -61,7 +61,10 @@ def allreduce_mean_(params, dist, world):
     off = 0
     for p in params:
         n = p.numel()
-        p.grad = flat[off:off + n].reshape(p.shape).clone()
+        if p.grad is None:
+            p.grad = flat[off:off + n].reshape(p.shape).clone()
+        else:       # in place: a captured step keeps writing into the same tensors
+            p.grad.copy_(flat[off:off + n].reshape(p.shape))
         off += n
     return flat
 
@@ -133,6 +136,8 @@ class AtomicNNTrainer:
         n_atoms = torch.tensor([s['n'] for s in self.structures], device=dev)
         self._batch = dict(
             nbr=bf.nbr, G=G, types=torch.as_tensor(bf.types, device=dev).long(),
+            sel=[torch.nonzero(torch.as_tensor(bf.types, device=dev) == a).reshape(-1)
+                 for a in range(len(self.elements))],
             sid=torch.repeat_interleave(torch.arange(len(self.structures), device=dev),
                                         n_atoms),
             n_atoms=n_atoms,
@@ -170,7 +175,7 @@ class AtomicNNTrainer:
         G_all = B['G'].detach().requires_grad_(True)
         e_atom = torch.zeros(G_all.shape[0], dtype=self.tdtype, device=self.device)
         for a, el in enumerate(self.elements):
-            sel = torch.nonzero(B['types'] == a).reshape(-1)
+            sel = B['sel'][a]
             if sel.numel():
                 e_atom = e_atom.index_add(0, sel, self._mlp(el, G_all[sel]))
         E = torch.zeros(nb, dtype=self.tdtype, device=self.device).index_add(
@@ -205,8 +210,46 @@ class AtomicNNTrainer:
     def allreduce_gradients(self, dist, world):
         allreduce_mean_(self.params, dist, world)
 
+    def enable_graph(self, warmup=3):
+        """Capture loss + backward of this rank's (fixed) batch in ONE CUDA graph: the
+        training step is launch-bound (hundreds of small torch kernels around the force
+        operator and its JVP), the geometry and all shapes are static.  `train_step`
+        then replays the graph; gradients land in the same tensors every step.  Returns
+        True when the capture worked (otherwise the eager path stays in use)."""
+        self._graph = None
+        try:
+            self._ensure_batch()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(warmup):
+                    for p in self.params:
+                        p.grad = None
+                    loss, _ = self.total_loss()
+                    loss.backward()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            for p in self.params:
+                p.grad = None
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                loss, parts = self.total_loss()
+                loss.backward()
+            self._graph = (g, loss, parts)
+        except Exception as exc:      # capture is an optimisation, never a requirement
+            self._graph = None
+            self.graph_error = f"{type(exc).__name__}: {exc}"
+            for p in self.params:
+                p.grad = None
+        return self._graph is not None
+
     def train_step(self, optimizer, dist=None, world=1):
-        loss, parts = self.gradients()
+        graph = getattr(self, '_graph', None)
+        if graph is not None:
+            graph[0].replay()
+            loss, parts = graph[1].detach(), graph[2]
+        else:
+            loss, parts = self.gradients()
         if dist is not None and world > 1:
             self.allreduce_gradients(dist, world)
         optimizer.step()
@@ -301,7 +344,7 @@ class TemperatureDependentTrainer(AtomicNNTrainer):
         U, S = z(), z()
         net = self.nn._net
         for a, el in enumerate(self.elements):
-            sel = torch.nonzero(B['types'] == a).reshape(-1)
+            sel = B['sel'][a]
             if not sel.numel():
                 continue
             hd = self.heads[el]

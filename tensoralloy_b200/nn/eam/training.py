@@ -125,17 +125,19 @@ class _Functions:
             self._shared[tag].requires_grad_(True)      # shared with a trainable function
         return self._shared[tag]
 
+    # (the leaves are created when the function table is built, not at the first call:
+    #  `EamTrainer.params` must list every trainable variable before the first step)
     def _zjw_rho(self, pot, el, fixed):
-        P = lambda k: self._p(pot, el, k, fixed)
-        return lambda r: _zhou_exp(r, P('f_eq'), P('beta'), P('lamda'), P('r_eq'))
+        fe, be, la, re = (self._p(pot, el, k, fixed) for k in ('f_eq', 'beta', 'lamda', 'r_eq'))
+        return lambda r: _zhou_exp(r, fe, be, la, re)
 
     def _zjw_phi(self, pot, term, fixed):
         a, b = get_elements_from_kbody_term(term)
 
         def same(el):
-            P = lambda k: self._p(pot, el, k, fixed)
-            return lambda r: (_zhou_exp(r, P('A'), P('alpha'), P('kappa'), P('r_eq')) -
-                              _zhou_exp(r, P('B'), P('beta'), P('lamda'), P('r_eq')))
+            A, al, ka, B, be, la, re = (self._p(pot, el, k, fixed) for k in
+                                        ('A', 'alpha', 'kappa', 'B', 'beta', 'lamda', 'r_eq'))
+            return lambda r: _zhou_exp(r, A, al, ka, re) - _zhou_exp(r, B, be, la, re)
         if a == b:
             return same(a)
         pa, pb, ra, rb = same(a), same(b), self._zjw_rho(pot, a, fixed), \
@@ -144,19 +146,21 @@ class _Functions:
         return lambda r: 0.5 * (ra(r) / rb(r) * pb(r) + rb(r) / ra(r) * pa(r))
 
     def _zjw_embed(self, pot, el, fixed):
-        P = lambda k: self._p(pot, el, k, fixed)
+        keys = ('Fn0', 'Fn1', 'Fn2', 'Fn3', 'F0', 'F1', 'F2', 'F3', 'eta', 'Fe', 'rho_e',
+                'rho_s')
+        Fn0, Fn1, Fn2, Fn3, F0, F1, F2, F3, eta, Fe, rho_e, rho_s = (
+            self._p(pot, el, k, fixed) for k in keys)
 
         def call(rho):
             # zjw04.py:279-389 (three branches selected by rho)
-            rho_e, rho_s = P('rho_e'), P('rho_s')
             rho_n, rho_0 = 0.85 * rho_e, 1.15 * rho_e
             x1 = rho / rho_n - 1.0
-            e1 = P('Fn0') + P('Fn1') * x1 + P('Fn2') * x1 ** 2 + P('Fn3') * x1 ** 3
+            e1 = Fn0 + Fn1 * x1 + Fn2 * x1 ** 2 + Fn3 * x1 ** 3
             x2 = rho / rho_e - 1.0
-            e2 = P('F0') + P('F1') * x2 + P('F2') * x2 ** 2 + P('F3') * x2 ** 3
+            e2 = F0 + F1 * x2 + F2 * x2 ** 2 + F3 * x2 ** 3
             safe = torch.where(rho >= rho_0, rho, torch.ones_like(rho) * rho_0.detach())
             x3 = safe / rho_s
-            e3 = P('Fe') * (1.0 - P('eta') * torch.log(x3)) * x3 ** P('eta')
+            e3 = Fe * (1.0 - eta * torch.log(x3)) * x3 ** eta
             return torch.where(rho < rho_n, e1, torch.where(rho < rho_0, e2, e3))
         return call
 
@@ -315,12 +319,12 @@ class EamTrainer:
     def allreduce_gradients(self, dist, world):
         allreduce_mean_(self.params, dist, world)
 
-    def train_step(self, optimizer, dist=None, world=1):
-        loss, parts = self.gradients()
-        if dist is not None and world > 1:
-            self.allreduce_gradients(dist, world)
-        optimizer.step()
-        return loss, parts
+    # CUDA-graph capture of loss + backward and the replaying train_step: shared with the
+    # AtomicNN trainer (same structure: fixed batch, static shapes)
+    from tensoralloy_b200.nn.atomic.training import AtomicNNTrainer as _A
+    enable_graph = _A.enable_graph
+    train_step = _A.train_step
+    del _A
 
     def named_parameters(self):
         """reference variable name -> leaf tensor (trainable and fixed)."""

@@ -93,6 +93,8 @@ def _check(nn, kind, structs, n_steps=10):
     for key in ('energy', 'forces', 'stress'):
         assert abs(parts[key].item() - ref_parts[key]) < 1e-9 * max(1.0, abs(ref_parts[key]))
     named = tr.named_parameters()
+    # every trainable variable is known to the optimiser before the first step
+    assert {id(t) for t in named.values() if t.requires_grad} == {id(t) for t in tr.params}
     checked = 0
     for name, r in ref_g.items():
         assert name in named, name
@@ -105,7 +107,13 @@ def _check(nn, kind, structs, n_steps=10):
         assert np.abs(g - r).max() < 1e-7 * scale, (name, np.abs(g - r).max(), scale)
         checked += 1
     assert checked >= 6
+    # the same step captured in one CUDA graph: identical gradients, then training
+    eager = {name: t.grad.clone() for name, t in named.items() if t.grad is not None}
+    assert tr.enable_graph(), getattr(tr, 'graph_error', '')
     opt = torch.optim.Adam(tr.params, lr=1e-3)
+    tr._graph[0].replay()
+    for name, g in eager.items():
+        assert torch.allclose(named[name].grad, g, rtol=1e-12, atol=1e-14), name
     l0 = loss.item()
     for _ in range(n_steps):
         l, _ = tr.train_step(opt)

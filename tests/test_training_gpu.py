@@ -66,6 +66,12 @@ def test_parameter_gradients_match_oracle():
                 g = b.grad.cpu().numpy()
                 r = ref_g[el][1][k]
                 assert np.abs(g - r).max() < 1e-8 * max(1.0, np.abs(r).max()), (el, k)
+        # the same step captured in one CUDA graph gives the same gradients
+        eager = [p.grad.clone() for p in tr.params]
+        assert tr.enable_graph(), getattr(tr, 'graph_error', '')
+        tr._graph[0].replay()
+        for p, g in zip(tr.params, eager):
+            assert torch.allclose(p.grad, g, rtol=1e-12, atol=1e-14)
         # a few Adam steps reduce the loss; parameters flow back into the model
         opt = torch.optim.Adam(tr.params, lr=1e-3)
         l0 = loss.item()

@@ -122,9 +122,11 @@ def c4(n_struct=32):
         tr.add_structure(atoms, -4.0 * len(base), rng.normal(scale=0.3, size=(len(base), 3)),
                          rng.normal(scale=0.01, size=6))
     opt = torch.optim.Adam(tr.params, lr=1e-3)
+    graphed = tr.enable_graph()
     t = timed(lambda: tr.train_step(opt), 5, warm=2)
     return {"config": f"C4 AtomicNN training step, Mo-Ni, {n_struct} structures x 108 atoms, "
-                      f"G2+G4 D=20, MLP [64,32], loss = E/atom + F + stress RMSE, Adam",
+                      f"G2+G4 D=20, MLP [64,32], loss = E/atom + F + stress RMSE, Adam"
+                      f"{', loss + backward as one CUDA graph' if graphed else ''}",
             "ms_per_step": t * 1e3, "structures_per_s": n_struct / t, "dtype": "f64"}
 
 
@@ -147,10 +149,12 @@ def c4_adp(n_struct=256):
         tr.add_structure(atoms, -4.0 * len(base), rng.normal(scale=0.3, size=(len(base), 3)),
                          rng.normal(scale=0.01, size=6))
     opt = torch.optim.Adam(tr.params, lr=1e-3)
+    graphed = tr.enable_graph()
     t = timed(lambda: tr.train_step(opt), 5, warm=2)
     return {"config": f"C4(ii) AdpNN training step, Mo-Ni, {n_struct} structures x 108 atoms, "
                       f"phi / rho / embed / dipole / quadrupole as 'nn' MLPs [32,32], rc 5.0, "
-                      f"loss = E/atom + F + stress RMSE, Adam",
+                      f"loss = E/atom + F + stress RMSE, Adam"
+                      f"{', loss + backward as one CUDA graph' if graphed else ''}",
             "ms_per_step": t * 1e3, "structures_per_s": n_struct / t, "dtype": "f64"}
 
 
