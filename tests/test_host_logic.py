@@ -155,3 +155,32 @@ def test_phonon_masses_and_units():
     ev, amu = 1.602176634e-19, 1.66053906660e-27
     assert abs(VaspToTHz - np.sqrt(ev / amu) / 1e-10 / (2 * np.pi) / 1e12) < 1e-4
     assert abs(VaspToCm / VaspToTHz - 33.356410) < 1e-6
+
+
+def test_c_abi_argument_errors_without_a_gpu():
+    """Status codes and tab_last_error() of the entry points added for batches, pair
+    operators and decomposition: argument / state validation happens before any CUDA call."""
+    import ctypes as C
+    from tensoralloy_b200 import _lib
+    L = _lib.lib()
+    h = C.c_void_p()
+    assert L.tab_nbr_create(C.byref(h)) == 0
+    try:
+        off = (C.c_int32 * 2)(0, 4)
+        cell = (C.c_double * 9)(*np.eye(3).ravel())
+        pbc = (C.c_int32 * 3)(1, 1, 1)
+        EINVAL, ESTATE = -1, -5
+        # no structures / null positions
+        assert L.tab_nbr_build_batch(h, 0, off, None, None, cell, pbc, 5.0, None) == EINVAL
+        assert L.tab_nbr_build_batch(h, 1, off, None, None, cell, pbc, 5.0, None) == EINVAL
+        assert b'tab_nbr_build_batch' in L.tab_last_error()
+        # operators on lists that were never built
+        assert L.tab_pairs_export(h, None, None, C.c_void_p(8), None) == ESTATE
+        assert b'before tab_nbr_build' in L.tab_last_error()
+        assert L.tab_pair_forces(h, C.c_void_p(8), None, None, None) == ESTATE
+        assert L.tab_pair_jvp(h, C.c_void_p(8), C.c_void_p(8), C.c_void_p(8), None) == ESTATE
+        assert L.tab_nbr_batch_size(h) == 0
+        assert L.tab_atomic_eval_dd(None, h, 0, None, None, None, None, None, None) == EINVAL
+        assert L.tab_eam_eval_dd(None, h, 0, None, None, None, None, None, None) == EINVAL
+    finally:
+        L.tab_nbr_free(h)
