@@ -41,6 +41,31 @@ def test_zhou_alcu_tables():
     assert np.abs(mixed - g['rphi_CuAl'])[1:].max() < 1e-12
 
 
+def test_independent_moni_zhou04_tables():
+    """MoNi_Zhou04.eam.alloy (NIST repository, written by Zhou's own Zhou04_create_v2.f --
+    NOT by the reference; the reference compares against it through LAMMPS,
+    nn/eam/tests/test_eam_alloy_nn.py:207-217): pins the Mo parameter set and the Mo-Ni
+    mixing rule.  The Fortran generator clamps r below ~0.5 r_e and uses its own continuation
+    of F above 1.15 rho_e, so the comparison covers r > 1.8 A and the first two branches of F."""
+    g = np.load(os.path.join(GOLD, 'MoNi_Zhou04_setfl.npz'))
+    pot = opot.get_potential('zjw04')
+    nr, dr = int(g['nr']), float(g['dr'])
+    r = torch.tensor(np.arange(nr) * dr)
+    rho = torch.tensor(np.arange(int(g['nrho'])) * float(g['drho']))
+    sel = (r > 1.8).numpy()
+    rs = r[torch.as_tensor(sel)]
+    for el in ('Mo', 'Ni'):
+        assert np.abs(pot.rho(rs, el).numpy() - g[f'rho_{el}'][sel]).max() < 1e-12
+        lim = (rho < 1.15 * pot.params[el]['rho_e']).numpy()
+        F = pot.embed(rho, el).numpy()
+        # the file carries F(0) = 1e-6 for Mo; everything else agrees to rounding
+        assert np.abs(F - g[f'F_{el}'])[lim].max() < 2e-6
+        assert np.abs(F - g[f'F_{el}'])[lim][1:].max() < 2e-6
+    for key, term in (('rphi_MoMo', 'MoMo'), ('rphi_NiMo', 'MoNi'), ('rphi_NiNi', 'NiNi')):
+        assert np.abs((pot.phi(rs, term) * rs).numpy() - g[key][sel]).max() < 1e-12
+    assert np.abs(g['rphi_MoMo'][sel]).max() > 10.0        # not a comparison of zeros
+
+
 def test_neighbor_oracle_known_counts():
     from tensoralloy_b200.atoms import bulk_fcc
     atoms = bulk_fcc('Ni', 3.52, (4, 4, 4))
