@@ -66,6 +66,20 @@ def test_independent_moni_zhou04_tables():
     assert np.abs(g['rphi_MoMo'][sel]).max() > 10.0        # not a comparison of zeros
 
 
+def test_sutton_chen_ag_funcfl_table():
+    """Ag.funcfl.eam, the golden of nn/eam/potentials/tests/test_sutton90.py:47-57 (LAMMPS
+    funcfl: F(rho), Z(r) with phi = 27.2 * 0.529 Z^2 / r eV, rho(r)): pins AgSutton90."""
+    g = np.load(os.path.join(GOLD, 'Ag_funcfl.npz'))
+    pot = opot.get_potential('sutton90')
+    r = torch.tensor(np.arange(len(g['Z'])) * float(g['dr']))
+    rho = torch.tensor(np.arange(len(g['F'])) * float(g['drho']))
+    s = slice(20, None)                       # r >= 0.2 A (the table diverges at r -> 0)
+    assert np.abs(pot.rho(r[s], 'Ag').numpy() / g['rho'][s] - 1.0).max() < 1e-12
+    assert np.abs(pot.embed(rho[1:], 'Ag').numpy() - g['F'][1:]).max() < 1e-12
+    phi = 27.2 * 0.529 * g['Z'][s] ** 2 / r[s].numpy()
+    assert np.abs(pot.phi(r[s], 'AgAg').numpy() / phi - 1.0).max() < 1e-12
+
+
 def test_neighbor_oracle_known_counts():
     from tensoralloy_b200.atoms import bulk_fcc
     atoms = bulk_fcc('Ni', 3.52, (4, 4, 4))
