@@ -402,10 +402,114 @@ class SplineTable(Potential):
         return self._eval('quadrupole', term, r)
 
 
+class AlFeMsah11(Potential):
+    """msah11.py:28-424 -- Mendelev et al. (2011) Al-Fe Finnis-Sinclair potential; no
+    trainable parameters.  phi: screened-Coulomb head, exp(cubic) bridge, sums of
+    a (r_k - r)^n H(r_k - r) H(r - r_lo) tails; rho: sum f_i max(r_i - r, 0)^order."""
+    name = 'msah11'
+
+    PHI = {
+        'AlAl': dict(
+            first=(1e-8, 1.60, [2433.5591473227, 0.1818, -22.713109144730, 0.5099,
+                                -6.6883008584622, 0.2802, -2.8597223982536, 0.02817,
+                                -1.4309258761180]),
+            second=(1.6, 2.25, [6.0801330531321, -2.3092752322555, 0.042696494305190,
+                                -0.07952189194038]),
+            polys=[(2.25, 3.2, [(17.222548257633, 4), (-13.838795389103, 5),
+                                (26.724085544227, 6), (-4.8730831082596, 7),
+                                (0.26111775221382, 8)]),
+                   (2.25, 4.8, [(-1.8864362756631, 4), (2.4323070821980, 5),
+                                (-4.0022263154653, 6), (1.3937173764119, 7),
+                                (-0.31993486318965, 8)]),
+                   (2.25, 6.5, [(0.30601966016455, 4), (-0.63945082587403, 5),
+                                (0.54057725028875, 6), (-0.21210673993915, 7),
+                                (0.03201431888287, 8)])]),
+        'FeFe': dict(
+            first=(1e-8, 1.0, [9734.2365892908, 0.1818, -28.616724320005, 0.5099,
+                               -8.4267310396064, 0.2802, -3.6030244464156, 0.02817,
+                               -1.8028536321603]),
+            second=(1.0, 2.05, [7.4122709384068, -0.64180690713367, -2.6043547961722,
+                                0.62625393931230]),
+            polys=[(2.05, hc, [(a, 3)]) for hc, a in zip(
+                [2.2, 2.3, 2.4, 2.5, 2.6, 2.7, 2.8, 3.0, 3.3, 3.7, 4.2, 4.7, 5.3],
+                [-27.444805994228, 15.738054058489, 2.2077118733936, -2.4989799053251,
+                 4.2099676494795, -0.77361294129713, 0.80656414937789, -2.3194358924605,
+                 2.6577406128280, -1.0260416933564, 0.35018615891957, -0.058531821042271,
+                 -0.0030458824556234])]),
+        'AlFe': dict(
+            first=(1e-8, 1.2, [4867.1182946454, 0.1818, -25.834107666296, 0.5099,
+                               -7.6073373918597, 0.2802, -3.2526756183596, 0.02817,
+                               -1.6275487829767]),
+            second=(1.2, 2.2, [6.6167846784367, -1.5208197629514, -0.73055022396300,
+                               -0.03879272494264]),
+            polys=[(2.2, 3.2, [(-4.148701943924, 4), (5.6697481153271, 5),
+                               (-1.7835153896441, 6), (-3.3886912738827, 7),
+                               (1.9720627768230, 8)]),
+                   (2.2, 6.2, [(0.094200713038410, 4), (-0.16163849208165, 5),
+                               (0.10154590006100, 6), (-0.027624717063181, 7),
+                               (0.0027505576632627, 8)])]),
+    }
+    RHO = {
+        'AlAl': (4, [0.00019850823042883, 0.10046665347629, 1.0054338881951E-01,
+                     0.099104582963213, 0.090086286376778, 0.0073022698419468,
+                     0.014583614223199, -0.0010327381407070, 0.0073219994475288,
+                     0.0095726042919017],
+                 [2.5, 2.6, 2.7, 2.8, 3.0, 3.4, 4.2, 4.8, 5.6, 6.5]),
+        'FeFe': (3, [11.686859407970, -0.014710740098830, 0.47193527075943],
+                 [2.4, 3.2, 4.2]),
+        'AlFe': (4, [0.010015421408039, 0.0098878643929526, 0.0098070326434207,
+                     0.0084594444746494, 0.0038057610928282, -0.0014091094540309,
+                     0.0074410802804324], [2.4, 2.5, 2.6, 2.8, 3.1, 5.0, 6.2]),
+    }
+
+    def defaults(self):
+        return {'Al': {}, 'Fe': {}}
+
+    @staticmethod
+    def _key(term):
+        a, b = _elements_of(term)
+        return a + b if a == b else 'AlFe'
+
+    def phi(self, r, term):
+        d = self.PHI[self._key(term)]
+        zero = torch.zeros_like(r)
+        lo, hi, c = d['first']
+        m = (r >= lo) & (r < hi)
+        x = torch.where(m, r, torch.ones_like(r))
+        y = (c[0] / x) * sum(c[1 + 2 * i] * torch.exp(c[2 + 2 * i] * x) for i in range(4))
+        out = torch.where(m, y, zero)
+        lo, hi, c = d['second']
+        m = (r >= lo) & (r < hi)
+        y = torch.exp(c[0] + c[1] * r + c[2] * r ** 2 + c[3] * r ** 3)
+        out = out + torch.where(m, y, zero)
+        for lo, hi, terms in d['polys']:
+            m = (r >= lo) & (r < hi)
+            x = torch.where(m, hi - r, zero)
+            out = out + sum(a * x ** n for a, n in terms)
+        return out
+
+    def rho(self, r, term):
+        els = _elements_of(term)
+        key = self._key(term) if len(els) == 2 else els[0] + els[0]
+        order, factors, cutoffs = self.RHO[key]
+        return sum(f * torch.clamp(rc - r, min=0.0) ** order
+                   for f, rc in zip(factors, cutoffs))
+
+    def embed(self, rho, element):
+        if element == 'Al':
+            m = rho >= 1e-12
+            x = torch.where(m, rho, torch.ones_like(rho))
+            y = -torch.sqrt(x) + 0.000093283590195398 * x ** 2 - \
+                0.0023491751192724 * x * torch.log(x)
+            return torch.where(m, y, torch.zeros_like(rho))
+        return -torch.sqrt(rho) - 0.00067314115586063 * rho ** 2 + \
+            0.000000076514905604792 * rho ** 4
+
+
 REGISTRY = {
     'zjw04': Zjw04, 'zjw04xc': Zjw04xc, 'zjw04uxc': Zjw04uxc,
     'zjw04xcp': Zjw04xcp, 'sutton90': AgSutton90, 'Be/1': AgrawalBe,
-    'grimes': RWGrimes, 'mishinh': MishinH,
+    'grimes': RWGrimes, 'mishinh': MishinH, 'msah11': AlFeMsah11,
 }
 
 

@@ -80,6 +80,24 @@ def test_sutton_chen_ag_funcfl_table():
     assert np.abs(pot.phi(r[s], 'AgAg').numpy() / phi - 1.0).max() < 1e-12
 
 
+def test_mendelev_al_fe_fs_table():
+    """Mendelev_Al_Fe.fs.eam: the reference exports its AlFeMsah11 functions to setfl and
+    compares them with this file at 1e-8 (nn/eam/tests/test_eam_fs_nn.py:60-83).  Pins the
+    msah11 restatement: piecewise phi (screened Coulomb / exp bridge / polynomial tails),
+    truncated-power densities, both embedding functions."""
+    g = np.load(os.path.join(GOLD, 'Mendelev_AlFe_fs.npz'))
+    pot = opot.get_potential('msah11')
+    r = torch.tensor(np.arange(len(g['rho_AlAl'])) * float(g['dr']))
+    rho = torch.tensor(np.arange(len(g['F_Al'])) * float(g['drho']))
+    for el in ('Al', 'Fe'):
+        assert np.abs(pot.embed(rho, el).numpy() - g['F_' + el]).max() < 1e-11
+    for key in ('AlAl', 'AlFe', 'FeAl', 'FeFe'):
+        assert np.abs(pot.rho(r, key).numpy() - g['rho_' + key]).max() < 1e-11
+    for key, term in (('AlAl', 'AlAl'), ('FeAl', 'AlFe'), ('FeFe', 'FeFe')):
+        assert np.abs((pot.phi(r, term) * r).numpy() - g['rphi_' + key])[1:].max() < 1e-10
+    assert np.abs(g['rphi_FeFe']).max() > 100.0
+
+
 def test_neighbor_oracle_known_counts():
     from tensoralloy_b200.atoms import bulk_fcc
     atoms = bulk_fcc('Ni', 3.52, (4, 4, 4))
