@@ -174,6 +174,16 @@ int tab_nbr_export(const tab_nbr *nbr, int32_t *d_i, int32_t *d_j, int32_t *d_S,
                                      output without bias.  p = n_hidden (<= 4), TAB_ACT_*,
                                      widths (<= 64); weights in the coefficient pool at
                                      4*aux doubles: [w0, b0][W1, b1]...[w_out], W in-major */
+#define TAB_FN_POWCUT_RHO    18   /* msah11.py:303-352  p = order, n, (f_i, rc_i) x n:
+                                   sum f_i max(rc_i - r, 0)^order                      */
+#define TAB_FN_MSAH_PHI      19   /* msah11.py:52-301   piecewise pair function in the
+                                   coefficient pool (aux, units of 4 doubles):
+                                   n_poly, first(lo, hi, c0, (b, c) x 4), second(lo, hi,
+                                   c0..c3), then per tail: lo, hi, n_term, (a, order) x n */
+#define TAB_FN_MSAH_EMBED_AL 20   /* msah11.py:400-411  p = c1, c2:
+                                   -sqrt(x) + c1 x^2 - c2 x ln x  (x >= 1e-12, else 0)  */
+#define TAB_FN_MSAH_EMBED_FE 21   /* msah11.py:412-420  p = c3, c4:
+                                   -sqrt(x) - c3 x^2 + c4 x^4                          */
 #define TAB_FN_MAX_PARAMS    32
 
 typedef struct tab_fn {

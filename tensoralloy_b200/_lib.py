@@ -36,6 +36,10 @@ FN_MISHIN_EMBED = 14
 FN_MISHIN_POLAR = 15
 FN_SPLINE = 16
 FN_MLP = 17
+FN_POWCUT_RHO = 18
+FN_MSAH_PHI = 19
+FN_MSAH_EMBED_AL = 20
+FN_MSAH_EMBED_FE = 21
 
 
 class TabFn(C.Structure):

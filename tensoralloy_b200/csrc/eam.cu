@@ -55,6 +55,7 @@ struct tab_model {
     int n_el = 0;
     bool zhou1 = false;    // single element, all-zjw04: shared-exponential fast path
     bool has_mlp_fn = false;   // some function is an 'nn' MLP (no analytic Hessian)
+    bool no_hessian = false;   // some function kind has no second-derivative evaluator
     Zhou1 z1;              // fe, beta, lamda, 1/re, A, alpha, kappa, B + folded terms
     bool z1_folded = false;   // prefactors positive: the folded float64 terms are usable
     DevBuf tables;         // tab_fn [2*n_el*n_el + n_el (+ 2*n_el*n_el)]
@@ -684,6 +685,7 @@ extern "C" int tab_eam_create(tab_model **out, int32_t kind, int32_t n_el,
                 return TAB_EUNSUPPORTED;
             }
         }
+        if (f.kind >= TAB_FN_POWCUT_RHO && f.kind <= TAB_FN_MSAH_EMBED_FE) m->no_hessian = true;
         if (f.kind == TAB_FN_ZHOU_RHO) f.p[3] = 1.0 / f.p[3];
         else if (f.kind == TAB_FN_ZHOU_PHI) f.p[6] = 1.0 / f.p[6];
         else if (f.kind == TAB_FN_ZHOU_PHI_MIX) {
@@ -736,6 +738,10 @@ int tab_eam_tables(tab_model *m, const tab_fn **rho, const tab_fn **phi,
                    const tab_fn **embed, int *n_el, int *kind) {
     if (m->has_mlp_fn) {
         tab_set_error("analytic Hessian: 'nn' (MLP) functions carry no second derivative");
+        return TAB_EUNSUPPORTED;
+    }
+    if (m->no_hessian) {
+        tab_set_error("analytic Hessian: the msah11 functions carry no second derivative yet");
         return TAB_EUNSUPPORTED;
     }
     const int nn = m->n_el * m->n_el;

@@ -373,6 +373,61 @@ __device__ __forceinline__ void spline_eval(const tab_fn &fn, const double *__re
     df = (Real(3) * c3 * d + Real(2) * c2) * d + c1;
 }
 
+// x^n and n x^(n-1) for small integer n
+template <typename Real>
+__device__ __forceinline__ void ipow_d(Real x, int n, Real &v, Real &dv) {
+    Real p1 = Real(1);
+    for (int k = 1; k < n; ++k) p1 *= x;
+    dv = (Real)n * p1;
+    v = p1 * x;
+}
+
+// msah11.py:52-157 -- the pair function of the Mendelev Al-Fe potential: a screened-Coulomb
+// head (c0 / r) sum b_i exp(c_i r) on [lo, hi), an exp(cubic) bridge, and tails
+// sum_k a_k (hi - r)^n_k on [lo, hi).  Constants in the coefficient pool (layout: tab200.h).
+template <typename Real>
+__device__ __forceinline__ void msah_phi(const double *__restrict__ c, Real r, Real &f,
+                                         Real &df) {
+    f = Real(0);
+    df = Real(0);
+    const int n_poly = (int)c[0];
+    const double *q = c + 1;
+    if ((double)r >= q[0] && (double)r < q[1]) {
+        Real s = Real(0), ds = Real(0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const Real b = (Real)q[3 + 2 * i], ci = (Real)q[4 + 2 * i];
+            const Real e = b * Math<Real>::exp_(ci * r);
+            s += e;
+            ds += ci * e;
+        }
+        const Real sc = (Real)q[2] / r;
+        f += sc * s;
+        df += sc * ds - sc * s / r;
+    }
+    q += 11;
+    if ((double)r >= q[0] && (double)r < q[1]) {
+        const Real c1 = (Real)q[3], c2 = (Real)q[4], c3 = (Real)q[5];
+        const Real e = Math<Real>::exp_((Real)q[2] + r * (c1 + r * (c2 + r * c3)));
+        f += e;
+        df += e * (c1 + r * (Real(2) * c2 + Real(3) * c3 * r));
+    }
+    q += 6;
+    for (int g = 0; g < n_poly; ++g) {
+        const int nt = (int)q[2];
+        if ((double)r >= q[0] && (double)r < q[1]) {
+            const Real x = (Real)q[1] - r;
+            for (int k = 0; k < nt; ++k) {
+                Real v, dv;
+                ipow_d<Real>(x, (int)q[4 + 2 * k], v, dv);
+                f += (Real)q[3 + 2 * k] * v;
+                df -= (Real)q[3 + 2 * k] * dv;
+            }
+        }
+        q += 3 + 2 * nt;
+    }
+}
+
 // NN = the model holds 'nn' (MLP) functions: only then is mlp_fn_eval (local arrays, a
 // stack frame and ~2x the registers) compiled into the calling kernel.
 template <typename Real, bool NN = false>
@@ -388,6 +443,24 @@ __device__ __forceinline__ void eval_pair_fn(const tab_fn &fn, Real r, Real &f,
     case TAB_FN_SPLINE:
         spline_eval<Real>(fn, pool, r, f, df);
         break;
+    case TAB_FN_MSAH_PHI:   // msah11.py:52-301
+        msah_phi<Real>(pool + (size_t)fn.aux * 4, r, f, df);
+        break;
+    case TAB_FN_POWCUT_RHO: {   // msah11.py:303-352
+        const int order = (int)p[0], n = (int)p[1];
+        f = Real(0);
+        df = Real(0);
+        for (int i = 0; i < n; ++i) {
+            const Real x = (Real)p[3 + 2 * i] - r;
+            if (x > Real(0)) {
+                Real v, dv;
+                ipow_d<Real>(x, order, v, dv);
+                f += (Real)p[2 + 2 * i] * v;
+                df -= (Real)p[2 + 2 * i] * dv;
+            }
+        }
+        break;
+    }
     case TAB_FN_ZHOU_RHO:   // zjw04.py:245-277
         zhou_exp<Real>(r, (Real)p[0], (Real)p[1], (Real)p[2], (Real)p[3], f, df);
         break;
@@ -510,6 +583,31 @@ __device__ __forceinline__ void eval_embed_fn(const tab_fn &fn, Real rho, Real &
     case TAB_FN_SPLINE:
         spline_eval<Real>(fn, pool, rho, F, dF);
         break;
+    case TAB_FN_MSAH_EMBED_AL: {   // msah11.py:400-411
+        if (rho >= Real(1e-12)) {
+            const Real c1 = (Real)fn.p[0], c2 = (Real)fn.p[1];
+            const Real sq = Math<Real>::sqrt_(rho), lg = Math<Real>::log_(rho);
+            F = -sq + c1 * rho * rho - c2 * rho * lg;
+            dF = Real(-0.5) / sq + Real(2) * c1 * rho - c2 * (lg + Real(1));
+        } else {
+            F = Real(0);
+            dF = Real(0);
+        }
+        break;
+    }
+    case TAB_FN_MSAH_EMBED_FE: {   // msah11.py:412-420
+        const Real c3 = (Real)fn.p[0], c4 = (Real)fn.p[1];
+        const Real r2 = rho * rho;
+        if (rho > Real(0)) {
+            const Real sq = Math<Real>::sqrt_(rho);
+            F = -sq - c3 * r2 + c4 * r2 * r2;
+            dF = Real(-0.5) / sq - Real(2) * c3 * rho + Real(4) * c4 * r2 * rho;
+        } else {
+            F = Real(0);
+            dF = Real(0);
+        }
+        break;
+    }
     case TAB_FN_ZHOU_EMBED:
         zhou_embed<Real>(fn.p, false, rho, F, dF);
         break;

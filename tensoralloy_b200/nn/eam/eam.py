@@ -156,7 +156,7 @@ class EamNN(BasicNN):
         # tabulated and 'nn' functions: one coefficient pool per model (units of 4
         # doubles); rebase the offsets of every provider after the first
         splines = [f for k, f in self._empirical_functions.items()
-                   if k.startswith("spline@") or k == 'nn']
+                   if k.startswith("spline@") or k in ('nn', 'msah11')]
         base = 0
         pools = []
         for sp in splines:

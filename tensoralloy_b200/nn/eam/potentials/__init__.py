@@ -4,7 +4,7 @@ Potential-function registry: maps the reference's potential names
 libtab200.  The arithmetic itself lives in csrc/potentials.cuh.
 """
 from tensoralloy_b200.nn.eam.potentials.empirical import (
-    AgrawalBe, AgSutton90, MishinH, RWGrimes)
+    AgrawalBe, AgSutton90, AlFeMsah11, MishinH, RWGrimes)
 from tensoralloy_b200.nn.eam.potentials.zjw04 import (
     Zjw04, Zjw04xc, Zjw04uxc, Zjw04xcp)
 
@@ -17,11 +17,8 @@ available_potentials = {
     'grimes': RWGrimes,
     'mishinh': MishinH,
     'Be/1': AgrawalBe,
+    'msah11': AlFeMsah11,
 }
-# `msah11` (Al-Fe Finnis-Sinclair, nn/eam/potentials/msah11.py) is a fixed table of
-# piecewise constants; it is served through the tabulated-spline path (setfl file
-# test_files/lammps/Mendelev_Al_Fe.fs.eam), not re-typed here.
-
 
 def get_potential(name):
     try:

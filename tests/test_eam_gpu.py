@@ -344,3 +344,43 @@ def test_nn_parametrised_functions(case):
         calc32 = TensorAlloyCalculator(nn)
         calc32.calculate(atoms, properties=['energy', 'forces'])
     assert abs(calc32.results['energy'] - ref['energy']) <= 2e-5 * max(abs(ref['energy']), 1.0)
+
+
+def test_msah11_al_fe_finnis_sinclair():
+    """AlFeMsah11 (nn/eam/potentials/msah11.py:28-424) through EamFsNN: piecewise pair
+    function from the coefficient pool, truncated-power densities, both embeddings.  The
+    oracle restatement is pinned to the reference's golden table (test_oracle_golden)."""
+    from tensoralloy_b200.atoms import Atoms
+    from tensoralloy_b200.calculator import TensorAlloyCalculator
+    from tensoralloy_b200.nn.eam import EamFsNN
+    from tensoralloy_b200.precision import precision_scope
+    pot = opot.get_potential('msah11')
+    rng = np.random.default_rng(17)
+    for a0, frac, sigma in ((4.05, 0.25, 0.08), (3.7, 0.7, 0.15)):
+        base = bulk_fcc('Al', a0, (3, 3, 3))
+        sym = ['Fe' if x < frac else 'Al' for x in rng.random(len(base))]
+        atoms = Atoms(sym, base.positions + rng.normal(scale=sigma, size=base.positions.shape),
+                      base.cell, True)
+        nn = EamFsNN(['Al', 'Fe'], custom_potentials='msah11',
+                     export_properties=('energy', 'forces', 'stress'))
+        ref = _calc_compare(nn, atoms, pot, 'fs', 6.5)
+        assert np.abs(ref['forces']).max() > 0.1
+        with precision_scope('medium'):
+            c32 = TensorAlloyCalculator(nn)
+            c32.calculate(atoms, properties=['energy', 'forces'])
+            # the reference itself warns against float32 for this potential
+            # (msah11.py:23-25): the polynomial tails cancel to ~1e-4 relative in float32
+            assert abs(c32.results['energy'] - ref['energy']) <= 5e-4 * abs(ref['energy'])
+    # pure elements (one species in the list)
+    fe = _rattled('Fe', 3.6, (3, 3, 3), 4)
+    _calc_compare(EamFsNN(['Fe'], custom_potentials='msah11'), fe, pot, 'fs', 5.3)
+    # no second derivatives for these kinds: the Hessian call fails loudly
+    with precision_scope('high'):
+        nn = EamFsNN(['Al', 'Fe'], custom_potentials='msah11',
+                     export_properties=('energy', 'forces', 'hessian'))
+        from tensoralloy_b200.transformer import UniversalTransformer
+        nn.attach_transformer(UniversalTransformer(['Al', 'Fe'], rcut=6.5))
+        small = Atoms(['Al', 'Fe', 'Al', 'Fe'], bulk_fcc('Al', 4.0, (1, 1, 1)).positions,
+                      bulk_fcc('Al', 4.0, (1, 1, 1)).cell, True)
+        with pytest.raises(Exception):
+            TensorAlloyCalculator(nn).calculate(small, properties=['hessian'])
