@@ -233,6 +233,14 @@ int tab_eam_pass2(tab_model *model, tab_nbr *nbr, int32_t precision,
                   const double *d_fprime_halo, double *d_energy, double *d_eatom,
                   double *d_forces, double *d_virial, void *stream);
 
+/* Tabulate ONE function of the model on a grid: the evaluator behind `export_to_setfl`
+ * (nn/eam/alloy.py:198-381, fs.py:205-..., adp.py:588-794, which run the TF graph on
+ * r = k dr, rho = k drho).  which: 0 rho, 1 phi, 2 embed, 3 dipole, 4 quadrupole; index:
+ * a * n_el + b (centre a, neighbour b) for pair functions, the element for the embedding.
+ * d_x, d_y [n] float64, d_dy (derivative) may be NULL. */
+int tab_eam_tabulate(tab_model *model, int32_t which, int32_t index, int32_t n,
+                     const double *d_x, double *d_y, double *d_dy, void *stream);
+
 /* Spatial decomposition without a second exchange: lists built by tab_nbr_build_dd over
  * [own atoms | inner halo (<= rc from the slab)] as the row-owning group + the outer halo
  * (rc .. 2 rc); rho, F', ADP moments and forces of the inner halo are recomputed on this

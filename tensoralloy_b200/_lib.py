@@ -103,7 +103,7 @@ EXPORTS = [
     'tab_atomic_descriptors', 'tab_atomic_forces', 'tab_atomic_jvp',
     'tab_launch_count', 'tab_launch_count_reset',
     'tab_nbr_build_batch', 'tab_nbr_batch_size',
-    'tab_pairs_export', 'tab_pair_forces', 'tab_pair_jvp', 'tab_atomic_eval_dd', 'tab_eam_eval_dd',
+    'tab_pairs_export', 'tab_pair_forces', 'tab_pair_jvp', 'tab_atomic_eval_dd', 'tab_eam_eval_dd', 'tab_eam_tabulate',
     'tab_profile_enable', 'tab_profile_read',
 ]
 
@@ -163,6 +163,7 @@ def lib():
     L.tab_atomic_descriptors.argtypes = [vp, vp, i32, vp, vp]
     L.tab_atomic_eval_dd.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, vp]
     L.tab_eam_eval_dd.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, vp]
+    L.tab_eam_tabulate.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp]
     L.tab_atomic_forces.argtypes = [vp, vp, i32, vp, vp, vp, vp]
     L.tab_atomic_jvp.argtypes = [vp, vp, i32, vp, vp, vp, vp]
     L.tab_profile_enable.argtypes = [i32]
@@ -400,6 +401,20 @@ class EamModel:
         check(lib().tab_eam_eval_dd(self._h, nbr.handle, int(precision), _ptr(mask),
                                     _ptr(energy), _ptr(eatom), _ptr(forces), _ptr(virial),
                                     _stream()), 'tab_eam_eval_dd')
+
+    TABLES = {'rho': 0, 'phi': 1, 'embed': 2, 'dipole': 3, 'quadrupole': 4}
+
+    def tabulate(self, which, index, x):
+        """Values and derivatives of one function of the model on the grid `x` (numpy
+        float64): tab_eam_tabulate."""
+        import torch
+        d_x = torch.as_tensor(np.ascontiguousarray(x, dtype=np.float64)).to('cuda')
+        d_y = torch.empty_like(d_x)
+        d_dy = torch.empty_like(d_x)
+        check(lib().tab_eam_tabulate(self._h, self.TABLES[which], int(index), int(d_x.numel()),
+                                     _ptr(d_x), _ptr(d_y), _ptr(d_dy), _stream()),
+              'tab_eam_tabulate')
+        return d_y.cpu().numpy(), d_dy.cpu().numpy()
 
     def pass1(self, nbr, precision, fprime=None):
         check(lib().tab_eam_pass1(self._h, nbr.handle, int(precision), _ptr(fprime),

@@ -1135,6 +1135,65 @@ extern "C" int tab_eam_eval_dd(tab_model *m, tab_nbr *nbr, int32_t precision,
     EAM_DISPATCH(eam_pass2, m, nbr, nullptr, d_energy, d_eatom, d_forces, d_virial, st, d_mask);
 }
 
+// Tabulation of one function of the model on a caller-supplied grid (export_to_setfl):
+// which = 0 rho, 1 phi, 2 embed, 3 dipole, 4 quadrupole; index = a * n_el + b (centre a,
+// neighbour b) for the pair functions, the element for the embedding.  float64.
+template <bool NN>
+__global__ void k_eam_tabulate(EamDev m, const tab_fn *__restrict__ fnp, int is_embed, int n,
+                               const double *__restrict__ x, double *__restrict__ y,
+                               double *__restrict__ dy) {
+    __shared__ tab_fn fn;
+    if (threadIdx.x == 0) fn = *fnp;
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double f, df;
+    if (is_embed) eval_embed_fn<double, NN>(fn, x[i], f, df, m.pool);
+    else eval_pair_fn<double, NN>(fn, x[i], f, df, m.pool);
+    y[i] = f;
+    if (dy) dy[i] = df;
+}
+
+extern "C" int tab_eam_tabulate(tab_model *m, int32_t which, int32_t index, int32_t n,
+                                const double *d_x, double *d_y, double *d_dy, void *stream) {
+    if (!m || n <= 0 || !d_x || !d_y) {
+        tab_set_error("tab_eam_tabulate: bad argument");
+        return TAB_EINVAL;
+    }
+    const int nn = m->n_el * m->n_el;
+    const bool adp = m->kind == TAB_EAM_ADP;
+    int off, count;
+    switch (which) {
+    case 0: off = 0; count = nn; break;
+    case 1: off = nn; count = nn; break;
+    case 2: off = 2 * nn; count = m->n_el; break;
+    case 3: off = 2 * nn + m->n_el; count = adp ? nn : 0; break;
+    case 4: off = 3 * nn + m->n_el; count = adp ? nn : 0; break;
+    default: off = 0; count = 0;
+    }
+    if (index < 0 || index >= count) {
+        tab_set_error("tab_eam_tabulate: no function %d of kind %d in this model", index, which);
+        return TAB_EINVAL;
+    }
+    EamDev dev;
+    dev.kind = m->kind;
+    dev.n_el = m->n_el;
+    dev.rho = m->tables.as<tab_fn>();
+    dev.phi = dev.rho + nn;
+    dev.embed = dev.rho + 2 * nn;
+    dev.pool = m->pool.as<double>();
+    cudaStream_t st = (cudaStream_t)stream;
+    const tab_fn *fnp = m->tables.as<tab_fn>() + off + index;
+    if (m->has_mlp_fn)
+        k_eam_tabulate<true><<<(n + 127) / 128, 128, 0, st>>>(dev, fnp, which == 2, n, d_x, d_y,
+                                                              d_dy);
+    else
+        k_eam_tabulate<false><<<(n + 127) / 128, 128, 0, st>>>(dev, fnp, which == 2, n, d_x,
+                                                               d_y, d_dy);
+    TAB_LAUNCH_CHECK();
+    return TAB_OK;
+}
+
 // Host-buffer convenience: see include/tab200.h.
 struct HostStage {
     DevBuf pos, types, out;

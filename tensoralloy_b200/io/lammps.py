@@ -133,3 +133,31 @@ def write_setfl(filename, setfl: SetFL, comments=("", "", ""), is_adp=False):
                 out.extend(f"{v: 20.16e}" for v in table[key].y)
     with open(filename, 'w') as fp:
         fp.write("\n".join(out) + "\n")
+
+
+def write_fs_setfl(filename, elements, nrho, drho, nr, dr, rcut, embed, rho, phi,
+                   atomic_masses, lattice_constants, lattice_types, comments=("", "", "")):
+    """eam/fs (Finnis-Sinclair) setfl layout, as written by the reference's
+    `EamFsNN.export_to_setfl` (fs.py:205-..., atsim `writeSetFLFinnisSinclair`): per element
+    a header, F(rho) and then ONE density table per partner element (the density at a centre
+    of that element from a neighbour of the partner); then r * phi for the pairs (i, j <= i).
+    embed[el] [nrho]; rho[el_centre + el_neighbour] [nr]; phi[sorted pair key] [nr]."""
+    from tensoralloy_b200.atoms import atomic_numbers
+    out = [str(c) for c in comments[:3]]
+    out.append(f"{len(elements)} " + " ".join(elements))
+    out.append(f"{nrho} {drho:.16e} {nr} {dr:.16e} {rcut:.16e}")
+    for k, el in enumerate(elements):
+        out.append(f"{atomic_numbers.get(el, 0)} {atomic_masses[k]:.16e} "
+                   f"{lattice_constants[k]:.16e} {lattice_types[k]}")
+        out.extend(f"{v: 20.16e}" for v in embed[el])
+        for other in elements:
+            out.extend(f"{v: 20.16e}" for v in rho[f"{el}{other}"])
+    r = np.linspace(0.0, nr * dr, nr, endpoint=False)
+    for i in range(len(elements)):
+        for j in range(i + 1):
+            key = "".join(sorted([elements[i], elements[j]]))
+            y = np.asarray(phi[key], dtype=np.float64) * r
+            y[0] = 0.0 if not np.isfinite(y[0]) else y[0]
+            out.extend(f"{v: 20.16e}" for v in y)
+    with open(filename, 'w') as fp:
+        fp.write("\n".join(out) + "\n")

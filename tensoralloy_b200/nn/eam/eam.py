@@ -181,6 +181,72 @@ class EamNN(BasicNN):
     def _evaluate(self, features, want_forces, want_virial, want_atomic):
         return self._evaluate_single(features, want_forces, want_virial, want_atomic)
 
+    # -- LAMMPS tables ---------------------------------------------------------
+    def export_to_setfl(self, setfl: str, nr: int, dr: float, nrho: int, drho: float,
+                        r0=1.0, rt=None, rho0=0.0, rhot=None, checkpoint=None,
+                        lattice_constants=None, lattice_types=None,
+                        use_ema_variables=True):
+        """Export this model to a LAMMPS setfl table (eam/alloy, eam/fs or adp by model
+        kind) -- the reference's `export_to_setfl` (alloy.py:198-381, fs.py, adp.py:588-794).
+        The functions are tabulated by the GPU evaluators that also serve the energy /
+        force kernels (`tab_eam_tabulate`) on r = k dr and rho = k drho, k = 0 .. n-1.  The
+        plotting arguments (r0, rt, rho0, rhot) and the checkpoint arguments of the reference
+        are accepted and ignored (no figures are drawn; the variables are the model's)."""
+        from tensoralloy_b200.io import lammps as io
+        from tensoralloy_b200.precision import precision_scope
+        lattice_constants = lattice_constants or {}
+        lattice_types = lattice_types or {}
+        els = self._elements
+        n_el = len(els)
+        with precision_scope('high'):
+            model = self._device_model()
+            r = np.arange(nr) * float(dr)
+            rho_grid = np.arange(nrho) * float(drho)
+            tab = lambda which, idx, x: model.tabulate(which, idx, x)[0]
+            embed = {el: tab('embed', a, rho_grid) for a, el in enumerate(els)}
+            pair_keys = [("".join(sorted([els[i], els[j]])), i, j)
+                         for i in range(n_el) for j in range(i, n_el)]
+            phi = {key: tab('phi', i * n_el + j, r) for key, i, j in pair_keys}
+        masses = self._atomic_masses()
+        lat = [float(lattice_constants.get(el, 0.0)) for el in els]
+        typ = [lattice_types.get(el, 'fcc') for el in els]
+        rcut = float(nr) * float(dr)
+        comments = (f"Contributor: tensoralloy_b200 ({self.__class__.__name__})",
+                    "LAMMPS setfl format",
+                    f"Conversion by tensoralloy_b200.nn.eam.{self.__class__.__name__}")
+        if self.kind == _lib.EAM_FS:
+            with precision_scope('high'):
+                rho = {f"{a}{b}": tab('rho', i * n_el + j, r)
+                       for i, a in enumerate(els) for j, b in enumerate(els)}
+            io.write_fs_setfl(setfl, els, nrho, drho, nr, dr, rcut, embed, rho, phi, masses,
+                              lat, typ, comments)
+            return
+        with precision_scope('high'):
+            # eam/alloy: the density contributed BY an atom of `el` (alloy.py:162-176)
+            rho = {el: tab('rho', j, r) for j, el in enumerate(els)}
+            dip = quad = {}
+            if self.kind == _lib.EAM_ADP:
+                dip = {key: tab('dipole', i * n_el + j, r) for key, i, j in pair_keys}
+                quad = {key: tab('quadrupole', i * n_el + j, r) for key, i, j in pair_keys}
+        # the file lists pairs as (i, j <= i) keyed el_i el_j in the reader's sequence
+        order = [f"{els[i]}{els[j]}" for i in range(n_el) for j in range(i, n_el)]
+        rekey = lambda d: {f"{els[i]}{els[j]}": d[key] for key, i, j in pair_keys} if d else {}
+        sp = lambda n, dx, y: io._spline(n, dx, y)
+        table = io.SetFL(
+            elements=list(els), rho={el: sp(nr, dr, rho[el]) for el in els},
+            phi={k: sp(nr, dr, v) for k, v in rekey(phi).items()},
+            embed={el: sp(nrho, drho, embed[el]) for el in els},
+            dipole={k: sp(nr, dr, v) for k, v in rekey(dip).items()},
+            quadrupole={k: sp(nr, dr, v) for k, v in rekey(quad).items()},
+            nr=nr, dr=dr, nrho=nrho, drho=drho, rcut=rcut, atomic_masses=masses,
+            lattice_constants=lat, lattice_types=typ)
+        assert list(table.phi) == order
+        io.write_setfl(setfl, table, comments, is_adp=self.kind == _lib.EAM_ADP)
+
+    def _atomic_masses(self):
+        from tensoralloy_b200.analysis.phonon import _MASSES
+        return [float(_MASSES.get(el, 0.0)) for el in self._elements]
+
     def _hessian(self, features):
         """[Nvap, 3, Nvap, 3] Hessian in GSL order incl. the virtual atom, the
         layout of the reference's `Output/Hessian` op (basic.py:410-421)."""
