@@ -685,7 +685,6 @@ extern "C" int tab_eam_create(tab_model **out, int32_t kind, int32_t n_el,
                 return TAB_EUNSUPPORTED;
             }
         }
-        if (f.kind >= TAB_FN_POWCUT_RHO && f.kind <= TAB_FN_MSAH_EMBED_FE) m->no_hessian = true;
         if (f.kind == TAB_FN_ZHOU_RHO) f.p[3] = 1.0 / f.p[3];
         else if (f.kind == TAB_FN_ZHOU_PHI) f.p[6] = 1.0 / f.p[6];
         else if (f.kind == TAB_FN_ZHOU_PHI_MIX) {
@@ -741,7 +740,8 @@ int tab_eam_tables(tab_model *m, const tab_fn **rho, const tab_fn **phi,
         return TAB_EUNSUPPORTED;
     }
     if (m->no_hessian) {
-        tab_set_error("analytic Hessian: the msah11 functions carry no second derivative yet");
+        tab_set_error("analytic Hessian: a function kind of this model carries no second "
+                      "derivative evaluator");
         return TAB_EUNSUPPORTED;
     }
     const int nn = m->n_el * m->n_el;

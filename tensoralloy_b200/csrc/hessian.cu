@@ -101,11 +101,46 @@ __device__ inline D2 spline_d2(const tab_fn &fn, const double *pool, D2 x) {
 
 __device__ const double *g_hess_pool = nullptr;   // set per launch (single stream use)
 
+// msah11.py:52-301 (layout of the constants: tab200.h, TAB_FN_MSAH_PHI)
+__device__ inline D2 msah_phi_d2(const double *c, D2 r) {
+    D2 out(0.0);
+    const int n_poly = (int)c[0];
+    const double *q = c + 1;
+    if (r.v >= q[0] && r.v < q[1]) {
+        D2 s(0.0);
+        for (int i = 0; i < 4; ++i) s = s + D2(q[3 + 2 * i]) * dexp(D2(q[4 + 2 * i]) * r);
+        out = out + D2(q[2]) * s / r;
+    }
+    q += 11;
+    if (r.v >= q[0] && r.v < q[1])
+        out = out + dexp(D2(q[2]) + r * (D2(q[3]) + r * (D2(q[4]) + r * D2(q[5]))));
+    q += 6;
+    for (int g = 0; g < n_poly; ++g) {
+        const int nt = (int)q[2];
+        if (r.v >= q[0] && r.v < q[1]) {
+            const D2 x = D2(q[1]) - r;
+            for (int k = 0; k < nt; ++k) out = out + D2(q[3 + 2 * k]) * dpow(x, q[4 + 2 * k]);
+        }
+        q += 3 + 2 * nt;
+    }
+    return out;
+}
+
 __device__ inline D2 eval_pair_d2(const tab_fn &fn, D2 r) {
     const double *p = fn.p;
     switch (fn.kind) {
     case TAB_FN_SPLINE:
         return spline_d2(fn, g_hess_pool, r);
+    case TAB_FN_MSAH_PHI:
+        return msah_phi_d2(g_hess_pool + (size_t)fn.aux * 4, r);
+    case TAB_FN_POWCUT_RHO: {   // msah11.py:303-352
+        D2 out(0.0);
+        const int n = (int)p[1];
+        for (int i = 0; i < n; ++i)
+            if (p[3 + 2 * i] - r.v > 0.0)
+                out = out + D2(p[2 + 2 * i]) * dpow(D2(p[3 + 2 * i]) - r, p[0]);
+        return out;
+    }
     case TAB_FN_ZHOU_RHO:
         return v_zhou(r, p[0], p[1], p[2], p[3]);
     case TAB_FN_ZHOU_PHI:
@@ -181,6 +216,14 @@ __device__ inline D2 eval_embed_d2(const tab_fn &fn, D2 rho) {
     switch (fn.kind) {
     case TAB_FN_SPLINE:
         return spline_d2(fn, g_hess_pool, rho);
+    case TAB_FN_MSAH_EMBED_AL:   // msah11.py:400-411
+        if (rho.v < 1e-12) return D2(0.0);
+        return -dsqrt(rho) + D2(p[0]) * rho * rho - D2(p[1]) * rho * dlog(rho);
+    case TAB_FN_MSAH_EMBED_FE: { // msah11.py:412-420
+        if (!(rho.v > 0.0)) return D2(0.0);
+        const D2 r2 = rho * rho;
+        return -dsqrt(rho) - D2(p[0]) * r2 + D2(p[1]) * r2 * r2;
+    }
     case TAB_FN_ZHOU_EMBED:
         return v_zhou_embed(p, false, rho);
     case TAB_FN_ZHOU_EMBED_XC:

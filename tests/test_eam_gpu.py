@@ -374,13 +374,21 @@ def test_msah11_al_fe_finnis_sinclair():
     # pure elements (one species in the list)
     fe = _rattled('Fe', 3.6, (3, 3, 3), 4)
     _calc_compare(EamFsNN(['Fe'], custom_potentials='msah11'), fe, pot, 'fs', 5.3)
-    # no second derivatives for these kinds: the Hessian call fails loudly
+    # analytic Hessian of the msah11 kinds (second-order dual numbers) vs oracle autograd
     with precision_scope('high'):
         nn = EamFsNN(['Al', 'Fe'], custom_potentials='msah11',
                      export_properties=('energy', 'forces', 'hessian'))
         from tensoralloy_b200.transformer import UniversalTransformer
         nn.attach_transformer(UniversalTransformer(['Al', 'Fe'], rcut=6.5))
-        small = Atoms(['Al', 'Fe', 'Al', 'Fe'], bulk_fcc('Al', 4.0, (1, 1, 1)).positions,
-                      bulk_fcc('Al', 4.0, (1, 1, 1)).cell, True)
-        with pytest.raises(Exception):
-            TensorAlloyCalculator(nn).calculate(small, properties=['hessian'])
+        base = bulk_fcc('Al', 4.0, (2, 2, 2))
+        sym = ['Fe' if x < 0.4 else 'Al' for x in rng.random(len(base))]
+        small = Atoms(sym, base.positions + rng.normal(scale=0.08, size=base.positions.shape),
+                      base.cell, True)
+        calc = TensorAlloyCalculator(nn)
+        calc.calculate(small, properties=['energy', 'forces', 'hessian'])
+        H = calc.get_hessian(small)
+    ref = oeam.eam_evaluate(pot, 'fs', ['Al', 'Fe'], sym, small.positions, small.cell,
+                            [1, 1, 1], 6.5, hessian=True)
+    n = len(small)
+    assert np.abs(H - ref['hessian'].reshape(3 * n, 3 * n)).max() < 1e-8
+    assert np.abs(H).max() > 1.0
