@@ -164,12 +164,76 @@ class _Functions:
             return torch.where(rho < rho_n, e1, torch.where(rho < rho_0, e2, e3))
         return call
 
+    # -- further empirical forms (same formulas as csrc/potentials.cuh) -------------------
+    def _pair_section(self, pot, term):
+        a, b = get_elements_from_kbody_term(term)
+        params = self.nn._empirical_functions[pot].params
+        return f"{a}{b}" if f"{a}{b}" in params else f"{b}{a}"
+
+    def _sutton(self, fn, section, fixed):
+        # sutton90.py:43-97
+        if fn == 'rho':
+            el = get_elements_from_kbody_term(section)[-1]
+            a = self._p('sutton90', el, 'a', fixed)
+            return lambda r: (a / r) ** 6
+        if fn == 'phi':
+            b = self._p('sutton90', self._pair_section('sutton90', section), 'b', fixed)
+            return lambda r: (b / r) ** 12
+        return lambda rho: -torch.sqrt(rho)
+
+    def _agrawal(self, fn, section, fixed):
+        # agrawal.py:57-152
+        el = get_elements_from_kbody_term(section)[-1] if fn == 'rho' else \
+            get_elements_from_kbody_term(section)[0]
+        P = lambda k: self._p('Be/1', el, k, fixed)
+        if fn == 'rho':
+            A, B, re, rc, m = P('A'), P('B'), P('re'), P('rc'), P('m')
+
+            def rho(r):
+                tail = A * torch.exp(-B * (rc - re))
+                return A * torch.exp(-B * (r - re)) - tail + \
+                    rc / m * (1.0 - (r / rc) ** m) * (-B * tail)
+            return rho
+        if fn == 'phi':
+            D, al, re, rc, m = P('D'), P('alpha'), P('re'), P('rc'), P('m')
+            morse = lambda x: D * (torch.exp(-2.0 * al * (x - re)) -
+                                   2.0 * torch.exp(-al * (x - re)))
+            dmorse = lambda x: (torch.exp(-al * (x - re)) -
+                                torch.exp(-2.0 * al * (x - re))) * (D * al * 2.0)
+            return lambda r: morse(r) - morse(rc) + rc / m * ((1.0 - (r / rc) ** m) *
+                                                              dmorse(rc))
+        F0, F1, be, ga = P('F0'), P('F1'), P('beta'), P('gamma')
+        return lambda rho: F0 * (1.0 - be * torch.log(torch.clamp(rho, min=1e-12))) * \
+            rho ** be + F1 * rho ** ga
+
+    def _grimes(self, fn, section, fixed):
+        # grimmes.py:41-101
+        if fn == 'phi':
+            sec = self._pair_section('grimes', section)
+            A, rh, C, D, ga, r0 = (self._p('grimes', sec, k, fixed)
+                                   for k in ('A', 'rho', 'C', 'D', 'gamma', 'r0'))
+            return lambda r: D * (torch.exp(-2.0 * ga * (r - r0)) -
+                                  2.0 * torch.exp(-ga * (r - r0))) + \
+                A * torch.exp(-r / rh) - C / r ** 6
+        el = get_elements_from_kbody_term(section)[-1]
+        if fn == 'rho':
+            n = self._p('grimes', el, 'n', fixed)
+            return lambda r: n / r ** 8 * (0.5 + 0.5 * torch.erf(20.0 * (r - 1.5)))
+        G = self._p('grimes', el, 'G', fixed)
+        return lambda rho: -G * torch.sqrt(rho)
+
     # -- dispatch -----------------------------------------------------------------------
     def get(self, fn, section):
         name = self.nn.potentials[section][fn]
         fixed = self._fixed(fn, section)
         if name == 'nn':
             return self._mlp(fn, section)
+        if name == 'sutton90' and fn in ('rho', 'phi', 'embed'):
+            return self._sutton(fn, section, fixed)
+        if name == 'Be/1' and fn in ('rho', 'phi', 'embed'):
+            return self._agrawal(fn, section, fixed)
+        if name == 'grimes' and fn in ('rho', 'phi', 'embed'):
+            return self._grimes(fn, section, fixed)
         if name in self.ZJW:
             if fn == 'rho':
                 return self._zjw_rho(name, get_elements_from_kbody_term(section)[-1], fixed)
@@ -179,7 +243,7 @@ class _Functions:
                 return self._zjw_embed(name, section, fixed)
         raise NotImplementedError(
             f"training of '{name}' {fn} functions is not implemented "
-            "(trainable forms: 'nn', 'zjw04')")
+            "(trainable forms: 'nn', 'zjw04', 'sutton90', 'Be/1', 'grimes')")
 
 
 class EamTrainer:

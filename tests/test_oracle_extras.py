@@ -74,3 +74,36 @@ def test_td_heads_algebra_and_variable_names():
     be.initialize_variables(seed=1)
     assert 'TD/Be/S/Output/bias' not in be.variables               # beryllium.py:66
     assert 'TD/Be/U/Output/bias' in be.variables
+
+
+def test_trainable_torch_forms_match_the_oracle_functions():
+    """The torch forms the EAM trainer differentiates (nn/eam/training.py, product code)
+    against the oracle's restatement of the same reference functions, on the CPU: zjw04
+    (incl. Al-Cu mixing and the three embedding branches), sutton90, AgrawalBe, grimes."""
+    from tensoralloy_b200.nn.eam import EamAlloyNN
+    from tensoralloy_b200.nn.eam.training import _Functions
+    r = torch.linspace(1.6, 6.4, 400, dtype=torch.float64)
+    cases = [('zjw04', ['Al', 'Cu'], 'zjw04', torch.linspace(0.5, 60.0, 400, dtype=torch.float64)),
+             ('sutton90', ['Ag'], 'sutton90', torch.linspace(0.5, 30.0, 200, dtype=torch.float64)),
+             ('Be/1', ['Be'], 'Be/1', torch.linspace(0.05, 3.0, 200, dtype=torch.float64)),
+             ('grimes', ['Pu'], 'grimes', torch.linspace(0.5, 30.0, 200, dtype=torch.float64))]
+    for name, els, oname, rho in cases:
+        nn = EamAlloyNN(els, custom_potentials=name)
+        fns = _Functions(nn, torch.float64, 'cpu')
+        ref = opot.get_potential(oname)
+        for el in els:
+            y = fns.get('rho', el)(r)
+            assert torch.allclose(y, ref.rho(r, el), rtol=1e-13, atol=1e-15), (name, el, 'rho')
+            y = fns.get('embed', el)(rho)
+            assert torch.allclose(y, ref.embed(rho, el), rtol=1e-13, atol=1e-14), (name, el)
+        for term in nn.unique_kbody_terms:
+            y = fns.get('phi', term)(r)
+            assert torch.allclose(y, ref.phi(r, term), rtol=1e-12, atol=1e-14), (name, term)
+        # every variable is a leaf known by its reference name, trainable by default
+        assert fns.params() and all(k.startswith('EAM/Shared/') for k in fns.named)
+    # fixed_functions freeze the variables of that function only
+    nn = EamAlloyNN(['Ag'], custom_potentials='sutton90', fixed_functions=['Ag.rho'])
+    fns = _Functions(nn, torch.float64, 'cpu')
+    fns.get('rho', 'Ag'), fns.get('phi', 'AgAg')
+    assert not fns.named['EAM/Shared/Ag/a'].requires_grad
+    assert fns.named['EAM/Shared/AgAg/b'].requires_grad
