@@ -101,7 +101,8 @@ class TensorAlloyCalculator(_AseCalculator):
     def __init__(self, graph_model_path, atoms=None, serial_mode=False):
         """
         graph_model_path : str or BasicNN
-            A frozen `.pb` exported by the reference (`BasicNN.export`,
+            A `.npz` in the LAMMPS-native layout (`export_to_lammps_native`,
+            atomic.py:304-480), a frozen `.pb` exported by the reference (`BasicNN.export`,
             basic.py:1017-1153) -- its transformer JSON and parameter constants
             are read, the TF graph itself is NOT executed -- or a model object
             with an attached transformer.
@@ -122,6 +123,16 @@ class TensorAlloyCalculator(_AseCalculator):
             self._model_dir = None
             self._nn = nn
             self._fp_precision = get_float_precision().name
+            self._api_version = "1.1"
+            self._predict_properties = list(nn.predict_properties)
+        elif str(graph_model_path).endswith('.npz'):
+            # the LAMMPS-native layout (atomic.py:304-480), io/native.py
+            from tensoralloy_b200.io.native import read_lammps_native
+            nn, precision = read_lammps_native(graph_model_path)
+            self._graph_model_path = graph_model_path
+            self._model_dir = dirname(graph_model_path)
+            self._nn = nn
+            self._fp_precision = precision
             self._api_version = "1.1"
             self._predict_properties = list(nn.predict_properties)
         else:

@@ -1,5 +1,5 @@
 """
-Reader of the reference's exported model files: frozen TensorFlow `GraphDef`
+Reader (and writer, see `write_graph_model`) of the reference's exported model files: frozen TensorFlow `GraphDef`
 `.pb` written by `BasicNN.export` (tensoralloy/nn/basic.py:1017-1153).
 
 The TF graph is NOT executed.  What is read:
@@ -108,6 +108,11 @@ def load_graph_model(path) -> LoadedModel:
                     precision = 'medium'
                 break
     scopes = {x.split('/')[0] for x in names}
+    if 'Model/params' in consts:          # written by `write_graph_model` below
+        nn = _model_from_params(consts, clf, ops)
+        return LoadedModel(nn=nn, precision=precision, api_version=meta('api', '1.0'),
+                           timestamp=meta('timestamp'), predict_properties=list(ops),
+                           ops=ops)
     if 'EAM' in scopes or 'ADP' in scopes:
         nn = _build_eam(g, consts, names, clf, 'ADP' if 'ADP' in scopes else 'EAM', ops)
     elif 'Atomic' in scopes:
@@ -229,4 +234,161 @@ def _build_atomic(g, consts, names, clf, ops):
                   export_properties=_export_properties(ops))
     for k, v in variables.items():
         nn.set_variable(k, v)
+    return nn
+
+
+# --------------------------------------------------------------------------
+# writer: `BasicNN.export` (basic.py:1017-1153)
+# --------------------------------------------------------------------------
+_OP_NAMES = {   # tensor names of the reference's output ops (basic.py:742-787)
+    'energy': 'Output/Energy/energy:0', 'atomic': 'Output/Energy/atomic:0',
+    'free_energy': 'Output/Energy/free_energy:0', 'eentropy': 'Output/Energy/eentropy:0',
+    'forces': 'Output/Forces/forces:0', 'stress': 'Output/Stress/Voigt/stress:0',
+    'total_pressure': 'Output/Pressure/pressure:0', 'hessian': 'Output/Hessian/hessian:0',
+    'elastic': 'Output/Elastic/elastic:0',
+}
+
+
+def _const_node(g, name, value, np_dtype=None):
+    from tensorboard.compat.proto import tensor_pb2, tensor_shape_pb2
+    node = g.node.add()
+    node.name = name
+    node.op = 'Const'
+    t = tensor_pb2.TensorProto()
+    if isinstance(value, (str, bytes)):
+        t.dtype = _DT_STRING
+        t.string_val.append(value.encode('utf-8') if isinstance(value, str) else value)
+        t.tensor_shape.CopyFrom(tensor_shape_pb2.TensorShapeProto())
+    else:
+        arr = np.ascontiguousarray(np.asarray(value, dtype=np_dtype))
+        t.dtype = {np.dtype(np.float32): _DT_FLOAT, np.dtype(np.float64): _DT_DOUBLE,
+                   np.dtype(np.int32): _DT_INT32, np.dtype(np.int64): _DT_INT64}[arr.dtype]
+        for d in arr.shape:
+            t.tensor_shape.dim.add().size = int(d)
+        t.tensor_content = arr.tobytes()
+    node.attr['dtype'].type = t.dtype
+    node.attr['value'].tensor.CopyFrom(t)
+    return node
+
+
+def _jsonable(x):
+    if isinstance(x, dict):
+        return {k: _jsonable(v) for k, v in x.items()}
+    if isinstance(x, (list, tuple)):
+        return [_jsonable(v) for v in x]
+    if isinstance(x, np.ndarray):
+        return x.tolist()
+    if isinstance(x, (np.floating, np.integer)):
+        return x.item()
+    return x
+
+
+def _shared_parameters(nn):
+    """{potential: {section: {key: value}}} of the empirical potentials an EAM-family
+    model uses, restricted to sections made of the model's own elements."""
+    from tensoralloy_b200.utils import get_elements_from_kbody_term
+    used = {name for fns in nn.potentials.values() for name in fns.values()
+            if name != 'nn' and not name.startswith('spline@')}
+    out = {}
+    for pname in sorted(used):
+        fn = nn._fn_of(*next((s, f) for s, fns in nn.potentials.items()
+                             for f, v in fns.items() if v == pname))
+        keep = {}
+        for section, vals in fn.params.items():
+            try:
+                els = get_elements_from_kbody_term(section)
+            except Exception:
+                els = [section]
+            if all(e in nn.elements for e in els):
+                keep[section] = _jsonable(vals)
+        out[pname] = keep
+    return out
+
+
+def write_graph_model(nn, output_graph_path, precision=None):
+    """A frozen `.pb` in the reference's node naming that `load_graph_model` (and so
+    `TensorAlloyCalculator(path)`) reads back: `Transformer/params`, `Metadata/*`
+    (basic.py:1075-1092), every variable as a `Const` node under its reference name
+    (`Atomic/<El>/Conv1d{k}/{kernel,bias}`, `EAM/Shared/<section>/<param>`, ...).
+
+    It is a PARAMETER CONTAINER: there is no TensorFlow in this image, so the file holds
+    no executable ops and the reference's TF calculator cannot run it (its
+    `Metadata/tf_version` says so).  Two extra constants make the round trip exact
+    without parsing op scopes: `Model/params` (JSON of `nn.as_dict()`) and, for the
+    EAM family, `Model/shared` (the shared potential parameters per potential)."""
+    from datetime import datetime
+    from tensorboard.compat.proto import graph_pb2
+    from tensoralloy_b200.precision import get_float_precision
+    if nn.transformer is None:
+        raise ValueError("A transformer must be attached before exporting to a pb file.")
+    precision = precision or get_float_precision().name
+    dt = np.float64 if precision == 'high' else np.float32
+    clf = nn.transformer
+    g = graph_pb2.GraphDef()
+    g.versions.producer = 134           # TF 1.15 GraphDef version, for protobuf readers
+    params = _jsonable(clf.as_dict())
+    _const_node(g, 'Transformer/params', json.dumps(params))
+    _const_node(g, 'Metadata/timestamp', str(datetime.today()))
+    _const_node(g, 'Metadata/precision', precision)
+    _const_node(g, 'Metadata/tf_version', 'none (tensoralloy_b200 parameter container)')
+    _const_node(g, 'Metadata/variational_energy', nn.variational_energy)
+    _const_node(g, 'Metadata/is_finite_temperature', int(nn.is_finite_temperature),
+                np.int32)
+    _const_node(g, 'Metadata/api', '1.1')
+    props = list(nn.predict_properties)
+    if nn.is_finite_temperature:
+        props += [p for p in ('free_energy', 'eentropy') if p not in props]
+    ops = {p: _OP_NAMES[p] for p in props if p in _OP_NAMES}
+    _const_node(g, 'Metadata/ops', json.dumps(ops))
+    _const_node(g, 'Model/params', json.dumps(_jsonable(nn.as_dict())))
+    if hasattr(nn, 'potentials'):
+        shared = _shared_parameters(nn)
+        _const_node(g, 'Model/shared', json.dumps(shared))
+        for pname, sections in shared.items():
+            for section, vals in sections.items():
+                for key, v in vals.items():
+                    name = f'{nn.scope}/Shared/{section}/{key}'
+                    if np.ndim(v) == 0 and not any(n.name == name for n in g.node):
+                        _const_node(g, name, v, dt)
+    if not getattr(nn, 'variables', None) and hasattr(nn, 'initialize_variables') \
+            and not hasattr(nn, 'potentials'):
+        nn.initialize_variables()
+    for name, value in nn.variables.items():
+        _const_node(g, name, value, dt)
+    with open(output_graph_path, 'wb') as fp:
+        fp.write(g.SerializeToString())
+
+
+def _model_from_params(consts, clf, ops):
+    """Rebuild the model of a file written by `write_graph_model`."""
+    cfg = json.loads(const_value(consts['Model/params']).decode('utf-8'))
+    cls_name = cfg.pop('class')
+    from tensoralloy_b200.nn import atomic as _atomic, eam as _eam
+    import tensoralloy_b200.nn.atomic.finite_temperature as _ft
+    cls = getattr(_atomic, cls_name, None) or getattr(_eam, cls_name, None) or \
+        getattr(_ft, cls_name, None)
+    if cls is None:
+        raise ValueError(f"unknown model class '{cls_name}'")
+    cfg['export_properties'] = [p for p in cfg.get('export_properties', [])] or \
+        _export_properties(ops)
+    nn = cls(**cfg)
+    nn.attach_transformer(clf)
+    if 'Model/shared' in consts:
+        shared = json.loads(const_value(consts['Model/shared']).decode('utf-8'))
+        for pname, sections in shared.items():
+            fn = nn._empirical_functions[pname]
+            for section, vals in sections.items():
+                for key, v in vals.items():
+                    if np.ndim(v) == 0:
+                        fn.set_param(section, key, v)
+                    else:
+                        fn.params.setdefault(section, {})[key] = v
+        nn._model = None
+    skip = ('Transformer/', 'Metadata/', 'Model/', f'{nn.scope}/Shared/')
+    for name, node in consts.items():
+        if name.startswith(skip):
+            continue
+        v = const_value(node)
+        if v is not None and not isinstance(v, bytes):
+            nn.set_variable(name, np.asarray(v, dtype=np.float64))
     return nn

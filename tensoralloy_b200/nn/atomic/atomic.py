@@ -54,6 +54,18 @@ class AtomicNN(BasicNN):
         self._out = None
 
     descriptor = property(lambda self: self._descriptor)
+    activation = property(lambda self: self._activation)
+    use_resnet_dt = property(lambda self: self._use_resnet_dt)
+    use_atomic_static_energy = property(lambda self: self._use_atomic_static_energy)
+
+    def export_to_lammps_native(self, model_path, checkpoint=None,
+                                use_ema_variables=True, dtype=np.float64):
+        """The `.npz` model file of LAMMPS `pair_style tensoralloy/native`
+        (atomic.py:304-480), written from the variables this object holds
+        (`checkpoint` / `use_ema_variables` are accepted for signature parity: there is
+        no TF checkpoint to restore).  io/native.py holds the layout."""
+        from tensoralloy_b200.io.native import write_lammps_native
+        write_lammps_native(self, model_path, dtype=dtype)
 
     def as_dict(self):
         return {"class": self.__class__.__name__, "elements": self._elements,

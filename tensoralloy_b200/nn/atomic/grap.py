@@ -78,6 +78,7 @@ class GenericRadialAtomicPotential:
     algorithm = property(lambda self: self._algorithm)
     moment_tensors = property(lambda self: self._moment_tensors)
     max_moment = property(lambda self: max(self._moment_tensors))
+    is_T_symmetric = property(lambda self: self._symmetric)
     grid = property(lambda self: self._grid)
 
     def as_dict(self):

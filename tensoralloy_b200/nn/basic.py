@@ -99,6 +99,23 @@ class BasicNN:
     def attach_transformer(self, clf):
         self._transformer = clf
 
+    def export(self, output_graph_path: str, checkpoint=None, keep_tmp_files=False,
+               use_ema_variables=True, mode=ModeKeys.PREDICT, **kwargs):
+        """basic.py:1017-1153.  Writes the frozen `.pb` layout (`Transformer/params`,
+        `Metadata/*`, every variable as a Const node under its reference name) that
+        `TensorAlloyCalculator(path)` loads; `mode=ModeKeys.NATIVE` writes the
+        LAMMPS-native `.npz` instead (basic.py:1037-1039).  The variables are the ones
+        this object holds: `checkpoint`, `keep_tmp_files` and `use_ema_variables` are
+        accepted for signature parity (no TF checkpoint, no temporary files).  See
+        io/graph_model.py `write_graph_model` for what the file is and is not."""
+        if self._transformer is None:
+            raise ValueError("A transformer must be attached before "
+                             "exporting to a pb file.")
+        if mode == ModeKeys.NATIVE:
+            return self.export_to_lammps_native(output_graph_path, **kwargs)
+        from tensoralloy_b200.io.graph_model import write_graph_model
+        write_graph_model(self, output_graph_path, precision=kwargs.get('precision'))
+
     def as_dict(self):
         raise NotImplementedError("This method must be overridden!")
 
