@@ -21,8 +21,9 @@ Differences to the reference, all on the safe side:
   * the reference drops the min-max input scaling (`xlo`, `xhi`,
     atomic.py:176-200) when it writes this file -- a model trained with
     `minmax_scale=True` would evaluate differently in LAMMPS.  Here the affine
-    map is folded into the first layer (W1' = W1 / (xhi - xlo),
-    b1' = b1 - xlo . W1'), which is exact (the first layer never carries a
+    map x' = (xhi - x) / (xhi - xlo) (0 where xhi = xlo, `div_no_nan`) is
+    folded into the first layer (W1' = -W1 / (xhi - xlo),
+    b1' = b1 + xhi / (xhi - xlo) . W1), which is exact (the first layer never carries a
     ResNet link, convolutional.py:272).
   * a descriptor whose `moment_tensors` skip a moment (e.g. [0, 2]) cannot be
     expressed (only `max_moment` is stored); the reference writes such a file
@@ -87,14 +88,12 @@ def _folded_layers(nn, element):
     W = [np.array(w, dtype=np.float64) for w in p['weights']]
     b = [None if x is None else np.array(x, dtype=np.float64) for x in p['biases']]
     if p['xlo'] is not None:
+        # atomic.py:199: x' = div_no_nan(xhi - x, xhi - xlo)
         lo, hi = p['xlo'], p['xhi']
-        if np.any(hi <= lo):
-            raise ValueError(f"{element}: xhi <= xlo, the min-max range was never "
-                             "fitted; export with minmax_scale=False or set xlo/xhi")
-        s = 1.0 / (hi - lo)
-        W0 = W[0] * s[:, None]
-        b0 = (b[0] if b[0] is not None else 0.0) - (lo * s) @ W[0]
-        W[0], b[0] = W0, np.asarray(b0, dtype=np.float64)
+        den = hi - lo
+        s = np.where(den == 0.0, 0.0, 1.0 / np.where(den == 0.0, 1.0, den))
+        b0 = (b[0] if b[0] is not None else 0.0) + (hi * s) @ W[0]
+        W[0], b[0] = -W[0] * s[:, None], np.asarray(b0, dtype=np.float64)
     return W, b
 
 
