@@ -25,6 +25,10 @@ class _Potential:
     def params(self):
         return self._params
 
+    # {section: [parameter, ...]} never trained by the reference (potentials.py:76-79);
+    # none of the potentials of this module declares any
+    fixed_parameters = property(lambda self: {})
+
     def set_param(self, section, key, value):
         self._params.setdefault(section, {})[key] = float(value)
 

@@ -44,6 +44,14 @@ class Zjw04:
     def params(self):
         return self._params
 
+    @property
+    def fixed_parameters(self):
+        """{section: [parameter, ...]} the reference never trains (zjw04.py:174-177: the
+        embedding parameters and r_eq of every element)."""
+        keys = ['F0', 'F1', 'F2', 'F3', 'Fn0', 'Fn1', 'Fn2', 'Fn3', 'Fe', 'eta', 'rho_e',
+                'rho_s', 'r_eq']
+        return {el: list(keys) for el in _load()['zjw04']}
+
     def set_param(self, section, key, value):
         """Override one variable (a loaded .pb constant or a trained value)."""
         self._params.setdefault(section, {})[key] = float(value)
@@ -85,6 +93,12 @@ class Zjw04xc(Zjw04):
         p['Be'] = copy.deepcopy(p['Mo'])
         return p
 
+    @property
+    def fixed_parameters(self):
+        """zjw04.py:427-429 (and :585-587 for xcp): r_eq of the single elements."""
+        return {sec: ['r_eq'] for sec in self.defaults
+                if len(get_elements_from_kbody_term(sec)) == 1}
+
 
 class Zjw04uxc(Zjw04xc):
     """zjw04.py:553-567."""
@@ -93,6 +107,8 @@ class Zjw04uxc(Zjw04xc):
     def __init__(self, params=None):
         super().__init__(params)
         self._name = 'Zjw04uxc'
+
+    fixed_parameters = property(lambda self: {})        # zjw04.py:566
 
 
 class Zjw04xcp(Zjw04xc):

@@ -63,9 +63,15 @@ def _zhou_exp(r, a, b, c, re):
 class _Functions:
     """Callable table of one model: `fn(kind, key)(x)`; owns the leaf tensors."""
 
-    ZJW = ('zjw04',)
+    ZJW = ('zjw04', 'zjw04xc', 'zjw04uxc', 'zjw04xcp')
 
-    def __init__(self, nn, tdtype, device):
+    def __init__(self, nn, tdtype, device, freeze_reference_fixed=True):
+        """freeze_reference_fixed: keep the parameters a potential class declares as
+        never trained (`fixed_parameters`, potentials.py:76-79,119-127 -- e.g. the
+        embedding parameters and r_eq of zjw04) out of the optimiser, as the reference
+        does.  False makes every shared variable of a non-fixed function a trainable
+        leaf (gradient checks)."""
+        self.freeze = freeze_reference_fixed
         self.nn = nn
         self.tdtype = tdtype
         self.device = device
@@ -115,8 +121,11 @@ class _Functions:
     # -- zjw04 --------------------------------------------------------------------------
     def _p(self, potential, section, key, fixed):
         tag = (section, key)
+        pot = self.nn._empirical_functions[potential]
+        if self.freeze and key in pot.fixed_parameters.get(section, ()):
+            fixed = True
         if tag not in self._shared:
-            value = self.nn._empirical_functions[potential].params[section][key]
+            value = pot.params[section][key]
             t = torch.tensor(float(value), dtype=self.tdtype, device=self.device,
                              requires_grad=not fixed)
             self._shared[tag] = t
@@ -145,11 +154,35 @@ class _Functions:
         # zjw04.py:229-243
         return lambda r: 0.5 * (ra(r) / rb(r) * pb(r) + rb(r) / ra(r) * pa(r))
 
+    def _zjw_phi_xcp(self, pot, term, fixed):
+        # zjw04.py:570-696: the A-B pair has its own parameter section
+        a, b = get_elements_from_kbody_term(term)
+        params = self.nn._empirical_functions[pot].params
+        sec = a if a == b else (term if term in params else f"{b}{a}")
+        A, al, ka, B, be, la, re = (self._p(pot, sec, k, fixed) for k in
+                                    ('A', 'alpha', 'kappa', 'B', 'beta', 'lamda', 'r_eq'))
+        return lambda r: _zhou_exp(r, A, al, ka, re) - _zhou_exp(r, B, be, la, re)
+
     def _zjw_embed(self, pot, el, fixed):
         keys = ('Fn0', 'Fn1', 'Fn2', 'Fn3', 'F0', 'F1', 'F2', 'F3', 'eta', 'Fe', 'rho_e',
                 'rho_s')
         Fn0, Fn1, Fn2, Fn3, F0, F1, F2, F3, eta, Fe, rho_e, rho_s = (
             self._p(pot, el, k, fixed) for k in keys)
+
+        def blended(rho):
+            # zjw04.py:440-550: the three branches blended by sigmoids
+            rho_n, rho_0 = 0.85 * rho_e, 1.15 * rho_e
+            x1 = rho / rho_n - 1.0
+            e1 = Fn0 + Fn1 * x1 + Fn2 * x1 ** 2 + Fn3 * x1 ** 3
+            x2 = rho / rho_e - 1.0
+            e2 = F0 + F1 * x2 + F2 * x2 ** 2 + F3 * x2 ** 3
+            x3 = rho / rho_s + 1e-8
+            e3 = Fe * (1.0 - eta * torch.log(x3)) * x3 ** eta
+            c1 = torch.sigmoid(2.0 * (rho_n - rho))
+            c3 = torch.sigmoid(2.0 * (rho - rho_0))
+            return c1 * e1 + (1.0 - (c1 + c3)) * e2 + c3 * e3
+        if pot != 'zjw04':
+            return blended
 
         def call(rho):
             # zjw04.py:279-389 (three branches selected by rho)
@@ -222,6 +255,74 @@ class _Functions:
         G = self._p('grimes', el, 'G', fixed)
         return lambda rho: -G * torch.sqrt(rho)
 
+    def _mishin(self, fn, section, fixed):
+        # mishin.py:20-315 (embed, dipole, quadrupole; its rho / phi read undefined
+        # variables upstream)
+        if fn == 'embed':
+            s1, s2, s3, s4, s5, s6, s7 = (self._p('mishinh', section, f's{k}', fixed)
+                                          for k in range(1, 8))
+            eps = 1e-14 if self.tdtype == torch.float64 else 1e-8
+
+            def embed(rho):
+                rho2 = rho * rho
+                omega = 1.0 - (1.0 - s6 * rho2) / (1.0 + s7 * rho2 * rho2)
+                return (s1 * rho + s2 * rho2 + s3 * rho * rho2 -
+                        s4 * torch.pow(rho + eps, s5)) * omega
+            return embed
+        sec = self._pair_section('mishinh', section)
+        pre = 'd' if fn == 'dipole' else 'q'
+        p1, p2, p3, rc, h = (self._p('mishinh', sec, k, fixed)
+                             for k in (pre + '1', pre + '2', pre + '3', 'rc', 'h'))
+
+        def polar(r):
+            # generic.py:52-84: (p1 exp(-p2 r) + p3) psi((r - rc) / h)
+            x4 = torch.relu(-(r - rc) / h) ** 4
+            return (p1 * torch.exp(-p2 * r) + p3) * (x4 / (1.0 + x4))
+        return polar
+
+    def _msah11(self, fn, section):
+        # msah11.py:28-424: constants only -- nothing to train, but the functions may sit
+        # next to trainable ones in a model
+        pot = self.nn._empirical_functions['msah11']
+        if fn == 'embed':
+            if section == 'Al':
+                def embed_al(rho):
+                    m = rho >= 1e-12
+                    x = torch.where(m, rho, torch.ones_like(rho))
+                    y = -torch.sqrt(x) + 0.000093283590195398 * x ** 2 - \
+                        0.0023491751192724 * x * torch.log(x)
+                    return torch.where(m, y, torch.zeros_like(rho))
+                return embed_al
+            if section != 'Fe':
+                raise KeyError(f"msah11: no embedding function for {section}")
+            return lambda rho: -torch.sqrt(rho) - 0.00067314115586063 * rho ** 2 + \
+                0.000000076514905604792 * rho ** 4
+        if fn == 'rho':
+            els = get_elements_from_kbody_term(section)
+            key = pot._key(section) if len(els) == 2 else els[0] + els[0]
+            order, factors, cutoffs = pot._RHO[key]
+            return lambda r: sum(f * torch.clamp(rc - r, min=0.0) ** order
+                                 for f, rc in zip(factors, cutoffs))
+        d = pot._PHI[pot._key(section)]
+
+        def phi(r):
+            zero = torch.zeros_like(r)
+            lo, hi, c = d['first']
+            m = (r >= lo) & (r < hi)
+            x = torch.where(m, r, torch.ones_like(r))
+            y = (c[0] / x) * sum(c[1 + 2 * i] * torch.exp(c[2 + 2 * i] * x) for i in range(4))
+            out = torch.where(m, y, zero)
+            lo, hi, c = d['second']
+            m = (r >= lo) & (r < hi)
+            out = out + torch.where(m, torch.exp(c[0] + c[1] * r + c[2] * r ** 2 +
+                                                 c[3] * r ** 3), zero)
+            for lo, hi, coef, orders in d['polys']:
+                m = (r >= lo) & (r < hi)
+                x = torch.where(m, hi - r, zero)
+                out = out + sum(a * x ** n for a, n in zip(coef, orders))
+            return out
+        return phi
+
     # -- dispatch -----------------------------------------------------------------------
     def get(self, fn, section):
         name = self.nn.potentials[section][fn]
@@ -234,23 +335,31 @@ class _Functions:
             return self._agrawal(fn, section, fixed)
         if name == 'grimes' and fn in ('rho', 'phi', 'embed'):
             return self._grimes(fn, section, fixed)
+        if name == 'mishinh' and fn in ('embed', 'dipole', 'quadrupole'):
+            return self._mishin(fn, section, fixed)
+        if name == 'msah11' and fn in ('rho', 'phi', 'embed'):
+            return self._msah11(fn, section)
         if name in self.ZJW:
             if fn == 'rho':
                 return self._zjw_rho(name, get_elements_from_kbody_term(section)[-1], fixed)
             if fn == 'phi':
+                if name == 'zjw04xcp':
+                    return self._zjw_phi_xcp(name, section, fixed)
                 return self._zjw_phi(name, section, fixed)
             if fn == 'embed':
                 return self._zjw_embed(name, section, fixed)
         raise NotImplementedError(
             f"training of '{name}' {fn} functions is not implemented "
-            "(trainable forms: 'nn', 'zjw04', 'sutton90', 'Be/1', 'grimes')")
+            "(trainable forms: 'nn', 'zjw04' / xc / uxc / xcp, 'sutton90', 'Be/1', "
+            "'grimes', 'mishinh' embed / dipole / quadrupole; 'msah11' as constants)")
 
 
 class EamTrainer:
     """Holds the structures of this rank in ONE batch handle (lists and pair vectors built
     once: the geometry does not change during training) and the torch leaves."""
 
-    def __init__(self, nn, device='cuda', loss_weights=None, per_atom_energy=True):
+    def __init__(self, nn, device='cuda', loss_weights=None, per_atom_energy=True,
+                 freeze_reference_fixed=True):
         self.nn = nn
         self.device = device
         self.dt = get_float_dtype()
@@ -260,7 +369,7 @@ class EamTrainer:
         self.loss_weights = dict(energy=1.0, forces=1.0, stress=1.0)
         self.loss_weights.update(loss_weights or {})
         self.per_atom_energy = per_atom_energy
-        self.fns = _Functions(nn, self.tdtype, device)
+        self.fns = _Functions(nn, self.tdtype, device, freeze_reference_fixed)
         els = self.elements
         self._rho, self._phi, self._embed, self._dip, self._quad = {}, {}, {}, {}, {}
         for a, ea in enumerate(els):

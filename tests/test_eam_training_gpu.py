@@ -41,9 +41,14 @@ def _oracle_fns(nn):
     """Oracle callables closing over LEAF tensors that carry the model's current values;
     returns (fns, leaves_fn) with leaves keyed by the reference variable names."""
     provider = nn._nn
-    zj = opot.get_potential('zjw04')
-    shared = zj.track_parameters()
+    pots, shared = {}, {}
     nn_leaves = {}
+
+    def empirical(name):
+        if name not in pots:
+            pots[name] = opot.get_potential(name)
+            pots[name].track_parameters()
+        return pots[name]
 
     def mlp(fn, section):
         arrays = provider.weights(fn, section)
@@ -67,21 +72,24 @@ def _oracle_fns(nn):
         def call(x, key):
             if nn.potentials[key][fn] == 'nn':
                 return mlp(fn, key)(x)
-            return getattr(zj, fn)(x, key)
+            return getattr(empirical(nn.potentials[key][fn]), fn)(x, key)
         return call
 
     fns = {fn: dispatch(fn) for fn in ('rho', 'phi', 'embed', 'dipole', 'quadrupole')}
 
     def leaves_fn():
         out = dict(nn_leaves)
-        for (section, key), t in shared.items():
-            out[f"{nn.scope}/Shared/{section}/{key}"] = t
+        for pot in pots.values():
+            for (section, key), t in pot.leaves.items():
+                out.setdefault(f"{nn.scope}/Shared/{section}/{key}", t)
         return out
     return fns, leaves_fn
 
 
 def _check(nn, kind, structs, n_steps=10):
-    tr = EamTrainer(nn)
+    # every shared variable as a leaf: the gradient check covers the parameters the
+    # reference keeps frozen (zjw04 embedding parameters, r_eq) too
+    tr = EamTrainer(nn, freeze_reference_fixed=False)
     for s in structs:
         tr.add_structure(s['atoms'], s['energy'], s['forces'], s['stress'])
     loss, parts = tr.gradients()
@@ -154,6 +162,31 @@ def test_adp_all_nn_parameter_gradients():
                 scale = 0.02 if ('Dipole' in name or 'Quadrupole' in name) else 0.2
                 nn.set_variable(name, value * scale)
         _check(nn, 'adp', structs)
+
+
+def test_adp_mishinh_and_nn_parameter_gradients():
+    """Trainable MishinH embedding / dipole / quadrupole functions (mishin.py:20-315) next to
+    zjw04 and 'nn' functions in one ADP model."""
+    structs = make_structures(2, seed=12)
+    with precision_scope('high'):
+        nn = AdpNN(ELEMENTS, custom_potentials={
+            'Mo': {'rho': 'zjw04', 'embed': 'nn'}, 'Ni': {'rho': 'nn', 'embed': 'zjw04'},
+            'MoMo': {'phi': 'zjw04', 'dipole': 'mishinh', 'quadrupole': 'nn'},
+            'MoNi': {'phi': 'nn', 'dipole': 'mishinh', 'quadrupole': 'mishinh'},
+            'NiNi': {'phi': 'zjw04', 'dipole': 'nn', 'quadrupole': 'mishinh'}},
+            hidden_sizes=[8, 6], minimize_properties=('energy', 'forces', 'stress'))
+        nn.attach_transformer(UniversalTransformer(ELEMENTS, rcut=RC))
+        nn.initialize_variables(seed=6)
+        for name, value in list(nn.variables.items()):
+            if name.endswith('Output/kernel'):
+                scale = 0.02 if ('Dipole' in name or 'Quadrupole' in name) else 0.2
+                nn.set_variable(name, value * scale)
+        tr = _check(nn, 'adp', structs)
+        assert tr.named_parameters()['ADP/Shared/MoNi/q1'].grad is not None
+        # by default the reference's never-trained parameters stay out of the optimiser
+        frozen = EamTrainer(nn).named_parameters()
+        assert not frozen['ADP/Shared/Ni/F0'].requires_grad
+        assert frozen['ADP/Shared/MoNi/d1'].requires_grad
 
 
 def test_eam_fs_all_nn_parameter_gradients():

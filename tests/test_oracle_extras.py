@@ -87,9 +87,12 @@ def test_trainable_torch_forms_match_the_oracle_functions():
              ('sutton90', ['Ag'], 'sutton90', torch.linspace(0.5, 30.0, 200, dtype=torch.float64)),
              ('Be/1', ['Be'], 'Be/1', torch.linspace(0.05, 3.0, 200, dtype=torch.float64)),
              ('grimes', ['Pu'], 'grimes', torch.linspace(0.5, 30.0, 200, dtype=torch.float64))]
+    rho60 = torch.linspace(0.5, 60.0, 400, dtype=torch.float64)
+    cases += [('zjw04xc', ['Al', 'Cu'], 'zjw04xc', rho60), ('zjw04uxc', ['Be', 'Ni'], 'zjw04uxc', rho60),
+              ('zjw04xcp', ['Mo', 'Ni'], 'zjw04xcp', rho60)]
     for name, els, oname, rho in cases:
         nn = EamAlloyNN(els, custom_potentials=name)
-        fns = _Functions(nn, torch.float64, 'cpu')
+        fns = _Functions(nn, torch.float64, 'cpu', freeze_reference_fixed=False)
         ref = opot.get_potential(oname)
         for el in els:
             y = fns.get('rho', el)(r)
@@ -107,3 +110,52 @@ def test_trainable_torch_forms_match_the_oracle_functions():
     fns.get('rho', 'Ag'), fns.get('phi', 'AgAg')
     assert not fns.named['EAM/Shared/Ag/a'].requires_grad
     assert fns.named['EAM/Shared/AgAg/b'].requires_grad
+
+
+def test_trainable_mishinh_and_constant_msah11_forms():
+    """MishinH embed / dipole / quadrupole (mishin.py:20-315) as trainable torch forms and the
+    constant Mendelev Al-Fe functions (msah11.py:28-424) against the oracle restatement."""
+    from tensoralloy_b200.nn.eam import AdpNN, EamFsNN
+    from tensoralloy_b200.nn.eam.training import _Functions
+    r = torch.linspace(1.2, 6.6, 500, dtype=torch.float64)
+    rho = torch.linspace(0.0, 3.0, 300, dtype=torch.float64)
+    nn = AdpNN(['Mo', 'Ni'], custom_potentials={
+        'Mo': {'rho': 'zjw04', 'embed': 'mishinh'}, 'Ni': {'rho': 'zjw04', 'embed': 'zjw04'},
+        'MoMo': {'phi': 'zjw04', 'dipole': 'mishinh', 'quadrupole': 'mishinh'},
+        'MoNi': {'phi': 'zjw04', 'dipole': 'mishinh', 'quadrupole': 'mishinh'},
+        'NiNi': {'phi': 'zjw04', 'dipole': 'mishinh', 'quadrupole': 'mishinh'}})
+    fns = _Functions(nn, torch.float64, 'cpu')
+    ref = opot.get_potential('mishinh')
+    y = fns.get('embed', 'Mo')(rho)
+    assert torch.allclose(y, ref.embed(rho, 'Mo'), rtol=1e-13, atol=1e-15)
+    for term in ('MoMo', 'MoNi', 'NiNi'):
+        assert torch.allclose(fns.get('dipole', term)(r), ref.dipole(r, term),
+                              rtol=1e-13, atol=1e-16), term
+        assert torch.allclose(fns.get('quadrupole', term)(r), ref.quadrupole(r, term),
+                              rtol=1e-13, atol=1e-16), term
+    assert fns.named['ADP/Shared/Mo/s5'].requires_grad
+    assert fns.named['ADP/Shared/NiNi/q2'].requires_grad
+    # gradients flow to the shared variables
+    fns.get('dipole', 'NiNi')(r).sum().backward()
+    assert fns.named['ADP/Shared/NiNi/d1'].grad is not None
+    # the reference never trains the embedding parameters / r_eq of zjw04 (zjw04.py:174-177)
+    fns.get('embed', 'Ni'), fns.get('rho', 'Ni')
+    assert not fns.named['ADP/Shared/Ni/F0'].requires_grad
+    assert not fns.named['ADP/Shared/Ni/r_eq'].requires_grad
+    assert fns.named['ADP/Shared/Ni/f_eq'].requires_grad
+
+    fs = EamFsNN(['Al', 'Fe'], custom_potentials='msah11')
+    fns = _Functions(fs, torch.float64, 'cpu')
+    ref = opot.get_potential('msah11')
+    rr = torch.linspace(0.5, 6.6, 700, dtype=torch.float64)
+    for term in ('AlAl', 'AlFe', 'FeFe'):
+        assert torch.allclose(fns.get('phi', term)(rr), ref.phi(rr, term),
+                              rtol=1e-13, atol=1e-14), term
+    for term in ('AlAl', 'AlFe', 'FeAl', 'FeFe'):
+        assert torch.allclose(fns.get('rho', term)(rr), ref.rho(rr, term),
+                              rtol=1e-13, atol=1e-16), term
+    rho = torch.linspace(0.0, 60.0, 300, dtype=torch.float64)
+    for el in ('Al', 'Fe'):
+        assert torch.allclose(fns.get('embed', el)(rho), ref.embed(rho, el),
+                              rtol=1e-13, atol=1e-15), el
+    assert not fns.params()              # constants only
