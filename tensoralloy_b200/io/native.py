@@ -115,10 +115,10 @@ def lammps_native_dict(nn, dtype=np.float64):
     layer_sizes = np.append(layer_sizes, 1).astype(np.int32)
     if nn.activation not in ACTFN:
         raise KeyError(nn.activation)
-    if list(desc.moment_tensors) != list(range(desc.max_moment + 1)):
+    if list(desc.moments()) != list(range(desc.max_moment + 1)):
         # the file stores max_moment only and its reader evaluates 0..max_moment
         raise ValueError("the npz layout stores `max_moment` only: moment_tensors must "
-                         f"be 0..{desc.max_moment}, got {list(desc.moment_tensors)}")
+                         f"be 0..{desc.max_moment}, got {list(desc.moments())}")
     for elt in elements:
         if elt not in atomic_masses:
             raise ValueError(f"no atomic mass for element {elt}")

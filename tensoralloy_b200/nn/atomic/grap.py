@@ -12,10 +12,18 @@ tau of the chosen algorithm f_tau(r) and every requested multipole moment:
 
 laid out per term as [tau][moment] (grap.py:419-457), terms in
 `kbody_terms_for_element[c]` order.  The arithmetic runs on the GPU
-(csrc/sf.cu: rad_fn, k_sf_forward, k_sf_backward); the new ("T_dm / M_dnac")
-mode of the reference produces the same numbers for moments <= 2
-(nn/atomic/tests/test_grap.py:152-200) and its `nn` algorithm / moment 3 are
-not built.
+(csrc/sf.cu: rad_fn, k_sf_forward, k_sf_backward).
+
+New mode (`legacy_mode=False`, the "T_dm / M_dnac" formulation, grap.py:596-680):
+the descriptor holds EVERY moment 0..max(moment_tensors) per (term, tau)
+(`ndims = (max_moment + 1) * len(algo) * n_elements`, grap.py:613) and, with the
+unsymmetric multiplicity tensor (grap.py:471-496: 1 | 1 1 1 | 1 2 2 1 2 1 over the
+unique index pairs), the same sums as above -- the reference's own test states the
+equality (nn/atomic/tests/test_grap.py:152-200).  It is served by the same kernels
+with the moment list widened to 0..max.  One deliberate difference: the reference
+writes the m = 0 entry as sign(P) * sqrt(P^2 + 1e-16); the kernels keep P itself
+(|difference| <= 5e-17 / |P|).  Not built, and refused loudly: the trainable `nn`
+algorithm, moment 3 and above, and `symmetric=True` (traceless T_dm) in new mode.
 """
 import numpy as np
 
@@ -55,6 +63,9 @@ class GenericRadialAtomicPotential:
         moment_tensors = sorted(set(int(m) for m in moment_tensors))
         if any(m not in (0, 1, 2) for m in moment_tensors):
             raise ValueError("GRAP: moments 0, 1, 2 are supported")
+        if not legacy_mode and symmetric and max(moment_tensors) >= 2:
+            raise ValueError("GRAP: symmetric=True (traceless T_dm) is not implemented "
+                             "in new mode")
         keys = ALGORITHMS[algorithm]
         if parameters is None:
             parameters = {'eta': [0.05, 4.0, 20.0, 80.0], 'omega': [0.0] * 4} \
@@ -103,9 +114,13 @@ class GenericRadialAtomicPotential:
         return None
 
     def moments(self):
+        """Moments the kernels accumulate, in layout order.  Legacy mode: the requested
+        ones (grap.py:419-457); new mode: all of 0..max (grap.py:613, 662-676)."""
+        if not self._legacy_mode:
+            return tuple(range(self.max_moment + 1))
         return tuple(self._moment_tensors)
 
     def dimension(self, angular=False):
         if angular:
             raise ValueError("GRAP is a radial descriptor: use angular=False")
-        return len(self._elements) * len(self._grid) * len(self._moment_tensors)
+        return len(self._elements) * len(self._grid) * len(self.moments())

@@ -184,3 +184,22 @@ def test_c_abi_argument_errors_without_a_gpu():
         assert L.tab_eam_eval_dd(None, h, 0, None, None, None, None, None, None) == EINVAL
     finally:
         L.tab_nbr_free(h)
+
+
+def test_grap_new_mode_layout_and_refusals():
+    """grap.py:613, 662-676: new mode holds every moment 0..max per (term, tau);
+    legacy mode only the requested ones (grap.py:419-457)."""
+    from tensoralloy_b200.nn.atomic import GenericRadialAtomicPotential as Grap
+    par = dict(eta=[0.5, 2.0, 8.0], omega=[0.0, 0.0, 0.0])
+    legacy = Grap(['Al', 'Be'], 'sf', par, moment_tensors=[0, 2])
+    new = Grap(['Al', 'Be'], 'sf', par, moment_tensors=[2], legacy_mode=False)
+    assert legacy.moments() == (0, 2) and legacy.dimension() == 2 * 3 * 2
+    assert new.moments() == (0, 1, 2) and new.dimension() == 2 * 3 * 3
+    assert new.as_dict()["moment_tensors"] == [2] and new.as_dict()["legacy_mode"] is False
+    with pytest.raises(ValueError, match="symmetric"):
+        Grap(['Be'], 'sf', par, moment_tensors=2, symmetric=True, legacy_mode=False)
+    Grap(['Be'], 'sf', par, moment_tensors=2, symmetric=True)    # ignored in legacy mode
+    with pytest.raises(ValueError, match="not implemented"):
+        Grap(['Be'], 'nn', {}, legacy_mode=False)
+    with pytest.raises(ValueError, match="moments 0, 1, 2"):
+        Grap(['Be'], 'sf', par, moment_tensors=3, legacy_mode=False)
