@@ -147,6 +147,23 @@ def descriptors(elements, types, R, cell, i, j, S, rc, acut=None, angular=True,
     return G
 
 
+def grap_radial(algorithm, prm, rij, rc):
+    """f_tau(r) of the closed-form GRAP algorithms (grap.py:121-209; generic.py:15-30,
+    87-100, 120-168), without cutoff."""
+    if algorithm == 'sf':
+        return torch.exp(-prm[0] * (rij - prm[1]) ** 2 / rc ** 2)
+    if algorithm == 'morse':
+        d, g, r0 = prm
+        return d * (torch.exp(-2.0 * g * (rij - r0)) - 2.0 * torch.exp(-g * (rij - r0)))
+    if algorithm == 'density':
+        a, b, re = prm
+        return a * torch.exp(-b * (rij / re - 1.0))
+    if algorithm == 'pexp':
+        rl, pl = prm
+        return torch.exp(-(rij / rl) ** pl)
+    raise ValueError(algorithm)
+
+
 def grap_descriptors(elements, types, R, cell, i, j, S, rc, algorithm, grid, moments,
                      cutoff='cosine'):
     """Legacy-mode GenericRadialAtomicPotential descriptors (nn/atomic/grap.py:384-466,
@@ -169,19 +186,7 @@ def grap_descriptors(elements, types, R, cell, i, j, S, rc, algorithm, grid, mom
     u = Dij / rij[:, None]                       # div_no_nan: r > 0 for real pairs
     cols = []
     for tau, prm in enumerate(grid):
-        if algorithm == 'sf':
-            v = torch.exp(-prm[0] * (rij - prm[1]) ** 2 / rc ** 2)
-        elif algorithm == 'morse':
-            d, g, r0 = prm
-            v = d * (torch.exp(-2.0 * g * (rij - r0)) - 2.0 * torch.exp(-g * (rij - r0)))
-        elif algorithm == 'density':
-            a, b, re = prm
-            v = a * torch.exp(-b * (rij / re - 1.0))
-        elif algorithm == 'pexp':
-            rl, pl = prm
-            v = torch.exp(-(rij / rl) ** pl)
-        else:
-            raise ValueError(algorithm)
+        v = grap_radial(algorithm, prm, rij, rc)
         w = v * fc
         for m in moments:
             # accumulate per (centre, term): index = centre * nel + term
@@ -203,6 +208,96 @@ def grap_descriptors(elements, types, R, cell, i, j, S, rc, algorithm, grid, mom
         for term in range(nel):
             G[:, (term * n_r + tau) * n_m + mi] = val[:, term]
     return G
+
+
+# -- GRAP new mode (grap.py:470-680) -------------------------------------------------
+_AB = [(0, 0), (0, 1), (0, 2), (1, 1), (1, 2), (2, 2)]                    # grap.py:505-506
+_ABC = [(0, 0, 0), (0, 0, 1), (0, 0, 2), (0, 1, 1), (0, 1, 2), (0, 2, 2),
+        (1, 1, 1), (1, 1, 2), (1, 2, 2), (2, 2, 2)]                          # grap.py:510-512
+
+
+def grap_multiplicity_tensor(max_moment, symmetric=False):
+    """T_dm over the UNIQUE Cartesian index tuples (grap.py:470-496)."""
+    d = {0: 1, 1: 4, 2: 10}.get(max_moment, 20)
+    T = np.zeros((d, min(max_moment, 3) + 1))
+    T[0, 0] = 1.0
+    if max_moment >= 1:
+        T[1:4, 1] = 1.0
+    if max_moment >= 2:
+        T[4:10, 2] = 1, 2, 2, 1, 2, 1
+        if symmetric:
+            T[0, 2] = -1.0 / 3.0
+    if max_moment >= 3:
+        T[10:20, 3] = 1, 3, 3, 3, 6, 3, 1, 3, 3, 1
+        if symmetric:
+            T[1:4, 3] = -3.0 / 5.0
+    return T
+
+
+def grap_moment_coeff(u, max_moment):
+    """M_d per pair over the unique index tuples (grap.py:498-535): 1 | u_a | u_a u_b
+    (a <= b) | u_a u_b u_c (a <= b <= c).  u: [P, 3] unit vectors."""
+    rows = [torch.ones_like(u[:, 0])]
+    if max_moment >= 1:
+        rows += [u[:, a] for a in range(3)]
+    if max_moment >= 2:
+        rows += [u[:, a] * u[:, b] for a, b in _AB]
+    if max_moment >= 3:
+        rows += [u[:, a] * u[:, b] * u[:, c] for a, b, c in _ABC]
+    return torch.stack(rows, 0)
+
+
+def grap_T_dm_full(max_moment):
+    """`get_T_dm` (grap.py:574-594): ones over the FULL 3^m index ranges."""
+    dims = [1, 4, 13, 40, 121, 364]
+    T = np.zeros((dims[max_moment], max_moment + 1))
+    lo = 0
+    for m in range(max_moment + 1):
+        T[lo:lo + 3 ** m, m] = 1.0
+        lo += 3 ** m
+    return T
+
+
+def grap_moment_tensor_full(u, max_moment):
+    """`get_moment_tensor` (grap.py:537-572): all 3^m products, row-major."""
+    rows = [torch.ones_like(u[:, :1]).T]
+    cur = rows[0]
+    for m in range(1, max_moment + 1):
+        cur = (cur[:, None, :] * u.T[None, :, :]).reshape(-1, u.shape[0])
+        rows.append(cur)
+    return torch.cat(rows, 0)
+
+
+def grap_descriptors_new_mode(elements, types, R, cell, i, j, S, rc, algorithm, grid,
+                              max_moment, cutoff='cosine', symmetric=False):
+    """`apply_model` of the new mode (grap.py:596-680) for the closed-form algorithms:
+    P = sum_j H_k M_d, S = P^2, Q = S . T_dm, G[m=0] = sign(P_0) sqrt(Q_0 + 1e-16),
+    G[m>0] = Q_m; layout per term [tau][m = 0..max_moment]."""
+    elements = sorted(elements)
+    n, nel = R.shape[0], len(elements)
+    dtype = R.dtype
+    fcut = _cut(cutoff)
+    ti, tj = torch.as_tensor(i), torch.as_tensor(j)
+    Dij = R[tj] - R[ti] + torch.as_tensor(S).to(dtype) @ cell
+    rij = torch.sqrt((Dij * Dij).sum(-1) + EPS[dtype])
+    types_t = torch.as_tensor(types)
+    ci, cj = types_t[ti], types_t[tj]
+    tidx = torch.where(ci == cj, torch.zeros_like(ci), cj - (cj > ci).long() + 1)
+    fc = fcut(rij, rc)
+    u = Dij / rij[:, None]
+    if max_moment > 3:
+        M, T = grap_moment_tensor_full(u, max_moment), grap_T_dm_full(max_moment)
+    else:
+        M, T = grap_moment_coeff(u, max_moment), grap_multiplicity_tensor(max_moment, symmetric)
+    T = torch.as_tensor(T, dtype=dtype)
+    H = torch.stack([grap_radial(algorithm, prm, rij, rc) * fc for prm in grid], 1)   # [P, K]
+    key = ti * nel + tidx
+    HM = H[:, :, None] * M.T[:, None, :]                                              # [P, K, D]
+    P = torch.zeros(n * nel, H.shape[1], M.shape[0], dtype=dtype).index_add(0, key, HM)
+    Q = (P * P) @ T                                                                   # [.., K, m]
+    G0 = torch.sqrt(Q[..., :1] + 1e-16) * torch.sign(P[..., :1])
+    G = torch.cat([G0, Q[..., 1:]], -1)
+    return G.reshape(n, nel * H.shape[1] * T.shape[1])
 
 
 def activation(name):

@@ -159,3 +159,83 @@ def test_trainable_mishinh_and_constant_msah11_forms():
         assert torch.allclose(fns.get('embed', el)(rho), ref.embed(rho, el),
                               rtol=1e-13, atol=1e-15), el
     assert not fns.params()              # constants only
+
+
+def test_grap_T_and_M_full_and_unique_forms_agree():
+    """nn/atomic/tests/test_grap.py:152-200 (`test_T_and_M`): sum_d T_dm M_d is the same
+    for the full 3^m tensors and for the unique tuples with multiplicities, m = 0..3."""
+    import torch
+    from oracle import atomic as oat
+    g = torch.Generator().manual_seed(5)
+    D = torch.randn(40, 3, generator=g, dtype=torch.float64)
+    u = D / D.norm(dim=1, keepdim=True)
+    for mm in range(4):
+        V = torch.as_tensor(oat.grap_T_dm_full(mm)).T @ oat.grap_moment_tensor_full(u, mm)
+        v = torch.as_tensor(oat.grap_multiplicity_tensor(mm)).T @ oat.grap_moment_coeff(u, mm)
+        assert V.shape == v.shape == (mm + 1, 40)
+        assert float((V - v).abs().max()) < 1e-8          # the reference's delta
+        assert float((V - v).abs().max()) < 1e-14
+
+
+def test_grap_new_mode_equals_legacy_mode():
+    """nn/atomic/tests/test_grap.py:46-105 (Be/W, pexp, polynomial cutoff, moments 0-2,
+    delta 1e-6) and :108-149 (`test_sign`: Fe bcc lattice sweep, morse, moments 0-1,
+    delta 1e-8): the two formulations of the reference give the same descriptors."""
+    import torch
+    from oracle import atomic as oat
+    from oracle import neighbor as onl
+    rng = np.random.default_rng(12)
+    # Be hcp 2x2x2 with eight W atoms, rattled
+    a, c = 2.29, 3.58
+    cell0 = np.array([[a, 0, 0], [-a / 2, a * np.sqrt(3) / 2, 0], [0, 0, c]])
+    base = np.array([[0, 0, 0], [1 / 3, 2 / 3, 1 / 2]]) @ cell0
+    pos = np.array([b + np.array([i, j, k]) @ cell0 for i in range(2) for j in range(2)
+                    for k in range(2) for b in base]) + rng.random((16, 3)) * 0.1
+    cell = cell0 * 2
+    types = np.array([0] * 8 + [1] * 8)
+    rc = 5.0
+    i, j, S = onl.neighbor_list(pos, cell, [1, 1, 1], rc)[:3]
+    R, h = torch.as_tensor(pos), torch.as_tensor(cell)
+    grid = [(rl, pl) for rl, pl in zip(np.linspace(1.0, 4.0, 4), [1.0, 2.0, 3.0, 2.5])]
+    legacy = oat.grap_descriptors(['Be', 'W'], types, R, h, i, j, S, rc, 'pexp', grid,
+                                  (0, 1, 2), cutoff='polynomial')
+    new = oat.grap_descriptors_new_mode(['Be', 'W'], types, R, h, i, j, S, rc, 'pexp', grid,
+                                        2, cutoff='polynomial')
+    assert legacy.shape == new.shape == (16, 2 * 4 * 3)
+    assert float((legacy - new).abs().max()) < 1e-10
+    # Fe bcc sweep, morse (sums change sign along the sweep -> exercises sign(P))
+    mgrid = [(1.0, 1.0, r0) for r0 in (3.3, 3.4, 3.5)]
+    seen_negative = False
+    for x in range(-20, 21, 4):
+        lat = 2.87 * (1.0 + x / 100.0)
+        pos = np.array([[0, 0, 0], [0.5, 0.5, 0.5]]) * lat
+        cell = np.eye(3) * lat
+        i, j, S = onl.neighbor_list(pos, cell, [1, 1, 1], 6.0)[:3]
+        R, h = torch.as_tensor(pos), torch.as_tensor(cell)
+        y = oat.grap_descriptors(['Fe'], np.zeros(2, int), R, h, i, j, S, 6.0, 'morse',
+                                 mgrid, (0, 1))
+        z = oat.grap_descriptors_new_mode(['Fe'], np.zeros(2, int), R, h, i, j, S, 6.0,
+                                          'morse', mgrid, 1)
+        assert y.shape == z.shape == (2, 6)
+        assert float((y - z).abs().max()) < 1e-8
+        seen_negative |= bool((y[:, 0::2] < 0).any())
+    assert seen_negative
+
+
+def test_grap_new_mode_symmetric_is_traceless_form():
+    """grap.py:485-494: symmetric T_dm subtracts P_0^2 / 3 from the m = 2 entry and
+    3/5 sum_a P_a^2 from the m = 3 entry (the traces of the moment tensors)."""
+    import torch
+    from oracle import atomic as oat
+    from oracle import neighbor as onl
+    rng = np.random.default_rng(3)
+    pos = rng.random((6, 3)) * 4.0
+    cell = np.eye(3) * 4.0
+    i, j, S = onl.neighbor_list(pos, cell, [1, 1, 1], 3.5)[:3]
+    R, h = torch.as_tensor(pos), torch.as_tensor(cell)
+    args = (['Be'], np.zeros(6, int), R, h, i, j, S, 3.5, 'sf', [(2.0, 0.0), (8.0, 1.0)], 3)
+    plain = oat.grap_descriptors_new_mode(*args).reshape(6, 2, 4)
+    sym = oat.grap_descriptors_new_mode(*args, symmetric=True).reshape(6, 2, 4)
+    assert torch.allclose(sym[..., :2], plain[..., :2], atol=0, rtol=0)
+    assert torch.allclose(sym[..., 2], plain[..., 2] - plain[..., 0] ** 2 / 3.0, atol=1e-13)
+    assert torch.allclose(sym[..., 3], plain[..., 3] - 0.6 * plain[..., 1], atol=1e-13)
