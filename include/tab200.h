@@ -299,6 +299,8 @@ typedef struct tab_atomic tab_atomic;
 #define TAB_RADIAL_MORSE   1
 #define TAB_RADIAL_DENSITY 2
 #define TAB_RADIAL_PEXP    3
+#define TAB_GRAP_SIGNED_SQRT_M0 1
+#define TAB_GRAP_TRACELESS      2
 
 typedef struct tab_sf_desc {
     int32_t n_el;
@@ -315,11 +317,17 @@ typedef struct tab_sf_desc {
      *   TAB_RADIAL_MORSE   D [e^{-2g(r-r0)} - 2 e^{-g(r-r0)}]    (D, gamma, r0)
      *   TAB_RADIAL_DENSITY A exp(-beta (r/re - 1))               (A, beta, re)
      *   TAB_RADIAL_PEXP    exp(-(r/rl)^pl)                       (rl, pl)
-     * moments[0..n_moments): subset of {0, 1, 2}; feature layout per term:
-     * [tau][moment].  n_moments == 0 means {0} (plain symmetry functions). */
+     * moments[0..n_moments): subset of {0, 1, 2, 3}; feature layout per term:
+     * [tau][moment].  n_moments == 0 means {0} (plain symmetry functions).
+     * grap_flags (new mode of the reference, grap.py:596-680):
+     *   TAB_GRAP_SIGNED_SQRT_M0  the m = 0 entry is sign(P) sqrt(P^2 + 1e-16) (grap.py:667-676)
+     *   TAB_GRAP_TRACELESS       `symmetric=True` multiplicity tensor (grap.py:485-494):
+     *                            m = 2 minus P_0^2 / 3, m = 3 minus 3/5 sum_a P_a^2;
+     *                            needs moments = 0..max */
     int32_t radial_kind;
     int32_t n_moments;
-    int32_t moments[3];
+    int32_t moments[4];
+    int32_t grap_flags;
     const double *p3;                      /* [n_r] or NULL */
 } tab_sf_desc;
 

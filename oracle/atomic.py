@@ -300,6 +300,19 @@ def grap_descriptors_new_mode(elements, types, R, cell, i, j, S, rc, algorithm, 
     return G.reshape(n, nel * H.shape[1] * T.shape[1])
 
 
+def grap_from_dict(grap, elements, types, R, h, nl, rc):
+    """grap: dict(algorithm, grid, moments, cutoff='cosine', new_mode=False,
+    symmetric=False) -> descriptors of the legacy or the new formulation."""
+    if grap.get('new_mode', False):
+        return grap_descriptors_new_mode(elements, types, R, h, nl[0], nl[1], nl[2], rc,
+                                         grap['algorithm'], grap['grid'],
+                                         max(grap['moments']), grap.get('cutoff', 'cosine'),
+                                         grap.get('symmetric', False))
+    return grap_descriptors(elements, types, R, h, nl[0], nl[1], nl[2], rc,
+                            grap['algorithm'], grap['grid'], grap['moments'],
+                            grap.get('cutoff', 'cosine'))
+
+
 def activation(name):
     name = name.lower()
     if name == 'softplus':
@@ -359,9 +372,7 @@ def atomic_evaluate(elements, symbols, positions, cell, pbc, rc, params, sf=None
 
     def energy_fn(R, h):
         if grap is not None:
-            G = grap_descriptors(elements, types, R, h, nl[0], nl[1], nl[2], rc,
-                                 grap['algorithm'], grap['grid'], grap['moments'],
-                                 grap.get('cutoff', 'cosine'))
+            G = grap_from_dict(grap, elements, types, R, h, nl, rc)
         else:
             G = descriptors(elements, types, R, h, nl[0], nl[1], nl[2], rc, acut_eff,
                             angular, ang_list=ang, **sf)

@@ -39,9 +39,7 @@ def loss_and_grads(elements, structures, params, rc, sf=None, acut=None, angular
         R = torch.tensor(pos, dtype=dtype, requires_grad=True)
         h = torch.tensor(cell, dtype=dtype, requires_grad=True)
         if grap is not None:      # GenericRadialAtomicPotential (nn/atomic/grap.py:384-466)
-            G = oat.grap_descriptors(elements, types, R, h, nl[0], nl[1], nl[2], rc,
-                                     grap['algorithm'], grap['grid'], grap['moments'],
-                                     grap.get('cutoff', 'cosine'))
+            G = oat.grap_from_dict(grap, elements, types, R, h, nl, rc)
         else:
             G = oat.descriptors(elements, types, R, h, nl[0], nl[1], nl[2], rc,
                                 acut if acut else rc, angular, **sf)

@@ -71,10 +71,12 @@ class TabSfDesc(C.Structure):
                 ('eta', _DP), ('omega', _DP), ('beta', _DP), ('gamma', _DP),
                 ('zeta', _DP),
                 ('radial_kind', C.c_int32), ('n_moments', C.c_int32),
-                ('moments', C.c_int32 * 3), ('p3', _DP)]
+                ('moments', C.c_int32 * 4), ('grap_flags', C.c_int32), ('p3', _DP)]
 
 
 RADIAL_KINDS = {'sf': 0, 'morse': 1, 'density': 2, 'pexp': 3}
+GRAP_SIGNED_SQRT_M0 = 1      # include/tab200.h: TAB_GRAP_*
+GRAP_TRACELESS = 2
 
 
 class TabMlpDesc(C.Structure):
@@ -470,9 +472,10 @@ class AtomicModel:
     """
 
     def __init__(self, n_el, rc, acut, radial, angular, cutoff, mlps,
-                 radial_kind='sf', moments=(0,)):
+                 radial_kind='sf', moments=(0,), grap_flags=0):
         """radial: list of parameter tuples (2 or 3 values per set, see
-        include/tab200.h: tab_sf_desc); moments: GRAP multipole moments."""
+        include/tab200.h: tab_sf_desc); moments: GRAP multipole moments; grap_flags:
+        GRAP_SIGNED_SQRT_M0 | GRAP_TRACELESS (new mode of the reference)."""
         self._keep = []
 
         def darr(vals):
@@ -493,7 +496,10 @@ class AtomicModel:
         sf.p3 = darr([r[2] if len(r) > 2 else 0.0 for r in radial])
         sf.radial_kind = RADIAL_KINDS[radial_kind]
         moments = sorted(set(int(x) for x in moments))
+        if len(moments) > 4:
+            raise ValueError("GRAP moments: subset of 0..3")
         sf.n_moments = len(moments)
+        sf.grap_flags = int(grap_flags)
         for k, mm in enumerate(moments):
             sf.moments[k] = mm
         ang = angular or []

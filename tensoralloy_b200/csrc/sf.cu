@@ -41,9 +41,11 @@ struct SfDev {
     int n_el, n_r, n_a, angular, cutoff;   // cutoff: 0 cosine, 1 polynomial(gamma=5)
     int d_r, dim;                          // d_r = n_el*n_r*n_mom ; dim = full descriptor length
     // radial family (GRAP, nn/atomic/grap.py): 0 sf (= Behler G2), 1 morse, 2 density,
-    // 3 pexp; moments = subset of {0, 1, 2} in ascending order (legacy-mode layout:
-    // per term, per tau, per moment)
-    int rad_kind, n_mom, mom[3], has_m1, has_m2;
+    // 3 pexp; moments = subset of {0, 1, 2, 3} in ascending order (layout: per term, per
+    // tau, per moment).  New mode of the reference (grap.py:596-680): new_m0 = the m = 0
+    // entry is sign(P) sqrt(P^2 + 1e-16); sym = traceless multiplicity tensor
+    // (grap.py:485-494: m = 2 minus P_0^2 / 3, m = 3 minus 3/5 sum_a P_a^2).
+    int rad_kind, n_mom, mom[4], has_m1, has_m2, has_m3, new_m0, sym;
     double rc, acut;
     double eta[SF_MAX_R], omega[SF_MAX_R], p3[SF_MAX_R];   // parameters 1, 2, 3 per set
     double beta[SF_MAX_A], gamma[SF_MAX_A], zeta[SF_MAX_A];
@@ -71,7 +73,7 @@ struct tab_atomic {
     DevBuf blob;        // double: weights, biases, xlo, xhi of every element + MlpDev table
     size_t mlp_table_off = 0;   // offset (in doubles) of the MlpDev table inside blob
     DevBuf G, dEdG, eat, gvec, fown;
-    DevBuf mom;         // GRAP moment sums [n, n_el, n_r, GRAP_MOM_W] (forward -> backward)
+    DevBuf mom;         // GRAP moment sums [n, n_el, n_r, 10 or 20] (forward -> backward)
 };
 
 // ---------------------------------------------------------------------------
@@ -183,8 +185,27 @@ __device__ __forceinline__ void rad_fn(const SfDev &sf, int tau, Real r, Real rc
     }
 }
 
-// moment sums of one (centre, term, tau): S0, Mx My Mz, Qxx Qyy Qzz Qyz Qxz Qxy
+// moment sums of one (centre, term, tau): S0, Mx My Mz, Qxx Qyy Qzz Qyz Qxz Qxy and, for
+// models with moment 3 (kernels instantiated with MW = 20), the ten unique third-order
+// sums Txxx Txxy Txxz Txyy Txyz Txzz Tyyy Tyyz Tyzz Tzzz (multiplicities 1 3 3 3 6 3 1 3 3 1,
+// grap.py:489-491)
 #define GRAP_MOM_W 10
+#define GRAP_MOM_W3 20
+__device__ __forceinline__ double grap_mult3(int q) {     // q = 10..19
+    return (q == 10 || q == 16 || q == 19) ? 1.0 : (q == 14 ? 6.0 : 3.0);
+}
+// any per-pair unit-vector moment (1, 2 or 3)
+__device__ __forceinline__ bool grap_vec(const SfDev &sf) {
+    return sf.has_m1 || sf.has_m2 || sf.has_m3;
+}
+// the backward / JVP kernels need the moment sums of the forward pass
+__host__ __device__ __forceinline__ bool grap_need_mom(const SfDev &sf) {
+    return sf.has_m1 || sf.has_m2 || sf.has_m3 || sf.new_m0;
+}
+// d/dP of sign(P) sqrt(P^2 + 1e-16)
+__device__ __forceinline__ double grap_dm0(double P) {
+    return fabs(P) / sqrt(P * P + 1e-16);
+}
 
 // shared-memory row layout per warp: 8 doubles per neighbour
 //   0..2 D, 3 r, 4 fc(r; acut), 5 dfc(r; acut)/dr, 6 type (as double), 7 1/r (0 if r = 0)
@@ -254,7 +275,7 @@ __device__ __forceinline__ int pair_term(int a, int b, int nel) {
 // ---------------------------------------------------------------------------
 // forward: descriptors
 // ---------------------------------------------------------------------------
-template <typename Real>
+template <typename Real, int MW>
 __global__ void __launch_bounds__(SF_WARPS * 32)
 k_sf_forward(int n, SfDev sf, int n_types, int row_cap,
              const Atom4 *__restrict__ atoms, const uint8_t *__restrict__ types_ext,
@@ -284,9 +305,9 @@ k_sf_forward(int n, SfDev sf, int n_types, int row_cap,
     for (int t = 0; t < sf.n_el; ++t) {
         const int term = radial_term(ti, t);
         for (int tau = 0; tau < sf.n_r; ++tau) {
-            Real acc[GRAP_MOM_W];
+            Real acc[MW];
 #pragma unroll
-            for (int q = 0; q < GRAP_MOM_W; ++q) acc[q] = Real(0);
+            for (int q = 0; q < MW; ++q) acc[q] = Real(0);
             for (int k = seg[t] + lane; k < seg[t + 1]; k += SF_TPA) {
                 const double *e = row + k * ROW_W;
                 const Real r = (Real)e[3];
@@ -295,7 +316,7 @@ k_sf_forward(int n, SfDev sf, int n_types, int row_cap,
                 rad_fn<Real>(sf, tau, r, rc2i, v, dv);
                 const Real w = v * f;
                 acc[0] += w;
-                if (sf.has_m1 || sf.has_m2) {
+                if (grap_vec(sf)) {
                     const Real ri = r != Real(0) ? Real(1) / r : Real(0);   // div_no_nan
                     const Real ux = (Real)e[0] * ri, uy = (Real)e[1] * ri, uz = (Real)e[2] * ri;
                     acc[1] += w * ux;
@@ -307,25 +328,48 @@ k_sf_forward(int n, SfDev sf, int n_types, int row_cap,
                     acc[7] += w * uy * uz;
                     acc[8] += w * ux * uz;
                     acc[9] += w * ux * uy;
+                    if (MW > GRAP_MOM_W) {
+                        const Real wxx = w * ux * ux, wyy = w * uy * uy, wzz = w * uz * uz;
+                        acc[10] += wxx * ux;
+                        acc[11] += wxx * uy;
+                        acc[12] += wxx * uz;
+                        acc[13] += wyy * ux;
+                        acc[14] += w * ux * uy * uz;
+                        acc[15] += wzz * ux;
+                        acc[16] += wyy * uy;
+                        acc[17] += wyy * uz;
+                        acc[18] += wzz * uy;
+                        acc[19] += wzz * uz;
+                    }
                 }
             }
-            double tot[GRAP_MOM_W];
-            const int nsum = (sf.has_m1 || sf.has_m2) ? GRAP_MOM_W : 1;
+            double tot[MW];
+            const int nsum = grap_need_mom(sf) ? MW : 1;
             for (int q = 0; q < nsum; ++q) tot[q] = block_sum((double)acc[q], red);
             if (lane == 0) {
                 double *gg = g + (size_t)(term * sf.n_r + tau) * sf.n_mom;
                 for (int mi = 0; mi < sf.n_mom; ++mi) {
                     const int mm = sf.mom[mi];
-                    if (mm == 0) gg[mi] = tot[0];
+                    if (mm == 0)
+                        gg[mi] = sf.new_m0 ? copysign(sqrt(tot[0] * tot[0] + 1e-16), tot[0]) *
+                                                 (tot[0] != 0.0 ? 1.0 : 0.0)
+                                           : tot[0];
                     else if (mm == 1) gg[mi] = tot[1] * tot[1] + tot[2] * tot[2] + tot[3] * tot[3];
-                    else
+                    else if (mm == 2)
                         gg[mi] = tot[4] * tot[4] + tot[5] * tot[5] + tot[6] * tot[6] +
-                                 2.0 * (tot[7] * tot[7] + tot[8] * tot[8] + tot[9] * tot[9]);
+                                 2.0 * (tot[7] * tot[7] + tot[8] * tot[8] + tot[9] * tot[9]) -
+                                 (sf.sym ? tot[0] * tot[0] * (1.0 / 3.0) : 0.0);
+                    else if (MW > GRAP_MOM_W) {
+                        double g3 = 0.0;
+                        for (int q = GRAP_MOM_W; q < MW; ++q) g3 += grap_mult3(q) * tot[q] * tot[q];
+                        if (sf.sym)
+                            g3 -= 0.6 * (tot[1] * tot[1] + tot[2] * tot[2] + tot[3] * tot[3]);
+                        gg[mi] = g3;
+                    }
                 }
                 if (mom && nsum > 1) {
-                    double *mo = mom + ((size_t)idx * sf.n_el * sf.n_r + term * sf.n_r + tau) *
-                                           GRAP_MOM_W;
-                    for (int q = 0; q < GRAP_MOM_W; ++q) mo[q] = tot[q];
+                    double *mo = mom + ((size_t)idx * sf.n_el * sf.n_r + term * sf.n_r + tau) * MW;
+                    for (int q = 0; q < MW; ++q) mo[q] = tot[q];
                 }
             }
         }
@@ -538,7 +582,7 @@ k_mlp(int n, int dim, const uint8_t *__restrict__ types_ext, const MlpDev *__res
 // ---------------------------------------------------------------------------
 // backward: per-entry gradients g_p = dE_i/dD_p
 // ---------------------------------------------------------------------------
-template <typename Real>
+template <typename Real, int MW>
 __global__ void __launch_bounds__(SF_WARPS * 32)
 k_sf_backward(int n, SfDev sf, int n_types, int row_cap,
               const Atom4 *__restrict__ atoms, const uint8_t *__restrict__ types_ext,
@@ -555,7 +599,7 @@ k_sf_backward(int n, SfDev sf, int n_types, int row_cap,
     {
         double *row = smem;
         const int cnt = stage_row<Real>(sf, idx, lane, SF_TPA, atoms, counts, slice_ptr, col, row);
-        const double *mo_atom = mom ? mom + (size_t)idx * sf.n_el * sf.n_r * GRAP_MOM_W : nullptr;
+        const double *mo_atom = mom ? mom + (size_t)idx * sf.n_el * sf.n_r * MW : nullptr;
         const int ti = (int)types_ext[idx];
         const double *c = dEdG + (size_t)idx * sf.dim;
         const Real rc = (Real)sf.rc, rc2i = Real(1) / (rc * rc);
@@ -665,13 +709,13 @@ k_sf_backward(int n, SfDev sf, int n_types, int row_cap,
                     rad_fn<Real>(sf, tau, ra, rc2i, v, dv);
                     const Real w = v * f, dw = dv * f + v * df;
                     const double *cc = c + (size_t)(term * sf.n_r + tau) * sf.n_mom;
-                    const double *mo = mo_atom ? mo_atom + (size_t)(term * sf.n_r + tau) *
-                                                               GRAP_MOM_W : nullptr;
+                    const double *mo = mo_atom ? mo_atom + (size_t)(term * sf.n_r + tau) * MW
+                                               : nullptr;
                     for (int mi = 0; mi < sf.n_mom; ++mi) {
                         const int mm = sf.mom[mi];
                         const Real ck = (Real)cc[mi];
                         if (mm == 0) {
-                            s_r += ck * dw;
+                            s_r += (sf.new_m0 && mo ? ck * (Real)grap_dm0(mo[0]) : ck) * dw;
                         } else if (mm == 1) {
                             // G = |M|^2, M = sum w u:  dG/dD = 2 [ (dw - w/r)(M.u) u + (w/r) M ]
                             const Real Mx = (Real)mo[1], My = (Real)mo[2], Mz = (Real)mo[3];
@@ -681,7 +725,7 @@ k_sf_backward(int n, SfDev sf, int n_types, int row_cap,
                             wx += Real(2) * ck * wr * Mx;
                             wy += Real(2) * ck * wr * My;
                             wz += Real(2) * ck * wr * Mz;
-                        } else {
+                        } else if (mm == 2) {
                             // G = sum_ab Q_ab^2, Q = sum w u (x) u:
                             //   dG/dD = 2 [ (dw - 2 w/r)(u.Q.u) u + 2 (w/r) Q.u ]
                             const Real Qxx = (Real)mo[4], Qyy = (Real)mo[5], Qzz = (Real)mo[6],
@@ -695,6 +739,38 @@ k_sf_backward(int n, SfDev sf, int n_types, int row_cap,
                             wx += Real(4) * ck * wr * qx;
                             wy += Real(4) * ck * wr * qy;
                             wz += Real(4) * ck * wr * qz;
+                            if (sf.sym)       // minus P_0^2 / 3
+                                s_r -= ck * Real(2.0 / 3.0) * (Real)mo[0] * dw;
+                        } else if (MW > GRAP_MOM_W) {
+                            // G = sum_abc T_abc^2, T = sum w u (x) u (x) u:
+                            //   dG/dD = 2 [ (dw - 3 w/r)(T:uuu) u + 3 (w/r) T:uu ]
+                            const Real Txxx = (Real)mo[10], Txxy = (Real)mo[11], Txxz = (Real)mo[12],
+                                       Txyy = (Real)mo[13], Txyz = (Real)mo[14], Txzz = (Real)mo[15],
+                                       Tyyy = (Real)mo[16], Tyyz = (Real)mo[17], Tyzz = (Real)mo[18],
+                                       Tzzz = (Real)mo[19];
+                            const Real xx = ux * ux, yy = uy * uy, zz = uz * uz, xy = ux * uy,
+                                       xz = ux * uz, yz = uy * uz;
+                            const Real tx = Txxx * xx + Txyy * yy + Txzz * zz +
+                                            Real(2) * (Txxy * xy + Txxz * xz + Txyz * yz);
+                            const Real ty = Txxy * xx + Tyyy * yy + Tyzz * zz +
+                                            Real(2) * (Txyy * xy + Txyz * xz + Tyyz * yz);
+                            const Real tz = Txxz * xx + Tyyz * yy + Tzzz * zz +
+                                            Real(2) * (Txyz * xy + Txzz * xz + Tyzz * yz);
+                            const Real tuuu = tx * ux + ty * uy + tz * uz;
+                            const Real wr = w * ri;
+                            s_r += Real(2) * ck * (dw - Real(3) * wr) * tuuu;
+                            wx += Real(6) * ck * wr * tx;
+                            wy += Real(6) * ck * wr * ty;
+                            wz += Real(6) * ck * wr * tz;
+                            if (sf.sym) {     // minus 3/5 |M|^2
+                                const Real cs = Real(-0.6) * ck;
+                                const Real Mx = (Real)mo[1], My = (Real)mo[2], Mz = (Real)mo[3];
+                                const Real mu = Mx * ux + My * uy + Mz * uz;
+                                s_r += Real(2) * cs * (dw - wr) * mu;
+                                wx += Real(2) * cs * wr * Mx;
+                                wy += Real(2) * cs * wr * My;
+                                wz += Real(2) * cs * wr * Mz;
+                            }
                         }
                     }
                 }
@@ -897,7 +973,7 @@ k_sf_reduce(int nb_e, const double *__restrict__ partial_e, int nb_v,
 // d(loss)/d(parameters) through dE/dG) -- the reference gets it from TF's
 // second-order autograd (nn/opt.py:132-157).
 // ---------------------------------------------------------------------------
-template <typename Real>
+template <typename Real, int MW>
 __global__ void __launch_bounds__(SF_WARPS * 32)
 k_sf_jvp(int n, int n_loc, SfDev sf, int n_types, int row_cap,
          const Atom4 *__restrict__ atoms, const uint8_t *__restrict__ types_ext,
@@ -944,15 +1020,17 @@ k_sf_jvp(int n, int n_loc, SfDev sf, int n_types, int row_cap,
     //        m = 2:  G = sum Q_ab^2, dG = 2 Q : dQ,
     //                dQ = sum [w' s u (x) u + (w / r) (dD_perp (x) u + u (x) dD_perp)]
     //      (M, Q = the moment sums of the forward pass, `mom`)
-    const bool grap = sf.has_m1 || sf.has_m2;
-    const double *mo_atom = (grap && mom) ? mom + (size_t)idx * sf.n_el * sf.n_r * GRAP_MOM_W
-                                          : nullptr;
+    //        m = 3:  G = sum T_abc^2, dG = 2 T : dT,
+    //                dT = sum [w' s u(x)u(x)u + (w / r) sym(dD_perp (x) u (x) u)]
+    const bool grap = grap_vec(sf);
+    const double *mo_atom = (grap_need_mom(sf) && mom)
+                                ? mom + (size_t)idx * sf.n_el * sf.n_r * MW : nullptr;
     for (int s = 0; s < sf.n_el; ++s) {
         const int term = radial_term(ti, s);
         for (int tau = 0; tau < sf.n_r; ++tau) {
-            Real acc[GRAP_MOM_W];
+            Real acc[MW];
 #pragma unroll
-            for (int q = 0; q < GRAP_MOM_W; ++q) acc[q] = Real(0);
+            for (int q = 0; q < MW; ++q) acc[q] = Real(0);
             for (int k = seg[s] + lane; k < seg[s + 1]; k += SF_TPA) {
                 const double *e = row + k * ROW_W;
                 const Real r = (Real)e[3], ri = (Real)e[7];
@@ -977,23 +1055,45 @@ k_sf_jvp(int n, int n_loc, SfDev sf, int n_types, int row_cap,
                     acc[7] += c1 * uy * uz + wr * (py * uz + pz * uy);
                     acc[8] += c1 * ux * uz + wr * (px * uz + pz * ux);
                     acc[9] += c1 * ux * uy + wr * (px * uy + py * ux);
+                    if (MW > GRAP_MOM_W) {
+                        const Real xx = ux * ux, yy = uy * uy, zz = uz * uz;
+                        acc[10] += c1 * xx * ux + Real(3) * wr * px * xx;
+                        acc[11] += c1 * xx * uy + wr * (Real(2) * px * ux * uy + xx * py);
+                        acc[12] += c1 * xx * uz + wr * (Real(2) * px * ux * uz + xx * pz);
+                        acc[13] += c1 * ux * yy + wr * (px * yy + Real(2) * ux * py * uy);
+                        acc[14] += c1 * ux * uy * uz +
+                                   wr * (px * uy * uz + ux * py * uz + ux * uy * pz);
+                        acc[15] += c1 * ux * zz + wr * (px * zz + Real(2) * ux * pz * uz);
+                        acc[16] += c1 * yy * uy + Real(3) * wr * py * yy;
+                        acc[17] += c1 * yy * uz + wr * (Real(2) * py * uy * uz + yy * pz);
+                        acc[18] += c1 * uy * zz + wr * (py * zz + Real(2) * uy * pz * uz);
+                        acc[19] += c1 * zz * uz + Real(3) * wr * pz * zz;
+                    }
                 }
             }
-            double tot[GRAP_MOM_W];
-            const int nsum = grap ? GRAP_MOM_W : 1;
+            double tot[MW];
+            const int nsum = grap ? MW : 1;
             for (int q = 0; q < nsum; ++q) tot[q] = block_sum((double)acc[q], red);
             if (lane == 0) {
                 double *tt = t + (size_t)(term * sf.n_r + tau) * sf.n_mom;
-                const double *mo = mo_atom ? mo_atom + (size_t)(term * sf.n_r + tau) * GRAP_MOM_W
+                const double *mo = mo_atom ? mo_atom + (size_t)(term * sf.n_r + tau) * MW
                                            : nullptr;
                 for (int mi = 0; mi < sf.n_mom; ++mi) {
                     const int mm = sf.mom[mi];
-                    if (mm == 0) tt[mi] = tot[0];
+                    if (mm == 0) tt[mi] = (sf.new_m0 && mo) ? grap_dm0(mo[0]) * tot[0] : tot[0];
                     else if (mm == 1)
                         tt[mi] = 2.0 * (mo[1] * tot[1] + mo[2] * tot[2] + mo[3] * tot[3]);
-                    else
+                    else if (mm == 2)
                         tt[mi] = 2.0 * (mo[4] * tot[4] + mo[5] * tot[5] + mo[6] * tot[6] +
-                                        2.0 * (mo[7] * tot[7] + mo[8] * tot[8] + mo[9] * tot[9]));
+                                        2.0 * (mo[7] * tot[7] + mo[8] * tot[8] + mo[9] * tot[9])) -
+                                 (sf.sym ? (2.0 / 3.0) * mo[0] * tot[0] : 0.0);
+                    else if (MW > GRAP_MOM_W) {
+                        double g3 = 0.0;
+                        for (int q = GRAP_MOM_W; q < MW; ++q) g3 += grap_mult3(q) * mo[q] * tot[q];
+                        if (sf.sym)
+                            g3 -= 0.6 * (mo[1] * tot[1] + mo[2] * tot[2] + mo[3] * tot[3]);
+                        tt[mi] = 2.0 * g3;
+                    }
                 }
             }
         }
@@ -1115,20 +1215,33 @@ extern "C" int tab_atomic_create(tab_atomic **out, const tab_sf_desc *d,
     }
     sf.rad_kind = d->radial_kind;
     sf.n_mom = d->n_moments > 0 ? d->n_moments : 1;
-    if (sf.rad_kind < 0 || sf.rad_kind > 3 || sf.n_mom > 3) {
+    if (sf.rad_kind < 0 || sf.rad_kind > 3 || sf.n_mom > 4) {
         tab_set_error("tab_atomic_create: unknown radial family / moments");
         delete m;
         return TAB_EINVAL;
     }
     for (int k = 0; k < sf.n_mom; ++k) {
         sf.mom[k] = d->n_moments > 0 ? d->moments[k] : 0;
-        if (sf.mom[k] < 0 || sf.mom[k] > 2) {
-            tab_set_error("tab_atomic_create: moment %d is not supported (0, 1, 2)", sf.mom[k]);
+        if (sf.mom[k] < 0 || sf.mom[k] > 3) {
+            tab_set_error("tab_atomic_create: moment %d is not supported (0 .. 3)", sf.mom[k]);
             delete m;
             return TAB_EUNSUPPORTED;
         }
         if (sf.mom[k] == 1) sf.has_m1 = 1;
         if (sf.mom[k] == 2) sf.has_m2 = 1;
+        if (sf.mom[k] == 3) sf.has_m3 = 1;
+    }
+    sf.new_m0 = (d->grap_flags & TAB_GRAP_SIGNED_SQRT_M0) ? 1 : 0;
+    sf.sym = (d->grap_flags & TAB_GRAP_TRACELESS) ? 1 : 0;
+    if (sf.sym) {
+        // the traceless entries subtract lower moments of the same list: they must be there
+        bool ok = true;
+        for (int k = 0; k < sf.n_mom; ++k) ok = ok && sf.mom[k] == k;
+        if (!ok) {
+            tab_set_error("tab_atomic_create: TAB_GRAP_TRACELESS needs moments 0..max");
+            delete m;
+            return TAB_EINVAL;
+        }
     }
     for (int k = 0; k < sf.n_a; ++k) {
         sf.beta[k] = d->beta[k];
@@ -1262,6 +1375,26 @@ extern "C" int tab_atomic_free(tab_atomic *m) {
 
 extern "C" int tab_atomic_dim(const tab_atomic *m) { return m ? m->sf.dim : 0; }
 
+// the geometry kernels exist in two widths of the moment-sum record: 10 (moments <= 2) and
+// 20 (moment 3); `sf` and `Real` are taken from the calling scope
+#define SF_MOM_W(sf) ((sf).has_m3 ? GRAP_MOM_W3 : GRAP_MOM_W)
+#define SF_LAUNCH(kern, grid, smem, st, ...)                                              \
+    do {                                                                                  \
+        if (sf.has_m3)                                                                    \
+            kern<Real, GRAP_MOM_W3><<<grid, SF_WARPS * 32, smem, st>>>(__VA_ARGS__);      \
+        else                                                                              \
+            kern<Real, GRAP_MOM_W><<<grid, SF_WARPS * 32, smem, st>>>(__VA_ARGS__);       \
+    } while (0)
+#define SF_SMEM_ATTR(kern)                                                                \
+    do {                                                                                  \
+        TAB_CUDA(cudaFuncSetAttribute(kern<Real, GRAP_MOM_W>,                             \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                                      220 * 1024));                                       \
+        TAB_CUDA(cudaFuncSetAttribute(kern<Real, GRAP_MOM_W3>,                            \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                                      220 * 1024));                                       \
+    } while (0)
+
 template <typename Real>
 static int atomic_run(tab_atomic *m, tab_nbr *nbr, double *d_energy, double *d_eatom,
                       double *d_forces, double *d_virial, double *d_desc,
@@ -1299,10 +1432,8 @@ static int atomic_run(tab_atomic *m, tab_nbr *nbr, double *d_energy, double *d_e
     static bool attr_done[2] = {false, false};
     const int ai = sizeof(Real) == 8 ? 0 : 1;
     if (!attr_done[ai]) {
-        TAB_CUDA(cudaFuncSetAttribute(k_sf_forward<Real>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        TAB_CUDA(cudaFuncSetAttribute(k_sf_backward<Real>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        SF_SMEM_ATTR(k_sf_forward);
+        SF_SMEM_ATTR(k_sf_backward);
         TAB_CUDA(cudaFuncSetAttribute(k_mlp<Real>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         attr_done[ai] = true;
@@ -1316,10 +1447,10 @@ static int atomic_run(tab_atomic *m, tab_nbr *nbr, double *d_energy, double *d_e
     TAB_TRY(m->fown.ensure(sizeof(double) * 3 * (size_t)n));
     TAB_TRY(nbr->partial.ensure(sizeof(double) * (8 * (size_t)nblk + nblk_c + 8)));
     const Atom4 *atoms = nbr->atoms.as<Atom4>();
-    const bool grap_moments = sf.has_m1 || sf.has_m2;
+    const bool grap_moments = grap_need_mom(sf);
     if (grap_moments)
-        TAB_TRY(m->mom.ensure(sizeof(double) * (size_t)n * sf.n_el * sf.n_r * GRAP_MOM_W));
-    k_sf_forward<Real><<<nblk, SF_WARPS * 32, smem_row, st>>>(
+        TAB_TRY(m->mom.ensure(sizeof(double) * (size_t)n * sf.n_el * sf.n_r * SF_MOM_W(sf)));
+    SF_LAUNCH(k_sf_forward, nblk, smem_row, st,
         n, sf, nbr->n_types, row_cap, atoms, nbr->types_ext.as<uint8_t>(),
         nbr->counts.as<int>(), nbr->tcounts.as<int>(), nbr->slice_ptr.as<uint32_t>(),
         nbr->col.as<uint32_t>(), m->G.as<double>(),
@@ -1368,7 +1499,7 @@ static int atomic_run(tab_atomic *m, tab_nbr *nbr, double *d_energy, double *d_e
     if (need_grad) {
         TAB_TRY(tab_nbr_ensure_reverse(nbr, st));
         TAB_TRY(m->gvec.ensure(sizeof(double) * 3 * (plane + 32)));
-        k_sf_backward<Real><<<nblk, SF_WARPS * 32, smem_row, st>>>(
+        SF_LAUNCH(k_sf_backward, nblk, smem_row, st,
             n, sf, nbr->n_types, row_cap, atoms, nbr->types_ext.as<uint8_t>(),
             nbr->counts.as<int>(), nbr->tcounts.as<int>(), nbr->slice_ptr.as<uint32_t>(),
             nbr->col.as<uint32_t>(), m->dEdG.as<double>(), m->gvec.as<double>(), plane,
@@ -1473,11 +1604,10 @@ static int forward_moments(tab_atomic *m, tab_nbr *nbr, cudaStream_t st) {
         tab_set_error("neighbour rows of %d entries exceed the shared-memory budget", row_cap);
         return TAB_EUNSUPPORTED;
     }
-    TAB_CUDA(cudaFuncSetAttribute(k_sf_forward<Real>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    SF_SMEM_ATTR(k_sf_forward);
     TAB_TRY(m->G.ensure(sizeof(double) * (size_t)n * sf.dim));
-    TAB_TRY(m->mom.ensure(sizeof(double) * (size_t)n * sf.n_el * sf.n_r * GRAP_MOM_W));
-    k_sf_forward<Real><<<n, SF_WARPS * 32, smem_row, st>>>(
+    TAB_TRY(m->mom.ensure(sizeof(double) * (size_t)n * sf.n_el * sf.n_r * SF_MOM_W(sf)));
+    SF_LAUNCH(k_sf_forward, n, smem_row, st,
         n, sf, nbr->n_types, row_cap, nbr->atoms.as<Atom4>(), nbr->types_ext.as<uint8_t>(),
         nbr->counts.as<int>(), nbr->tcounts.as<int>(), nbr->slice_ptr.as<uint32_t>(),
         nbr->col.as<uint32_t>(), m->G.as<double>(), m->mom.as<double>());
@@ -1492,8 +1622,7 @@ static int atomic_forces_from(tab_atomic *m, tab_nbr *nbr, const double *d_dedg,
     const SfDev &sf = m->sf;
     const int row_cap = nbr->nnl_max > 0 ? nbr->nnl_max : 1;
     const size_t smem_row = (size_t)row_cap * ROW_W * sizeof(double);
-    TAB_CUDA(cudaFuncSetAttribute(k_sf_backward<Real>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    SF_SMEM_ATTR(k_sf_backward);
     const int nblk = n, nblk_c = (n + 3) / 4;
     TAB_TRY(m->dEdG.ensure(sizeof(double) * (size_t)n * sf.dim));
     TAB_TRY(m->eat.ensure(sizeof(double) * (size_t)n));
@@ -1502,7 +1631,7 @@ static int atomic_forces_from(tab_atomic *m, tab_nbr *nbr, const double *d_dedg,
     TAB_TRY(tab_nbr_ensure_reverse(nbr, st));
     const size_t plane = (size_t)nbr->ell_rows * 32;
     TAB_TRY(m->gvec.ensure(sizeof(double) * 3 * (plane + 32)));
-    const bool grap_moments = sf.has_m1 || sf.has_m2;
+    const bool grap_moments = grap_need_mom(sf);
     if (grap_moments) TAB_TRY(forward_moments<Real>(m, nbr, st));
     const size_t tot = (size_t)n * sf.dim;
     k_rows_to_sorted<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(
@@ -1510,7 +1639,7 @@ static int atomic_forces_from(tab_atomic *m, tab_nbr *nbr, const double *d_dedg,
     TAB_LAUNCH_CHECK();
     TAB_CUDA(cudaMemsetAsync(m->eat.p, 0, sizeof(double) * (size_t)n, st));
     double *partial = nbr->partial.as<double>();
-    k_sf_backward<Real><<<nblk, SF_WARPS * 32, smem_row, st>>>(
+    SF_LAUNCH(k_sf_backward, nblk, smem_row, st,
         n, sf, nbr->n_types, row_cap, nbr->atoms.as<Atom4>(), nbr->types_ext.as<uint8_t>(),
         nbr->counts.as<int>(), nbr->tcounts.as<int>(), nbr->slice_ptr.as<uint32_t>(),
         nbr->col.as<uint32_t>(), m->dEdG.as<double>(), m->gvec.as<double>(), plane,
@@ -1553,10 +1682,9 @@ static int atomic_jvp(tab_atomic *m, tab_nbr *nbr, const double *d_u, const doub
         tab_set_error("neighbour rows of %d entries exceed the shared-memory budget", row_cap);
         return TAB_EUNSUPPORTED;
     }
-    TAB_CUDA(cudaFuncSetAttribute(k_sf_jvp<Real>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    SF_SMEM_ATTR(k_sf_jvp);
     const int nblk = n;
-    const bool grap_moments = sf.has_m1 || sf.has_m2;
+    const bool grap_moments = grap_need_mom(sf);
     if (grap_moments) TAB_TRY(forward_moments<Real>(m, nbr, st));   // before G is reused as T
     TAB_TRY(m->fown.ensure(sizeof(double) * 3 * (size_t)n));
     TAB_TRY(m->G.ensure(sizeof(double) * (size_t)n * sf.dim));
@@ -1564,7 +1692,7 @@ static int atomic_jvp(tab_atomic *m, tab_nbr *nbr, const double *d_u, const doub
     k_rows_to_sorted<<<(unsigned)(((size_t)n * 3 + 255) / 256), 256, 0, st>>>(
         n, 3, nbr->perm.as<int>(), d_u, m->fown.as<double>());
     TAB_LAUNCH_CHECK();
-    k_sf_jvp<Real><<<nblk, SF_WARPS * 32, smem, st>>>(
+    SF_LAUNCH(k_sf_jvp, nblk, smem, st,
         n, nbr->n_loc, sf, nbr->n_types, row_cap, nbr->atoms.as<Atom4>(),
         nbr->types_ext.as<uint8_t>(), nbr->counts.as<int>(), nbr->tcounts.as<int>(),
         nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>(), nbr->ghost_owner.as<int>(),

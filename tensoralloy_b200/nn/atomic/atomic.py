@@ -154,7 +154,8 @@ class AtomicNN(BasicNN):
             len(self._elements), clf.rcut, clf.acut,
             sf.radial_sets(), sf.angular_sets() if clf.angular else None,
             sf.cutoff_function, [self.mlp_params(el) for el in self._elements],
-            radial_kind=sf.radial_kind(), moments=sf.moments())
+            radial_kind=sf.radial_kind(), moments=sf.moments(),
+            grap_flags=getattr(sf, 'grap_flags', lambda: 0)())
         return self._model
 
     def required_cutoff(self):

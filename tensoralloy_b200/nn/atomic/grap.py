@@ -9,6 +9,7 @@ tau of the chosen algorithm f_tau(r) and every requested multipole moment:
     m = 0   sum_j f(r_ij) fc(r_ij)
     m = 1   sum_a  ( sum_j f fc d_a / r )^2              a in x, y, z
     m = 2   sum_ab ( sum_j f fc d_a d_b / r^2 )^2        all 9 (a, b)
+    m = 3   sum_abc ( sum_j f fc d_a d_b d_c / r^3 )^2   all 27 (a, b, c); new mode only
 
 laid out per term as [tau][moment] (grap.py:419-457), terms in
 `kbody_terms_for_element[c]` order.  The arithmetic runs on the GPU
@@ -20,10 +21,13 @@ the descriptor holds EVERY moment 0..max(moment_tensors) per (term, tau)
 unsymmetric multiplicity tensor (grap.py:471-496: 1 | 1 1 1 | 1 2 2 1 2 1 over the
 unique index pairs), the same sums as above -- the reference's own test states the
 equality (nn/atomic/tests/test_grap.py:152-200).  It is served by the same kernels
-with the moment list widened to 0..max.  One deliberate difference: the reference
-writes the m = 0 entry as sign(P) * sqrt(P^2 + 1e-16); the kernels keep P itself
-(|difference| <= 5e-17 / |P|).  Not built, and refused loudly: the trainable `nn`
-algorithm, moment 3 and above, and `symmetric=True` (traceless T_dm) in new mode.
+with the moment list widened to 0..max and two flags of the C ABI
+(include/tab200.h: TAB_GRAP_SIGNED_SQRT_M0 -- the m = 0 entry is
+sign(P) sqrt(P^2 + 1e-16), grap.py:667-676; TAB_GRAP_TRACELESS -- `symmetric=True`,
+grap.py:485-494).  Moment 3 (ten unique third-order sums, multiplicities
+1 3 3 3 6 3 1 3 3 1) exists in new mode only, as in the reference (its legacy loop
+stops at 2, grap.py:434-457).  Not built, and refused loudly: the trainable `nn`
+algorithm (grap.py:211-234) and moments 4, 5 (`get_moment_tensor`, grap.py:537-572).
 """
 import numpy as np
 
@@ -61,11 +65,10 @@ class GenericRadialAtomicPotential:
         if isinstance(moment_tensors, int):
             moment_tensors = [moment_tensors]
         moment_tensors = sorted(set(int(m) for m in moment_tensors))
-        if any(m not in (0, 1, 2) for m in moment_tensors):
-            raise ValueError("GRAP: moments 0, 1, 2 are supported")
-        if not legacy_mode and symmetric and max(moment_tensors) >= 2:
-            raise ValueError("GRAP: symmetric=True (traceless T_dm) is not implemented "
-                             "in new mode")
+        allowed = (0, 1, 2) if legacy_mode else (0, 1, 2, 3)
+        if any(m not in allowed for m in moment_tensors):
+            raise ValueError("GRAP: moments 0, 1, 2 (legacy mode) / 0 .. 3 (new mode) "
+                             "are supported")
         keys = ALGORITHMS[algorithm]
         if parameters is None:
             parameters = {'eta': [0.05, 4.0, 20.0, 80.0], 'omega': [0.0] * 4} \
@@ -119,6 +122,13 @@ class GenericRadialAtomicPotential:
         if not self._legacy_mode:
             return tuple(range(self.max_moment + 1))
         return tuple(self._moment_tensors)
+
+    def grap_flags(self):
+        """include/tab200.h TAB_GRAP_*: the two new-mode details the kernels switch on
+        (legacy mode ignores `symmetric`, grap.py:384-466)."""
+        if self._legacy_mode:
+            return 0
+        return 1 | (2 if self._symmetric else 0)
 
     def dimension(self, angular=False):
         if angular:

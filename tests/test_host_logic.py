@@ -196,10 +196,13 @@ def test_grap_new_mode_layout_and_refusals():
     assert legacy.moments() == (0, 2) and legacy.dimension() == 2 * 3 * 2
     assert new.moments() == (0, 1, 2) and new.dimension() == 2 * 3 * 3
     assert new.as_dict()["moment_tensors"] == [2] and new.as_dict()["legacy_mode"] is False
-    with pytest.raises(ValueError, match="symmetric"):
-        Grap(['Be'], 'sf', par, moment_tensors=2, symmetric=True, legacy_mode=False)
-    Grap(['Be'], 'sf', par, moment_tensors=2, symmetric=True)    # ignored in legacy mode
+    assert legacy.grap_flags() == 0 and new.grap_flags() == 1
+    sym = Grap(['Be'], 'sf', par, moment_tensors=3, symmetric=True, legacy_mode=False)
+    assert sym.grap_flags() == 3 and sym.moments() == (0, 1, 2, 3)
+    assert Grap(['Be'], 'sf', par, moment_tensors=2, symmetric=True).grap_flags() == 0
     with pytest.raises(ValueError, match="not implemented"):
         Grap(['Be'], 'nn', {}, legacy_mode=False)
     with pytest.raises(ValueError, match="moments 0, 1, 2"):
-        Grap(['Be'], 'sf', par, moment_tensors=3, legacy_mode=False)
+        Grap(['Be'], 'sf', par, moment_tensors=3)                 # legacy stops at 2
+    with pytest.raises(ValueError, match="moments 0, 1, 2"):
+        Grap(['Be'], 'sf', par, moment_tensors=4, legacy_mode=False)
