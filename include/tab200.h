@@ -310,7 +310,7 @@ typedef struct tab_sf_desc {
     double  rc, acut;
     const double *eta, *omega;             /* [n_r] */
     const double *beta, *gamma, *zeta;     /* [n_a] */
-    /* GenericRadialAtomicPotential, legacy mode (nn/atomic/grap.py:121-466): the
+    /* GenericRadialAtomicPotential (nn/atomic/grap.py:121-466 legacy mode, :470-680 new mode): the
      * radial family and its multipole moments.  Parameters 1, 2 of set tau live in
      * eta[tau], omega[tau], parameter 3 in p3[tau]:
      *   TAB_RADIAL_SF      exp(-eta (r-omega)^2 / rc^2)          (= Behler G2)
@@ -383,7 +383,7 @@ int tab_atomic_descriptors(tab_atomic *model, tab_nbr *nbr, int32_t precision,
  *                       d_u [n,3], d_A [9] on the device, d_out [n, dim])
  * so a force / stress loss back-propagates to the network parameters through c --
  * what the reference obtains from TF second-order autograd (nn/opt.py:132-157).  Symmetry
- * functions and the GRAP families with moments 0, 1, 2 (the moment sums of the lists are
+ * functions and the GRAP families with moments 0 .. 3 (the moment sums of the lists are
  * recomputed inside the call); single-structure and batch handles (d_virial / d_A per
  * structure). */
 int tab_atomic_forces(tab_atomic *model, tab_nbr *nbr, int32_t precision,
