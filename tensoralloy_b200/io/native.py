@@ -30,6 +30,9 @@ Differences to the reference, all on the safe side:
     without complaint, here it is a ValueError.
   * the `nn` (filter network) algorithm of GRAP is not built:
     `use_fnn = 1` files are rejected on read.
+  * the file does not record `legacy_mode`; a file with `is_T_symmetric = 1` or
+    `max_moment = 3` (new-mode-only features, grap.py:434-457, 485-494) reads back as a
+    new-mode descriptor, any other file as a legacy one (equal numbers there).
 """
 import numpy as np
 
@@ -186,14 +189,18 @@ def read_lammps_native(model_path, export_properties=('energy', 'forces', 'stres
     params = {k: np.asarray(z[f"descriptor::{k}"], dtype=np.float64).reshape(-1).tolist()
               for k in METHOD_KEYS[algo]}
     max_moment = int(z["max_moment"])
-    if max_moment > 2:
-        raise ValueError("npz model: moments up to 2 are supported")
+    if max_moment > 3:
+        raise ValueError("npz model: moments up to 3 are supported")
     fct = {v: k for k, v in FCTYPE.items()}[int(z["fctype"])]
     act = {v: k for k, v in ACTFN.items()}[int(z["actfn"])]
     sym = bool(int(z["is_T_symmetric"])) if "is_T_symmetric" in z.files else False
+    # the file does not say which formulation trained the model; they agree for moments
+    # <= 2 with the plain multiplicity tensor (test_grap.py:46-149), so only a traceless
+    # T_dm or moment 3 (both exist in new mode only, grap.py:434-457, 485-494) select it
     desc = GenericRadialAtomicPotential(
         elements, algorithm=algo, parameters=params, param_space_method='pair',
-        moment_tensors=list(range(max_moment + 1)), cutoff_function=fct, symmetric=sym)
+        moment_tensors=list(range(max_moment + 1)), cutoff_function=fct, symmetric=sym,
+        legacy_mode=not (sym or max_moment > 2))
     sizes = [int(x) for x in np.asarray(z["layer_sizes"]).reshape(-1)]
     if len(sizes) != int(z["nlayers"]) or sizes[-1] != 1:
         raise ValueError("npz model: inconsistent layer_sizes / nlayers")

@@ -326,3 +326,39 @@ def test_pb_export_evaluates_like_the_source_model(tmp_path):
     assert np.abs(a.results['forces'] - b.results['forces']).max() < 1e-12
     assert np.abs(a.results['stress'] - b.results['stress']).max() < 1e-12
     assert np.abs(a.results['forces']).max() > 1e-3
+
+
+def test_npz_round_trip_keeps_the_new_mode_details(tmp_path):
+    """`is_T_symmetric` and `max_moment` = 3 exist in the reference's new mode only
+    (grap.py:434-457, 485-494): a file carrying either reads back as a new-mode model;
+    plain files with moments <= 2 stay legacy (the two agree there)."""
+    from tensoralloy_b200.io import native
+    from tensoralloy_b200.nn.atomic import GenericRadialAtomicPotential as Grap
+    par = dict(rl=[1.5, 2.5], pl=[2.0, 3.0])
+
+    def model(**kw):
+        desc = Grap(['Be'], 'pexp', par, **kw)
+        nn = AtomicNN(['Be'], desc, hidden_sizes=[8, 8], minmax_scale=False,
+                      export_properties=('energy', 'forces', 'stress'))
+        nn.attach_transformer(UniversalTransformer(['Be'], rcut=5.0, angular=False))
+        nn.initialize_variables(seed=1)
+        return nn
+
+    for kw, flags, moments in ((dict(moment_tensors=3, symmetric=True, legacy_mode=False), 3,
+                                (0, 1, 2, 3)),
+                               (dict(moment_tensors=2, symmetric=True, legacy_mode=False), 3,
+                                (0, 1, 2)),
+                               (dict(moment_tensors=3, legacy_mode=False), 1, (0, 1, 2, 3)),
+                               (dict(moment_tensors=[0, 1, 2]), 0, (0, 1, 2))):
+        src = model(**kw)
+        path = str(tmp_path / f"m{flags}_{len(moments)}.npz")
+        src.export_to_lammps_native(path)
+        z = np.load(path)
+        assert int(z["max_moment"]) == moments[-1]
+        assert int(z["is_T_symmetric"]) == int(bool(kw.get('symmetric', False)))
+        back, _ = native.read_lammps_native(path)
+        d = back.descriptor
+        assert d.grap_flags() == flags and d.moments() == moments
+        assert d.dimension() == src.descriptor.dimension()
+        for key in ("Atomic/Be/Conv1d1/kernel", "Atomic/Be/Output/kernel"):
+            assert np.array_equal(back.get_variable(key), src.get_variable(key))
