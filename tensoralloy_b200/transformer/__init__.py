@@ -1,4 +1,5 @@
-from tensoralloy_b200.transformer.universal import UniversalTransformer
+from tensoralloy_b200.transformer.universal import (BatchUniversalTransformer,
+                                                    UniversalTransformer)
 from tensoralloy_b200.transformer.vap import VirtualAtomMap
 
-__all__ = ["UniversalTransformer", "VirtualAtomMap"]
+__all__ = ["UniversalTransformer", "BatchUniversalTransformer", "VirtualAtomMap"]

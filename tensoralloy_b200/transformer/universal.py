@@ -343,3 +343,116 @@ def _bounding_cell(positions, cell, pbc, rc):
         out[k] = v * max(hi - lo, 1.0)
         origin = origin + v * lo
     return out, origin
+
+
+class BatchUniversalTransformer(UniversalTransformer):
+    """Mirror of the reference's mini-batch transformer (transformer/universal.py:921-1388):
+    same constructor, `as_dict`, size properties and `as_descriptor_transformer`.
+
+    The reference needs the maxima (`max_occurs`, `nij_max`, `nnl_max`, ...) to PAD every
+    structure of a batch to `[B, N + 1, 3]` / `[B, nij_max, .]` tensors.  Here a batch is one
+    extended atom array with one sliced neighbour table (`get_batch_features`,
+    csrc/nbr_batch.cuh) and nothing is padded; the maxima are kept as the CONTRACT of the
+    dataset: `get_batch_features` refuses a batch larger than `batch_size`, a structure that
+    exceeds `max_occurs` and one with more than `nij_max` pairs (the reference fails late, in
+    `scatter_nd` or in the VirtualAtomMap).  The TFRecord codec (`encode`, `decode_protobuf`,
+    universal.py:1205-1330) belongs to the input pipeline, which is out of scope
+    (DESIGN.md 7): both raise NotImplementedError."""
+
+    def __init__(self, max_occurs, rcut, acut=None, angular=False, periodic=True,
+                 symmetric=True, nij_max=None, nijk_max=None, nnl_max=None, ij2k_max=None,
+                 batch_size=None, use_forces=True, use_stress=False):
+        max_occurs = Counter({k: int(v) for k, v in dict(max_occurs).items()})
+        super().__init__(elements=sorted(max_occurs.keys()), rcut=rcut, acut=acut,
+                         angular=angular, periodic=periodic, symmetric=symmetric,
+                         use_computed_dists=True)
+        self._nij_max = nij_max
+        self._nijk_max = nijk_max
+        self._nnl_max = nnl_max
+        self._ij2k_max = ij2k_max
+        self._batch_size = batch_size
+        self._use_forces = use_forces
+        self._use_stress = use_stress
+        self._max_occurs = max_occurs
+        self._max_n_atoms = sum(max_occurs.values())
+
+    def as_dict(self) -> Dict:
+        return {'class': self.__class__.__name__, 'max_occurs': dict(self._max_occurs),
+                'rcut': self._rcut, 'acut': self._acut, 'angular': self._angular,
+                'nij_max': self._nij_max, 'nijk_max': self._nijk_max,
+                'nnl_max': self._nnl_max, 'ij2k_max': self._ij2k_max,
+                'batch_size': self._batch_size, 'use_forces': self._use_forces,
+                'use_stress': self._use_stress}
+
+    batch_size = property(lambda self: self._batch_size)
+    nij_max = property(lambda self: self._nij_max)
+    nijk_max = property(lambda self: self._nijk_max)
+    nnl_max = property(lambda self: self._nnl_max)
+    ij2k_max = property(lambda self: self._ij2k_max)
+    max_occurs = property(lambda self: self._max_occurs)
+    max_n_atoms = property(lambda self: self._max_n_atoms)
+    use_forces = property(lambda self: self._use_forces)
+    use_stress = property(lambda self: self._use_stress)
+
+    def as_descriptor_transformer(self) -> UniversalTransformer:
+        """universal.py:1040-1048."""
+        return UniversalTransformer(elements=sorted(self._max_occurs.keys()),
+                                    rcut=self._rcut, acut=self._acut, angular=self._angular,
+                                    periodic=self._periodic, symmetric=self._symmetric)
+
+    def get_g_shape(self, features=None, angular=False):
+        """Shape of the reference's padded descriptor tensor (universal.py:1112-1127)."""
+        if angular:
+            return [self._batch_size, self._max_na_terms, self._max_n_atoms + 1,
+                    self._nnl_max, self._ij2k_max]
+        return [self._batch_size, self._max_nr_terms, self._max_n_atoms + 1,
+                self._nnl_max, 1]
+
+    @staticmethod
+    def get_row_split_axis():
+        return 2
+
+    def get_row_split_sizes(self, _=None):
+        """universal.py:1137-1144: the virtual atom, then `max_occurs` per element."""
+        return [1] + [self._max_occurs[e] for e in self._elements]
+
+    def check_occurs(self, images):
+        """Every structure must fit the declared `max_occurs` (the reference's
+        VirtualAtomMap asserts the same, vap.py:52-60)."""
+        lut = self._z_lut()
+        n_el = len(self._elements)
+        limit = np.array([self._max_occurs[e] for e in self._elements])
+        for k, atoms in enumerate(images):
+            types = lut[np.asarray(atoms.numbers)]
+            if (types < 0).any():
+                continue            # reported by get_batch_features with the symbols
+            counts = np.bincount(types, minlength=n_el)
+            if (counts > limit).any():
+                e = self._elements[int(np.argmax(counts > limit))]
+                raise ValueError(f"structure {k}: {counts[self._elements.index(e)]} atoms of "
+                                 f"{e} exceed max_occurs[{e}] = {self._max_occurs[e]}")
+
+    def get_batch_features(self, images, rc=None, nbr=None) -> BatchDeviceFeatures:
+        if self._batch_size is not None and len(images) > self._batch_size:
+            raise ValueError(f"{len(images)} structures exceed batch_size = "
+                             f"{self._batch_size}")
+        self.check_occurs(images)
+        feats = super().get_batch_features(images, rc=rc, nbr=nbr)
+        if self._nij_max is not None:
+            # pairs per structure from the per-atom row lengths (caller order)
+            counts = feats.nbr.counts().cpu().numpy().astype(np.int64)
+            csum = np.concatenate(([0], np.cumsum(counts)))
+            nij = csum[feats.offsets[1:]] - csum[feats.offsets[:-1]]
+            if nij.size and int(nij.max()) > self._nij_max:
+                raise ValueError(f"structure {int(nij.argmax())}: nij = {int(nij.max())} "
+                                 f"exceeds nij_max = {self._nij_max}")
+        return feats
+
+    def encode(self, atoms):
+        raise NotImplementedError("TFRecord encoding belongs to the reference's input "
+                                  "pipeline (out of scope); pass ase-like Atoms objects to "
+                                  "get_batch_features / the trainers instead")
+
+    def decode_protobuf(self, example_proto):
+        raise NotImplementedError("TFRecord decoding belongs to the reference's input "
+                                  "pipeline (out of scope)")

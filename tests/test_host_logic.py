@@ -206,3 +206,38 @@ def test_grap_new_mode_layout_and_refusals():
         Grap(['Be'], 'sf', par, moment_tensors=3)                 # legacy stops at 2
     with pytest.raises(ValueError, match="moments 0, 1, 2"):
         Grap(['Be'], 'sf', par, moment_tensors=4, legacy_mode=False)
+
+
+def test_batch_universal_transformer_mirror():
+    """transformer/universal.py:921-1048, 1112-1144: constructor, as_dict, sizes,
+    as_descriptor_transformer, row splits; host-side refusals."""
+    from collections import Counter
+    from tensoralloy_b200.atoms import Atoms
+    from tensoralloy_b200.transformer import BatchUniversalTransformer, UniversalTransformer
+    blf = BatchUniversalTransformer(Counter({'W': 8, 'Be': 8}), rcut=5.0, acut=4.0,
+                                    angular=True, nij_max=500, nijk_max=4000, nnl_max=40,
+                                    ij2k_max=10, batch_size=4, use_stress=True)
+    assert blf.elements == ['Be', 'W'] and blf.max_n_atoms == 16
+    d = blf.as_dict()
+    assert d['class'] == 'BatchUniversalTransformer' and d['max_occurs'] == {'W': 8, 'Be': 8}
+    assert (d['nij_max'], d['nijk_max'], d['nnl_max'], d['ij2k_max'], d['batch_size']) == \
+        (500, 4000, 40, 10, 4)
+    assert d['use_forces'] is True and d['use_stress'] is True
+    assert blf.get_row_split_sizes(None) == [1, 8, 8] and blf.get_row_split_axis() == 2
+    assert blf.get_g_shape(None) == [4, blf.max_nr_terms, 17, 40, 1]
+    assert blf.get_g_shape(None, angular=True) == [4, blf.max_na_terms, 17, 40, 10]
+    clf = blf.as_descriptor_transformer()
+    assert type(clf) is UniversalTransformer
+    assert clf.as_dict() == UniversalTransformer(['Be', 'W'], rcut=5.0, acut=4.0,
+                                                 angular=True).as_dict()
+    assert clf.kbody_terms_for_element == blf.kbody_terms_for_element
+    ok = Atoms(['Be'] * 8 + ['W'] * 3, np.random.default_rng(0).random((11, 3)) * 5,
+               np.eye(3) * 5, True)
+    blf.check_occurs([ok, ok])
+    big = Atoms(['Be'] * 9, np.random.default_rng(0).random((9, 3)) * 5, np.eye(3) * 5, True)
+    with pytest.raises(ValueError, match="max_occurs"):
+        blf.check_occurs([ok, big])
+    with pytest.raises(ValueError, match="batch_size"):
+        blf.get_batch_features([ok] * 5)
+    with pytest.raises(NotImplementedError):
+        blf.encode(ok)
