@@ -207,8 +207,13 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"EAM Ni fcc zjw04 rc={RC} E+F+virial, bounded "
-                               f"sample of the 1M-atom case ({n} atoms)"},
+        "config": {"workload": f"EAM Ni fcc {args.cells}^3 cells ({4 * args.cells ** 3} atoms "
+                               f"total), zjw04, rc={RC}, rattle {SIGMA} A seed {SEED}, "
+                               f"E+F+virial",
+                   "sample": f"each step = one neighbour list + E+F+virial of a bounded "
+                             f"sample of that workload: Ni fcc {cells}^3 cells ({n} atoms), "
+                             f"same generator / rattle / potential / cutoff",
+                   "parallelism": f"{cores} host threads (torch CPU float64), rank 0 only"},
         "cpu_baseline": {"value": full, "unit": UNIT, "cores": cores,
                          "kind": "port", "sample": sample},
         "e2e": {"value": full, "unit": UNIT, "h2d_bytes_per_step": 0,
