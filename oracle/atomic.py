@@ -290,7 +290,16 @@ def grap_descriptors_new_mode(elements, types, R, cell, i, j, S, rc, algorithm, 
     else:
         M, T = grap_moment_coeff(u, max_moment), grap_multiplicity_tensor(max_moment, symmetric)
     T = torch.as_tensor(T, dtype=dtype)
-    H = torch.stack([grap_radial(algorithm, prm, rij, rc) * fc for prm in grid], 1)   # [P, K]
+    if algorithm == 'nn':
+        # NNAlgorithm (grap.py:211-234, 619-646): one filter network r -> K values shared by
+        # every (centre, neighbour) element pair, no output bias; grid = dict(weights,
+        # biases, activation, use_resnet_dt) with h_abck_modifier 0 (H input = r)
+        W = [torch.as_tensor(w, dtype=dtype) for w in grid['weights']]
+        b = [None if v is None else torch.as_tensor(v, dtype=dtype) for v in grid['biases']]
+        H = mlp(rij[:, None], W, b, grid.get('activation', 'softplus'),
+                grid.get('use_resnet_dt', True), None, all_outputs=True) * fc[:, None]
+    else:
+        H = torch.stack([grap_radial(algorithm, prm, rij, rc) * fc for prm in grid], 1)  # [P, K]
     key = ti * nel + tidx
     HM = H[:, :, None] * M.T[:, None, :]                                              # [P, K, D]
     P = torch.zeros(n * nel, H.shape[1], M.shape[0], dtype=dtype).index_add(0, key, HM)
@@ -334,7 +343,7 @@ def activation(name):
     raise ValueError(name)
 
 
-def mlp(x, weights, biases, act, use_resnet_dt=False, out_bias=None):
+def mlp(x, weights, biases, act, use_resnet_dt=False, out_bias=None, all_outputs=False):
     """convolutional.py:257-290.  weights[k]: [in, out]; last = output layer."""
     fn = activation(act)
     h = x
@@ -348,7 +357,7 @@ def mlp(x, weights, biases, act, use_resnet_dt=False, out_bias=None):
     out = h @ weights[nh]
     if out_bias is not None:
         out = out + out_bias
-    return out[:, 0]
+    return out if all_outputs else out[:, 0]
 
 
 def atomic_evaluate(elements, symbols, positions, cell, pbc, rc, params, sf=None,

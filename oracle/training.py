@@ -15,10 +15,13 @@ from oracle import neighbor
 
 
 def loss_and_grads(elements, structures, params, rc, sf=None, acut=None, angular=True,
-                   minmax=None, weights=(1.0, 1.0, 1.0), eps=1e-14, grap=None):
+                   minmax=None, weights=(1.0, 1.0, 1.0), eps=1e-14, grap=None,
+                   extra_leaves=None):
     """structures: list of dict(symbols, positions, cell, pbc, energy, forces, stress).
     params[el]: dict(weights=[np], biases=[np or None], activation, use_resnet_dt,
-    out_bias).  Returns (loss, {el: ([dW...], [db...])})."""
+    out_bias).  Returns (loss, parts, {el: ([dW...], [db...])}); with `extra_leaves` (torch
+    leaves the descriptor closes over, e.g. the GRAP filter network handed in through
+    grap['grid']) their gradients are returned under the key '__extra__'."""
     elements = sorted(elements)
     dtype = torch.float64
     P = {}
@@ -89,8 +92,12 @@ def loss_and_grads(elements, structures, params, rc, sf=None, acut=None, angular
             if v is not None:
                 leaves.append(v)
                 index.append((el, 'b', k))
-    grads = torch.autograd.grad(loss, leaves, allow_unused=True)
+    extra = list(extra_leaves or [])
+    grads = torch.autograd.grad(loss, leaves + extra, allow_unused=True)
     out = {el: ({}, {}) for el in elements}
+    if extra:
+        out['__extra__'] = [None if g is None else g.numpy() for g in grads[len(leaves):]]
+        grads = grads[:len(leaves)]
     for (el, kind, k), g in zip(index, grads):
         out[el][0 if kind == 'W' else 1][k] = None if g is None else g.numpy()
     return (float(loss.detach()), {'energy': float(le.detach()),

@@ -90,6 +90,9 @@ class AtomicNN(BasicNN):
         (atomic.py:181-182)."""
         rng = np.random.default_rng(seed)
         dim = self._dim()
+        if getattr(self._descriptor, 'algorithm', None) == 'nn':
+            from tensoralloy_b200.nn.atomic.grap_nn import initialize_filter_variables
+            initialize_filter_variables(self, np.random.default_rng(seed + 1))
         for el in self._elements:
             sizes = [dim] + list(self._hidden_sizes[el])
             for k in range(len(sizes) - 1):
@@ -150,6 +153,9 @@ class AtomicNN(BasicNN):
             self.initialize_variables()
         clf = self._transformer
         sf = self._descriptor
+        if getattr(sf, 'algorithm', None) == 'nn':
+            raise ValueError("GRAP/nn (trainable filter network) is not served by the "
+                             "descriptor kernels: use nn.atomic.grap_nn.GrapFilterTrainer")
         self._model = _lib.AtomicModel(
             len(self._elements), clf.rcut, clf.acut,
             sf.radial_sets(), sf.angular_sets() if clf.angular else None,

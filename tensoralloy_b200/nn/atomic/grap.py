@@ -26,8 +26,10 @@ with the moment list widened to 0..max and two flags of the C ABI
 sign(P) sqrt(P^2 + 1e-16), grap.py:667-676; TAB_GRAP_TRACELESS -- `symmetric=True`,
 grap.py:485-494).  Moment 3 (ten unique third-order sums, multiplicities
 1 3 3 3 6 3 1 3 3 1) exists in new mode only, as in the reference (its legacy loop
-stops at 2, grap.py:434-457).  Not built, and refused loudly: the trainable `nn`
-algorithm (grap.py:211-234) and moments 4, 5 (`get_moment_tensor`, grap.py:537-572).
+stops at 2, grap.py:434-457).  The trainable `nn` algorithm (a filter network r -> R^K,
+grap.py:211-234) is served by nn/atomic/grap_nn.py (torch over the library's pair vectors
+and pair-force op), not by the descriptor kernels.  Not built, and refused loudly: moments
+4, 5 (`get_moment_tensor`, grap.py:537-572).
 """
 import numpy as np
 
@@ -58,7 +60,14 @@ class GenericRadialAtomicPotential:
                  param_space_method='pair', moment_tensors=0,
                  cutoff_function='cosine', symmetric=False, legacy_mode=True,
                  h_abck_modifier=None):
-        if algorithm not in ALGORITHMS:
+        self._algo_nn = None
+        if algorithm == 'nn':
+            # grap.py:296-301: the filter network exists in new mode only
+            if legacy_mode:
+                raise ValueError("The NN algorithm cannot be used for GRAP legacy mode")
+            from tensoralloy_b200.nn.atomic.grap_nn import NNAlgorithm
+            self._algo_nn = NNAlgorithm(parameters)
+        elif algorithm not in ALGORITHMS:
             raise ValueError(f"GRAP: algorithm '{algorithm}' is not implemented")
         if param_space_method not in ('cross', 'pair'):
             raise ValueError("param_space_method must be 'cross' or 'pair'")
@@ -69,6 +78,17 @@ class GenericRadialAtomicPotential:
         if any(m not in allowed for m in moment_tensors):
             raise ValueError("GRAP: moments 0, 1, 2 (legacy mode) / 0 .. 3 (new mode) "
                              "are supported")
+        if self._algo_nn is not None:
+            self._elements = sorted(list(elements))
+            self._algorithm = 'nn'
+            self._parameters = self._algo_nn.as_dict()
+            self._param_space_method = param_space_method
+            self._grid = [{} for _ in range(len(self._algo_nn))]     # one row per filter
+            self._moment_tensors = moment_tensors
+            self._cutoff_function = cutoff_function
+            self._symmetric = symmetric
+            self._legacy_mode = legacy_mode
+            return
         keys = ALGORITHMS[algorithm]
         if parameters is None:
             parameters = {'eta': [0.05, 4.0, 20.0, 80.0], 'omega': [0.0] * 4} \
@@ -90,6 +110,7 @@ class GenericRadialAtomicPotential:
     elements = property(lambda self: self._elements)
     cutoff_function = property(lambda self: self._cutoff_function)
     algorithm = property(lambda self: self._algorithm)
+    algorithm_object = property(lambda self: self._algo_nn)       # NNAlgorithm or None
     moment_tensors = property(lambda self: self._moment_tensors)
     max_moment = property(lambda self: max(self._moment_tensors))
     is_T_symmetric = property(lambda self: self._symmetric)
@@ -110,6 +131,9 @@ class GenericRadialAtomicPotential:
         return self._algorithm
 
     def radial_sets(self):
+        if self._algo_nn is not None:
+            raise ValueError("GRAP/nn has no closed-form parameter sets: the filter network "
+                             "is evaluated by nn.atomic.grap_nn.GrapFilterTrainer")
         keys = ALGORITHMS[self._algorithm]
         return [tuple(row[k] for k in keys) for row in self._grid]
 

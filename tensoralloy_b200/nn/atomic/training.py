@@ -84,11 +84,14 @@ class AtomicNNTrainer:
     the geometry does not change during training) and the torch parameters."""
 
     def __init__(self, nn, device='cuda', loss_weights=None, per_atom_energy=True):
+        self.model = nn._device_model()          # geometry side (weights unused)
+        self._init_common(nn, device, loss_weights, per_atom_energy)
+
+    def _init_common(self, nn, device, loss_weights, per_atom_energy):
         self.nn = nn
         self.device = device
         self.dt = get_float_dtype()
         self.tdtype = torch.float64 if self.dt.name == 'float64' else torch.float32
-        self.model = nn._device_model()          # geometry side (weights unused)
         self.elements = nn.elements
         self.loss_weights = dict(energy=1.0, forces=1.0, stress=1.0)
         self.loss_weights.update(loss_weights or {})

@@ -200,8 +200,13 @@ def test_grap_new_mode_layout_and_refusals():
     sym = Grap(['Be'], 'sf', par, moment_tensors=3, symmetric=True, legacy_mode=False)
     assert sym.grap_flags() == 3 and sym.moments() == (0, 1, 2, 3)
     assert Grap(['Be'], 'sf', par, moment_tensors=2, symmetric=True).grap_flags() == 0
-    with pytest.raises(ValueError, match="not implemented"):
-        Grap(['Be'], 'nn', {}, legacy_mode=False)
+    with pytest.raises(ValueError, match="legacy mode"):          # grap.py:296-299
+        Grap(['Be'], 'nn', {})
+    fnn = Grap(['Be', 'W'], 'nn', dict(num_filters=6, hidden_sizes=[8, 8]),
+               moment_tensors=2, legacy_mode=False)
+    assert fnn.dimension() == 2 * 6 * 3 and fnn.as_dict()["parameters"]["num_filters"] == 6
+    with pytest.raises(ValueError, match="h_abck_modifier"):
+        Grap(['Be'], 'nn', dict(h_abck_modifier=2), legacy_mode=False)
     with pytest.raises(ValueError, match="moments 0, 1, 2"):
         Grap(['Be'], 'sf', par, moment_tensors=3)                 # legacy stops at 2
     with pytest.raises(ValueError, match="moments 0, 1, 2"):
