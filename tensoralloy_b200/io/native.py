@@ -28,8 +28,9 @@ Differences to the reference, all on the safe side:
   * a descriptor whose `moment_tensors` skip a moment (e.g. [0, 2]) cannot be
     expressed (only `max_moment` is stored); the reference writes such a file
     without complaint, here it is a ValueError.
-  * the `nn` (filter network) algorithm of GRAP is not built:
-    `use_fnn = 1` files are rejected on read.
+  * `use_fnn = 1` files (GRAP `nn` algorithm: `fnn::*` keys, atomic.py:408-438) are
+    written and read; such a model is served by nn/atomic/grap_nn.py (GrapFilterTrainer),
+    not by TensorAlloyCalculator.
   * the file does not record `legacy_mode`; a file with `is_T_symmetric = 1` or
     `max_moment = 3` (new-mode-only features, grap.py:434-457, 485-494) reads back as a
     new-mode descriptor, any other file as a legacy one (equal numbers there).
@@ -134,9 +135,32 @@ def lammps_native_dict(nn, dtype=np.float64):
             "precision": np.int32(64 if dtype == np.float64 else 32),
             "use_fnn": np.int32(0)}
     algo = desc.algorithm
-    data["descriptor::method"] = np.int32(METHOD[algo])
-    for key in METHOD_KEYS[algo]:                       # as_dict(convert_to_pairs=True)
-        data[f"descriptor::{key}"] = np.array([row[key] for row in desc.grid], dtype=dtype)
+    if algo == 'nn':
+        # atomic.py:408-438: the filter network; kernels squeezed as the reference does
+        # (the first one, [1, 1, 1, 1, h], becomes 1-D)
+        from tensoralloy_b200.nn.atomic.grap_nn import filter_params
+        a, fp = desc.algorithm_object, filter_params(nn)
+        if a.activation not in ACTFN:
+            raise KeyError(a.activation)
+        data["use_fnn"] = np.int32(1)
+        data["fnn::nlayers"] = np.int32(len(a.hidden_sizes) + 1)
+        data["fnn::layer_sizes"] = np.array(list(a.hidden_sizes) + [a.num_filters],
+                                            dtype=np.int32)
+        data["fnn::num_filters"] = np.int32(a.num_filters)
+        data["fnn::actfn"] = np.int32(ACTFN[a.activation])
+        data["fnn::use_resnet_dt"] = np.int32(a.use_resnet_dt)
+        data["fnn::apply_output_bias"] = np.int32(0)
+        data["fnn::h_abck_modifier"] = np.int32(a.h_abck_modifier)
+        nf = len(fp['weights'])
+        for j in range(nf):
+            data[f"fnn::weights_0_{j}"] = np.squeeze(fp['weights'][j]).astype(dtype)
+            if j < nf - 1:
+                data[f"fnn::biases_0_{j}"] = np.squeeze(fp['biases'][j]).astype(dtype)
+    else:
+        data["descriptor::method"] = np.int32(METHOD[algo])
+        for key in METHOD_KEYS[algo]:                   # as_dict(convert_to_pairs=True)
+            data[f"descriptor::{key}"] = np.array([row[key] for row in desc.grid],
+                                                  dtype=dtype)
     data["nlayers"] = np.int32(len(layer_sizes))
     data["max_moment"] = np.int32(desc.max_moment)
     data["actfn"] = np.int32(ACTFN[nn.activation])
@@ -174,8 +198,7 @@ def read_lammps_native(model_path, export_properties=('energy', 'forces', 'stres
     missing = [k for k in need if k not in z.files and k != "descriptor::method"]
     if missing:
         raise ValueError(f"npz model: missing keys {missing}")
-    if int(z["use_fnn"]) if "use_fnn" in z.files else 0:
-        raise ValueError("npz model: the GRAP `nn` (filter network) algorithm is not built")
+    use_fnn = bool(int(z["use_fnn"])) if "use_fnn" in z.files else False
     if "tdnp" in z.files and int(z["tdnp"]):
         raise ValueError("npz model: temperature-dependent (tdnp) files are not supported")
     nelt = int(z["nelt"])
@@ -185,9 +208,25 @@ def read_lammps_native(model_path, export_properties=('energy', 'forces', 'stres
     for e in elements:
         if e not in atomic_numbers:
             raise ValueError(f"npz model: unknown element '{e}'")
-    algo = {v: k for k, v in METHOD.items()}[int(z["descriptor::method"])]
-    params = {k: np.asarray(z[f"descriptor::{k}"], dtype=np.float64).reshape(-1).tolist()
-              for k in METHOD_KEYS[algo]}
+    if use_fnn:
+        algo = 'nn'
+        fsizes = [int(x) for x in np.asarray(z["fnn::layer_sizes"]).reshape(-1)]
+        if len(fsizes) != int(z["fnn::nlayers"]) or fsizes[-1] != int(z["fnn::num_filters"]):
+            raise ValueError("npz model: inconsistent fnn::layer_sizes / nlayers / num_filters")
+        if int(z["fnn::apply_output_bias"]) if "fnn::apply_output_bias" in z.files else 0:
+            raise ValueError("npz model: a filter network with an output bias is not "
+                             "something the reference writes (atomic.py:418)")
+        params = dict(hidden_sizes=fsizes[:-1], num_filters=fsizes[-1],
+                      activation={v: k for k, v in ACTFN.items()}[int(z["fnn::actfn"])],
+                      use_resnet_dt=bool(int(z["fnn::use_resnet_dt"])),
+                      h_abck_modifier=int(z["fnn::h_abck_modifier"])
+                      if "fnn::h_abck_modifier" in z.files else 0)
+    else:
+        if "descriptor::method" not in z.files:
+            raise ValueError("npz model: missing keys ['descriptor::method']")
+        algo = {v: k for k, v in METHOD.items()}[int(z["descriptor::method"])]
+        params = {k: np.asarray(z[f"descriptor::{k}"], dtype=np.float64).reshape(-1).tolist()
+                  for k in METHOD_KEYS[algo]}
     max_moment = int(z["max_moment"])
     if max_moment > 3:
         raise ValueError("npz model: moments up to 3 are supported")
@@ -200,7 +239,7 @@ def read_lammps_native(model_path, export_properties=('energy', 'forces', 'stres
     desc = GenericRadialAtomicPotential(
         elements, algorithm=algo, parameters=params, param_space_method='pair',
         moment_tensors=list(range(max_moment + 1)), cutoff_function=fct, symmetric=sym,
-        legacy_mode=not (sym or max_moment > 2))
+        legacy_mode=not (sym or max_moment > 2 or use_fnn))
     sizes = [int(x) for x in np.asarray(z["layer_sizes"]).reshape(-1)]
     if len(sizes) != int(z["nlayers"]) or sizes[-1] != 1:
         raise ValueError("npz model: inconsistent layer_sizes / nlayers")
@@ -229,5 +268,18 @@ def read_lammps_native(model_path, export_properties=('energy', 'forces', 'stres
         if out_bias:
             nn.set_variable(f"{nn.scope}/{e}/Output/bias",
                             np.asarray(z[f"biases_{i}_{last}"], dtype=np.float64).reshape(1))
+    if use_fnn:
+        from tensoralloy_b200.nn.atomic.grap_nn import filter_scope
+        fan = 1
+        nf = len(fsizes)
+        for j in range(nf):
+            w = np.asarray(z[f"fnn::weights_0_{j}"], dtype=np.float64).reshape(fan, fsizes[j])
+            name = f"Conv3d{j + 1}" if j < nf - 1 else "Output"
+            nn.set_variable(f"{filter_scope(nn)}/{name}/kernel", w[None, None, None])
+            if j < nf - 1:
+                nn.set_variable(f"{filter_scope(nn)}/{name}/bias",
+                                np.asarray(z[f"fnn::biases_0_{j}"],
+                                           dtype=np.float64).reshape(-1))
+            fan = fsizes[j]
     precision = 'medium' if ("precision" in z.files and int(z["precision"]) == 32) else 'high'
     return nn, precision

@@ -31,7 +31,13 @@ from tensoralloy_b200 import _lib
 from tensoralloy_b200.nn import losses
 from tensoralloy_b200.nn.atomic.training import VOIGT, AtomicNNTrainer, _activation
 
-FILTER_SCOPE = "Filters"
+
+
+def filter_scope(nn):
+    """`{scope}/Filters` -- the reference reads `Atomic/Filters/Conv3d{k}/kernel:0` when it
+    exports the model (atomic.py:421-438)."""
+    return f"{nn.scope}/Filters"
+
 # unique Cartesian index tuples and multiplicities of T_dm (grap.py:470-512)
 _AB = ((0, 0), (0, 1), (0, 2), (1, 1), (1, 2), (2, 2))
 _AB_MULT = (1.0, 2.0, 2.0, 1.0, 2.0, 1.0)
@@ -58,7 +64,7 @@ class NNAlgorithm:
                              "(not implemented); use 0")
         if self.ckpt is not None:
             raise ValueError("GRAP/nn: initialising the filters from an npz checkpoint is "
-                             "not implemented; set the `Filters/*` variables instead")
+                             "not implemented; set the `Atomic/Filters/*` variables instead")
         if self.num_filters < 1 or not self.hidden_sizes:
             raise ValueError("GRAP/nn: num_filters >= 1 and at least one hidden layer")
 
@@ -80,11 +86,11 @@ def initialize_filter_variables(nn, rng):
     for k in range(len(sizes) - 1):
         w = np.clip(rng.normal(size=(sizes[k], sizes[k + 1])), -2.0, 2.0) * \
             np.sqrt(2.0 / sizes[k]) / 0.87962566103423978
-        nn.set_variable(f"{FILTER_SCOPE}/Conv3d{k + 1}/kernel", w[None, None, None])
-        nn.set_variable(f"{FILTER_SCOPE}/Conv3d{k + 1}/bias", np.zeros(sizes[k + 1]))
+        nn.set_variable(f"{filter_scope(nn)}/Conv3d{k + 1}/kernel", w[None, None, None])
+        nn.set_variable(f"{filter_scope(nn)}/Conv3d{k + 1}/bias", np.zeros(sizes[k + 1]))
     w = np.clip(rng.normal(size=(sizes[-1], algo.num_filters)), -2.0, 2.0) * \
         np.sqrt(2.0 / sizes[-1]) / 0.87962566103423978
-    nn.set_variable(f"{FILTER_SCOPE}/Output/kernel", w[None, None, None])
+    nn.set_variable(f"{filter_scope(nn)}/Output/kernel", w[None, None, None])
 
 
 def filter_params(nn):
@@ -92,14 +98,14 @@ def filter_params(nn):
     algo = nn.descriptor.algorithm_object
     W, b = [], []
     k = 1
-    while f"{FILTER_SCOPE}/Conv3d{k}/kernel" in nn.variables:
-        w = nn.get_variable(f"{FILTER_SCOPE}/Conv3d{k}/kernel")
+    while f"{filter_scope(nn)}/Conv3d{k}/kernel" in nn.variables:
+        w = nn.get_variable(f"{filter_scope(nn)}/Conv3d{k}/kernel")
         W.append(w.reshape(w.shape[-2], w.shape[-1]))
-        b.append(nn.get_variable(f"{FILTER_SCOPE}/Conv3d{k}/bias").reshape(-1))
+        b.append(nn.get_variable(f"{filter_scope(nn)}/Conv3d{k}/bias").reshape(-1))
         k += 1
     if not W:
-        raise ValueError("GRAP/nn: the `Filters/*` variables are not initialised")
-    w = nn.get_variable(f"{FILTER_SCOPE}/Output/kernel")
+        raise ValueError("GRAP/nn: the `Atomic/Filters/*` variables are not initialised")
+    w = nn.get_variable(f"{filter_scope(nn)}/Output/kernel")
     W.append(w.reshape(w.shape[-2], w.shape[-1]))
     b.append(None)
     return dict(weights=W, biases=b, activation=algo.activation,
@@ -287,7 +293,7 @@ class GrapFilterTrainer(AtomicNNTrainer):
                     nn.set_variable(f"{name}/bias", L['b'][k].detach().cpu().numpy())
         nh = len(self.filters['W']) - 1
         for k, w in enumerate(self.filters['W']):
-            name = f"{FILTER_SCOPE}/" + (f"Conv3d{k + 1}" if k < nh else "Output")
+            name = f"{filter_scope(nn)}/" + (f"Conv3d{k + 1}" if k < nh else "Output")
             nn.set_variable(f"{name}/kernel", w.detach().cpu().numpy()[None, None, None])
             if self.filters['b'][k] is not None:
                 nn.set_variable(f"{name}/bias", self.filters['b'][k].detach().cpu().numpy())

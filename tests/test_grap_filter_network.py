@@ -46,7 +46,7 @@ def make_model(elements, rc, max_moment, symmetric, cutoff='cosine'):
     nn.initialize_variables(seed=3)
     rng = np.random.default_rng(9)
     for k in (1, 2):      # non-zero filter biases
-        key = f"Filters/Conv3d{k}/bias"
+        key = f"Atomic/Filters/Conv3d{k}/bias"
         nn.set_variable(key, rng.normal(size=nn.get_variable(key).shape) * 0.3)
     for el in elements:
         key = f"Atomic/{el}/Output/kernel"
@@ -135,9 +135,9 @@ def test_filter_variables_round_trip_and_frozen_filters():
     structs = make_structures(1)
     with precision_scope('high'):
         nn = make_model(elements, rc, 1, False)
-        assert nn.get_variable("Filters/Conv3d1/kernel").shape == (1, 1, 1, 1, 8)
-        assert nn.get_variable("Filters/Output/kernel").shape == (1, 1, 1, 8, 5)
-        assert "Filters/Output/bias" not in nn.variables        # output_bias=False
+        assert nn.get_variable("Atomic/Filters/Conv3d1/kernel").shape == (1, 1, 1, 1, 8)
+        assert nn.get_variable("Atomic/Filters/Output/kernel").shape == (1, 1, 1, 8, 5)
+        assert "Atomic/Filters/Output/bias" not in nn.variables        # output_bias=False
         with pytest.raises(ValueError, match="GrapFilterTrainer"):
             nn._device_model()
         tr = cpu_trainer(nn, structs, rc)

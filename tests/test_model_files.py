@@ -167,9 +167,9 @@ def test_npz_error_behaviour(tmp_path):
         nn.export_to_lammps_native(str(tmp_path / 'x.npz'))
     good = _grap_model(elements=('Be',), resnet=False)
     data = native.lammps_native_dict(good)
-    data["use_fnn"] = np.int32(1)
+    data["use_fnn"] = np.int32(1)                      # claims a filter network, has none
     np.savez(str(tmp_path / 'fnn.npz'), **data)
-    with pytest.raises(ValueError, match="filter network"):
+    with pytest.raises(KeyError):
         native.read_lammps_native(str(tmp_path / 'fnn.npz'))
     with pytest.raises(ValueError, match="max_moment"):
         _grap_model(elements=('Be',), moments=(0, 2)).export_to_lammps_native(
@@ -362,3 +362,41 @@ def test_npz_round_trip_keeps_the_new_mode_details(tmp_path):
         assert d.dimension() == src.descriptor.dimension()
         for key in ("Atomic/Be/Conv1d1/kernel", "Atomic/Be/Output/kernel"):
             assert np.array_equal(back.get_variable(key), src.get_variable(key))
+
+
+def test_npz_round_trip_of_a_filter_network_model(tmp_path):
+    """atomic.py:408-438: `use_fnn = 1` and the `fnn::*` keys of the GRAP `nn` algorithm."""
+    from tensoralloy_b200.io import native
+    from tensoralloy_b200.nn.atomic import GenericRadialAtomicPotential as Grap
+    from tensoralloy_b200.nn.atomic.grap_nn import filter_params
+    desc = Grap(['Be', 'W'], 'nn', dict(num_filters=5, hidden_sizes=[8, 8],
+                                        activation='tanh', use_resnet_dt=True),
+                moment_tensors=2, symmetric=True, legacy_mode=False,
+                cutoff_function='polynomial')
+    nn = AtomicNN(['Be', 'W'], desc, hidden_sizes=[8, 8], activation='softplus',
+                  minmax_scale=False, export_properties=('energy', 'forces', 'stress'))
+    nn.attach_transformer(UniversalTransformer(['Be', 'W'], rcut=5.0, angular=False))
+    nn.initialize_variables(seed=2)
+    nn.set_variable("Atomic/Filters/Conv3d2/bias", np.linspace(-0.2, 0.3, 8))
+    path = str(tmp_path / 'fnn.npz')
+    nn.export_to_lammps_native(path)
+    z = np.load(path)
+    assert int(z["use_fnn"]) == 1 and "descriptor::method" not in z.files
+    assert int(z["fnn::nlayers"]) == 3 and z["fnn::layer_sizes"].tolist() == [8, 8, 5]
+    assert int(z["fnn::num_filters"]) == 5 and int(z["fnn::actfn"]) == 2       # tanh
+    assert int(z["fnn::use_resnet_dt"]) == 1 and int(z["fnn::apply_output_bias"]) == 0
+    assert int(z["fnn::h_abck_modifier"]) == 0
+    assert z["fnn::weights_0_0"].shape == (8,) and z["fnn::weights_0_1"].shape == (8, 8)
+    assert z["fnn::weights_0_2"].shape == (8, 5) and "fnn::biases_0_2" not in z.files
+    assert int(z["max_moment"]) == 2 and int(z["is_T_symmetric"]) == 1
+    back, _ = native.read_lammps_native(path)
+    d = back.descriptor
+    assert d.algorithm == 'nn' and d.grap_flags() == 3 and d.moments() == (0, 1, 2)
+    assert d.as_dict()["parameters"] == desc.as_dict()["parameters"]
+    a, b = filter_params(nn), filter_params(back)
+    for x, y in zip(a['weights'], b['weights']):
+        assert np.array_equal(x, y)
+    for x, y in zip(a['biases'][:-1], b['biases'][:-1]):
+        assert np.array_equal(x, y)
+    for key in ("Atomic/W/Conv1d1/kernel", "Atomic/Be/Output/kernel"):
+        assert np.array_equal(back.get_variable(key), nn.get_variable(key))
