@@ -116,6 +116,7 @@ class AtomicNN(BasicNN):
     def set_variable(self, name, value):
         self._variables[name] = np.asarray(value, dtype=np.float64)
         self._model = None
+        self._filter_eval = None
 
     def get_variable(self, name):
         return self._variables[name]
@@ -175,4 +176,20 @@ class AtomicNN(BasicNN):
         return g.cpu().numpy()
 
     def _evaluate(self, features, want_forces, want_virial, want_atomic):
+        if getattr(self._descriptor, 'algorithm', None) == 'nn':
+            return self._evaluate_filter_network(features, want_forces or want_virial)
         return self._evaluate_single(features, want_forces, want_virial, want_atomic)
+
+    def _evaluate_filter_network(self, features, want_forces):
+        """GRAP `nn` algorithm (nn/atomic/grap_nn.py): torch on the device over the
+        library's pair vectors and pair-force op."""
+        from tensoralloy_b200.nn.atomic.grap_nn import FilterEvaluator
+        if getattr(self, '_filter_eval', None) is None:      # reset by set_variable
+            self._filter_eval = FilterEvaluator(self)
+        e_atom, f, w = self._filter_eval(features.nbr, features.types, want_forces=want_forces)
+        raw = {'energy': float(e_atom.sum().item()),
+               'energy/atom': e_atom.double().cpu().numpy()}
+        if want_forces:
+            raw['forces'] = f.double().cpu().numpy()
+            raw['virial'] = w[0].double().cpu().numpy()
+        return raw

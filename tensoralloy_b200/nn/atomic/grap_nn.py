@@ -165,6 +165,67 @@ def filter_descriptors(D, key, n_rows, W, b, act, resnet, cutoff, rc, max_moment
     return torch.stack(cols, dim=2)
 
 
+class FilterEvaluator:
+    """E, per-atom E, forces and virial of ONE structure (or one batch handle) for a model
+    with the `nn` algorithm: the inference side of `AtomicNN._evaluate`
+    (`TensorAlloyCalculator.calculate`).  Same ops as the trainer, parameters as constants:
+    pair vectors from the library, filters + moment sums + atomic networks in torch on the
+    device, forces / virial through `tab_pair_forces`."""
+
+    def __init__(self, nn, device='cuda', pair_force=None):
+        from tensoralloy_b200.precision import get_float_dtype
+        self.nn, self.device = nn, device
+        self.dt = get_float_dtype()
+        self.tdtype = torch.float64 if self.dt.name == 'float64' else torch.float32
+        t = lambda a: torch.tensor(np.asarray(a), dtype=self.tdtype, device=device)
+        fp = filter_params(nn)
+        self.filters = dict(W=[t(w) for w in fp['weights']],
+                            b=[None if v is None else t(v) for v in fp['biases']],
+                            act=_activation(fp['activation']), resnet=fp['use_resnet_dt'])
+        self.layers = {}
+        for el in nn.elements:
+            p = nn.mlp_params(el)
+            self.layers[el] = dict(
+                W=[t(w) for w in p['weights']],
+                b=[None if v is None else t(v) for v in p['biases']],
+                act=_activation(p['activation']), resnet=p['use_resnet_dt'],
+                xlo=None if p['xlo'] is None else t(p['xlo']),
+                xhi=None if p['xhi'] is None else t(p['xhi']))
+        if pair_force is None:
+            from tensoralloy_b200.nn.eam.training import PairForce
+            pair_force = PairForce.apply
+        self._pair_force = pair_force
+
+    _mlp = AtomicNNTrainer._mlp
+
+    def __call__(self, nbr, types, pairs=None, want_forces=True):
+        """types: element index per atom (caller order).  Returns (e_atom [N], F [N,3] or
+        None, W [B,3,3] or None) as tensors of the working precision."""
+        nn, desc = self.nn, self.nn.descriptor
+        i, j, D = pairs if pairs is not None else nbr.pairs()
+        i, j = i.long(), j.long()
+        types = torch.as_tensor(np.asarray(types), device=self.device).long()
+        n, nel = types.shape[0], len(nn.elements)
+        ti, tj = types[i], types[j]
+        term = torch.where(ti == tj, torch.zeros_like(ti), tj - (tj > ti).long() + 1)
+        D = D.to(self.tdtype).detach().requires_grad_(want_forces)
+        F = self.filters
+        G = filter_descriptors(D, i * nel + term, n * nel, F['W'], F['b'], F['act'],
+                               F['resnet'], desc.cutoff_function, nn.transformer.rcut,
+                               desc.max_moment, desc.is_T_symmetric, self.dt.eps)
+        G = G.reshape(n, -1)
+        e_atom = torch.zeros(n, dtype=self.tdtype, device=self.device)
+        for a, el in enumerate(nn.elements):
+            sel = torch.nonzero(types == a).reshape(-1)
+            if sel.numel():
+                e_atom = e_atom.index_add(0, sel, self._mlp(el, G[sel]))
+        if not want_forces:
+            return e_atom.detach(), None, None
+        g = torch.autograd.grad(e_atom.sum(), D)[0]
+        forces, W = self._pair_force(g, nbr)
+        return e_atom.detach(), forces, W
+
+
 class GrapFilterTrainer(AtomicNNTrainer):
     """Training step (and, through `evaluate`, E / F / stress) of an AtomicNN over a GRAP
     descriptor with the `nn` algorithm.  Leaves: the per-element atomic networks (as in

@@ -164,3 +164,37 @@ def test_filter_variables_round_trip_and_frozen_filters():
         assert len(trf.params) == sum(len(trf.layers[e]['W']) +
                                       sum(v is not None for v in trf.layers[e]['b'])
                                       for e in elements)
+
+
+def test_filter_evaluator_matches_oracle_energy_forces_stress():
+    """The inference side (`AtomicNN._evaluate` of a model with the `nn` algorithm):
+    per-atom energies, forces and virial against the oracle's autograd, CPU stand-in for the
+    pair-force op."""
+    from oracle import atomic as oat
+    from tensoralloy_b200.nn.atomic.grap_nn import FilterEvaluator
+    elements, rc = ['Mo', 'Ni'], 4.5
+    st = make_structures(1, seed=8)[0]
+    with precision_scope('high'):
+        nn = make_model(elements, rc, 3, True, 'polynomial')
+        i, j, S = onl.neighbor_list(st['positions'], st['cell'], st['pbc'], rc)[:3]
+        D = torch.as_tensor(st['positions'][j] - st['positions'][i] + S @ st['cell'])
+        ti, tj = torch.as_tensor(i).long(), torch.as_tensor(j).long()
+        n = len(st['positions'])
+        ev = FilterEvaluator(nn, device='cpu',
+                             pair_force=torch_pair_force(ti, tj, torch.zeros(len(i)).long(),
+                                                         n, 1, D))
+        types = np.array([elements.index(x) for x in st['symbols']])
+        e_atom, F, W = ev(None, types, pairs=(ti, tj, D))
+        fp = filter_params(nn)
+        grap = dict(algorithm='nn', grid=fp, moments=[0, 1, 2, 3], cutoff='polynomial',
+                    new_mode=True, symmetric=True)
+        params = {el: nn.mlp_params(el) for el in elements}
+        ref = oat.atomic_evaluate(elements, st['symbols'], st['positions'], st['cell'],
+                                  st['pbc'], rc, params, angular=False, grap=grap)
+    vol = abs(np.linalg.det(st['cell']))
+    assert abs(e_atom.sum().item() - ref['energy']) / n < 1e-12
+    assert np.abs(F.numpy() - ref['forces']).max() < 1e-10
+    st6 = np.array([W[0, a, b].item() for a, b in ((0, 0), (1, 1), (2, 2), (1, 2), (0, 2),
+                                                    (0, 1))]) / vol
+    assert np.abs(st6 - ref['stress']).max() < 1e-10
+    assert np.abs(ref['forces']).max() > 1e-3

@@ -56,3 +56,27 @@ def test_filter_network_training_step_on_the_gpu():
         E, F, S = tr.evaluate()
         assert E.shape == (2,) and F.shape[1] == 3 and S.shape == (2, 6)
         assert torch.isfinite(F).all()
+
+
+def test_calculator_serves_a_filter_network_model():
+    """TensorAlloyCalculator over an AtomicNN with the GRAP `nn` algorithm: energy, forces and
+    stress against the oracle (1e-10 eV/atom, 1e-8 eV/A)."""
+    from oracle import atomic as oat
+    from tensoralloy_b200.calculator import TensorAlloyCalculator
+    elements, rc = ['Mo', 'Ni'], 4.5
+    st = cpu.make_structures(1, seed=8)[0]
+    atoms = st['atoms']
+    with precision_scope('high'):
+        nn = cpu.make_model(elements, rc, 3, True, 'polynomial')
+        calc = TensorAlloyCalculator(nn)
+        calc.calculate(atoms, properties=['energy', 'forces', 'stress'])
+        e, f, s = calc.results['energy'], calc.get_forces(atoms), calc.get_stress(atoms)
+        fp = filter_params(nn)
+        grap = dict(algorithm='nn', grid=fp, moments=[0, 1, 2, 3], cutoff='polynomial',
+                    new_mode=True, symmetric=True)
+        params = {el: nn.mlp_params(el) for el in elements}
+        ref = oat.atomic_evaluate(elements, st['symbols'], st['positions'], st['cell'],
+                                  st['pbc'], rc, params, angular=False, grap=grap)
+    assert abs(e - ref['energy']) / len(atoms) < 1e-10
+    assert np.abs(f - ref['forces']).max() < 1e-8
+    assert np.abs(s - ref['stress']).max() < 1e-8
