@@ -246,3 +246,28 @@ def test_batch_universal_transformer_mirror():
         blf.get_batch_features([ok] * 5)
     with pytest.raises(NotImplementedError):
         blf.encode(ok)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference`: ONE JSON line with the keys the driver reads; the oracle
+    port on a small bounded sample (the default sample is 16^3 cells)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference',
+                          '--steps', '1', '--warmup', '3', '--ref-cells', '6'],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [ln for ln in res.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "atom-evals/s" and d["value"] > 0
+    assert d["metric"].startswith("atom-evals/sec (E+F+virial)") and d["higher_is_better"]
+    assert d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] >= 3
+    assert d["dtype"] == "f64" and d["data"] == "synthetic" and d["vs_baseline"] is None
+    assert "1000188 atoms" in d["config"]["workload"] and "sample" in d["config"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": 0}
