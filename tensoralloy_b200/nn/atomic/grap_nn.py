@@ -59,12 +59,24 @@ class NNAlgorithm:
         self.ckpt = p.get("ckpt", None)
         self.trainable = bool(p.get("trainable", True))
         self.h_abck_modifier = int(p.get("h_abck_modifier", 0))
+        if isinstance(self.ckpt, str):
+            # grap.py:248-262: an npz checkpoint (a `use_fnn` model file) overrides the
+            # architecture keys
+            npz = np.load(self.ckpt)
+            actfn = {0: "relu", 1: "softplus", 2: "tanh", 3: "squareplus"}
+            self.activation = actfn.get(int(npz["fnn::actfn"]))
+            self.hidden_sizes = [int(x) for x in npz["fnn::layer_sizes"].tolist()]
+            self.num_filters = self.hidden_sizes.pop(-1)
+            self.use_resnet_dt = int(npz["fnn::use_resnet_dt"]) == 1
+            if "fnn::trainable" in npz.files:
+                self.trainable = int(npz["fnn::trainable"]) == 1
+            if "fnn::h_abck_modifier" in npz.files:
+                self.h_abck_modifier = int(npz["fnn::h_abck_modifier"])
+        elif self.ckpt is not None:
+            raise ValueError("GRAP/nn: `ckpt` must be the path of an npz file or None")
         if self.h_abck_modifier != 0:
             raise ValueError("GRAP/nn: h_abck_modifier 1 / 2 need covalent radii "
                              "(not implemented); use 0")
-        if self.ckpt is not None:
-            raise ValueError("GRAP/nn: initialising the filters from an npz checkpoint is "
-                             "not implemented; set the `Atomic/Filters/*` variables instead")
         if self.num_filters < 1 or not self.hidden_sizes:
             raise ValueError("GRAP/nn: num_filters >= 1 and at least one hidden layer")
 
@@ -83,6 +95,23 @@ def initialize_filter_variables(nn, rng):
     `Filters/Output` layer (rank-5 input -> Conv3d names, convolutional.py:219,266-288)."""
     algo = nn.descriptor.algorithm_object
     sizes = [1] + list(algo.hidden_sizes)
+    if isinstance(algo.ckpt, str):
+        # convolutional.py:219-254: constant initialisers from `fnn::weights_0_{j}` /
+        # `fnn::biases_0_{j}` (NNAlgorithm took the architecture from the same file)
+        npz = np.load(algo.ckpt)
+        if not int(npz["use_fnn"]) if "use_fnn" in npz.files else True:
+            raise ValueError(f"GRAP/nn: {algo.ckpt} holds no filter network (use_fnn = 0)")
+        full = sizes + [algo.num_filters]
+        for k in range(len(full) - 1):
+            name = f"Conv3d{k + 1}" if k < len(full) - 2 else "Output"
+            w = np.asarray(npz[f"fnn::weights_0_{k}"], dtype=np.float64).reshape(
+                full[k], full[k + 1])
+            nn.set_variable(f"{filter_scope(nn)}/{name}/kernel", w[None, None, None])
+            if k < len(full) - 2:
+                nn.set_variable(f"{filter_scope(nn)}/{name}/bias",
+                                np.asarray(npz[f"fnn::biases_0_{k}"],
+                                           dtype=np.float64).reshape(-1))
+        return
     for k in range(len(sizes) - 1):
         w = np.clip(rng.normal(size=(sizes[k], sizes[k + 1])), -2.0, 2.0) * \
             np.sqrt(2.0 / sizes[k]) / 0.87962566103423978

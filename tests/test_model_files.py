@@ -400,3 +400,36 @@ def test_npz_round_trip_of_a_filter_network_model(tmp_path):
         assert np.array_equal(x, y)
     for key in ("Atomic/W/Conv1d1/kernel", "Atomic/Be/Output/kernel"):
         assert np.array_equal(back.get_variable(key), nn.get_variable(key))
+
+
+def test_filter_network_initialised_from_an_npz_checkpoint(tmp_path):
+    """grap.py:248-262, convolutional.py:219-254: `ckpt` = a `use_fnn` npz file gives the
+    architecture and the initial filter weights."""
+    from tensoralloy_b200.nn.atomic import GenericRadialAtomicPotential as Grap
+    from tensoralloy_b200.nn.atomic.grap_nn import filter_params
+
+    def model(parameters, seed):
+        desc = Grap(['Be'], 'nn', parameters, moment_tensors=1, legacy_mode=False)
+        nn = AtomicNN(['Be'], desc, hidden_sizes=[8], minmax_scale=False)
+        nn.attach_transformer(UniversalTransformer(['Be'], rcut=5.0, angular=False))
+        nn.initialize_variables(seed=seed)
+        return nn
+
+    src = model(dict(num_filters=3, hidden_sizes=[6, 6], activation='tanh',
+                     use_resnet_dt=False), seed=4)
+    src.set_variable("Atomic/Filters/Conv3d1/bias", np.linspace(0.1, 0.6, 6))
+    path = str(tmp_path / 'filters.npz')
+    src.export_to_lammps_native(path)
+    new = model(dict(ckpt=path, num_filters=99, hidden_sizes=[1]), seed=77)
+    a = new.descriptor.algorithm_object
+    assert (a.hidden_sizes, a.num_filters, a.activation, a.use_resnet_dt) == \
+        ([6, 6], 3, 'tanh', False)
+    assert new.descriptor.dimension() == 1 * 3 * 2
+    p, q = filter_params(src), filter_params(new)
+    for x, y in zip(p['weights'], q['weights']):
+        assert np.array_equal(x, y)
+    assert np.array_equal(p['biases'][0], q['biases'][0])
+    plain = str(tmp_path / 'plain.npz')
+    _grap_model(elements=('Be',)).export_to_lammps_native(plain)
+    with pytest.raises(KeyError):                       # no fnn:: keys in a closed-form file
+        model(dict(ckpt=plain), seed=1)
