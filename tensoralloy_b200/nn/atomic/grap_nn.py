@@ -23,6 +23,7 @@ which the reference obtains from TF second-order autograd (nn/opt.py:132-157).
 covalent radii, which are not vendored: refused.
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -59,9 +60,10 @@ class NNAlgorithm:
         self.ckpt = p.get("ckpt", None)
         self.trainable = bool(p.get("trainable", True))
         self.h_abck_modifier = int(p.get("h_abck_modifier", 0))
-        if isinstance(self.ckpt, str):
+        if isinstance(self.ckpt, str) and os.path.exists(self.ckpt):
             # grap.py:248-262: an npz checkpoint (a `use_fnn` model file) overrides the
-            # architecture keys
+            # architecture keys.  A path that no longer exists (a model file read back on
+            # another machine: `as_dict` keeps the key) leaves the stored keys in force.
             npz = np.load(self.ckpt)
             actfn = {0: "relu", 1: "softplus", 2: "tanh", 3: "squareplus"}
             self.activation = actfn.get(int(npz["fnn::actfn"]))
@@ -72,7 +74,7 @@ class NNAlgorithm:
                 self.trainable = int(npz["fnn::trainable"]) == 1
             if "fnn::h_abck_modifier" in npz.files:
                 self.h_abck_modifier = int(npz["fnn::h_abck_modifier"])
-        elif self.ckpt is not None:
+        elif self.ckpt is not None and not isinstance(self.ckpt, str):
             raise ValueError("GRAP/nn: `ckpt` must be the path of an npz file or None")
         if self.h_abck_modifier != 0:
             raise ValueError("GRAP/nn: h_abck_modifier 1 / 2 need covalent radii "
@@ -96,6 +98,8 @@ def initialize_filter_variables(nn, rng):
     algo = nn.descriptor.algorithm_object
     sizes = [1] + list(algo.hidden_sizes)
     if isinstance(algo.ckpt, str):
+        if not os.path.exists(algo.ckpt):
+            raise FileNotFoundError(f"GRAP/nn: filter checkpoint {algo.ckpt} not found")
         # convolutional.py:219-254: constant initialisers from `fnn::weights_0_{j}` /
         # `fnn::biases_0_{j}` (NNAlgorithm took the architecture from the same file)
         npz = np.load(algo.ckpt)
