@@ -180,6 +180,13 @@ class AtomicNN(BasicNN):
             return self._evaluate_filter_network(features, want_forces or want_virial)
         return self._evaluate_single(features, want_forces, want_virial, want_atomic)
 
+    def evaluate_batch(self, batch, want_forces=True, want_virial=True, want_atomic=True):
+        if getattr(self._descriptor, 'algorithm', None) == 'nn':
+            raise NotImplementedError(
+                "batched inference of a GRAP/nn model: queue the structures in "
+                "nn.atomic.grap_nn.GrapFilterTrainer and call .evaluate()")
+        return super().evaluate_batch(batch, want_forces, want_virial, want_atomic)
+
     def _evaluate_filter_network(self, features, want_forces):
         """GRAP `nn` algorithm (nn/atomic/grap_nn.py): torch on the device over the
         library's pair vectors and pair-force op."""

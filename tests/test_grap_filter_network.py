@@ -140,6 +140,8 @@ def test_filter_variables_round_trip_and_frozen_filters():
         assert "Atomic/Filters/Output/bias" not in nn.variables        # output_bias=False
         with pytest.raises(ValueError, match="GrapFilterTrainer"):
             nn._device_model()
+        with pytest.raises(NotImplementedError, match="GrapFilterTrainer"):
+            nn.evaluate_batch(None)
         tr = cpu_trainer(nn, structs, rc)
         E0, F0, S0 = tr.evaluate()
         assert F0.shape == (len(structs[0]['positions']), 3) and S0.shape == (1, 6)
