@@ -271,3 +271,30 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": 0}
+
+
+def test_grap_parameter_grid_and_serialization():
+    """nn/atomic/tests/test_grap.py:25-46 (`test_gen_algorithm`, `test_serialization`) and
+    grap.py:45-72: 'pair' zips the lists, 'cross' is sklearn's ParameterGrid (keys sorted, last
+    key fastest); `as_dict` round-trips through the constructor."""
+    from tensoralloy_b200.nn.atomic import GenericRadialAtomicPotential as Grap
+    rl, pl = [1.0, 2.0, 3.0, 4.0, 5.0], [2.0, 3.0, 4.0, 5.0, 6.0]
+    pair = Grap(['Be'], 'pexp', dict(rl=rl, pl=pl), param_space_method='pair')
+    assert len(pair.grid) == 5
+    for i, row in enumerate(pair.grid):
+        assert row['rl'] == rl[i] and row['pl'] == pl[i]
+    assert pair.radial_sets() == list(zip(rl, pl))
+    with pytest.raises(ValueError, match="same length"):
+        Grap(['Be'], 'pexp', dict(rl=rl, pl=pl[:3]), param_space_method='pair')
+    cross = Grap(['Be'], 'sf', dict(eta=[1.0, 2.0], omega=[0.0, 0.5, 1.0]),
+                 param_space_method='cross')
+    assert [(r['eta'], r['omega']) for r in cross.grid] == \
+        [(1.0, 0.0), (1.0, 0.5), (1.0, 1.0), (2.0, 0.0), (2.0, 0.5), (2.0, 1.0)]
+    d = cross.as_dict()
+    assert d["@class"] == "GenericRadialAtomicPotential" and d["algorithm"] == "sf"
+    again = Grap(**{k: v for k, v in d.items() if not k.startswith('@')})
+    assert again.as_dict() == d and again.grid == cross.grid
+    with pytest.raises(ValueError, match="required"):
+        Grap(['Be'], 'morse', dict(D=[1.0], gamma=[1.0]))            # r0 missing
+    with pytest.raises(ValueError, match="param_space_method"):
+        Grap(['Be'], 'sf', dict(eta=[1.0], omega=[0.0]), param_space_method='zip')
