@@ -1,0 +1,73 @@
+"""The reference's own known-answer tests for the loss arithmetic and the cutoff functions
+(tensoralloy/nn/tests/test_losses.py:23-230, test_cutoff.py:23-95), re-run on the torch
+restatements used by the training step (nn/losses.py), on the oracle's cutoffs and on the
+torch cutoff of the filter-network path.  The "simple" formulas are the ones the reference
+tests state."""
+import numpy as np
+import torch
+
+from oracle import atomic as oat
+from tensoralloy_b200.nn import losses
+from tensoralloy_b200.nn.atomic.grap_nn import _cutoff
+from tensoralloy_b200.precision import precision_scope
+
+
+def test_energy_loss_per_atom_rmse():
+    # test_losses.py:23-51 ('medium' precision, delta 1e-8 on the float32 value there;
+    # the eps under the square root is the dtype eps, losses.py:69-95)
+    rng = np.random.default_rng(0)
+    x, y = rng.uniform(0.0, 3.0, 6), rng.uniform(0.0, 3.0, 6)
+    n = rng.integers(1, 5, 6).astype(float)
+    y_rmse = np.sqrt(np.mean((x / n - y / n) ** 2))
+    with precision_scope('high'):
+        got = losses.energy_loss(torch.tensor(x), torch.tensor(y), torch.tensor(n)).item()
+        assert abs(got - np.sqrt(y_rmse ** 2 + 1e-14)) < 1e-14
+        assert abs(got - y_rmse) < 1e-8
+        total = losses.energy_loss(torch.tensor(x), torch.tensor(y), torch.tensor(n),
+                                   per_atom_loss=False, weight=2.0).item()
+        assert abs(total - 2.0 * np.sqrt(np.mean((x - y) ** 2))) < 1e-8
+    with precision_scope('medium'):
+        got32 = losses.energy_loss(torch.tensor(x, dtype=torch.float32),
+                                   torch.tensor(y, dtype=torch.float32),
+                                   torch.tensor(n, dtype=torch.float32)).item()
+        assert abs(got32 - y_rmse) < 1e-6
+
+
+def test_forces_loss_over_real_atoms_with_weight():
+    # test_losses.py:90-130: RMSE over the real atoms of every structure, weight 10
+    rng = np.random.default_rng(1)
+    n_atoms = [5, 6, 4, 8, 5, 3]
+    x = [rng.uniform(0.0, 3.0, (n, 3)) for n in n_atoms]
+    y = [rng.uniform(0.0, 3.0, (n, 3)) for n in n_atoms]
+    sq = np.concatenate([(a - b) ** 2 for a, b in zip(x, y)])
+    y_rmse = np.sqrt(np.mean(sq))
+    with precision_scope('high'):
+        got = losses.forces_loss(torch.tensor(np.concatenate(x)),
+                                 torch.tensor(np.concatenate(y)), weight=10.0).item()
+    assert abs(got - 10.0 * y_rmse) < 1e-8
+
+
+def test_stress_loss_voigt_rmse():
+    # test_losses.py:187-204
+    rng = np.random.default_rng(2)
+    x, y = rng.uniform(0.1, 3.0, (8, 6)), rng.uniform(0.1, 3.0, (8, 6))
+    with precision_scope('high'):
+        got = losses.stress_loss(torch.tensor(x), torch.tensor(y)).item()
+    assert abs(got - np.sqrt(np.mean((x - y) ** 2))) < 1e-8
+
+
+def test_cutoff_functions_match_the_simple_forms():
+    # test_cutoff.py:23-95: r = 1 .. 10 in 91 steps, rc = 6, gamma = 5
+    rc, gamma = 6.0, 5.0
+    r = np.linspace(1.0, 10.0, num=91, endpoint=True)
+    cos_simple = np.where(r <= rc, 0.5 * (np.cos(np.pi * r / rc) + 1.0), 0.0)
+    d = r / rc
+    poly_simple = np.where(r <= rc, 1.0 + gamma * d ** (gamma + 1.0) - (gamma + 1.0) * d ** gamma,
+                           0.0)
+    t = torch.tensor(r)
+    assert np.abs(oat.cosine_cutoff(t, rc).numpy() - cos_simple).max() < 1e-14
+    assert np.abs(oat.polynomial_cutoff(t, rc).numpy() - poly_simple).max() < 1e-14
+    assert np.abs(_cutoff('cosine', t, rc).numpy() - cos_simple).max() < 1e-14
+    assert np.abs(_cutoff('polynomial', t, rc).numpy() - poly_simple).max() < 1e-14
+    t32 = torch.tensor(r, dtype=torch.float32)
+    assert np.abs(_cutoff('cosine', t32, rc).numpy() - cos_simple).max() < 1e-7   # the reference's delta
