@@ -1,0 +1,99 @@
+"""`io.read.read_file` / `io.units.get_conversion_units` against the reference's reader
+tests (tensoralloy/io/tests/test_read.py:19-96, test_units.py:19-48) on the same files
+(fixtures copied by tests/golden/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from tensoralloy_b200.io.read import Dataset, read_file
+from tensoralloy_b200.io.units import get_conversion_units
+
+GOLD = os.path.join(os.path.dirname(__file__), 'golden')
+# ase.units (CODATA 2014)
+KCAL, MOL, HARTREE, GPA = 2.611447418269555e+22, 6.022140857e+23, 27.211386024367243, \
+    1.0 / 160.21766208
+
+
+def test_read_xyz():
+    # test_read.py:19-29
+    db = read_file(os.path.join(GOLD, 'B28_2frames.xyz'), num_examples=2)
+    atoms = db[1]
+    assert len(db) == 2
+    assert abs(atoms.positions[1, 1] - 10.65007390) < 1e-7
+    assert abs(atoms.info['energy'] - (-78.51063520)) < 1e-7
+    assert atoms.cell.sum() > 1e-8 and np.allclose(atoms.cell, np.eye(3) * 20.0)
+    assert np.array_equal(atoms.info['forces'], np.zeros((28, 3)))     # local minima
+    assert db.metadata['extxyz'] is False and db.metadata['max_occurs'] == {'B': 28}
+    assert len(read_file(os.path.join(GOLD, 'B28_2frames.xyz'), num_examples=1)) == 1
+
+
+def test_read_extxyz():
+    # test_read.py:32-52
+    db = read_file(os.path.join(GOLD, 'examples.extxyz'))
+    atoms = db[1]
+    assert len(db) == 2 and len(atoms) == 21
+    assert abs(atoms.info['forces'][0, 2] - 2.49790655) < 1e-6
+    assert abs(atoms.info['energy'] - (-17637.613286)) < 1e-6
+    assert db.metadata['max_occurs'] == {'C': 10, 'H': 8, 'O': 4}
+    assert db.metadata['periodic'] is False and db.metadata['stress'] is False
+    assert db.max_occurs['C'] == 10 and not db.has_stress
+    # fmax filter (read.py:119-121)
+    fmax = max(np.abs(a.info['forces']).max() for a in db)
+    assert len(read_file(os.path.join(GOLD, 'examples.extxyz'), fmax=fmax * 0.999)) == 1
+
+
+def test_read_snap_stress_in_kbar():
+    # test_read.py:55-72
+    db = read_file(os.path.join(GOLD, 'snap_Ni_id11.extxyz'), units={"stress": "kbar"})
+    atoms = db[0]
+    assert abs(atoms.info['stress'][0] - (-0.01388831152640921)) < 1e-8
+    assert atoms.info['stress'].shape == (6,) and db.has_stress
+    assert atoms.info['source'] == "Ni.AIMD.0"
+    assert np.allclose(atoms.info['weights'], [1.0, 1.0, 0.0])
+    assert atoms.pbc.all() and db.has_periodic_structures
+    assert abs(atoms.cell[1, 0] - (-1.239893)) < 1e-9          # rows = lattice vectors
+
+
+def test_read_electron_temperature_and_entropy():
+    # test_read.py:85-96; the 3x3 stress of this file becomes the Voigt vector
+    db = read_file(os.path.join(GOLD, 'Be_liquid_4000K_1frame.extxyz'), num_examples=3)
+    atoms = db[0]
+    assert abs(atoms.info['etemperature'] - 0.34469373) < 1e-6
+    assert abs(atoms.info['eentropy'] - 14.939843166274024) < 1e-6
+    assert abs(atoms.info['stress'][0] - (-0.38507292526334685)) < 1e-12
+    assert abs(atoms.info['stress'][3] - 1.0410837221973275e-08) < 1e-16    # yz
+    assert len(atoms) == 128 and 'free_energy' in atoms.info
+
+
+def test_unit_conversion():
+    # test_units.py:19-48
+    to_eV, _, to_s = get_conversion_units({'energy': 'kcal/mol*Hartree/eV',
+                                           'stress': '0.1*GPa'})
+    assert abs(to_eV - KCAL / MOL * HARTREE) < 1e-12 and abs(to_s - 0.1 * GPA) < 1e-15
+    assert abs(get_conversion_units({'stress': 'kbar'})[2] - 0.1 * GPA) < 1e-15
+    assert abs(get_conversion_units({'stress': 'eV/Angstrom**3'})[2] - 1.0) < 1e-15
+    assert get_conversion_units(None) == (1.0, 1.0, 1.0)
+    db = read_file(os.path.join(GOLD, 'examples.extxyz'), units={'energy': 'kcal/mol'})
+    assert abs(db[1].info['energy'] - (-17637.613286 * KCAL / MOL)) < 1e-6
+    with pytest.raises(ValueError, match="unknown unit"):
+        get_conversion_units({'energy': '__import__("os")'})
+
+
+def test_dataset_feeds_a_trainer_and_errors():
+    db = read_file(os.path.join(GOLD, 'Be_liquid_4000K_1frame.extxyz'))
+
+    class Sink:
+        def __init__(self):
+            self.rows = []
+
+        def add_structure(self, atoms, energy, forces, stress):
+            self.rows.append((atoms, energy, forces, stress))
+
+    sink = db.fill(Sink())
+    assert len(sink.rows) == 1 and sink.rows[0][2].shape == (128, 3)
+    assert sink.rows[0][3].shape == (6,) and isinstance(db, Dataset)
+    with pytest.raises(ValueError, match="Unknown file type"):
+        read_file('x.cif')
+    with pytest.raises(NotImplementedError):
+        read_file('x.db')
