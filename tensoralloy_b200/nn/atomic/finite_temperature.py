@@ -27,6 +27,7 @@ from typing import List
 
 import numpy as np
 
+from tensoralloy_b200.atoms_utils import get_electron_temperature
 from tensoralloy_b200.nn.atomic.atomic import AtomicNN
 from tensoralloy_b200.precision import get_float_dtype
 
@@ -252,7 +253,7 @@ class TemperatureDependentAtomicNN(AtomicNN):
     def _evaluate(self, features, want_forces, want_virial, want_atomic):
         import torch
         n = features.n_atoms
-        etemp = float(features.atoms.info.get('etemperature', 0.0))
+        etemp = float(get_electron_temperature(features.atoms))
         types = torch.as_tensor(np.asarray(features.types), device='cuda').long()
         t_atom = torch.full((n,), etemp, dtype=torch.float64, device='cuda')
         per_atom, sums, forces, virial = self._run(features.nbr, types, t_atom, None, 1,
@@ -274,7 +275,7 @@ class TemperatureDependentAtomicNN(AtomicNN):
         nb = batch.n_struct
         lens = np.diff(batch.offsets)
         sid = torch.as_tensor(np.repeat(np.arange(nb), lens), device='cuda').long()
-        temps = np.array([float(a.info.get('etemperature', 0.0)) for a in batch.images])
+        temps = np.array([float(get_electron_temperature(a)) for a in batch.images])
         t_atom = torch.as_tensor(np.repeat(temps, lens), device='cuda')
         types = torch.as_tensor(np.asarray(batch.types), device='cuda').long()
         per_atom, sums, forces, virial = self._run(batch.nbr, types, t_atom, sid, nb,

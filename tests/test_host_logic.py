@@ -298,3 +298,20 @@ def test_grap_parameter_grid_and_serialization():
         Grap(['Be'], 'morse', dict(D=[1.0], gamma=[1.0]))            # r0 missing
     with pytest.raises(ValueError, match="param_space_method"):
         Grap(['Be'], 'sf', dict(eta=[1.0], omega=[0.0]), param_space_method='zip')
+
+
+def test_atoms_utils_lookup_order():
+    """atoms_utils.py:14-69: info, then info['data'], then info['key_value_pairs']."""
+    from tensoralloy_b200 import atoms_utils as au
+    from tensoralloy_b200.atoms import Atoms
+    atoms = Atoms(['Be'], [[0, 0, 0]], np.eye(3) * 3, True)
+    assert au.get_electron_temperature(atoms) == 0.0 and au.get_electron_entropy(atoms) == 0.0
+    atoms.info['key_value_pairs'] = {'etemperature': 0.3, 'eentropy': 2.0}
+    assert au.get_electron_temperature(atoms) == 0.3 and au.get_electron_entropy(atoms) == 2.0
+    atoms.info['data'] = {'etemperature': 0.2}
+    assert au.get_electron_temperature(atoms) == 0.2
+    au.set_electron_temperature(atoms, 0.1)
+    au.set_electron_entropy(atoms, 5.0)
+    au.set_kinetic_energy(atoms, 1.5)
+    assert (au.get_electron_temperature(atoms), au.get_electron_entropy(atoms),
+            au.get_kinetic_energy(atoms)) == (0.1, 5.0, 1.5)
