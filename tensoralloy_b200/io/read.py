@@ -24,7 +24,35 @@ import numpy as np
 from tensoralloy_b200.atoms import Atoms
 from tensoralloy_b200.io.units import get_conversion_units
 
-XYZ_FORMATS = ('normal', 'xyz', 'extxyz')
+XYZ_FORMATS = ('normal', 'xyz', 'extxyz', 'stepmax')
+HARTREE = 27.211386024367243            # ase.units.Hartree (CODATA 2014)
+
+
+def cellpar_to_cell(cellpar):
+    """ase.geometry.cellpar_to_cell with its default orientation (a along x, b in the xy
+    plane): [a, b, c, alpha, beta, gamma] (A, degrees) -> rows = lattice vectors."""
+    a, b, c, alpha, beta, gamma = [float(x) for x in cellpar]
+
+    def cosd(x):            # exact zeros at 90 degrees, as ASE does
+        return 0.0 if abs(abs(x) - 90.0) < 1e-12 else np.cos(np.radians(x))
+
+    ca, cb, cg = cosd(alpha), cosd(beta), cosd(gamma)
+    sg = 1.0 if abs(abs(gamma) - 90.0) < 1e-12 else np.sin(np.radians(gamma))
+    cy = (ca - cb * cg) / sg
+    cz = np.sqrt(max(1.0 - cb * cb - cy * cy, 0.0))
+    return np.array([[a, 0.0, 0.0], [b * cg, b * sg, 0.0], [c * cb, c * cy, c * cz]])
+
+
+def cell_to_cellpar(cell):
+    """ase.geometry.cell_to_cellpar: lengths and angles (degrees)."""
+    cell = np.asarray(cell, dtype=np.float64).reshape(3, 3)
+    L = np.linalg.norm(cell, axis=1)
+    ang = []
+    for i, j in ((1, 2), (0, 2), (0, 1)):
+        ll = L[i] * L[j]
+        ang.append(np.degrees(np.arccos(np.clip(cell[i] @ cell[j] / ll, -1, 1)))
+                   if ll > 1e-16 else 90.0)
+    return np.array(list(L) + ang)
 _VOIGT = ((0, 0), (1, 1), (2, 2), (1, 2), (0, 2), (0, 1))
 _KV = re.compile(r'(\w[\w\-:.]*)\s*=\s*("[^"]*"|\{[^}]*\}|\S+)')
 
@@ -122,6 +150,15 @@ def _atoms_from_frame(n, comment, rows, extxyz):
             pbc = [t.upper().startswith('T') for t in shlex.split(head.pop('pbc'))]
         for k, v in head.items():
             info[k] = _value(v)
+    elif extxyz is None:
+        # STEPMAX xyz (io/xyz.py:18-31, read.py:101-112): energy in Hartree, six cell
+        # parameters and the label 'Cartesian'
+        cols = [('species', 'S', 1), ('pos', 'R', 3)]
+        f = comment.split()
+        if len(f) != 8 or f[-1].lower() != 'cartesian':
+            raise ValueError("stepmax xyz: expected 'energy a b c alpha beta gamma Cartesian'")
+        info['energy'] = float(f[0]) * HARTREE
+        cell, pbc = cellpar_to_cell(f[1:7]), True
     else:
         cols = [('species', 'S', 1), ('pos', 'R', 3)]
         info['energy'] = float(comment.split()[0])
@@ -168,7 +205,7 @@ def _read_xyz_like(filename, units, extxyz, num_examples=None, fmax=None):
             if np.abs(atoms.cell).sum() < 1e-8:
                 atoms.cell = np.eye(3) * (20.0 + (len(atoms) // 50) * 5.0)
             info['energy'] = float(info['energy']) * to_eV
-            if extxyz and 'forces' in info:
+            if extxyz is True and 'forces' in info:
                 info['forces'] = info['forces'] * to_eV_A
             else:
                 info['forces'] = np.zeros_like(atoms.positions)
@@ -187,7 +224,7 @@ def _read_xyz_like(filename, units, extxyz, num_examples=None, fmax=None):
             for symbol, cnt in Counter(atoms.get_chemical_symbols()).items():
                 max_occurs[symbol] = max(max_occurs[symbol], cnt)
             images.append(atoms)
-    metadata = {'max_occurs': dict(max_occurs), 'extxyz': extxyz, 'forces': True,
+    metadata = {'max_occurs': dict(max_occurs), 'extxyz': extxyz is True, 'forces': True,
                 'stress': bool(use_stress), 'periodic': periodic,
                 'unit_conversion': {'energy': to_eV, 'forces': to_eV_A, 'stress': to_eV_A3}}
     return Dataset(images, metadata)
@@ -195,8 +232,9 @@ def _read_xyz_like(filename, units, extxyz, num_examples=None, fmax=None):
 
 def read_file(filename, units=None, num_examples=None, file_type=None, verbose=False,
               append_to=None, fmax=None):
-    """read.py:190-246.  `file_type`: 'extxyz', 'xyz' / 'normal' (second line = energy);
-    'db' (SQLite) and 'stepmax' are refused -- the stores are out of scope."""
+    """read.py:190-246.  `file_type`: 'extxyz', 'xyz' / 'normal' (second line = energy),
+    'stepmax' (energy in Hartree + cell parameters); 'db' (SQLite) is refused -- the stores
+    are out of scope."""
     if file_type is None:
         file_type = splitext(filename)[1][1:]
     if units is None:
@@ -207,6 +245,8 @@ def read_file(filename, units=None, num_examples=None, file_type=None, verbose=F
         return _read_xyz_like(filename, units, True, num_examples, fmax)
     if file_type in ('xyz', 'normal'):
         return _read_xyz_like(filename, units, False, num_examples, fmax)
-    if file_type in ('db', 'stepmax'):
-        raise NotImplementedError(f"file type '{file_type}' is not supported here")
+    if file_type == 'stepmax':
+        return _read_xyz_like(filename, units, None, num_examples, fmax)
+    if file_type == 'db':
+        raise NotImplementedError("SQLite databases are out of scope (DESIGN.md 7)")
     raise ValueError("Unknown file type: {}".format(file_type))

@@ -6,7 +6,8 @@ import os
 import numpy as np
 import pytest
 
-from tensoralloy_b200.io.read import Dataset, read_file
+from tensoralloy_b200.io.read import (Dataset, cell_to_cellpar, cellpar_to_cell,
+                                      read_file)
 from tensoralloy_b200.io.units import get_conversion_units
 
 GOLD = os.path.join(os.path.dirname(__file__), 'golden')
@@ -55,6 +56,23 @@ def test_read_snap_stress_in_kbar():
     assert abs(atoms.cell[1, 0] - (-1.239893)) < 1e-9          # rows = lattice vectors
 
 
+def test_read_stepmax_xyz():
+    # test_read.py:75-82
+    db = read_file(os.path.join(GOLD, 'Pu8.stepmax.xyz'), num_examples=1, file_type='stepmax')
+    atoms = db[0]
+    cellpars = cell_to_cellpar(atoms.cell)
+    assert abs(atoms.positions[0, 2] - 3.301309) < 1e-7
+    assert abs(cellpars[2] - 6.7942123514756485) < 1e-6
+    assert abs(cellpars[4] - 79.74117275500237) < 1e-9 and abs(cellpars[3] - 90.0) < 1e-9
+    assert abs(atoms.info['energy'] - (-32.4 * 27.211386024367243)) < 1e-6
+    assert atoms.pbc.all() and np.array_equal(atoms.info['forces'], np.zeros((8, 3)))
+    # triclinic round trip of the cell-parameter helpers
+    par = [3.0, 4.0, 5.0, 80.0, 95.0, 110.0]
+    assert np.allclose(cell_to_cellpar(cellpar_to_cell(par)), par, atol=1e-12)
+    assert np.allclose(cellpar_to_cell([2.0, 3.0, 4.0, 90, 90, 90]), np.diag([2.0, 3.0, 4.0]),
+                       atol=0)
+
+
 def test_read_electron_temperature_and_entropy():
     # test_read.py:85-96; the 3x3 stress of this file becomes the Voigt vector
     db = read_file(os.path.join(GOLD, 'Be_liquid_4000K_1frame.extxyz'), num_examples=3)
@@ -97,3 +115,5 @@ def test_dataset_feeds_a_trainer_and_errors():
         read_file('x.cif')
     with pytest.raises(NotImplementedError):
         read_file('x.db')
+    with pytest.raises(ValueError, match="stepmax"):
+        read_file(os.path.join(GOLD, 'B28_2frames.xyz'), file_type='stepmax')
