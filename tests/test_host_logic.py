@@ -315,3 +315,34 @@ def test_atoms_utils_lookup_order():
     au.set_kinetic_energy(atoms, 1.5)
     assert (au.get_electron_temperature(atoms), au.get_electron_entropy(atoms),
             au.get_kinetic_energy(atoms)) == (0.1, 5.0, 1.5)
+
+
+def test_ctypes_mirrors_match_the_header_layouts(tmp_path):
+    """Every struct that crosses the C ABI: sizeof and the offset of every field as gcc lays
+    out include/tab200.h must equal the ctypes mirror in _lib.py."""
+    import ctypes as C
+    import shutil
+    import subprocess
+    from tensoralloy_b200 import _lib
+    if shutil.which('gcc') is None:
+        pytest.skip("gcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pairs = (('tab_fn', _lib.TabFn), ('tab_sf_desc', _lib.TabSfDesc),
+             ('tab_mlp_desc', _lib.TabMlpDesc))
+    prog = ['#include <stdio.h>', '#include <stddef.h>', '#include "tab200.h"', 'int main(){']
+    for cname, cls in pairs:
+        prog.append(f'printf("{cname} sizeof %zu\\n", sizeof({cname}));')
+        for field, _ in cls._fields_:
+            prog.append(f'printf("{cname} {field} %zu\\n", offsetof({cname}, {field}));')
+    prog.append('return 0;}')
+    src = tmp_path / 'layout.c'
+    src.write_text('\n'.join(prog))
+    exe = tmp_path / 'layout'
+    subprocess.run(['gcc', '-I', os.path.join(root, 'include'), str(src), '-o', str(exe)],
+                   check=True, capture_output=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    got = {(a, b): int(c) for a, b, c in (ln.split() for ln in out.splitlines())}
+    for cname, cls in pairs:
+        assert got[(cname, 'sizeof')] == C.sizeof(cls), cname
+        for field, _ in cls._fields_:
+            assert got[(cname, field)] == getattr(cls, field).offset, (cname, field)
