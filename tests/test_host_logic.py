@@ -346,3 +346,24 @@ def test_ctypes_mirrors_match_the_header_layouts(tmp_path):
         assert got[(cname, 'sizeof')] == C.sizeof(cls), cname
         for field, _ in cls._fields_:
             assert got[(cname, field)] == getattr(cls, field).offset, (cname, field)
+
+
+def test_ctypes_prototypes_have_the_header_arity():
+    """Every entry point whose argtypes are declared in _lib.py takes as many arguments as
+    its prototype in include/tab200.h (a silent mismatch would corrupt the call frame)."""
+    from tensoralloy_b200 import _build, _lib
+    _build.build_library()
+    header = open(os.path.join(ROOT, 'include', 'tab200.h')).read()
+    header = re.sub(r'/\*.*?\*/', '', header, flags=re.S)
+    protos = dict(re.findall(r'\b(tab_[a-z0-9_]+)\s*\(([^)]*)\)\s*;', header))
+    L = _lib.lib()
+    checked = 0
+    for name, args in protos.items():
+        fn = getattr(L, name)
+        if fn.argtypes is None:
+            continue
+        args = args.strip()
+        arity = 0 if args in ('', 'void') else len(args.split(','))
+        assert len(fn.argtypes) == arity, (name, len(fn.argtypes), arity)
+        checked += 1
+    assert checked >= 30, checked
