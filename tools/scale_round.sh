@@ -1,3 +1,6 @@
+#!/bin/bash
+# dev tool (run under `gpurun --gpus 8`): the 8- and 4-GPU bench lines of the headline config,
+# strong and weak scaling, with and without the CUDA-graph step -> gpurun_out/scale_<tag>.json
 mkdir -p gpurun_out
 run() { # N tag extra...
   N=$1; tag=$2; shift; shift
