@@ -239,3 +239,61 @@ def test_grap_new_mode_symmetric_is_traceless_form():
     assert torch.allclose(sym[..., :2], plain[..., :2], atol=0, rtol=0)
     assert torch.allclose(sym[..., 2], plain[..., 2] - plain[..., 0] ** 2 / 3.0, atol=1e-13)
     assert torch.allclose(sym[..., 3], plain[..., 3] - 0.6 * plain[..., 1], atol=1e-13)
+
+
+def test_grap_new_mode_oracle_forces_and_stress_by_finite_differences():
+    """The new-mode restatement (moment 3, traceless form, and the `nn` filter network) that
+    anchors the GPU parity tests: autograd forces = -dE/dR and stress = (dE/d strain) / V by
+    central differences."""
+    import torch
+    from oracle import atomic as oat
+    from tensoralloy_b200.atoms import bulk_fcc
+    rng = np.random.default_rng(2)
+    base = bulk_fcc('Ni', 3.6, (2, 2, 2))
+    pos = base.positions + rng.normal(scale=0.08, size=base.positions.shape)
+    cell = np.asarray(base.cell)
+    sym = ['Mo' if k % 3 == 0 else 'Ni' for k in range(len(pos))]
+    elements, rc = ['Mo', 'Ni'], 4.5
+    K = 3
+
+    def net(n_in, sizes, seed):
+        r = np.random.default_rng(seed)
+        dims = [n_in] + sizes
+        W = [r.normal(size=(dims[k], dims[k + 1])) * 0.4 for k in range(len(sizes))]
+        b = [r.normal(size=dims[k + 1]) * 0.1 for k in range(len(sizes) - 1)] + [None]
+        return W, b
+
+    fW, fb = net(1, [6, 6, K], 1)
+    cases = [dict(algorithm='pexp', grid=[(1.5, 2.0), (2.5, 3.0), (2.0, 1.0)], symmetric=True),
+             dict(algorithm='nn', grid=dict(weights=fW, biases=fb, activation='tanh',
+                                            use_resnet_dt=True), symmetric=False)]
+    for case in cases:
+        grap = dict(moments=[0, 1, 2, 3], cutoff='cosine', new_mode=True, **case)
+        dim = 2 * K * 4
+        params = {}
+        for k, el in enumerate(elements):
+            W, b = net(dim, [8, 1], 10 + k)
+            params[el] = dict(weights=[w * 0.2 for w in W], biases=b, activation='softplus',
+                              use_resnet_dt=False, out_bias=None)
+
+        def run(p, c):
+            return oat.atomic_evaluate(elements, sym, p, c, [1, 1, 1], rc, params,
+                                       angular=False, grap=grap)
+        ref = run(pos, cell)
+        assert np.abs(ref['forces']).max() > 1e-3
+        h = 1e-5
+        for a, c in ((0, 0), (7, 1), (20, 2)):
+            p1, p2 = pos.copy(), pos.copy()
+            p1[a, c] += h
+            p2[a, c] -= h
+            fd = -(run(p1, cell)['energy'] - run(p2, cell)['energy']) / (2 * h)
+            assert abs(fd - ref['forces'][a, c]) < 1e-7 * max(1.0, abs(fd)), (case['algorithm'], a)
+        eps, vol = 1e-6, abs(np.linalg.det(cell))
+        for (i, j), v in (((0, 0), 0), ((1, 2), 3)):
+            st = np.zeros((3, 3))
+            st[i, j] = st[j, i] = eps if i == j else eps / 2
+            Fp, Fm = np.eye(3) + st, np.eye(3) - st
+            de = (run(pos @ Fp, cell @ Fp)['energy'] - run(pos @ Fm, cell @ Fm)['energy']) \
+                / (2 * eps)
+            assert abs(de / vol - ref['stress'][v]) < 1e-7 * max(1.0, abs(de / vol)), \
+                (case['algorithm'], v)
