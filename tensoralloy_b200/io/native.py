@@ -228,8 +228,8 @@ def read_lammps_native(model_path, export_properties=('energy', 'forces', 'stres
         params = {k: np.asarray(z[f"descriptor::{k}"], dtype=np.float64).reshape(-1).tolist()
                   for k in METHOD_KEYS[algo]}
     max_moment = int(z["max_moment"])
-    if max_moment > 3:
-        raise ValueError("npz model: moments up to 3 are supported")
+    if max_moment > 5:
+        raise ValueError("npz model: moments up to 5 are supported")       # grap.py:578-579
     fct = {v: k for k, v in FCTYPE.items()}[int(z["fctype"])]
     act = {v: k for k, v in ACTFN.items()}[int(z["actfn"])]
     sym = bool(int(z["is_T_symmetric"])) if "is_T_symmetric" in z.files else False

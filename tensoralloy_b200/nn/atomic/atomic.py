@@ -154,9 +154,10 @@ class AtomicNN(BasicNN):
             self.initialize_variables()
         clf = self._transformer
         sf = self._descriptor
-        if getattr(sf, 'algorithm', None) == 'nn':
-            raise ValueError("GRAP/nn (trainable filter network) is not served by the "
-                             "descriptor kernels: use nn.atomic.grap_nn.GrapFilterTrainer")
+        if getattr(sf, 'uses_torch_path', lambda: False)():
+            raise ValueError("GRAP with the `nn` filter network or moments 4 / 5 is not "
+                             "served by the descriptor kernels: use "
+                             "nn.atomic.grap_nn.GrapFilterTrainer")
         self._model = _lib.AtomicModel(
             len(self._elements), clf.rcut, clf.acut,
             sf.radial_sets(), sf.angular_sets() if clf.angular else None,
@@ -176,14 +177,14 @@ class AtomicNN(BasicNN):
         return g.cpu().numpy()
 
     def _evaluate(self, features, want_forces, want_virial, want_atomic):
-        if getattr(self._descriptor, 'algorithm', None) == 'nn':
+        if getattr(self._descriptor, 'uses_torch_path', lambda: False)():
             return self._evaluate_filter_network(features, want_forces or want_virial)
         return self._evaluate_single(features, want_forces, want_virial, want_atomic)
 
     def evaluate_batch(self, batch, want_forces=True, want_virial=True, want_atomic=True):
-        if getattr(self._descriptor, 'algorithm', None) == 'nn':
+        if getattr(self._descriptor, 'uses_torch_path', lambda: False)():
             raise NotImplementedError(
-                "batched inference of a GRAP/nn model: queue the structures in "
+                "batched inference of a GRAP model on the torch path: queue the structures in "
                 "nn.atomic.grap_nn.GrapFilterTrainer and call .evaluate()")
         return super().evaluate_batch(batch, want_forces, want_virial, want_atomic)
 

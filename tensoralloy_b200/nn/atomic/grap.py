@@ -28,8 +28,9 @@ grap.py:485-494).  Moment 3 (ten unique third-order sums, multiplicities
 1 3 3 3 6 3 1 3 3 1) exists in new mode only, as in the reference (its legacy loop
 stops at 2, grap.py:434-457).  The trainable `nn` algorithm (a filter network r -> R^K,
 grap.py:211-234) is served by nn/atomic/grap_nn.py (torch over the library's pair vectors
-and pair-force op), not by the descriptor kernels.  Not built, and refused loudly: moments
-4, 5 (`get_moment_tensor`, grap.py:537-572).
+and pair-force op), not by the descriptor kernels, and so are moments 4 and 5 (full 3^m
+moment tensors with unit weights for every moment, no traceless form: `get_moment_tensor` /
+`get_T_dm`, grap.py:537-594).
 """
 import numpy as np
 
@@ -74,9 +75,10 @@ class GenericRadialAtomicPotential:
         if isinstance(moment_tensors, int):
             moment_tensors = [moment_tensors]
         moment_tensors = sorted(set(int(m) for m in moment_tensors))
-        allowed = (0, 1, 2) if legacy_mode else (0, 1, 2, 3)
+        allowed = (0, 1, 2) if legacy_mode else (0, 1, 2, 3, 4, 5)
         if any(m not in allowed for m in moment_tensors):
-            raise ValueError("GRAP: moments 0, 1, 2 (legacy mode) / 0 .. 3 (new mode) "
+            # grap.py:434-457 (legacy loop stops at 2), :578-579 (new mode: <= 5)
+            raise ValueError("GRAP: moments 0, 1, 2 (legacy mode) / 0 .. 5 (new mode) "
                              "are supported")
         if self._algo_nn is not None:
             self._elements = sorted(list(elements))
@@ -146,6 +148,12 @@ class GenericRadialAtomicPotential:
         if not self._legacy_mode:
             return tuple(range(self.max_moment + 1))
         return tuple(self._moment_tensors)
+
+    def uses_torch_path(self):
+        """True for the descriptors the CUDA descriptor kernels do not serve -- the trainable
+        `nn` filter network and moments 4 / 5 (full 3^m moment tensors): they run through
+        nn/atomic/grap_nn.py (torch on the device over the library's pair operators)."""
+        return self._algorithm == 'nn' or (not self._legacy_mode and self.max_moment > 3)
 
     def grap_flags(self):
         """include/tab200.h TAB_GRAP_*: the two new-mode details the kernels switch on

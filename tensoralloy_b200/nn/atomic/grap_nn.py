@@ -163,22 +163,58 @@ def filter_network(r, W, b, act, resnet):
     return h @ W[nh]
 
 
-def filter_descriptors(D, key, n_rows, W, b, act, resnet, cutoff, rc, max_moment,
-                       symmetric, eps):
+def closed_form_radial(algorithm, grid, rc):
+    """f_tau(r) of the closed-form algorithms (grap.py:121-209) as one torch function
+    r [P] -> [P, K]; `grid` = descriptor.radial_sets()."""
+    def fn(r):
+        cols = []
+        for prm in grid:
+            if algorithm == 'sf':
+                cols.append(torch.exp(-prm[0] * (r - prm[1]) ** 2 / rc ** 2))
+            elif algorithm == 'morse':
+                d, g, r0 = prm
+                cols.append(d * (torch.exp(-2.0 * g * (r - r0)) - 2.0 * torch.exp(-g * (r - r0))))
+            elif algorithm == 'density':
+                a, beta, re = prm
+                cols.append(a * torch.exp(-beta * (r / re - 1.0)))
+            elif algorithm == 'pexp':
+                rl, pl = prm
+                cols.append(torch.exp(-(r / rl) ** pl))
+            else:
+                raise ValueError(algorithm)
+        return torch.stack(cols, dim=1)
+    return fn
+
+
+def filter_descriptors(D, key, n_rows, radial, cutoff, rc, max_moment, symmetric, eps):
     """New-mode GRAP descriptors from the directed pair vectors (grap.py:596-680).
-    D [P, 3]; key [P] = centre * n_el + term (row of the moment sums); n_rows = n * n_el.
-    Returns [n_rows, K, max_moment + 1]; the caller reshapes to [n, n_el * K * (M + 1)]."""
+    D [P, 3]; key [P] = centre * n_el + term (row of the moment sums); n_rows = n * n_el;
+    radial: r [P] -> H [P, K] without the cutoff (the filter network or the closed forms).
+    Returns [n_rows, K, max_moment + 1]; the caller reshapes to [n, n_el * K * (M + 1)].
+
+    Moments <= 3 use the unique Cartesian index tuples with their multiplicities
+    (`_get_moment_coeff_tensor` / `_get_multiplicity_tensor`, grap.py:470-535); a descriptor
+    with max_moment 4 or 5 uses the full 3^m products with unit weights for EVERY moment and
+    has no traceless form (`get_moment_tensor` / `get_T_dm`, grap.py:537-594, 655-660)."""
     r = torch.sqrt(torch.sum(D * D, dim=1) + eps)                 # universal.py:470-473
-    H = filter_network(r, W, b, act, resnet) * _cutoff(cutoff, r, rc)[:, None]   # [P, K]
+    H = radial(r) * _cutoff(cutoff, r, rc)[:, None]                # [P, K]
     K = H.shape[1]
     z = lambda *shape: torch.zeros(*shape, dtype=D.dtype, device=D.device)
     P0 = z(n_rows, K).index_add(0, key, H)
     cols = [torch.sign(P0) * torch.sqrt(P0 * P0 + 1e-16)]         # grap.py:667-676
-    if max_moment >= 1:
-        u = D / r[:, None]
-        P1 = z(n_rows, K, 3).index_add(0, key, H[:, :, None] * u[:, None, :])
-        S1 = torch.sum(P1 * P1, dim=2)
-        cols.append(S1)
+    if max_moment == 0:
+        return torch.stack(cols, dim=2)
+    u = D / r[:, None]
+    if max_moment > 3:
+        m = torch.ones(D.shape[0], 1, dtype=D.dtype, device=D.device)
+        for _ in range(max_moment):
+            m = (m[:, :, None] * u[:, None, :]).reshape(D.shape[0], -1)       # [P, 3^k]
+            P = z(n_rows, K, m.shape[1]).index_add(0, key, H[:, :, None] * m[:, None, :])
+            cols.append(torch.sum(P * P, dim=2))
+        return torch.stack(cols, dim=2)
+    P1 = z(n_rows, K, 3).index_add(0, key, H[:, :, None] * u[:, None, :])
+    S1 = torch.sum(P1 * P1, dim=2)
+    cols.append(S1)
     if max_moment >= 2:
         m2 = torch.stack([u[:, a] * u[:, c] for a, c in _AB], dim=1)          # [P, 6]
         P2 = z(n_rows, K, 6).index_add(0, key, H[:, :, None] * m2[:, None, :])
@@ -198,6 +234,15 @@ def filter_descriptors(D, key, n_rows, W, b, act, resnet, cutoff, rc, max_moment
     return torch.stack(cols, dim=2)
 
 
+def _radial_of(nn, filters):
+    """The radial part of the model's descriptor as a torch function of r."""
+    desc = nn.descriptor
+    if desc.algorithm == 'nn':
+        return lambda r: filter_network(r, filters['W'], filters['b'], filters['act'],
+                                        filters['resnet'])
+    return closed_form_radial(desc.algorithm, desc.radial_sets(), nn.transformer.rcut)
+
+
 class FilterEvaluator:
     """E, per-atom E, forces and virial of ONE structure (or one batch handle) for a model
     with the `nn` algorithm: the inference side of `AtomicNN._evaluate`
@@ -211,10 +256,13 @@ class FilterEvaluator:
         self.dt = get_float_dtype()
         self.tdtype = torch.float64 if self.dt.name == 'float64' else torch.float32
         t = lambda a: torch.tensor(np.asarray(a), dtype=self.tdtype, device=device)
-        fp = filter_params(nn)
-        self.filters = dict(W=[t(w) for w in fp['weights']],
-                            b=[None if v is None else t(v) for v in fp['biases']],
-                            act=_activation(fp['activation']), resnet=fp['use_resnet_dt'])
+        self.filters = None
+        if nn.descriptor.algorithm == 'nn':
+            fp = filter_params(nn)
+            self.filters = dict(W=[t(w) for w in fp['weights']],
+                                b=[None if v is None else t(v) for v in fp['biases']],
+                                act=_activation(fp['activation']),
+                                resnet=fp['use_resnet_dt'])
         self.layers = {}
         for el in nn.elements:
             p = nn.mlp_params(el)
@@ -242,9 +290,8 @@ class FilterEvaluator:
         ti, tj = types[i], types[j]
         term = torch.where(ti == tj, torch.zeros_like(ti), tj - (tj > ti).long() + 1)
         D = D.to(self.tdtype).detach().requires_grad_(want_forces)
-        F = self.filters
-        G = filter_descriptors(D, i * nel + term, n * nel, F['W'], F['b'], F['act'],
-                               F['resnet'], desc.cutoff_function, nn.transformer.rcut,
+        G = filter_descriptors(D, i * nel + term, n * nel, _radial_of(nn, self.filters),
+                               desc.cutoff_function, nn.transformer.rcut,
                                desc.max_moment, desc.is_T_symmetric, self.dt.eps)
         G = G.reshape(n, -1)
         e_atom = torch.zeros(n, dtype=self.tdtype, device=self.device)
@@ -267,17 +314,21 @@ class GrapFilterTrainer(AtomicNNTrainer):
     def __init__(self, nn, device='cuda', loss_weights=None, per_atom_energy=True,
                  pair_force=None):
         desc = nn.descriptor
-        if getattr(desc, 'algorithm', None) != 'nn':
-            raise ValueError("GrapFilterTrainer needs GenericRadialAtomicPotential("
-                             "algorithm='nn')")
+        if not getattr(desc, 'uses_torch_path', lambda: False)():
+            raise ValueError("GrapFilterTrainer serves GenericRadialAtomicPotential in new "
+                             "mode with algorithm='nn' or moments 4 / 5; other descriptors "
+                             "train through AtomicNNTrainer (descriptor kernels)")
         self._init_common(nn, device, loss_weights, per_atom_energy)
-        fp = filter_params(nn)
-        trainable = desc.algorithm_object.trainable
-        mk = self._leaf if trainable else \
-            (lambda a: torch.tensor(np.asarray(a), dtype=self.tdtype, device=device))
-        self.filters = dict(W=[mk(w) for w in fp['weights']],
-                            b=[None if v is None else mk(v) for v in fp['biases']],
-                            act=_activation(fp['activation']), resnet=fp['use_resnet_dt'])
+        self.filters = None
+        if desc.algorithm == 'nn':
+            fp = filter_params(nn)
+            trainable = desc.algorithm_object.trainable
+            mk = self._leaf if trainable else \
+                (lambda a: torch.tensor(np.asarray(a), dtype=self.tdtype, device=device))
+            self.filters = dict(W=[mk(w) for w in fp['weights']],
+                                b=[None if v is None else mk(v) for v in fp['biases']],
+                                act=_activation(fp['activation']),
+                                resnet=fp['use_resnet_dt'])
         if pair_force is None:
             from tensoralloy_b200.nn.eam.training import PairForce
             pair_force = PairForce.apply
@@ -320,8 +371,7 @@ class GrapFilterTrainer(AtomicNNTrainer):
         B = self._batch
         desc = self.nn.descriptor
         n, nel = B['types'].shape[0], len(self.elements)
-        F = self.filters
-        G = filter_descriptors(D, B['key'], n * nel, F['W'], F['b'], F['act'], F['resnet'],
+        G = filter_descriptors(D, B['key'], n * nel, _radial_of(self.nn, self.filters),
                                desc.cutoff_function, self.nn.transformer.rcut,
                                desc.max_moment, desc.is_T_symmetric, self.dt.eps)
         return G.reshape(n, -1)                   # [n, term * K * (M + 1)]
@@ -385,6 +435,8 @@ class GrapFilterTrainer(AtomicNNTrainer):
                 nn.set_variable(f"{name}/kernel", w.detach().cpu().numpy()[None])
                 if L['b'][k] is not None:
                     nn.set_variable(f"{name}/bias", L['b'][k].detach().cpu().numpy())
+        if self.filters is None:
+            return
         nh = len(self.filters['W']) - 1
         for k, w in enumerate(self.filters['W']):
             name = f"{filter_scope(nn)}/" + (f"Conv3d{k + 1}" if k < nh else "Output")

@@ -33,10 +33,12 @@ def make_structures(n_struct=2, seed=5):
     return out
 
 
-def make_model(elements, rc, max_moment, symmetric, cutoff='cosine'):
+def make_model(elements, rc, max_moment, symmetric, cutoff='cosine', algorithm='nn'):
+    parameters = dict(num_filters=5, hidden_sizes=[8, 8], activation='softplus',
+                      use_resnet_dt=True) if algorithm == 'nn' else \
+        dict(rl=[1.5, 2.5, 2.0], pl=[2.0, 3.0, 1.0])
     desc = GenericRadialAtomicPotential(
-        elements, 'nn', dict(num_filters=5, hidden_sizes=[8, 8], activation='softplus',
-                             use_resnet_dt=True),
+        elements, algorithm, parameters,
         moment_tensors=max_moment, cutoff_function=cutoff, symmetric=symmetric,
         legacy_mode=False)
     nn = AtomicNN(elements, desc, hidden_sizes=[16, 16], activation='softplus',
@@ -45,7 +47,7 @@ def make_model(elements, rc, max_moment, symmetric, cutoff='cosine'):
     nn.attach_transformer(UniversalTransformer(elements, rcut=rc, angular=False))
     nn.initialize_variables(seed=3)
     rng = np.random.default_rng(9)
-    for k in (1, 2):      # non-zero filter biases
+    for k in ((1, 2) if algorithm == 'nn' else ()):      # non-zero filter biases
         key = f"Atomic/Filters/Conv3d{k}/bias"
         nn.set_variable(key, rng.normal(size=nn.get_variable(key).shape) * 0.3)
     for el in elements:
@@ -200,3 +202,80 @@ def test_filter_evaluator_matches_oracle_energy_forces_stress():
                                                     (0, 1))]) / vol
     assert np.abs(st6 - ref['stress']).max() < 1e-10
     assert np.abs(ref['forces']).max() > 1e-3
+
+
+@pytest.mark.parametrize("algorithm,max_moment", [('pexp', 4), ('nn', 5)])
+def test_moments_4_and_5_use_the_full_moment_tensors(algorithm, max_moment):
+    """grap.py:537-594, 655-660: with max_moment > 3 every moment is the full 3^m tensor with
+    unit weights and `symmetric` has no effect; closed-form algorithms take the same torch
+    path as the filter network.  Loss and every parameter gradient against the oracle."""
+    elements, rc = ['Mo', 'Ni'], 4.5
+    structs = make_structures()
+    with precision_scope('high'):
+        nn = make_model(elements, rc, max_moment, True, 'cosine', algorithm)
+        assert nn.descriptor.uses_torch_path()
+        assert nn.descriptor.dimension() == 2 * (5 if algorithm == 'nn' else 3) * (max_moment + 1)
+        with pytest.raises(ValueError, match="GrapFilterTrainer"):
+            nn._device_model()
+        tr = cpu_trainer(nn, structs, rc)
+        loss, parts = tr.gradients()
+        leaves = []
+        if algorithm == 'nn':
+            fp = filter_params(nn)
+            leaves = [torch.tensor(w, dtype=torch.float64, requires_grad=True)
+                      for w in fp['weights']] + \
+                     [torch.tensor(v, dtype=torch.float64, requires_grad=True)
+                      for v in fp['biases'] if v is not None]
+            nW = len(fp['weights'])
+            grid = dict(weights=leaves[:nW], biases=leaves[nW:] + [None],
+                        activation=fp['activation'], use_resnet_dt=fp['use_resnet_dt'])
+        else:
+            grid = nn.descriptor.radial_sets()
+        grap = dict(algorithm=algorithm, grid=grid, moments=list(range(max_moment + 1)),
+                    cutoff='cosine', new_mode=True, symmetric=True)
+        params = {el: nn.mlp_params(el) for el in elements}
+        ref_loss, ref_parts, ref_g = otr.loss_and_grads(elements, structs, params, rc,
+                                                        angular=False, grap=grap,
+                                                        extra_leaves=leaves)
+    assert abs(loss.item() - ref_loss) < 1e-10 * max(1.0, abs(ref_loss))
+    for key in ('energy', 'forces', 'stress'):
+        assert abs(parts[key].item() - ref_parts[key]) < 1e-10
+    for el in elements:
+        for k, w in enumerate(tr.layers[el]['W']):
+            r = ref_g[el][0][k]
+            assert np.abs(w.grad.numpy() - r).max() < 1e-9 * max(1.0, np.abs(r).max()), (el, k)
+    if algorithm == 'nn':
+        mine = [w.grad for w in tr.filters['W']] + \
+               [v.grad for v in tr.filters['b'] if v is not None]
+        for g, r in zip(mine, ref_g['__extra__']):
+            assert np.abs(g.numpy() - r).max() < 1e-9 * max(1.0, np.abs(r).max())
+    else:
+        assert tr.filters is None
+        tr.sync_to_model()
+
+
+def test_closed_form_descriptors_on_the_torch_path_equal_the_kernel_formulation():
+    """For moments <= 3 the torch path and the oracle's legacy-style restatement (which the
+    CUDA kernels are tested against) must give the same descriptors: ties the two product
+    paths together."""
+    from oracle import atomic as oat
+    from tensoralloy_b200.nn.atomic.grap_nn import closed_form_radial, filter_descriptors
+    st = make_structures(1, seed=3)[0]
+    elements, rc = ['Mo', 'Ni'], 4.5
+    i, j, S = onl.neighbor_list(st['positions'], st['cell'], st['pbc'], rc)[:3]
+    D = torch.as_tensor(st['positions'][j] - st['positions'][i] + S @ st['cell'])
+    types = np.array([elements.index(x) for x in st['symbols']])
+    ti, tj = torch.as_tensor(types[i]), torch.as_tensor(types[j])
+    term = torch.where(ti == tj, torch.zeros_like(ti), tj - (tj > ti).long() + 1)
+    n = len(types)
+    for algorithm, grid, cutoff in (('sf', [(0.5, 0.0), (4.0, 1.0)], 'cosine'),
+                                    ('morse', [(0.5, 1.2, 2.2), (1.0, 0.8, 2.6)], 'polynomial'),
+                                    ('density', [(1.0, 3.0, 2.2), (2.0, 5.0, 2.4)], 'cosine'),
+                                    ('pexp', [(1.5, 2.0), (2.5, 3.0)], 'polynomial')):
+        G = filter_descriptors(D, torch.as_tensor(i).long() * 2 + term, n * 2,
+                               closed_form_radial(algorithm, grid, rc), cutoff, rc, 2, False,
+                               1e-14).reshape(n, -1)
+        ref = oat.grap_descriptors(elements, types, torch.as_tensor(st['positions']),
+                                   torch.as_tensor(st['cell']), i, j, S, rc, algorithm, grid,
+                                   (0, 1, 2), cutoff)
+        assert float((G - ref).abs().max()) < 1e-10 * max(1.0, float(ref.abs().max())), algorithm

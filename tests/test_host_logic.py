@@ -209,8 +209,11 @@ def test_grap_new_mode_layout_and_refusals():
         Grap(['Be'], 'nn', dict(h_abck_modifier=2), legacy_mode=False)
     with pytest.raises(ValueError, match="moments 0, 1, 2"):
         Grap(['Be'], 'sf', par, moment_tensors=3)                 # legacy stops at 2
+    five = Grap(['Be'], 'sf', par, moment_tensors=5, legacy_mode=False)
+    assert five.uses_torch_path() and five.moments() == (0, 1, 2, 3, 4, 5)
+    assert not sym.uses_torch_path() and not legacy.uses_torch_path()
     with pytest.raises(ValueError, match="moments 0, 1, 2"):
-        Grap(['Be'], 'sf', par, moment_tensors=4, legacy_mode=False)
+        Grap(['Be'], 'sf', par, moment_tensors=6, legacy_mode=False)
 
 
 def test_batch_universal_transformer_mirror():
