@@ -4,7 +4,7 @@ neighbour lists come from the oracle's ASE restatement and the library's pair-fo
 (`tab_pair_forces` / `tab_pair_jvp`, include/tab200.h) is replaced by its definition in
 torch -- F_i = sum_{p in row i} g_p - sum_{p -> i} g_p, W = sum_p sym(g_p (x) D_p) -- so
 that the descriptor algebra, both networks and the double backward are checked without a
-GPU; tests/test_zz_grap_filter_gpu.py runs the same comparison through the library."""
+GPU; tests/test_zzz_grap_filter_gpu.py runs the same comparison through the library."""
 import numpy as np
 import pytest
 import torch
