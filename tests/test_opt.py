@@ -1,0 +1,73 @@
+"""nn/opt.py: learning-rate schedules (TF's closed forms), optimiser factory, the train op
+with global step and moving averages (reference: nn/utils.py:77-150, nn/opt.py:89-166)."""
+import math
+
+import pytest
+import torch
+
+from tensoralloy_b200.nn.opt import OptParameters, TrainOp, get_learning_rate, get_optimizer
+
+
+def test_learning_rate_schedules():
+    assert get_learning_rate(500, 0.01) == 0.01
+    kw = dict(learning_rate=0.01, decay_rate=0.9, decay_steps=1000)
+    assert abs(get_learning_rate(2500, decay_function='exponential', **kw)
+               - 0.01 * 0.9 ** 2.5) < 1e-18
+    assert abs(get_learning_rate(2500, decay_function='exponential', staircase=True, **kw)
+               - 0.01 * 0.9 ** 2) < 1e-18
+    assert abs(get_learning_rate(2500, decay_function='inverse_time', **kw)
+               - 0.01 / (1 + 0.9 * 2.5)) < 1e-18
+    assert abs(get_learning_rate(2500, decay_function='natural_exp', **kw)
+               - 0.01 * math.exp(-0.9 * 2.5)) < 1e-18
+    with pytest.raises(ValueError, match="not supported"):
+        get_learning_rate(1, decay_function='cosine')
+
+
+def test_optimizer_factory_defaults():
+    p = [torch.zeros(3, requires_grad=True)]
+    adam = get_optimizer(p, 0.01, 'adam', beta1=0.8)
+    assert isinstance(adam, torch.optim.Adam) and adam.defaults['betas'] == (0.8, 0.999)
+    assert adam.defaults['eps'] == 1e-8
+    assert get_optimizer(p, 0.01, 'adamw').defaults['weight_decay'] == 1e-4
+    assert isinstance(get_optimizer(p, 0.01, 'Nadam'), torch.optim.NAdam)
+    assert get_optimizer(p, 0.01, 'adadelta').defaults['rho'] == 0.95
+    rms = get_optimizer(p, 0.01, 'rmsprop', momentum=0.5)
+    assert rms.defaults['alpha'] == 0.9 and rms.defaults['momentum'] == 0.5
+    sgd = get_optimizer(p, 0.01, 'sgd')
+    assert sgd.defaults['momentum'] == 0.9 and sgd.defaults['nesterov'] is True
+    with pytest.raises(ValueError, match="Supported SGD optimizers"):
+        get_optimizer(p, 0.01, 'lbfgs')
+
+
+def test_train_op_step_learning_rate_and_moving_average():
+    w = torch.tensor([1.0, -2.0], dtype=torch.float64, requires_grad=True)
+    op = TrainOp([w], OptParameters(method='adam', learning_rate=0.1,
+                                    decay_function='exponential', decay_rate=0.5,
+                                    decay_steps=2))
+    w0 = w.detach().clone()
+    w.grad = torch.tensor([0.5, -0.25], dtype=torch.float64)
+    lr = op.step()
+    assert lr == 0.1 and op.global_step == 1
+    # first Adam step: m_hat / (sqrt(v_hat) + eps) = sign(g) up to eps
+    expect = w0 - 0.1 * torch.sign(w.grad)
+    assert torch.allclose(w.detach(), expect, atol=1e-7)
+    assert torch.allclose(op.shadow[0], 0.999 * w0 + 0.001 * w.detach(), atol=1e-15)
+    lr2 = op.step()
+    assert abs(lr2 - 0.1 * 0.5 ** 0.5) < 1e-15 and op.global_step == 2
+    ema = op.ema_values()[0]
+    op.swap_in_ema()
+    assert torch.equal(w.detach(), ema)
+
+
+def test_train_op_drives_a_trainer_like_object_to_the_minimum():
+    """`trainer.train_step(optimizer)` only needs `.step()`: minimise a quadratic."""
+    w = torch.tensor([3.0, -1.0], dtype=torch.float64, requires_grad=True)
+    target = torch.tensor([0.5, 2.0], dtype=torch.float64)
+    op = TrainOp([w], OptParameters(method='sgd', learning_rate=0.05,
+                                    additional_kwargs=dict(momentum=0.5)))
+    for _ in range(300):
+        op.zero_grad()
+        loss = ((w - target) ** 2).sum()
+        loss.backward()
+        op.step()
+    assert torch.allclose(w.detach(), target, atol=1e-6) and op.global_step == 300
