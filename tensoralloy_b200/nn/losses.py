@@ -1,15 +1,25 @@
 """
 Loss arithmetic of the reference (tensoralloy/nn/losses.py), restated on torch
 tensors for the training step:
-  RMSE = sqrt(mean((x - y)^2) + eps)          losses.py:69-95  (eps = dtype eps)
-  energy: optionally per atom                 losses.py:204-282 (:250-253)
-  forces: over the real atoms only            losses.py:285-332
-  stress: on the Voigt 6-vectors              losses.py:394-456
-  total  = sum of the enabled weighted terms  nn/basic.py:626
+  RMSE    = sqrt(mean((x - y)^2) + eps)                  losses.py:69-95  (eps = dtype eps)
+  rRMSE   = mean(|x - y|_2 / |x|_2) over the rows        losses.py:53-66
+  logcosh = mean(d + softplus(-2 d) - log 2), d = x - y  losses.py:44-50, 98-121
+  ylogy   = mean(x (log max(x, 1e-12) - log max(y, 1e-12))^2)   losses.py:124-153
+  energy: optionally per atom                            losses.py:204-282 (:250-253)
+  forces: over the real atoms only                       losses.py:285-391
+  stress: on the Voigt 6-vectors                         losses.py:394-456
+  pressure: on the scalar total pressure (no rRMSE)      losses.py:459-504
+  static or dynamic (linear / log-scaled in the global step) loss weights   losses.py:171-201
+  total  = sum of the enabled weighted terms             nn/basic.py:626
+`labels` come first, as in the reference.
 """
+import math
+
 import torch
 
 from tensoralloy_b200.precision import get_float_dtype
+
+METHODS = ('rmse', 'rrmse', 'logcosh', 'ylogy')
 
 
 def rmse(x, y, eps=None):
@@ -18,18 +28,72 @@ def rmse(x, y, eps=None):
     return torch.sqrt(torch.mean((x - y) ** 2) + eps)
 
 
-def energy_loss(labels, predictions, n_atoms, per_atom_loss=True, weight=1.0):
+def mae(x, y):
+    """The MAE every loss of the reference reports beside its value."""
+    return torch.mean(torch.abs(x - y))
+
+
+def relative_rmse(labels, predictions):
+    if labels.dim() == 1:
+        labels, predictions = labels.reshape(-1, 1), predictions.reshape(-1, 1)
+    upper = torch.linalg.norm(labels - predictions, dim=1)
+    lower = torch.linalg.norm(labels, dim=1)
+    return torch.mean(upper / lower)
+
+
+def logcosh(labels, predictions):
+    d = labels - predictions
+    return torch.mean(d + torch.nn.functional.softplus(-2.0 * d) - math.log(2.0))
+
+
+def ylogy(labels, predictions):
+    logx = torch.log(torch.clamp(labels, min=1e-12))
+    logy = torch.log(torch.clamp(predictions, min=1e-12))
+    return torch.mean((logx - logy) ** 2 * labels)
+
+
+def _raw(method, labels, predictions, allowed):
+    if method not in METHODS:
+        raise KeyError(method)                    # LossMethod[options.method]
+    if method not in allowed:
+        raise ValueError(f"loss method '{method}' is not available for this property")
+    return {'rmse': rmse, 'rrmse': relative_rmse, 'logcosh': logcosh,
+            'ylogy': ylogy}[method](labels, predictions)
+
+
+def dynamic_weight(weight, global_step=0, max_train_steps=None, logscale=False):
+    """losses.py:171-201: a float is a constant weight; a pair (w0, w1) moves from w0 to w1
+    over `max_train_steps`, linearly or linearly in log10."""
+    if isinstance(weight, (int, float)):
+        return float(weight)
+    w0, w1 = weight
+    if max_train_steps is None:
+        raise ValueError("a dynamic loss weight needs max_train_steps")
+    if logscale:
+        l0, l1 = math.log10(w0), math.log10(w1)
+        return 10.0 ** (l0 + (l1 - l0) / max_train_steps * global_step)
+    return w0 + (w1 - w0) / max_train_steps * global_step
+
+
+def energy_loss(labels, predictions, n_atoms, per_atom_loss=True, weight=1.0, method='rmse'):
     if per_atom_loss:
         n = n_atoms.to(labels.dtype)
-        return weight * rmse(labels / n, predictions / n)
-    return weight * rmse(labels, predictions)
+        labels, predictions = labels / n, predictions / n
+    return weight * _raw(method, labels, predictions, METHODS)
 
 
-def forces_loss(labels, predictions, weight=1.0):
+def forces_loss(labels, predictions, weight=1.0, method='rmse'):
     """labels / predictions: [total real atoms, 3] (padding already removed)."""
-    return weight * rmse(labels, predictions)
+    return weight * _raw(method, labels, predictions, ('rmse', 'rrmse', 'logcosh'))
 
 
-def stress_loss(labels, predictions, weight=1.0):
+def stress_loss(labels, predictions, weight=1.0, method='rmse'):
     """labels / predictions: [batch, 6] Voigt, eV/A^3."""
-    return weight * rmse(labels, predictions)
+    return weight * _raw(method, labels, predictions, ('rmse', 'rrmse', 'logcosh'))
+
+
+def pressure_loss(labels, predictions, weight=1.0, method='rmse'):
+    """labels / predictions: [batch] total pressure (losses.py:459-504: rmse or logcosh)."""
+    if labels.dim() != 1 or predictions.dim() != 1:
+        raise ValueError("pressure loss: rank-1 tensors expected")
+    return weight * _raw(method, labels, predictions, ('rmse', 'logcosh'))

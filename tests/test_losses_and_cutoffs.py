@@ -71,3 +71,37 @@ def test_cutoff_functions_match_the_simple_forms():
     assert np.abs(_cutoff('polynomial', t, rc).numpy() - poly_simple).max() < 1e-14
     t32 = torch.tensor(r, dtype=torch.float32)
     assert np.abs(_cutoff('cosine', t32, rc).numpy() - cos_simple).max() < 1e-7   # the reference's delta
+
+
+def test_other_loss_methods_and_dynamic_weights():
+    """losses.py:44-66 (logcosh = keras form, relative RMSE), :124-153 (ylogy), :171-201
+    (static / dynamic weights), :459-504 (pressure: rmse or logcosh only)."""
+    import pytest
+    rng = np.random.default_rng(3)
+    x, y = rng.uniform(0.1, 3.0, (7, 3)), rng.uniform(0.1, 3.0, (7, 3))
+    tx, ty = torch.tensor(x), torch.tensor(y)
+    with precision_scope('high'):
+        assert abs(losses.forces_loss(tx, ty, method='logcosh').item()
+                   - np.mean(np.log(np.cosh(x - y)))) < 1e-12
+        assert abs(losses.forces_loss(tx, ty, method='rrmse').item()
+                   - np.mean(np.linalg.norm(x - y, axis=1) / np.linalg.norm(x, axis=1))) < 1e-12
+        e, p, n = tx[:, 0], ty[:, 0], torch.tensor(rng.integers(1, 5, 7).astype(float))
+        xe, ye = (e / n).numpy(), (p / n).numpy()
+        assert abs(losses.energy_loss(e, p, n, method='ylogy').item()
+                   - np.mean(xe * (np.log(xe) - np.log(ye)) ** 2)) < 1e-12
+        assert abs(losses.energy_loss(e, p, n, method='rrmse').item()
+                   - np.mean(np.abs(xe - ye) / np.abs(xe))) < 1e-12
+        assert abs(losses.mae(tx, ty).item() - np.mean(np.abs(x - y))) < 1e-15
+        assert abs(losses.pressure_loss(e, p, weight=2.0).item()
+                   - 2.0 * np.sqrt(np.mean((x[:, 0] - y[:, 0]) ** 2) + 1e-14)) < 1e-12
+        with pytest.raises(ValueError, match="not available"):
+            losses.pressure_loss(e, p, method='rrmse')
+        with pytest.raises(ValueError, match="not available"):
+            losses.stress_loss(tx, ty, method='ylogy')
+        with pytest.raises(KeyError):
+            losses.energy_loss(e, p, n, method='huber')
+    assert losses.dynamic_weight(0.5) == 0.5
+    assert abs(losses.dynamic_weight((1.0, 3.0), 250, 1000) - 1.5) < 1e-15
+    assert abs(losses.dynamic_weight((1.0, 100.0), 500, 1000, logscale=True) - 10.0) < 1e-12
+    with pytest.raises(ValueError, match="max_train_steps"):
+        losses.dynamic_weight((1.0, 2.0), 3)
