@@ -1,41 +1,35 @@
 """
 Per-structure scalars kept in `atoms.info` -- mirror of tensoralloy/atoms_utils.py:14-69:
 the electron temperature (eV) and electron entropy of finite-temperature data and the kinetic
-energy; a value may also sit in `info['data']` or `info['key_value_pairs']` (structures read
-back from the reference's SQLite store).
+energy (eV).  A value may also sit one level down, in `info['data']` or
+`info['key_value_pairs']` (structures read back from the reference's SQLite store); writes
+always go to the top level.
 """
+_NESTED = ('data', 'key_value_pairs')
 
 
-def _get(atoms, prop, default):
+def _lookup(atoms, key, default=0.0):
     info = atoms.info
-    if prop in info:
-        return info.get(prop)
-    if 'data' in info and prop in info['data']:
-        return info['data'][prop]
-    if 'key_value_pairs' in info and prop in info['key_value_pairs']:
-        return info['key_value_pairs'][prop]
+    if key in info:
+        return info[key]
+    for holder in _NESTED:
+        inner = info.get(holder)
+        if isinstance(inner, dict) and key in inner:
+            return inner[key]
     return default
 
 
-def get_electron_temperature(atoms) -> float:
-    return _get(atoms, 'etemperature', 0.0)
+def _accessors(key):
+    def getter(atoms) -> float:
+        return _lookup(atoms, key)
+
+    def setter(atoms, value: float):
+        atoms.info[key] = value
+    getter.__doc__ = f"`{key}` of the structure (0.0 when absent)."
+    setter.__doc__ = f"Store `{key}` in `atoms.info`."
+    return getter, setter
 
 
-def set_electron_temperature(atoms, t: float):
-    atoms.info['etemperature'] = t
-
-
-def get_electron_entropy(atoms) -> float:
-    return _get(atoms, 'eentropy', 0.0)
-
-
-def set_electron_entropy(atoms, eentropy: float):
-    atoms.info['eentropy'] = eentropy
-
-
-def get_kinetic_energy(atoms) -> float:
-    return _get(atoms, 'kinetic_energy', 0.0)
-
-
-def set_kinetic_energy(atoms, ke: float):
-    atoms.info['kinetic_energy'] = ke
+get_electron_temperature, set_electron_temperature = _accessors('etemperature')
+get_electron_entropy, set_electron_entropy = _accessors('eentropy')
+get_kinetic_energy, set_kinetic_energy = _accessors('kinetic_energy')
