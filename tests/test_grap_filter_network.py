@@ -279,3 +279,29 @@ def test_closed_form_descriptors_on_the_torch_path_equal_the_kernel_formulation(
                                    torch.as_tensor(st['cell']), i, j, S, rc, algorithm, grid,
                                    (0, 1, 2), cutoff)
         assert float((G - ref).abs().max()) < 1e-10 * max(1.0, float(ref.abs().max())), algorithm
+
+
+def test_training_loop_with_the_train_op_reduces_the_loss():
+    """trainer.train_step(TrainOp): gradients -> update -> moving averages, end to end on the
+    CPU stand-in; the loss of the fixed batch goes down and the averaged parameters can be
+    written back into the model."""
+    from tensoralloy_b200.nn.opt import OptParameters, TrainOp
+    elements, rc = ['Mo', 'Ni'], 4.5
+    structs = make_structures(2, seed=11)
+    with precision_scope('high'):
+        nn = make_model(elements, rc, 2, False)
+        tr = cpu_trainer(nn, structs, rc)
+        op = TrainOp(tr.params, OptParameters(method='adam', learning_rate=2e-3,
+                                              decay_function='exponential', decay_rate=0.9,
+                                              decay_steps=10))
+        first, _ = tr.train_step(op)
+        for _ in range(40):
+            last, parts = tr.train_step(op)
+        assert op.global_step == 41 and abs(op.learning_rate() - 2e-3 * 0.9 ** 4.1) < 1e-15
+        assert last.item() < 0.9 * first.item(), (first.item(), last.item())
+        assert set(parts) == {'energy', 'forces', 'stress'}
+        before = nn.get_variable("Atomic/Filters/Output/kernel").copy()
+        op.swap_in_ema()
+        tr.sync_to_model()
+        after = nn.get_variable("Atomic/Filters/Output/kernel")
+        assert after.shape == before.shape and not np.array_equal(after, before)
