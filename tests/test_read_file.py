@@ -117,3 +117,38 @@ def test_dataset_feeds_a_trainer_and_errors():
         read_file('x.db')
     with pytest.raises(ValueError, match="stepmax"):
         read_file(os.path.join(GOLD, 'B28_2frames.xyz'), file_type='stepmax')
+
+
+def test_read_vasp_xml():
+    # io/tests/test_vasp.py:21-28 (kB / eV of ase.units, CODATA 2014)
+    from tensoralloy_b200 import atoms_utils
+    from tensoralloy_b200.io.vasp import read_vasp_xml
+    kB = 8.6173303e-05
+    atoms = next(read_vasp_xml(os.path.join(GOLD, 'Be_hcp_4000K_vasprun.xml.gz'), index=0))
+    assert abs(atoms_utils.get_electron_temperature(atoms) - 4000.0 * kB) < 1e-6
+    assert abs(atoms_utils.get_electron_entropy(atoms) - 0.2210591) < 1e-6
+    info = atoms.info
+    assert info['forces'].shape == (len(atoms), 3) and info['stress'].shape == (6,)
+    assert set(atoms.get_chemical_symbols()) == {'Be'} and atoms.pbc.all()
+    # E(sigma -> 0) lies between the free energy F and the internal energy U = F + sigma S
+    hot = next(read_vasp_xml(os.path.join(GOLD, 'Be_hcp_4000K_vasprun.xml.gz'), index=0,
+                             finite_temperature=True))
+    U, F = hot.info['energy'], hot.info['free_energy']
+    assert abs(U - (F + 0.2210591 * 4000.0 * kB)) < 1e-5
+    assert F < info['energy'] < U
+    assert abs(info['energy'] - 0.5 * (U + F)) < 1e-3        # first-order smearing correction
+    # positions: scaled coordinates times the cell of the same step
+    assert np.all(np.linalg.solve(atoms.cell.T, atoms.positions.T).T < 1.0 + 1e-9)
+
+
+def test_read_vasp_md_xml():
+    # io/tests/test_vasp.py:31-39
+    from tensoralloy_b200.atoms_utils import get_kinetic_energy
+    from tensoralloy_b200.io.vasp import read_vasp_xml
+    path = os.path.join(GOLD, 'Be_md_vasprun.xml.gz')
+    trajectory = list(read_vasp_xml(path, index=slice(0, 10), finite_temperature=True))
+    assert len(trajectory) == 10
+    assert abs(get_kinetic_energy(trajectory[4]) - 48.64234933) < 1e-8
+    assert len(list(read_vasp_xml(path, index=[0, 3]))) == 2
+    last = next(read_vasp_xml(path))                           # index = -1
+    assert np.array_equal(last.positions, trajectory[9].positions)
