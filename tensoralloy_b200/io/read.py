@@ -66,6 +66,26 @@ class Dataset:
         self.images = list(images)
         self.metadata = dict(metadata)
 
+    @classmethod
+    def from_images(cls, images, extxyz=True):
+        """A dataset over labelled `Atoms` from any reader (e.g. `io.vasp.read_vasp_xml`):
+        every `atoms.info` holds at least `energy`; missing forces become zeros; the
+        metadata dict is rebuilt as `read_file` would (read.py:178-187)."""
+        images = list(images)
+        max_occurs, periodic = Counter(), False
+        use_stress = bool(images) and all('stress' in a.info for a in images)
+        for k, atoms in enumerate(images):
+            if 'energy' not in atoms.info:
+                raise ValueError(f"structure {k} has no energy label")
+            if 'forces' not in atoms.info:
+                atoms.info['forces'] = np.zeros_like(atoms.positions)
+            periodic = bool(np.any(atoms.pbc)) or periodic
+            for symbol, cnt in Counter(atoms.get_chemical_symbols()).items():
+                max_occurs[symbol] = max(max_occurs[symbol], cnt)
+        return cls(images, {'max_occurs': dict(max_occurs), 'extxyz': extxyz, 'forces': True,
+                            'stress': use_stress, 'periodic': periodic,
+                            'unit_conversion': {'energy': 1.0, 'forces': 1.0, 'stress': 1.0}})
+
     max_occurs = property(lambda self: Counter(self.metadata['max_occurs']))
     has_stress = property(lambda self: bool(self.metadata.get('stress')))
     has_periodic_structures = property(lambda self: bool(self.metadata.get('periodic')))

@@ -152,3 +152,14 @@ def test_read_vasp_md_xml():
     assert len(list(read_vasp_xml(path, index=[0, 3]))) == 2
     last = next(read_vasp_xml(path))                           # index = -1
     assert np.array_equal(last.positions, trajectory[9].positions)
+
+
+def test_dataset_from_vasp_trajectory():
+    from tensoralloy_b200.io.vasp import read_vasp_xml
+    db = Dataset.from_images(read_vasp_xml(os.path.join(GOLD, 'Be_md_vasprun.xml.gz'),
+                                           index=slice(0, 3), finite_temperature=True))
+    assert len(db) == 3 and db.has_stress and db.has_periodic_structures
+    assert list(db.max_occurs) == ['Be'] and db.max_occurs['Be'] == len(db[0])
+    e, f, s = db.labels(1)
+    assert f.shape == (len(db[1]), 3) and s.shape == (6,) and np.isfinite(e)
+    assert db[1].info['etemperature'] > 0.0
