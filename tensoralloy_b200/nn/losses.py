@@ -97,3 +97,17 @@ def pressure_loss(labels, predictions, weight=1.0, method='rmse'):
     if labels.dim() != 1 or predictions.dim() != 1:
         raise ValueError("pressure loss: rank-1 tensors expected")
     return weight * _raw(method, labels, predictions, ('rmse', 'logcosh'))
+
+
+def l2_regularization_loss(variables, l2_weight, weight=0.0, decayed=True, decay_rate=0.99,
+                           decay_steps=1000, global_step=0):
+    """losses.py:507-550 with the layers' regulariser (convolutional.py:207-210, 262-265:
+    `l2_regularizer(l2_weight)` on every kernel and bias = l2_weight * sum(w^2) / 2): the sum
+    over `variables`, times the option weight, which decays exponentially in the global step
+    (`L2LossOptions`, dataclasses.py:158-166).  Returns None for weight 0, as the reference."""
+    if weight == 0.0:
+        return None
+    total = sum(0.5 * l2_weight * torch.sum(v * v) for v in variables)
+    if decayed:
+        weight = weight * decay_rate ** (float(global_step) / float(decay_steps))
+    return weight * total

@@ -105,3 +105,15 @@ def test_other_loss_methods_and_dynamic_weights():
     assert abs(losses.dynamic_weight((1.0, 100.0), 500, 1000, logscale=True) - 10.0) < 1e-12
     with pytest.raises(ValueError, match="max_train_steps"):
         losses.dynamic_weight((1.0, 2.0), 3)
+
+
+def test_l2_regularization_loss():
+    # losses.py:507-550: weight 0 -> None; decayed weight = w * rate^(step / steps)
+    ws = [torch.tensor([[1.0, -2.0], [0.5, 0.0]]), torch.tensor([3.0])]
+    assert losses.l2_regularization_loss(ws, 0.01) is None
+    raw = 0.5 * 0.01 * (1 + 4 + 0.25 + 9)
+    got = losses.l2_regularization_loss(ws, 0.01, weight=0.2, decayed=False).item()
+    assert abs(got - 0.2 * raw) < 1e-9
+    got = losses.l2_regularization_loss(ws, 0.01, weight=0.2, decay_rate=0.5, decay_steps=100,
+                                        global_step=200).item()
+    assert abs(got - 0.2 * 0.25 * raw) < 1e-9
