@@ -111,3 +111,26 @@ def l2_regularization_loss(variables, l2_weight, weight=0.0, decayed=True, decay
     if decayed:
         weight = weight * decay_rate ** (float(global_step) / float(decay_steps))
     return weight * total
+
+
+def adaptive_sample_weight(true_forces, sid, n_struct, metric, method, *args):
+    """losses.py:553-586: a per-structure sample weight that shrinks for structures with very
+    large forces.  true_forces [total atoms, 3] with `sid` [total atoms] = structure of each
+    atom (the unpadded form of the reference's [batch, N + 1, 3]).
+      metric 'norm'  f = sqrt(sum |F|^2 / n_atoms)      'fmax'  f = max |F_ia|
+      method 'sigmoid', args = (slope, center, wmax, wmin):  wmin + wmax sigmoid(slope (center - f))"""
+    if metric == 'norm':
+        sq = torch.zeros(n_struct, dtype=true_forces.dtype, device=true_forces.device)
+        sq = sq.index_add(0, sid, torch.sum(true_forces * true_forces, dim=1))
+        n = torch.bincount(sid, minlength=n_struct).to(true_forces.dtype)
+        f = torch.sqrt(torch.where(n > 0, sq / torch.clamp(n, min=1.0), torch.zeros_like(sq)))
+    elif metric == 'fmax':
+        f = torch.zeros(n_struct, dtype=true_forces.dtype, device=true_forces.device)
+        f = f.scatter_reduce(0, sid, true_forces.abs().amax(dim=1), reduce='amax',
+                             include_self=True)
+    else:
+        raise ValueError("Only the norm and fmax metric is implemented")
+    if method != 'sigmoid':
+        raise ValueError("Only the sigmoid method is implemented")
+    slope, center, wmax, wmin = [float(a) for a in args]
+    return torch.sigmoid(slope * (center - f)) * wmax + wmin

@@ -117,3 +117,25 @@ def test_l2_regularization_loss():
     got = losses.l2_regularization_loss(ws, 0.01, weight=0.2, decay_rate=0.5, decay_steps=100,
                                         global_step=200).item()
     assert abs(got - 0.2 * 0.25 * raw) < 1e-9
+
+
+def test_adaptive_sample_weight():
+    # losses.py:553-586
+    import pytest
+    rng = np.random.default_rng(5)
+    n_atoms = [4, 2, 5]
+    F = [rng.normal(scale=s, size=(n, 3)) for n, s in zip(n_atoms, (0.1, 3.0, 1.0))]
+    sid = torch.tensor(np.repeat(np.arange(3), n_atoms))
+    t = torch.tensor(np.concatenate(F))
+    args = (2.0, 1.0, 0.9, 0.1)
+    w = losses.adaptive_sample_weight(t, sid, 3, 'norm', 'sigmoid', *args).numpy()
+    f = np.array([np.sqrt((x ** 2).sum() / len(x)) for x in F])
+    assert np.allclose(w, 0.1 + 0.9 / (1 + np.exp(-2.0 * (1.0 - f))), atol=1e-14)
+    w = losses.adaptive_sample_weight(t, sid, 3, 'fmax', 'sigmoid', *args).numpy()
+    f = np.array([np.abs(x).max() for x in F])
+    assert np.allclose(w, 0.1 + 0.9 / (1 + np.exp(-2.0 * (1.0 - f))), atol=1e-14)
+    assert w[1] < w[2] < w[0]                          # large forces -> small weight
+    with pytest.raises(ValueError, match="norm and fmax"):
+        losses.adaptive_sample_weight(t, sid, 3, 'mean', 'sigmoid', *args)
+    with pytest.raises(ValueError, match="sigmoid"):
+        losses.adaptive_sample_weight(t, sid, 3, 'norm', 'linear', *args)
