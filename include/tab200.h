@@ -121,6 +121,22 @@ int tab_nbr_batch_size(const tab_nbr *nbr);   /* 0 = single structure */
 int tab_nbr_update(tab_nbr *nbr, const double *d_pos, const double *h_cell,
                    void *stream);
 
+/* MD-valid list reuse.  The reference rebuilds its lists on every call
+ * (transformer/universal.py:58, one ase neighbor_list per get_np_feed_dict).  A handle with a
+ * skin builds its lists with the radius rc + skin; the EAM / ADP pair kernels mask r >= rc
+ * (entries beyond the model's cutoff contribute exactly 0; the symmetry-function kernels are
+ * masked by their cutoff function), so that tab_nbr_update + evaluation equals a fresh build +
+ * evaluation as long as no atom has moved further than skin / 2 since the build.
+ *   tab_nbr_set_skin          sticky; takes effect at the next build (0 = exact lists)
+ *   tab_nbr_max_displacement  largest |R - R_build| seen by the LAST tab_nbr_update (0 right
+ *                             after a build); synchronises the stream (4-byte read-back);
+ *                             *h_skin (may be NULL) receives the skin of the current lists.
+ *                             A caller rebuilds when 2 * max_disp > skin.
+ * Lists with a skin are refused by the consumers that hand list entries to the caller
+ * (tab_nbr_export, tab_pairs_export, tab_eam_hessian): build those with skin = 0. */
+int tab_nbr_set_skin(tab_nbr *nbr, double skin);
+int tab_nbr_max_displacement(tab_nbr *nbr, double *h_max_disp, double *h_skin, void *stream);
+
 /* Sizes, the quantities of neighbor.py:34-47 NeighborSize.  nij = number of
  * directed pairs; nnl_max = max neighbours of one atom (all species);
  * n_ext = owned + ghost atoms held on the device. */

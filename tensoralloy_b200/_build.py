@@ -7,8 +7,10 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 CSRC = ROOT / 'tensoralloy_b200' / 'csrc'
 SOURCES = ['scan.cu', 'nbr.cu', 'eam.cu', 'sf.cu', 'hessian.cu', 'pairs.cu']
+# -cudart shared: the library carries no private copy of the CUDA runtime (and none of its
+# entry-point tables); it uses the libcudart.so.12 already loaded by torch / the system one
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3',
-              '-std=c++17', '-Xcompiler', '-fPIC', '-shared']
+              '-std=c++17', '-Xcompiler', '-fPIC', '-shared', '-cudart', 'shared']
 
 
 def _nvcc():
@@ -27,12 +29,14 @@ def needs_build():
     return any(d.stat().st_mtime > out.stat().st_mtime for d in deps)
 
 
-def build_library(force=False, verbose=False):
-    out = CSRC / 'libtab200.so'
-    if not force and not needs_build():
+def build_library(force=False, verbose=False, defines=(), out_name='libtab200.so'):
+    """`defines` / `out_name`: A/B variants of the kernels (tools/var_bench.sh), selected at
+    run time with TAB200_LIB."""
+    out = CSRC / out_name
+    if not force and out_name == 'libtab200.so' and not needs_build():
         return out
-    cmd = [_nvcc()] + NVCC_FLAGS + [f'-I{ROOT / "include"}', f'-I{CSRC}',
-                                   '-o', str(out)] + [str(CSRC / s) for s in SOURCES]
+    cmd = [_nvcc()] + NVCC_FLAGS + [f'-D{d}' for d in defines] + \
+        [f'-I{ROOT / "include"}', f'-I{CSRC}', '-o', str(out)] + [str(CSRC / s) for s in SOURCES]
     if verbose:
         cmd.insert(1, '-Xptxas')
         cmd.insert(2, '-v')

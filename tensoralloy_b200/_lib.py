@@ -107,6 +107,7 @@ EXPORTS = [
     'tab_nbr_build_batch', 'tab_nbr_batch_size',
     'tab_pairs_export', 'tab_pair_forces', 'tab_pair_jvp', 'tab_atomic_eval_dd', 'tab_eam_eval_dd', 'tab_eam_tabulate',
     'tab_profile_enable', 'tab_profile_read',
+    'tab_nbr_set_skin', 'tab_nbr_max_displacement',
 ]
 
 
@@ -133,6 +134,8 @@ def lib():
     L.tab_nbr_build_dd.argtypes = [vp, i32, i32, vp, vp, C.POINTER(dbl),
                                    C.POINTER(dbl), C.POINTER(i32), dbl, vp]
     L.tab_nbr_update.argtypes = [vp, vp, C.POINTER(dbl), vp]
+    L.tab_nbr_set_skin.argtypes = [vp, dbl]
+    L.tab_nbr_max_displacement.argtypes = [vp, C.POINTER(dbl), C.POINTER(dbl), vp]
     L.tab_nbr_build_batch.argtypes = [vp, i32, C.POINTER(i32), vp, vp, C.POINTER(dbl),
                                       C.POINTER(i32), dbl, vp]
     L.tab_nbr_batch_size.argtypes = [vp]
@@ -301,6 +304,35 @@ class NeighborList:
         c = _cell9(cell) if cell is not None else None
         check(lib().tab_nbr_update(self._h, _ptr(d_pos), c, _stream()),
               'tab_nbr_update')
+
+    def set_skin(self, skin):
+        """Lists of the NEXT build get the radius rc + skin; the pair kernels mask r >= rc
+        (include/tab200.h: MD-valid list reuse)."""
+        check(lib().tab_nbr_set_skin(self._h, float(skin)), 'tab_nbr_set_skin')
+        self.skin = float(skin)
+
+    def max_displacement(self):
+        """(largest |R - R_build| of the last update, skin of the current lists)."""
+        d, s = C.c_double(), C.c_double()
+        check(lib().tab_nbr_max_displacement(self._h, C.byref(d), C.byref(s), _stream()),
+              'tab_nbr_max_displacement')
+        return float(d.value), float(s.value)
+
+    def step(self, d_pos, d_types, cell, pbc, rc):
+        """One MD step of the lists: refresh the positions; rebuild when an atom has moved more
+        than half the skin since the last build (always, for lists without a skin).  Returns
+        True when the lists were rebuilt.  The result of the following evaluation equals the
+        one on freshly built lists (the reference's semantics, universal.py:58)."""
+        if self.n != int(d_pos.shape[0]) or getattr(self, 'skin', 0.0) <= 0.0 or \
+                self.n_struct > 0:
+            self.build(d_pos, d_types, cell, pbc, rc)
+            return True
+        self.update(d_pos)
+        disp, skin = self.max_displacement()
+        if not (2.0 * disp <= skin):
+            self.build(d_pos, d_types, cell, pbc, rc)
+            return True
+        return False
 
     def sizes(self):
         nij, nnl, next_ = C.c_int64(), C.c_int32(), C.c_int32()

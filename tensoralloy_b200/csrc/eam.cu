@@ -49,6 +49,10 @@ static void zterm_fold(ZTerm &t, double a, double b, double c, double re) {
     t.nb_re = -b / re;
 }
 
+struct ZPair;
+static ZPair *eamz_new_pair(const Zhou1 &z);
+static void eamz_free_pair(ZPair *p);
+
 struct tab_model {
     int family = 0;        // 0 = EAM
     int kind = 0;
@@ -58,6 +62,7 @@ struct tab_model {
     bool no_hessian = false;   // some function kind has no second-derivative evaluator
     Zhou1 z1;              // fe, beta, lamda, 1/re, A, alpha, kappa, B + folded terms
     bool z1_folded = false;   // prefactors positive: the folded float64 terms are usable
+    struct ZPair *zp = nullptr;   // the same, in the form of the lane-split kernels (eam_fast.cuh)
     DevBuf tables;         // tab_fn [2*n_el*n_el + n_el (+ 2*n_el*n_el)]
     DevBuf pool;           // spline coefficients
     tab_fn embed0;         // host copy (fast path epilogue parameters)
@@ -169,7 +174,7 @@ k_eam_rho(int n, const Atom4 *__restrict__ atoms,
           const int *__restrict__ perm, EamDev m, Zhou1 z, tab_fn embed0,
           double *__restrict__ fprime, double *__restrict__ fembed,
           double *__restrict__ fprime_caller, double2 *__restrict__ pcache,
-          const int *__restrict__ blk_first) {
+          const int *__restrict__ blk_first, double rcm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     tab_fn *tabs = reinterpret_cast<tab_fn *>(smem_raw);
     __shared__ double s_etab[TAB_EXP_TAB];
@@ -205,7 +210,8 @@ k_eam_rho(int n, const Atom4 *__restrict__ atoms,
             const int tj = (int)(c >> TAB_COL_TYPE_SHIFT);
             eval_pair_fn<Real, NN>(tabs[ti * m.n_el + tj], r, f, df, m.pool);
         }
-        rho += f;
+        // lists with a skin: entries beyond the model's cutoff contribute exactly 0
+        rho += (double)r < rcm ? f : Real(0);
     }
     if (FAST && !(sizeof(Real) == 8 && !CACHE)) rho *= (Real)z.fe;
     Real F, dF;
@@ -226,12 +232,13 @@ __global__ void k_spread_w(int n_owned, int n_loc, int n_ext,
                            const double *__restrict__ halo_v,
                            const int *__restrict__ perm,
                            const int *__restrict__ ghost_owner,
-                           Atom4 *__restrict__ atoms) {
+                           Atom4 *__restrict__ atoms, double scale = 1.0, double shift = 0.0) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_ext) return;
     const int o = e < n_loc ? e : ghost_owner[e - n_loc];
     // halo_v == NULL (recompute mode): F' of the outer halo is never needed by an own atom
-    atoms[e].w = o < n_owned ? v[o] : (halo_v ? halo_v[perm[o] - n_owned] : 0.0);
+    const double fp = o < n_owned ? v[o] : (halo_v ? halo_v[perm[o] - n_owned] : 0.0);
+    atoms[e].w = fma(fp, scale, shift);      // (1, 0): F' itself; the lane-split kernels fold
 }
 
 // ---------------------------------------------------------------------------
@@ -246,7 +253,7 @@ k_eam_force(int n, const Atom4 *__restrict__ atoms,
             const double *__restrict__ fembed, double *__restrict__ eatom,
             double *__restrict__ forces, double *__restrict__ partial,
             const double2 *__restrict__ pcache, const int *__restrict__ blk_first,
-            const int *__restrict__ own_mask) {
+            const int *__restrict__ own_mask, double rcm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     tab_fn *tabs = reinterpret_cast<tab_fn *>(smem_raw);
     __shared__ double red[EAM_T / 32][7];
@@ -308,6 +315,10 @@ k_eam_force(int n, const Atom4 *__restrict__ atoms,
                 else eval_pair_fn<Real, NN>(tabs[tj * m.n_el + ti], r, rji, drji, m.pool);
                 eval_pair_fn<Real, NN>(tabs[nn + ti * m.n_el + tj], r, phi, dphi, m.pool);
                 der = fpi * drij + fpj * drji + dphi;
+            }
+            if (!((double)r < rcm)) {      // beyond the model's cutoff (skin)
+                der = Real(0);
+                phi = Real(0);
             }
             const Real s = der * rinv;
             const Real gx = s * dx, gy = s * dy, gz = s * dz;
@@ -373,7 +384,7 @@ k_adp_rho(int n, const Atom4 *__restrict__ atoms,
           const uint8_t *__restrict__ types_ext, const int *__restrict__ counts,
           const uint32_t *__restrict__ slice_ptr, const uint32_t *__restrict__ col,
           EamDev m, double *__restrict__ fprime, double *__restrict__ fembed,
-          double *__restrict__ moments, const int *__restrict__ blk_first) {
+          double *__restrict__ moments, const int *__restrict__ blk_first, double rcm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     tab_fn *tabs = reinterpret_cast<tab_fn *>(smem_raw);
     const int nn = m.n_el * m.n_el;
@@ -401,6 +412,7 @@ k_adp_rho(int n, const Atom4 *__restrict__ atoms,
         eval_pair_fn<Real, NN>(tabs[ti * m.n_el + tj], r, f, df, m.pool);
         eval_pair_fn<Real, NN>(t_dip[ti * m.n_el + tj], r, u, du, m.pool);
         eval_pair_fn<Real, NN>(t_quad[ti * m.n_el + tj], r, w, dw, m.pool);
+        if (!((double)r < rcm)) f = u = w = Real(0);
         rho += f;
 #pragma unroll
         for (int t = 0; t < ADP_MAX_EL; ++t) {
@@ -459,7 +471,7 @@ k_adp_force(int n, const Atom4 *__restrict__ atoms,
             const double *__restrict__ moments, const double *__restrict__ fembed,
             double *__restrict__ eatom, double *__restrict__ forces,
             double *__restrict__ partial, const int *__restrict__ blk_first,
-            const int *__restrict__ own_mask) {
+            const int *__restrict__ own_mask, double rcm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     tab_fn *tabs = reinterpret_cast<tab_fn *>(smem_raw);
     __shared__ double red[EAM_T / 32][7];
@@ -495,6 +507,8 @@ k_adp_force(int n, const Atom4 *__restrict__ atoms,
             eval_pair_fn<Real, NN>(tabs[nn + ti * m.n_el + tj], r, phi, dphi, m.pool);
             eval_pair_fn<Real, NN>(t_dip[ti * m.n_el + tj], r, u, du, m.pool);
             eval_pair_fn<Real, NN>(t_quad[ti * m.n_el + tj], r, w, dw, m.pool);
+            if (!((double)r < rcm))
+                drij = drji = phi = dphi = u = du = w = dw = Real(0);
             // EAM part, symmetric in the pair
             const Real s = (fpi * drij + fpj * drji + dphi) * rinv;
             Real gx = s * dx, gy = s * dy, gz = s * dz;
@@ -726,6 +740,7 @@ extern "C" int tab_eam_create(tab_model **out, int32_t kind, int32_t n_el,
             zterm_fold(z.t_a, z.A, z.alpha, z.kappa, re);
             zterm_fold(z.t_b, z.B, z.beta, z.lamda, re);
             z.fe_over_B = z.fe / z.B;
+            m->zp = eamz_new_pair(z);
         }
     }
     *out = m;
@@ -771,6 +786,7 @@ extern "C" int tab_model_free(tab_model *m) {
     if (!m) return TAB_OK;
     m->tables.release();
     m->pool.release();
+    eamz_free_pair(m->zp);
     delete m;
     return TAB_OK;
 }
@@ -827,6 +843,7 @@ struct EamLaunch {
     const int *blk_first;    // batch handles: blocks cut at structure boundaries, else NULL
     const int *struct_blk;
     int n_red;               // grid of k_reduce_partials (1, or the number of structures)
+    double rcm;              // mask radius: +inf, or the model's cutoff for lists with a skin
 };
 
 // batch handles: the pair-kernel block table for blocks of EAM_T atoms (cached in nbr)
@@ -878,6 +895,7 @@ static int eam_prepare(tab_model *m, tab_nbr *nbr, bool fast, EamLaunch &L,
     L.dev.embed = L.dev.rho + 2 * nn;
     L.dev.pool = m->pool.as<double>();
     L.z = m->z1;
+    L.rcm = nbr->skin_built > 0.0 ? nbr->rc_model : (double)INFINITY;
     L.smem = fast ? 0 : (size_t)(2 * nn + m->n_el) * sizeof(tab_fn);
     return TAB_OK;
 }
@@ -895,11 +913,140 @@ static bool pair_cache_enabled() {
     return on == 1;
 }
 
+// the float64 fast path folds prefactors into exponents and drops the underflow guard
+static bool zhou1_f64_ok(const tab_model *m, const tab_nbr *nbr) {
+    if (!m->zhou1 || !m->z1_folded) return false;
+    const double xmax = nbr->grid.rc * m->z1.re;
+    const double bmax = m->z1.alpha > m->z1.beta ? m->z1.alpha : m->z1.beta;
+    return bmax * (xmax + 1.0) < 600.0;
+}
+
+// ---------------------------------------------------------------------------
+// lane-split kernels of the single-element zjw04 model (eam_fast.cuh)
+// ---------------------------------------------------------------------------
+#include "eam_fast.cuh"
+
+static ZPair *eamz_new_pair(const Zhou1 &z) {
+    ZPair *p = new ZPair();
+    zpair_fold(*p, z);
+    return p;
+}
+static void eamz_free_pair(ZPair *p) { delete p; }
+
+static int env_int(const char *name, int dflt) {
+    const char *e = getenv(name);
+    return e && *e ? atoi(e) : dflt;
+}
+
+// lanes per atom of the fast kernels (TAB_EAMZ_L = 1 | 2 | 4 | 8 for A/B runs; 0 = the
+// thread-per-atom kernels of round 1)
+// (read on every call: the tests and the A/B tools switch them inside one process)
+static int eamz_lanes() {
+    const int L = env_int("TAB_EAMZ_L", EAMZ_L);
+    return (L == 0 || L == 1 || L == 2 || L == 4 || L == 8) ? L : EAMZ_L;
+}
+static int eamz_vir() { return env_int("TAB_EAMZ_VIR", EAMZ_VIR) ? 1 : 0; }
+
+static bool eamz_usable(const tab_model *m, const tab_nbr *nbr, int precision) {
+    if (eamz_lanes() == 0 || !m->zhou1 || !m->z1_folded || !m->zp || nbr->n_struct > 0)
+        return false;
+    if (precision == TAB_PRECISION_HIGH) return zhou1_f64_ok(m, nbr);
+    // float32: exponents of the three terms must stay inside ex2's range
+    return zhou1_f64_ok(m, nbr) && (m->z1.alpha > m->z1.beta ? m->z1.alpha : m->z1.beta) *
+                                           (nbr->grid.rc * m->z1.re + 1.0) < 80.0;
+}
+
+static QScale eamz_qscale(const tab_model *m, const tab_nbr *nbr) {
+    QScale q;
+    const double d = nbr->q_delta;
+    q.x_per_q = (float)(d * m->z1.re);
+    q.eps_q = (float)(1e-8 / (d * d));
+    q.rc2_q = (float)(tab_mask_rc2(nbr) / (d * d));
+    q.pad_ = 0.f;
+    q.ox = nbr->q_origin[0];
+    q.oy = nbr->q_origin[1];
+    q.oz = nbr->q_origin[2];
+    q.ddelta = d;
+    return q;
+}
+
+#define EAMZ_FOR_L(L_, CALL)                        \
+    switch (L_) {                                   \
+    case 1: { constexpr int LL = 1; CALL; } break;  \
+    case 2: { constexpr int LL = 2; CALL; } break;  \
+    case 4: { constexpr int LL = 4; CALL; } break;  \
+    default: { constexpr int LL = 8; CALL; } break; \
+    }
+
+template <int L>
+static int eamz_pass1_L(tab_model *m, tab_nbr *nbr, int precision, double *d_fprime_caller,
+                        double *fprime, double *fembed, cudaStream_t st) {
+    TAB_TRY(ensure_lanesplit<L>(nbr, st));
+    const int n = nbr->n;
+    constexpr int G = 32 / L;
+    const long long threads = (long long)((n + G - 1) / G) * 32;
+    const int nblk = (int)((threads + EAMZ_T - 1) / EAMZ_T);
+    if (precision == TAB_PRECISION_HIGH) {
+        k_eamz_rho<L><<<nblk, EAMZ_T, 0, st>>>(
+            n, nbr->atoms.as<Atom4>(), nbr->ls_ptr.as<uint32_t>(),
+            nbr->ls_col.as<uint32_t>(), nbr->perm.as<int>(), *m->zp, tab_mask_rc2(nbr),
+            m->embed0, fprime, fembed, d_fprime_caller);
+    } else {
+        TAB_TRY(tab_nbr_ensure_rec16(nbr, st));
+        k_eamz_rho_f32<L><<<nblk, EAMZ_T, 0, st>>>(
+            n, nbr->rec16.as<Rec16>(), nbr->ls_ptr.as<uint32_t>(),
+            nbr->ls_col.as<uint32_t>(), nbr->perm.as<int>(), *m->zp, eamz_qscale(m, nbr),
+            m->embed0, fprime, fembed, d_fprime_caller);
+    }
+    TAB_LAUNCH_CHECK();
+    return TAB_OK;
+}
+
+template <int L>
+static int eamz_pass2_L(tab_model *m, tab_nbr *nbr, int precision, const double *fembed,
+                        double *d_eatom, double *d_forces, const int *d_own_mask, int *nblk_out,
+                        cudaStream_t st) {
+    TAB_TRY(ensure_lanesplit<L>(nbr, st));
+    const int n = nbr->n;
+    constexpr int G = 32 / L;
+    const long long threads = (long long)((n + G - 1) / G) * 32;
+    const int nblk = (int)((threads + EAMZ_T - 1) / EAMZ_T);
+    *nblk_out = nblk;
+    TAB_TRY(nbr->partial.ensure(sizeof(double) * 8 * (size_t)nblk));
+    // the F (x) R form needs both rows of a real pair in this rank's sums: not with an own-mask
+    const bool vir = eamz_vir() && !d_own_mask;
+    if (precision == TAB_PRECISION_HIGH) {
+        auto k = vir ? k_eamz_force<L, 1> : k_eamz_force<L, 0>;
+        k<<<nblk, EAMZ_T, 0, st>>>(
+            n, nbr->n, nbr->atoms.as<Atom4>(),
+            nbr->ls_ptr.as<uint32_t>(), nbr->ls_col.as<uint32_t>(), nbr->perm.as<int>(), *m->zp,
+            tab_mask_rc2(nbr), fembed, d_eatom, d_forces, nbr->partial.as<double>(), d_own_mask);
+    } else {
+        auto k = vir ? k_eamz_force_f32<L, 1> : k_eamz_force_f32<L, 0>;
+        k<<<nblk, EAMZ_T, 0, st>>>(
+            n, nbr->n, nbr->rec16.as<Rec16>(),
+            nbr->ls_ptr.as<uint32_t>(), nbr->ls_col.as<uint32_t>(), nbr->perm.as<int>(), *m->zp,
+            eamz_qscale(m, nbr), fembed, d_eatom, d_forces, nbr->partial.as<double>(),
+            d_own_mask);
+    }
+    TAB_LAUNCH_CHECK();
+    return TAB_OK;
+}
+
 template <typename Real, bool FAST>
 static int eam_pass1(tab_model *m, tab_nbr *nbr, double *d_fprime_caller,
                      cudaStream_t st) {
     EamLaunch L;
     TAB_TRY(eam_prepare(m, nbr, FAST, L, st));
+    const int prec = sizeof(Real) == 8 ? TAB_PRECISION_HIGH : TAB_PRECISION_MEDIUM;
+    if (FAST && eamz_usable(m, nbr, prec)) {
+        nbr->pcache_valid = false;
+        prof_mark(0, st);
+        EAMZ_FOR_L(eamz_lanes(), TAB_TRY(eamz_pass1_L<LL>(m, nbr, prec, d_fprime_caller,
+                                                          L.fprime, L.fembed, st)));
+        prof_mark(1, st);
+        return TAB_OK;
+    }
     const bool cache = FAST && sizeof(Real) == 8 && pair_cache_enabled();
     if (cache) TAB_TRY(nbr->pcache.ensure(sizeof(double2) * 32 * (size_t)(nbr->ell_rows + 1)));
     nbr->pcache_valid = false;
@@ -910,19 +1057,19 @@ static int eam_pass1(tab_model *m, tab_nbr *nbr, double *d_fprime_caller,
             nbr->n, nbr->atoms.as<Atom4>(), nbr->types_ext.as<uint8_t>(),
             nbr->counts.as<int>(), nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>(),
             nbr->perm.as<int>(), L.dev, L.z, m->embed0, L.fprime, L.fembed,
-            d_fprime_caller, nbr->pcache.as<double2>(), L.blk_first);
+            d_fprime_caller, nbr->pcache.as<double2>(), L.blk_first, L.rcm);
     else if (!FAST && m->has_mlp_fn)
         k_eam_rho<Real, false, false, true><<<L.nblk, EAM_T, L.smem, st>>>(
             nbr->n, nbr->atoms.as<Atom4>(), nbr->types_ext.as<uint8_t>(),
             nbr->counts.as<int>(), nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>(),
             nbr->perm.as<int>(), L.dev, L.z, m->embed0, L.fprime, L.fembed,
-            d_fprime_caller, nullptr, L.blk_first);
+            d_fprime_caller, nullptr, L.blk_first, L.rcm);
     else
         k_eam_rho<Real, FAST, false, false><<<L.nblk, EAM_T, L.smem, st>>>(
             nbr->n, nbr->atoms.as<Atom4>(), nbr->types_ext.as<uint8_t>(),
             nbr->counts.as<int>(), nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>(),
             nbr->perm.as<int>(), L.dev, L.z, m->embed0, L.fprime, L.fembed,
-            d_fprime_caller, nullptr, L.blk_first);
+            d_fprime_caller, nullptr, L.blk_first, L.rcm);
     TAB_LAUNCH_CHECK();
     nbr->pcache_valid = cache;
     prof_mark(1, st);
@@ -939,6 +1086,34 @@ static int eam_pass2(tab_model *m, tab_nbr *nbr, const double *d_fprime_halo,
         tab_set_error("tab_eam_pass2: halo atoms present but no halo F' given");
         return TAB_EINVAL;
     }
+    const int prec = sizeof(Real) == 8 ? TAB_PRECISION_HIGH : TAB_PRECISION_MEDIUM;
+    if (FAST && eamz_usable(m, nbr, prec)) {
+        // w = F' fe / B - 1/2 (see k_eamz_force)
+        if (prec == TAB_PRECISION_HIGH) {
+            k_spread_w<<<(nbr->n_ext + 255) / 256, 256, 0, st>>>(
+                nbr->n, nbr->n_loc, nbr->n_ext, L.fprime, d_fprime_halo, nbr->perm.as<int>(),
+                nbr->ghost_owner.as<int>(), nbr->atoms.as<Atom4>(), m->zp->fe_over_B, -0.5);
+        } else {
+            TAB_TRY(tab_nbr_ensure_rec16(nbr, st));
+            k_spread_w_rec<<<(nbr->n_ext + 255) / 256, 256, 0, st>>>(
+                nbr->n, nbr->n_loc, nbr->n_ext, L.fprime, d_fprime_halo, nbr->perm.as<int>(),
+                nbr->ghost_owner.as<int>(), m->zp->fe_over_B, -0.5, nbr->rec16.as<Rec16>());
+        }
+        TAB_LAUNCH_CHECK();
+        prof_mark(2, st);
+        int nblk = 0;
+        EAMZ_FOR_L(eamz_lanes(), TAB_TRY(eamz_pass2_L<LL>(m, nbr, prec, L.fembed, d_eatom,
+                                                          d_forces, d_own_mask, &nblk, st)));
+        prof_mark(3, st);
+        if (d_energy || d_virial) {
+            k_reduce_partials<<<1, 256, 0, st>>>(nblk, nbr->partial.as<double>(), d_energy,
+                                                 d_virial, nullptr);
+            TAB_LAUNCH_CHECK();
+        }
+        prof_mark(4, st);
+        if (g_prof_on && g_prof_calls < PROF_MAX_CALLS) ++g_prof_calls;
+        return TAB_OK;
+    }
     k_spread_w<<<(nbr->n_ext + 255) / 256, 256, 0, st>>>(
         nbr->n, nbr->n_loc, nbr->n_ext, L.fprime, d_fprime_halo, nbr->perm.as<int>(),
         nbr->ghost_owner.as<int>(), nbr->atoms.as<Atom4>());
@@ -951,19 +1126,19 @@ static int eam_pass2(tab_model *m, tab_nbr *nbr, const double *d_fprime_halo,
             nbr->n, nbr->atoms.as<Atom4>(), nbr->types_ext.as<uint8_t>(),
             nbr->counts.as<int>(), nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>(),
             nbr->perm.as<int>(), L.dev, L.z, L.fembed, d_eatom, d_forces,
-            nbr->partial.as<double>(), nbr->pcache.as<double2>(), L.blk_first, d_own_mask);
+            nbr->partial.as<double>(), nbr->pcache.as<double2>(), L.blk_first, d_own_mask, L.rcm);
     else if (!FAST && m->has_mlp_fn)
         k_eam_force<Real, false, false, true><<<L.nblk, EAM_T, L.smem, st>>>(
             nbr->n, nbr->atoms.as<Atom4>(), nbr->types_ext.as<uint8_t>(),
             nbr->counts.as<int>(), nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>(),
             nbr->perm.as<int>(), L.dev, L.z, L.fembed, d_eatom, d_forces,
-            nbr->partial.as<double>(), nullptr, L.blk_first, d_own_mask);
+            nbr->partial.as<double>(), nullptr, L.blk_first, d_own_mask, L.rcm);
     else
         k_eam_force<Real, FAST, false, false><<<L.nblk, EAM_T, L.smem, st>>>(
             nbr->n, nbr->atoms.as<Atom4>(), nbr->types_ext.as<uint8_t>(),
             nbr->counts.as<int>(), nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>(),
             nbr->perm.as<int>(), L.dev, L.z, L.fembed, d_eatom, d_forces,
-            nbr->partial.as<double>(), nullptr, L.blk_first, d_own_mask);
+            nbr->partial.as<double>(), nullptr, L.blk_first, d_own_mask, L.rcm);
     TAB_LAUNCH_CHECK();
     prof_mark(3, st);
     if (d_energy || d_virial) {
@@ -995,7 +1170,7 @@ static int adp_pass1(tab_model *m, tab_nbr *nbr, cudaStream_t st, bool recompute
     kr<<<L.nblk, EAM_T, L.smem, st>>>(
         nbr->n, nbr->atoms.as<Atom4>(), nbr->types_ext.as<uint8_t>(),
         nbr->counts.as<int>(), nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>(),
-        L.dev, L.fprime, L.fembed, nbr->adp.as<double>(), L.blk_first);
+        L.dev, L.fprime, L.fembed, nbr->adp.as<double>(), L.blk_first, L.rcm);
     TAB_LAUNCH_CHECK();
     if (nbr->n_ext > nbr->n_loc) {
         k_adp_spread<<<(nbr->n_ext - nbr->n_loc + 255) / 256, 256, 0, st>>>(
@@ -1024,7 +1199,7 @@ static int adp_pass2(tab_model *m, tab_nbr *nbr, double *d_energy, double *d_eat
         nbr->n, nbr->atoms.as<Atom4>(), nbr->types_ext.as<uint8_t>(),
         nbr->counts.as<int>(), nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>(),
         nbr->perm.as<int>(), L.dev, nbr->adp.as<double>(), L.fembed, d_eatom, d_forces,
-        nbr->partial.as<double>(), L.blk_first, d_own_mask);
+        nbr->partial.as<double>(), L.blk_first, d_own_mask, L.rcm);
     TAB_LAUNCH_CHECK();
     prof_mark(3, st);
     if (d_energy || d_virial) {
@@ -1035,14 +1210,6 @@ static int adp_pass2(tab_model *m, tab_nbr *nbr, double *d_energy, double *d_eat
     prof_mark(4, st);
     if (g_prof_on && g_prof_calls < PROF_MAX_CALLS) ++g_prof_calls;
     return TAB_OK;
-}
-
-// the float64 fast path folds prefactors into exponents and drops the underflow guard
-static bool zhou1_f64_ok(const tab_model *m, const tab_nbr *nbr) {
-    if (!m->zhou1 || !m->z1_folded) return false;
-    const double xmax = nbr->grid.rc * m->z1.re;
-    const double bmax = m->z1.alpha > m->z1.beta ? m->z1.alpha : m->z1.beta;
-    return bmax * (xmax + 1.0) < 600.0;
 }
 
 #define EAM_DISPATCH(FN, ...)                                                        \

@@ -441,6 +441,11 @@ extern "C" int tab_eam_hessian(tab_model *m, tab_nbr *nbr, double *d_hessian,
         tab_set_error("tab_eam_hessian: halo atoms (domain decomposition) not supported");
         return TAB_EUNSUPPORTED;
     }
+    if (nbr->skin_built > 0.0) {
+        tab_set_error("tab_eam_hessian: the lists carry a skin (entries beyond rc); build with "
+                      "skin = 0");
+        return TAB_ESTATE;
+    }
     if (nbr->n_struct > 0) {
         tab_set_error("tab_eam_hessian: batch handles are not supported (one structure per call)");
         return TAB_EUNSUPPORTED;

@@ -132,31 +132,74 @@ __global__ void k_rank_in_cell(int n, const int *__restrict__ cell_of,
     perm_out[start + rank] = i;
 }
 
-__global__ void k_gather_owned(int n, const double *__restrict__ pos,
-                               const int *__restrict__ types, Grid g,
-                               const int *__restrict__ perm,
-                               const int *__restrict__ s0,
-                               Atom4 *__restrict__ atoms,
-                               uint8_t *__restrict__ types_ext) {
+// fixed-point frame of the float32 records (tab_internal.h Rec16); inv_delta == 0: unused
+struct QFrame {
+    double ox, oy, oz, inv_delta;
+};
+
+__device__ __forceinline__ Rec16 make_rec16(const QFrame &q, double x, double y, double z) {
+    Rec16 r;
+    r.qx = __double2int_rn((x - q.ox) * q.inv_delta);
+    r.qy = __double2int_rn((y - q.oy) * q.inv_delta);
+    r.qz = __double2int_rn((z - q.oz) * q.inv_delta);
+    r.w = 0.f;
+    return r;
+}
+
+// REF = 1: build (store the reference positions of the displacement check);
+// REF = 2: refresh (largest squared displacement since the build -> disp[0], float bits)
+template <int REF>
+__global__ void __launch_bounds__(256)
+k_gather_owned(int n, const double *__restrict__ pos, const int *__restrict__ types, Grid g,
+               const int *__restrict__ perm, const int *__restrict__ s0,
+               Atom4 *__restrict__ atoms, uint8_t *__restrict__ types_ext,
+               double *__restrict__ pos_ref, unsigned int *__restrict__ disp, QFrame qf,
+               Rec16 *__restrict__ rec16) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n) return;
-    const int i = perm[idx];
-    double x = pos[3 * i], y = pos[3 * i + 1], z = pos[3 * i + 2];
-    const int s = s0[i];
-    if (s != tab_pack_shift(0, 0, 0)) {
-        int a, b, c;
-        tab_unpack_shift(s, a, b, c);
-        x -= a * g.h[0] + b * g.h[3] + c * g.h[6];
-        y -= a * g.h[1] + b * g.h[4] + c * g.h[7];
-        z -= a * g.h[2] + b * g.h[5] + c * g.h[8];
+    float d2 = 0.f;
+    if (idx < n) {
+        const int i = perm[idx];
+        double x = pos[3 * i], y = pos[3 * i + 1], z = pos[3 * i + 2];
+        const int s = s0[i];
+        if (s != tab_pack_shift(0, 0, 0)) {
+            int a, b, c;
+            tab_unpack_shift(s, a, b, c);
+            x -= a * g.h[0] + b * g.h[3] + c * g.h[6];
+            y -= a * g.h[1] + b * g.h[4] + c * g.h[7];
+            z -= a * g.h[2] + b * g.h[5] + c * g.h[8];
+        }
+        Atom4 r;
+        r.x = x;
+        r.y = y;
+        r.z = z;
+        r.w = 0.0;
+        atoms[idx] = r;
+        if (rec16) rec16[idx] = make_rec16(qf, x, y, z);
+        if (types_ext) types_ext[idx] = types ? (uint8_t)types[i] : (uint8_t)0;
+        if (REF == 1 && pos_ref) {
+            pos_ref[3 * (size_t)idx] = x;
+            pos_ref[3 * (size_t)idx + 1] = y;
+            pos_ref[3 * (size_t)idx + 2] = z;
+        }
+        if (REF == 2 && pos_ref) {
+            const double ex = x - pos_ref[3 * (size_t)idx], ey = y - pos_ref[3 * (size_t)idx + 1],
+                         ez = z - pos_ref[3 * (size_t)idx + 2];
+            // rounded UP: the check must never under-report
+            d2 = __double2float_ru(ex * ex + ey * ey + ez * ez);
+        }
     }
-    Atom4 r;
-    r.x = x;
-    r.y = y;
-    r.z = z;
-    r.w = 0.0;
-    atoms[idx] = r;
-    if (types_ext) types_ext[idx] = types ? (uint8_t)types[i] : (uint8_t)0;
+    if (REF == 2 && disp) {
+        __shared__ float s_mx[8];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) d2 = fmaxf(d2, __shfl_xor_sync(0xffffffffu, d2, d));
+        if ((threadIdx.x & 31) == 0) s_mx[threadIdx.x >> 5] = d2;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < 8; ++w) d2 = fmaxf(d2, s_mx[w]);
+            // non-negative floats order like their bit patterns; NaN (0x7fc00000) sorts on top
+            if (d2 != 0.f) atomicMax(disp, __float_as_uint(d2));
+        }
+    }
 }
 
 // one thread per extended cell.  Table entry = {start_a, count_a, start_b,
@@ -204,7 +247,8 @@ __global__ void k_fill_ghosts(Grid g, int n_loc,
                               Atom4 *__restrict__ atoms,
                               uint8_t *__restrict__ types_ext,
                               int *__restrict__ ghost_owner,
-                              int *__restrict__ ghost_S, int refresh_only) {
+                              int *__restrict__ ghost_S, int refresh_only, QFrame qf,
+                              Rec16 *__restrict__ rec16) {
     const int lin = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (lin >= g.n_ecells) return;
@@ -242,6 +286,7 @@ __global__ void k_fill_ghosts(Grid g, int n_loc,
         a.y += sy;
         a.z += sz;
         atoms[dst + k] = a;
+        if (rec16) rec16[dst + k] = make_rec16(qf, a.x, a.y, a.z);
         if (!refresh_only) {
             types_ext[dst + k] = types_ext[src];
             ghost_owner[dst + k - n_loc] = (int)src;
@@ -997,7 +1042,8 @@ extern "C" int tab_nbr_free(tab_nbr *nbr) {
                       &nbr->ext_tab, &nbr->gcount, &nbr->gstart,
                       &nbr->slice_w, &nbr->slice_ptr, &nbr->col, &nbr->scan_tmp,
                       &nbr->stats, &nbr->row_ptr, &nbr->rho, &nbr->partial, &nbr->adp,
-                      &nbr->tcounts, &nbr->rev, &nbr->pcache, &nbr->rows_tmp};
+                      &nbr->tcounts, &nbr->rev, &nbr->pcache, &nbr->rows_tmp,
+                      &nbr->pos_ref, &nbr->disp, &nbr->ls_ptr, &nbr->ls_col, &nbr->rec16};
     for (DevBuf *b : bufs) b->release();
     delete nbr;
     return TAB_OK;
@@ -1005,12 +1051,107 @@ extern "C" int tab_nbr_free(tab_nbr *nbr) {
 
 static inline int nblocks(long long n, int t) { return (int)((n + t - 1) / t); }
 
+static QFrame qframe_of(const tab_nbr *nbr) {
+    QFrame q;
+    q.ox = nbr->q_origin[0];
+    q.oy = nbr->q_origin[1];
+    q.oz = nbr->q_origin[2];
+    q.inv_delta = nbr->q_inv_delta;
+    return q;
+}
+
+// Fixed-point frame of the float32 records: Cartesian bounding box of the binning frame
+// plus the reach of the ghost images and some room for drift; delta = power of two.
+static void setup_qframe(tab_nbr *nbr) {
+    const Grid &g = nbr->grid;
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int c = 0; c < 8; ++c)
+        for (int k = 0; k < 3; ++k) {
+            const double v = g.origin[k] + ((c & 1) ? g.h[k] : 0.0) + ((c & 2) ? g.h[3 + k] : 0.0) +
+                             ((c & 4) ? g.h[6 + k] : 0.0);
+            lo[k] = fmin(lo[k], v);
+            hi[k] = fmax(hi[k], v);
+        }
+    const double margin = 2.0 * g.rc + 8.0;
+    double ext = 0.0;
+    for (int k = 0; k < 3; ++k) {
+        nbr->q_origin[k] = lo[k] - margin;
+        ext = fmax(ext, hi[k] - lo[k] + 2.0 * margin);
+    }
+    int e;
+    frexp(ext / 1073741824.0, &e);            // ext / 2^30 = m 2^e, m in [0.5, 1)
+    nbr->q_delta = ldexp(1.0, e);             // >= ext / 2^30: coordinates fit 31 bits
+    nbr->q_inv_delta = ldexp(1.0, -e);
+}
+
+// The sentinel record (extended index n_ext): a point far outside the frame, so that every
+// pair with it fails the cutoff mask.  Fixed point: all real coordinates are >= 0, the
+// sentinel sits at -2^30 per axis (differences stay inside int32).
+__global__ void k_sentinels(int n_ext, double ox, double oy, double oz, Atom4 *atoms,
+                            Rec16 *rec16) {
+    Atom4 a;
+    a.x = ox - 1.0e4;
+    a.y = oy - 1.0e4;
+    a.z = oz - 1.0e4;
+    a.w = 0.0;
+    atoms[n_ext] = a;
+    if (rec16) {
+        Rec16 r;
+        r.qx = r.qy = r.qz = -(1 << 30);
+        r.w = 0.f;
+        rec16[n_ext] = r;
+    }
+}
+
+static int write_sentinels(tab_nbr *nbr, bool with_rec16, cudaStream_t st) {
+    const Grid &g = nbr->grid;
+    k_sentinels<<<1, 1, 0, st>>>(nbr->n_ext, g.origin[0], g.origin[1], g.origin[2],
+                                 nbr->atoms.as<Atom4>(),
+                                 with_rec16 ? nbr->rec16.as<Rec16>() : nullptr);
+    TAB_LAUNCH_CHECK();
+    return TAB_OK;
+}
+
+__global__ void k_make_rec16(int n_ext, const Atom4 *__restrict__ atoms, QFrame qf,
+                             Rec16 *__restrict__ rec16) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_ext) return;
+    const Atom4 a = atoms[e];
+    rec16[e] = make_rec16(qf, a.x, a.y, a.z);
+}
+
+// float32 records of the current positions (first use on a handle; afterwards the build and
+// the refresh kernels keep them up to date)
+int tab_nbr_ensure_rec16(tab_nbr *nbr, cudaStream_t st) {
+    if (nbr->rec16_valid) return TAB_OK;
+    nbr->want_rec16 = true;
+    setup_qframe(nbr);
+    TAB_TRY(nbr->rec16.ensure(sizeof(Rec16) * ((size_t)nbr->n_ext + 1)));
+    TAB_TRY(write_sentinels(nbr, true, st));
+    k_make_rec16<<<(nbr->n_ext + 255) / 256, 256, 0, st>>>(nbr->n_ext, nbr->atoms.as<Atom4>(),
+                                                          qframe_of(nbr), nbr->rec16.as<Rec16>());
+    TAB_LAUNCH_CHECK();
+    nbr->rec16_valid = true;
+    return TAB_OK;
+}
+
 static int refresh_positions(tab_nbr *nbr, const double *d_pos, cudaStream_t st) {
     const Grid &g = nbr->grid;
     nbr->pcache_valid = false;
-    k_gather_owned<<<nblocks(nbr->n_loc, 256), 256, 0, st>>>(
-        nbr->n_loc, d_pos, nullptr, g, nbr->perm.as<int>(), nbr->s0.as<int>(),
-        nbr->atoms.as<Atom4>(), nullptr);
+    const bool track = nbr->skin_built > 0.0;
+    Rec16 *rec = nbr->rec16_valid ? nbr->rec16.as<Rec16>() : nullptr;
+    const QFrame qf = qframe_of(nbr);
+    if (track) {
+        TAB_CUDA(cudaMemsetAsync(nbr->disp.p, 0, 4 * sizeof(unsigned int), st));
+        k_gather_owned<2><<<nblocks(nbr->n_loc, 256), 256, 0, st>>>(
+            nbr->n_loc, d_pos, nullptr, g, nbr->perm.as<int>(), nbr->s0.as<int>(),
+            nbr->atoms.as<Atom4>(), nullptr, nbr->pos_ref.as<double>(),
+            nbr->disp.as<unsigned int>(), qf, rec);
+    } else {
+        k_gather_owned<0><<<nblocks(nbr->n_loc, 256), 256, 0, st>>>(
+            nbr->n_loc, d_pos, nullptr, g, nbr->perm.as<int>(), nbr->s0.as<int>(),
+            nbr->atoms.as<Atom4>(), nullptr, nullptr, nullptr, qf, rec);
+    }
     TAB_LAUNCH_CHECK();
     if (nbr->n_ghost > 0) {
         k_fill_ghosts<<<nblocks((long long)g.n_ecells * 32, 256), 256, 0, st>>>(
@@ -1018,7 +1159,7 @@ static int refresh_positions(tab_nbr *nbr, const double *d_pos, cudaStream_t st)
             nbr->gstart.as<uint32_t>(), nbr->gcount.as<uint32_t>(),
             nbr->ext_tab.as<uint4>(), nbr->atoms.as<Atom4>(),
             nbr->types_ext.as<uint8_t>(), nbr->ghost_owner.as<int>(),
-            nbr->ghost_S.as<int>(), 1);
+            nbr->ghost_S.as<int>(), 1, qf, rec);
         TAB_LAUNCH_CHECK();
     }
     return TAB_OK;
@@ -1042,6 +1183,12 @@ extern "C" int tab_nbr_build_dd(tab_nbr *nbr, int32_t n_owned, int32_t n_halo,
     nbr->pcache_valid = false;
     nbr->n_struct = 0;          // single structure (a batch handle may be reused)
     nbr->has_row_ptr = false;
+    nbr->ls_L = 0;
+    nbr->rec16_valid = false;
+    // lists with a skin: radius rc + skin, the pair kernels mask r >= rc
+    nbr->rc_model = rc;
+    nbr->skin_built = nbr->skin;
+    rc += nbr->skin;
     Grid &g = nbr->grid;
     const int n = n_owned, n_loc = (int)n_loc_ll;
     TAB_TRY(setup_grid(g, n_loc, h_cell, h_origin, h_pbc, rc));
@@ -1112,14 +1259,29 @@ extern "C" int tab_nbr_build_dd(tab_nbr *nbr, int32_t n_owned, int32_t n_halo,
     }
     nbr->n_ghost = (int)n_ghost;
     nbr->n_ext = n_loc + nbr->n_ghost;
-    TAB_TRY(nbr->atoms.ensure(sizeof(Atom4) * (size_t)nbr->n_ext));
+    // one record past the end: the SENTINEL that pads the lane-split rows (eam_fast.cuh)
+    TAB_TRY(nbr->atoms.ensure(sizeof(Atom4) * ((size_t)nbr->n_ext + 1)));
     TAB_TRY(nbr->types_ext.ensure((size_t)nbr->n_ext + 16));
     TAB_TRY(nbr->ghost_owner.ensure(sizeof(int) * (size_t)(nbr->n_ghost + 1)));
     TAB_TRY(nbr->ghost_S.ensure(sizeof(int) * (size_t)(nbr->n_ghost + 1)));
 
-    k_gather_owned<<<nblocks(n_loc, 256), 256, 0, st>>>(
+    Rec16 *rec = nullptr;
+    if (nbr->want_rec16) {
+        setup_qframe(nbr);
+        TAB_TRY(nbr->rec16.ensure(sizeof(Rec16) * ((size_t)nbr->n_ext + 1)));
+        rec = nbr->rec16.as<Rec16>();
+    }
+    TAB_TRY(write_sentinels(nbr, rec != nullptr, st));
+    const QFrame qf = qframe_of(nbr);
+    if (nbr->skin_built > 0.0) {
+        TAB_TRY(nbr->pos_ref.ensure(sizeof(double) * 3 * (size_t)n_loc));
+        TAB_TRY(nbr->disp.ensure(4 * sizeof(unsigned int)));
+        TAB_CUDA(cudaMemsetAsync(nbr->disp.p, 0, 4 * sizeof(unsigned int), st));
+    }
+    k_gather_owned<1><<<nblocks(n_loc, 256), 256, 0, st>>>(
         n_loc, d_pos, d_types, g, nbr->perm.as<int>(), nbr->s0.as<int>(),
-        nbr->atoms.as<Atom4>(), nbr->types_ext.as<uint8_t>());
+        nbr->atoms.as<Atom4>(), nbr->types_ext.as<uint8_t>(),
+        nbr->skin_built > 0.0 ? nbr->pos_ref.as<double>() : nullptr, nullptr, qf, rec);
     TAB_LAUNCH_CHECK();
     if (nbr->n_ghost > 0) {
         k_fill_ghosts<<<nblocks((long long)g.n_ecells * 32, 256), 256, 0, st>>>(
@@ -1127,9 +1289,10 @@ extern "C" int tab_nbr_build_dd(tab_nbr *nbr, int32_t n_owned, int32_t n_halo,
             nbr->gstart.as<uint32_t>(), nbr->gcount.as<uint32_t>(),
             nbr->ext_tab.as<uint4>(), nbr->atoms.as<Atom4>(),
             nbr->types_ext.as<uint8_t>(), nbr->ghost_owner.as<int>(),
-            nbr->ghost_S.as<int>(), 0);
+            nbr->ghost_S.as<int>(), 0, qf, rec);
         TAB_LAUNCH_CHECK();
     }
+    nbr->rec16_valid = rec != nullptr;
 
     ExactCtx x;
     x.pos = d_pos;
@@ -1315,6 +1478,37 @@ extern "C" int tab_nbr_update(tab_nbr *nbr, const double *d_pos, const double *h
     return refresh_positions(nbr, d_pos, (cudaStream_t)stream);
 }
 
+extern "C" int tab_nbr_set_skin(tab_nbr *nbr, double skin) {
+    if (!nbr || !(skin >= 0.0)) {
+        tab_set_error("tab_nbr_set_skin: bad argument");
+        return TAB_EINVAL;
+    }
+    nbr->skin = skin;
+    return TAB_OK;
+}
+
+extern "C" int tab_nbr_max_displacement(tab_nbr *nbr, double *h_disp, double *h_skin,
+                                        void *stream) {
+    if (!nbr || !h_disp) return TAB_EINVAL;
+    if (!nbr->built) {
+        tab_set_error("tab_nbr_max_displacement before tab_nbr_build");
+        return TAB_ESTATE;
+    }
+    if (h_skin) *h_skin = nbr->skin_built;
+    if (!(nbr->skin_built > 0.0)) {
+        *h_disp = 0.0;          // lists without a skin: every update needs a rebuild anyway
+        return TAB_OK;
+    }
+    unsigned int bits = 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    TAB_CUDA(cudaMemcpyAsync(&bits, nbr->disp.p, sizeof(bits), cudaMemcpyDeviceToHost, st));
+    TAB_CUDA(cudaStreamSynchronize(st));
+    float d2;
+    memcpy(&d2, &bits, sizeof(d2));
+    *h_disp = d2 == d2 ? sqrt((double)d2) : (double)INFINITY;     // NaN positions: rebuild
+    return TAB_OK;
+}
+
 extern "C" int tab_nbr_sizes(const tab_nbr *nbr, int64_t *nij, int32_t *nnl_max,
                              int32_t *n_ext) {
     if (!nbr) return TAB_EINVAL;
@@ -1342,6 +1536,12 @@ extern "C" int tab_nbr_export(const tab_nbr *cnbr, int32_t *d_i, int32_t *d_j,
     tab_nbr *nbr = const_cast<tab_nbr *>(cnbr);
     if (!nbr || !d_i || !d_j || !d_S) return TAB_EINVAL;
     if (!nbr->built) return TAB_ESTATE;
+    if (nbr->skin_built > 0.0) {
+        tab_set_error("tab_nbr_export: the lists carry a skin of %g A (entries beyond rc); "
+                      "build with skin = 0 for the reference's (ilist, jlist, n1)",
+                      nbr->skin_built);
+        return TAB_ESTATE;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     const int n = nbr->n;
     TAB_TRY(nbr->row_ptr.ensure(sizeof(uint32_t) * (size_t)n));

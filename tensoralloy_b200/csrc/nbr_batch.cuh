@@ -263,6 +263,10 @@ extern "C" int tab_nbr_build_batch(tab_nbr *nbr, int32_t n_struct, const int32_t
         return TAB_EINVAL;
     }
     nbr->built = false;
+    nbr->skin_built = 0.0;      // batch handles are rebuilt per batch: no skin
+    nbr->rc_model = rc;
+    nbr->ls_L = 0;
+    nbr->rec16_valid = false;
     nbr->pcache_valid = false;
     nbr->has_rev = false;
     nbr->has_row_ptr = false;

@@ -209,6 +209,10 @@ static int pair_checks(tab_nbr *nbr, const char *who) {
         tab_set_error("%s: halo atoms (domain decomposition) are not supported", who);
         return TAB_EUNSUPPORTED;
     }
+    if (nbr->skin_built > 0.0) {
+        tab_set_error("%s: the lists carry a skin (entries beyond rc); build with skin = 0", who);
+        return TAB_ESTATE;
+    }
     return TAB_OK;
 }
 
