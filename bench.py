@@ -8,19 +8,27 @@ Gaussian rattle sigma 0.05 A seed 611, zjw04 EAM, rc = 6.5 A, float64).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-One "step" = one MD force step over the whole structure with the neighbour
-lists resident: refresh the cell-sorted positions from the caller's array, rho
-pass, F' spread, force/energy/virial pass, reduction.  `value` is timed on the
-device with inputs already resident in HBM; `e2e` is the same metric through
-the reference-facing API (TensorAlloyCalculator-equivalent host call) with HOST
-buffers: H2D of the positions, neighbour REBUILD (the reference rebuilds its
-lists on every `calculate`), evaluation, D2H of energy + forces + virial.
+`value`: one "step" = one MD force step with MOVING atoms and MD-valid list reuse: the atoms
+advance by a fixed velocity field (Gaussian, scaled so that the fastest atom uses up half the
+skin in 9.5 steps: a rebuild on every 10th step); per step the positions are refreshed on the
+lists (`tab_nbr_update`, which also measures the largest displacement since the last build),
+the lists are REBUILT when an atom has moved more than skin / 2, then rho pass, F' spread,
+force/energy/virial pass, reduction.  Lists carry a skin (default 0.3 A) and the pair kernels
+mask r >= rc, so every step's result equals the one on freshly built lists (the reference
+rebuilds per call, transformer/universal.py:58).  `value` is the amortised rate over the timed
+steps, rebuilds included; `resident` holds the pure list-reuse step.  Inputs are resident in HBM.
+`e2e` is the same metric through the C ABI's host call with HOST buffers: H2D of the positions,
+neighbour REBUILD at exactly rc on every call, evaluation, D2H of energy + forces + virial;
+`e2e_calculator` is the same through `TensorAlloyCalculator.calculate` (the reference's
+Python boundary).  `extra.medium` repeats `value` in float32 (the reference's default precision).
+`check` compares E_atom and F of randomly sampled atoms of THIS run with the oracle evaluated
+on their 2 rc environments cut out of the host positions, and carries the energy / force
+checksums that must agree between N = 1, 2, 4, 8.
 The index arrays alone (86 M entries x 4 B = 344 MB) exceed the 126 MB L2, so
-consecutive timed iterations cannot be served from cache ("inputs larger than
-L2").
+consecutive timed iterations cannot be served from cache ("inputs larger than L2").
 
 N > 1 (torchrun, one rank per GPU): 1-D slab decomposition along x with
-ghost-atom halo exchange over NCCL; see tensoralloy_b200/domain.py.
+ghost-atom halo exchange over NVLink peer memory; see tensoralloy_b200/domain.py.
 """
 import argparse
 import json
@@ -55,16 +63,13 @@ def make_lattice(cells, seed=SEED):
     return pos, cell
 
 
-# FP64 instructions per pair in the k_eam_force loop of the zjw04 fast path (SASS count)
-FP64_PER_PAIR = {'high': 83, 'medium': 0}
-
-
-def load_traffic(kernel):
-    """DRAM bytes per launch of `kernel` from the committed ncu capture (or None)."""
-    path = os.path.join(ROOT, 'profiles', 'r01k_traffic.json')
+def load_profile(tag):
+    """Numbers of a committed ncu capture (profiles/<tag>_traffic.json written by
+    tools/ncu_summary.py) -- NOT measured by this run; the line says so."""
+    path = os.path.join(ROOT, 'profiles', f'{tag}_traffic.json')
     try:
         with open(path) as fp:
-            return json.load(fp).get(kernel)
+            return json.load(fp)
     except Exception:
         return None
 
@@ -225,8 +230,124 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------
+# parity evidence on the headline ("the headline config has no parity evidence")
+# ---------------------------------------------------------------------------
+def sampled_check(pos_all, cell, idx, eatom, forces, per_call=64):
+    """Oracle E_atom / F of the atoms `idx` from their 2 rc environments: an atom's energy
+    needs its neighbours (rc), its force the F'(rho) of those neighbours, i.e. THEIR
+    neighbours (2 rc).  The environments are cut out of the periodic structure (minimum
+    image), laid out side by side in one non-periodic box and handed to the oracle
+    (oracle/eam.py, the CPU restatement of the reference) -- `per_call` clusters per call.
+    Returns (max |dE_atom|, max |dF|) against the GPU values `eatom[k]`, `forces[k]`."""
+    from scipy.spatial import cKDTree
+    from oracle import eam as oeam
+    from oracle import potentials as opot
+    L = np.diag(cell).copy()
+    posw = np.mod(pos_all, L)
+    tree = cKDTree(posw, boxsize=L)
+    pot = opot.get_potential('zjw04')
+    max_de = max_df = 0.0
+    span = 4.0 * RC + 10.0
+    for lo in range(0, len(idx), per_call):
+        chunk = idx[lo:lo + per_call]
+        parts, centres, off = [], [], 0
+        for k, i in enumerate(chunk):
+            nb = np.asarray(tree.query_ball_point(posw[i], 2.0 * RC))
+            D = posw[nb] - posw[i]
+            D -= L * np.round(D / L)
+            centres.append(off + int(np.flatnonzero(nb == i)[0]))
+            off += len(nb)
+            parts.append(D + np.array([span * (k + 0.5), 0.5 * span, 0.5 * span]))
+        P = np.concatenate(parts)
+        ref = oeam.eam_evaluate(pot, 'alloy', ['Ni'], ['Ni'] * len(P), P,
+                                np.diag([span * len(chunk), span, span]), [0, 0, 0], RC)
+        sel = slice(lo, lo + len(chunk))
+        max_de = max(max_de, float(np.abs(eatom[sel] - ref['energy/atom'][centres]).max()))
+        max_df = max(max_df, float(np.abs(forces[sel] - ref['forces'][centres]).max()))
+    return max_de, max_df
+
+
+# ---------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------
+def timed(fn, steps, barrier, torch, dist, world):
+    """K calls of fn between two events on the current stream, barrier + synchronize on both
+    sides, max over ranks.  Returns ms per call."""
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(steps):
+        fn()
+    ev1.record()
+    barrier()
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item()) / steps
+
+
+def measure(runner, args, precision, barrier, torch, dist, world, _lib):
+    """value (MD cycle), resident step and per-kernel times of one precision."""
+    runner.set_precision(precision)
+    for _ in range(args.warmup):
+        runner.md_step()
+    barrier()
+    # per-kernel event timing + launch count of the resident step (eager launches)
+    _lib.profile_enable(True)
+    _lib.lib().tab_launch_count_reset()
+    n_res = max(3, min(args.steps, 10))
+    resident_ms = timed(runner.resident_step, n_res, barrier, torch, dist, world)
+    launches_res = int(_lib.lib().tab_launch_count()) // n_res
+    kernel_ms, _ = _lib.profile_read()
+    _lib.profile_enable(False)
+    graphed = False
+    if world > 1 and not args.no_graph:
+        graphed = runner.enable_graph()
+        for _ in range(args.warmup):
+            runner.md_step()
+        barrier()
+        resident_ms = timed(runner.resident_step, n_res, barrier, torch, dist, world)
+    runner.rebuilds = 0
+    _lib.lib().tab_launch_count_reset()
+    ms_per_step = timed(runner.md_step, args.steps, barrier, torch, dist, world)
+    launches = int(_lib.lib().tab_launch_count())
+    if graphed:
+        launches += launches_res * (args.steps - runner.rebuilds)
+    return {"ms_per_step": ms_per_step, "resident_ms": resident_ms, "kernel_ms": kernel_ms,
+            "launches": launches, "rebuilds": runner.rebuilds, "graphed": graphed}
+
+
+def roofline_block(m, runner, hbm, which, precision, kernel_name, tag):
+    n_loc, nij = runner.n_local, runner.nij_local
+    w = 8 if precision == 'high' else 4
+    rec = 32 if precision == 'high' else 16
+    # SURVEY.md 8(d), force pass: 4 B column index per list entry + own record + 3 force
+    # components and E_atom written as float64 (the C ABI's output type)
+    alg_bytes = 4.0 * nij + (rec + 32.0) * n_loc
+    force_ms = m["kernel_ms"][2]
+    achieved = alg_bytes / (force_ms * 1e-3) / 1e9 if force_ms > 0 else None
+    prof = load_profile(tag) or {}
+    out = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": hbm,
+           "unit": "GB/s", "frac": (achieved / hbm) if achieved else None,
+           "traffic": prof.get(kernel_name), "peak_source": which,
+           "traffic_source": (f"profiles/{tag}_traffic.json (ncu --set full of an earlier run "
+                              f"of this command, not measured in this run)"
+                              if prof.get(kernel_name) else None),
+           "algorithmic_bytes_per_launch": alg_bytes,
+           "pairs_in_lists": nij,
+           "kernel_ms": {"rho_pass": m["kernel_ms"][0], "spread": m["kernel_ms"][1],
+                         "force_pass": m["kernel_ms"][2], "reduce": m["kernel_ms"][3]},
+           "step_hbm_frac": ((8.0 * nij + (2 * rec + 12 * 8) * n_loc) /
+                             (m["resident_ms"] * 1e-3) / 1e9 / hbm)}
+    if precision == 'high':
+        out["note"] = ("float64 analytic zjw04 is bound by the FP64 pipe (64 lanes/clk/SM), not "
+                       "by HBM: DESIGN.md section 4 gives the instruction counts and the ncu "
+                       "pipe utilisation; the HBM fraction is reported as BASELINE.json asks")
+    w = w  # noqa
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -249,15 +370,16 @@ def run_ours(args):
     pot = get_potential('zjw04')
     model = _lib.EamModel(_lib.EAM_ALLOY, 1, [pot.rho('Ni')], [pot.phi('NiNi')],
                           [pot.embed('Ni')])
-    precision = _lib.PRECISION_HIGH if args.precision == 'high' \
-        else _lib.PRECISION_MEDIUM
+    prec_id = {'high': _lib.PRECISION_HIGH, 'medium': _lib.PRECISION_MEDIUM}
 
     if world > 1:
         from tensoralloy_b200.domain import SlabDomain
         runner = SlabDomain(model, cells, A_NI, RC, SIGMA, SEED, world, rank,
-                            scaling=args.scaling, precision=precision)
+                            scaling=args.scaling, precision=prec_id[args.precision],
+                            skin=args.skin)
     else:
-        runner = SingleGpu(model, cells, precision)
+        runner = SingleGpu(model, cells, prec_id[args.precision], args.skin)
+    runner.prec_id = prec_id
     n_total = runner.n_total
 
     def barrier():
@@ -265,54 +387,18 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- value: device-resident step ------------------------------------
-    for _ in range(args.warmup):
-        runner.step()
-    barrier()
-    graphed = False
-    if world > 1:
-        # per-kernel event timing and the launch count need eager launches: take them
-        # from a few untimed steps, then capture the step in a CUDA graph
-        _lib.profile_enable(True)
-        _lib.lib().tab_launch_count_reset()
-        for _ in range(3):
-            runner.step()
-        barrier()
-        launches_per_step = int(_lib.lib().tab_launch_count()) // 3
-        kernel_ms, calls = _lib.profile_read()
-        _lib.profile_enable(False)
-        if not args.no_graph:
-            graphed = runner.enable_graph()
-            for _ in range(args.warmup):
-                runner.step()
-            barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    if world == 1:
-        _lib.profile_enable(True)
-        _lib.lib().tab_launch_count_reset()
-    ev0 = torch.cuda.Event(enable_timing=True)
-    ev1 = torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for _ in range(args.steps):
-        runner.step()
-    ev1.record()
-    barrier()
-    ms = ev0.elapsed_time(ev1)
-    if world == 1:
-        launches = int(_lib.lib().tab_launch_count())
-        kernel_ms, calls = _lib.profile_read()
-        _lib.profile_enable(False)
-    else:
-        launches = launches_per_step * args.steps
-    t = torch.tensor([ms], dtype=torch.float64, device='cuda')
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    ms_per_step = ms / args.steps
-    value = n_total / (ms_per_step * 1e-3)
+    main = measure(runner, args, args.precision, barrier, torch, dist, world, _lib)
+    value = n_total / (main["ms_per_step"] * 1e-3)
+    nij_main = runner.nij_local
+    other = 'medium' if args.precision == 'high' else 'high'
+    extra = None
+    if not args.no_extra:
+        extra = measure(runner, args, other, barrier, torch, dist, world, _lib)
+        nij_extra = runner.nij_local
+        runner.set_precision(args.precision)
 
     # ---- e2e: host buffers through the public host call -------------------
     e2e_steps = max(2, min(args.steps, args.e2e_steps))
@@ -320,10 +406,8 @@ def run_ours(args):
         runner.step_e2e()
     barrier()
     t0 = time.perf_counter()
-    ev0.record()
     for _ in range(e2e_steps):
         runner.step_e2e()
-    ev1.record()
     barrier()
     wall = (time.perf_counter() - t0) * 1e3
     t = torch.tensor([wall], dtype=torch.float64, device='cuda')
@@ -331,68 +415,63 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item()) / e2e_steps
     e2e_value = n_total / (e2e_ms * 1e-3)
-    clocks = sampler.stop() if rank == 0 else None     # sampled over both timed regions
+    e2e_calc = runner.e2e_calculator(e2e_steps) if (world == 1 and not args.no_extra) else None
+    clocks = sampler.stop() if rank == 0 else None     # sampled over the timed regions
+
+    # ---- parity evidence: sampled oracle check + checksums -------------------
+    check = runner.check(args.check_atoms, dist if world > 1 else None, sampled_check)
 
     if rank == 0:
         hbm, which = load_peaks()
-        n_loc = runner.n_local
-        nij = runner.nij_local
-        # force pass = 4 B col index per pair + own Atom4 (32 B)
-        # + 3w force write + w E_atom write = 4 n + 8 w per atom (w = 8)
-        alg_bytes = 4.0 * nij + 64.0 * n_loc
-        force_ms = kernel_ms[2]
-        achieved = alg_bytes / (force_ms * 1e-3) / 1e9 if force_ms > 0 else None
-        sm_mhz = float((clocks or {}).get('sm_mhz') or 1965.0)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": args.scaling if world > 1 else "weak",
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": main["ms_per_step"],
+            "higher_is_better": True,
+            "scaling": args.scaling if world > 1 else "strong",
             "vs_baseline": None,
             "dtype": "f64" if args.precision == 'high' else "f32",
             "data": "synthetic",
             "config": {
                 "workload": f"EAM Ni fcc {cells}^3 cells ({n_total} atoms total), "
                             f"zjw04, rc={RC}, rattle {SIGMA} A seed {SEED}, "
-                            f"E+F+virial with resident neighbour lists",
-                "atoms": n_total, "pairs_local": nij,
+                            f"E+F+virial per MD step, atoms moving, lists with a "
+                            f"{runner.skin} A skin rebuilt when an atom has moved skin/2 "
+                            f"(every 10th step), rebuilds inside the timed region",
+                "atoms": n_total, "pairs_local": nij_main,
+                "rebuilds_in_timed_steps": main["rebuilds"],
+                "md_valid": runner.md_valid,
                 "parallelism": runner.describe(),
-                "cache": "inputs larger than L2 (neighbour index arrays 344 MB "
+                "cache": "inputs larger than L2 (neighbour index arrays >= 344 MB "
                          "per 1M atoms > 126 MB L2)"},
-            "roofline": {
-                "bound": "hbm", "kernel": "k_eam_force<double,zhou1>",
-                "achieved": achieved, "peak": hbm, "unit": "GB/s",
-                "frac": (achieved / hbm) if achieved else None,
-                "traffic": (load_traffic("k_eam_force<double,zhou1>")
-                            if (world == 1 and args.precision == 'high'
-                                and cells == 63) else None),
-                "peak_source": which,
-                "algorithmic_bytes_per_launch": alg_bytes,
-                "kernel_ms": {"rho_pass": kernel_ms[0], "spread": kernel_ms[1],
-                              "force_pass": kernel_ms[2], "reduce": kernel_ms[3]},
-                "fp64_pipe_active_pct_ncu": 64.9,
-                # the binding compute limit next to the HBM figure: SASS-counted FP64
-                # instructions of the force loop (tools/sass_loop.py) x pairs / measured
-                # duration, against 64 FP64 lanes/clk/SM x 148 SMs x the sampled SM clock
-                "fp64": ({"instr_per_pair": FP64_PER_PAIR[args.precision],
-                          "achieved_ginstr_s": FP64_PER_PAIR[args.precision] * nij /
-                          (force_ms * 1e-3) / 1e9,
-                          "peak_ginstr_s": 64 * 148 * sm_mhz * 1e6 / 1e9,
-                          "frac": FP64_PER_PAIR[args.precision] * nij / (force_ms * 1e-3) /
-                          (64 * 148 * sm_mhz * 1e6)}
-                         if (force_ms > 0 and args.precision == 'high') else None),
-                "note": "float64 analytic zjw04 is bound by the FP64 pipe and the L1 "
-                        "gather path together (ncu: FP64 pipe 65% of cycles active at 83 "
-                        "FP64 instructions per pair, L1 50%, DRAM 8%, DRAM bytes within 10% "
-                        "of algorithmic; profiles/r01k_*), not by HBM; the HBM fraction is "
-                        "reported as BASELINE.json asks"},
+            "resident": {"ms_per_step": main["resident_ms"],
+                         "value": n_total / (main["resident_ms"] * 1e-3),
+                         "what": "list-reuse step alone (position refresh + displacement "
+                                 "tracking + rho + spread + force + reduce), no rebuild"},
+            "roofline": roofline_block(main, runner, hbm, which, args.precision,
+                                       KERNEL_NAME[args.precision], PROFILE_TAG),
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": runner.h2d_bytes,
                     "d2h_bytes_per_step": runner.d2h_bytes,
                     "ms_per_step": e2e_ms,
-                    "includes": "H2D positions, neighbour rebuild, E+F+virial, D2H"},
-            "gpu_launches": launches,
+                    "includes": "H2D positions, neighbour rebuild at exactly rc, E+F+virial, "
+                                "D2H (tab_eam_compute_host, pinned host buffers)"},
+            "gpu_launches": main["launches"],
+            "check": check,
             "clocks": clocks,
         }
+        if e2e_calc is not None:
+            line["e2e_calculator"] = e2e_calc
+        if extra is not None:
+            runner.nij_local = nij_extra
+            line["extra"] = {other: {
+                "value": n_total / (extra["ms_per_step"] * 1e-3), "unit": UNIT,
+                "dtype": "f32" if other == 'medium' else "f64",
+                "ms_per_step": extra["ms_per_step"],
+                "rebuilds_in_timed_steps": extra["rebuilds"],
+                "resident_ms_per_step": extra["resident_ms"],
+                "roofline": roofline_block(extra, runner, hbm, which, other,
+                                           KERNEL_NAME[other], PROFILE_TAG)}}
+            runner.nij_local = nij_main
         if world == 1 and not args.no_cpu_baseline:
             full, ev, n_cpu, cores, sec = cpu_reference_run(args.ref_cells, 2, 1)
             line["cpu_baseline"] = {
@@ -409,23 +488,38 @@ def run_ours(args):
     return result_line
 
 
+KERNEL_NAME = {'high': 'k_eamz_force<f64>', 'medium': 'k_eamz_force_f32'}
+PROFILE_TAG = 'r02'
+
+
 class SingleGpu:
     """N = 1: the whole structure on cuda:0."""
+    md_valid = True
 
-    def __init__(self, model, cells, precision):
+    def __init__(self, model, cells, precision, skin):
         import torch
         from tensoralloy_b200 import _lib
+        self.torch = torch
         self.model = model
         self.precision = precision
+        self.skin = skin
         pos, cell = make_lattice(cells)
         self.cell = cell
-        self.n_total = self.n_local = len(pos)
+        self.n_total = self.n_local = n = len(pos)
         self.h_pos = torch.from_numpy(pos).pin_memory()
         self.d_pos = self.h_pos.to('cuda')
+        # velocity field of the MD cycle: Gaussian, the fastest atom covers skin / 2 in 9.5
+        # steps -> the displacement check asks for a rebuild on every 10th step
+        g = torch.Generator(device='cuda')
+        g.manual_seed(SEED)
+        self.d_vel = torch.randn((n, 3), generator=g, dtype=torch.float64, device='cuda')
+        vmax = float(torch.linalg.norm(self.d_vel, dim=1).max())
+        self.d_vel *= (0.5 * max(skin, 1e-3) / 9.5) / vmax
         self.nbr = _lib.NeighborList()
+        self.nbr.set_skin(skin)
         self.nbr.build(self.d_pos, None, cell, [1, 1, 1], RC)
         self.nij_local = self.nbr.sizes()[0]
-        n = self.n_local
+        self.rebuilds = 0
         self.d_e = torch.zeros(1, dtype=torch.float64, device='cuda')
         self.d_f = torch.zeros((n, 3), dtype=torch.float64, device='cuda')
         self.d_v = torch.zeros(9, dtype=torch.float64, device='cuda')
@@ -437,10 +531,21 @@ class SingleGpu:
         self.h2d_bytes = n * 24
         self.d2h_bytes = n * 24 + 80
 
+    def set_precision(self, name):
+        self.precision = self.prec_id[name]
+
     def describe(self):
         return "single GPU"
 
-    def step(self):
+    def md_step(self):
+        self.d_pos.add_(self.d_vel)
+        if self.nbr.step(self.d_pos, None, self.cell, [1, 1, 1], RC):
+            self.rebuilds += 1
+            self.nij_local = self.nbr.sizes()[0]
+        self.model.eval(self.nbr, self.precision, energy=self.d_e, forces=self.d_f,
+                        virial=self.d_v)
+
+    def resident_step(self):
         self.nbr.update(self.d_pos)
         self.model.eval(self.nbr, self.precision, energy=self.d_e, forces=self.d_f,
                         virial=self.d_v)
@@ -449,6 +554,83 @@ class SingleGpu:
         self.model.compute_host(self.nbr_e2e, self.precision, self.h_pos, None,
                                 self.cell, [1, 1, 1], RC, True, self.h_e, None,
                                 self.h_f, self.h_v)
+
+    def e2e_calculator(self, steps):
+        """The same evaluation through the reference's Python boundary: the positions of an
+        Atoms object change, TensorAlloyCalculator.calculate builds the lists, evaluates and
+        fills `results` with numpy arrays."""
+        from tensoralloy_b200.atoms import Atoms
+        from tensoralloy_b200.calculator import TensorAlloyCalculator
+        from tensoralloy_b200.nn.eam import EamAlloyNN
+        from tensoralloy_b200.precision import precision_scope
+        from tensoralloy_b200.transformer import UniversalTransformer
+        name = 'high' if self.precision == self.prec_id['high'] else 'medium'
+        with precision_scope(name):
+            nn = EamAlloyNN(elements=['Ni'], custom_potentials='zjw04')
+            nn.attach_transformer(UniversalTransformer(['Ni'], rcut=RC))
+            calc = TensorAlloyCalculator(nn)
+            pos = self.h_pos.numpy()
+            atoms = Atoms(numbers=np.full(len(pos), 28), positions=pos, cell=self.cell,
+                          pbc=True)
+            shift = np.zeros(3)
+            times = []
+            for it in range(steps + 1):
+                shift[0] = 1e-3 * it            # new positions on every call (no result cache)
+                atoms.positions = pos + shift
+                t0 = time.perf_counter()
+                calc.calculate(atoms, properties=['energy', 'forces', 'stress'])
+                self.torch.cuda.synchronize()
+                if it > 0:
+                    times.append(time.perf_counter() - t0)
+        ms = 1e3 * statistics.mean(times)
+        return {"value": self.n_total / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+                "includes": "TensorAlloyCalculator.calculate(atoms, ['energy', 'forces', "
+                            "'stress']): Atoms.copy, VAP / type maps, H2D from the numpy "
+                            "array, list build, kernels, D2H into numpy results"}
+
+    def check(self, n_sample, dist=None, sampled=None):
+        torch = self.torch
+        n = self.n_local
+        ea = torch.zeros(n, dtype=torch.float64, device='cuda')
+        exact = self.nbr_e2e
+        out = {}
+        pos = self.d_pos.cpu().numpy()
+        # the CURRENT (moved) positions: reused skin lists vs the oracle
+        self.nbr.update(self.d_pos)
+        disp, skin = self.nbr.max_displacement()
+        self.model.eval(self.nbr, self.precision, energy=self.d_e, eatom=ea,
+                        forces=self.d_f, virial=self.d_v)
+        torch.cuda.synchronize()
+        rng = np.random.default_rng(SEED)
+        idx = np.sort(rng.choice(n, size=min(n_sample, n), replace=False))
+        t_idx = torch.from_numpy(idx).cuda()
+        f_s = self.d_f[t_idx].cpu().numpy()
+        e_s = ea[t_idx].cpu().numpy()
+        max_de, max_df = sampled_check(pos, self.cell, idx, e_s, f_s)
+        e_skin, v_skin = self.d_e.item(), self.d_v.cpu().numpy().copy()
+        f_skin = self.d_f.clone()
+        # the same positions on freshly built exact lists (the reference's per-call rebuild)
+        exact.set_skin(0.0)
+        exact.build(self.d_pos, None, self.cell, [1, 1, 1], RC)
+        self.model.eval(exact, self.precision, energy=self.d_e, forces=self.d_f,
+                        virial=self.d_v)
+        torch.cuda.synchronize()
+        tol_e, tol_f = (1e-10, 1e-8) if self.precision == self.prec_id['high'] else \
+            (1e-5 * 4.45, 1e-5 * float(self.d_f.abs().max()))
+        out.update({
+            "n_sampled": int(len(idx)), "max_dE_atom": max_de, "max_dF": max_df,
+            "tol_dE_atom": tol_e, "tol_dF": tol_f,
+            "ok": bool(max_de <= tol_e and max_df <= tol_f),
+            "against": "oracle (CPU restatement of the reference) on the 2 rc environment of "
+                       "every sampled atom, positions of the last timed step",
+            "energy": e_skin, "f_l2": float(torch.linalg.norm(f_skin)),
+            "virial_trace": float(v_skin[0] + v_skin[4] + v_skin[8]),
+            "max_disp_since_build": disp, "skin": skin,
+            "reused_vs_fresh_lists": {
+                "dE_per_atom": abs(e_skin - self.d_e.item()) / n,
+                "max_dF": float((f_skin - self.d_f).abs().max()),
+                "max_dvirial_per_atom": float(np.abs(v_skin - self.d_v.cpu().numpy()).max()) / n}})
+        return out
 
 
 class StdoutGuard:
@@ -483,6 +665,12 @@ def main():
     ap.add_argument('--scaling', default='strong', choices=['strong', 'weak'])
     ap.add_argument('--e2e-steps', type=int, default=10)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-extra', action='store_true',
+                    help='skip the other precision and the calculator e2e leg')
+    ap.add_argument('--skin', type=float, default=0.3,
+                    help='skin of the resident lists (A); the MD cycle rebuilds on every 10th step')
+    ap.add_argument('--check-atoms', type=int, default=256,
+                    help='atoms compared with the oracle after the timed region')
     ap.add_argument('--no-graph', action='store_true',
                     help='N > 1: launch the step eagerly instead of as one CUDA graph')
     args = ap.parse_args()

@@ -100,6 +100,11 @@ int tab_peer_put(const double *d_src, int32_t n, const uint64_t *d_peer_ptrs,
                  int32_t n_peers, int32_t slot, void *stream);
 int tab_sum_slots(const double *d_slots, int32_t n_slots, int32_t n, double *d_out,
                   void *stream);
+/*   tab_reduce_slots  as tab_sum_slots for the entries [0, n_sum); the entries [n_sum, n) are
+ *                     reduced with MAX (the largest displacement since the list build rides
+ *                     along with the [E, virial] sums: one collective decides the rebuild). */
+int tab_reduce_slots(const double *d_slots, int32_t n_slots, int32_t n, int32_t n_sum,
+                     double *d_out, void *stream);
 
 /* Batch of independent structures in ONE handle ("structure-parallel batches"; replaces
  * the padded [B, N+1, 3] / [B, nij_max, .] tensors of BatchUniversalTransformer,
@@ -136,6 +141,9 @@ int tab_nbr_update(tab_nbr *nbr, const double *d_pos, const double *h_cell,
  * (tab_nbr_export, tab_pairs_export, tab_eam_hessian): build those with skin = 0. */
 int tab_nbr_set_skin(tab_nbr *nbr, double skin);
 int tab_nbr_max_displacement(tab_nbr *nbr, double *h_max_disp, double *h_skin, void *stream);
+/* the same quantity written to DEVICE memory (*d_out, Angstrom) without a synchronisation: the
+ * spatial decomposition reduces it over the ranks inside the step (tab_reduce_slots). */
+int tab_nbr_displacement_device(tab_nbr *nbr, double *d_out, void *stream);
 
 /* Sizes, the quantities of neighbor.py:34-47 NeighborSize.  nij = number of
  * directed pairs; nnl_max = max neighbours of one atom (all species);

@@ -107,7 +107,8 @@ EXPORTS = [
     'tab_nbr_build_batch', 'tab_nbr_batch_size',
     'tab_pairs_export', 'tab_pair_forces', 'tab_pair_jvp', 'tab_atomic_eval_dd', 'tab_eam_eval_dd', 'tab_eam_tabulate',
     'tab_profile_enable', 'tab_profile_read',
-    'tab_nbr_set_skin', 'tab_nbr_max_displacement',
+    'tab_nbr_set_skin', 'tab_nbr_max_displacement', 'tab_nbr_displacement_device',
+    'tab_reduce_slots',
 ]
 
 
@@ -145,6 +146,8 @@ def lib():
     L.tab_pack_rows.argtypes = [vp, vp, i32, i32, C.POINTER(dbl), vp, vp]
     L.tab_peer_put.argtypes = [vp, i32, vp, i32, i32, vp]
     L.tab_sum_slots.argtypes = [vp, i32, i32, vp, vp]
+    L.tab_reduce_slots.argtypes = [vp, i32, i32, i32, vp, vp]
+    L.tab_nbr_displacement_device.argtypes = [vp, vp, vp]
     L.tab_nbr_sizes.argtypes = [vp, C.POINTER(i64), C.POINTER(i32),
                                 C.POINTER(i32)]
     L.tab_nbr_counts.argtypes = [vp, vp, vp]
@@ -226,9 +229,11 @@ def peer_put(src, peer_ptrs, slot):
                              int(peer_ptrs.numel()), int(slot), _stream()), 'tab_peer_put')
 
 
-def sum_slots(slots, n_slots, out):
-    check(lib().tab_sum_slots(_ptr(slots), int(n_slots), int(out.numel()), _ptr(out),
-                              _stream()), 'tab_sum_slots')
+def sum_slots(slots, n_slots, out, n_sum=None):
+    """out[q] = sum over the slots for q < n_sum (default: all), max over the slots beyond."""
+    n = int(out.numel())
+    check(lib().tab_reduce_slots(_ptr(slots), int(n_slots), n, n if n_sum is None else int(n_sum),
+                                 _ptr(out), _stream()), 'tab_reduce_slots')
 
 
 class NeighborList:
@@ -317,6 +322,11 @@ class NeighborList:
         check(lib().tab_nbr_max_displacement(self._h, C.byref(d), C.byref(s), _stream()),
               'tab_nbr_max_displacement')
         return float(d.value), float(s.value)
+
+    def displacement_to(self, d_out):
+        """max |R - R_build| of the last update -> d_out[0] (device float64), no sync."""
+        check(lib().tab_nbr_displacement_device(self._h, _ptr(d_out), _stream()),
+              'tab_nbr_displacement_device')
 
     def step(self, d_pos, d_types, cell, pbc, rc):
         """One MD step of the lists: refresh the positions; rebuild when an atom has moved more

@@ -945,7 +945,7 @@ static int eamz_lanes() {
     const int L = env_int("TAB_EAMZ_L", EAMZ_L);
     return (L == 0 || L == 1 || L == 2 || L == 4 || L == 8) ? L : EAMZ_L;
 }
-static int eamz_vir() { return env_int("TAB_EAMZ_VIR", EAMZ_VIR) ? 1 : 0; }
+
 
 static bool eamz_usable(const tab_model *m, const tab_nbr *nbr, int precision) {
     if (eamz_lanes() == 0 || !m->zhou1 || !m->z1_folded || !m->zp || nbr->n_struct > 0)
@@ -981,22 +981,21 @@ static QScale eamz_qscale(const tab_model *m, const tab_nbr *nbr) {
 template <int L>
 static int eamz_pass1_L(tab_model *m, tab_nbr *nbr, int precision, double *d_fprime_caller,
                         double *fprime, double *fembed, cudaStream_t st) {
-    TAB_TRY(ensure_lanesplit<L>(nbr, st));
+    LsView v;
+    TAB_TRY(ensure_lanesplit<L>(nbr, st, v));
     const int n = nbr->n;
     constexpr int G = 32 / L;
     const long long threads = (long long)((n + G - 1) / G) * 32;
     const int nblk = (int)((threads + EAMZ_T - 1) / EAMZ_T);
     if (precision == TAB_PRECISION_HIGH) {
         k_eamz_rho<L><<<nblk, EAMZ_T, 0, st>>>(
-            n, nbr->atoms.as<Atom4>(), nbr->ls_ptr.as<uint32_t>(),
-            nbr->ls_col.as<uint32_t>(), nbr->perm.as<int>(), *m->zp, tab_mask_rc2(nbr),
-            m->embed0, fprime, fembed, d_fprime_caller);
+            n, nbr->atoms.as<Atom4>(), v.ptr, v.w, v.col, nbr->perm.as<int>(), *m->zp,
+            tab_mask_rc2(nbr), m->embed0, fprime, fembed, d_fprime_caller);
     } else {
         TAB_TRY(tab_nbr_ensure_rec16(nbr, st));
         k_eamz_rho_f32<L><<<nblk, EAMZ_T, 0, st>>>(
-            n, nbr->rec16.as<Rec16>(), nbr->ls_ptr.as<uint32_t>(),
-            nbr->ls_col.as<uint32_t>(), nbr->perm.as<int>(), *m->zp, eamz_qscale(m, nbr),
-            m->embed0, fprime, fembed, d_fprime_caller);
+            n, nbr->rec16.as<Rec16>(), v.ptr, v.w, v.col, nbr->perm.as<int>(), *m->zp,
+            eamz_qscale(m, nbr), m->embed0, fprime, fembed, d_fprime_caller);
     }
     TAB_LAUNCH_CHECK();
     return TAB_OK;
@@ -1006,26 +1005,21 @@ template <int L>
 static int eamz_pass2_L(tab_model *m, tab_nbr *nbr, int precision, const double *fembed,
                         double *d_eatom, double *d_forces, const int *d_own_mask, int *nblk_out,
                         cudaStream_t st) {
-    TAB_TRY(ensure_lanesplit<L>(nbr, st));
+    LsView v;
+    TAB_TRY(ensure_lanesplit<L>(nbr, st, v));
     const int n = nbr->n;
     constexpr int G = 32 / L;
     const long long threads = (long long)((n + G - 1) / G) * 32;
     const int nblk = (int)((threads + EAMZ_T - 1) / EAMZ_T);
     *nblk_out = nblk;
     TAB_TRY(nbr->partial.ensure(sizeof(double) * 8 * (size_t)nblk));
-    // the F (x) R form needs both rows of a real pair in this rank's sums: not with an own-mask
-    const bool vir = eamz_vir() && !d_own_mask;
     if (precision == TAB_PRECISION_HIGH) {
-        auto k = vir ? k_eamz_force<L, 1> : k_eamz_force<L, 0>;
-        k<<<nblk, EAMZ_T, 0, st>>>(
-            n, nbr->n, nbr->atoms.as<Atom4>(),
-            nbr->ls_ptr.as<uint32_t>(), nbr->ls_col.as<uint32_t>(), nbr->perm.as<int>(), *m->zp,
+        k_eamz_force<L><<<nblk, EAMZ_T, 0, st>>>(
+            n, nbr->atoms.as<Atom4>(), v.ptr, v.w, v.col, nbr->perm.as<int>(), *m->zp,
             tab_mask_rc2(nbr), fembed, d_eatom, d_forces, nbr->partial.as<double>(), d_own_mask);
     } else {
-        auto k = vir ? k_eamz_force_f32<L, 1> : k_eamz_force_f32<L, 0>;
-        k<<<nblk, EAMZ_T, 0, st>>>(
-            n, nbr->n, nbr->rec16.as<Rec16>(),
-            nbr->ls_ptr.as<uint32_t>(), nbr->ls_col.as<uint32_t>(), nbr->perm.as<int>(), *m->zp,
+        k_eamz_force_f32<L><<<nblk, EAMZ_T, 0, st>>>(
+            n, nbr->rec16.as<Rec16>(), v.ptr, v.w, v.col, nbr->perm.as<int>(), *m->zp,
             eamz_qscale(m, nbr), fembed, d_eatom, d_forces, nbr->partial.as<double>(),
             d_own_mask);
     }

@@ -10,9 +10,9 @@
 //     ~21.5 lines (measured 22.5 wavefronts per gather, profiles/r01k); the L consecutive entries
 //     of one row are neighbours in memory, L = 4 brings a gather down to ~14.6 lines, L = 8 to
 //     ~13.4 (tools/sim_gather_lines.py reproduces the measured figure and these).
-//   * virial in the form  W = - sum_i F_i^real (x) R_i + 1/2 sum_{p: j image/halo} g_p (x) D_p
-//     (identity for symmetric pair gradients, derivation in DESIGN.md): the six per-pair FMAs
-//     of g (x) D are only spent on pairs whose neighbour is a periodic image or a halo atom.
+//   * neighbour records prefetched D steps ahead through a register ring, the index stream two
+//     ring lengths further; rows padded with a sentinel entry so that the loops carry no
+//     per-lane trip counts and no predicated loads.
 //   * r < rc mask: lists built with a skin hold entries beyond the model's cutoff; they
 //     contribute exactly 0, so a reused list equals a fresh one (transformer/universal.py:58
 //     rebuilds per call).
@@ -24,7 +24,7 @@
 #define EAMZ_T 128
 #endif
 #ifndef EAMZ_L
-#define EAMZ_L 4          // lanes per atom (template parameter of the kernels; A/B: profiles/r02*)
+#define EAMZ_L 1          // lanes per atom (template parameter of the kernels; A/B: profiles/r02*)
 #endif
 #ifndef EAMZ_MINB_RHO
 #define EAMZ_MINB_RHO 6
@@ -32,8 +32,15 @@
 #ifndef EAMZ_MINB_FORCE
 #define EAMZ_MINB_FORCE 5
 #endif
-#ifndef EAMZ_VIR
-#define EAMZ_VIR 1        // 1: F (x) R form of the virial, 0: six FMAs on every pair
+#ifndef EAMZ_PF64
+#define EAMZ_PF64 1       // neighbour records in flight per thread (float64: 8 registers each)
+#endif
+#ifndef EAMZ_PF32
+#define EAMZ_PF32 1       // float32: 4 registers each
+#endif
+#define EAMZ_PF_MAX (TAB_SPARE_ROWS / 2)   // 2 x this many rows are readable past the last group
+#ifndef EAMZ_IDX_LD
+#define EAMZ_IDX_LD(p) __ldcs(p)     // the index stream is read once: evict-first
 #endif
 
 // ---------------------------------------------------------------------------
@@ -64,9 +71,9 @@ k_ls_fill(int n, int n_pad, uint32_t sentinel, const int *__restrict__ counts,
     constexpr int G = 32 / L;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n_pad) {
-        // the two rows after the last group (the loops prefetch two rows ahead)
+        // the rows after the last group (the loops prefetch indices 2 x EAMZ_PF rows ahead)
         const int k = idx - n_pad;
-        if (k < 64) ls_col[total_rows * 32u + k] = sentinel;
+        if (k < 32 * 2 * EAMZ_PF_MAX) ls_col[total_rows * 32u + k] = sentinel;
         return;
     }
     const int g = idx / G;
@@ -82,31 +89,48 @@ k_ls_fill(int n, int n_pad, uint32_t sentinel, const int *__restrict__ counts,
     for (int k = cnt; k < (int)(w * L); ++k) dst[(size_t)(k / L) * 32u + (k % L)] = sentinel;
 }
 
+// The arrays the kernels traverse: for L = 1 the lists themselves when the builder left them
+// sentinel-padded with spare rows (no copy), else the lane-split copy.
+struct LsView {
+    const uint32_t *ptr, *w, *col;
+};
+
 template <int L>
-static int ensure_lanesplit(tab_nbr *nbr, cudaStream_t st) {
+static int ensure_lanesplit(tab_nbr *nbr, cudaStream_t st, LsView &v) {
+    if (L == 1 && nbr->col_padded) {
+        v.ptr = nbr->slice_ptr.as<uint32_t>();
+        v.w = nbr->slice_w.as<uint32_t>();
+        v.col = nbr->col.as<uint32_t>();
+        return TAB_OK;
+    }
+    v.ptr = nbr->ls_ptr.as<uint32_t>();
+    v.w = nbr->ls_w.as<uint32_t>();
+    v.col = nbr->ls_col.as<uint32_t>();
     if (nbr->ls_L == L) return TAB_OK;
     constexpr int G = 32 / L;
     const int n = nbr->n, n_groups = (n + G - 1) / G;
     TAB_TRY(nbr->ls_ptr.ensure(sizeof(uint32_t) * (size_t)(n_groups + 2)));
+    TAB_TRY(nbr->ls_w.ensure(sizeof(uint32_t) * (size_t)(n_groups + 2)));
     TAB_TRY(nbr->stats.ensure(5 * sizeof(unsigned long long)));
     // widths of n_groups groups + one zero: the scan then leaves ls_ptr[n_groups] = total
-    TAB_CUDA(cudaMemsetAsync(nbr->ls_ptr.as<uint32_t>() + n_groups, 0, sizeof(uint32_t), st));
+    TAB_CUDA(cudaMemsetAsync(nbr->ls_w.as<uint32_t>() + n_groups, 0, sizeof(uint32_t), st));
     k_ls_widths<L><<<(n_groups + 127) / 128, 128, 0, st>>>(n, nbr->counts.as<int>(),
-                                                           nbr->ls_ptr.as<uint32_t>());
+                                                           nbr->ls_w.as<uint32_t>());
     TAB_LAUNCH_CHECK();
     unsigned long long *d_total = nbr->stats.as<unsigned long long>() + 2;
-    TAB_TRY(tab_scan_exclusive_u32(nbr->ls_ptr.as<uint32_t>(), nbr->ls_ptr.as<uint32_t>(),
+    TAB_TRY(tab_scan_exclusive_u32(nbr->ls_w.as<uint32_t>(), nbr->ls_ptr.as<uint32_t>(),
                                    n_groups + 1, d_total, nbr->scan_tmp, st));
     unsigned long long total = 0;
     TAB_CUDA(cudaMemcpyAsync(&total, d_total, sizeof(total), cudaMemcpyDeviceToHost, st));
     TAB_CUDA(cudaStreamSynchronize(st));
     nbr->ls_rows = (long long)total;
-    TAB_TRY(nbr->ls_col.ensure(sizeof(uint32_t) * 32 * (size_t)(total + 2)));
+    TAB_TRY(nbr->ls_col.ensure(sizeof(uint32_t) * 32 * (size_t)(total + 2 * EAMZ_PF_MAX)));
     const int n_pad = n_groups * G;
-    k_ls_fill<L><<<(n_pad + 64 + 127) / 128, 128, 0, st>>>(
+    k_ls_fill<L><<<(n_pad + 64 * EAMZ_PF_MAX + 127) / 128, 128, 0, st>>>(
         n, n_pad, (uint32_t)nbr->n_ext, nbr->counts.as<int>(), nbr->slice_ptr.as<uint32_t>(),
         nbr->col.as<uint32_t>(), nbr->ls_ptr.as<uint32_t>(), nbr->ls_col.as<uint32_t>(), total);
     TAB_LAUNCH_CHECK();
+    v.col = nbr->ls_col.as<uint32_t>();
     nbr->ls_L = L;
     return TAB_OK;
 }
@@ -118,6 +142,7 @@ struct LaneRow {
     bool active;
     const uint32_t *cp;
     __device__ __forceinline__ LaneRow(int n, const uint32_t *__restrict__ ls_ptr,
+                                       const uint32_t *__restrict__ ls_w,
                                        const uint32_t *__restrict__ ls_col) {
         constexpr int G = 32 / L;
         const int lane = threadIdx.x & 31;
@@ -125,15 +150,50 @@ struct LaneRow {
         idx = g * G + lane / L;
         part = lane % L;
         active = idx < n;
-        uint32_t p0 = 0, p1 = 0;
+        uint32_t p0 = 0;
+        steps = 0;
         if (g * G < n) {
             p0 = ls_ptr[g];
-            p1 = ls_ptr[g + 1];
+            steps = (int)ls_w[g];
         }
-        steps = (int)(p1 - p0);
         cp = ls_col + ((size_t)p0 * 32u + lane);
     }
 };
+
+// Software-pipelined traversal of a lane's part of the row.  D records are in flight: a ring
+// of D + 1 register slots, the record of step s + D is requested into the slot freed by step
+// s - 1 before step s is evaluated (no register copies); the entries run two ring lengths
+// further ahead (the index stream comes from DRAM).  Everything is unconditional: the rows past
+// a group are readable (next group or the sentinel rows) and hold valid indices.
+template <int D, typename Rec, typename F>
+__device__ __forceinline__ void for_each_entry(const uint32_t *__restrict__ cp, int steps,
+                                               const Rec *__restrict__ recs, F &&body) {
+    constexpr int NB = D + 1;
+    static_assert(3 * D + 2 <= 2 * EAMZ_PF_MAX, "spare rows after the last group");
+    Rec buf[NB];
+    uint32_t ci[NB], ci2[NB];
+#pragma unroll
+    for (int k = 0; k < D; ++k) buf[k] = recs[EAMZ_IDX_LD(cp + k * 32) & TAB_COL_IDX_MASK];
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+        // next use of slot k: step k + NB for k < D, step D for the free slot
+        const int s1 = k < D ? k + NB : D;
+        ci[k] = EAMZ_IDX_LD(cp + s1 * 32);
+        ci2[k] = EAMZ_IDX_LD(cp + (s1 + NB) * 32);
+    }
+    for (int t = 0; t < steps; t += NB) {
+#pragma unroll
+        for (int d = 0; d < NB; ++d) {
+            if (t + d < steps) {                 // warp-uniform
+                const int sn = (d + D) % NB;     // slot of step s + D (freed by step s - 1)
+                buf[sn] = recs[ci[sn] & TAB_COL_IDX_MASK];
+                ci[sn] = ci2[sn];
+                ci2[sn] = EAMZ_IDX_LD(cp + (size_t)(t + d + D + 2 * NB) * 32u);
+                body(buf[d]);
+            }
+        }
+    }
+}
 
 // sum over the L lanes of an atom
 template <int L, typename T>
@@ -169,7 +229,12 @@ __device__ __forceinline__ void block_partials(double (&acc)[7], double *__restr
 // (degree 5: truncation 4e-17).  The rounding of y (|y| < 2^11) costs 1.2e-15 relative.
 // 23 FP64 instructions for f and df/dr, 17 for f alone.
 // ---------------------------------------------------------------------------
+#ifndef EAMZ_RHO_TABLE
+#define EAMZ_RHO_TABLE 0  // pass 1 sits on the L1 data pipe (83 % busy, profiles/r02b): its
+#endif                    // exponential is the table-free polynomial (6 more FP64 ops, no LDS)
+
 struct ZT2 {
+    double tr, tc;        // natural exponent t = tr * r + tc  (table-free exp of pass 1)
     double yr, yc;        // y = yr * r + yc
     double ire, nkappa;   // u = r / re - kappa = ire * r + nkappa
     double c20;           // 20 / re
@@ -188,6 +253,8 @@ struct ZPair {
 
 static void zt2_fold(ZT2 &t, double a, double b, double c, double re) {
     const double S = 64.0 * 1.4426950408889634074;
+    t.tr = -b / re;
+    t.tc = b + log(a);
     t.yr = -b * S / re;
     t.yc = (b + log(a)) * S;
     t.ire = 1.0 / re;
@@ -224,24 +291,25 @@ __device__ __forceinline__ double zexp64(double y, const double *__restrict__ et
     const int n = __double2loint(zz);
     const double fr = y - (zz - SHIFT);        // exact, |fr| <= 1/2
     // exp(c fr), c = ln2 / 64
-    double e = 1.2676118923200506e-12;               // c^5 / 120
-    e = fma(e, fr, 5.8521082468723563e-10);          // c^4 / 24
-    e = fma(e, fr, 2.1614469394785756e-07);          // c^3 / 6
-    e = fma(e, fr, 5.8652907259685552e-05);          // c^2 / 2
+    double e = 1.2417843701716925e-12;               // c^5 / 120
+    e = fma(e, fr, 5.7328516886404021e-10);          // c^4 / 24
+    e = fma(e, fr, 2.1173137155464775e-07);          // c^3 / 6
+    e = fma(e, fr, 5.8649049550561697e-05);          // c^2 / 2
     e = fma(e, fr, 1.0830424696249145e-02);          // c
     e = fma(e, fr, 1.0);
     e *= etab[n & 63];
     return __hiloint2double(__double2hiint(e) + ((n >> 6) << 20), __double2loint(e));
 }
 
-template <bool DERIV>
+template <bool DERIV, bool TABLE = true>
 __device__ __forceinline__ void zt2_eval(double r, const ZT2 &p,
                                          const double *__restrict__ etab, double &f,
                                          double &df) {
     const double u = fma(r, p.ire, p.nkappa);
     const double u2 = u * u, u4 = u2 * u2, u8 = u4 * u4, u16 = u8 * u8;
     const double q = tab_rcp(fma(u16, u4, 1.0));
-    const double e = zexp64(fma(r, p.yr, p.yc), etab);
+    const double e = TABLE ? zexp64(fma(r, p.yr, p.yc), etab)
+                           : zexp<0>(fma(r, p.tr, p.tc), nullptr);
     f = e * q;
     if (DERIV) {
         // df/dr = f (-(20 / re) u^19 q - b / re)
@@ -261,33 +329,25 @@ __device__ __forceinline__ void load_exp2_tab64(double *s_tab) {
 template <int L>
 __global__ void __launch_bounds__(EAMZ_T, EAMZ_MINB_RHO)
 k_eamz_rho(int n, const Atom4 *__restrict__ atoms, const uint32_t *__restrict__ ls_ptr,
-           const uint32_t *__restrict__ ls_col, const int *__restrict__ perm, ZPair z,
+           const uint32_t *__restrict__ ls_w, const uint32_t *__restrict__ ls_col, const int *__restrict__ perm, ZPair z,
            double rc2m, tab_fn embed0, double *__restrict__ fprime,
            double *__restrict__ fembed, double *__restrict__ fprime_caller) {
-    __shared__ double s_etab[64];
-    load_exp2_tab64(s_etab);
-    const LaneRow<L> row(n, ls_ptr, ls_col);
+    __shared__ double s_etab[EAMZ_RHO_TABLE ? 64 : 1];
+    if (EAMZ_RHO_TABLE) load_exp2_tab64(s_etab);
+    const LaneRow<L> row(n, ls_ptr, ls_w, ls_col);
     double rho = 0.0;
     if (row.steps > 0) {
         Atom4 me;
         me.x = me.y = me.z = 0.0;
         if (row.active) me = atoms[row.idx];
-        uint32_t c1 = row.cp[32];
-        Atom4 a = atoms[row.cp[0] & TAB_COL_IDX_MASK];
-#pragma unroll 2
-        for (int t = 0; t < row.steps; ++t) {
-            // the records of step t + 1 and the indices of step t + 2 are in flight (the two
-            // rows after a group are readable: next group or the sentinel rows)
-            const Atom4 an = atoms[c1 & TAB_COL_IDX_MASK];
-            c1 = row.cp[(size_t)(t + 2) * 32u];
+        for_each_entry<EAMZ_PF64>(row.cp, row.steps, atoms, [&](const Atom4 &a) {
             const double dx = a.x - me.x, dy = a.y - me.y, dz = a.z - me.z;
             const double s = fma(dx, dx, fma(dy, dy, fma(dz, dz, 1e-14)));
             const double r = s * tab_rsqrt(s);
             double f, df;
-            zt2_eval<false>(r, z.rho, s_etab, f, df);
+            zt2_eval<false, EAMZ_RHO_TABLE != 0>(r, z.rho, s_etab, f, df);
             rho += s < rc2m ? f : 0.0;
-            a = an;
-        }
+        });
     }
     rho = lanes_sum<L>(rho);
     if (row.active && row.part == 0) {
@@ -302,40 +362,28 @@ k_eamz_rho(int n, const Atom4 *__restrict__ atoms, const uint32_t *__restrict__ 
 // ---------------------------------------------------------------------------
 // pass 2, float64.  Atom4.w holds  w = F'(rho) fe / B - 1/2  (k_spread_w with scale and shift),
 // so that  dE/dr = (F'_i + F'_j) rho'(r) + phi'(r) = (w_i + w_j) B-term' + A-term'.
-// n_real: list entries below it are own, non-image atoms.
+// Virial: every undirected pair is visited from both ends, half of g (x) D each.
+// (The form  W = -sum_i F_i^real (x) R_i + 1/2 sum_{image pairs} g (x) D  saves the six
+// per-pair FMAs but was SLOWER on the 1 M-atom box, 0.79 vs 0.68 ms: the warps next to the
+// box faces -- 17 % of all -- take the image branch on nearly every step.  profiles/r02a.)
 // ---------------------------------------------------------------------------
-template <int L, int VIR>
+template <int L>
 __global__ void __launch_bounds__(EAMZ_T, EAMZ_MINB_FORCE)
-k_eamz_force(int n, int n_real, const Atom4 *__restrict__ atoms,
-             const uint32_t *__restrict__ ls_ptr, const uint32_t *__restrict__ ls_col,
-             const int *__restrict__ perm, ZPair z, double rc2m,
-             const double *__restrict__ fembed, double *__restrict__ eatom,
+k_eamz_force(int n, const Atom4 *__restrict__ atoms, const uint32_t *__restrict__ ls_ptr,
+             const uint32_t *__restrict__ ls_w, const uint32_t *__restrict__ ls_col, const int *__restrict__ perm, ZPair z,
+             double rc2m, const double *__restrict__ fembed, double *__restrict__ eatom,
              double *__restrict__ forces, double *__restrict__ partial,
              const int *__restrict__ own_mask) {
     __shared__ double s_etab[64];
-    // VIR == 1: image / halo pairs are rare; their sums live in shared memory, not registers
-    __shared__ double s_gh[VIR ? 9 : 1][EAMZ_T];
     load_exp2_tab64(s_etab);
-    const LaneRow<L> row(n, ls_ptr, ls_col);
+    const LaneRow<L> row(n, ls_ptr, ls_w, ls_col);
     double fx = 0, fy = 0, fz = 0, ep = 0;
     double vxx = 0, vyy = 0, vzz = 0, vyz = 0, vxz = 0, vxy = 0;
-    if (VIR) {
-#pragma unroll
-        for (int q = 0; q < 9; ++q) s_gh[q][threadIdx.x] = 0.0;
-    }
-    Atom4 me;
-    me.x = me.y = me.z = me.w = 0.0;
-    if (row.active) me = atoms[row.idx];
     if (row.steps > 0) {
-        uint32_t c0 = row.cp[0];
-        uint32_t c1 = row.cp[32];
-        Atom4 a = atoms[c0 & TAB_COL_IDX_MASK];
-#pragma unroll 2
-        for (int t = 0; t < row.steps; ++t) {
-            const Atom4 an = atoms[c1 & TAB_COL_IDX_MASK];
-            const uint32_t cc = c0;
-            c0 = c1;
-            c1 = row.cp[(size_t)(t + 2) * 32u];
+        Atom4 me;
+        me.x = me.y = me.z = me.w = 0.0;
+        if (row.active) me = atoms[row.idx];
+        for_each_entry<EAMZ_PF64>(row.cp, row.steps, atoms, [&](const Atom4 &a) {
             const double dx = a.x - me.x, dy = a.y - me.y, dz = a.z - me.z;
             const double s = fma(dx, dx, fma(dy, dy, fma(dz, dz, 1e-14)));
             const double rinv = tab_rsqrt(s);
@@ -347,57 +395,25 @@ k_eamz_force(int n, int n_real, const Atom4 *__restrict__ atoms,
             const double der = fma(me.w + a.w, dgb, dga);
             const double sc = in ? der * rinv : 0.0;
             ep += in ? ga - gb : 0.0;
-            if (VIR) {
-                fx = fma(sc, dx, fx);
-                fy = fma(sc, dy, fy);
-                fz = fma(sc, dz, fz);
-                if (in && (int)(cc & TAB_COL_IDX_MASK) >= n_real) {
-                    const double gx = sc * dx, gy = sc * dy, gz = sc * dz;
-                    volatile double *g = &s_gh[0][threadIdx.x];   // keep the sums OUT of registers
-                    g[0 * EAMZ_T] += gx;
-                    g[1 * EAMZ_T] += gy;
-                    g[2 * EAMZ_T] += gz;
-                    g[3 * EAMZ_T] = fma(gx, dx, g[3 * EAMZ_T]);
-                    g[4 * EAMZ_T] = fma(gy, dy, g[4 * EAMZ_T]);
-                    g[5 * EAMZ_T] = fma(gz, dz, g[5 * EAMZ_T]);
-                    g[6 * EAMZ_T] = fma(gy, dz, g[6 * EAMZ_T]);
-                    g[7 * EAMZ_T] = fma(gx, dz, g[7 * EAMZ_T]);
-                    g[8 * EAMZ_T] = fma(gx, dy, g[8 * EAMZ_T]);
-                }
-            } else {
-                const double gx = sc * dx, gy = sc * dy, gz = sc * dz;
-                fx += gx;
-                fy += gy;
-                fz += gz;
-                vxx = fma(gx, dx, vxx);
-                vyy = fma(gy, dy, vyy);
-                vzz = fma(gz, dz, vzz);
-                vyz = fma(gy, dz, vyz);
-                vxz = fma(gx, dz, vxz);
-                vxy = fma(gx, dy, vxy);
-            }
-            a = an;
-        }
+            const double gx = sc * dx, gy = sc * dy, gz = sc * dz;
+            fx += gx;
+            fy += gy;
+            fz += gz;
+            vxx = fma(gx, dx, vxx);
+            vyy = fma(gy, dy, vyy);
+            vzz = fma(gz, dz, vzz);
+            vyz = fma(gy, dz, vyz);
+            vxz = fma(gx, dz, vxz);
+            vxy = fma(gx, dy, vxy);
+        });
     }
     double acc[7];
-    if (VIR) {
-        // this lane's share:  -(f - f_gh) (x) R_i + 1/2 sum_gh g (x) D   (symmetric part)
-        const double *g = &s_gh[0][threadIdx.x];
-        const double rx = fx - g[0 * EAMZ_T], ry = fy - g[1 * EAMZ_T], rz = fz - g[2 * EAMZ_T];
-        acc[1] = fma(-rx, me.x, 0.5 * g[3 * EAMZ_T]);
-        acc[2] = fma(-ry, me.y, 0.5 * g[4 * EAMZ_T]);
-        acc[3] = fma(-rz, me.z, 0.5 * g[5 * EAMZ_T]);
-        acc[4] = 0.5 * (g[6 * EAMZ_T] - fma(ry, me.z, rz * me.y));
-        acc[5] = 0.5 * (g[7 * EAMZ_T] - fma(rx, me.z, rz * me.x));
-        acc[6] = 0.5 * (g[8 * EAMZ_T] - fma(rx, me.y, ry * me.x));
-    } else {
-        acc[1] = 0.5 * vxx;
-        acc[2] = 0.5 * vyy;
-        acc[3] = 0.5 * vzz;
-        acc[4] = 0.5 * vyz;
-        acc[5] = 0.5 * vxz;
-        acc[6] = 0.5 * vxy;
-    }
+    acc[1] = 0.5 * vxx;
+    acc[2] = 0.5 * vyy;
+    acc[3] = 0.5 * vzz;
+    acc[4] = 0.5 * vyz;
+    acc[5] = 0.5 * vxz;
+    acc[6] = 0.5 * vxy;
     fx = lanes_sum<L>(fx);
     fy = lanes_sum<L>(fy);
     fz = lanes_sum<L>(fz);
@@ -456,21 +472,16 @@ __device__ __forceinline__ float f_rsqrt(float x) {
 template <int L>
 __global__ void __launch_bounds__(EAMZ_T, 8)
 k_eamz_rho_f32(int n, const Rec16 *__restrict__ recs, const uint32_t *__restrict__ ls_ptr,
-               const uint32_t *__restrict__ ls_col, const int *__restrict__ perm, ZPair z,
+               const uint32_t *__restrict__ ls_w, const uint32_t *__restrict__ ls_col, const int *__restrict__ perm, ZPair z,
                QScale qs, tab_fn embed0, double *__restrict__ fprime,
                double *__restrict__ fembed, double *__restrict__ fprime_caller) {
-    const LaneRow<L> row(n, ls_ptr, ls_col);
+    const LaneRow<L> row(n, ls_ptr, ls_w, ls_col);
     float rho = 0.f;
     if (row.steps > 0) {
         Rec16 me;
         me.qx = me.qy = me.qz = 0;
         if (row.active) me = recs[row.idx];
-        uint32_t c1 = row.cp[32];
-        Rec16 a = recs[row.cp[0] & TAB_COL_IDX_MASK];
-#pragma unroll 2
-        for (int t = 0; t < row.steps; ++t) {
-            const Rec16 an = recs[c1 & TAB_COL_IDX_MASK];
-            c1 = row.cp[(size_t)(t + 2) * 32u];
+        for_each_entry<EAMZ_PF32>(row.cp, row.steps, recs, [&](const Rec16 &a) {
             const float dx = (float)(a.qx - me.qx), dy = (float)(a.qy - me.qy),
                         dz = (float)(a.qz - me.qz);
             const float s = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, qs.eps_q)));
@@ -479,8 +490,7 @@ k_eamz_rho_f32(int n, const Rec16 *__restrict__ recs, const uint32_t *__restrict
             const float u2 = u * u, u4 = u2 * u2, u8 = u4 * u4, u16 = u8 * u8;
             const float f = f_ex2(fmaf(x, z.f_yx_rho, z.f_yc_rho)) * f_rcp(fmaf(u16, u4, 1.f));
             rho += s < qs.rc2_q ? f : 0.f;
-            a = an;
-        }
+        });
     }
     rho = lanes_sum<L>(rho);
     if (row.active && row.part == 0) {
@@ -492,40 +502,23 @@ k_eamz_rho_f32(int n, const Rec16 *__restrict__ recs, const uint32_t *__restrict
     }
 }
 
-// Rec16.w = F'(rho) fe / B - 1/2 as in the float64 kernel.  The F (x) R form of the virial takes
-// the positions relative to the block's first atom (float32 force sums times 200 A coordinates
-// would cost two digits): the block also sums its real-pair forces, which carry the offset.
-template <int L, int VIR>
+// Rec16.w = F'(rho) fe / B - 1/2 as in the float64 kernel.
+template <int L>
 __global__ void __launch_bounds__(EAMZ_T, 8)
-k_eamz_force_f32(int n, int n_real, const Rec16 *__restrict__ recs,
-                 const uint32_t *__restrict__ ls_ptr, const uint32_t *__restrict__ ls_col,
-                 const int *__restrict__ perm, ZPair z, QScale qs,
-                 const double *__restrict__ fembed, double *__restrict__ eatom,
+k_eamz_force_f32(int n, const Rec16 *__restrict__ recs, const uint32_t *__restrict__ ls_ptr,
+                 const uint32_t *__restrict__ ls_w, const uint32_t *__restrict__ ls_col, const int *__restrict__ perm, ZPair z,
+                 QScale qs, const double *__restrict__ fembed, double *__restrict__ eatom,
                  double *__restrict__ forces, double *__restrict__ partial,
                  const int *__restrict__ own_mask) {
-    __shared__ float s_gh[VIR ? 9 : 1][EAMZ_T];
-    __shared__ double s_f3[EAMZ_T / 32][3];
-    const LaneRow<L> row(n, ls_ptr, ls_col);
+    const LaneRow<L> row(n, ls_ptr, ls_w, ls_col);
     float fx = 0, fy = 0, fz = 0, ep = 0;
     float vxx = 0, vyy = 0, vzz = 0, vyz = 0, vxz = 0, vxy = 0;
-    if (VIR) {
-#pragma unroll
-        for (int q = 0; q < 9; ++q) s_gh[q][threadIdx.x] = 0.f;
-    }
-    Rec16 me;
-    me.qx = me.qy = me.qz = 0;
-    me.w = 0.f;
-    if (row.active) me = recs[row.idx];
     if (row.steps > 0) {
-        uint32_t c0 = row.cp[0];
-        uint32_t c1 = row.cp[32];
-        Rec16 a = recs[c0 & TAB_COL_IDX_MASK];
-#pragma unroll 2
-        for (int t = 0; t < row.steps; ++t) {
-            const Rec16 an = recs[c1 & TAB_COL_IDX_MASK];
-            const uint32_t cc = c0;
-            c0 = c1;
-            c1 = row.cp[(size_t)(t + 2) * 32u];
+        Rec16 me;
+        me.qx = me.qy = me.qz = 0;
+        me.w = 0.f;
+        if (row.active) me = recs[row.idx];
+        for_each_entry<EAMZ_PF32>(row.cp, row.steps, recs, [&](const Rec16 &a) {
             const float dx = (float)(a.qx - me.qx), dy = (float)(a.qy - me.qy),
                         dz = (float)(a.qz - me.qz);
             const float s = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, qs.eps_q)));
@@ -548,68 +541,26 @@ k_eamz_force_f32(int n, int n_real, const Rec16 *__restrict__ recs,
             // (dE/dr / r) D = (dE/dr / (delta r_q)) (delta D_q): delta cancels
             const float sc = in ? der * rinv : 0.f;
             ep += in ? ga - gb : 0.f;
-            if (VIR) {
-                fx = fmaf(sc, dx, fx);
-                fy = fmaf(sc, dy, fy);
-                fz = fmaf(sc, dz, fz);
-                if (in && (int)(cc & TAB_COL_IDX_MASK) >= n_real) {
-                    const float gx = sc * dx, gy = sc * dy, gz = sc * dz;
-                    volatile float *g = &s_gh[0][threadIdx.x];
-                    g[0 * EAMZ_T] += gx;
-                    g[1 * EAMZ_T] += gy;
-                    g[2 * EAMZ_T] += gz;
-                    g[3 * EAMZ_T] = fmaf(gx, dx, g[3 * EAMZ_T]);
-                    g[4 * EAMZ_T] = fmaf(gy, dy, g[4 * EAMZ_T]);
-                    g[5 * EAMZ_T] = fmaf(gz, dz, g[5 * EAMZ_T]);
-                    g[6 * EAMZ_T] = fmaf(gy, dz, g[6 * EAMZ_T]);
-                    g[7 * EAMZ_T] = fmaf(gx, dz, g[7 * EAMZ_T]);
-                    g[8 * EAMZ_T] = fmaf(gx, dy, g[8 * EAMZ_T]);
-                }
-            } else {
-                const float gx = sc * dx, gy = sc * dy, gz = sc * dz;
-                fx += gx;
-                fy += gy;
-                fz += gz;
-                vxx = fmaf(gx, dx, vxx);
-                vyy = fmaf(gy, dy, vyy);
-                vzz = fmaf(gz, dz, vzz);
-                vyz = fmaf(gy, dz, vyz);
-                vxz = fmaf(gx, dz, vxz);
-                vxy = fmaf(gx, dy, vxy);
-            }
-            a = an;
-        }
+            const float gx = sc * dx, gy = sc * dy, gz = sc * dz;
+            fx += gx;
+            fy += gy;
+            fz += gz;
+            vxx = fmaf(gx, dx, vxx);
+            vyy = fmaf(gy, dy, vyy);
+            vzz = fmaf(gz, dz, vzz);
+            vyz = fmaf(gy, dz, vyz);
+            vxz = fmaf(gx, dz, vxz);
+            vxy = fmaf(gx, dy, vxy);
+        });
     }
     double acc[7];
-    const double hd = 0.5 * qs.ddelta;
-    double frx = 0.0, fry = 0.0, frz = 0.0;     // this lane's real-pair force sums
-    if (VIR) {
-        const float *g = &s_gh[0][threadIdx.x];
-        // block origin = first atom of the block (always exists)
-        const int first = (int)((blockIdx.x * blockDim.x) >> 5) * (32 / L);
-        const Rec16 org = recs[first];
-        const double px = (double)(me.qx - org.qx) * qs.ddelta,
-                     py = (double)(me.qy - org.qy) * qs.ddelta,
-                     pz = (double)(me.qz - org.qz) * qs.ddelta;
-        if (row.active) {
-            frx = (double)(fx - g[0 * EAMZ_T]);
-            fry = (double)(fy - g[1 * EAMZ_T]);
-            frz = (double)(fz - g[2 * EAMZ_T]);
-        }
-        acc[1] = fma(-frx, px, hd * (double)g[3 * EAMZ_T]);
-        acc[2] = fma(-fry, py, hd * (double)g[4 * EAMZ_T]);
-        acc[3] = fma(-frz, pz, hd * (double)g[5 * EAMZ_T]);
-        acc[4] = fma(hd, (double)g[6 * EAMZ_T], -0.5 * fma(fry, pz, frz * py));
-        acc[5] = fma(hd, (double)g[7 * EAMZ_T], -0.5 * fma(frx, pz, frz * px));
-        acc[6] = fma(hd, (double)g[8 * EAMZ_T], -0.5 * fma(frx, py, fry * px));
-    } else {
-        acc[1] = hd * (double)vxx;
-        acc[2] = hd * (double)vyy;
-        acc[3] = hd * (double)vzz;
-        acc[4] = hd * (double)vyz;
-        acc[5] = hd * (double)vxz;
-        acc[6] = hd * (double)vxy;
-    }
+    const double hd = 0.5 * qs.ddelta;      // g (x) D_q carries one factor delta
+    acc[1] = hd * (double)vxx;
+    acc[2] = hd * (double)vyy;
+    acc[3] = hd * (double)vzz;
+    acc[4] = hd * (double)vyz;
+    acc[5] = hd * (double)vxz;
+    acc[6] = hd * (double)vxy;
     fx = lanes_sum<L>(fx);
     fy = lanes_sum<L>(fy);
     fz = lanes_sum<L>(fz);
@@ -633,41 +584,6 @@ k_eamz_force_f32(int n, int n_real, const Rec16 *__restrict__ recs,
     if (!mine || !row.active)
 #pragma unroll
         for (int q = 0; q < 7; ++q) acc[q] = 0.0;
-    if (VIR) {
-        // - (sum of the block's real-pair forces) (x) block origin
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            frx += __shfl_xor_sync(0xffffffffu, frx, d);
-            fry += __shfl_xor_sync(0xffffffffu, fry, d);
-            frz += __shfl_xor_sync(0xffffffffu, frz, d);
-        }
-        if ((threadIdx.x & 31) == 0) {
-            s_f3[threadIdx.x >> 5][0] = frx;
-            s_f3[threadIdx.x >> 5][1] = fry;
-            s_f3[threadIdx.x >> 5][2] = frz;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double bx = 0, by = 0, bz = 0;
-#pragma unroll
-            for (int w = 0; w < EAMZ_T / 32; ++w) {
-                bx += s_f3[w][0];
-                by += s_f3[w][1];
-                bz += s_f3[w][2];
-            }
-            const int first = (int)((blockIdx.x * blockDim.x) >> 5) * (32 / L);
-            const Rec16 org = recs[first];
-            const double ox = fma((double)org.qx, qs.ddelta, qs.ox),
-                         oy = fma((double)org.qy, qs.ddelta, qs.oy),
-                         oz = fma((double)org.qz, qs.ddelta, qs.oz);
-            acc[1] -= bx * ox;
-            acc[2] -= by * oy;
-            acc[3] -= bz * oz;
-            acc[4] -= 0.5 * (by * oz + bz * oy);
-            acc[5] -= 0.5 * (bx * oz + bz * ox);
-            acc[6] -= 0.5 * (bx * oy + by * ox);
-        }
-    }
     block_partials(acc, partial);
 }
 

@@ -407,7 +407,7 @@ k_fill(int n, Grid g, ExactCtx x, const int *__restrict__ cell_of,
        const uint4 *__restrict__ ext_tab, int n_types,
        const int *__restrict__ tcounts,
        const uint32_t *__restrict__ slice_w,
-       const uint32_t *__restrict__ slice_ptr, uint32_t *__restrict__ col) {
+       const uint32_t *__restrict__ slice_ptr, uint32_t *__restrict__ col, uint32_t pad) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int s = idx >> 5, lane = idx & 31;
     if (s >= (n + 31) / 32) return;
@@ -437,7 +437,7 @@ k_fill(int n, Grid g, ExactCtx x, const int *__restrict__ cell_of,
         }
     }
     const uint32_t w = slice_w[s];
-    for (; k < w; ++k) base[(size_t)k * 32u] = TAB_COL_PAD;
+    for (; k < w; ++k) base[(size_t)k * 32u] = pad;
 }
 
 // ---- warp-per-atom variants (small systems: the 32 lanes test 32 candidates at a
@@ -449,7 +449,7 @@ k_nbr_warp(int n, Grid g, ExactCtx x, const int *__restrict__ cell_of,
            const Atom4 *__restrict__ atoms, const uint8_t *__restrict__ types_ext,
            const uint4 *__restrict__ ext_tab, int n_types, int *__restrict__ counts,
            int *__restrict__ tcounts, const uint32_t *__restrict__ slice_w,
-           const uint32_t *__restrict__ slice_ptr, uint32_t *__restrict__ col) {
+           const uint32_t *__restrict__ slice_ptr, uint32_t *__restrict__ col, uint32_t pad) {
     const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (idx >= n) return;
@@ -531,7 +531,7 @@ k_nbr_warp(int n, Grid g, ExactCtx x, const int *__restrict__ cell_of,
         // pad the rest of this atom's column up to the slice width
         const uint32_t w = slice_w[idx >> 5];
         const uint32_t have = (uint32_t)counts[idx];
-        for (uint32_t k = have + lane; k < w; k += 32) base[(size_t)k * 32u] = TAB_COL_PAD;
+        for (uint32_t k = have + lane; k < w; k += 32) base[(size_t)k * 32u] = pad;
     }
 }
 
@@ -847,12 +847,30 @@ __global__ void k_slice_stats(int n, const int *__restrict__ counts,
 // columns of the padding lanes of the last (partial) slice
 __global__ void k_pad_tail(int n, const uint32_t *__restrict__ slice_w,
                            const uint32_t *__restrict__ slice_ptr,
-                           uint32_t *__restrict__ col) {
+                           uint32_t *__restrict__ col, uint32_t pad) {
     const int lane = threadIdx.x & 31;
     const int s = (n - 1) >> 5;
     if (s * 32 + lane < n) return;
     uint32_t *base = col + ((size_t)slice_ptr[s] * 32u + lane);
-    for (uint32_t k = 0; k < slice_w[s]; ++k) base[(size_t)k * 32u] = TAB_COL_PAD;
+    for (uint32_t k = 0; k < slice_w[s]; ++k) base[(size_t)k * 32u] = pad;
+}
+
+// Rows that pair loops may read without looking at the counts (eam_fast.cuh): every slot
+// past an atom's count up to the slice width holds the SENTINEL entry, and so do `extra` rows
+// after the slice (fixed-stride rows: up to the stride; compact rows: only after the last slice,
+// the rows after any other slice are the next slice's, initialised the same way).
+__global__ void __launch_bounds__(128)
+k_pad_sentinel(int n, int n_slices, uint32_t pad, uint32_t extra, uint32_t stride,
+               const int *__restrict__ counts, const uint32_t *__restrict__ slice_w,
+               const uint32_t *__restrict__ slice_ptr, uint32_t *__restrict__ col) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = idx >> 5;
+    if (s >= n_slices) return;
+    const uint32_t cnt = idx < n ? (uint32_t)counts[idx] : 0u;
+    uint32_t hi = slice_w[s] + extra;
+    if (s != n_slices - 1) hi = stride ? min(hi, stride) : slice_w[s];
+    uint32_t *base = col + ((size_t)slice_ptr[s] * 32u + (idx & 31));
+    for (uint32_t k = cnt; k < hi; ++k) base[(size_t)k * 32u] = pad;
 }
 
 __global__ void k_scatter_counts(int n, const int *__restrict__ perm,
@@ -1043,7 +1061,8 @@ extern "C" int tab_nbr_free(tab_nbr *nbr) {
                       &nbr->slice_w, &nbr->slice_ptr, &nbr->col, &nbr->scan_tmp,
                       &nbr->stats, &nbr->row_ptr, &nbr->rho, &nbr->partial, &nbr->adp,
                       &nbr->tcounts, &nbr->rev, &nbr->pcache, &nbr->rows_tmp,
-                      &nbr->pos_ref, &nbr->disp, &nbr->ls_ptr, &nbr->ls_col, &nbr->rec16};
+                      &nbr->pos_ref, &nbr->disp, &nbr->ls_ptr, &nbr->ls_col, &nbr->ls_w,
+                      &nbr->rec16};
     for (DevBuf *b : bufs) b->release();
     delete nbr;
     return TAB_OK;
@@ -1184,6 +1203,7 @@ extern "C" int tab_nbr_build_dd(tab_nbr *nbr, int32_t n_owned, int32_t n_halo,
     nbr->n_struct = 0;          // single structure (a batch handle may be reused)
     nbr->has_row_ptr = false;
     nbr->ls_L = 0;
+    nbr->col_padded = false;
     nbr->rec16_valid = false;
     // lists with a skin: radius rc + skin, the pair kernels mask r >= rc
     nbr->rc_model = rc;
@@ -1347,7 +1367,7 @@ extern "C" int tab_nbr_build_dd(tab_nbr *nbr, int32_t n_owned, int32_t n_halo,
         }
         wcap = (wcap + 7u) & ~7u;
         for (int attempt = 0;; ++attempt) {
-            const size_t row_words = (size_t)nbr->n_slices * wcap * 32u + 32u;
+            const size_t row_words = ((size_t)nbr->n_slices * wcap + TAB_SPARE_ROWS) * 32u + 32u;
             DevBuf &rows = multi ? nbr->rows_tmp : nbr->col;
             TAB_TRY(rows.ensure(sizeof(uint32_t) * row_words));
             k_nbr_tile<<<n_tiles, NBT_THREADS, 0, st>>>(
@@ -1392,6 +1412,14 @@ extern "C" int tab_nbr_build_dd(tab_nbr *nbr, int32_t n_owned, int32_t n_halo,
             k_fixed_slices<<<nblocks(max(n, nbr->n_slices), 256), 256, 0, st>>>(
                 n, nbr->n_slices, wcap, nbr->counts.as<int>(), nbr->slice_ptr.as<uint32_t>(),
                 nbr->tcounts.as<int>());
+            TAB_LAUNCH_CHECK();
+            // fixed-stride rows: sentinel entries past the counts (and the spare rows, which for
+            // the last slice lie beyond the stride: the buffer holds TAB_SPARE_ROWS more)
+            k_pad_sentinel<<<nblocks(nthreads, 128), 128, 0, st>>>(
+                n, nbr->n_slices, (uint32_t)nbr->n_ext, TAB_SPARE_ROWS, wcap,
+                nbr->counts.as<int>(), nbr->slice_w.as<uint32_t>(),
+                nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>());
+            nbr->col_padded = true;
         }
         TAB_LAUNCH_CHECK();
         nbr->wcap_hint = (uint32_t)(nbr->nnl_max + nbr->nnl_max / 8 + 24);
@@ -1404,7 +1432,7 @@ extern "C" int tab_nbr_build_dd(tab_nbr *nbr, int32_t n_owned, int32_t n_halo,
         k_nbr_warp<false><<<nblocks((long long)n * 32, 128), 128, 0, st>>>(
             n, g, x, nbr->cell_of.as<int>(), nbr->atoms.as<Atom4>(),
             nbr->types_ext.as<uint8_t>(), nbr->ext_tab.as<uint4>(), nbr->n_types,
-            nbr->counts.as<int>(), nbr->tcounts.as<int>(), nullptr, nullptr, nullptr);
+            nbr->counts.as<int>(), nbr->tcounts.as<int>(), nullptr, nullptr, nullptr, 0u);
     } else {
         k_count<<<nblocks(n, 128), 128, 0, st>>>(
             n, g, x, nbr->cell_of.as<int>(), nbr->atoms.as<Atom4>(),
@@ -1427,18 +1455,18 @@ extern "C" int tab_nbr_build_dd(tab_nbr *nbr, int32_t n_owned, int32_t n_halo,
         tab_set_error("neighbour table too large (%lld rows)", nbr->ell_rows);
         return TAB_EUNSUPPORTED;
     }
-    TAB_TRY(nbr->col.ensure(sizeof(uint32_t) * 32 * (size_t)(nbr->ell_rows + 1)));
+    TAB_TRY(nbr->col.ensure(sizeof(uint32_t) * 32 * (size_t)(nbr->ell_rows + 1 + TAB_SPARE_ROWS)));
     if (warp_mode) {
         k_nbr_warp<true><<<nblocks((long long)n * 32, 128), 128, 0, st>>>(
             n, g, x, nbr->cell_of.as<int>(), nbr->atoms.as<Atom4>(),
             nbr->types_ext.as<uint8_t>(), nbr->ext_tab.as<uint4>(), nbr->n_types,
             nbr->counts.as<int>(), nbr->tcounts.as<int>(), nbr->slice_w.as<uint32_t>(),
-            nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>());
+            nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>(), (uint32_t)nbr->n_ext);
         TAB_LAUNCH_CHECK();
         if (n & 31) {
             k_pad_tail<<<1, 32, 0, st>>>(n, nbr->slice_w.as<uint32_t>(),
                                          nbr->slice_ptr.as<uint32_t>(),
-                                         nbr->col.as<uint32_t>());
+                                         nbr->col.as<uint32_t>(), (uint32_t)nbr->n_ext);
             TAB_LAUNCH_CHECK();
         }
     } else {
@@ -1446,9 +1474,15 @@ extern "C" int tab_nbr_build_dd(tab_nbr *nbr, int32_t n_owned, int32_t n_halo,
             n, g, x, nbr->cell_of.as<int>(), nbr->atoms.as<Atom4>(),
             nbr->types_ext.as<uint8_t>(), nbr->ext_tab.as<uint4>(), nbr->n_types,
             nbr->tcounts.as<int>(), nbr->slice_w.as<uint32_t>(),
-            nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>());
+            nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>(), (uint32_t)nbr->n_ext);
         TAB_LAUNCH_CHECK();
     }
+    // the spare rows after the last slice
+    k_pad_sentinel<<<nblocks(nthreads, 128), 128, 0, st>>>(
+        n, nbr->n_slices, (uint32_t)nbr->n_ext, TAB_SPARE_ROWS, 0u, nbr->counts.as<int>(),
+        nbr->slice_w.as<uint32_t>(), nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>());
+    TAB_LAUNCH_CHECK();
+    nbr->col_padded = true;
     nbr->built = true;
     return TAB_OK;
 }
@@ -1614,13 +1648,24 @@ __global__ void k_peer_put(int n, int n_peers, int slot, const double *__restric
     dst[(size_t)slot * n + q] = src[q];
 }
 
-__global__ void k_sum_slots(int n_slots, int n, const double *__restrict__ slots,
+// entries [0, n_sum) are summed in rank order, entries [n_sum, n) reduced with max
+__global__ void k_sum_slots(int n_slots, int n, int n_sum, const double *__restrict__ slots,
                             double *__restrict__ out) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n) return;
     double v = 0.0;
-    for (int s = 0; s < n_slots; ++s) v += slots[(size_t)s * n + q];   // fixed order
+    if (q < n_sum) {
+        for (int s = 0; s < n_slots; ++s) v += slots[(size_t)s * n + q];   // fixed order
+    } else {
+        v = slots[q];
+        for (int s = 1; s < n_slots; ++s) v = fmax(v, slots[(size_t)s * n + q]);
+    }
     out[q] = v;
+}
+
+__global__ void k_disp_to(const unsigned int *__restrict__ disp, double *__restrict__ out) {
+    const float d2 = __uint_as_float(disp[0]);
+    out[0] = d2 == d2 ? sqrt((double)d2) : (double)INFINITY;
 }
 
 extern "C" int tab_peer_put(const double *d_src, int32_t n, const uint64_t *d_peer_ptrs,
@@ -1641,7 +1686,34 @@ extern "C" int tab_sum_slots(const double *d_slots, int32_t n_slots, int32_t n,
         tab_set_error("tab_sum_slots: bad argument");
         return TAB_EINVAL;
     }
-    k_sum_slots<<<nblocks(n, 128), 128, 0, (cudaStream_t)stream>>>(n_slots, n, d_slots, d_out);
+    k_sum_slots<<<nblocks(n, 128), 128, 0, (cudaStream_t)stream>>>(n_slots, n, n, d_slots, d_out);
+    TAB_LAUNCH_CHECK();
+    return TAB_OK;
+}
+
+extern "C" int tab_reduce_slots(const double *d_slots, int32_t n_slots, int32_t n,
+                                int32_t n_sum, double *d_out, void *stream) {
+    if (!d_slots || !d_out || n <= 0 || n_slots <= 0 || n_sum < 0 || n_sum > n) {
+        tab_set_error("tab_reduce_slots: bad argument");
+        return TAB_EINVAL;
+    }
+    k_sum_slots<<<nblocks(n, 128), 128, 0, (cudaStream_t)stream>>>(n_slots, n, n_sum, d_slots,
+                                                                  d_out);
+    TAB_LAUNCH_CHECK();
+    return TAB_OK;
+}
+
+extern "C" int tab_nbr_displacement_device(tab_nbr *nbr, double *d_out, void *stream) {
+    if (!nbr || !d_out) return TAB_EINVAL;
+    if (!nbr->built) {
+        tab_set_error("tab_nbr_displacement_device before tab_nbr_build");
+        return TAB_ESTATE;
+    }
+    if (!(nbr->skin_built > 0.0)) {
+        tab_set_error("tab_nbr_displacement_device: the lists carry no skin");
+        return TAB_ESTATE;
+    }
+    k_disp_to<<<1, 1, 0, (cudaStream_t)stream>>>(nbr->disp.as<unsigned int>(), d_out);
     TAB_LAUNCH_CHECK();
     return TAB_OK;
 }

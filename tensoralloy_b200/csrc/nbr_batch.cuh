@@ -244,7 +244,7 @@ kb_nbr(int N, double rc, const BStruct *__restrict__ S, const int *__restrict__ 
     } else {
         const uint32_t w = slice_w[idx >> 5];
         const uint32_t have = (uint32_t)counts[idx];
-        for (uint32_t k = have + lane; k < w; k += 32) base[(size_t)k * 32u] = TAB_COL_PAD;
+        for (uint32_t k = have + lane; k < w; k += 32) base[(size_t)k * 32u] = TAB_COL_PAD;   // batch rows are read through the counts only
     }
 }
 
@@ -266,6 +266,7 @@ extern "C" int tab_nbr_build_batch(tab_nbr *nbr, int32_t n_struct, const int32_t
     nbr->skin_built = 0.0;      // batch handles are rebuilt per batch: no skin
     nbr->rc_model = rc;
     nbr->ls_L = 0;
+    nbr->col_padded = false;
     nbr->rec16_valid = false;
     nbr->pcache_valid = false;
     nbr->has_rev = false;
@@ -440,7 +441,8 @@ extern "C" int tab_nbr_build_batch(tab_nbr *nbr, int32_t n_struct, const int32_t
     TAB_LAUNCH_CHECK();
     if (N & 31) {
         k_pad_tail<<<1, 32, 0, st>>>(N, nbr->slice_w.as<uint32_t>(),
-                                     nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>());
+                                     nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>(),
+                                     TAB_COL_PAD);
         TAB_LAUNCH_CHECK();
     }
     nbr->built = true;

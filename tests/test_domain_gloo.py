@@ -122,3 +122,63 @@ def test_flat_gradient_allreduce_mean_gloo():
     for rank, ga, gb in results:
         assert ga == [[1.5, 1.5]] * 3
         assert gb == [0.0, 0.5, 1.0, 1.5]
+
+
+def _migrate_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from tensoralloy_b200.atoms import fcc_positions
+        from tensoralloy_b200.domain import DistComm, SlabLayout
+        rc, skin = 6.5, 0.4
+        pos, cell = fcc_positions(3.52, 4 * world, 3, 3)
+        rng = np.random.default_rng(611)
+        pos = pos + rng.normal(scale=0.05, size=pos.shape)
+        lx = cell[0, 0]
+        pos[:, 0] = np.mod(pos[:, 0], lx)
+        lay = SlabLayout(lx, world, rank, rc, skin)
+        ids = np.flatnonzero(lay.owned_mask(pos[:, 0]))
+        comm = DistComm(lay)
+        state = torch.from_numpy(np.concatenate(
+            [pos[ids], np.zeros((len(ids), 3)), ids[:, None].astype(np.float64)], axis=1))
+        ok = True
+        for cycle in range(4):
+            # every atom drifts to the right by up to 1.5 A (same field on all ranks, by id):
+            # some leave through the high face, rank world - 1 wraps them to rank 0
+            drift = np.random.default_rng(cycle).uniform(0.0, 1.5, size=len(pos))
+            state[:, 0] += torch.from_numpy(drift[state[:, 6].numpy().astype(np.int64)])
+            state = comm.migrate(state)
+            x = state[:, 0].numpy()
+            ok = ok and bool(np.all(lay.owned_mask(x)) and np.all(x >= lay.lo - 1e-12))
+            n = torch.tensor([float(state.shape[0])], dtype=torch.float64)
+            comm.allreduce_sum(n)
+            ok = ok and int(n.item()) == len(pos)
+        # ids: every atom exactly once over the ranks
+        mine = torch.zeros(len(pos), dtype=torch.float64)
+        mine[state[:, 6].numpy().astype(np.int64)] += 1.0
+        comm.allreduce_sum(mine)
+        q.put((rank, ok, bool((mine == 1.0).all())))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_slab_migration_gloo(world):
+    """Rebuild-time migration of owned atoms between slabs (domain.DistComm.migrate): after
+    every cycle each rank holds exactly the atoms of its slab, nothing is lost or duplicated,
+    atoms leaving through the periodic boundary arrive at the other end of the ring."""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_migrate_worker, args=(r, world, port, q))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, ok, once in results:
+        assert ok, f"rank {rank}: atoms outside the slab / atom count changed"
+        assert once, "an atom is owned by no rank or by two"

@@ -54,13 +54,16 @@ def _check32(res, ref, n):
     assert abs(e - ref['energy']) <= 1e-5 * abs(ref['energy'])
     fscale = np.abs(ref['forces']).max()
     assert np.abs(f - ref['forces']).max() <= 1e-5 * fscale
-    vscale = max(np.abs(ref['virial']).max(), 1e-5 * abs(ref['energy']))
+    # the virial is a sum of pair terms g (x) D of both signs that nearly cancels at the
+    # equilibrium density (|W| ~ 25 eV against sum |g.D| ~ |E| ~ 1e3 eV for 256 Ni atoms): the
+    # rounding error of a float32 evaluation scales with the terms, not with their sum
+    vscale = max(np.abs(ref['virial']).max(), abs(ref['energy']))
     assert np.abs(v - ref['virial']).max() <= 1e-5 * vscale
 
 
 @pytest.fixture
 def env_guard():
-    saved = {k: os.environ.get(k) for k in ('TAB_EAMZ_L', 'TAB_EAMZ_VIR')}
+    saved = {k: os.environ.get(k) for k in ('TAB_EAMZ_L',)}
     yield
     for k, v in saved.items():
         if v is None:
@@ -72,8 +75,8 @@ def env_guard():
 @pytest.mark.parametrize('cells,pbc', [((4, 4, 4), (1, 1, 1)), ((2, 2, 2), (1, 1, 1)),
                                        ((3, 3, 3), (1, 1, 0)), ((5, 4, 3), (0, 0, 0))])
 def test_lane_split_variants(env_guard, cells, pbc):
-    """Every lane count and both virial forms equal the oracle (multi-image cells, mixed and
-    no periodicity included: the F (x) R form treats images as 'ghost' pairs)."""
+    """Every lane count equals the oracle (multi-image cells, mixed and no periodicity
+    included)."""
     atoms = bulk_fcc('Ni', 3.52, cells)
     rng = np.random.default_rng(611)
     pos = atoms.positions + rng.normal(scale=0.05, size=atoms.positions.shape)
@@ -89,14 +92,12 @@ def test_lane_split_variants(env_guard, cells, pbc):
         if not pbc[k]:
             frame[k] = frame[k] * 1.2 + np.eye(3)[k]
             org[k] = -1.0
-    for L in (0, 1, 2, 4, 8):
-        for vir in (0, 1):
-            os.environ['TAB_EAMZ_L'] = str(L)
-            os.environ['TAB_EAMZ_VIR'] = str(vir)
-            nl = _lib.NeighborList()
-            nl.build_dd(d_pos, None, n, frame, org, pbc, RC)
-            _check64(_eval(model, nl, n, 0), ref, n)
-            _check32(_eval(model, nl, n, 1), ref, n)
+    for L in (0, 1, 2, 4, 8):       # 0 = the thread-per-atom kernels of round 1
+        os.environ['TAB_EAMZ_L'] = str(L)
+        nl = _lib.NeighborList()
+        nl.build_dd(d_pos, None, n, frame, org, pbc, RC)
+        _check64(_eval(model, nl, n, 0), ref, n)
+        _check32(_eval(model, nl, n, 1), ref, n)
 
 
 def test_zjw04xc_embedding_through_fast_kernels(env_guard):
@@ -205,7 +206,7 @@ def test_tile_build_with_skin_32k():
     assert np.abs(a[3] - b[3]).max() / n < 1e-10
     a32 = _eval(model, exact, n, 1)
     b32 = _eval(model, skin, n, 1)
-    assert np.abs(a32[2] - b32[2]).max() < 1e-6
+    assert np.abs(a32[2] - b32[2]).max() < 1e-5 * np.abs(a32[2]).max()
     pos3 = pos2 + 0.25                                      # rigid shift: every atom moved 0.43
     assert skin.step(torch.tensor(pos3, dtype=torch.float64, device='cuda'), None, atoms.cell,
                      [1, 1, 1], RC) is True

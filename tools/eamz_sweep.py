@@ -62,7 +62,7 @@ def main():
     ap.add_argument('--child', action='store_true')
     ap.add_argument('--libs', default='')
     ap.add_argument('--lanes', default='0,1,2,4,8')
-    ap.add_argument('--virs', default='0,1')
+    ap.add_argument('--virs', default='0')
     ap.add_argument('--precisions', default='high,medium')
     args = ap.parse_args()
     if args.child:
