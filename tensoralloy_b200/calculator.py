@@ -65,7 +65,18 @@ except Exception:   # noqa
 
         def calculate(self, atoms=None, properties=('energy',),
                       system_changes=all_changes):
-            if atoms is not None:
+            if atoms is None:
+                return
+            mine = self.atoms
+            if mine is not None and mine is not atoms and len(mine) == len(atoms) and \
+                    np.array_equal(mine.numbers, atoms.numbers):
+                # same atoms, new geometry: refresh the snapshot in place (a fresh copy of a
+                # million-atom structure costs more in page faults than the evaluation)
+                np.copyto(mine.positions, atoms.positions)
+                mine.cell = np.array(atoms.cell, dtype=np.float64)
+                mine.pbc = np.array(atoms.pbc, dtype=bool)
+                mine.info = dict(atoms.info)
+            else:
                 self.atoms = atoms.copy()
 
         def get_property(self, name, atoms=None, allow_calculation=True):
@@ -297,7 +308,9 @@ class TensorAlloyCalculator(_AseCalculator):
             want_stress = bool({'stress', 'total_pressure', 'elastic', 'total_stress'}
                                & properties)
             want_forces = 'forces' in properties or want_stress
-            raw = self._nn._evaluate(features, want_forces, want_stress, True)
+            want_atomic = bool({'energy/atom', 'atomic'} & properties) or \
+                self._is_finite_temperature
+            raw = self._nn._evaluate(features, want_forces, want_stress, want_atomic)
             if 'hessian' in properties:
                 raw['hessian'] = self._nn._hessian(features)
             if 'elastic' in properties:

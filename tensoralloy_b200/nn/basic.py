@@ -146,17 +146,38 @@ class BasicNN:
         raw = self._evaluate(features, want_forces, want_stress, True)
         return self._finalize(raw, features, properties)
 
+    # Per-atom results are copied out of the pinned staging buffer into numpy arrays of their
+    # own (what a caller of the reference gets from sess.run).  For MD loops over large
+    # structures the page faults of a fresh 24 MB array per call cost more than the kernels:
+    # with `reuse_result_buffers = True` the arrays of two alternating, persistent sets are
+    # overwritten instead -- the results of a call then stay valid until the second next call.
+    reuse_result_buffers = False
+
+    def _owned(self, key, src, dtype):
+        if not self.reuse_result_buffers:
+            return src.astype(dtype)
+        pool = self.__dict__.setdefault('_result_pool', [{}, {}])
+        flip = self.__dict__.get('_result_flip', 0)
+        slot = pool[flip]
+        dst = slot.get(key)
+        if dst is None or dst.shape != src.shape or dst.dtype != np.dtype(dtype):
+            dst = np.empty(src.shape, dtype=dtype)
+            slot[key] = dst
+        np.copyto(dst, src, casting='unsafe')
+        return dst
+
     def _finalize(self, raw, features, properties):
         dtype = get_float_dtype().as_numpy_dtype
         vap = features.vap
         to_gsl = (lambda a: a) if vap.is_identity else \
             (lambda a: vap.map_array(a.reshape(len(a), -1), reverse=False)[1:].reshape(
                 (vap.max_vap_natoms - 1,) + a.shape[1:]))
+        self.__dict__['_result_flip'] = 1 - self.__dict__.get('_result_flip', 0)
         pred = {'energy': dtype(raw['energy'])}
         if 'energy/atom' in raw:
-            pred['energy/atom'] = to_gsl(raw['energy/atom']).astype(dtype)
+            pred['energy/atom'] = self._owned('energy/atom', to_gsl(raw['energy/atom']), dtype)
         if 'forces' in raw:
-            pred['forces'] = to_gsl(raw['forces']).astype(dtype)
+            pred['forces'] = self._owned('forces', to_gsl(raw['forces']), dtype)
         if 'virial' in raw and ('stress' in properties or
                                 'total_pressure' in properties or
                                 'elastic' in properties):
@@ -187,7 +208,18 @@ class BasicNN:
                    eatom=buf[o_e:o_f] if want_atomic else None,
                    forces=buf[o_f:].view(n, 3) if want_forces else None,
                    virial=buf[o_v:o_e] if want_virial else None)
-        host = buf.cpu().numpy()
+        # one device->host copy into a persistent PINNED buffer; only what was asked for
+        hbuf = getattr(self, '_flat_host', None)
+        if hbuf is None or hbuf.numel() != size:
+            hbuf = torch.zeros(size, dtype=torch.float64).pin_memory()
+            self._flat_host = hbuf
+        hbuf[:o_e].copy_(buf[:o_e], non_blocking=True)
+        if want_atomic:
+            hbuf[o_e:o_f].copy_(buf[o_e:o_f], non_blocking=True)
+        if want_forces:
+            hbuf[o_f:].copy_(buf[o_f:], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        host = hbuf.numpy()
         return (host[0:nb], host[o_v:o_e].reshape(nb, 3, 3), host[o_e:o_f],
                 host[o_f:].reshape(n, 3))
 
@@ -201,24 +233,26 @@ class BasicNN:
             raise NotImplementedError("batched evaluation of finite-temperature models")
         e, w, ea, f = self._eval_flat(batch.nbr, batch.n_atoms, batch.n_struct,
                                       want_forces, want_virial, want_atomic)
-        raw = {'energy': e}
+        # (copies: the staging buffer is overwritten by the next call)
+        raw = {'energy': e.copy()}
         if want_virial:
-            raw['virial'] = w
+            raw['virial'] = w.copy()
         if want_atomic:
-            raw['energy/atom'] = ea
+            raw['energy/atom'] = ea.copy()
         if want_forces:
-            raw['forces'] = f
+            raw['forces'] = f.copy()
         return raw
 
     def _evaluate_single(self, features, want_forces, want_virial, want_atomic):
         """`_evaluate` of the models whose device handle has an `eval` entry point."""
         e, w, ea, f = self._eval_flat(features.nbr, features.n_atoms, 1, want_forces,
                                       want_virial, want_atomic)
-        raw = {'energy': e[0]}
+        # views of the pinned staging buffer: `_finalize` copies them into arrays of their own
+        raw = {'energy': float(e[0])}
         if want_atomic:
-            raw['energy/atom'] = ea.copy()
+            raw['energy/atom'] = ea
         if want_forces:
-            raw['forces'] = f.copy()
+            raw['forces'] = f
         if want_virial:
             raw['virial'] = w[0].copy()
         return raw

@@ -153,6 +153,20 @@ class UniversalTransformer:
         cached_atoms, cached = self._types_cache
         if cached_atoms is atoms and cached is not None and len(cached) == len(atoms):
             return cached
+        numbers = getattr(atoms, 'numbers', None)
+        if numbers is not None:
+            # through the atomic numbers: no per-atom Python strings (1 M atoms: 0.2 s -> 2 ms)
+            lut = self._z_lut()
+            numbers = np.asarray(numbers)
+            if numbers.size and (numbers.min() < 0 or numbers.max() >= len(lut)):
+                raise ValueError("atomic numbers outside the periodic table")
+            types = lut[numbers]
+            if (types < 0).any():
+                bad = sorted({chemical_symbols[z] for z in np.unique(numbers[types < 0])})
+                raise ValueError(f"elements {bad} are not supported by this transformer")
+            types = types.astype(np.int32)
+            self._types_cache = (atoms, types)
+            return types
         symbols = np.asarray(atoms.get_chemical_symbols())
         els = np.asarray(self._elements)
         idx = np.searchsorted(els, symbols)
@@ -249,62 +263,62 @@ class UniversalTransformer:
             self._zlut = lut
         return self._zlut
 
-    # -- reference wire format (universal.py:46-112,851-893) -------------------
+    # -- reference wire format (universal.py:46-233,728-785,851-893) ----------------
     def get_np_feed_dict(self, atoms):
-        """The reference's PREDICT-mode feed dict, rebuilt from the GPU list."""
+        """The reference's PREDICT-mode feed dict, rebuilt from the GPU list: every key of
+        universal.py:851-893 incl. the angular ones (`g4.v2g_map`, `g4.ilist / jlist / klist`,
+        `g4.n1 / n2 / n3`, `ij2k_max`).  Slots follow the canonical pair order
+        (transformer/wire_format.py)."""
         import torch
+        from tensoralloy_b200.transformer import wire_format as wf
         np_dtype = get_float_dtype().as_numpy_dtype
         feats = self.get_device_features(atoms)
         vap = feats.vap
         i, j, S = feats.nbr.export()
         torch.cuda.synchronize()
-        i = i.cpu().numpy().astype(np.int64)
-        j = j.cpu().numpy().astype(np.int64)
-        S = S.cpu().numpy()
-        types = feats.types
-        n_el = self._n_elements
-        # index of the k-body term inside kbody_terms_for_element[centre]
-        ti, tj = types[i], types[j]
-        tlist = np.where(ti == tj, 0, tj - (tj > ti).astype(np.int64) + 1
-                         ).astype(np.int32) if n_el > 1 else np.zeros(len(i), np.int32)
-        l2g = vap.local_to_gsl_array
-        ilist = l2g[i + 1].astype(np.int32)
-        jlist = l2g[j + 1].astype(np.int32)
-        nij = len(i)
-        # slot counter per (centre, term) in list order (universal.py:90-101)
-        key = i * self._max_nr_terms + tlist
-        order = np.argsort(key, kind='stable')
-        ks = key[order]
-        first = np.concatenate(([True], ks[1:] != ks[:-1])) if nij else np.zeros(0, bool)
-        start = np.maximum.accumulate(np.where(first, np.arange(nij), 0))
-        inc = np.empty(nij, dtype=np.int32)
-        inc[order] = (np.arange(nij) - start).astype(np.int32)
-        v2g = np.zeros((nij, 5), dtype=np.int32)
-        v2g[:, 0] = tlist
-        v2g[:, 1] = ilist
-        v2g[:, 2] = inc
-        v2g[:, 4] = 1
-        positions = vap.map_positions(np.asarray(atoms.positions))
+        return self._feed_dict_from_list(atoms, vap, feats.types, feats.cell, feats.volume,
+                                         i.cpu().numpy(), j.cpu().numpy(), S.cpu().numpy(),
+                                         np_dtype)
+
+    def _feed_dict_from_list(self, atoms, vap, types, cell, volume, i, j, S, np_dtype):
+        """Host part of `get_np_feed_dict` (pure numpy; the CPU tests drive it with the
+        oracle's neighbour list)."""
+        from tensoralloy_b200.transformer import wire_format as wf
+        pos = np.asarray(atoms.positions, dtype=np.float64)
+        arr = wf.build_feed_arrays(i, j, S, pos, cell, types, vap.local_to_gsl_array,
+                                   self._elements, self._kbody_terms_for_element,
+                                   self._rcut, self._acut, self._angular, self._symmetric)
+        v2g = arr["g2.v2g_map"]
         feed = dict()
         if self._use_computed_dists:
-            feed["positions"] = positions.astype(np_dtype)
-            feed["cell"] = feats.cell.astype(np_dtype)
-            feed["volume"] = np_dtype(feats.volume)
+            feed["positions"] = vap.map_positions(pos).astype(np_dtype)
+            feed["cell"] = np.asarray(cell, dtype=np.float64).astype(np_dtype)
+            feed["volume"] = np_dtype(volume)
         feed["n_atoms_vap"] = np.int32(vap.max_vap_natoms)
-        feed["nnl_max"] = np.int32(inc.max() + 1 if nij else 0)
+        feed["nnl_max"] = np.int32(v2g[:, 2].max() + 1 if len(v2g) else 0)
         feed["atom_masks"] = vap.atom_masks.astype(np_dtype)
         feed["etemperature"] = np_dtype(atoms.info.get('etemperature', 0.0))
         feed["row_splits"] = np.int32([1] + [vap.max_occurs[e] for e in self._elements])
         feed["g2.v2g_map"] = v2g
         if self._use_computed_dists:
-            feed["g2.ilist"] = ilist
-            feed["g2.jlist"] = jlist
-            feed["g2.n1"] = S.astype(np_dtype)
+            feed["g2.ilist"] = arr["g2.ilist"]
+            feed["g2.jlist"] = arr["g2.jlist"]
+            feed["g2.n1"] = arr["g2.n1"].astype(np_dtype)
         else:
-            D = (np.asarray(atoms.positions)[j] - np.asarray(atoms.positions)[i]
-                 + S.astype(np.float64) @ feats.cell)
-            d = np.sqrt((D * D).sum(axis=1))
-            feed["g2.rij"] = np.concatenate((d[:, None], D), axis=1).T.astype(np_dtype)
+            feed["g2.rij"] = np.concatenate((arr["g2.d"][:, None], arr["g2.D"]),
+                                            axis=1).T.astype(np_dtype)
+        if self._angular:
+            g4 = arr["g4.v2g_map"]
+            feed["ij2k_max"] = np.int32(g4[:, 3].max() + 1 if len(g4) else 0)
+            feed["g4.v2g_map"] = g4
+            if self._use_computed_dists:
+                for key in ("g4.ilist", "g4.jlist", "g4.klist"):
+                    feed[key] = arr[key]
+                for key in ("g4.n1", "g4.n2", "g4.n3"):
+                    feed[key] = arr[key].astype(np_dtype)
+            else:
+                raise NotImplementedError(
+                    "g4.rijk (use_computed_dists=False with angular terms)")
         return feed
 
     def get_feed_dict(self, atoms):
