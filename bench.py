@@ -292,6 +292,11 @@ def measure(runner, args, precision, barrier, torch, dist, world, _lib):
     runner.set_precision(precision)
     for _ in range(args.warmup):
         runner.md_step()
+    if world > 1:
+        # one rebuild inside the warm-up: the first one pays for the lazy set-up of the NCCL
+        # point-to-point channels that carry the migrating atoms
+        runner.rebuild()
+        runner.md_step()
     barrier()
     # per-kernel event timing + launch count of the resident step (eager launches)
     _lib.profile_enable(True)
@@ -309,13 +314,19 @@ def measure(runner, args, precision, barrier, torch, dist, world, _lib):
         barrier()
         resident_ms = timed(runner.resident_step, n_res, barrier, torch, dist, world)
     runner.rebuilds = 0
+    if args.rebuild_profile and hasattr(runner, 'rebuild_profile'):
+        runner.rebuild_profile = {}
     _lib.lib().tab_launch_count_reset()
     ms_per_step = timed(runner.md_step, args.steps, barrier, torch, dist, world)
     launches = int(_lib.lib().tab_launch_count())
     if graphed:
         launches += launches_res * (args.steps - runner.rebuilds)
+    prof = getattr(runner, 'rebuild_profile', None)
+    if prof is not None:
+        runner.rebuild_profile = None
     return {"ms_per_step": ms_per_step, "resident_ms": resident_ms, "kernel_ms": kernel_ms,
-            "launches": launches, "rebuilds": runner.rebuilds, "graphed": graphed}
+            "launches": launches, "rebuilds": runner.rebuilds, "graphed": graphed,
+            "rebuild_profile_ms": prof}
 
 
 def roofline_block(m, runner, hbm, which, precision, kernel_name, tag):
@@ -439,6 +450,7 @@ def run_ours(args):
                             f"(every 10th step), rebuilds inside the timed region",
                 "atoms": n_total, "pairs_local": nij_main,
                 "rebuilds_in_timed_steps": main["rebuilds"],
+                "rebuild_profile_ms": main.get("rebuild_profile_ms"),
                 "md_valid": runner.md_valid,
                 "parallelism": runner.describe(),
                 "cache": "inputs larger than L2 (neighbour index arrays >= 344 MB "
@@ -671,6 +683,8 @@ def main():
                     help='skin of the resident lists (A); the MD cycle rebuilds on every 10th step')
     ap.add_argument('--check-atoms', type=int, default=256,
                     help='atoms compared with the oracle after the timed region')
+    ap.add_argument('--rebuild-profile', action='store_true',
+                    help='N > 1: time the phases of every rebuild (adds synchronisations)')
     ap.add_argument('--no-graph', action='store_true',
                     help='N > 1: launch the step eagerly instead of as one CUDA graph')
     args = ap.parse_args()

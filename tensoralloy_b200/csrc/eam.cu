@@ -989,12 +989,12 @@ static int eamz_pass1_L(tab_model *m, tab_nbr *nbr, int precision, double *d_fpr
     const int nblk = (int)((threads + EAMZ_T - 1) / EAMZ_T);
     if (precision == TAB_PRECISION_HIGH) {
         k_eamz_rho<L><<<nblk, EAMZ_T, 0, st>>>(
-            n, nbr->atoms.as<Atom4>(), v.ptr, v.w, v.wc, v.col, nbr->perm.as<int>(), *m->zp,
+            n, nbr->atoms.as<Atom4>(), v.ptr, v.w, v.col, nbr->perm.as<int>(), *m->zp,
             tab_mask_rc2(nbr), m->embed0, fprime, fembed, d_fprime_caller);
     } else {
         TAB_TRY(tab_nbr_ensure_rec16(nbr, st));
         k_eamz_rho_f32<L><<<nblk, EAMZ_T, 0, st>>>(
-            n, nbr->rec16.as<Rec16>(), v.ptr, v.w, v.wc, v.col, nbr->perm.as<int>(), *m->zp,
+            n, nbr->rec16.as<Rec16>(), v.ptr, v.w, v.col, nbr->perm.as<int>(), *m->zp,
             eamz_qscale(m, nbr), m->embed0, fprime, fembed, d_fprime_caller);
     }
     TAB_LAUNCH_CHECK();
@@ -1015,11 +1015,11 @@ static int eamz_pass2_L(tab_model *m, tab_nbr *nbr, int precision, const double 
     TAB_TRY(nbr->partial.ensure(sizeof(double) * 8 * (size_t)nblk));
     if (precision == TAB_PRECISION_HIGH) {
         k_eamz_force<L><<<nblk, EAMZ_T, 0, st>>>(
-            n, nbr->atoms.as<Atom4>(), v.ptr, v.w, v.wc, v.col, nbr->perm.as<int>(), *m->zp,
+            n, nbr->atoms.as<Atom4>(), v.ptr, v.w, v.col, nbr->perm.as<int>(), *m->zp,
             tab_mask_rc2(nbr), fembed, d_eatom, d_forces, nbr->partial.as<double>(), d_own_mask);
     } else {
         k_eamz_force_f32<L><<<nblk, EAMZ_T, 0, st>>>(
-            n, nbr->rec16.as<Rec16>(), v.ptr, v.w, v.wc, v.col, nbr->perm.as<int>(), *m->zp,
+            n, nbr->rec16.as<Rec16>(), v.ptr, v.w, v.col, nbr->perm.as<int>(), *m->zp,
             eamz_qscale(m, nbr), fembed, d_eatom, d_forces, nbr->partial.as<double>(),
             d_own_mask);
     }

@@ -15,7 +15,10 @@
 //     per-lane trip counts and no predicated loads.
 //   * r < rc mask: lists built with a skin hold entries beyond the model's cutoff; they
 //     contribute exactly 0, so a reused list equals a fresh one (transformer/universal.py:58
-//     rebuilds per call).
+//     rebuilds per call).  (Ordering the rows inside-first at build time and skipping the skin
+//     part by warp vote was built and measured: the vote saves the arithmetic but not the
+//     gather, pass 1 sits on the L1 data pipe and gained nothing, pass 2 gained 12 %, and the
+//     1.4 ms ordering kernel per rebuild ate it -- profiles/README.md, r02e.)
 //   * float32 ('medium'): 16-byte fixed-point records (tab_internal.h Rec16), geometry, functions
 //     and per-atom sums in float32, block sums in float64.
 #pragma once
@@ -93,17 +96,14 @@ k_ls_fill(int n, int n_pad, uint32_t sentinel, const int *__restrict__ counts,
 // sentinel-padded with spare rows (no copy), else the lane-split copy.
 struct LsView {
     const uint32_t *ptr, *w, *col;
-    const uint32_t *wc;      // rows of the inside-first part of each group, or NULL (all rows)
 };
 
 template <int L>
 static int ensure_lanesplit(tab_nbr *nbr, cudaStream_t st, LsView &v) {
-    v.wc = nullptr;
     if (L == 1 && nbr->col_padded) {
         v.ptr = nbr->slice_ptr.as<uint32_t>();
         v.w = nbr->slice_w.as<uint32_t>();
         v.col = nbr->col.as<uint32_t>();
-        if (nbr->has_wcore) v.wc = nbr->slice_wc.as<uint32_t>();
         return TAB_OK;
     }
     if (nbr->ls_L == L) {
@@ -146,12 +146,10 @@ static int ensure_lanesplit(tab_nbr *nbr, cudaStream_t st, LsView &v) {
 template <int L>
 struct LaneRow {
     int idx, part, steps;      // steps = width of the group: the same for the whole warp
-    int steps_core;            // rows of the inside-first part (= steps for unordered rows)
     bool active;
     const uint32_t *cp;
     __device__ __forceinline__ LaneRow(int n, const uint32_t *__restrict__ ls_ptr,
                                        const uint32_t *__restrict__ ls_w,
-                                       const uint32_t *__restrict__ ls_wc,
                                        const uint32_t *__restrict__ ls_col) {
         constexpr int G = 32 / L;
         const int lane = threadIdx.x & 31;
@@ -161,11 +159,9 @@ struct LaneRow {
         active = idx < n;
         uint32_t p0 = 0;
         steps = 0;
-        steps_core = 0;
         if (g * G < n) {
             p0 = ls_ptr[g];
             steps = (int)ls_w[g];
-            steps_core = ls_wc ? min((int)ls_wc[g], steps) : steps;
         }
         cp = ls_col + ((size_t)p0 * 32u + lane);
     }
@@ -221,9 +217,6 @@ __device__ __forceinline__ void for_each_entry_simple(const uint32_t *__restrict
         a = an;
     }
 }
-
-struct VoteOn { static constexpr bool value = true; };
-struct VoteOff { static constexpr bool value = false; };
 
 #ifndef EAMZ_RING32
 #define EAMZ_RING32 0
@@ -366,38 +359,27 @@ __device__ __forceinline__ void load_exp2_tab64(double *s_tab) {
 template <int L>
 __global__ void __launch_bounds__(EAMZ_T, EAMZ_MINB_RHO)
 k_eamz_rho(int n, const Atom4 *__restrict__ atoms, const uint32_t *__restrict__ ls_ptr,
-           const uint32_t *__restrict__ ls_w, const uint32_t *__restrict__ ls_wc,
-        const uint32_t *__restrict__ ls_col, const int *__restrict__ perm, ZPair z,
+           const uint32_t *__restrict__ ls_w, const uint32_t *__restrict__ ls_col, const int *__restrict__ perm, ZPair z,
            double rc2m, tab_fn embed0, double *__restrict__ fprime,
            double *__restrict__ fembed, double *__restrict__ fprime_caller) {
     __shared__ double s_etab[EAMZ_RHO_TABLE ? 64 : 1];
     if (EAMZ_RHO_TABLE) load_exp2_tab64(s_etab);
-    const LaneRow<L> row(n, ls_ptr, ls_w, ls_wc, ls_col);
+    const LaneRow<L> row(n, ls_ptr, ls_w, ls_col);
     double rho = 0.0;
     if (row.steps > 0) {
         Atom4 me;
         me.x = me.y = me.z = 0.0;
         if (row.active) me = atoms[row.idx];
-        auto body = [&](const Atom4 &a, auto vote_tag) {
-            constexpr bool vote = decltype(vote_tag)::value;
+        auto body = [&](const Atom4 &a) {
             const double dx = a.x - me.x, dy = a.y - me.y, dz = a.z - me.z;
             const double s = fma(dx, dx, fma(dy, dy, fma(dz, dz, 1e-14)));
-            // skin lists are ordered "inside first" (k_sort_rows): past that part whole warps skip
-            if (vote && !__any_sync(0xffffffffu, s < rc2m)) return;
             const double r = s * tab_rsqrt(s);
             double f, df;
             zt2_eval<false, EAMZ_RHO_TABLE != 0>(r, z.rho, s_etab, f, df);
             rho += s < rc2m ? f : 0.0;
         };
-        // rows ordered inside-first: the part every lane may need, then the skin part, where a
-        // step is evaluated only if some lane's pair has come inside the cutoff
-        auto core = [&](const Atom4 &a) { body(a, VoteOff()); };
-        auto tail = [&](const Atom4 &a) { body(a, VoteOn()); };
-        if (EAMZ_RING64) for_each_entry<EAMZ_PF64>(row.cp, row.steps_core, atoms, core);
-        else for_each_entry_simple(row.cp, row.steps_core, atoms, core);
-        if (row.steps > row.steps_core)
-            for_each_entry_simple(row.cp + (size_t)row.steps_core * 32u,
-                                  row.steps - row.steps_core, atoms, tail);
+        if (EAMZ_RING64) for_each_entry<EAMZ_PF64>(row.cp, row.steps, atoms, body);
+        else for_each_entry_simple(row.cp, row.steps, atoms, body);
     }
     rho = lanes_sum<L>(rho);
     if (row.active && row.part == 0) {
@@ -420,25 +402,22 @@ k_eamz_rho(int n, const Atom4 *__restrict__ atoms, const uint32_t *__restrict__ 
 template <int L>
 __global__ void __launch_bounds__(EAMZ_T, EAMZ_MINB_FORCE)
 k_eamz_force(int n, const Atom4 *__restrict__ atoms, const uint32_t *__restrict__ ls_ptr,
-             const uint32_t *__restrict__ ls_w, const uint32_t *__restrict__ ls_wc,
-        const uint32_t *__restrict__ ls_col, const int *__restrict__ perm, ZPair z,
+             const uint32_t *__restrict__ ls_w, const uint32_t *__restrict__ ls_col, const int *__restrict__ perm, ZPair z,
              double rc2m, const double *__restrict__ fembed, double *__restrict__ eatom,
              double *__restrict__ forces, double *__restrict__ partial,
              const int *__restrict__ own_mask) {
     __shared__ double s_etab[64];
     load_exp2_tab64(s_etab);
-    const LaneRow<L> row(n, ls_ptr, ls_w, ls_wc, ls_col);
+    const LaneRow<L> row(n, ls_ptr, ls_w, ls_col);
     double fx = 0, fy = 0, fz = 0, ep = 0;
     double vxx = 0, vyy = 0, vzz = 0, vyz = 0, vxz = 0, vxy = 0;
     if (row.steps > 0) {
         Atom4 me;
         me.x = me.y = me.z = me.w = 0.0;
         if (row.active) me = atoms[row.idx];
-        auto body = [&](const Atom4 &a, auto vote_tag) {
-            constexpr bool vote = decltype(vote_tag)::value;
+        auto body = [&](const Atom4 &a) {
             const double dx = a.x - me.x, dy = a.y - me.y, dz = a.z - me.z;
             const double s = fma(dx, dx, fma(dy, dy, fma(dz, dz, 1e-14)));
-            if (vote && !__any_sync(0xffffffffu, s < rc2m)) return;
             const double rinv = tab_rsqrt(s);
             const double r = s * rinv;
             double ga, dga, gb, dgb;
@@ -459,15 +438,8 @@ k_eamz_force(int n, const Atom4 *__restrict__ atoms, const uint32_t *__restrict_
             vxz = fma(gx, dz, vxz);
             vxy = fma(gx, dy, vxy);
         };
-        // rows ordered inside-first: the part every lane may need, then the skin part, where a
-        // step is evaluated only if some lane's pair has come inside the cutoff
-        auto core = [&](const Atom4 &a) { body(a, VoteOff()); };
-        auto tail = [&](const Atom4 &a) { body(a, VoteOn()); };
-        if (EAMZ_RING64) for_each_entry<EAMZ_PF64>(row.cp, row.steps_core, atoms, core);
-        else for_each_entry_simple(row.cp, row.steps_core, atoms, core);
-        if (row.steps > row.steps_core)
-            for_each_entry_simple(row.cp + (size_t)row.steps_core * 32u,
-                                  row.steps - row.steps_core, atoms, tail);
+        if (EAMZ_RING64) for_each_entry<EAMZ_PF64>(row.cp, row.steps, atoms, body);
+        else for_each_entry_simple(row.cp, row.steps, atoms, body);
     }
     double acc[7];
     acc[1] = 0.5 * vxx;
@@ -534,35 +506,27 @@ __device__ __forceinline__ float f_rsqrt(float x) {
 template <int L>
 __global__ void __launch_bounds__(EAMZ_T, 8)
 k_eamz_rho_f32(int n, const Rec16 *__restrict__ recs, const uint32_t *__restrict__ ls_ptr,
-               const uint32_t *__restrict__ ls_w, const uint32_t *__restrict__ ls_wc,
-        const uint32_t *__restrict__ ls_col, const int *__restrict__ perm, ZPair z,
+               const uint32_t *__restrict__ ls_w, const uint32_t *__restrict__ ls_col, const int *__restrict__ perm, ZPair z,
                QScale qs, tab_fn embed0, double *__restrict__ fprime,
                double *__restrict__ fembed, double *__restrict__ fprime_caller) {
-    const LaneRow<L> row(n, ls_ptr, ls_w, ls_wc, ls_col);
+    const LaneRow<L> row(n, ls_ptr, ls_w, ls_col);
     float rho = 0.f;
     if (row.steps > 0) {
         Rec16 me;
         me.qx = me.qy = me.qz = 0;
         if (row.active) me = recs[row.idx];
-        auto body = [&](const Rec16 &a, auto vote_tag) {
-            constexpr bool vote = decltype(vote_tag)::value;
+        auto body = [&](const Rec16 &a) {
             const float dx = (float)(a.qx - me.qx), dy = (float)(a.qy - me.qy),
                         dz = (float)(a.qz - me.qz);
             const float s = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, qs.eps_q)));
-            if (vote && !__any_sync(0xffffffffu, s < qs.rc2_q)) return;
             const float x = (s * f_rsqrt(s)) * qs.x_per_q;
             const float u = x - z.f_k_rho;
             const float u2 = u * u, u4 = u2 * u2, u8 = u4 * u4, u16 = u8 * u8;
             const float f = f_ex2(fmaf(x, z.f_yx_rho, z.f_yc_rho)) * f_rcp(fmaf(u16, u4, 1.f));
             rho += s < qs.rc2_q ? f : 0.f;
         };
-        auto core = [&](const Rec16 &a) { body(a, VoteOff()); };
-        auto tail = [&](const Rec16 &a) { body(a, VoteOn()); };
-        if (EAMZ_RING32) for_each_entry<EAMZ_PF32>(row.cp, row.steps_core, recs, core);
-        else for_each_entry_simple(row.cp, row.steps_core, recs, core);
-        if (row.steps > row.steps_core)
-            for_each_entry_simple(row.cp + (size_t)row.steps_core * 32u,
-                                  row.steps - row.steps_core, recs, tail);
+        if (EAMZ_RING32) for_each_entry<EAMZ_PF32>(row.cp, row.steps, recs, body);
+        else for_each_entry_simple(row.cp, row.steps, recs, body);
     }
     rho = lanes_sum<L>(rho);
     if (row.active && row.part == 0) {
@@ -578,12 +542,11 @@ k_eamz_rho_f32(int n, const Rec16 *__restrict__ recs, const uint32_t *__restrict
 template <int L>
 __global__ void __launch_bounds__(EAMZ_T, 8)
 k_eamz_force_f32(int n, const Rec16 *__restrict__ recs, const uint32_t *__restrict__ ls_ptr,
-                 const uint32_t *__restrict__ ls_w, const uint32_t *__restrict__ ls_wc,
-        const uint32_t *__restrict__ ls_col, const int *__restrict__ perm, ZPair z,
+                 const uint32_t *__restrict__ ls_w, const uint32_t *__restrict__ ls_col, const int *__restrict__ perm, ZPair z,
                  QScale qs, const double *__restrict__ fembed, double *__restrict__ eatom,
                  double *__restrict__ forces, double *__restrict__ partial,
                  const int *__restrict__ own_mask) {
-    const LaneRow<L> row(n, ls_ptr, ls_w, ls_wc, ls_col);
+    const LaneRow<L> row(n, ls_ptr, ls_w, ls_col);
     float fx = 0, fy = 0, fz = 0, ep = 0;
     float vxx = 0, vyy = 0, vzz = 0, vyz = 0, vxz = 0, vxy = 0;
     if (row.steps > 0) {
@@ -591,12 +554,10 @@ k_eamz_force_f32(int n, const Rec16 *__restrict__ recs, const uint32_t *__restri
         me.qx = me.qy = me.qz = 0;
         me.w = 0.f;
         if (row.active) me = recs[row.idx];
-        auto body = [&](const Rec16 &a, auto vote_tag) {
-            constexpr bool vote = decltype(vote_tag)::value;
+        auto body = [&](const Rec16 &a) {
             const float dx = (float)(a.qx - me.qx), dy = (float)(a.qy - me.qy),
                         dz = (float)(a.qz - me.qz);
             const float s = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, qs.eps_q)));
-            if (vote && !__any_sync(0xffffffffu, s < qs.rc2_q)) return;
             const float rinv = f_rsqrt(s);           // 1 / r_q
             const float x = (s * rinv) * qs.x_per_q;
             // both denominators through one reciprocal
@@ -627,13 +588,8 @@ k_eamz_force_f32(int n, const Rec16 *__restrict__ recs, const uint32_t *__restri
             vxz = fmaf(gx, dz, vxz);
             vxy = fmaf(gx, dy, vxy);
         };
-        auto core = [&](const Rec16 &a) { body(a, VoteOff()); };
-        auto tail = [&](const Rec16 &a) { body(a, VoteOn()); };
-        if (EAMZ_RING32) for_each_entry<EAMZ_PF32>(row.cp, row.steps_core, recs, core);
-        else for_each_entry_simple(row.cp, row.steps_core, recs, core);
-        if (row.steps > row.steps_core)
-            for_each_entry_simple(row.cp + (size_t)row.steps_core * 32u,
-                                  row.steps - row.steps_core, recs, tail);
+        if (EAMZ_RING32) for_each_entry<EAMZ_PF32>(row.cp, row.steps, recs, body);
+        else for_each_entry_simple(row.cp, row.steps, recs, body);
     }
     double acc[7];
     const double hd = 0.5 * qs.ddelta;      // g (x) D_q carries one factor delta

@@ -33,8 +33,6 @@
 #include <math.h>
 #include <stdlib.h>
 
-#include <utility>
-
 #include "tab_internal.h"
 
 #define B TAB_TILE_B
@@ -857,63 +855,6 @@ __global__ void k_pad_tail(int n, const uint32_t *__restrict__ slice_w,
     for (uint32_t k = 0; k < slice_w[s]; ++k) base[(size_t)k * 32u] = pad;
 }
 
-// Lists with a skin, one species: the entries of every row are regrouped (out of place) as
-//   [ pairs inside the model's cutoff at build time | the others, nearest first (16 bins) ]
-// The order inside a row is free (no consumer depends on it; the reference's own order inside a
-// row is ASE's and pinned by nothing).  The pair kernels of eam_fast.cuh test r < rc before
-// the function evaluation and skip a step when no lane of the warp is inside: with this order
-// the steps past the "inside" part of the rows are skipped by whole warps, so the ~45 % more
-// entries a 0.3 A skin adds to rattled fcc Ni (its 48-atom shell at 6.585 A sits just outside
-// rc = 6.5) cost a distance test each, not a function evaluation.
-#define SORT_BINS 16
-__global__ void __launch_bounds__(128)
-k_sort_rows(int n, const Atom4 *__restrict__ atoms, const int *__restrict__ counts,
-            const uint32_t *__restrict__ slice_ptr, const uint32_t *__restrict__ col_in,
-            uint32_t *__restrict__ col_out, uint32_t *__restrict__ slice_wc, double rc,
-            double inv_bin, int kmax) {
-    extern __shared__ unsigned char smem_sort[];
-    // hist[SORT_BINS + 1][128] ints, then keys[kmax][128] bytes
-    int *hist = reinterpret_cast<int *>(smem_sort);
-    unsigned char *keys = smem_sort + sizeof(int) * (SORT_BINS + 1) * 128;
-    const int tid = threadIdx.x;
-    const int idx = blockIdx.x * blockDim.x + tid;
-#pragma unroll
-    for (int b = 0; b <= SORT_BINS; ++b) hist[b * 128 + tid] = 0;
-    const bool live = idx < n;
-    const size_t base = live ? (size_t)slice_ptr[idx >> 5] * 32u + (idx & 31) : 0;
-    const int cnt = live ? min(counts[idx], kmax) : 0;
-    Atom4 me;
-    me.x = me.y = me.z = 0.0;
-    if (live) me = atoms[idx];
-    const double rc2 = rc * rc;
-    for (int k = 0; k < cnt; ++k) {
-        const Atom4 a = atoms[col_in[base + (size_t)k * 32u] & TAB_COL_IDX_MASK];
-        const double dx = a.x - me.x, dy = a.y - me.y, dz = a.z - me.z;
-        const double d2 = dx * dx + dy * dy + dz * dz;
-        int key = 0;
-        if (!(d2 < rc2)) key = 1 + min(SORT_BINS - 1, (int)((sqrt(d2) - rc) * inv_bin));
-        keys[k * 128 + tid] = (unsigned char)key;
-        ++hist[key * 128 + tid];
-    }
-    // width of the "inside" part of the slice = the largest inside-count of its 32 atoms
-    int wc = hist[tid];
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) wc = max(wc, __shfl_xor_sync(0xffffffffu, wc, d));
-    if ((tid & 31) == 0 && (idx >> 5) < (n + 31) / 32) slice_wc[idx >> 5] = (uint32_t)wc;
-    int run = 0;
-#pragma unroll
-    for (int b = 0; b <= SORT_BINS; ++b) {
-        const int c = hist[b * 128 + tid];
-        hist[b * 128 + tid] = run;
-        run += c;
-    }
-    for (int k = 0; k < cnt; ++k) {
-        const int key = keys[k * 128 + tid];
-        const int dst = hist[key * 128 + tid]++;
-        col_out[base + (size_t)dst * 32u] = col_in[base + (size_t)k * 32u];
-    }
-}
-
 // Rows that pair loops may read without looking at the counts (eam_fast.cuh): every slot
 // past an atom's count up to the slice width holds the SENTINEL entry, and so do `extra` rows
 // after the slice (fixed-stride rows: up to the stride; compact rows: only after the last slice,
@@ -1120,7 +1061,7 @@ extern "C" int tab_nbr_free(tab_nbr *nbr) {
                       &nbr->slice_w, &nbr->slice_ptr, &nbr->col, &nbr->scan_tmp,
                       &nbr->stats, &nbr->row_ptr, &nbr->rho, &nbr->partial, &nbr->adp,
                       &nbr->tcounts, &nbr->rev, &nbr->pcache, &nbr->rows_tmp,
-                      &nbr->pos_ref, &nbr->disp, &nbr->ls_ptr, &nbr->ls_col, &nbr->ls_w, &nbr->slice_wc,
+                      &nbr->pos_ref, &nbr->disp, &nbr->ls_ptr, &nbr->ls_col, &nbr->ls_w,
                       &nbr->rec16};
     for (DevBuf *b : bufs) b->release();
     delete nbr;
@@ -1240,33 +1181,6 @@ static int refresh_positions(tab_nbr *nbr, const double *d_pos, cudaStream_t st)
             nbr->ghost_S.as<int>(), 1, qf, rec);
         TAB_LAUNCH_CHECK();
     }
-    return TAB_OK;
-}
-
-// see k_sort_rows; `row_words`: size of the list buffer
-static int sort_rows_by_distance(tab_nbr *nbr, size_t row_words, cudaStream_t st) {
-    nbr->has_wcore = false;
-    if (!(nbr->skin_built > 0.0) || nbr->n_types != 1 || nbr->nnl_max <= 0) return TAB_OK;
-    static int on = -1;
-    if (on < 0) {
-        const char *e = getenv("TAB_NBR_SORT_ROWS");
-        on = (e && e[0] == '0') ? 0 : 1;
-    }
-    if (!on) return TAB_OK;
-    const int kmax = nbr->nnl_max;
-    const size_t smem = sizeof(int) * (SORT_BINS + 1) * 128 + (size_t)kmax * 128;
-    if (smem > 200 * 1024) return TAB_OK;        // rows too long for the key cache: keep the order
-    TAB_TRY(nbr->rows_tmp.ensure(sizeof(uint32_t) * row_words));
-    TAB_TRY(nbr->slice_wc.ensure(sizeof(uint32_t) * (size_t)(nbr->n_slices + 1)));
-    TAB_CUDA(cudaFuncSetAttribute(k_sort_rows, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem));
-    k_sort_rows<<<nblocks(nbr->n, 128), 128, smem, st>>>(
-        nbr->n, nbr->atoms.as<Atom4>(), nbr->counts.as<int>(), nbr->slice_ptr.as<uint32_t>(),
-        nbr->col.as<uint32_t>(), nbr->rows_tmp.as<uint32_t>(), nbr->slice_wc.as<uint32_t>(),
-        nbr->rc_model, (double)SORT_BINS / nbr->skin_built, kmax);
-    TAB_LAUNCH_CHECK();
-    std::swap(nbr->col, nbr->rows_tmp);
-    nbr->has_wcore = true;
     return TAB_OK;
 }
 
@@ -1499,8 +1413,6 @@ extern "C" int tab_nbr_build_dd(tab_nbr *nbr, int32_t n_owned, int32_t n_halo,
                 n, nbr->n_slices, wcap, nbr->counts.as<int>(), nbr->slice_ptr.as<uint32_t>(),
                 nbr->tcounts.as<int>());
             TAB_LAUNCH_CHECK();
-            TAB_TRY(sort_rows_by_distance(
-                nbr, ((size_t)nbr->n_slices * wcap + TAB_SPARE_ROWS) * 32u + 32u, st));
             // fixed-stride rows: sentinel entries past the counts (and the spare rows, which for
             // the last slice lie beyond the stride: the buffer holds TAB_SPARE_ROWS more)
             k_pad_sentinel<<<nblocks(nthreads, 128), 128, 0, st>>>(
@@ -1565,7 +1477,6 @@ extern "C" int tab_nbr_build_dd(tab_nbr *nbr, int32_t n_owned, int32_t n_halo,
             nbr->slice_ptr.as<uint32_t>(), nbr->col.as<uint32_t>(), (uint32_t)nbr->n_ext);
         TAB_LAUNCH_CHECK();
     }
-    TAB_TRY(sort_rows_by_distance(nbr, 32 * (size_t)(nbr->ell_rows + 1 + TAB_SPARE_ROWS), st));
     // the spare rows after the last slice
     k_pad_sentinel<<<nblocks(nthreads, 128), 128, 0, st>>>(
         n, nbr->n_slices, (uint32_t)nbr->n_ext, TAB_SPARE_ROWS, 0u, nbr->counts.as<int>(),

@@ -267,7 +267,6 @@ extern "C" int tab_nbr_build_batch(tab_nbr *nbr, int32_t n_struct, const int32_t
     nbr->rc_model = rc;
     nbr->ls_L = 0;
     nbr->col_padded = false;
-    nbr->has_wcore = false;
     nbr->rec16_valid = false;
     nbr->pcache_valid = false;
     nbr->has_rev = false;

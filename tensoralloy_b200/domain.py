@@ -205,6 +205,8 @@ class PeerComm:
         self.red = torch.zeros(16, dtype=torch.float64, device=device)      # my partial sums
         self.red_out = torch.zeros(16, dtype=torch.float64, device=device)
         self._apply(table, n_send_left, n_send_right)
+        torch.cuda.synchronize()
+        dist.barrier()
 
     def _gather_counts(self, n_owned, n_send_left, n_send_right):
         torch, dist = self.torch, self.dist
@@ -245,8 +247,9 @@ class PeerComm:
         self.dst_pos_r = self.hdl.get_buffer(R, (n_send_right, 3), f64, 3 * owned[R])
         self.dst_fp_l = self.hdl.get_buffer(L, (n_send_left,), f64, self.off_fp + from_l[L])
         self.dst_fp_r = self.hdl.get_buffer(R, (n_send_right,), f64, self.off_fp)
-        torch.cuda.synchronize()
-        self.dist.barrier()
+        # (no barrier here: a rebuild follows a completed step, whose last device barrier
+        # every rank has passed -- nobody reads the old regions any more; the all_gather of the
+        # counts orders the ranks before anyone stores into the new ones)
 
     def fence(self, channel):
         """All ranks have issued (and completed) the stores before this point."""
@@ -423,6 +426,7 @@ class SlabDomain:
         self._want_graph = False
         self.peer = None
         self.rebuilds = 0
+        self.rebuild_profile = None      # dict: accumulates ms per phase of `rebuild`
         self._need_rebuild = False
         self.d_move = torch.zeros(1, dtype=torch.float64, device=device)   # 1: atoms advance
         self._moving = False
@@ -445,7 +449,8 @@ class SlabDomain:
         self._attach(first=True)
 
     # -- (re)attachment of the rank state to the communication buffers -----------
-    def _attach(self, first=False):
+    def _attach(self, first=False, lap=None):
+        lap = lap or (lambda name: None)
         r = self.rank_state
         if self.peer is not None:
             pc = self.peer
@@ -457,8 +462,11 @@ class SlabDomain:
             n_l, n_r = self.comm.exchange_counts(len(r.idx_l), len(r.idx_r), self.device)
             r.set_halo_counts(n_l, n_r)
         self.d_vel = self.state[:, 3:6].contiguous()
+        lap('layout')
         self._exchange_positions()
+        lap('halo_exchange')
         r.build()
+        lap('list_build')
         self.n_local = r.n_owned
         self.nij_local = r.nbr.sizes()[0]
         self.h2d_bytes = r.n_owned * 24
@@ -526,8 +534,10 @@ class SlabDomain:
     def enable_graph(self, warmup=2):
         """Capture the resident-list step (kernels, peer stores, barriers, reduction)
         in one CUDA graph.  Returns True when the capture worked.  The graph is
-        re-captured after every rebuild (the owned / halo counts change)."""
+        re-captured after every rebuild (the owned / halo counts change): the re-captures
+        share the first capture's memory pool and side stream and skip the warm-up."""
         import torch
+        first = not self._want_graph or getattr(self, '_graph_pool', None) is None
         self._want_graph = True
         if self.peer is None and self.layout.world > 1:
             # NCCL point-to-point inside a stream capture is not robust (a capture that
@@ -536,28 +546,42 @@ class SlabDomain:
             self.graph_error = "graph capture needs the peer-memory path"
             return False
         try:
-            # warm-up launches must not move the atoms
-            self._set_moving(False)
-            side = torch.cuda.Stream()
+            if first:
+                # warm-up launches must not move the atoms
+                self._set_moving(False)
+                self._graph_stream = torch.cuda.Stream()
+                side = self._graph_stream
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    for _ in range(warmup):
+                        self._step_body()
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                self._graph_pool = torch.cuda.graph_pool_handle()
+            # low-level capture: the torch.cuda.graph context manager runs gc.collect() and
+            # empty_cache() on entry (5 ms per capture, measured) -- a re-capture happens at
+            # every list rebuild
+            g = torch.cuda.CUDAGraph()
+            side = self._graph_stream
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
-                for _ in range(warmup):
+                g.capture_begin(pool=self._graph_pool)
+                try:
                     self._step_body()
+                finally:
+                    g.capture_end()
             torch.cuda.current_stream().wait_stream(side)
-            torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self._step_body()
             # the capture itself does not run the kernels: nothing has moved
             self.graph = g
         except Exception as exc:
             self.graph = None
             self.graph_error = f"{type(exc).__name__}: {exc}"
-        # all ranks or none (a mixed ring would deadlock in the barriers)
-        flag = torch.tensor([1 if self.graph is not None else 0], device='cuda')
-        self.comm.dist.all_reduce(flag, op=self.comm.dist.ReduceOp.MIN)
-        if int(flag.item()) == 0:
-            self.graph = None
+        if first or self.graph is None:
+            # all ranks or none (a mixed ring would deadlock in the barriers)
+            flag = torch.tensor([1 if self.graph is not None else 0], device='cuda')
+            self.comm.dist.all_reduce(flag, op=self.comm.dist.ReduceOp.MIN)
+            if int(flag.item()) == 0:
+                self.graph = None
         return self.graph is not None
 
     def step(self):
@@ -574,15 +598,31 @@ class SlabDomain:
     # -- MD cycle ----------------------------------------------------------------
     def rebuild(self):
         """Migrate, recompute the send sets, exchange, rebuild the lists (collective)."""
+        import time
         r = self.rank_state
+        torch = self.torch
+        prof = self.rebuild_profile
+        tick = [time.perf_counter()]
+
+        def lap(name):
+            if prof is not None:
+                if self.device != 'cpu':
+                    torch.cuda.synchronize()
+                now = time.perf_counter()
+                prof[name] = prof.get(name, 0.0) + (now - tick[0]) * 1e3
+                tick[0] = now
+
         self.state[:, 0:3] = r.d_pos_owned
         self.state = self.comm.migrate(self.state)
+        lap('migrate')
         r.set_owned(self.state[:, 0:3])
+        lap('send_sets')
         self.graph = None
-        self._attach()
+        self._attach(lap=lap)
         self.rebuilds += 1
         if self._want_graph:
             self.enable_graph()
+            lap('graph_capture')
 
     def md_step(self):
         """One MD step with moving atoms.  The decision to rebuild is taken BEFORE the lists

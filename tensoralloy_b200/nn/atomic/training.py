@@ -125,6 +125,7 @@ class AtomicNNTrainer:
                                     volume=float(atoms.get_volume()), energy=t(energy),
                                     forces=t(forces), stress=t(stress)))
         self._batch = None
+        self._graph = None      # a captured step belongs to the old batch
 
     def _ensure_batch(self):
         """Lists + descriptors of ALL queued structures in one device handle (kept: the
@@ -238,7 +239,10 @@ class AtomicNNTrainer:
             with torch.cuda.graph(g):
                 loss, parts = self.total_loss()
                 loss.backward()
-            self._graph = (g, loss, parts)
+            # the replay writes into the gradient tensors allocated during the capture: keep
+            # them, so that `train_step` can re-attach them if a caller detached them
+            # (`optimizer.zero_grad()` sets p.grad = None by default)
+            self._graph = (g, loss, parts, [p.grad for p in self.params])
         except Exception as exc:      # capture is an optimisation, never a requirement
             self._graph = None
             self.graph_error = f"{type(exc).__name__}: {exc}"
@@ -249,6 +253,9 @@ class AtomicNNTrainer:
     def train_step(self, optimizer, dist=None, world=1):
         graph = getattr(self, '_graph', None)
         if graph is not None:
+            for p, g in zip(self.params, graph[3]):
+                if p.grad is not g:          # detached or replaced since the capture
+                    p.grad = g
             graph[0].replay()
             loss, parts = graph[1].detach(), graph[2]
         else:

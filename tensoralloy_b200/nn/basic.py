@@ -258,8 +258,54 @@ class BasicNN:
         return raw
 
     def _hessian(self, features):
-        raise NotImplementedError(
-            f"{self.__class__.__name__} has no analytic Hessian kernel yet")
+        """[Nvap, 3, Nvap, 3] Hessian in GSL order incl. the virtual atom (the layout of the
+        reference's `Output/Hessian` op, basic.py:410-421).  Models with a closed-form kernel
+        (EAM / FS, csrc/hessian.cu) override this; every other model (ADP, AtomicNN, EAM with
+        'nn' functions, ...) gets the derivative of its ANALYTIC forces, `_hessian_from_forces`."""
+        return self._embed_hessian(self._hessian_from_forces(features), features)
+
+    @staticmethod
+    def _embed_hessian(H, features):
+        vap = features.vap
+        nv = vap.max_vap_natoms
+        idx = vap.local_to_gsl_array[1:]
+        n = len(idx)
+        out = np.zeros((nv, 3, nv, 3), dtype=np.float64)
+        out[np.ix_(idx, range(3), idx, range(3))] = np.asarray(H).reshape(n, 3, n, 3)
+        return out
+
+    def _hessian_from_forces(self, features, step=1e-4):
+        """d2E / dR_a dR_b = -dF_a / dR_b [N,3,N,3] (caller order) from the analytic force
+        kernels: fourth-order central differences in every coordinate on the FIXED lists of
+        the structure (`tab_nbr_update`), which is what tf.hessians of the reference's graph
+        differentiates too (the neighbour metadata are constants of the graph).  The step is
+        small (1e-4 A: truncation step^4 F^(5) / 30 is negligible, rounding ~1e-15 / step =
+        1e-11 eV/A^2) because cutoff functions are only C1 at rc: a stencil that straddles rc for
+        some pair averages a jump of the second derivative, which the pointwise autograd Hessian
+        of the reference does not.  tests/test_hessian_gpu.py: 1e-7 eV/A^2 against the oracle's
+        autograd Hessian.  4 x 3N force evaluations."""
+        import torch
+        nbr, d_pos = features.nbr, features.d_pos
+        n = features.n_atoms
+        base = d_pos.clone()
+        H = np.zeros((n, 3, n, 3), dtype=np.float64)
+        coef = ((2.0, -1.0), (1.0, 8.0), (-1.0, -8.0), (-2.0, 1.0))
+        try:
+            for b in range(n):
+                for beta in range(3):
+                    acc = np.zeros((n, 3))
+                    for mult, w in coef:
+                        pos = base.clone()
+                        pos[b, beta] += mult * step
+                        nbr.update(pos)
+                        acc += w * self._evaluate(features, True, False, False)['forces']
+                    H[:, :, b, beta] = -acc / (12.0 * step)
+        finally:
+            nbr.update(base)
+            torch.cuda.synchronize()
+        # the exact Hessian is symmetric: average out the O(step^4) asymmetry
+        H2 = H.reshape(3 * n, 3 * n)
+        return (0.5 * (H2 + H2.T)).reshape(n, 3, n, 3)
 
     def _elastic(self, features):
         """Elastic constant tensor [6,6] in GPa with the reference's definition

@@ -250,10 +250,13 @@ class EamNN(BasicNN):
     def _hessian(self, features):
         """[Nvap, 3, Nvap, 3] Hessian in GSL order incl. the virtual atom, the
         layout of the reference's `Output/Hessian` op (basic.py:410-421)."""
-        H = self._device_model().hessian(features.nbr).cpu().numpy()
-        vap = features.vap
-        nv = vap.max_vap_natoms
-        idx = vap.local_to_gsl_array[1:]
-        out = np.zeros((nv, 3, nv, 3), dtype=np.float64)
-        out[np.ix_(idx, range(3), idx, range(3))] = H
-        return out
+        model = self._device_model()
+        try:
+            H = model.hessian(features.nbr).cpu().numpy()
+        except _lib.TabError as exc:
+            # ADP and 'nn' (MLP) functions have no closed-form second-derivative kernel: the
+            # analytic forces are differentiated instead (BasicNN._hessian_from_forces)
+            if 'status -4' not in str(exc):
+                raise
+            H = self._hessian_from_forces(features)
+        return self._embed_hessian(H, features)

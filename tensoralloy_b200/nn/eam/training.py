@@ -394,6 +394,7 @@ class EamTrainer:
                                     volume=float(atoms.get_volume()), energy=t(energy),
                                     forces=t(forces), stress=t(stress)))
         self._batch = None
+        self._graph = None      # a captured step belongs to the old batch
 
     def _ensure_batch(self):
         if self._batch is not None:

@@ -63,11 +63,18 @@ def get_optimizer(params, learning_rate, method='adam', **kwargs):
         return torch.optim.Adam(params, lr=learning_rate,
                                 betas=(kwargs.get('beta1', 0.9), 0.999), eps=1e-8)
     if m == 'adamw':
-        return torch.optim.AdamW(params, lr=learning_rate, eps=1e-8,
-                                 weight_decay=kwargs.get('decay', 1e-4))
+        # tf.contrib.opt.AdamWOptimizer (nn/utils.py:126-129) decays the variables by
+        # `weight_decay * var` per step, NOT scaled by the learning rate; torch's AdamW applies
+        # lr * weight_decay.  DecoupledAdam below keeps the reference's form.
+        return DecoupledAdam(params, lr=learning_rate, eps=1e-8,
+                             betas=(kwargs.get('beta1', 0.9), 0.999),
+                             decay=kwargs.get('decay', 1e-4))
     if m == 'nadam':
-        return torch.optim.NAdam(params, lr=learning_rate,
-                                 betas=(kwargs.get('beta1', 0.9), 0.999), eps=1e-8)
+        # tf.contrib.opt.NadamOptimizer = Adam with a Nesterov step and a CONSTANT beta1
+        # (torch.optim.NAdam follows Dozat's momentum schedule mu_t, momentum_decay 4e-3)
+        return DecoupledAdam(params, lr=learning_rate, eps=1e-8,
+                             betas=(kwargs.get('beta1', 0.9), 0.999), decay=0.0,
+                             nesterov=True)
     if m == 'adadelta':
         return torch.optim.Adadelta(params, lr=learning_rate, rho=kwargs.get('rho', 0.95),
                                     eps=1e-8)
@@ -79,6 +86,43 @@ def get_optimizer(params, learning_rate, method='adam', **kwargs):
                                momentum=kwargs.get('momentum', 0.9),
                                nesterov=kwargs.get('use_nesterov', True))
     raise ValueError("Supported SGD optimizers: adam, nadam, adadelta, rmsprop.")
+
+
+class DecoupledAdam(torch.optim.Optimizer):
+    """Adam in the arithmetic of TF 1.15 (`training_ops.cc` ApplyAdam):
+        lr_t = lr sqrt(1 - beta2^t) / (1 - beta1^t)
+        m <- beta1 m + (1 - beta1) g ;  v <- beta2 v + (1 - beta2) g^2
+        var <- var - lr_t m / (sqrt(v) + eps)             (eps OUTSIDE the bias correction)
+    `nesterov=True` is tf.contrib's NadamOptimizer (use_nesterov): the step uses
+    beta1 m + (1 - beta1) g instead of m.  `decay > 0` is tf.contrib's AdamWOptimizer
+    (DecoupledWeightDecayExtension): var <- var - decay * var before the Adam step,
+    independent of the learning rate."""
+
+    def __init__(self, params, lr, betas=(0.9, 0.999), eps=1e-8, decay=0.0, nesterov=False):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, decay=decay,
+                                      nesterov=nesterov))
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        for group in self.param_groups:
+            b1, b2 = group['betas']
+            for p in group['params']:
+                if p.grad is None:
+                    continue
+                st = self.state[p]
+                if not st:
+                    st['t'] = 0
+                    st['m'] = torch.zeros_like(p)
+                    st['v'] = torch.zeros_like(p)
+                st['t'] += 1
+                t, m, v, g = st['t'], st['m'], st['v'], p.grad
+                if group['decay']:
+                    p.mul_(1.0 - group['decay'])
+                m.mul_(b1).add_(g, alpha=1.0 - b1)
+                v.mul_(b2).addcmul_(g, g, value=1.0 - b2)
+                lr_t = group['lr'] * (1.0 - b2 ** t) ** 0.5 / (1.0 - b1 ** t)
+                num = m.mul(b1).add_(g, alpha=1.0 - b1) if group['nesterov'] else m
+                p.addcdiv_(num, v.sqrt().add_(group['eps']), value=-lr_t)
 
 
 class TrainOp:
@@ -115,7 +159,9 @@ class TrainOp:
         return lr
 
     def zero_grad(self):
-        self.optimizer.zero_grad(set_to_none=True)
+        # keep the tensors: a CUDA-graph training step (trainer.enable_graph) replays into the
+        # gradient tensors of its capture
+        self.optimizer.zero_grad(set_to_none=False)
 
     def ema_values(self):
         """The moving averages, in the order of `params` (what the reference exports with

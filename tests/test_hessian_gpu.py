@@ -97,3 +97,63 @@ def test_binary_alloy_hessian():
     ref = oeam.eam_evaluate(opot.get_potential('zjw04'), 'alloy', ['Mo', 'Ni'], sym,
                             atoms.positions, atoms.cell, [1, 1, 1], 5.5, hessian=True)
     assert np.abs(H - ref['hessian'].reshape(3 * n, 3 * n)).max() < 1e-8
+
+
+def test_adp_hessian_from_analytic_forces():
+    """AdpNN has no closed-form second-derivative kernel (csrc/hessian.cu refuses ADP): the
+    calculator serves `hessian` by fourth-order differences of the ANALYTIC forces on fixed
+    lists (BasicNN._hessian_from_forces) -- against the oracle's autograd Hessian of the ADP
+    energy (tf.hessians of the reference works for every model, basic.py:410-421)."""
+    from tensoralloy_b200.nn.eam import AdpNN
+    om = opot.get_potential('mishinh')
+    oz = opot.get_potential('zjw04')
+    fns = {'rho': oz.rho, 'phi': oz.phi, 'embed': oz.embed,
+           'dipole': om.dipole, 'quadrupole': om.quadrupole}
+    cp = {'Ni': {'rho': 'zjw04', 'embed': 'zjw04'},
+          'NiNi': {'phi': 'zjw04', 'dipole': 'mishinh', 'quadrupole': 'mishinh'}}
+    atoms = bulk_fcc('Ni', 3.52, (2, 2, 2))
+    atoms.positions += np.random.default_rng(11).normal(scale=0.05, size=atoms.positions.shape)
+    with precision_scope('high'):
+        nn = AdpNN(['Ni'], custom_potentials=cp,
+                   export_properties=['energy', 'forces', 'hessian'])
+        nn.attach_transformer(UniversalTransformer(['Ni'], rcut=5.0))
+        calc = TensorAlloyCalculator(nn)
+        H = calc.get_hessian(atoms)
+    n = len(atoms)
+    ref = oeam.eam_evaluate(None, 'adp', ['Ni'], atoms.get_chemical_symbols(), atoms.positions,
+                            atoms.cell, [1, 1, 1], 5.0, hessian=True, fns=fns)
+    Href = ref['hessian'].reshape(3 * n, 3 * n)
+    assert np.abs(H - H.T).max() < 1e-12
+    assert np.abs(H - Href).max() < 1e-7 * max(np.abs(Href).max(), 1.0)
+
+
+def test_atomic_nn_hessian_from_analytic_forces():
+    """AtomicNN (G2 + G4 + MLP) Hessian through the calculator vs the oracle's autograd
+    Hessian, Be hcp 3x3x2 (the reference's phonon workflow runs on NN potentials,
+    analysis/phonon.py:520-534)."""
+    from oracle import atomic as oat
+    from tensoralloy_b200.nn.atomic import AtomicNN, SymmetryFunction
+    atoms = bulk_hcp('Be', 2.2644, 3.5673, (3, 3, 2))
+    atoms.positions += np.random.default_rng(4).normal(scale=0.02, size=atoms.positions.shape)
+    elements = ['Be']
+    with precision_scope('high'):
+        clf = UniversalTransformer(elements, rcut=4.5, angular=True)
+        nn = AtomicNN(elements, SymmetryFunction(elements), minmax_scale=False,
+                      export_properties=('energy', 'forces', 'hessian'))
+        nn.attach_transformer(clf)
+        nn.initialize_variables(seed=611)
+        key = "Atomic/Be/Output/kernel"
+        nn.set_variable(key, nn.get_variable(key) * 0.02)
+        calc = TensorAlloyCalculator(nn)
+        H = calc.get_hessian(atoms)
+    params = {'Be': nn.mlp_params('Be')}
+    sfd = nn.descriptor.as_dict()
+    sf = {k: tuple(sfd[k]) for k in ('eta', 'omega', 'beta', 'gamma', 'zeta')}
+    sf['cutoff'] = sfd['cutoff_function']
+    ref = oat.atomic_evaluate(elements, atoms.get_chemical_symbols(), atoms.positions,
+                              atoms.cell, atoms.pbc, 4.5, params, sf=sf, angular=True,
+                              minmax={'Be': None}, hessian=True)
+    n = len(atoms)
+    Href = ref['hessian'].reshape(3 * n, 3 * n)
+    assert np.abs(H - Href).max() < 1e-7 * max(np.abs(Href).max(), 1.0)
+    assert np.abs(H.reshape(n, 3, n, 3).sum(axis=2)).max() < 1e-7      # acoustic sum rule

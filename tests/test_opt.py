@@ -28,8 +28,11 @@ def test_optimizer_factory_defaults():
     adam = get_optimizer(p, 0.01, 'adam', beta1=0.8)
     assert isinstance(adam, torch.optim.Adam) and adam.defaults['betas'] == (0.8, 0.999)
     assert adam.defaults['eps'] == 1e-8
-    assert get_optimizer(p, 0.01, 'adamw').defaults['weight_decay'] == 1e-4
-    assert isinstance(get_optimizer(p, 0.01, 'Nadam'), torch.optim.NAdam)
+    from tensoralloy_b200.nn.opt import DecoupledAdam
+    adamw = get_optimizer(p, 0.01, 'adamw')
+    assert isinstance(adamw, DecoupledAdam) and adamw.defaults['decay'] == 1e-4
+    nadam = get_optimizer(p, 0.01, 'Nadam')
+    assert isinstance(nadam, DecoupledAdam) and nadam.defaults['nesterov'] is True
     assert get_optimizer(p, 0.01, 'adadelta').defaults['rho'] == 0.95
     rms = get_optimizer(p, 0.01, 'rmsprop', momentum=0.5)
     assert rms.defaults['alpha'] == 0.9 and rms.defaults['momentum'] == 0.5
@@ -71,3 +74,45 @@ def test_train_op_drives_a_trainer_like_object_to_the_minimum():
         loss.backward()
         op.step()
     assert torch.allclose(w.detach(), target, atol=1e-6) and op.global_step == 300
+
+
+def test_tf_style_adamw_and_nadam_steps():
+    """tf.contrib AdamWOptimizer: var -= decay * var, NOT scaled by the learning rate, then the
+    TF Adam step (eps outside the bias correction); tf.contrib NadamOptimizer: the same Adam
+    with the Nesterov numerator beta1 m + (1 - beta1) g and a constant beta1."""
+    from tensoralloy_b200.nn.opt import DecoupledAdam
+    x0, g = 2.0, 0.5
+    lr, b1, b2, eps, decay = 0.01, 0.9, 0.999, 1e-8, 1e-2
+    p = torch.tensor([x0], dtype=torch.float64, requires_grad=True)
+    opt = DecoupledAdam([p], lr=lr, betas=(b1, b2), eps=eps, decay=decay)
+    x, m, v = x0, 0.0, 0.0
+    for t in range(1, 4):
+        p.grad = torch.tensor([g], dtype=torch.float64)
+        opt.step()
+        x *= 1.0 - decay
+        m = b1 * m + (1 - b1) * g
+        v = b2 * v + (1 - b2) * g * g
+        x -= lr * (1 - b2 ** t) ** 0.5 / (1 - b1 ** t) * m / (v ** 0.5 + eps)
+        assert abs(p.item() - x) < 1e-14
+    q = torch.tensor([x0], dtype=torch.float64, requires_grad=True)
+    opt = DecoupledAdam([q], lr=lr, betas=(b1, b2), eps=eps, nesterov=True)
+    x, m, v = x0, 0.0, 0.0
+    for t in range(1, 4):
+        q.grad = torch.tensor([g], dtype=torch.float64)
+        opt.step()
+        m = b1 * m + (1 - b1) * g
+        v = b2 * v + (1 - b2) * g * g
+        x -= lr * (1 - b2 ** t) ** 0.5 / (1 - b1 ** t) * (b1 * m + (1 - b1) * g) / (v ** 0.5 + eps)
+        assert abs(q.item() - x) < 1e-14
+
+
+def test_zero_grad_keeps_the_gradient_tensors():
+    """A CUDA-graph training step replays into the gradient tensors of its capture:
+    TrainOp.zero_grad must not detach them."""
+    from tensoralloy_b200.nn.opt import TrainOp
+    p = torch.zeros(3, requires_grad=True)
+    op = TrainOp([p])
+    p.grad = torch.ones(3)
+    g = p.grad
+    op.zero_grad()
+    assert p.grad is g and float(g.abs().sum()) == 0.0

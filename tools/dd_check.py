@@ -61,6 +61,34 @@ def main():
         ok = ok and good
         print(f"rank {rank} {mode}: peer={dom.peer is not None} dE/N={de:.2e} dF={df:.2e} "
               f"dV/N={dv:.2e} {'OK' if good else 'FAIL'}", flush=True)
+    # MD cycle: moving atoms, lists with a skin, collective rebuild decision, migration of the
+    # atoms that leave their slab, CUDA-graph step re-captured after every rebuild; after 25
+    # steps the decomposed forces equal a single-GPU evaluation of the SAME positions
+    skin = 0.3
+    md = SlabDomain(model, cells, a, rc, sigma, seed, world, rank, scaling='strong', skin=skin)
+    md.vstep_max *= 4.0
+    md.state[:, 3:6] *= 4.0          # faster atoms: more than one rebuild, atoms cross faces
+    md.d_vel = md.state[:, 3:6].contiguous()
+    if md.peer is not None:
+        md.enable_graph()
+    n0 = md.rank_state.n_owned
+    for _ in range(25):
+        md.md_step()
+    torch.cuda.synchronize()
+    pos_all, f_all = md.gather_global()
+    tot = md._totals().cpu().numpy()
+    nl2 = _lib.NeighborList()
+    d_all = torch.tensor(pos_all, device='cuda')
+    nl2.build(d_all, None, cell, [1, 1, 1], rc)
+    model.eval(nl2, 0, energy=e, forces=f, virial=v)
+    de = abs(tot[0] - e.item()) / len(pos)
+    df = np.abs(f_all - f.cpu().numpy()).max()
+    dv = np.abs(tot[1:10] - v.cpu().numpy()).max() / len(pos)
+    good = de < 1e-10 and df < 1e-8 and dv < 1e-8 and md.rebuilds >= 2
+    ok = ok and good
+    print(f"rank {rank} md-cycle: rebuilds={md.rebuilds} owned {n0}->{md.rank_state.n_owned} "
+          f"graph={md.graph is not None} dE/N={de:.2e} dF={df:.2e} dV/N={dv:.2e} "
+          f"{'OK' if good else 'FAIL'}", flush=True)
     if dom.peer is None:
         print(f"rank {rank}: peer path unavailable: {getattr(dom, 'peer_error', '?')}")
     flag = torch.tensor([1 if ok else 0], device='cuda')
