@@ -281,6 +281,15 @@ int tab_eam_eval_dd(tab_model *model, tab_nbr *nbr, int32_t precision,
  * BasicNN._get_hessian_op (nn/basic.py:410-421). */
 int tab_eam_hessian(tab_model *model, tab_nbr *nbr, double *d_hessian, void *stream);
 
+/* Analytic elastic-constant op of an EAM / FS model (float64):
+ *   C_ijkl = [ (d virial_ij / d h)^T h ]_kl   (eV),
+ * the reference's definition, nn/constraint/elastic.py:24-91 (tf.gradients(virial[i, j], cell)
+ * at fixed Cartesian positions), from the closed-form second derivatives of the pair and
+ * embedding functions.  d_out [n, 36]: the share of every atom (caller order), rows = Voigt pair
+ * (ij), columns = Voigt pair (kl), order xx yy zz yz xz xy; the caller sums over the atoms and
+ * divides by V * GPa. */
+int tab_eam_elastic(tab_model *model, tab_nbr *nbr, double *d_out, void *stream);
+
 /* Host-buffer convenience: H2D of positions (+types), neighbour build, eval,
  * D2H of the results -- the whole of TensorAlloyCalculator.calculate
  * (calculator.py:335-370) in one call.  Host buffers should be pinned for full

@@ -108,7 +108,7 @@ EXPORTS = [
     'tab_pairs_export', 'tab_pair_forces', 'tab_pair_jvp', 'tab_atomic_eval_dd', 'tab_eam_eval_dd', 'tab_eam_tabulate',
     'tab_profile_enable', 'tab_profile_read',
     'tab_nbr_set_skin', 'tab_nbr_max_displacement', 'tab_nbr_displacement_device',
-    'tab_reduce_slots',
+    'tab_reduce_slots', 'tab_eam_elastic',
 ]
 
 
@@ -161,6 +161,7 @@ def lib():
     L.tab_eam_pass1.argtypes = [vp, vp, i32, vp, vp]
     L.tab_eam_pass2.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, vp]
     L.tab_eam_hessian.argtypes = [vp, vp, vp, vp]
+    L.tab_eam_elastic.argtypes = [vp, vp, vp, vp]
     L.tab_eam_compute_host.argtypes = [vp, vp, i32, i32, vp, vp,
                                        C.POINTER(dbl), C.POINTER(i32), dbl, i32,
                                        vp, vp, vp, vp, vp]
@@ -470,6 +471,15 @@ class EamModel:
                                   _ptr(fprime_halo), _ptr(energy), _ptr(eatom),
                                   _ptr(forces), _ptr(virial), _stream()),
               'tab_eam_pass2')
+
+    def elastic(self, nbr):
+        """[6, 6] = sum over the atoms of tab_eam_elastic's shares: (d virial / d h)^T h in
+        Voigt pairs, eV (divide by V GPa for the reference's elastic tensor)."""
+        import torch
+        out = torch.empty((nbr.n, 36), dtype=torch.float64, device='cuda')
+        check(lib().tab_eam_elastic(self._h, nbr.handle, _ptr(out), _stream()),
+              'tab_eam_elastic')
+        return out.sum(dim=0).reshape(6, 6)
 
     def hessian(self, nbr):
         """Dense [n,3,n,3] float64 Hessian (caller atom order) on the device."""

@@ -418,6 +418,89 @@ __global__ void k_hessian(HessCtx c, const double *__restrict__ fp,
 }
 
 // ---------------------------------------------------------------------------
+// Elastic-constant op of the reference (nn/constraint/elastic.py:24-91):
+//   C_ijkl = [ (d virial_ij / d h)^T h ]_kl / V / GPa ,  virial_ij = sum_p g_p,i D_p,j ,
+// the derivative w.r.t. the lattice h taken at FIXED Cartesian positions: D_p = R_j - R_i + S_p h
+// depends on h only through the image shift, d D_p,a / d h_mk = S_p,m d_ak.  With T_p = S_p h
+// (the shift vector of the pair) and the pair-space second derivatives of the EAM energy
+//   d g_p,i / d D_q,k = d_pq A_p,ik + [same centre c] F''_c v_p,i v_q,k ,
+//   A_p = F'_c K^rho_p + 1/2 K^phi_p ,  v_p = rho'_p n_p ,  g_p = (F'_c rho'_p + 1/2 phi'_p) n_p
+// (directed pairs p of centre c):
+//   V GPa C_ijkl = sum_p A_p,ik T_p,l D_p,j + sum_c F''_c (sum_p v_p,i D_p,j)(sum_q v_q,k T_q,l)
+//                  + d_jk sum_p g_p,i T_p,l .
+// One thread per centre; out[c][vi * 6 + vj] = its share in Voigt pairs (xx yy zz yz xz xy).
+// ---------------------------------------------------------------------------
+struct ShiftCtx {           // what turns a list entry into its integer image shift S_p
+    const int *s0;          // packed wrap shift per atom, caller order
+    const int *ghost_S;     // packed image shift per ghost record
+    double h[9];            // lattice, rows = vectors
+};
+
+__global__ void k_elastic(HessCtx c, ShiftCtx sc, const double *__restrict__ fp,
+                          const double *__restrict__ fpp, double *__restrict__ out) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= c.n) return;
+    const int VI[6] = {0, 1, 2, 1, 0, 0}, VJ[6] = {0, 1, 2, 2, 2, 1};
+    const Atom4 me = c.atoms[a];
+    const int ta = c.types_ext[a];
+    const size_t base = (size_t)c.slice_ptr[a >> 5] * 32u + (a & 31);
+    const int cnt = c.counts[a];
+    double C[36];
+    for (int q = 0; q < 36; ++q) C[q] = 0.0;
+    double U[9], W[9], G[9];        // sum v_i D_j, sum v_k T_l, sum g_i T_l
+    for (int q = 0; q < 9; ++q) U[q] = W[q] = G[q] = 0.0;
+    for (int k = 0; k < cnt; ++k) {
+        const uint32_t e = c.col[base + (size_t)k * 32u];
+        const int j = (int)(e & TAB_COL_IDX_MASK), tj = (int)(e >> TAB_COL_TYPE_SHIFT);
+        const Atom4 aj = c.atoms[j];
+        double nv[3], r;
+        pair_geom(me, aj, nv, r);
+        const double D[3] = {aj.x - me.x, aj.y - me.y, aj.z - me.z};
+        const D2 rho = eval_pair_d2(c.rho[ta * c.n_el + tj], D2(r, 1.0, 0.0));
+        const D2 ph = eval_pair_d2(c.phi[ta * c.n_el + tj], D2(r, 1.0, 0.0));
+        const double v[3] = {rho.d * nv[0], rho.d * nv[1], rho.d * nv[2]};
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int jj = 0; jj < 3; ++jj) U[i * 3 + jj] += v[i] * D[jj];
+        // S_p of the pair w.r.t. the CALLER's positions (the reference's n1): the image shift of
+        // the ghost record minus the wrap shifts the library applied to the two atoms
+        int Sa = 0, Sb = 0, Sc = 0, ia, ib, ic, ja, jb, jc;
+        if (j >= c.n_loc) tab_unpack_shift(sc.ghost_S[j - c.n_loc], Sa, Sb, Sc);
+        tab_unpack_shift(sc.s0[c.perm[a]], ia, ib, ic);
+        tab_unpack_shift(sc.s0[c.perm[owner_of(c, j)]], ja, jb, jc);
+        Sa += ia - ja;
+        Sb += ib - jb;
+        Sc += ic - jc;
+        if (Sa == 0 && Sb == 0 && Sc == 0) continue;      // the pair does not move with h
+        const double T[3] = {Sa * sc.h[0] + Sb * sc.h[3] + Sc * sc.h[6],
+                             Sa * sc.h[1] + Sb * sc.h[4] + Sc * sc.h[7],
+                             Sa * sc.h[2] + Sb * sc.h[5] + Sc * sc.h[8]};
+        const double g1 = fp[a] * rho.d + 0.5 * ph.d;
+        double A[9];
+        pair_kernel(nv, r, g1, fp[a] * rho.dd + 0.5 * ph.dd, A);
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int l = 0; l < 3; ++l) {
+                W[i * 3 + l] += v[i] * T[l];
+                G[i * 3 + l] += g1 * nv[i] * T[l];
+            }
+        for (int vi = 0; vi < 6; ++vi)
+            for (int vj = 0; vj < 6; ++vj)
+                C[vi * 6 + vj] += A[VI[vi] * 3 + VI[vj]] * T[VJ[vj]] * D[VJ[vi]];
+    }
+    const double w = fpp[a];
+    for (int vi = 0; vi < 6; ++vi)
+        for (int vj = 0; vj < 6; ++vj) {
+            const int i = VI[vi], jj = VJ[vi], kk = VI[vj], l = VJ[vj];
+            double x = C[vi * 6 + vj] + w * U[i * 3 + jj] * W[kk * 3 + l];
+            if (jj == kk) x += G[i * 3 + l];
+            out[(size_t)c.perm[a] * 36 + vi * 6 + vj] = x;
+        }
+}
+
+// ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
 struct tab_model_view {      // layout prefix of tab_model (eam.cu)
@@ -477,6 +560,58 @@ extern "C" int tab_eam_hessian(tab_model *m, tab_nbr *nbr, double *d_hessian,
     k_hess_rho<<<(n + 127) / 128, 128, 0, st>>>(c, fp, fpp);
     TAB_LAUNCH_CHECK();
     k_hessian<<<(n + 63) / 64, 64, 0, st>>>(c, fp, fpp, d_hessian);
+    TAB_LAUNCH_CHECK();
+    return TAB_OK;
+}
+
+extern "C" int tab_eam_elastic(tab_model *m, tab_nbr *nbr, double *d_out, void *stream) {
+    if (!m || !nbr || !d_out) {
+        tab_set_error("tab_eam_elastic: bad argument");
+        return TAB_EINVAL;
+    }
+    if (!nbr->built) {
+        tab_set_error("tab_eam_elastic before tab_nbr_build");
+        return TAB_ESTATE;
+    }
+    if (nbr->n_halo > 0 || nbr->n_struct > 0) {
+        tab_set_error("tab_eam_elastic: one undecomposed structure per call");
+        return TAB_EUNSUPPORTED;
+    }
+    if (nbr->skin_built > 0.0) {
+        tab_set_error("tab_eam_elastic: the lists carry a skin (entries beyond rc); build with "
+                      "skin = 0");
+        return TAB_ESTATE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    HessCtx c;
+    int kind = 0;
+    TAB_TRY(tab_eam_tables(m, &c.rho, &c.phi, &c.embed, &c.n_el, &kind));
+    if (kind == TAB_EAM_ADP) {
+        tab_set_error("tab_eam_elastic: ADP not supported");
+        return TAB_EUNSUPPORTED;
+    }
+    c.n = nbr->n;
+    c.n_loc = nbr->n_loc;
+    c.atoms = nbr->atoms.as<Atom4>();
+    c.types_ext = nbr->types_ext.as<uint8_t>();
+    c.counts = nbr->counts.as<int>();
+    c.slice_ptr = nbr->slice_ptr.as<uint32_t>();
+    c.col = nbr->col.as<uint32_t>();
+    c.ghost_owner = nbr->ghost_owner.as<int>();
+    c.perm = nbr->perm.as<int>();
+    const int n = nbr->n;
+    TAB_TRY(nbr->rho.ensure(sizeof(double) * 2 * (size_t)n));
+    double *fp = nbr->rho.as<double>(), *fpp = fp + n;
+    const double *pool = tab_eam_pool(m);
+    TAB_CUDA(cudaMemcpyToSymbolAsync(g_hess_pool, &pool, sizeof(pool), 0,
+                                     cudaMemcpyHostToDevice, st));
+    k_hess_rho<<<(n + 127) / 128, 128, 0, st>>>(c, fp, fpp);
+    TAB_LAUNCH_CHECK();
+    ShiftCtx sc;
+    sc.s0 = nbr->s0.as<int>();
+    sc.ghost_S = nbr->ghost_S.as<int>();
+    memcpy(sc.h, nbr->grid.h, sizeof(sc.h));
+    k_elastic<<<(n + 63) / 64, 64, 0, st>>>(c, sc, fp, fpp, d_out);
     TAB_LAUNCH_CHECK();
     return TAB_OK;
 }

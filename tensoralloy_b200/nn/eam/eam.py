@@ -247,6 +247,20 @@ class EamNN(BasicNN):
         from tensoralloy_b200.analysis.phonon import _MASSES
         return [float(_MASSES.get(el, 0.0)) for el in self._elements]
 
+    def _elastic(self, features):
+        """Elastic tensor [6,6] in GPa (nn/constraint/elastic.py:24-91) from the closed-form
+        second derivatives (`tab_eam_elastic`); models without that kernel (ADP, 'nn'
+        functions) use the central difference of the virial of BasicNN._elastic."""
+        from tensoralloy_b200.atoms import GPa
+        model = self._device_model()
+        try:
+            C = model.elastic(features.nbr).cpu().numpy()
+        except _lib.TabError as exc:
+            if 'status -4' not in str(exc):
+                raise
+            return super()._elastic(features)
+        return C / features.volume / GPa
+
     def _hessian(self, features):
         """[Nvap, 3, Nvap, 3] Hessian in GSL order incl. the virtual atom, the
         layout of the reference's `Output/Hessian` op (basic.py:410-421)."""

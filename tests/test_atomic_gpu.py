@@ -90,9 +90,15 @@ def _compare(atoms, elements, rc, acut=None, angular=True, sf_kwargs=None,
         calc32 = TensorAlloyCalculator(nn)
         calc32.calculate(atoms, properties=['energy', 'forces'])
         e32, f32 = calc32.results['energy'], calc32.get_forces(atoms)
-    assert abs(e32 - ref['energy']) <= 2e-5 * max(abs(ref['energy']), 1.0)
     fscale = max(np.abs(ref['forces']).max(), 1e-2)
-    assert np.abs(f32 - ref['forces']).max() <= 1e-3 * fscale
+    print('float32: dE/|E|', abs(e32 - ref['energy']) / max(abs(ref['energy']), 1.0),
+          'dF/Fmax', np.abs(f32 - ref['forces']).max() / fscale)
+    # 'medium': 1e-5 relative (north star) on the energy; the forces of G2 + G4 models are sums
+    # of ~4 000 triple terms of both signs per atom evaluated and accumulated in float32 --
+    # measured 2e-7 .. 1.9e-5 of the largest force over the cases of this file (printed above):
+    # the bound is 3e-5
+    assert abs(e32 - ref['energy']) <= 1e-5 * max(abs(ref['energy']), 1.0)
+    assert np.abs(f32 - ref['forces']).max() <= 3e-5 * fscale
     return ref
 
 
@@ -228,8 +234,12 @@ def _grap_compare(atoms, elements, rc, algorithm, parameters, moments, method='p
         calc32 = TensorAlloyCalculator(nn)
         calc32.calculate(atoms, properties=['energy', 'forces'])
         e32, f32 = calc32.results['energy'], calc32.get_forces(atoms)
-    assert abs(e32 - ref['energy']) <= 2e-5 * max(abs(ref['energy']), 1.0)
-    assert np.abs(f32 - ref['forces']).max() <= 1e-3 * max(np.abs(ref['forces']).max(), 1e-2)
+    print('float32:', algorithm, moments, 'dE/|E|',
+          abs(e32 - ref['energy']) / max(abs(ref['energy']), 1.0), 'dF/Fmax',
+          np.abs(f32 - ref['forces']).max() / max(np.abs(ref['forces']).max(), 1e-2))
+    # 'medium' (GRAP: pair sums only): measured <= 1.6e-6 of the largest force
+    assert abs(e32 - ref['energy']) <= 1e-5 * max(abs(ref['energy']), 1.0)
+    assert np.abs(f32 - ref['forces']).max() <= 1e-5 * max(np.abs(ref['forces']).max(), 1e-2)
     return ref
 
 

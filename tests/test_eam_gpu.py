@@ -53,7 +53,11 @@ def compare(pot_name, elements, symbols, pos, cell, pbc, rc):
                                precision=1)
     assert abs(e32 - ref['energy']) <= 1e-5 * abs(ref['energy'])
     fscale = max(np.abs(ref['forces']).max(), 1e-3)
-    assert np.abs(f32 - ref['forces']).max() <= 2e-5 * fscale + 1e-5
+    print('float32: dE/|E|', abs(e32 - ref['energy']) / abs(ref['energy']),
+          'dF/Fmax', np.abs(f32 - ref['forces']).max() / fscale, 'Fmax', fscale)
+    # 1e-5 of the force scale (measured <= 2.5e-6); on the perfect lattice the forces vanish
+    # by symmetry and the scale is that of a rattled one (0.05 eV/A)
+    assert np.abs(f32 - ref['forces']).max() <= 1e-5 * max(fscale, 0.05)
     return ref
 
 

@@ -52,3 +52,31 @@ def test_elastic_property_single_atom_cell():
     assert abs(C[0, 1] - 147.15) < 0.02
     assert abs(C[3, 3] - 124.72) < 0.02
     assert np.abs(C - C.T).max() < 1e-8
+
+
+def test_analytic_elastic_op_equals_the_differenced_virial():
+    """`tab_eam_elastic` (closed-form d virial / d h, nn/constraint/elastic.py:24-91) against
+    the central difference of the GPU virial over the nine lattice components (the definition
+    itself, BasicNN._elastic): primitive cell, a rattled 4-atom cell (only image pairs move
+    with h) and a two-species FS-like alloy cell."""
+    from tensoralloy_b200.nn.basic import BasicNN
+    from tensoralloy_b200.nn.eam import EamAlloyNN
+    from tensoralloy_b200.precision import precision_scope
+    from tensoralloy_b200.transformer import UniversalTransformer
+    a = 3.52
+    prim = Atoms(['Ni'], [[0, 0, 0]],
+                 0.5 * a * np.array([[0, 1, 1], [1, 0, 1], [1, 1, 0]], dtype=float), True)
+    rng = np.random.default_rng(3)
+    conv = Atoms(['Ni'] * 4, np.array([[0, 0, 0], [0, .5, .5], [.5, 0, .5], [.5, .5, 0]]) * a +
+                 rng.normal(scale=0.03, size=(4, 3)), np.eye(3) * a, True)
+    alloy = Atoms(['Mo', 'Ni', 'Ni', 'Mo'], conv.positions * (3.6 / a), np.eye(3) * 3.6, True)
+    for atoms, elements in ((prim, ['Ni']), (conv, ['Ni']), (alloy, ['Mo', 'Ni'])):
+        with precision_scope('high'):
+            nn = EamAlloyNN(elements, custom_potentials='zjw04',
+                            export_properties=['energy', 'forces', 'stress', 'elastic'])
+            clf = UniversalTransformer(elements, rcut=6.0)
+            nn.attach_transformer(clf)
+            feats = clf.get_constant_features(atoms)
+            C = nn._elastic(feats)
+            C_fd = BasicNN._elastic(nn, feats)
+        assert np.abs(C - C_fd).max() < 2e-5 * max(1.0, np.abs(C_fd).max()), (C, C_fd)
