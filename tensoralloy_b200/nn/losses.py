@@ -22,10 +22,26 @@ from tensoralloy_b200.precision import get_float_dtype
 METHODS = ('rmse', 'rrmse', 'logcosh', 'ylogy')
 
 
-def rmse(x, y, eps=None):
+def _weights(sample_weight, like, normalized_weight):
+    """losses.py:79-87: optional per-sample weights; `normalized_weight` divides them by their
+    sum (and by the trailing extent of `like` for rank > 1), so that the weighted SUM below
+    replaces the mean."""
+    w = sample_weight
+    if normalized_weight:
+        w = w / torch.sum(w)
+        if w.dim() > 1:
+            w = w / float(like[0].numel())
+    return w
+
+
+def rmse(x, y, eps=None, sample_weight=None, normalized_weight=False):
     if eps is None:
         eps = get_float_dtype().eps
-    return torch.sqrt(torch.mean((x - y) ** 2) + eps)
+    if sample_weight is not None:
+        mse = torch.sum((x - y) ** 2 * _weights(sample_weight, x, normalized_weight))
+    else:
+        mse = torch.mean((x - y) ** 2)
+    return torch.sqrt(mse + eps)
 
 
 def mae(x, y):
@@ -41,24 +57,32 @@ def relative_rmse(labels, predictions):
     return torch.mean(upper / lower)
 
 
-def logcosh(labels, predictions):
+def logcosh(labels, predictions, sample_weight=None, normalized_weight=False):
     d = labels - predictions
-    return torch.mean(d + torch.nn.functional.softplus(-2.0 * d) - math.log(2.0))
+    v = d + torch.nn.functional.softplus(-2.0 * d) - math.log(2.0)
+    if sample_weight is not None:
+        return torch.sum(v * _weights(sample_weight, labels, normalized_weight))
+    return torch.mean(v)
 
 
-def ylogy(labels, predictions):
+def ylogy(labels, predictions, sample_weight=None, normalized_weight=False):
     logx = torch.log(torch.clamp(labels, min=1e-12))
     logy = torch.log(torch.clamp(predictions, min=1e-12))
-    return torch.mean((logx - logy) ** 2 * labels)
+    v = (logx - logy) ** 2 * labels
+    if sample_weight is not None:
+        return torch.sum(v * _weights(sample_weight, labels, normalized_weight))
+    return torch.mean(v)
 
 
-def _raw(method, labels, predictions, allowed):
+def _raw(method, labels, predictions, allowed, sample_weight=None, normalized_weight=False):
     if method not in METHODS:
         raise KeyError(method)                    # LossMethod[options.method]
     if method not in allowed:
         raise ValueError(f"loss method '{method}' is not available for this property")
-    return {'rmse': rmse, 'rrmse': relative_rmse, 'logcosh': logcosh,
-            'ylogy': ylogy}[method](labels, predictions)
+    if method == 'rrmse':                         # losses.py:53-66 takes no weights
+        return relative_rmse(labels, predictions)
+    return {'rmse': rmse, 'logcosh': logcosh, 'ylogy': ylogy}[method](
+        labels, predictions, sample_weight=sample_weight, normalized_weight=normalized_weight)
 
 
 def dynamic_weight(weight, global_step=0, max_train_steps=None, logscale=False):
@@ -75,16 +99,33 @@ def dynamic_weight(weight, global_step=0, max_train_steps=None, logscale=False):
     return w0 + (w1 - w0) / max_train_steps * global_step
 
 
-def energy_loss(labels, predictions, n_atoms, per_atom_loss=True, weight=1.0, method='rmse'):
+def energy_loss(labels, predictions, n_atoms, per_atom_loss=True, weight=1.0, method='rmse',
+                sample_weight=None, normalized_weight=False):
+    """losses.py:204-282; `sample_weight` [batch] (e.g. `adaptive_sample_weight`)."""
     if per_atom_loss:
         n = n_atoms.to(labels.dtype)
         labels, predictions = labels / n, predictions / n
-    return weight * _raw(method, labels, predictions, METHODS)
+    return weight * _raw(method, labels, predictions, METHODS, sample_weight,
+                         normalized_weight)
 
 
-def forces_loss(labels, predictions, weight=1.0, method='rmse'):
-    """labels / predictions: [total real atoms, 3] (padding already removed)."""
-    return weight * _raw(method, labels, predictions, ('rmse', 'rrmse', 'logcosh'))
+def forces_loss(labels, predictions, weight=1.0, method='rmse', sample_weight=None, sid=None,
+                normalized_weight=True):
+    """losses.py:285-391 (`_absolute_forces_loss`: rmse or logcosh; the reference asserts
+    against rrmse).  labels / predictions: [total real atoms, 3] (padding already removed).
+    `sample_weight` [batch] with `sid` [total atoms] = structure of every atom: each atom
+    carries its structure's weight; normalised by (sum of the atom weights x 3), the weighted
+    sum over atoms and components replaces the mean (losses.py:308-322)."""
+    if method == 'rrmse':
+        raise ValueError("loss method 'rrmse' is not available for the forces "
+                         "(losses.py:297)")
+    w = None
+    if sample_weight is not None:
+        w = sample_weight[sid] if sid is not None else sample_weight
+        if normalized_weight:
+            w = w / (torch.sum(w) * 3.0)
+        w = w.unsqueeze(1)
+    return weight * _raw(method, labels, predictions, ('rmse', 'logcosh'), w, False)
 
 
 def stress_loss(labels, predictions, weight=1.0, method='rmse'):

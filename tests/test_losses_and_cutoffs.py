@@ -83,7 +83,9 @@ def test_other_loss_methods_and_dynamic_weights():
     with precision_scope('high'):
         assert abs(losses.forces_loss(tx, ty, method='logcosh').item()
                    - np.mean(np.log(np.cosh(x - y)))) < 1e-12
-        assert abs(losses.forces_loss(tx, ty, method='rrmse').item()
+        with pytest.raises(ValueError, match="not available"):
+            losses.forces_loss(tx, ty, method='rrmse')      # losses.py:297 asserts against it
+        assert abs(losses.stress_loss(tx, ty, method='rrmse').item()
                    - np.mean(np.linalg.norm(x - y, axis=1) / np.linalg.norm(x, axis=1))) < 1e-12
         e, p, n = tx[:, 0], ty[:, 0], torch.tensor(rng.integers(1, 5, 7).astype(float))
         xe, ye = (e / n).numpy(), (p / n).numpy()
@@ -139,3 +141,36 @@ def test_adaptive_sample_weight():
         losses.adaptive_sample_weight(t, sid, 3, 'mean', 'sigmoid', *args)
     with pytest.raises(ValueError, match="sigmoid"):
         losses.adaptive_sample_weight(t, sid, 3, 'norm', 'linear', *args)
+
+
+def test_sample_weights():
+    """losses.py:69-153 (energy: weighted SUM of squares, weights optionally normalised by their
+    sum) and :285-332 (forces: every atom carries its structure's weight, normalised by
+    (sum of atom weights) x 3) -- with `adaptive_sample_weight` (:553-586) as the source."""
+    rng = np.random.default_rng(9)
+    with precision_scope('high'):
+        e, p = torch.tensor(rng.normal(size=5)), torch.tensor(rng.normal(size=5))
+        n = torch.tensor([3.0, 4.0, 2.0, 5.0, 3.0])
+        w = torch.tensor(rng.uniform(0.2, 1.0, 5))
+        d = (e / n - p / n).numpy()
+        wn = (w / w.sum()).numpy()
+        assert abs(losses.energy_loss(e, p, n, sample_weight=w, normalized_weight=True).item()
+                   - np.sqrt(np.sum(d * d * wn) + 1e-14)) < 1e-14
+        assert abs(losses.energy_loss(e, p, n, sample_weight=w).item()
+                   - np.sqrt(np.sum(d * d * w.numpy()) + 1e-14)) < 1e-14
+        assert abs(losses.energy_loss(e, p, n, method='logcosh', sample_weight=w,
+                                      normalized_weight=True).item()
+                   - np.sum(np.log(np.cosh(d)) * wn)) < 1e-13
+        sid = torch.tensor([0] * 3 + [1] * 4 + [2] * 2 + [3] * 5 + [4] * 3)
+        f, g = torch.tensor(rng.normal(size=(17, 3))), torch.tensor(rng.normal(size=(17, 3)))
+        wa = w[sid].numpy()
+        wa = wa / (wa.sum() * 3.0)
+        df = (f - g).numpy()
+        assert abs(losses.forces_loss(f, g, sample_weight=w, sid=sid).item()
+                   - np.sqrt(np.sum(df * df * wa[:, None]) + 1e-14)) < 1e-14
+        # equal weights, normalised = the plain mean
+        one = torch.ones(5, dtype=torch.float64)
+        assert abs(losses.forces_loss(f, g, sample_weight=one, sid=sid).item()
+                   - losses.forces_loss(f, g).item()) < 1e-14
+        aw = losses.adaptive_sample_weight(f, sid, 5, 'fmax', 'sigmoid', 2.0, 1.5, 1.0, 0.1)
+        assert aw.shape == (5,) and float(aw.min()) > 0.1
