@@ -352,6 +352,14 @@ def roofline_block(m, runner, hbm, which, precision, kernel_name, tag):
            "step_hbm_frac": ((8.0 * nij + (2 * rec + 12 * 8) * n_loc) /
                              (m["resident_ms"] * 1e-3) / 1e9 / hbm)}
     if precision == 'high':
+        # the compute-side roofline of the float64 kernels: FP64 instructions per list entry
+        # counted in the SASS of the pair loops against 64 FP64 lanes per
+        # clock and SM, at the B200's 1.965 GHz boost clock
+        fp64_ms = (34 + 80) * nij / (64.0 * 148 * 1.965e9) * 1e3
+        pair_ms = m["kernel_ms"][0] + m["kernel_ms"][2]
+        out["fp64_pipe"] = {"instr_per_entry": {"rho_pass": 34, "force_pass": 80},
+                            "floor_ms": fp64_ms, "measured_ms": pair_ms,
+                            "frac": fp64_ms / pair_ms if pair_ms > 0 else None}
         out["note"] = ("float64 analytic zjw04 is bound by the FP64 pipe (64 lanes/clk/SM), not "
                        "by HBM: DESIGN.md section 4 gives the instruction counts and the ncu "
                        "pipe utilisation; the HBM fraction is reported as BASELINE.json asks")
@@ -580,6 +588,7 @@ class SingleGpu:
         with precision_scope(name):
             nn = EamAlloyNN(elements=['Ni'], custom_potentials='zjw04')
             nn.attach_transformer(UniversalTransformer(['Ni'], rcut=RC))
+            nn.reuse_result_buffers = True     # MD-loop mode of the calculator (nn/basic.py)
             calc = TensorAlloyCalculator(nn)
             pos = self.h_pos.numpy()
             atoms = Atoms(numbers=np.full(len(pos), 28), positions=pos, cell=self.cell,
@@ -597,8 +606,10 @@ class SingleGpu:
         ms = 1e3 * statistics.mean(times)
         return {"value": self.n_total / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
                 "includes": "TensorAlloyCalculator.calculate(atoms, ['energy', 'forces', "
-                            "'stress']): Atoms.copy, VAP / type maps, H2D from the numpy "
-                            "array, list build, kernels, D2H into numpy results"}
+                            "'stress']): snapshot of the Atoms, VAP / type maps, H2D from the "
+                            "numpy array, list build, kernels, D2H into pinned staging, copy "
+                            "into the results arrays (reuse_result_buffers = True: two "
+                            "alternating persistent sets instead of fresh arrays)"}
 
     def check(self, n_sample, dist=None, sampled=None):
         torch = self.torch

@@ -1357,7 +1357,9 @@ extern "C" int tab_nbr_build_dd(tab_nbr *nbr, int32_t n_owned, int32_t n_halo,
         // row capacity: last build of this handle, else the mean density
         const bool multi = nbr->n_types > 1;
         uint32_t wcap;
-        if (nbr->wcap_hint > 0 && nbr->wcap_hint_n == n_loc) wcap = nbr->wcap_hint;
+        // (valid while the atom count stays within 5 %: a rank of a spatial decomposition gains
+        // and loses a few atoms at every rebuild)
+        if (nbr->wcap_hint > 0 && abs(nbr->wcap_hint_n - n_loc) * 20 <= n_loc) wcap = nbr->wcap_hint;
         else {
             const double vol = fabs(g.h[0] * (g.h[4] * g.h[8] - g.h[5] * g.h[7]) -
                                     g.h[1] * (g.h[3] * g.h[8] - g.h[5] * g.h[6]) +

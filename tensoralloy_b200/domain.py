@@ -70,6 +70,18 @@ def _graph_exec_update(live, captured):
         return False
 
 
+def _where_static(mask, count):
+    """Indices of the set entries of a 1-D mask whose number is already known on the host
+    (ascending): `nonzero` without its device-to-host read-back."""
+    import torch
+    if count == 0:
+        return torch.zeros(0, dtype=torch.int64, device=mask.device)
+    try:
+        return torch.nonzero_static(mask, size=int(count)).flatten()
+    except (RuntimeError, NotImplementedError):
+        return torch.nonzero(mask).flatten()
+
+
 class SlabLayout:
     """Pure geometry: which atoms a rank owns and which it sends where."""
 
@@ -207,6 +219,8 @@ class PeerComm:
     allocated once (`slack` above the first layout); `configure` recomputes the views after
     every rebuild, when the owned / halo counts of the ranks have changed.
     """
+    MIG_CAP = 16384      # atoms that may leave through one face between two rebuilds
+    MIG_COLS = 7         # position, velocity, id
 
     def __init__(self, layout, n_owned, n_send_left, n_send_right, device, slack=1.12):
         import torch
@@ -236,6 +250,23 @@ class PeerComm:
                                      dtype=torch.int64, device=device)
         self.red = torch.zeros(16, dtype=torch.float64, device=device)      # my partial sums
         self.red_out = torch.zeros(16, dtype=torch.float64, device=device)
+        # rebuild-time exchanges through the same peer mappings (no NCCL call, one read-back
+        # each): the migration mailbox [2 directions][1 + MIG_CAP * MIG_COLS] (count, then
+        # rows) and the table of every rank's [n_owned, n_send_left, n_send_right]
+        self.mail = symm.empty(2 * (1 + self.MIG_CAP * self.MIG_COLS), dtype=torch.float64,
+                               device=device)
+        self.mail.zero_()
+        self.mail_hdl = symm.rendezvous(self.mail, group)
+        self.counts = symm.empty(4 * world, dtype=torch.float64, device=device)
+        self.counts.zero_()
+        self.counts_hdl = symm.rendezvous(self.counts, group)
+        self.counts_ptrs = torch.tensor([int(p) for p in self.counts_hdl.buffer_ptrs],
+                                        dtype=torch.int64, device=device)
+        L, R = layout.left, layout.right
+        box = 1 + self.MIG_CAP * self.MIG_COLS
+        # what I send to the left lands in the left neighbour's "from the right" box, ...
+        self.mail_to_l = self.mail_hdl.get_buffer(L, (box,), torch.float64, box)
+        self.mail_to_r = self.mail_hdl.get_buffer(R, (box,), torch.float64, 0)
         self._apply(table, n_send_left, n_send_right)
         torch.cuda.synchronize()
         dist.barrier()
@@ -250,9 +281,65 @@ class PeerComm:
         return [t.tolist() for t in table]
 
     def configure(self, n_owned, n_send_left, n_send_right):
-        """New owned / send counts (after a migration): recompute every view."""
-        self._apply(self._gather_counts(n_owned, n_send_left, n_send_right),
-                    n_send_left, n_send_right)
+        """New owned / send counts (after a migration): recompute every view.  The counts
+        travel through the symmetric count table: one kernel stores mine into every rank's
+        table, a device barrier, one read-back."""
+        from tensoralloy_b200 import _lib
+        torch = self.torch
+        world, rank = self.layout.world, self.layout.rank
+        mine = torch.tensor([n_owned, n_send_left, n_send_right, 0.0], dtype=torch.float64,
+                            device=self.device)
+        _lib.peer_put(mine, self.counts_ptrs, rank)
+        self.counts_hdl.barrier(channel=3)
+        table = self.counts.view(world, 4)[:, :3].to(torch.int64).tolist()
+        self._apply(table, n_send_left, n_send_right)
+
+    def migrate(self, state):
+        """`DistComm.migrate` over the peer mappings: the atoms that left the slab are stored
+        straight into the ring neighbours' mailboxes (count + rows), one device barrier, one
+        read-back of the two received counts.  The received rows are appended in a fixed order
+        (from the left, then from the right; each in the sender's order)."""
+        torch = self.torch
+        lay = self.layout
+        state = state.clone()
+        x = torch.remainder(state[:, 0], lay.lx)
+        x = torch.where(x >= lay.lx, torch.zeros_like(x), x)
+        state[:, 0] = x
+        owner = lay.owner_of(x).to(torch.int64)
+        # 0 keep, 1 to the left, 2 to the right, 3 further away (an error)
+        code = torch.where(owner == lay.rank, 0, torch.where(
+            owner == lay.left, 1, torch.where(owner == lay.right, 2, 3)))
+        if lay.world == 2:
+            code = torch.where(owner == lay.rank, 0, 2)      # left == right: one other rank
+        n_keep, n_l, n_r, n_bad = torch.bincount(code, minlength=4).tolist()      # read-back 1
+        if n_bad:
+            raise RuntimeError("an atom moved further than to the adjacent slab between two "
+                               "list rebuilds")
+        if max(n_l, n_r) > self.MIG_CAP:
+            raise RuntimeError(f"{max(n_l, n_r)} atoms leave through one face: more than the "
+                               f"migration mailbox holds ({self.MIG_CAP})")
+        c = self.MIG_COLS
+        kept = state[_where_static(code == 0, n_keep)]
+        self.mail_to_l[0] = float(n_l)
+        self.mail_to_r[0] = float(n_r)
+        if n_l:
+            self.mail_to_l[1:1 + n_l * c] = state[_where_static(code == 1, n_l)].reshape(-1)
+        if n_r:
+            self.mail_to_r[1:1 + n_r * c] = state[_where_static(code == 2, n_r)].reshape(-1)
+        self.mail_hdl.barrier(channel=4)
+        box = 1 + self.MIG_CAP * c
+        got = self.mail[[0, box]].tolist()                                      # read-back 2
+        a, b = int(got[0]), int(got[1])
+        parts = [kept]
+        if a:
+            parts.append(self.mail[1:1 + a * c].view(a, c))
+        if b:
+            parts.append(self.mail[box + 1:box + 1 + b * c].view(b, c))
+        out = torch.cat(parts, dim=0).contiguous()
+        # (a mailbox is not overwritten before its owner has copied it out: the peers' next
+        # stores into it come after the device barrier of `configure`, which this rank enters
+        # after the copy above, in stream order)
+        return out
 
     def _apply(self, table, n_send_left, n_send_right):
         torch = self.torch
@@ -328,8 +415,12 @@ class SlabRank:
         self._pos0 = pos_owned.to(device).contiguous()
         self.n_owned = int(self._pos0.shape[0])
         m_l, m_r = self.lay.send_masks(self._pos0[:, 0])
-        self.idx_l = torch.nonzero(m_l).flatten()
-        self.idx_r = torch.nonzero(m_r).flatten()
+        # both index sets with ONE read-back: stable sort of the membership code, counts
+        # (an atom may be in both sets when the slab is narrower than 2 (rc + skin) + ...: the
+        # two sets are therefore formed separately from the same pass)
+        n_l, n_r = torch.stack([m_l.sum(), m_r.sum()]).tolist()
+        self.idx_l = _where_static(m_l, n_l)
+        self.idx_r = _where_static(m_r, n_r)
         self.shift_l = [self.lay.shift_to_left, 0.0, 0.0]
         self.shift_r = [self.lay.shift_to_right, 0.0, 0.0]
         f64 = dict(dtype=torch.float64, device=device)
@@ -507,8 +598,9 @@ class SlabDomain:
     def set_precision(self, name):
         self.precision = self.prec_id[name]
         self.rank_state.precision = self.precision
-        if self.graph is not None:
-            self.enable_graph()         # the captured kernels depend on the precision
+        # the captured kernels depend on the precision: the next steps run eagerly (first use
+        # of a precision allocates inside the library) and `md_step` captures again
+        self.graph = None
 
     def describe(self):
         lay = self.layout
@@ -600,7 +692,9 @@ class SlabDomain:
             side = self._graph_stream
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
-                g.capture_begin(pool=self._graph_pool)
+                # thread_local: CUDA calls of other threads (the NCCL watchdog polls events)
+                # must not invalidate the capture
+                g.capture_begin(pool=self._graph_pool, capture_error_mode="thread_local")
                 try:
                     self._step_body()
                 finally:
@@ -617,12 +711,16 @@ class SlabDomain:
         except Exception as exc:
             self.graph = None
             self.graph_error = f"{type(exc).__name__}: {exc}"
-        if first or self.graph is None:
-            # all ranks or none (a mixed ring would deadlock in the barriers)
+        if first:
+            # one answer for the whole job (bench.py reports it).  Re-captures do not need the
+            # agreement: a replayed graph and an eager step issue the same kernels, stores and
+            # device barriers, so ranks may differ without waiting on each other
             flag = torch.tensor([1 if self.graph is not None else 0], device='cuda')
             self.comm.dist.all_reduce(flag, op=self.comm.dist.ReduceOp.MIN)
             if int(flag.item()) == 0:
                 self.graph = None
+        if self.graph is None:
+            self._want_graph = False        # do not try again after every rebuild
         return self.graph is not None
 
     def step(self):
@@ -654,16 +752,16 @@ class SlabDomain:
                 tick[0] = now
 
         self.state[:, 0:3] = r.d_pos_owned
-        self.state = self.comm.migrate(self.state)
+        self.state = self.peer.migrate(self.state) if self.peer is not None else \
+            self.comm.migrate(self.state)
         lap('migrate')
         r.set_owned(self.state[:, 0:3])
         lap('send_sets')
         self.graph = None               # (the executable graph survives in _graph_exec)
         self._attach(lap=lap)
         self.rebuilds += 1
-        if self._want_graph:
-            self.enable_graph()
-            lap('graph_capture')
+        # the step that follows runs eagerly (with the new sizes: every library buffer that has
+        # to grow does so outside a capture); `md_step` re-captures after it
 
     def md_step(self):
         """One MD step with moving atoms.  The decision to rebuild is taken BEFORE the lists
@@ -675,6 +773,17 @@ class SlabDomain:
             self._need_rebuild = False
         self._set_moving(True)
         self.step()
+        if self.graph is None and self._want_graph and self.skin > 0.0:
+            import time
+            if self.rebuild_profile is not None:
+                self.torch.cuda.synchronize()       # (the eager step is not part of it)
+            t0 = time.perf_counter()
+            self.enable_graph()
+            if self.rebuild_profile is not None:
+                self.torch.cuda.synchronize()
+                self.rebuild_profile['graph_capture'] = \
+                    self.rebuild_profile.get('graph_capture', 0.0) + \
+                    (time.perf_counter() - t0) * 1e3
         if self.skin > 0.0:
             disp = float(self._totals()[10].item())      # synchronises the step
             self._need_rebuild = not (2.0 * (disp + self.vstep_max) <= self.skin)

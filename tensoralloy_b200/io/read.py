@@ -113,6 +113,56 @@ class Dataset:
         return trainer
 
 
+    # -- TFRecord files (train/dataset/dataset.py:168-400) -----------------------------
+    def record_signature(self, transformer):
+        """dataset.py:260-278: 'k{2|3}-rc{rcut:.2f}-fp{32|64}'."""
+        from tensoralloy_b200.precision import get_float_dtype
+        bits = 32 if get_float_dtype().as_numpy_dtype == np.float32 else 64
+        return f"k{3 if transformer.angular else 2}-rc{transformer.rcut:.2f}-fp{bits}"
+
+    def to_records(self, savedir, transformer, name='dataset', test_size=0.2, seed=611,
+                   write='all', neighbor_lists=None):
+        """Split into a training and a test subset (sklearn `train_test_split`, or the given
+        1-based test ids) and write each as one TFRecord file of encoded examples, named as the
+        reference names them: `{name}-{test|train}-{signature}-{size}.universal.tfrecords`
+        (dataset.py:280-342).  `transformer`: a `BatchUniversalTransformer` with `nij_max`
+        (and `nijk_max`) set.  Returns {'test': path, 'train': path} of the files written."""
+        import os
+        from tensoralloy_b200.transformer.tfrecord import TFRecordWriter
+        assert write in ('all', 'eval', 'train')
+        ids = list(range(1, 1 + len(self)))
+        if isinstance(test_size, (list, tuple)):
+            test = list(test_size)
+            train = [x for x in ids if x not in test]
+        else:
+            from sklearn.model_selection import train_test_split
+            train, test = train_test_split(ids, random_state=seed, test_size=test_size)
+        os.makedirs(savedir, exist_ok=True)
+        sig = self.record_signature(transformer)
+        out = {}
+        for key, subset in (('test', test), ('train', train)):
+            if write != 'all' and write != {'test': 'eval', 'train': 'train'}[key]:
+                continue
+            path = os.path.join(savedir,
+                                f"{name}-{key}-{sig}-{len(subset)}.universal.tfrecords")
+            with TFRecordWriter(path) as writer:
+                for k in subset:
+                    nl = None if neighbor_lists is None else neighbor_lists[k - 1]
+                    writer.write(transformer.encode(self.images[k - 1],
+                                                    neighbor_list=nl).SerializeToString())
+            out[key] = path
+        return out
+
+    @classmethod
+    def from_records(cls, filename, transformer):
+        """The labelled structures of one TFRecord file (written by `to_records` or by the
+        reference with the same transformer settings)."""
+        from tensoralloy_b200.transformer.tfrecord import read_tfrecords
+        images = [transformer.decode_atoms(transformer.decode_protobuf(rec))
+                  for rec in read_tfrecords(filename)]
+        return cls.from_images(images)
+
+
 def _parse_header(line):
     out = {}
     for key, val in _KV.findall(line):

@@ -370,8 +370,8 @@ class BatchUniversalTransformer(UniversalTransformer):
     dataset: `get_batch_features` refuses a batch larger than `batch_size`, a structure that
     exceeds `max_occurs` and one with more than `nij_max` pairs (the reference fails late, in
     `scatter_nd` or in the VirtualAtomMap).  The TFRecord codec (`encode`, `decode_protobuf`,
-    universal.py:1205-1330) belongs to the input pipeline, which is out of scope
-    (DESIGN.md 7): both raise NotImplementedError."""
+    universal.py:1205-1330) writes and reads the reference's record layout through
+    transformer/tfrecord.py (no TensorFlow): the padded TRAIN-mode maps exist only there."""
 
     def __init__(self, max_occurs, rcut, acut=None, angular=False, periodic=True,
                  symmetric=True, nij_max=None, nijk_max=None, nnl_max=None, ij2k_max=None,
@@ -462,11 +462,195 @@ class BatchUniversalTransformer(UniversalTransformer):
                                  f"exceeds nij_max = {self._nij_max}")
         return feats
 
-    def encode(self, atoms):
-        raise NotImplementedError("TFRecord encoding belongs to the reference's input "
-                                  "pipeline (out of scope); pass ase-like Atoms objects to "
-                                  "get_batch_features / the trainers instead")
+    # -- TFRecord codec (universal.py:1177-1330, base.py:365-437) ---------------------
+    def get_dataset_vap(self, atoms) -> VirtualAtomMap:
+        """The map for the DATASET's `max_occurs` (the reference's batch-mode
+        `get_vap_transformer`, base.py:206-226), cached by the run-length encoding of the symbol
+        sequence.  (`get_vap_transformer` stays the per-structure map: evaluation results of
+        this package are never padded.)"""
+        key = ('batch', atoms.get_chemical_formula(mode='reduce'))
+        if key not in self._vap_transformers:
+            self._vap_transformers[key] = VirtualAtomMap(self._max_occurs,
+                                                         atoms.get_chemical_symbols())
+        return self._vap_transformers[key]
+
+    def _neighbor_list(self, atoms, rc):
+        """(i, j, S) of `atoms` within rc from the GPU list builder."""
+        import torch
+        saved = self._types_cache
+        feats = UniversalTransformer.get_device_features(self, atoms, rc=rc)
+        i, j, S = feats.nbr.export()
+        torch.cuda.synchronize()
+        self._types_cache = saved
+        return i.cpu().numpy(), j.cpu().numpy(), S.cpu().numpy()
+
+    def get_metadata(self, atoms, vap=None, neighbor_list=None):
+        """TRAIN-mode metadata of one structure (universal.py:1050-1086): the maps carry a
+        leading batch-index column (6 columns; filled by the batching step) and every array is
+        padded with zero rows to `nij_max` / `nijk_max`.  `neighbor_list` = (i, j, S) within
+        max(rcut, acut) replaces the GPU list builder (CPU tests)."""
+        from tensoralloy_b200.transformer import wire_format as wf
+        np_dtype = get_float_dtype().as_numpy_dtype
+        vap = vap or self.get_dataset_vap(atoms)
+        rmax = max(self._rcut, self._acut) if (self._angular and self._acut) else self._rcut
+        i, j, S = neighbor_list if neighbor_list is not None else \
+            self._neighbor_list(atoms, rmax)
+        types = self._z_lut()[np.asarray(atoms.numbers)]
+        arr = wf.build_feed_arrays(i, j, S, np.asarray(atoms.positions, dtype=np.float64),
+                                   np.asarray(atoms.get_cell(complete=True), dtype=np.float64),
+                                   types, vap.local_to_gsl_array, self._elements,
+                                   self._kbody_terms_for_element, self._rcut, self._acut,
+                                   self._angular, self._symmetric)
+
+        def padded(a, n_max, what):
+            n = a.shape[0]
+            n_max = n if n_max is None else int(n_max)
+            if n > n_max:
+                raise ValueError(f"{what} = {n} exceeds {what}_max = {n_max}")
+            out = np.zeros((n_max,) + a.shape[1:], dtype=a.dtype)
+            out[:n] = a
+            return out
+
+        def train_map(v2g, n_max, what):
+            out = np.zeros((v2g.shape[0], 6), dtype=np.int32)
+            out[:, 1:] = v2g
+            return padded(out, n_max, what)
+
+        meta = {"g2.v2g_map": train_map(arr["g2.v2g_map"], self._nij_max, 'nij'),
+                "g2.ilist": padded(arr["g2.ilist"], self._nij_max, 'nij'),
+                "g2.jlist": padded(arr["g2.jlist"], self._nij_max, 'nij'),
+                "g2.n1": padded(arr["g2.n1"].astype(np_dtype), self._nij_max, 'nij')}
+        if self._angular:
+            meta["g4.v2g_map"] = train_map(arr["g4.v2g_map"], self._nijk_max, 'nijk')
+            for key in ("g4.ilist", "g4.jlist", "g4.klist"):
+                meta[key] = padded(arr[key], self._nijk_max, 'nijk')
+            for key in ("g4.n1", "g4.n2", "g4.n3"):
+                meta[key] = padded(arr[key].astype(np_dtype), self._nijk_max, 'nijk')
+        return meta
+
+    def encode(self, atoms, neighbor_list=None):
+        """One structure -> `Example` (tfrecord.py; `.SerializeToString()` is the record the
+        reference's `tf.train.Example` yields): universal.py:1219-1230 + base.py:383-437.
+        Labels come from `atoms.info` ('energy', 'forces', 'stress' in eV/A^3 Voigt,
+        'etemperature', 'eentropy'), missing ones count as zero (the reference attaches a
+        zero `SinglePointCalculator`)."""
+        from tensoralloy_b200.transformer.tfrecord import Example, bytes_feature, int64_feature
+        from tensoralloy_b200.io.units import _UNITS
+        GPa = _UNITS['GPa']
+        np_dtype = get_float_dtype().as_numpy_dtype
+        vap = self.get_dataset_vap(atoms)
+        info = getattr(atoms, 'info', {})
+        n = len(atoms)
+
+        def raw(a):
+            return bytes_feature(np.ascontiguousarray(a, dtype=np_dtype).tobytes())
+
+        energy = np.atleast_1d(float(info.get('energy', 0.0))).astype(np_dtype)
+        etemp = np.atleast_1d(float(info.get('etemperature', 0.0))).astype(np_dtype)
+        eentropy = np.atleast_1d(float(info.get('eentropy', 0.0))).astype(np_dtype)
+        feats = {
+            'positions': raw(vap.map_positions(np.asarray(atoms.positions))),
+            'cell': raw(atoms.get_cell(complete=True)),
+            'n_atoms_vap': int64_feature(n),
+            'volume': raw(np.atleast_1d(atoms.get_volume())),
+            'energy': raw(energy),
+            'free_energy': raw(energy - etemp * eentropy),
+            'atom_masks': raw(vap.atom_masks),
+            'eentropy': raw(eentropy),
+            'etemperature': raw(etemp),
+        }
+        if self._use_forces:
+            forces = np.asarray(info.get('forces', np.zeros((n, 3))), dtype=np.float64)
+            feats['forces'] = raw(vap.map_forces(forces.reshape(n, 3)))
+        if self._use_stress:
+            stress = np.asarray(info.get('stress', np.zeros(6)), dtype=np.float64).reshape(6)
+            stress = stress.astype(np_dtype)
+            feats['stress'] = raw(stress)
+            feats['total_pressure'] = raw(np.atleast_1d(-stress[:3].mean() / GPa))
+        meta = self.get_metadata(atoms, vap=vap, neighbor_list=neighbor_list)
+        g2 = np.concatenate((meta["g2.v2g_map"], meta["g2.ilist"][:, None],
+                             meta["g2.jlist"][:, None]), axis=1).astype(np.int32)
+        feats['g2.indices'] = bytes_feature(g2.tobytes())
+        feats['g2.shifts'] = bytes_feature(meta["g2.n1"].tobytes())
+        if self._angular:
+            g4 = np.concatenate((meta["g4.v2g_map"], meta["g4.ilist"][:, None],
+                                 meta["g4.jlist"][:, None], meta["g4.klist"][:, None]),
+                                axis=1).astype(np.int32)
+            feats['g4.indices'] = bytes_feature(g4.tobytes())
+            feats['g4.shifts'] = bytes_feature(np.concatenate(
+                (meta["g4.n1"], meta["g4.n2"], meta["g4.n3"]), axis=1).tobytes())
+        return Example(feats)
 
     def decode_protobuf(self, example_proto):
-        raise NotImplementedError("TFRecord decoding belongs to the reference's input "
-                                  "pipeline (out of scope)")
+        """Serialised `Example` (bytes) -> the dict of arrays of universal.py:1232-1319 (numpy
+        instead of tf.Tensor).  The sizes are the transformer's (`max_n_atoms`, `nij_max`,
+        `nijk_max`): a record of another size raises, as `set_shape` does."""
+        from tensoralloy_b200.transformer.tfrecord import Example
+        if self._nij_max is None or (self._angular and self._nijk_max is None):
+            raise ValueError("decode_protobuf needs nij_max (and nijk_max for angular "
+                             "transformers)")
+        np_dtype = get_float_dtype().as_numpy_dtype
+        feats = Example.FromString(example_proto).features
+        n1 = self._max_n_atoms + 1
+
+        def raw(key, shape, dtype=np_dtype):
+            if key not in feats or feats[key].kind != 'bytes_list' or \
+                    len(feats[key].value) != 1:
+                raise KeyError(f"feature '{key}' is missing from the example")
+            a = np.frombuffer(feats[key].value[0], dtype=dtype)
+            if a.size != int(np.prod(shape, dtype=np.int64)):
+                raise ValueError(f"feature '{key}': {a.size} values, expected shape "
+                                 f"{tuple(shape)}")
+            return a.reshape(shape).copy()
+
+        out = {
+            'positions': raw('positions', (n1, 3)),
+            'n_atoms_vap': np.int64(feats['n_atoms_vap'].value[0]),
+            'energy': raw('energy', (1,))[0],
+            'cell': raw('cell', (3, 3)),
+            'volume': raw('volume', (1,))[0],
+            'atom_masks': raw('atom_masks', (n1,)),
+            'etemperature': raw('etemperature', (1,))[0],
+            'eentropy': raw('eentropy', (1,))[0],
+            'free_energy': raw('free_energy', (1,))[0],
+        }
+        if self._use_forces:
+            out['forces'] = raw('forces', (n1, 3))
+        if self._use_stress:
+            out['stress'] = raw('stress', (6,))
+            out['total_pressure'] = raw('total_pressure', (1,))[0]
+        g2 = raw('g2.indices', (self._nij_max, 8), np.int32)
+        out['g2.v2g_map'] = g2[:, :6]
+        out['g2.ilist'] = g2[:, 6]
+        out['g2.jlist'] = g2[:, 7]
+        out['g2.n1'] = raw('g2.shifts', (self._nij_max, 3))
+        if self._angular:
+            g4 = raw('g4.indices', (self._nijk_max, 9), np.int32)
+            out['g4.v2g_map'] = g4[:, :6]
+            out['g4.ilist'], out['g4.jlist'], out['g4.klist'] = g4[:, 6], g4[:, 7], g4[:, 8]
+            sh = raw('g4.shifts', (self._nijk_max, 9))
+            out['g4.n1'], out['g4.n2'], out['g4.n3'] = sh[:, 0:3], sh[:, 3:6], sh[:, 6:9]
+        return out
+
+    def decode_atoms(self, decoded):
+        """A decoded example back to a labelled `Atoms` (GSL order undone): what the trainers
+        of this package consume (`add_structure(atoms, energy, forces, stress)`).  The element
+        of every real atom follows from its GSL slot (row splits = `max_occurs` per element in
+        sorted order)."""
+        from tensoralloy_b200.atoms import Atoms
+        mask = decoded['atom_masks'] > 0
+        symbols_gsl = [None]
+        for e in self._elements:
+            symbols_gsl.extend([e] * self._max_occurs[e])
+        rows = np.flatnonzero(mask)
+        info = {'energy': float(decoded['energy']),
+                'etemperature': float(decoded['etemperature']),
+                'eentropy': float(decoded['eentropy'])}
+        if 'forces' in decoded:
+            info['forces'] = np.asarray(decoded['forces'], dtype=np.float64)[rows]
+        if 'stress' in decoded:
+            info['stress'] = np.asarray(decoded['stress'], dtype=np.float64)
+        cell = np.asarray(decoded['cell'], dtype=np.float64)
+        return Atoms([symbols_gsl[r] for r in rows],
+                     np.asarray(decoded['positions'], dtype=np.float64)[rows], cell,
+                     pbc=self._periodic and abs(np.linalg.det(cell)) > 1e-12, info=info)

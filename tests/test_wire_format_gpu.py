@@ -38,3 +38,23 @@ def test_get_np_feed_dict_bit_exact(name, angular, acut):
     # positions in GSL order with the virtual atom in row 0 (vap.py:26-56)
     assert np.array_equal(feed["positions"][0], np.zeros(3))
     assert feed["positions"].shape[0] == feed["n_atoms_vap"]
+
+
+@pytest.mark.parametrize('angular', [False, True])
+def test_tfrecord_example_from_gpu_list(angular):
+    """`BatchUniversalTransformer.encode` with the GPU list builder writes the same record,
+    byte for byte, as with the oracle's neighbour list (universal.py:1219-1230)."""
+    from tensoralloy_b200.transformer import BatchUniversalTransformer
+    atoms, _ = _cases()['moni']
+    atoms.info.update(energy=-3.25, forces=np.full((len(atoms), 3), 0.125))
+    rc = 4.0
+    nl = onl.neighbor_list(atoms.positions, atoms.cell, atoms.pbc, rc)[:3]
+    clf = BatchUniversalTransformer({'Mo': 20, 'Ni': 30}, rcut=rc, angular=angular,
+                                    nij_max=len(nl[0]) + 7,
+                                    nijk_max=60000 if angular else None)
+    with precision_scope('high'):
+        a = clf.encode(atoms).SerializeToString()
+        b = clf.encode(atoms, neighbor_list=nl).SerializeToString()
+        assert a == b
+        dec = clf.decode_protobuf(a)
+    assert dec['energy'] == -3.25 and int(dec['g2.v2g_map'][:, 5].sum()) == len(nl[0])

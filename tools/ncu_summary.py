@@ -45,7 +45,9 @@ if len(sys.argv) > 3:
                      "dram__bytes_read.sum + dram__bytes_write.sum"}
     for r in data:
         nm = r[name_col]
-        key = 'k_eam_force<double,zhou1>' if 'k_eam_force<double' in nm else \
-            'k_eam_rho<double,zhou1>' if 'k_eam_rho<double' in nm else nm.split('(')[0]
+        base = nm.split('(')[0].split('<')[0]
+        key = {'k_eamz_force': 'k_eamz_force<f64>', 'k_eamz_rho': 'k_eamz_rho<f64>'}.get(base, base)
+        if key in out:          # several launches of one kernel: keep the first
+            continue
         out[key] = int(to_bytes(r[cr], units[cr]) + to_bytes(r[cw], units[cw]))
     json.dump(out, open(sys.argv[3], 'w'), indent=1)
