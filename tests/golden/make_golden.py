@@ -102,7 +102,40 @@ def copy_text_fixtures():
             fp.write(ET.tostring(root))
 
 
+def copy_databases():
+    """ASE SQLite databases of the reference (tests/test_neighbor.py:20-36 reads qm7m.db;
+    snap-Ni.db's metadata record holds the neighbour maxima the reference computed for it).
+    qm7m.db whole (3 structures); of snap-Ni.db the structures that attain the recorded maxima
+    (ids 99, 264, 266, 290: found with the oracle's list over all 461 structures, every recorded
+    maximum reproduced) plus three more, re-written with this package's writer, metadata kept."""
+    import os
+    import sys
+    sys.path.insert(0, str(OUT.parents[1]))
+    from tensoralloy_b200.io.sqlite import CoreDatabase
+    shutil.copy(REF / 'datasets' / 'qm7m' / 'qm7m.db', OUT / 'qm7m.db')
+    os.chmod(OUT / 'qm7m.db', 0o644)
+    tmp = OUT / '_snap_full.db'
+    shutil.copy(REF.parent / 'tensoralloy' / 'data' / 'datasets' / 'snap-Ni.db', tmp)
+    os.chmod(tmp, 0o644)
+    full = CoreDatabase(tmp)
+    sub_path = OUT / 'snap_Ni_subset.db'
+    if sub_path.exists():
+        sub_path.unlink()
+    sub = CoreDatabase(sub_path)
+    ids = [1, 11, 99, 150, 264, 266, 290]
+    for k in ids:
+        a = full.get_atoms(id=k, add_additional_information=True)
+        sub.write(a, key_value_pairs=a.info.get('key_value_pairs'), data=a.info.get('data'))
+    md = full.metadata
+    md['subset_of'] = {'file': 'tensoralloy/data/datasets/snap-Ni.db', 'ids': ids}
+    sub.metadata = md
+    sub.close()
+    full.close()
+    tmp.unlink()
+
+
 def main():
+    copy_databases()
     for name in ('zjw04_Ni.alloy.eam', 'Zhou_AlCu.alloy.eam'):
         d = read_setfl(REF / 'lammps' / name)
         np.savez_compressed(OUT / (name.replace('.alloy.eam', '') + '_setfl.npz'), **d)
