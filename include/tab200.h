@@ -455,6 +455,35 @@ int tab_profile_read(double *ms, int32_t *calls);
 int64_t tab_launch_count(void);
 void    tab_launch_count_reset(void);
 
+/* Temperature-dependent heads of the finite-temperature AtomicNN in one kernel
+ * (replaces the three 1x1-convolution chains and the tf.gradients call of
+ * nn/atomic/finite_temperature.py:92-304; entropy models: 'default', 'Sommerfeld' :120-166,
+ * and the beryllium free-electron form nn/atomic/special/beryllium.py:23-77).
+ * Per element e: H[e] maps the descriptors (sizes[0] = dim; xlo / xhi of H[e] = min-max map)
+ * to nH values through a linear last layer; S[e] and U[e] map [H, T] (nH + 1 values) to one
+ * value.  Layer conventions as tab_mlp_desc (biases[n_layers - 1] + output_bias = bias of the
+ * last layer).  algo: 0 default (S = s), 1 Sommerfeld (S = s T); special: 0 none, 1 Be. */
+typedef struct tab_td tab_td;
+typedef struct tab_td_desc {
+    int32_t n_elements;
+    int32_t dim;
+    int32_t algo;
+    int32_t special;
+    const tab_mlp_desc *H, *S, *U;        /* [n_elements] each */
+} tab_td_desc;
+
+int tab_td_create(tab_td **out, const tab_td_desc *desc);
+int tab_td_free(tab_td *td);
+
+/* d_types int32 [n] (element index), d_G [n, dim] descriptors (tab_atomic_descriptors),
+ * d_T [n] electron temperature of every atom (eV).  Outputs, float64 on the device, caller
+ * atom order: d_U, d_S, d_F [n] (internal energy, electron entropy, free energy F = U - T S
+ * per atom) and d_dFdG [n, dim] -- the input of tab_atomic_forces, which yields the forces and
+ * the virial of the FREE energy (basic.py:190-202). */
+int tab_td_eval(tab_td *td, int32_t n, const int32_t *d_types, const double *d_G,
+                const double *d_T, int32_t precision, double *d_U, double *d_S, double *d_F,
+                double *d_dFdG, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -87,6 +87,12 @@ class TabMlpDesc(C.Structure):
                 ('xlo', _DP), ('xhi', _DP)]
 
 
+class TabTdDesc(C.Structure):
+    _fields_ = [('n_elements', C.c_int32), ('dim', C.c_int32), ('algo', C.c_int32),
+                ('special', C.c_int32), ('H', C.POINTER(TabMlpDesc)),
+                ('S', C.POINTER(TabMlpDesc)), ('U', C.POINTER(TabMlpDesc))]
+
+
 class TabError(RuntimeError):
     """A libtab200 call returned a non-zero status."""
 
@@ -108,7 +114,7 @@ EXPORTS = [
     'tab_pairs_export', 'tab_pair_forces', 'tab_pair_jvp', 'tab_atomic_eval_dd', 'tab_eam_eval_dd', 'tab_eam_tabulate',
     'tab_profile_enable', 'tab_profile_read',
     'tab_nbr_set_skin', 'tab_nbr_max_displacement', 'tab_nbr_displacement_device',
-    'tab_reduce_slots', 'tab_eam_elastic',
+    'tab_reduce_slots', 'tab_eam_elastic', 'tab_td_create', 'tab_td_free', 'tab_td_eval',
 ]
 
 
@@ -175,6 +181,9 @@ def lib():
     L.tab_eam_tabulate.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp]
     L.tab_atomic_forces.argtypes = [vp, vp, i32, vp, vp, vp, vp]
     L.tab_atomic_jvp.argtypes = [vp, vp, i32, vp, vp, vp, vp]
+    L.tab_td_create.argtypes = [pp, C.POINTER(TabTdDesc)]
+    L.tab_td_free.argtypes = [vp]
+    L.tab_td_eval.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp]
     L.tab_profile_enable.argtypes = [i32]
     L.tab_profile_read.argtypes = [C.POINTER(dbl), C.POINTER(i32)]
     L.tab_launch_count.restype = i64
@@ -512,6 +521,83 @@ def profile_read():
     calls = C.c_int32()
     check(lib().tab_profile_read(ms, C.byref(calls)), 'tab_profile_read')
     return list(ms), int(calls.value)
+
+
+def _fill_mlp_desc(d, m, keep):
+    """One network -> TabMlpDesc.  m: dict(weights=[np [in, out] ...], biases=[np or None ...],
+    activation, use_resnet_dt, output_bias, xlo, xhi); `keep` collects the arrays whose
+    memory the descriptor points to."""
+    def darr(vals):
+        a = np.ascontiguousarray(np.asarray(vals, dtype=np.float64).reshape(-1))
+        keep.append(a)
+        return a.ctypes.data_as(_DP)
+
+    W = m['weights']
+    if len(W) > 8:
+        raise ValueError("at most 8 layers (hidden + output) are supported")
+    d.n_layers = len(W)
+    for k, w in enumerate(W):
+        w = np.asarray(w, dtype=np.float64)
+        d.sizes[k] = w.shape[0]
+        d.sizes[k + 1] = w.shape[1]
+        d.weights[k] = darr(w)
+        b = m['biases'][k] if k < len(m['biases']) else None
+        d.biases[k] = darr(b) if b is not None else None
+    d.activation = ACTIVATIONS[m.get('activation', 'softplus').lower()]
+    d.use_resnet_dt = int(bool(m.get('use_resnet_dt', False)))
+    d.output_bias = int(bool(m.get('output_bias', False)))
+    if m.get('xlo') is not None and m.get('xhi') is not None:
+        d.xlo = darr(m['xlo'])
+        d.xhi = darr(m['xhi'])
+
+
+class TdHeads:
+    """Owner of one `tab_td` handle: the H / S / U networks of the finite-temperature model
+    (`tab_td_eval`: U, S, F per atom and dF/dG in one kernel).
+
+    heads : per element (sorted order) dict(H=..., S=..., U=...) of network dicts as
+            `_fill_mlp_desc` takes them (H carries xlo / xhi)
+    algo  : 'default' | 'Sommerfeld';  special : None | 'Be'
+    """
+
+    def __init__(self, dim, heads, algo='default', special=None):
+        self._keep = []
+        n_el = len(heads)
+        self._H = (TabMlpDesc * n_el)()
+        self._S = (TabMlpDesc * n_el)()
+        self._U = (TabMlpDesc * n_el)()
+        for e, h in enumerate(heads):
+            _fill_mlp_desc(self._H[e], h['H'], self._keep)
+            _fill_mlp_desc(self._S[e], h['S'], self._keep)
+            _fill_mlp_desc(self._U[e], h['U'], self._keep)
+        d = TabTdDesc()
+        d.n_elements, d.dim = n_el, int(dim)
+        d.algo = {'default': 0, 'sommerfeld': 1}[str(algo).lower()]
+        d.special = {None: 0, 'Be': 1}[special]
+        d.H, d.S, d.U = self._H, self._S, self._U
+        self.dim = int(dim)
+        self._h = C.c_void_p()
+        check(lib().tab_td_create(C.byref(self._h), C.byref(d)), 'tab_td_create')
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().tab_td_free(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    def eval(self, types, G, T, precision=PRECISION_HIGH):
+        """types int32 [n], G float64 [n, dim], T float64 [n] (cuda) ->
+        (U, S, F [n], dFdG [n, dim]) float64 cuda tensors."""
+        import torch
+        n = int(types.shape[0])
+        out = torch.empty((3, n), dtype=torch.float64, device='cuda')
+        dfdg = torch.empty((n, self.dim), dtype=torch.float64, device='cuda')
+        check(lib().tab_td_eval(self._h, n, _ptr(types), _ptr(G), _ptr(T), int(precision),
+                                _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(dfdg),
+                                _stream()), 'tab_td_eval')
+        return out[0], out[1], out[2], dfdg
 
 
 class AtomicModel:

@@ -35,12 +35,12 @@
 
 #include "tab_internal.h"
 
-#define B TAB_TILE_B
 
 // ---------------------------------------------------------------------------
 // cell indexing
 // ---------------------------------------------------------------------------
 __host__ __device__ inline int owned_rank(const Grid &g, int cx, int cy, int cz) {
+    const int B = g.tb;
     const int tx = cx / B, ty = cy / B, tz = cz / B;
     const int lx = cx % B, ly = cy % B, lz = cz % B;
     return ((tz * g.tl[1] + ty) * g.tl[0] + tx) * (B * B * B) + (lz * B + ly) * B + lx;
@@ -48,6 +48,7 @@ __host__ __device__ inline int owned_rank(const Grid &g, int cx, int cy, int cz)
 
 __host__ __device__ inline void owned_unrank(const Grid &g, int rank, int &cx,
                                              int &cy, int &cz) {
+    const int B = g.tb;
     const int local = rank % (B * B * B);
     int t = rank / (B * B * B);
     const int tx = t % g.tl[0];
@@ -249,8 +250,10 @@ __global__ void k_fill_ghosts(Grid g, int n_loc,
                               int *__restrict__ ghost_owner,
                               int *__restrict__ ghost_S, int refresh_only, QFrame qf,
                               Rec16 *__restrict__ rec16) {
-    const int lin = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
+    // 32 lanes per cell of full width, 8 per half-width cell (~4 atoms)
+    const int lpc = g.tb == 4 ? 8 : 32;
+    const int lin = (blockIdx.x * blockDim.x + threadIdx.x) / lpc;
+    const int lane = threadIdx.x & (lpc - 1);
     if (lin >= g.n_ecells) return;
     const uint32_t cnt = gcount[lin];
     if (cnt == 0) return;
@@ -279,7 +282,7 @@ __global__ void k_fill_ghosts(Grid g, int n_loc,
     const double sy = S[0] * g.h[1] + S[1] * g.h[4] + S[2] * g.h[7];
     const double sz = S[0] * g.h[2] + S[1] * g.h[5] + S[2] * g.h[8];
     const int packed = tab_pack_shift(S[0], S[1], S[2]);
-    for (uint32_t k = lane; k < cnt; k += 32) {
+    for (uint32_t k = lane; k < cnt; k += lpc) {
         const uint32_t src = k < cnt_a ? src_a + k : src_b + (k - cnt_a);
         Atom4 a = atoms[src];
         a.x += sx;
@@ -293,6 +296,24 @@ __global__ void k_fill_ghosts(Grid g, int n_loc,
             ghost_S[dst + k - n_loc] = packed;
         }
     }
+}
+
+// per-step refresh of the ghost records: one thread per ghost atom (source index and image
+// shift were stored by k_fill_ghosts at build time)
+__global__ void k_refresh_ghosts(int n_ghost, int n_loc, Grid g,
+                                 const int *__restrict__ ghost_owner,
+                                 const int *__restrict__ ghost_S, Atom4 *__restrict__ atoms,
+                                 QFrame qf, Rec16 *__restrict__ rec16) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_ghost) return;
+    int S[3];
+    tab_unpack_shift(ghost_S[k], S[0], S[1], S[2]);
+    Atom4 a = atoms[ghost_owner[k]];
+    a.x += S[0] * g.h[0] + S[1] * g.h[3] + S[2] * g.h[6];
+    a.y += S[0] * g.h[1] + S[1] * g.h[4] + S[2] * g.h[7];
+    a.z += S[0] * g.h[2] + S[1] * g.h[5] + S[2] * g.h[8];
+    atoms[n_loc + k] = a;
+    if (rec16) rec16[n_loc + k] = make_rec16(qf, a.x, a.y, a.z);
 }
 
 struct ExactCtx {
@@ -630,19 +651,18 @@ k_nbr_tile(int n, Grid g, ExactCtx x, const Atom4 *__restrict__ atoms,
            int *__restrict__ counts, uint32_t *__restrict__ rows) {
     __shared__ float4 cand[NBT_CAP];        // x, y, z relative to the box centre; entry bits
     __shared__ uint4 cell_tab[NBT_CELLS];   // {start_a, count_a, start_b, count_b}
-    __shared__ int cell_pc[NBT_CELLS];      // packed box coordinates of the cell
     __shared__ int cell_off[NBT_CELLS + 1]; // candidate offset of the cell in the batch
     __shared__ int warp_tot[NBT_THREADS / 32];
-    __shared__ uint32_t tile_start[B * B * B + 1];
+    __shared__ uint32_t tile_start[TAB_TILE_B_MAX * TAB_TILE_B_MAX * TAB_TILE_B_MAX + 1];
 
+    const int B = g.tb, B3 = B * B * B;
     const int tile = blockIdx.x;
     const int tid = threadIdx.x;
-    if (tid < B * B * B) tile_start[tid] = cell_start[tile * (B * B * B) + tid];
-    if (tid == B * B * B - 1)
-        tile_start[B * B * B] = cell_start[tile * (B * B * B) + tid] +
-                                cell_count[tile * (B * B * B) + tid];
+    if (tid < B3) tile_start[tid] = cell_start[tile * B3 + tid];
+    if (tid == B3 - 1)
+        tile_start[B3] = cell_start[tile * B3 + tid] + cell_count[tile * B3 + tid];
     __syncthreads();
-    const int a0 = (int)tile_start[0], a1 = (int)tile_start[B * B * B];
+    const int a0 = (int)tile_start[0], a1 = (int)tile_start[B3];
     if (a1 <= a0) return;
 
     int t3[3];
@@ -680,9 +700,11 @@ k_nbr_tile(int n, Grid g, ExactCtx x, const Atom4 *__restrict__ atoms,
         uint32_t e_self = 0;
         if (active) {
             e_self = (uint32_t)idx | ((uint32_t)types_ext[idx] << TAB_COL_TYPE_SHIFT);
-            int l = -1;
-#pragma unroll
-            for (int q = 0; q < B * B * B; ++q) l += tile_start[q] <= (uint32_t)idx ? 1 : 0;
+            // my cell of the tile: the last one that starts at or before idx (empty cells
+            // share their start with the next one)
+            int l = 0;
+            for (int step = B3 >> 1; step > 0; step >>= 1)
+                l += tile_start[l + step] <= (uint32_t)idx ? step : 0;
             mx = t3[0] * B + l % B - b0[0];
             my = t3[1] * B + (l / B) % B - b0[1];
             mz = t3[2] * B + l / (B * B) - b0[2];
@@ -706,7 +728,6 @@ k_nbr_tile(int n, Grid g, ExactCtx x, const Atom4 *__restrict__ atoms,
                 const uint4 t = ext_tab[((b0[2] + qz + g.g[2]) * g.ne[1] + (b0[1] + qy + g.g[1])) *
                                             g.ne[0] + (b0[0] + qx + g.g[0])];
                 cell_tab[tid] = t;
-                cell_pc[tid] = qx | (qy << 8) | (qz << 16);
                 mine = (int)(t.y + t.w);
             }
             int incl = mine;
@@ -720,7 +741,7 @@ k_nbr_tile(int n, Grid g, ExactCtx x, const Atom4 *__restrict__ atoms,
             int wbase = 0;
 #pragma unroll
             for (int w = 0; w < NBT_THREADS / 32; ++w) wbase += w < (tid >> 5) ? warp_tot[w] : 0;
-            cell_off[tid] = wbase + incl - mine;
+            cell_off[tid] = wbase + incl - mine;      // (= the total for tid >= batch_cells)
             if (tid == NBT_THREADS - 1) cell_off[NBT_CELLS] = wbase + incl;
             __syncthreads();
             const int total = cell_off[NBT_CELLS];
@@ -745,20 +766,28 @@ k_nbr_tile(int n, Grid g, ExactCtx x, const Atom4 *__restrict__ atoms,
                 }
                 __syncthreads();
                 if (active) {
-                    for (int c = 0; c < batch_cells; ++c) {
-                        const int pc = cell_pc[c];
-                        const int ddx = (pc & 255) - mx, ddy = ((pc >> 8) & 255) - my,
-                                  ddz = (pc >> 16) - mz;
-                        if (abs(ddx) > sr0 || abs(ddy) > sr1 || abs(ddz) > sr2) continue;
-                        const int kbeg = max(cell_off[c], w0) - w0;
-                        const int kend = min(cell_off[c + 1], w1) - w0;
-                        const uint32_t kk0 = kk;
-                        // fast path needs room for the whole segment (rows have slack)
-                        if (kk + (uint32_t)(kend - kbeg) > wcap ||
-                            nbt_scan(kbeg, kend, cand, fx, fy, fz, thr_hi, thr_lo, e_self, base,
-                                     kk)) {
-                            kk = kk0;
-                            nbt_scan_exact(kbeg, kend, cand, atoms, idx, wcap, base, kk, g, x);
+                    // the neighbourhood row by row: for fixed (z, y) the cells x - sr .. x + sr
+                    // are consecutive box cells, i.e. ONE contiguous run of staged candidates
+                    // (clipped to this batch of cells and this window of candidates).  Rows in
+                    // ascending (z, y): the candidate order of for_each_neighbor().
+                    const int x_lo = max(mx - sr0, 0), x_hi = min(mx + sr0, bn[0] - 1);
+                    for (int qz = max(mz - sr2, 0); qz <= min(mz + sr2, bn[2] - 1); ++qz) {
+                        for (int qy = max(my - sr1, 0); qy <= min(my + sr1, bn[1] - 1); ++qy) {
+                            const int q = (qz * bn[1] + qy) * bn[0];
+                            const int c0 = max(q + x_lo - batch, 0);
+                            const int c1 = min(q + x_hi + 1 - batch, batch_cells);
+                            if (c1 <= c0) continue;
+                            const int kbeg = max(cell_off[c0], w0) - w0;
+                            const int kend = min(cell_off[c1], w1) - w0;
+                            if (kend <= kbeg) continue;
+                            const uint32_t kk0 = kk;
+                            // fast path needs room for the whole run (rows have slack)
+                            if (kk + (uint32_t)(kend - kbeg) > wcap ||
+                                nbt_scan(kbeg, kend, cand, fx, fy, fz, thr_hi, thr_lo, e_self,
+                                         base, kk)) {
+                                kk = kk0;
+                                nbt_scan_exact(kbeg, kend, cand, atoms, idx, wcap, base, kk, g, x);
+                            }
                         }
                     }
                 }
@@ -983,8 +1012,13 @@ static void invert3(const double *h, double *inv, double *det_out) {
     *det_out = det;
 }
 
+// `subdiv` = 1: cells at least rc wide, 27-cell neighbourhoods, tiles of 2 x 2 x 2 cells;
+// `subdiv` = 2: cells at least rc / 2 wide, 125-cell neighbourhoods (15.6 rc^3 of candidates
+// instead of 27 rc^3), tiles of 4 x 4 x 4 cells -- the same tile volume
 static int setup_grid(Grid &g, int n, const double *h_cell, const double *h_origin,
-                      const int *h_pbc, double rc) {
+                      const int *h_pbc, double rc, int subdiv) {
+    g.tb = subdiv == 2 ? 4 : 2;
+    const int B = g.tb;
     memcpy(g.h, h_cell, 9 * sizeof(double));
     for (int k = 0; k < 3; ++k) g.origin[k] = h_origin ? h_origin[k] : 0.0;
     double det;
@@ -1005,7 +1039,7 @@ static int setup_grid(Grid &g, int n, const double *h_cell, const double *h_orig
                                 g.hinv[6 + k] * g.hinv[6 + k]);
         fd[k] = 1.0 / nrm;
         g.pbc[k] = h_pbc[k] ? 1 : 0;
-        int nb = (int)floor(fd[k] / rpad);
+        int nb = (int)floor(fd[k] * subdiv / rpad);
         if (nb < 1) nb = 1;
         g.nb[k] = nb;
         cells *= nb;
@@ -1173,12 +1207,9 @@ static int refresh_positions(tab_nbr *nbr, const double *d_pos, cudaStream_t st)
     }
     TAB_LAUNCH_CHECK();
     if (nbr->n_ghost > 0) {
-        k_fill_ghosts<<<nblocks((long long)g.n_ecells * 32, 256), 256, 0, st>>>(
-            g, nbr->n_loc, nbr->cell_start.as<uint32_t>(), nbr->cell_count.as<uint32_t>(),
-            nbr->gstart.as<uint32_t>(), nbr->gcount.as<uint32_t>(),
-            nbr->ext_tab.as<uint4>(), nbr->atoms.as<Atom4>(),
-            nbr->types_ext.as<uint8_t>(), nbr->ghost_owner.as<int>(),
-            nbr->ghost_S.as<int>(), 1, qf, rec);
+        k_refresh_ghosts<<<nblocks(nbr->n_ghost, 256), 256, 0, st>>>(
+            nbr->n_ghost, nbr->n_loc, g, nbr->ghost_owner.as<int>(), nbr->ghost_S.as<int>(),
+            nbr->atoms.as<Atom4>(), qf, rec);
         TAB_LAUNCH_CHECK();
     }
     return TAB_OK;
@@ -1211,7 +1242,10 @@ extern "C" int tab_nbr_build_dd(tab_nbr *nbr, int32_t n_owned, int32_t n_halo,
     rc += nbr->skin;
     Grid &g = nbr->grid;
     const int n = n_owned, n_loc = (int)n_loc_ll;
-    TAB_TRY(setup_grid(g, n_loc, h_cell, h_origin, h_pbc, rc));
+    // large systems (the tile kernel): half-width cells.  TAB_NBR_SUBDIV=1|2 overrides (A/B)
+    int subdiv = n_loc > 20000 ? 2 : 1;
+    if (const char *env = getenv("TAB_NBR_SUBDIV")) subdiv = atoi(env) == 2 ? 2 : 1;
+    TAB_TRY(setup_grid(g, n_loc, h_cell, h_origin, h_pbc, rc, subdiv));
     nbr->n = n;
     nbr->n_halo = n_halo;
     nbr->n_loc = n_loc;
@@ -1304,7 +1338,7 @@ extern "C" int tab_nbr_build_dd(tab_nbr *nbr, int32_t n_owned, int32_t n_halo,
         nbr->skin_built > 0.0 ? nbr->pos_ref.as<double>() : nullptr, nullptr, qf, rec);
     TAB_LAUNCH_CHECK();
     if (nbr->n_ghost > 0) {
-        k_fill_ghosts<<<nblocks((long long)g.n_ecells * 32, 256), 256, 0, st>>>(
+        k_fill_ghosts<<<nblocks((long long)g.n_ecells * (g.tb == 4 ? 8 : 32), 256), 256, 0, st>>>(
             g, n_loc, nbr->cell_start.as<uint32_t>(), nbr->cell_count.as<uint32_t>(),
             nbr->gstart.as<uint32_t>(), nbr->gcount.as<uint32_t>(),
             nbr->ext_tab.as<uint4>(), nbr->atoms.as<Atom4>(),
@@ -1337,7 +1371,7 @@ extern "C" int tab_nbr_build_dd(tab_nbr *nbr, int32_t n_owned, int32_t n_halo,
         for (int k = 0; k < 3; ++k) {
             const double len = sqrt(g.h[3 * k] * g.h[3 * k] + g.h[3 * k + 1] * g.h[3 * k + 1] +
                                     g.h[3 * k + 2] * g.h[3 * k + 2]);
-            R += 0.5 * len * (double)(B + 2 * g.sr[k] + 2) / (double)g.nb[k];
+            R += 0.5 * len * (double)(g.tb + 2 * g.sr[k] + 2) / (double)g.nb[k];
         }
         const double eps = 5.97e-8;
         const double bw = 2.0 * (2.0 * 1.7321 * rc * (2.0 * R + rc) * eps + 4.0 * g.rc2 * eps);
@@ -1349,7 +1383,7 @@ extern "C" int tab_nbr_build_dd(tab_nbr *nbr, int32_t n_owned, int32_t n_halo,
         warp_mode = !strcmp(env, "warp");
         tile_mode = !strcmp(env, "tile") && tile_ok;
     }
-    const int n_tiles = g.n_slots / (B * B * B);
+    const int n_tiles = g.n_slots / (g.tb * g.tb * g.tb);
     TAB_TRY(nbr->tcounts.ensure(sizeof(int) * (size_t)n * nbr->n_types));
     unsigned long long h_stats[3];
 

@@ -19,8 +19,10 @@ TD/<El>/{H,S,U}/Output/{kernel,bias}, TD/<El>/{xlo,xhi}.
 
 Device path: descriptors G and the force / virial assembly F = J(R)^T dF/dG are the
 libtab200 kernels (tab_atomic_descriptors, tab_atomic_forces: k_sf_forward,
-k_sf_backward, k_sf_collect); the three small heads between them run as float64 /
-float32 GEMMs on the same device through torch (cuBLAS) with autograd providing dF/dG.
+k_sf_backward, k_sf_collect); the three heads, the entropy model and dF/dG between them are
+ONE kernel (tab_td_eval, csrc/td_heads.cu: tiles of 8 atoms, activations in shared memory).
+The torch formulation of the heads (`_net`, `_entropy`) remains for the training step
+(`TemperatureDependentTrainer`: autograd over the parameters).
 There is no CPU path: `_lib` raises without libtab200.so and the tensors live on cuda.
 """
 from typing import List
@@ -120,6 +122,7 @@ class TemperatureDependentAtomicNN(AtomicNN):
     def set_variable(self, name, value):
         super().set_variable(name, value)
         self._torch_params = None
+        self._td_heads = None
 
     def head_params(self, el, head):
         """One head's layers as plain arrays (what the oracle consumes)."""
@@ -205,42 +208,49 @@ class TemperatureDependentAtomicNN(AtomicNN):
             S = S * T
         return S
 
+    def _device_heads(self):
+        """The three networks of every element as one `tab_td` handle (csrc/td_heads.cu)."""
+        from tensoralloy_b200 import _lib
+        if getattr(self, '_td_heads', None) is not None:
+            return self._td_heads
+        heads = []
+        for el in self._elements:
+            nets = {}
+            for h in ('H', 'S', 'U'):
+                p = self.head_params(el, h)
+                biases = list(p['biases'])
+                biases[-1] = p['out_bias']
+                nets[h] = dict(weights=p['weights'], biases=biases, activation=p['activation'],
+                               use_resnet_dt=p['use_resnet_dt'],
+                               output_bias=p['out_bias'] is not None)
+            mm = self.minmax(el)
+            if mm:
+                nets['H']['xlo'], nets['H']['xhi'] = mm
+            heads.append(nets)
+        self._td_heads = _lib.TdHeads(self._dim(), heads, self._finite_temperature.algo,
+                                      self.special)
+        return self._td_heads
+
     def _run(self, nbr, types, t_atom, sid, nb, want_grad):
         """Shared core of the single-structure and the batched evaluation.  t_atom: per-atom
         electron temperature (cuda); sid: structure of each atom or None.  Returns per-atom
-        U, S, F (float64 numpy), per-structure sums, and forces / virials [nb, 9]."""
+        U, S, F (float64 numpy), per-structure sums, and forces / virials [nb, 9].
+        Descriptors (`tab_atomic_descriptors`) -> heads, entropy model and dF/dG
+        (`tab_td_eval`) -> forces and virial of the free energy (`tab_atomic_forces`)."""
         import torch
         dt = get_float_dtype()
-        tdtype = torch.float64 if dt.name == 'float64' else torch.float32
         model = self._device_model()
         n = int(types.shape[0])
-        G = model.descriptors(nbr, dt.tab_precision).to(tdtype).requires_grad_(True)
-        heads_all = self._torch_heads(tdtype)
-        t_atom = t_atom.to(tdtype)
-        U = torch.zeros(n, dtype=tdtype, device='cuda')
-        S = torch.zeros(n, dtype=tdtype, device='cuda')
-        for a, el in enumerate(self._elements):
-            sel = torch.nonzero(types == a).reshape(-1)
-            if not sel.numel():
-                continue
-            hd = heads_all[el]
-            x = G[sel]
-            if hd['xlo'] is not None:
-                den = hd['xhi'] - hd['xlo']
-                x = torch.where(den == 0, torch.zeros_like(x), (hd['xhi'] - x) / den)
-            H = self._net(hd['H'], x)
-            T = t_atom[sel]
-            Ht = torch.cat([H, T[:, None]], dim=1)
-            U = U.index_add(0, sel, self._net(hd['U'], Ht)[:, 0])
-            S = S.index_add(0, sel, self._entropy(hd, Ht, T))
-        F = U - t_atom * S
+        G = model.descriptors(nbr, dt.tab_precision)
+        U, S, F, dfdg = self._device_heads().eval(types.to(torch.int32).contiguous(), G,
+                                                  t_atom.to(torch.float64).contiguous(),
+                                                  dt.tab_precision)
         forces = virial = None
         if want_grad:
-            dedg = torch.autograd.grad(F.sum(), G)[0].to(torch.float64).contiguous()
             forces = torch.empty((n, 3), dtype=torch.float64, device='cuda')
             virial = torch.empty(nb * 9, dtype=torch.float64, device='cuda')
-            model.forces_from_dedg(nbr, dedg, forces, virial, dt.tab_precision)
-        per_atom = torch.stack([U.detach(), S.detach(), F.detach()]).to(torch.float64)
+            model.forces_from_dedg(nbr, dfdg, forces, virial, dt.tab_precision)
+        per_atom = torch.stack([U, S, F])
         if sid is None:
             sums = per_atom.sum(dim=1, keepdim=True)
         else:
