@@ -483,6 +483,9 @@ int tab_td_free(tab_td *td);
 int tab_td_eval(tab_td *td, int32_t n, const int32_t *d_types, const double *d_G,
                 const double *d_T, int32_t precision, double *d_U, double *d_S, double *d_F,
                 double *d_dFdG, void *stream);
+/* 0 = every weight transfer (TMA bulk copy) of the evaluations so far completed; 1 = one
+ * timed out and the outputs of that call hold NaN.  Synchronises the stream. */
+int tab_td_status(tab_td *td, int32_t *out, void *stream);
 
 #ifdef __cplusplus
 }

@@ -114,7 +114,7 @@ EXPORTS = [
     'tab_pairs_export', 'tab_pair_forces', 'tab_pair_jvp', 'tab_atomic_eval_dd', 'tab_eam_eval_dd', 'tab_eam_tabulate',
     'tab_profile_enable', 'tab_profile_read',
     'tab_nbr_set_skin', 'tab_nbr_max_displacement', 'tab_nbr_displacement_device',
-    'tab_reduce_slots', 'tab_eam_elastic', 'tab_td_create', 'tab_td_free', 'tab_td_eval',
+    'tab_reduce_slots', 'tab_eam_elastic', 'tab_td_create', 'tab_td_free', 'tab_td_eval', 'tab_td_status',
 ]
 
 
@@ -183,6 +183,7 @@ def lib():
     L.tab_atomic_jvp.argtypes = [vp, vp, i32, vp, vp, vp, vp]
     L.tab_td_create.argtypes = [pp, C.POINTER(TabTdDesc)]
     L.tab_td_free.argtypes = [vp]
+    L.tab_td_status.argtypes = [vp, C.POINTER(i32), vp]
     L.tab_td_eval.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp]
     L.tab_profile_enable.argtypes = [i32]
     L.tab_profile_read.argtypes = [C.POINTER(dbl), C.POINTER(i32)]
@@ -598,6 +599,12 @@ class TdHeads:
                                 _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(dfdg),
                                 _stream()), 'tab_td_eval')
         return out[0], out[1], out[2], dfdg
+
+    def status(self):
+        """0, or 1 when a weight transfer of an earlier `eval` timed out (outputs are NaN)."""
+        flag = C.c_int32(0)
+        check(lib().tab_td_status(self._h, C.byref(flag), _stream()), 'tab_td_status')
+        return int(flag.value)
 
 
 class AtomicModel:

@@ -251,6 +251,8 @@ class TemperatureDependentAtomicNN(AtomicNN):
             virial = torch.empty(nb * 9, dtype=torch.float64, device='cuda')
             model.forces_from_dedg(nbr, dfdg, forces, virial, dt.tab_precision)
         per_atom = torch.stack([U, S, F])
+        if self._device_heads().status():
+            raise RuntimeError("tab_td_eval: a weight transfer timed out on the device")
         if sid is None:
             sums = per_atom.sum(dim=1, keepdim=True)
         else:

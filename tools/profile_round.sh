@@ -20,6 +20,13 @@ ncu --set full --clock-control none --import-source on -k regex:'k_eamz' -s 6 -c
     > gpurun_out/${tag}_ncu_$prec.log 2>&1
 done
 python tools/build_breakdown.py 0.3 > gpurun_out/${tag}_build.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv \
+    --log-file gpurun_out/${tag}_build_launches.csv python tools/build_breakdown.py 0.3 > gpurun_out/${tag}_ncu_build_list.log 2>&1
+python tools/agg_launches.py gpurun_out/${tag}_build_launches.csv > gpurun_out/${tag}_build_launches_by_kernel.txt 2>&1
+python tools/build_breakdown.py 0.0 >> gpurun_out/${tag}_build.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv \
+    --log-file gpurun_out/${tag}_build_exact_launches.csv python tools/build_breakdown.py 0.0 > gpurun_out/${tag}_ncu_build_exact_list.log 2>&1
+python tools/agg_launches.py gpurun_out/${tag}_build_exact_launches.csv > gpurun_out/${tag}_build_exact_launches_by_kernel.txt 2>&1
 ncu --set full --clock-control none --import-source on -k regex:'k_nbr_tile' -s 4 -c 1 -f \
     -o gpurun_out/${tag}_nbr python tools/build_breakdown.py 0.3 > gpurun_out/${tag}_ncu_nbr.log 2>&1
 python tools/bench_configs.py > gpurun_out/${tag}_other_configs.jsonl 2> gpurun_out/${tag}_other_configs.err
