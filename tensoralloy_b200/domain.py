@@ -328,7 +328,7 @@ class PeerComm:
             self.mail_to_r[1:1 + n_r * c] = state[_where_static(code == 2, n_r)].reshape(-1)
         self.mail_hdl.barrier(channel=4)
         box = 1 + self.MIG_CAP * c
-        got = self.mail[[0, box]].tolist()                                      # read-back 2
+        got = torch.stack((self.mail[0], self.mail[box])).tolist()              # read-back 2
         a, b = int(got[0]), int(got[1])
         parts = [kept]
         if a:
@@ -432,8 +432,11 @@ class SlabRank:
         self.d_out = torch.zeros(16, **f64)
         self.d_f = torch.zeros((self.n_owned, 3), **f64)
         self.d_ea = None
-        self.h_out = torch.zeros(16, dtype=torch.float64).pin_memory() \
-            if device != 'cpu' else torch.zeros(16, dtype=torch.float64)
+        if getattr(self, 'h_out', None) is None:
+            # once per rank: pinning host memory synchronises the device and can take
+            # milliseconds (measured: a 10 ms outlier inside a rebuild)
+            self.h_out = torch.zeros(16, dtype=torch.float64).pin_memory() \
+                if device != 'cpu' else torch.zeros(16, dtype=torch.float64)
         self.h_f = None
         self.h_pos = None
 

@@ -45,7 +45,7 @@ if len(sys.argv) > 3:
                      "dram__bytes_read.sum + dram__bytes_write.sum"}
     for r in data:
         nm = r[name_col]
-        base = nm.split('(')[0].split('<')[0]
+        base = nm.split('(')[0].split('<')[0].replace('void ', '').strip()
         key = {'k_eamz_force': 'k_eamz_force<f64>', 'k_eamz_rho': 'k_eamz_rho<f64>'}.get(base, base)
         if key in out:          # several launches of one kernel: keep the first
             continue
