@@ -584,7 +584,8 @@ k_nbr_warp(int n, Grid g, ExactCtx x, const int *__restrict__ cell_of,
 //      wide, so re-scans touch ~0.1 % of the segments of a random structure.
 #define NBT_THREADS 256
 #define NBT_CAP 2048      // staged candidates per window (16 B each)
-#define NBT_CELLS 256     // box cells whose table entries are cached per batch
+#define NBT_CELLS 512     // box cells whose table entries are cached per batch (8^3 box)
+#define NBT_CPT (NBT_CELLS / NBT_THREADS)
 
 // Speculative scan of one cell segment: band candidates count as hits; returns
 // true when any candidate fell into the band (the caller then restores kk and
@@ -719,50 +720,71 @@ k_nbr_tile(int n, Grid g, ExactCtx x, const Atom4 *__restrict__ atoms,
         for (int batch = 0; batch < box_cells; batch += NBT_CELLS) {
             const int batch_cells = min(NBT_CELLS, box_cells - batch);
             __syncthreads();              // previous users of the tables / buffers are done
-            // every thread owns one box cell: table entry, packed coordinates, and an
-            // exclusive block scan of the candidate counts
-            int mine = 0;
-            if (tid < batch_cells) {
-                const int q = batch + tid;
-                const int qx = q % bn[0], qy = (q / bn[0]) % bn[1], qz = q / (bn[0] * bn[1]);
-                const uint4 t = ext_tab[((b0[2] + qz + g.g[2]) * g.ne[1] + (b0[1] + qy + g.g[1])) *
-                                            g.ne[0] + (b0[0] + qx + g.g[0])];
-                cell_tab[tid] = t;
-                mine = (int)(t.y + t.w);
-            }
-            int incl = mine;
+            // every thread owns NBT_CPT box cells (c = tid, tid + NBT_THREADS, ...): table entries
+            // (all loads issued before the first use), then an exclusive block scan of the
+            // candidate counts, one round per group of NBT_THREADS cells
+            uint4 tabs[NBT_CPT];
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, incl, d);
-                if ((tid & 31) >= d) incl += v;
+            for (int h = 0; h < NBT_CPT; ++h) {
+                const int c = h * NBT_THREADS + tid;
+                tabs[h] = make_uint4(0u, 0u, 0u, 0u);
+                if (c < batch_cells) {
+                    const int q = batch + c;
+                    const int qx = q % bn[0], qy = (q / bn[0]) % bn[1], qz = q / (bn[0] * bn[1]);
+                    tabs[h] = ext_tab[((b0[2] + qz + g.g[2]) * g.ne[1] + (b0[1] + qy + g.g[1])) *
+                                          g.ne[0] + (b0[0] + qx + g.g[0])];
+                }
             }
-            if ((tid & 31) == 31) warp_tot[tid >> 5] = incl;
-            __syncthreads();
-            int wbase = 0;
+            int base_tot = 0;
 #pragma unroll
-            for (int w = 0; w < NBT_THREADS / 32; ++w) wbase += w < (tid >> 5) ? warp_tot[w] : 0;
-            cell_off[tid] = wbase + incl - mine;      // (= the total for tid >= batch_cells)
-            if (tid == NBT_THREADS - 1) cell_off[NBT_CELLS] = wbase + incl;
+            for (int h = 0; h < NBT_CPT; ++h) {
+                const int c = h * NBT_THREADS + tid;
+                const int mine = (int)(tabs[h].y + tabs[h].w);
+                cell_tab[c] = tabs[h];
+                int incl = mine;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, incl, d);
+                    if ((tid & 31) >= d) incl += v;
+                }
+                if ((tid & 31) == 31) warp_tot[tid >> 5] = incl;
+                __syncthreads();
+                int wbase = 0, all = 0;
+#pragma unroll
+                for (int w = 0; w < NBT_THREADS / 32; ++w) {
+                    wbase += w < (tid >> 5) ? warp_tot[w] : 0;
+                    all += warp_tot[w];
+                }
+                cell_off[c] = base_tot + wbase + incl - mine;   // (= the total past batch_cells)
+                base_tot += all;
+                __syncthreads();          // warp_tot is reused by the next round
+            }
+            if (tid == 0) cell_off[NBT_CELLS] = base_tot;
             __syncthreads();
             const int total = cell_off[NBT_CELLS];
 
             for (int w0 = 0; w0 < total; w0 += NBT_CAP) {
                 const int w1 = min(total, w0 + NBT_CAP);
                 if (w0 > 0) __syncthreads();          // the previous window has been consumed
-                // stage the window: one warp per cell
-                for (int c = tid >> 5; c < batch_cells; c += NBT_THREADS / 32) {
-                    const int c0 = cell_off[c];
-                    const uint4 t = cell_tab[c];
-                    const int lo = max(c0, w0), hi = min(c0 + (int)(t.y + t.w), w1);
-                    for (int u = lo + (tid & 31); u < hi; u += 32) {
-                        const int o = u - c0;
-                        const uint32_t j = o < (int)t.y ? t.x + (uint32_t)o
-                                                        : t.z + (uint32_t)(o - (int)t.y);
-                        const Atom4 a = atoms[j];
-                        const uint32_t e = j | ((uint32_t)types_ext[j] << TAB_COL_TYPE_SHIFT);
-                        cand[u - w0] = make_float4((float)(a.x - ctr[0]), (float)(a.y - ctr[1]),
-                                                   (float)(a.z - ctr[2]), __uint_as_float(e));
+                // stage the window: one thread per candidate (a half-width cell holds ~4 atoms:
+                // a warp per cell would idle 28 lanes and serialise 512 cells over 8 warps).  The
+                // candidate's cell = the last one that starts at or before it (binary search in
+                // the offsets; empty cells share their start with the next one).
+                for (int u = w0 + tid; u < w1; u += NBT_THREADS) {
+                    int lo = 0, hi = batch_cells;
+                    while (hi - lo > 1) {
+                        const int mid = (lo + hi) >> 1;
+                        if (cell_off[mid] <= u) lo = mid;
+                        else hi = mid;
                     }
+                    const uint4 t = cell_tab[lo];
+                    const int o = u - cell_off[lo];
+                    const uint32_t j = o < (int)t.y ? t.x + (uint32_t)o
+                                                    : t.z + (uint32_t)(o - (int)t.y);
+                    const Atom4 a = atoms[j];
+                    const uint32_t e = j | ((uint32_t)types_ext[j] << TAB_COL_TYPE_SHIFT);
+                    cand[u - w0] = make_float4((float)(a.x - ctr[0]), (float)(a.y - ctr[1]),
+                                               (float)(a.z - ctr[2]), __uint_as_float(e));
                 }
                 __syncthreads();
                 if (active) {

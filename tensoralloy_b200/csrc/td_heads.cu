@@ -133,6 +133,13 @@ __device__ __forceinline__ bool td_mbar_wait(uint64_t *bar, uint32_t parity) {
     return false;
 }
 
+// the activation as a real function: inlined into the unrolled epilogues (A / NG copies of eight
+// activation kinds per operation kind) it made 380 KB of code and 9 % instruction-fetch stalls
+template <typename Real>
+__device__ __noinline__ Real td_act(int kind, Real z, Real &d) {
+    return act_fn<Real>(kind, z, d);
+}
+
 // A consecutive values of a pool row as 16-byte shared-memory loads
 template <typename Real, int A>
 __device__ __forceinline__ void td_load(const Real *p, Real (&v)[A]) {
@@ -310,7 +317,7 @@ __device__ __forceinline__ void td_gemm(TdStream<Real> &st, const TdOp &op, Real
             } else {
                 Real dzv[AT];
 #pragma unroll
-                for (int a = 0; a < AT; ++a) v[a] = act_fn<Real>(op.act, v[a] + b, dzv[a]);
+                for (int a = 0; a < AT; ++a) v[a] = td_act<Real>(op.act, v[a] + b, dzv[a]);
                 td_store<Real, AT>(pool + ((size_t)op.dz_off + o) * RS, dzv);
                 if (op.res_off >= 0) {
                     Real r[AT];
