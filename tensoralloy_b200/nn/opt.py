@@ -15,9 +15,11 @@ place).
   moving average  shadow = d * shadow + (1 - d) * variable after every update, d = 0.999
                   (utils.py:416); `use_ema_variables` of the export path = `ema_values()`
 
-One arithmetic difference to TF 1.x is inherent to the torch optimisers: Adam-type updates
-divide by sqrt(v_hat) + eps where TF divides by sqrt(v) + eps with the bias correction folded
-into the step size; the two agree to O(eps).
+`adam` runs torch.optim.Adam: it divides by sqrt(v_hat) + eps where TF divides by sqrt(v) + eps
+with the bias correction folded into the step size; the two agree to O(eps).  `adamw`, `nadam`
+and `rmsprop` are small optimisers of this module in TF's own arithmetic (`DecoupledAdam`,
+`TfRMSprop`), because the torch classes of the same name differ materially (weight decay scaled
+by lr, Dozat's momentum schedule, lr outside the momentum accumulator).
 """
 import math
 from dataclasses import dataclass, field
@@ -79,8 +81,10 @@ def get_optimizer(params, learning_rate, method='adam', **kwargs):
         return torch.optim.Adadelta(params, lr=learning_rate, rho=kwargs.get('rho', 0.95),
                                     eps=1e-8)
     if m == 'rmsprop':
-        return torch.optim.RMSprop(params, lr=learning_rate, alpha=kwargs.get('decay', 0.9),
-                                   momentum=kwargs.get('momentum', 0.0), eps=1e-10)
+        # TF keeps the learning rate INSIDE the momentum accumulator and epsilon under the
+        # square root (torch.optim.RMSprop: outside both): the two differ once lr decays
+        return TfRMSprop(params, lr=learning_rate, decay=kwargs.get('decay', 0.9),
+                         momentum=kwargs.get('momentum', 0.0), eps=1e-10)
     if m == 'sgd':
         return torch.optim.SGD(params, lr=learning_rate,
                                momentum=kwargs.get('momentum', 0.9),
@@ -123,6 +127,32 @@ class DecoupledAdam(torch.optim.Optimizer):
                 lr_t = group['lr'] * (1.0 - b2 ** t) ** 0.5 / (1.0 - b1 ** t)
                 num = m.mul(b1).add_(g, alpha=1.0 - b1) if group['nesterov'] else m
                 p.addcdiv_(num, v.sqrt().add_(group['eps']), value=-lr_t)
+
+
+class TfRMSprop(torch.optim.Optimizer):
+    """tf.train.RMSPropOptimizer (`training_ops.cc` ApplyRMSProp, centered = False):
+        ms  <- decay ms + (1 - decay) g^2          (ms starts at ONE, as TF initialises it)
+        mom <- momentum mom + lr g / sqrt(ms + eps)
+        var <- var - mom"""
+
+    def __init__(self, params, lr=1e-2, decay=0.9, momentum=0.0, eps=1e-10):
+        super().__init__(params, dict(lr=lr, decay=decay, momentum=momentum, eps=eps))
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        for group in self.param_groups:
+            for p in group['params']:
+                if p.grad is None:
+                    continue
+                st = self.state[p]
+                if not st:
+                    st['ms'] = torch.ones_like(p)
+                    st['mom'] = torch.zeros_like(p)
+                ms, mom, g = st['ms'], st['mom'], p.grad
+                ms.mul_(group['decay']).addcmul_(g, g, value=1.0 - group['decay'])
+                mom.mul_(group['momentum']).addcdiv_(g, (ms + group['eps']).sqrt_(),
+                                                     value=group['lr'])
+                p.sub_(mom)
 
 
 class TrainOp:

@@ -2,6 +2,7 @@
 with global step and moving averages (reference: nn/utils.py:77-150, nn/opt.py:89-166)."""
 import math
 
+import numpy as np
 import pytest
 import torch
 
@@ -35,7 +36,9 @@ def test_optimizer_factory_defaults():
     assert isinstance(nadam, DecoupledAdam) and nadam.defaults['nesterov'] is True
     assert get_optimizer(p, 0.01, 'adadelta').defaults['rho'] == 0.95
     rms = get_optimizer(p, 0.01, 'rmsprop', momentum=0.5)
-    assert rms.defaults['alpha'] == 0.9 and rms.defaults['momentum'] == 0.5
+    from tensoralloy_b200.nn.opt import TfRMSprop
+    assert isinstance(rms, TfRMSprop)
+    assert rms.defaults['decay'] == 0.9 and rms.defaults['momentum'] == 0.5
     sgd = get_optimizer(p, 0.01, 'sgd')
     assert sgd.defaults['momentum'] == 0.9 and sgd.defaults['nesterov'] is True
     with pytest.raises(ValueError, match="Supported SGD optimizers"):
@@ -116,3 +119,24 @@ def test_zero_grad_keeps_the_gradient_tensors():
     g = p.grad
     op.zero_grad()
     assert p.grad is g and float(g.abs().sum()) == 0.0
+
+
+def test_rmsprop_follows_tf_arithmetic_under_a_decaying_learning_rate():
+    """tf.train.RMSPropOptimizer (ApplyRMSProp): ms starts at 1, epsilon under the root, the
+    learning rate INSIDE the momentum accumulator -- hand-rolled recurrence over 5 steps with a
+    learning rate that halves every step."""
+    w = torch.tensor([0.5, -1.5], dtype=torch.float64, requires_grad=True)
+    op = TrainOp([w], OptParameters(method='rmsprop', learning_rate=0.1,
+                                    decay_function='exponential', decay_rate=0.5, decay_steps=1,
+                                    additional_kwargs={'decay': 0.8, 'momentum': 0.6}))
+    x = w.detach().clone().numpy()
+    ms, mom = np.ones(2), np.zeros(2)
+    for k in range(5):
+        g = 2.0 * x + np.array([0.3, -0.1]) * (k + 1)
+        w.grad = torch.tensor(g)
+        op.step()
+        lr = 0.1 * 0.5 ** k
+        ms = 0.8 * ms + 0.2 * g * g
+        mom = 0.6 * mom + lr * g / np.sqrt(ms + 1e-10)
+        x = x - mom
+        assert np.allclose(w.detach().numpy(), x, rtol=0, atol=1e-15)
