@@ -106,6 +106,27 @@ int tab_sum_slots(const double *d_slots, int32_t n_slots, int32_t n, double *d_o
 int tab_reduce_slots(const double *d_slots, int32_t n_slots, int32_t n, int32_t n_sum,
                      double *d_out, void *stream);
 
+/* Rebuild-time kernels of the spatial decomposition (csrc/dd.cu; no reference counterpart).
+ * Stable partitions (count -> scan -> scatter, no atomics: reproducible order).
+ *   tab_dd_partition  migration: d_state [n, ncol] float64 rows, column 0 = x.  x is wrapped
+ *                     into [0, lx); rows whose slab floor(x / width) is `rank` go to d_keep
+ *                     (capacity n rows), rows of the left / right ring neighbour to
+ *                     d_mail_left / d_mail_right = [count, rows ...] (float64; may be
+ *                     peer-mapped buffers of the neighbour GPUs; capacity mail_cap rows).
+ *                     d_counts int32 [8]: kept, to the left, to the right, lost (further than
+ *                     an adjacent slab), 1 if a mailbox overflowed.  d_work: int32
+ *                     [3 ceil(n / 256)] scratch.
+ *   tab_dd_send_sets  halo send sets: indices (int64, ascending) of the atoms with
+ *                     x < x_left_below -> d_idx_left, x >= x_right_from -> d_idx_right (an atom
+ *                     may be in both); d_counts int32 [2]; d_work int32 [2 ceil(n / 256)]. */
+int tab_dd_partition(const double *d_state, int32_t n, int32_t ncol, double lx, double width,
+                     int32_t world, int32_t rank, double *d_keep, double *d_mail_left,
+                     double *d_mail_right, int32_t mail_cap, int32_t *d_counts,
+                     int32_t *d_work, void *stream);
+int tab_dd_send_sets(const double *d_pos, int32_t n, double x_left_below, double x_right_from,
+                     int64_t *d_idx_left, int64_t *d_idx_right, int32_t *d_counts,
+                     int32_t *d_work, void *stream);
+
 /* Batch of independent structures in ONE handle ("structure-parallel batches"; replaces
  * the padded [B, N+1, 3] / [B, nij_max, .] tensors of BatchUniversalTransformer,
  * transformer/universal.py:921-1388, and the per-structure ASE neighbour lists behind them).

@@ -6,7 +6,7 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
 CSRC = ROOT / 'tensoralloy_b200' / 'csrc'
-SOURCES = ['scan.cu', 'nbr.cu', 'eam.cu', 'sf.cu', 'hessian.cu', 'pairs.cu', 'td_heads.cu']
+SOURCES = ['scan.cu', 'nbr.cu', 'eam.cu', 'sf.cu', 'hessian.cu', 'pairs.cu', 'td_heads.cu', 'dd.cu']
 # -cudart shared: the library carries no private copy of the CUDA runtime (and none of its
 # entry-point tables); it uses the libcudart.so.12 already loaded by torch / the system one
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3',

@@ -115,6 +115,7 @@ EXPORTS = [
     'tab_profile_enable', 'tab_profile_read',
     'tab_nbr_set_skin', 'tab_nbr_max_displacement', 'tab_nbr_displacement_device',
     'tab_reduce_slots', 'tab_eam_elastic', 'tab_td_create', 'tab_td_free', 'tab_td_eval', 'tab_td_status',
+    'tab_dd_partition', 'tab_dd_send_sets',
 ]
 
 
@@ -181,6 +182,9 @@ def lib():
     L.tab_eam_tabulate.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp]
     L.tab_atomic_forces.argtypes = [vp, vp, i32, vp, vp, vp, vp]
     L.tab_atomic_jvp.argtypes = [vp, vp, i32, vp, vp, vp, vp]
+    L.tab_dd_partition.argtypes = [vp, i32, i32, dbl, dbl, i32, i32, vp, vp, vp, i32, vp, vp,
+                                   vp]
+    L.tab_dd_send_sets.argtypes = [vp, i32, dbl, dbl, vp, vp, vp, vp, vp]
     L.tab_td_create.argtypes = [pp, C.POINTER(TabTdDesc)]
     L.tab_td_free.argtypes = [vp]
     L.tab_td_status.argtypes = [vp, C.POINTER(i32), vp]
@@ -238,6 +242,23 @@ def peer_put(src, peer_ptrs, slot):
     """src[0..n) -> slot `slot` of every peer buffer (device int64 array of addresses)."""
     check(lib().tab_peer_put(_ptr(src), int(src.numel()), _ptr(peer_ptrs),
                              int(peer_ptrs.numel()), int(slot), _stream()), 'tab_peer_put')
+
+
+def dd_partition(state, lx, width, world, rank, keep, mail_left, mail_right, mail_cap, counts,
+                 work):
+    """tab_dd_partition: migration of the rows of `state` [n, ncol] (see include/tab200.h)."""
+    n, ncol = int(state.shape[0]), int(state.shape[1])
+    check(lib().tab_dd_partition(_ptr(state), n, ncol, float(lx), float(width), int(world),
+                                 int(rank), _ptr(keep), _ptr(mail_left), _ptr(mail_right),
+                                 int(mail_cap), _ptr(counts), _ptr(work), _stream()),
+          'tab_dd_partition')
+
+
+def dd_send_sets(pos, x_left_below, x_right_from, idx_left, idx_right, counts, work):
+    """tab_dd_send_sets: indices of the atoms within reach of the low / high face."""
+    check(lib().tab_dd_send_sets(_ptr(pos), int(pos.shape[0]), float(x_left_below),
+                                 float(x_right_from), _ptr(idx_left), _ptr(idx_right),
+                                 _ptr(counts), _ptr(work), _stream()), 'tab_dd_send_sets')
 
 
 def sum_slots(slots, n_slots, out, n_sum=None):

@@ -70,18 +70,6 @@ def _graph_exec_update(live, captured):
         return False
 
 
-def _where_static(mask, count):
-    """Indices of the set entries of a 1-D mask whose number is already known on the host
-    (ascending): `nonzero` without its device-to-host read-back."""
-    import torch
-    if count == 0:
-        return torch.zeros(0, dtype=torch.int64, device=mask.device)
-    try:
-        return torch.nonzero_static(mask, size=int(count)).flatten()
-    except (RuntimeError, NotImplementedError):
-        return torch.nonzero(mask).flatten()
-
-
 class SlabLayout:
     """Pure geometry: which atoms a rank owns and which it sends where."""
 
@@ -295,51 +283,69 @@ class PeerComm:
         self._apply(table, n_send_left, n_send_right)
 
     def migrate(self, state):
-        """`DistComm.migrate` over the peer mappings: the atoms that left the slab are stored
-        straight into the ring neighbours' mailboxes (count + rows), one device barrier, one
-        read-back of the two received counts.  The received rows are appended in a fixed order
-        (from the left, then from the right; each in the sender's order)."""
+        """`DistComm.migrate` over the peer mappings, on the device: `tab_dd_partition` wraps x,
+        classifies every row (keep / left / right neighbour), compacts the kept rows and stores
+        the leaving rows with their count straight into the ring neighbours' mailboxes (three
+        launches, stable order); one device barrier; ONE read-back of [kept, left, right, lost,
+        overflow] and the two received counts.  The received rows are appended in a fixed order
+        (from the left, then from the right; each in the sender's order).  Returns a view of
+        one of two alternating buffers."""
+        from tensoralloy_b200 import _lib
         torch = self.torch
         lay = self.layout
-        state = state.clone()
-        x = torch.remainder(state[:, 0], lay.lx)
-        x = torch.where(x >= lay.lx, torch.zeros_like(x), x)
-        state[:, 0] = x
-        owner = lay.owner_of(x).to(torch.int64)
-        # 0 keep, 1 to the left, 2 to the right, 3 further away (an error)
-        code = torch.where(owner == lay.rank, 0, torch.where(
-            owner == lay.left, 1, torch.where(owner == lay.right, 2, 3)))
-        if lay.world == 2:
-            code = torch.where(owner == lay.rank, 0, 2)      # left == right: one other rank
-        n_keep, n_l, n_r, n_bad = torch.bincount(code, minlength=4).tolist()      # read-back 1
-        if n_bad:
-            raise RuntimeError("an atom moved further than to the adjacent slab between two "
-                               "list rebuilds")
-        if max(n_l, n_r) > self.MIG_CAP:
-            raise RuntimeError(f"{max(n_l, n_r)} atoms leave through one face: more than the "
-                               f"migration mailbox holds ({self.MIG_CAP})")
-        c = self.MIG_COLS
-        kept = state[_where_static(code == 0, n_keep)]
-        self.mail_to_l[0] = float(n_l)
-        self.mail_to_r[0] = float(n_r)
-        if n_l:
-            self.mail_to_l[1:1 + n_l * c] = state[_where_static(code == 1, n_l)].reshape(-1)
-        if n_r:
-            self.mail_to_r[1:1 + n_r * c] = state[_where_static(code == 2, n_r)].reshape(-1)
+        n, c = int(state.shape[0]), self.MIG_COLS
+        state = state.contiguous()
+        cap = n + 2 * self.MIG_CAP
+        self._mig_flip = 1 - getattr(self, '_mig_flip', 0)
+        bufs = self.__dict__.setdefault('_mig_bufs', [None, None])
+        keep = bufs[self._mig_flip]
+        if keep is None or keep.shape[0] < cap or keep.data_ptr() == state.data_ptr():
+            keep = bufs[self._mig_flip] = torch.empty((cap + cap // 8, c), dtype=torch.float64,
+                                                      device=self.device)
+        nwork = 3 * ((n + 255) // 256) + 8
+        if getattr(self, '_mig_work', None) is None or self._mig_work.numel() < nwork:
+            self._mig_work = torch.empty(2 * nwork, dtype=torch.int32, device=self.device)
+            self._mig_counts = torch.zeros(8, dtype=torch.int32, device=self.device)
+        _lib.dd_partition(state, lay.lx, lay.width, lay.world, lay.rank, keep, self.mail_to_l,
+                          self.mail_to_r, self.MIG_CAP, self._mig_counts, self._mig_work)
         self.mail_hdl.barrier(channel=4)
         box = 1 + self.MIG_CAP * c
-        got = torch.stack((self.mail[0], self.mail[box])).tolist()              # read-back 2
-        a, b = int(got[0]), int(got[1])
-        parts = [kept]
+        got = torch.cat((self._mig_counts[:5].to(torch.float64), self.mail[0:1],
+                         self.mail[box:box + 1])).tolist()                    # the read-back
+        n_keep, n_l, n_r, n_lost, overflow, a, b = (int(v) for v in got)
+        if n_lost:
+            raise RuntimeError("an atom moved further than to the adjacent slab between two "
+                               "list rebuilds")
+        if overflow:
+            raise RuntimeError(f"{max(n_l, n_r)} atoms leave through one face: more than the "
+                               f"migration mailbox holds ({self.MIG_CAP})")
         if a:
-            parts.append(self.mail[1:1 + a * c].view(a, c))
+            keep[n_keep:n_keep + a] = self.mail[1:1 + a * c].view(a, c)
         if b:
-            parts.append(self.mail[box + 1:box + 1 + b * c].view(b, c))
-        out = torch.cat(parts, dim=0).contiguous()
+            keep[n_keep + a:n_keep + a + b] = self.mail[box + 1:box + 1 + b * c].view(b, c)
         # (a mailbox is not overwritten before its owner has copied it out: the peers' next
         # stores into it come after the device barrier of `configure`, which this rank enters
-        # after the copy above, in stream order)
-        return out
+        # after the copies above, in stream order)
+        return keep[:n_keep + a + b]
+
+    def configure_device(self, n_owned, d_send_counts):
+        """`configure` with the send counts still on the device (int32 [2] written by
+        `tab_dd_send_sets`): they go into the count table without a detour through the host;
+        the read-back of the table is the only synchronisation.  Returns (n_send_left,
+        n_send_right) of this rank."""
+        from tensoralloy_b200 import _lib
+        torch = self.torch
+        world, rank = self.layout.world, self.layout.rank
+        mine = torch.empty(4, dtype=torch.float64, device=self.device)
+        mine[0] = float(n_owned)
+        mine[1:3] = d_send_counts[:2]
+        mine[3] = 0.0
+        _lib.peer_put(mine, self.counts_ptrs, rank)
+        self.counts_hdl.barrier(channel=3)
+        table = self.counts.view(world, 4)[:, :3].to(torch.int64).tolist()
+        n_l, n_r = table[rank][1], table[rank][2]
+        self._apply(table, n_l, n_r)
+        return n_l, n_r
 
     def _apply(self, table, n_send_left, n_send_right):
         torch = self.torch
@@ -408,26 +414,41 @@ class SlabRank:
 
     def set_owned(self, pos_owned):
         """(Re)define the owned atoms: numpy or device tensor [n, 3], wrapped x."""
+        self.set_owned_begin(pos_owned)
+        n_l, n_r = self.d_send_counts.tolist()          # one read-back for both counts
+        self.set_owned_finish(n_l, n_r)
+
+    def set_owned_begin(self, pos_owned):
+        """Owned positions + the send sets (atoms within rc + skin of the faces) as ONE library
+        call, `tab_dd_send_sets`: both index lists and their lengths stay on the device
+        (`d_send_counts`); `set_owned_finish` takes the lengths once the host knows them."""
         torch = self.torch
         device = self.device
         if not torch.is_tensor(pos_owned):
             pos_owned = torch.from_numpy(np.ascontiguousarray(pos_owned))
         self._pos0 = pos_owned.to(device).contiguous()
-        self.n_owned = int(self._pos0.shape[0])
-        m_l, m_r = self.lay.send_masks(self._pos0[:, 0])
-        # both index sets with ONE read-back: stable sort of the membership code, counts
-        # (an atom may be in both sets when the slab is narrower than 2 (rc + skin) + ...: the
-        # two sets are therefore formed separately from the same pass)
-        n_l, n_r = torch.stack([m_l.sum(), m_r.sum()]).tolist()
-        self.idx_l = _where_static(m_l, n_l)
-        self.idx_r = _where_static(m_r, n_r)
+        n = self.n_owned = int(self._pos0.shape[0])
+        if getattr(self, '_idx_buf', None) is None or self._idx_buf.shape[1] < n:
+            self._idx_buf = torch.empty((2, n + n // 8 + 64), dtype=torch.int64, device=device)
+            self._send_work = torch.empty(2 * ((n + n // 8 + 64 + 255) // 256) + 8,
+                                          dtype=torch.int32, device=device)
+            self.d_send_counts = torch.zeros(2, dtype=torch.int32, device=device)
+        self._lib.dd_send_sets(self._pos0, self.lay.lo + self.lay.reach,
+                               self.lay.hi - self.lay.reach, self._idx_buf[0],
+                               self._idx_buf[1], self.d_send_counts, self._send_work)
+
+    def set_owned_finish(self, n_l, n_r):
+        torch = self.torch
+        device = self.device
+        self.idx_l = self._idx_buf[0, :n_l]
+        self.idx_r = self._idx_buf[1, :n_r]
         self.shift_l = [self.lay.shift_to_left, 0.0, 0.0]
         self.shift_r = [self.lay.shift_to_right, 0.0, 0.0]
         f64 = dict(dtype=torch.float64, device=device)
-        self.send_pos_l = torch.empty((len(self.idx_l), 3), **f64)
-        self.send_pos_r = torch.empty((len(self.idx_r), 3), **f64)
-        self.send_fp_l = torch.empty(len(self.idx_l), **f64)
-        self.send_fp_r = torch.empty(len(self.idx_r), **f64)
+        self.send_pos_l = torch.empty((n_l, 3), **f64)
+        self.send_pos_r = torch.empty((n_r, 3), **f64)
+        self.send_fp_l = torch.empty(n_l, **f64)
+        self.send_fp_r = torch.empty(n_r, **f64)
         self.d_fp = torch.zeros(self.n_owned, **f64)
         self.d_out = torch.zeros(16, **f64)
         self.d_f = torch.zeros((self.n_owned, 3), **f64)
@@ -575,12 +596,12 @@ class SlabDomain:
         self._attach(first=True)
 
     # -- (re)attachment of the rank state to the communication buffers -----------
-    def _attach(self, first=False, lap=None):
+    def _attach(self, first=False, lap=None, configured=False):
         lap = lap or (lambda name: None)
         r = self.rank_state
         if self.peer is not None:
             pc = self.peer
-            if not first:
+            if not first and not configured:
                 pc.configure(r.n_owned, len(r.idx_l), len(r.idx_r))
             r.set_halo_counts(pc.n_from_l, pc.n_from_r, pos_loc=pc.pos_loc,
                               fp_halo=pc.fp_halo, out=pc.red)
@@ -758,10 +779,18 @@ class SlabDomain:
         self.state = self.peer.migrate(self.state) if self.peer is not None else \
             self.comm.migrate(self.state)
         lap('migrate')
-        r.set_owned(self.state[:, 0:3])
+        configured = False
+        if self.peer is not None:
+            # send sets and the exchange of the new counts without a host detour: one read-back
+            r.set_owned_begin(self.state[:, 0:3])
+            n_l, n_r = self.peer.configure_device(r.n_owned, r.d_send_counts)
+            r.set_owned_finish(n_l, n_r)
+            configured = True
+        else:
+            r.set_owned(self.state[:, 0:3])
         lap('send_sets')
         self.graph = None               # (the executable graph survives in _graph_exec)
-        self._attach(lap=lap)
+        self._attach(lap=lap, configured=configured)
         self.rebuilds += 1
         # the step that follows runs eagerly (with the new sizes: every library buffer that has
         # to grow does so outside a capture); `md_step` re-captures after it

@@ -1,0 +1,14 @@
+#!/bin/bash
+# 2 GPUs: dd kernels unit test, multi-GPU tests, md-cycle check, bench N = 2 with the rebuild profile
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_domain_gpu.py tests/test_domain_multigpu.py -m gpu -q -x > gpurun_out/r02za_dd_tests.log 2>&1
+echo "tests rc=$?"; tail -5 gpurun_out/r02za_dd_tests.log
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29551 tools/dd_check.py 12 > gpurun_out/r02za_dd_check.log 2>&1
+echo "dd_check rc=$?"; grep "md-cycle" gpurun_out/r02za_dd_check.log | head -4
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29572 bench.py --gpus 2 --steps 20 --warmup 5 --rebuild-profile --no-extra > gpurun_out/r02za_bench_n2.json 2> gpurun_out/r02za_bench_n2.err
+echo "bench rc=$?"; python - <<'PY'
+import json
+d=json.load(open('gpurun_out/r02za_bench_n2.json'))
+print('n2 value %.4g ms %.4f resident %.4f e2e %.3f'%(d['value'],d['ms_per_step'],d['resident']['ms_per_step'],d['e2e']['ms_per_step']), {k:round(v,2) for k,v in d['config']['rebuild_profile_ms'].items()}, d['check']['ok'], d['check']['energy'], d['check']['f_l2'], d['check']['atoms_accounted_for'])
+PY
+grep -v "^W\|^\[W\|OMP\|^\*\|^$\|NCCL" gpurun_out/r02za_bench_n2.err | tail -5
