@@ -83,49 +83,64 @@ def load_peaks():
     return 6650.0, 'fallback'
 
 
+_SAMPLER_CHILD = r"""
+import json, signal, sys, time
+idx, period = int(sys.argv[1]), float(sys.argv[2])
+stop = [False]
+signal.signal(signal.SIGTERM, lambda *a: stop.__setitem__(0, True))
+sm, mx, reasons, src = [], [], 0, 'nvml'
+try:
+    import pynvml as n
+    n.nvmlInit()
+    h = n.nvmlDeviceGetHandleByIndex(idx)
+    get_r = getattr(n, 'nvmlDeviceGetCurrentClocksEventReasons', None) or \
+        n.nvmlDeviceGetCurrentClocksThrottleReasons
+    mx.append(float(n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)))
+    print('ready', flush=True)
+    while not stop[0]:
+        try:
+            sm.append(float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)))
+            reasons |= int(get_r(h))
+        except Exception:
+            pass
+        time.sleep(period)
+except Exception:
+    src = 'none'
+    print('ready', flush=True)
+    while not stop[0]:
+        time.sleep(0.02)
+print(json.dumps({'sm': sm, 'mx': mx, 'reasons': reasons, 'source': src}), flush=True)
+"""
+
+
 class ClockSampler:
-    """SM clock + throttle reasons DURING the timed regions.  NVML (pynvml) is polled
-    every ~2 ms from a thread (the device-timed region is only ~25 ms long); if
-    NVML is unavailable the nvidia-smi query of the profiling recipe is used."""
+    """SM clock + throttle reasons DURING the timed regions.  NVML is polled every ~2 ms (the
+    device-timed region is only ~25 ms long) by a CHILD PROCESS: a polling thread inside the
+    benchmark process competes with the step's own launches for the interpreter lock and for the
+    driver (measured at 8 ranks: rank 0, the one that samples, became the straggler of every
+    rebuild).  If NVML is unavailable the nvidia-smi query of the profiling recipe is used from
+    a thread at 0.2 s."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
     NAMES = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+    BITS = {'hw_slowdown': 0x8, 'sw_power_cap': 0x4, 'sw_thermal_slowdown': 0x20,
+            'hw_thermal_slowdown': 0x40}
 
     def __init__(self, index=0):
         self.index = index
+        vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+        self.phys = int(vis.split(',')[index]) if vis and len(vis.split(',')) > index and \
+            vis.split(',')[index].isdigit() else index
         self.sm, self.mx, self.reasons = [], [], set()
         self._stop = threading.Event()
         self._t = None
-        self._nvml = None
-        try:
-            import pynvml
-            pynvml.nvmlInit()
-            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
-            phys = int(vis.split(',')[index]) if vis and vis.split(',')[index].isdigit() \
-                else index
-            self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
-            self._nvml = pynvml
-        except Exception:
-            self._nvml = None
-
-    def _poll_nvml(self):
-        n = self._nvml
-        self.sm.append(float(n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM)))
-        self.mx.append(float(n.nvmlDeviceGetMaxClockInfo(self._h, n.NVML_CLOCK_SM)))
-        r = n.nvmlDeviceGetCurrentClocksEventReasons(self._h) \
-            if hasattr(n, 'nvmlDeviceGetCurrentClocksEventReasons') \
-            else n.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
-        bits = {'hw_slowdown': 0x8, 'sw_power_cap': 0x4, 'sw_thermal_slowdown': 0x20,
-                'hw_thermal_slowdown': 0x40}
-        for name, bit in bits.items():
-            if r & bit:
-                self.reasons.add(name)
+        self._child = None
 
     def _poll_smi(self):
         out = subprocess.run(
-            ['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.Q}',
+            ['nvidia-smi', f'--id={self.phys}', f'--query-gpu={self.Q}',
              '--format=csv,noheader,nounits'], capture_output=True, text=True,
             timeout=5).stdout.strip()
         if not out:
@@ -137,29 +152,51 @@ class ClockSampler:
             if v.lower().startswith('active'):
                 self.reasons.add(name)
 
-    def _run(self):
+    def _run_smi(self):
         while not self._stop.is_set():
             try:
-                if self._nvml is not None:
-                    self._poll_nvml()
-                else:
-                    self._poll_smi()
+                self._poll_smi()
             except Exception:
                 pass
-            self._stop.wait(0.002 if self._nvml is not None else 0.2)
+            self._stop.wait(0.2)
 
     def start(self):
-        self._t = threading.Thread(target=self._run, daemon=True)
-        self._t.start()
+        try:
+            self._child = subprocess.Popen(
+                [sys.executable, '-c', _SAMPLER_CHILD, str(self.phys), '0.002'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            if self._child.stdout.readline().strip() != 'ready':
+                raise RuntimeError("sampler child did not start")
+        except Exception:
+            self._child = None
+            self._t = threading.Thread(target=self._run_smi, daemon=True)
+            self._t.start()
 
     def stop(self):
-        self._stop.set()
-        if self._t:
-            self._t.join(timeout=6)
+        source = 'nvidia-smi'
+        if self._child is not None:
+            try:
+                self._child.terminate()                  # SIGTERM to the child's own pid
+                out, _ = self._child.communicate(timeout=10)
+                d = json.loads(out.strip().splitlines()[-1])
+                self.sm, self.mx = d['sm'], d['mx']
+                self.reasons = {k for k, bit in self.BITS.items() if d['reasons'] & bit}
+                source = 'nvml (child process)' if d['source'] == 'nvml' else 'none'
+            except Exception:
+                source = 'none'
+            if source == 'none':
+                try:
+                    self._poll_smi()                     # one sample rather than none
+                    source = 'nvidia-smi'
+                except Exception:
+                    pass
+        else:
+            self._stop.set()
+            if self._t:
+                self._t.join(timeout=6)
         return {"sm_mhz": statistics.median(self.sm) if self.sm else None,
                 "sm_max_mhz": max(self.mx) if self.mx else None,
-                "reasons": sorted(self.reasons), "samples": len(self.sm),
-                "source": "nvml" if self._nvml is not None else "nvidia-smi"}
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "source": source}
 
 
 # ---------------------------------------------------------------------------
