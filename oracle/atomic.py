@@ -293,10 +293,17 @@ def grap_descriptors_new_mode(elements, types, R, cell, i, j, S, rc, algorithm, 
     if algorithm == 'nn':
         # NNAlgorithm (grap.py:211-234, 619-646): one filter network r -> K values shared by
         # every (centre, neighbour) element pair, no output bias; grid = dict(weights,
-        # biases, activation, use_resnet_dt) with h_abck_modifier 0 (H input = r)
+        # biases, activation, use_resnet_dt[, h_abck_modifier, rcov])
         W = [torch.as_tensor(w, dtype=dtype) for w in grid['weights']]
         b = [None if v is None else torch.as_tensor(v, dtype=dtype) for v in grid['biases']]
-        H = mlp(rij[:, None], W, b, grid.get('activation', 'softplus'),
+        # grap.py:621-632: h_abck_modifier 1 / 2 feed r / r_cov or exp(-r / r_cov) of the CENTRE
+        # element; grid['rcov'] = {element: covalent radius} (ase.data.covalent_radii there)
+        mod = int(grid.get('h_abck_modifier', 0))
+        h_in = rij
+        if mod:
+            rcov = torch.as_tensor([grid['rcov'][e] for e in elements], dtype=dtype)[ci]
+            h_in = rij / rcov if mod == 1 else torch.exp(-(rij / rcov))
+        H = mlp(h_in[:, None], W, b, grid.get('activation', 'softplus'),
                 grid.get('use_resnet_dt', True), None, all_outputs=True) * fc[:, None]
     else:
         H = torch.stack([grap_radial(algorithm, prm, rij, rc) * fc for prm in grid], 1)  # [P, K]

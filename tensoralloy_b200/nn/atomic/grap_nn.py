@@ -19,8 +19,9 @@ neighbour lists stays in libtab200 --
 same device so that autograd (create_graph) provides dE/dD_p and every parameter gradient,
 which the reference obtains from TF second-order autograd (nn/opt.py:132-157).
 
-`h_abck_modifier` 1 / 2 (input r / r_cov, exp(-r / r_cov); grap.py:621-632) need ASE's
-covalent radii, which are not vendored: refused.
+`h_abck_modifier` 1 / 2 (filter input r / r_cov, exp(-r / r_cov) with the covalent radius of
+the centre element; grap.py:621-632) use the Cordero-2008 table stated in `atoms.py` (the
+source of ASE's `covalent_radii`; ASE itself is not installed here).
 """
 import math
 import os
@@ -76,9 +77,9 @@ class NNAlgorithm:
                 self.h_abck_modifier = int(npz["fnn::h_abck_modifier"])
         elif self.ckpt is not None and not isinstance(self.ckpt, str):
             raise ValueError("GRAP/nn: `ckpt` must be the path of an npz file or None")
-        if self.h_abck_modifier != 0:
-            raise ValueError("GRAP/nn: h_abck_modifier 1 / 2 need covalent radii "
-                             "(not implemented); use 0")
+        if self.h_abck_modifier not in (0, 1, 2):
+            raise ValueError(f"GRAP/nn: unknown h_abck_modifier {self.h_abck_modifier} "
+                             "(0: r, 1: r / r_cov, 2: exp(-r / r_cov))")
         if self.num_filters < 1 or not self.hidden_sizes:
             raise ValueError("GRAP/nn: num_filters >= 1 and at least one hidden layer")
 
@@ -186,7 +187,17 @@ def closed_form_radial(algorithm, grid, rc):
     return fn
 
 
-def filter_descriptors(D, key, n_rows, radial, cutoff, rc, max_moment, symmetric, eps):
+def centre_covalent_radii(elements, centre_types, dtype, device):
+    """r_cov of the CENTRE atom of every pair (grap.py:623-628: the reference evaluates the
+    filter input per centre element)."""
+    from tensoralloy_b200.atoms import atomic_numbers, covalent_radii
+    table = torch.tensor([covalent_radii[atomic_numbers[e]] for e in elements], dtype=dtype,
+                         device=device)
+    return table[centre_types]
+
+
+def filter_descriptors(D, key, n_rows, radial, cutoff, rc, max_moment, symmetric, eps,
+                       modifier=0, rcov=None):
     """New-mode GRAP descriptors from the directed pair vectors (grap.py:596-680).
     D [P, 3]; key [P] = centre * n_el + term (row of the moment sums); n_rows = n * n_el;
     radial: r [P] -> H [P, K] without the cutoff (the filter network or the closed forms).
@@ -197,7 +208,11 @@ def filter_descriptors(D, key, n_rows, radial, cutoff, rc, max_moment, symmetric
     with max_moment 4 or 5 uses the full 3^m products with unit weights for EVERY moment and
     has no traceless form (`get_moment_tensor` / `get_T_dm`, grap.py:537-594, 655-660)."""
     r = torch.sqrt(torch.sum(D * D, dim=1) + eps)                 # universal.py:470-473
-    H = radial(r) * _cutoff(cutoff, r, rc)[:, None]                # [P, K]
+    # input of the radial functions (`h_abck_modifier`, grap.py:621-632): r, r / r_cov or
+    # exp(-r / r_cov) with the covalent radius of the centre atom (`rcov` [P]); the cutoff and
+    # the moments always see r itself
+    h_in = r if modifier == 0 else (r / rcov if modifier == 1 else torch.exp(-r / rcov))
+    H = radial(h_in) * _cutoff(cutoff, r, rc)[:, None]             # [P, K]
     K = H.shape[1]
     z = lambda *shape: torch.zeros(*shape, dtype=D.dtype, device=D.device)
     P0 = z(n_rows, K).index_add(0, key, H)
@@ -232,6 +247,11 @@ def filter_descriptors(D, key, n_rows, radial, cutoff, rc, max_moment, symmetric
             S3 = S3 - 0.6 * S1                                     # grap.py:492-494
         cols.append(S3)
     return torch.stack(cols, dim=2)
+
+
+def _modifier_of(nn):
+    desc = nn.descriptor
+    return int(desc.algorithm_object.h_abck_modifier) if desc.algorithm == 'nn' else 0
 
 
 def _radial_of(nn, filters):
@@ -290,9 +310,12 @@ class FilterEvaluator:
         ti, tj = types[i], types[j]
         term = torch.where(ti == tj, torch.zeros_like(ti), tj - (tj > ti).long() + 1)
         D = D.to(self.tdtype).detach().requires_grad_(want_forces)
+        mod = _modifier_of(nn)
         G = filter_descriptors(D, i * nel + term, n * nel, _radial_of(nn, self.filters),
                                desc.cutoff_function, nn.transformer.rcut,
-                               desc.max_moment, desc.is_T_symmetric, self.dt.eps)
+                               desc.max_moment, desc.is_T_symmetric, self.dt.eps, mod,
+                               centre_covalent_radii(nn.elements, ti, self.tdtype, self.device)
+                               if mod else None)
         G = G.reshape(n, -1)
         e_atom = torch.zeros(n, dtype=self.tdtype, device=self.device)
         for a, el in enumerate(nn.elements):
@@ -357,7 +380,7 @@ class GrapFilterTrainer(AtomicNNTrainer):
         # index of the k-body term inside the centre's list [cc, c-x1, ...] (utils.py:262-273)
         term = torch.where(ti == tj, torch.zeros_like(ti), tj - (tj > ti).long() + 1)
         return dict(
-            nbr=nbr, key=i * nel + term, D=D.to(self.tdtype), types=types,
+            nbr=nbr, key=i * nel + term, D=D.to(self.tdtype), types=types, centre=ti,
             sel=[torch.nonzero(types == a).reshape(-1) for a in range(nel)],
             sid=torch.repeat_interleave(torch.arange(len(S), device=dev), n_atoms),
             n_atoms=n_atoms,
@@ -371,9 +394,12 @@ class GrapFilterTrainer(AtomicNNTrainer):
         B = self._batch
         desc = self.nn.descriptor
         n, nel = B['types'].shape[0], len(self.elements)
+        mod = _modifier_of(self.nn)
         G = filter_descriptors(D, B['key'], n * nel, _radial_of(self.nn, self.filters),
                                desc.cutoff_function, self.nn.transformer.rcut,
-                               desc.max_moment, desc.is_T_symmetric, self.dt.eps)
+                               desc.max_moment, desc.is_T_symmetric, self.dt.eps, mod,
+                               centre_covalent_radii(self.elements, B['centre'], self.tdtype,
+                                                     self.device) if mod else None)
         return G.reshape(n, -1)                   # [n, term * K * (M + 1)]
 
     def energies(self, D):

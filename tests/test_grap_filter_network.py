@@ -33,9 +33,11 @@ def make_structures(n_struct=2, seed=5):
     return out
 
 
-def make_model(elements, rc, max_moment, symmetric, cutoff='cosine', algorithm='nn'):
+def make_model(elements, rc, max_moment, symmetric, cutoff='cosine', algorithm='nn',
+               h_abck_modifier=0):
     parameters = dict(num_filters=5, hidden_sizes=[8, 8], activation='softplus',
-                      use_resnet_dt=True) if algorithm == 'nn' else \
+                      use_resnet_dt=True, h_abck_modifier=h_abck_modifier) \
+        if algorithm == 'nn' else \
         dict(rl=[1.5, 2.5, 2.0], pl=[2.0, 3.0, 1.0])
     desc = GenericRadialAtomicPotential(
         elements, algorithm, parameters,
@@ -170,16 +172,18 @@ def test_filter_variables_round_trip_and_frozen_filters():
                                       for e in elements)
 
 
-def test_filter_evaluator_matches_oracle_energy_forces_stress():
+@pytest.mark.parametrize("modifier", [0, 1, 2])
+def test_filter_evaluator_matches_oracle_energy_forces_stress(modifier):
     """The inference side (`AtomicNN._evaluate` of a model with the `nn` algorithm):
     per-atom energies, forces and virial against the oracle's autograd, CPU stand-in for the
-    pair-force op."""
+    pair-force op.  `h_abck_modifier` 1 / 2 (grap.py:621-632): the filter input is r / r_cov or
+    exp(-r / r_cov) of the centre element (Mo 1.54 A, Ni 1.24 A, Cordero 2008)."""
     from oracle import atomic as oat
     from tensoralloy_b200.nn.atomic.grap_nn import FilterEvaluator
     elements, rc = ['Mo', 'Ni'], 4.5
     st = make_structures(1, seed=8)[0]
     with precision_scope('high'):
-        nn = make_model(elements, rc, 3, True, 'polynomial')
+        nn = make_model(elements, rc, 3, True, 'polynomial', h_abck_modifier=modifier)
         i, j, S = onl.neighbor_list(st['positions'], st['cell'], st['pbc'], rc)[:3]
         D = torch.as_tensor(st['positions'][j] - st['positions'][i] + S @ st['cell'])
         ti, tj = torch.as_tensor(i).long(), torch.as_tensor(j).long()
@@ -189,12 +193,18 @@ def test_filter_evaluator_matches_oracle_energy_forces_stress():
                                                          n, 1, D))
         types = np.array([elements.index(x) for x in st['symbols']])
         e_atom, F, W = ev(None, types, pairs=(ti, tj, D))
-        fp = filter_params(nn)
+        fp = dict(filter_params(nn), h_abck_modifier=modifier, rcov={'Mo': 1.54, 'Ni': 1.24})
         grap = dict(algorithm='nn', grid=fp, moments=[0, 1, 2, 3], cutoff='polynomial',
                     new_mode=True, symmetric=True)
         params = {el: nn.mlp_params(el) for el in elements}
         ref = oat.atomic_evaluate(elements, st['symbols'], st['positions'], st['cell'],
                                   st['pbc'], rc, params, angular=False, grap=grap)
+        if modifier:
+            # the modifier changes the result (it is not silently ignored)
+            plain = dict(grap, grid=dict(fp, h_abck_modifier=0))
+            other = oat.atomic_evaluate(elements, st['symbols'], st['positions'], st['cell'],
+                                        st['pbc'], rc, params, angular=False, grap=plain)
+            assert abs(other['energy'] - ref['energy']) > 1e-6
     vol = abs(np.linalg.det(st['cell']))
     assert abs(e_atom.sum().item() - ref['energy']) / n < 1e-12
     assert np.abs(F.numpy() - ref['forces']).max() < 1e-10

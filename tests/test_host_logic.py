@@ -206,7 +206,7 @@ def test_grap_new_mode_layout_and_refusals():
                moment_tensors=2, legacy_mode=False)
     assert fnn.dimension() == 2 * 6 * 3 and fnn.as_dict()["parameters"]["num_filters"] == 6
     with pytest.raises(ValueError, match="h_abck_modifier"):
-        Grap(['Be'], 'nn', dict(h_abck_modifier=2), legacy_mode=False)
+        Grap(['Be'], 'nn', dict(h_abck_modifier=3), legacy_mode=False)
     with pytest.raises(ValueError, match="moments 0, 1, 2"):
         Grap(['Be'], 'sf', par, moment_tensors=3)                 # legacy stops at 2
     five = Grap(['Be'], 'sf', par, moment_tensors=5, legacy_mode=False)
