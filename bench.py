@@ -84,8 +84,9 @@ def load_peaks():
 
 
 _SAMPLER_CHILD = r"""
-import json, signal, sys, time
+import json, os, signal, sys, time
 idx, period = int(sys.argv[1]), float(sys.argv[2])
+parent = os.getppid()
 stop = [False]
 signal.signal(signal.SIGTERM, lambda *a: stop.__setitem__(0, True))
 sm, mx, reasons, src = [], [], 0, 'nvml'
@@ -97,7 +98,7 @@ try:
         n.nvmlDeviceGetCurrentClocksThrottleReasons
     mx.append(float(n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)))
     print('ready', flush=True)
-    while not stop[0]:
+    while not stop[0] and os.getppid() == parent:      # (an orphan ends itself)
         try:
             sm.append(float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)))
             reasons |= int(get_r(h))
@@ -107,7 +108,7 @@ try:
 except Exception:
     src = 'none'
     print('ready', flush=True)
-    while not stop[0]:
+    while not stop[0] and os.getppid() == parent:
         time.sleep(0.02)
 print(json.dumps({'sm': sm, 'mx': mx, 'reasons': reasons, 'source': src}), flush=True)
 """
