@@ -41,7 +41,9 @@
 #define TD_MAX_WIDTH 256            // 2 columns per thread
 #define TD_MAX_OPS 64
 #define TD_STAGES 4                 // weight chunks in the ring (TD_STAGES - 1 in flight)
+#ifndef TD_WBUF_BYTES
 #define TD_WBUF_BYTES (16 * 1024)   // one weight chunk, float64 (float32: half)
+#endif
 #define TD_SMEM_MAX (220 * 1024)
 #define TD_SPIN_LIMIT (1u << 24)
 
