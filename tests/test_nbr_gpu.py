@@ -141,3 +141,40 @@ def test_tile_kernel_boundary_distances(monkeypatch):
     _assert_modes_equal(pos, cell, [1, 1, 1], rc, None, monkeypatch)
     monkeypatch.setenv('TAB_NBR_MODE', 'tile')
     assert_same_list(pos, cell, [1, 1, 1], rc)
+
+
+def test_half_width_cells_on_odd_geometries(monkeypatch):
+    """TAB_NBR_SUBDIV=2 forces the large-system grid (cells >= rc / 2, tiles of 4 x 4 x 4 cells,
+    125-cell neighbourhoods walked row by row) onto the small odd cases above: several species,
+    triclinic cells, mixed / no periodicity, > 2048 candidates per box (rows split over
+    candidate windows), a box thinner than the cutoff, rc exactly on a shell.  Same rows in the
+    same order as the thread-per-atom kernels on the same grid, and ASE's list."""
+    monkeypatch.setenv('TAB_NBR_SUBDIV', '2')
+    rng = np.random.default_rng(9)
+    cell = np.array([[60.0, 0.0, 0.0], [11.0, 55.0, 0.0], [4.0, -7.0, 48.0]])
+    n = 14000
+    pos = rng.random((n, 3)) @ cell
+    types = rng.integers(0, 3, size=n)
+    for pbc in ([1, 1, 1], [1, 0, 1], [0, 0, 0]):
+        _assert_modes_equal(pos, cell, pbc, 5.0, types, monkeypatch)
+    monkeypatch.setenv('TAB_NBR_MODE', 'tile')
+    assert_same_list(pos[:3000] * 0.5, cell * 0.5, [1, 1, 0], 5.0)
+    assert_same_list(pos[:2500] * 0.4, cell * 0.4, [0, 1, 0], 5.0)
+    # dense: 2.2 atoms / A^3, ~9000 candidates per box
+    cell = np.diag([16.0, 16.0, 16.0])
+    pos = rng.random((9000, 3)) @ cell
+    _assert_modes_equal(pos, cell, [1, 1, 1], 4.0, None, monkeypatch)
+    monkeypatch.setenv('TAB_NBR_MODE', 'tile')
+    assert_same_list(pos[:1500], cell, [1, 1, 1], 4.0)
+    # thin box, two species
+    cell = np.diag([120.0, 5.0, 40.0])
+    pos = rng.random((3000, 3)) @ cell
+    _assert_modes_equal(pos, cell, [1, 1, 1], 6.0, rng.integers(0, 2, size=3000), monkeypatch)
+    monkeypatch.setenv('TAB_NBR_MODE', 'tile')
+    assert_same_list(pos, cell, [1, 1, 1], 6.0)
+    # rc exactly on a shell of the perfect lattice
+    pos, cell = fcc_positions(3.52, 12, 12, 12)
+    rc = 3.52 * np.sqrt(2.0)
+    _assert_modes_equal(pos, cell, [1, 1, 1], rc, None, monkeypatch)
+    monkeypatch.setenv('TAB_NBR_MODE', 'tile')
+    assert_same_list(pos, cell, [1, 1, 1], rc)
