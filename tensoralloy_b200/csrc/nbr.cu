@@ -1120,7 +1120,24 @@ extern "C" int tab_nbr_free(tab_nbr *nbr) {
                       &nbr->pos_ref, &nbr->disp, &nbr->ls_ptr, &nbr->ls_col, &nbr->ls_w,
                       &nbr->rec16};
     for (DevBuf *b : bufs) b->release();
+    if (nbr->h_pin) cudaFreeHost(nbr->h_pin);
     delete nbr;
+    return TAB_OK;
+}
+
+// page-locked target of the build's small read-backs (a copy into pageable memory is staged by
+// the driver and blocks the calling thread longer)
+static int nbr_pinned(tab_nbr *nbr, unsigned long long **out) {
+    if (!nbr->h_pin) {
+        cudaError_t e = cudaHostAlloc((void **)&nbr->h_pin, 8 * sizeof(unsigned long long),
+                                      cudaHostAllocDefault);
+        if (e != cudaSuccess) {
+            nbr->h_pin = nullptr;
+            tab_set_error("cudaHostAlloc -> %s", cudaGetErrorString(e));
+            return TAB_ENOMEM;
+        }
+    }
+    *out = nbr->h_pin;
     return TAB_OK;
 }
 
@@ -1319,8 +1336,11 @@ extern "C" int tab_nbr_build_dd(tab_nbr *nbr, int32_t n_owned, int32_t n_halo,
     TAB_TRY(tab_scan_exclusive_u32(nbr->gcount.as<uint32_t>(),
                                    nbr->gstart.as<uint32_t>(), g.n_ecells, d_stats + 2,
                                    nbr->scan_tmp, st));
-    unsigned long long two[3] = {0, 0, 0};   // [n_ghost, max type, atoms far outside the frame]
-    TAB_CUDA(cudaMemcpyAsync(two, d_stats + 2, sizeof(two), cudaMemcpyDeviceToHost, st));
+    unsigned long long *h_pin;
+    TAB_TRY(nbr_pinned(nbr, &h_pin));
+    unsigned long long *two = h_pin;         // [n_ghost, max type, atoms far outside the frame]
+    TAB_CUDA(cudaMemcpyAsync(two, d_stats + 2, 3 * sizeof(unsigned long long),
+                             cudaMemcpyDeviceToHost, st));
     TAB_CUDA(cudaStreamSynchronize(st));
     const unsigned long long n_ghost = two[0];
     nbr->n_types = (int)two[1] + 1;
@@ -1407,7 +1427,7 @@ extern "C" int tab_nbr_build_dd(tab_nbr *nbr, int32_t n_owned, int32_t n_halo,
     }
     const int n_tiles = g.n_slots / (g.tb * g.tb * g.tb);
     TAB_TRY(nbr->tcounts.ensure(sizeof(int) * (size_t)n * nbr->n_types));
-    unsigned long long h_stats[3];
+    unsigned long long *h_stats = h_pin + 4;
 
     if (tile_mode) {
         // row capacity: last build of this handle, else the mean density
@@ -1441,7 +1461,7 @@ extern "C" int tab_nbr_build_dd(tab_nbr *nbr, int32_t n_owned, int32_t n_halo,
                 TAB_TRY(tab_scan_exclusive_u32(nbr->slice_w.as<uint32_t>(),
                                                nbr->slice_ptr.as<uint32_t>(), nbr->n_slices,
                                                d_stats + 2, nbr->scan_tmp, st));
-            TAB_CUDA(cudaMemcpyAsync(h_stats, d_stats, sizeof(h_stats),
+            TAB_CUDA(cudaMemcpyAsync(h_stats, d_stats, 3 * sizeof(unsigned long long),
                                      cudaMemcpyDeviceToHost, st));
             TAB_CUDA(cudaStreamSynchronize(st));
             if (h_stats[1] <= wcap) break;
@@ -1504,7 +1524,8 @@ extern "C" int tab_nbr_build_dd(tab_nbr *nbr, int32_t n_owned, int32_t n_halo,
     TAB_TRY(tab_scan_exclusive_u32(nbr->slice_w.as<uint32_t>(),
                                    nbr->slice_ptr.as<uint32_t>(), nbr->n_slices,
                                    d_stats + 2, nbr->scan_tmp, st));
-    TAB_CUDA(cudaMemcpyAsync(h_stats, d_stats, sizeof(h_stats), cudaMemcpyDeviceToHost, st));
+    TAB_CUDA(cudaMemcpyAsync(h_stats, d_stats, 3 * sizeof(unsigned long long),
+                             cudaMemcpyDeviceToHost, st));
     TAB_CUDA(cudaStreamSynchronize(st));
     nbr->nij = (long long)h_stats[0];
     nbr->nnl_max = (int)h_stats[1];
