@@ -573,6 +573,9 @@ class SingleGpu:
         self.d_vel = torch.randn((n, 3), generator=g, dtype=torch.float64, device='cuda')
         vmax = float(torch.linalg.norm(self.d_vel, dim=1).max())
         self.d_vel *= (0.5 * max(skin, 1e-3) / 9.5) / vmax
+        # the integrator's bound on one step's displacement (here exact): lets the rebuild
+        # decision run one step behind the device instead of blocking it (NeighborList.step)
+        self.vstep_max = 0.5 * max(skin, 1e-3) / 9.5
         self.nbr = _lib.NeighborList()
         self.nbr.set_skin(skin)
         self.nbr.build(self.d_pos, None, cell, [1, 1, 1], RC)
@@ -597,7 +600,7 @@ class SingleGpu:
 
     def md_step(self):
         self.d_pos.add_(self.d_vel)
-        if self.nbr.step(self.d_pos, None, self.cell, [1, 1, 1], RC):
+        if self.nbr.step(self.d_pos, None, self.cell, [1, 1, 1], RC, max_step=self.vstep_max):
             self.rebuilds += 1
             self.nij_local = self.nbr.sizes()[0]
         self.model.eval(self.nbr, self.precision, energy=self.d_e, forces=self.d_f,

@@ -297,6 +297,7 @@ class NeighborList:
             assert d_types.is_cuda and d_types.dtype == torch.int32
         self.n = int(d_pos.shape[0])
         self.n_struct = 0
+        self._disp_pending = None        # fresh lists: no displacement reading is in flight
         check(lib().tab_nbr_build(self._h, self.n, _ptr(d_pos), _ptr(d_types),
                                   _cell9(cell), _pbc3(pbc), float(rc), _stream()),
               'tab_nbr_build')
@@ -360,20 +361,50 @@ class NeighborList:
         check(lib().tab_nbr_displacement_device(self._h, _ptr(d_out), _stream()),
               'tab_nbr_displacement_device')
 
-    def step(self, d_pos, d_types, cell, pbc, rc):
+    def step(self, d_pos, d_types, cell, pbc, rc, max_step=None):
         """One MD step of the lists: refresh the positions; rebuild when an atom has moved more
         than half the skin since the last build (always, for lists without a skin).  Returns
         True when the lists were rebuilt.  The result of the following evaluation equals the
-        one on freshly built lists (the reference's semantics, universal.py:58)."""
+        one on freshly built lists (the reference's semantics, universal.py:58).
+
+        `max_step` (an upper bound of any atom's displacement in ONE step, e.g. dt * |v|_max
+        from the integrator) makes the decision non-blocking: the displacement of every refresh
+        is read back asynchronously, and the lists are rebuilt as soon as the PREVIOUS reading
+        plus `max_step` could exceed skin / 2 -- never later than the blocking rule, at most one
+        step earlier -- so the host does not wait for the device between the refresh and the
+        evaluation kernels."""
         if self.n != int(d_pos.shape[0]) or getattr(self, 'skin', 0.0) <= 0.0 or \
                 self.n_struct > 0:
             self.build(d_pos, d_types, cell, pbc, rc)
+            self._disp_pending = None
+            return True
+        if max_step is None:
+            self.update(d_pos)
+            disp, skin = self.max_displacement()
+            self._disp_pending = None
+            if not (2.0 * disp <= skin):
+                self.build(d_pos, d_types, cell, pbc, rc)
+                return True
+            return False
+        import torch
+        pending = getattr(self, '_disp_pending', None)
+        if pending is None:
+            last = 0.0                   # fresh lists (or the first pipelined call)
+        else:
+            pending.synchronize()        # the refresh of the previous step: long finished
+            last = float(self._h_disp[0])
+        if not (2.0 * (last + float(max_step)) <= self.skin):
+            self.build(d_pos, d_types, cell, pbc, rc)
+            self._disp_pending = None
             return True
         self.update(d_pos)
-        disp, skin = self.max_displacement()
-        if not (2.0 * disp <= skin):
-            self.build(d_pos, d_types, cell, pbc, rc)
-            return True
+        if getattr(self, '_d_disp', None) is None:
+            self._d_disp = torch.zeros(1, dtype=torch.float64, device='cuda')
+            self._h_disp = torch.zeros(1, dtype=torch.float64).pin_memory()
+        self.displacement_to(self._d_disp)
+        self._h_disp.copy_(self._d_disp, non_blocking=True)
+        self._disp_pending = torch.cuda.Event()
+        self._disp_pending.record()
         return False
 
     def sizes(self):

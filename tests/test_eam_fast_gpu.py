@@ -210,3 +210,62 @@ def test_tile_build_with_skin_32k():
     pos3 = pos2 + 0.25                                      # rigid shift: every atom moved 0.43
     assert skin.step(torch.tensor(pos3, dtype=torch.float64, device='cuda'), None, atoms.cell,
                      [1, 1, 1], RC) is True
+
+
+def test_pipelined_rebuild_decision_matches_fresh_lists():
+    """`NeighborList.step(..., max_step=...)`: the rebuild decision runs one step behind the
+    device (previous displacement reading + the bound of one step) instead of blocking it.
+    Every evaluation still equals the one on freshly built lists, and the lists are rebuilt no
+    later than the blocking rule would (here: one step earlier at most)."""
+    import torch
+    from tensoralloy_b200 import _lib
+    from tensoralloy_b200.atoms import fcc_positions
+    from tensoralloy_b200.nn.eam.potentials import get_potential
+    pos, cell = fcc_positions(3.52, 14, 14, 14)
+    rng = np.random.default_rng(5)
+    pos = pos + rng.normal(scale=0.05, size=pos.shape)
+    n = len(pos)
+    pot = get_potential('zjw04')
+    model = _lib.EamModel(_lib.EAM_ALLOY, 1, [pot.rho('Ni')], [pot.phi('NiNi')],
+                          [pot.embed('Ni')])
+    skin, rc = 0.3, 6.5
+    vel = rng.normal(size=(n, 3))
+    vstep = 0.5 * skin / 6.3
+    vel *= vstep / np.linalg.norm(vel, axis=1).max()
+    d_pos = torch.tensor(pos, device='cuda')
+    d_vel = torch.tensor(vel, device='cuda')
+    runs = {}
+    for mode in ('blocking', 'pipelined'):
+        nbr = _lib.NeighborList()
+        nbr.set_skin(skin)
+        p = d_pos.clone()
+        nbr.build(p, None, cell, [1, 1, 1], rc)
+        e = torch.zeros(1, dtype=torch.float64, device='cuda')
+        f = torch.zeros((n, 3), dtype=torch.float64, device='cuda')
+        v = torch.zeros(9, dtype=torch.float64, device='cuda')
+        rebuilt, out = [], []
+        for k in range(20):
+            p.add_(d_vel)
+            rebuilt.append(nbr.step(p, None, cell, [1, 1, 1], rc,
+                                    max_step=vstep if mode == 'pipelined' else None))
+            model.eval(nbr, _lib.PRECISION_HIGH, energy=e, forces=f, virial=v)
+            out.append((e.item(), f.clone()))
+        runs[mode] = (rebuilt, out, p)
+    # fresh lists at every step: the reference's semantics
+    fresh = _lib.NeighborList()
+    p = d_pos.clone()
+    e = torch.zeros(1, dtype=torch.float64, device='cuda')
+    f = torch.zeros((n, 3), dtype=torch.float64, device='cuda')
+    v = torch.zeros(9, dtype=torch.float64, device='cuda')
+    for k in range(20):
+        p.add_(d_vel)
+        fresh.build(p, None, cell, [1, 1, 1], rc)
+        model.eval(fresh, _lib.PRECISION_HIGH, energy=e, forces=f, virial=v)
+        for mode in runs:
+            ek, fk = runs[mode][1][k]
+            assert abs(ek - e.item()) < 1e-10 * n, (mode, k)
+            assert (fk - f).abs().max().item() < 1e-8, (mode, k)
+    rb, rp = runs['blocking'][0], runs['pipelined'][0]
+    assert sum(rb) >= 2 and sum(rp) >= sum(rb)
+    first_b, first_p = rb.index(True), rp.index(True)
+    assert first_b - 1 <= first_p <= first_b          # never later, at most one step earlier
