@@ -255,6 +255,16 @@ class PeerComm:
         # what I send to the left lands in the left neighbour's "from the right" box, ...
         self.mail_to_l = self.mail_hdl.get_buffer(L, (box,), torch.float64, box)
         self.mail_to_r = self.mail_hdl.get_buffer(R, (box,), torch.float64, 0)
+        # the migration's two alternating row buffers, its scratch and its counters: allocated
+        # here, not inside the first rebuilds (an allocation synchronises the device, and under
+        # a graph's private pool it was measured at several milliseconds)
+        cap = int(slack * max(owned)) + 2 * self.MIG_CAP + 64
+        self._mig_bufs = [torch.empty((cap, self.MIG_COLS), dtype=torch.float64, device=device)
+                          for _ in range(2)]
+        self._mig_flip = 0
+        self._mig_work = torch.empty(2 * (3 * ((cap + 255) // 256) + 8), dtype=torch.int32,
+                                     device=device)
+        self._mig_counts = torch.zeros(8, dtype=torch.int32, device=device)
         self._apply(table, n_send_left, n_send_right)
         torch.cuda.synchronize()
         dist.barrier()
@@ -296,16 +306,15 @@ class PeerComm:
         n, c = int(state.shape[0]), self.MIG_COLS
         state = state.contiguous()
         cap = n + 2 * self.MIG_CAP
-        self._mig_flip = 1 - getattr(self, '_mig_flip', 0)
-        bufs = self.__dict__.setdefault('_mig_bufs', [None, None])
+        self._mig_flip = 1 - self._mig_flip
+        bufs = self._mig_bufs
         keep = bufs[self._mig_flip]
-        if keep is None or keep.shape[0] < cap or keep.data_ptr() == state.data_ptr():
+        if keep.shape[0] < cap or keep.data_ptr() == state.data_ptr():
             keep = bufs[self._mig_flip] = torch.empty((cap + cap // 8, c), dtype=torch.float64,
                                                       device=self.device)
         nwork = 3 * ((n + 255) // 256) + 8
-        if getattr(self, '_mig_work', None) is None or self._mig_work.numel() < nwork:
+        if self._mig_work.numel() < nwork:
             self._mig_work = torch.empty(2 * nwork, dtype=torch.int32, device=self.device)
-            self._mig_counts = torch.zeros(8, dtype=torch.int32, device=self.device)
         _lib.dd_partition(state, lay.lx, lay.width, lay.world, lay.rank, keep, self.mail_to_l,
                           self.mail_to_r, self.MIG_CAP, self._mig_counts, self._mig_work)
         self.mail_hdl.barrier(channel=4)
@@ -574,7 +583,8 @@ class SlabDomain:
         self.peer = None
         self.rebuilds = 0
         self.rebuild_profile = None      # dict: accumulates ms per phase of `rebuild`
-        self._need_rebuild = False
+        self._since_build = -1          # md steps since the lists were built (-1: fresh lists)
+        self._disp_ring = None
         self.d_move = torch.zeros(1, dtype=torch.float64, device=device)   # 1: atoms advance
         self._moving = False
         self.rank_state = SlabRank(model, self.layout, self.state[:, 0:3], ly, lz, precision,
@@ -791,34 +801,57 @@ class SlabDomain:
         lap('send_sets')
         self.graph = None               # (the executable graph survives in _graph_exec)
         self._attach(lap=lap, configured=configured)
+        self._since_build = -1          # fresh lists, no step on them yet
         self.rebuilds += 1
         # the step that follows runs eagerly (with the new sizes: every library buffer that has
         # to grow does so outside a capture); `md_step` re-captures after it
 
     def md_step(self):
         """One MD step with moving atoms.  The decision to rebuild is taken BEFORE the lists
-        could become invalid: after every step the largest displacement since the build
-        (max over the ranks, part of the step's reduction) is read back; when one more step
-        at the fastest atom's speed could exceed skin / 2, the next step rebuilds first."""
-        if self._need_rebuild or self.skin <= 0.0:
+        could become invalid and WITHOUT waiting for the device: the largest displacement since
+        the build (max over the ranks, part of every step's reduction) is read back
+        asynchronously; step s after a build knows the reading of step s - 2 (long finished) and
+        rebuilds first when that reading plus two steps at the fastest atom's speed could exceed
+        skin / 2.  Every rank sees the same readings, so the decision is collective without a
+        message; the host runs one step ahead of the device instead of stalling it at every
+        step (at 8 GPUs the stall was > 10 % of a 0.28 ms step)."""
+        torch = self.torch
+        s = self._since_build + 1          # index of this step since the lists were built
+        if self.skin <= 0.0:
+            need = True
+        else:
+            if s <= 1:
+                bound = (s + 1) * self.vstep_max
+            else:
+                ev, buf = self._disp_ring[s % 2]          # written by step s - 2
+                ev.synchronize()
+                bound = float(buf[0]) + 2.0 * self.vstep_max
+            need = not (2.0 * bound <= self.skin)
+        if need:
             self.rebuild()
-            self._need_rebuild = False
+            s = 0
+        self._since_build = s
         self._set_moving(True)
         self.step()
         if self.graph is None and self._want_graph and self.skin > 0.0:
             import time
             if self.rebuild_profile is not None:
-                self.torch.cuda.synchronize()       # (the eager step is not part of it)
+                torch.cuda.synchronize()            # (the eager step is not part of it)
             t0 = time.perf_counter()
             self.enable_graph()
             if self.rebuild_profile is not None:
-                self.torch.cuda.synchronize()
+                torch.cuda.synchronize()
                 self.rebuild_profile['graph_capture'] = \
                     self.rebuild_profile.get('graph_capture', 0.0) + \
                     (time.perf_counter() - t0) * 1e3
         if self.skin > 0.0:
-            disp = float(self._totals()[10].item())      # synchronises the step
-            self._need_rebuild = not (2.0 * (disp + self.vstep_max) <= self.skin)
+            if self._disp_ring is None:
+                self._disp_ring = [(torch.cuda.Event(),
+                                    torch.zeros(1, dtype=torch.float64).pin_memory())
+                                   for _ in range(2)]
+            ev, buf = self._disp_ring[s % 2]
+            buf.copy_(self._totals()[10:11], non_blocking=True)
+            ev.record()
 
     def resident_step(self):
         self._set_moving(False)
@@ -834,6 +867,7 @@ class SlabDomain:
         r.d_pos_owned.copy_(r.h_pos, non_blocking=True)
         self._exchange_positions()
         r.build()
+        self._since_build = -1          # fresh lists at the current positions
         r.pass1()
         self._exchange_fprime()
         r.pass2()
